@@ -1,0 +1,188 @@
+"""Python-side mirror of the C ABI in include/lmot.h (ctypes; used by tests/, bench.py and __graft_entry__).
+
+The product is liblmot.so (CUDA kernels for sm_100a behind `extern "C"`).  This module only loads it and
+marshals numpy arrays / raw device pointers; it contains NO implementation of any pipeline stage and there is
+no CPU fallback: if the library is missing or no CUDA device is usable, construction raises.
+
+Entry points mirror the reference's four free functions:
+    Lmot.ground_remove(points)            <- groundRemove           ground_removal.cpp:177
+    Lmot.component_cluster(elevated)      <- componentClustering    component_clustering.cpp:260
+    Lmot.box_fit(elevated, grid, k)       <- boxFitting             box_fitting.cpp:422
+    Lmot.track_step(boxes, ts, v, yaw)    <- getOriginPoints + immUkfJpdaf   imm_ukf_jpda.cpp:74,704
+    Lmot.frame(points, ts, v, yaw)        <- all four, device resident between stages
+
+The directory name is not a Python identifier; import it with
+    importlib.import_module("3d-lidar-multi-object-tracking_b200")
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblmot.so")
+TRACK_DUMP_DOUBLES = 236
+
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4
+RULE_INTENDED, RULE_GCC13_O2_COMPAT = 0, 1
+
+
+class LmotError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"lmot status {status}: {msg}")
+        self.status = status
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("r_min", C.c_float), ("r_max", C.c_float), ("t_hmin", C.c_float), ("t_hmax", C.c_float),
+        ("t_hdiff", C.c_float), ("h_sensor", C.c_float), ("ground_tolerance", C.c_double),
+        ("roi_m", C.c_float),
+        ("ram_points", C.c_int), ("l_slope_dist", C.c_int), ("l_num_points", C.c_int), ("sensor_height", C.c_float),
+        ("t_height_min", C.c_float), ("t_height_max", C.c_float), ("t_width_min", C.c_float), ("t_width_max", C.c_float),
+        ("t_len_min", C.c_float), ("t_len_max", C.c_float), ("t_area_max", C.c_float),
+        ("t_ratio_min", C.c_float), ("t_ratio_max", C.c_float), ("min_len_ratio", C.c_float), ("t_pt_per_m3", C.c_float),
+        ("min_cluster_points", C.c_int), ("rule_filter", C.c_int),
+        ("oracle_compat_first_frame", C.c_int),
+        ("max_points", C.c_int), ("max_clusters", C.c_int), ("max_boxes", C.c_int), ("max_tracks", C.c_int),
+    ]
+
+
+class TrackOut(C.Structure):
+    _fields_ = [
+        ("cap", C.c_int), ("n_tracks", C.c_int), ("n_vis", C.c_int),
+        ("targets", C.POINTER(C.c_float)), ("vandyaw", C.POINTER(C.c_double)), ("track_manage", C.POINTER(C.c_int32)),
+        ("is_static", C.POINTER(C.c_uint8)), ("is_vis", C.POINTER(C.c_uint8)), ("vis_bb", C.POINTER(C.c_float)),
+    ]
+
+
+class FrameOut(C.Structure):
+    _fields_ = [
+        ("n_elevated", C.c_int), ("n_ground", C.c_int), ("num_cluster", C.c_int), ("n_boxes", C.c_int),
+        ("boxes", C.POINTER(C.c_float)), ("max_boxes", C.c_int), ("tracks", TrackOut),
+    ]
+
+
+# every symbol include/lmot.h declares (tests assert the library exports all of them)
+ABI_SYMBOLS = [
+    "lmot_default_params", "lmot_create", "lmot_destroy", "lmot_strerror", "lmot_last_error", "lmot_build_info",
+    "lmot_set_stream", "lmot_ground_remove", "lmot_component_cluster", "lmot_box_fit", "lmot_track_step", "lmot_frame",
+    "lmot_frame_dev", "lmot_frame_fetch", "lmot_ground_remove_dev", "lmot_detect_dev", "lmot_sync",
+    "lmot_tracker_reset", "lmot_tracker_num_tracks", "lmot_tracker_dump", "lmot_tracker_load",
+    "lmot_debug_polar_grid", "lmot_debug_cell_index", "lmot_debug_label_grid", "lmot_selftest_atan2f",
+    "lmot_enable_timing", "lmot_last_stage_ms",
+]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load liblmot.so (raises OSError when it has not been built: there is nothing to fall back to)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OSError(f"{LIB_PATH} not built -- run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = C.CDLL(LIB_PATH)
+        lib.lmot_strerror.restype = C.c_char_p
+        lib.lmot_last_error.restype = C.c_char_p
+        lib.lmot_build_info.restype = C.c_char_p
+        lib.lmot_last_error.argtypes = [C.c_void_p]
+        lib.lmot_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Params), C.c_int]
+        lib.lmot_destroy.argtypes = [C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def default_params() -> Params:
+    p = Params()
+    load_library().lmot_default_params(C.byref(p))
+    return p
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _pts(points):
+    p = np.ascontiguousarray(points, dtype=np.float32)
+    if p.ndim != 2 or p.shape[1] < 3:
+        raise ValueError("points must be (N, >=3) float32")
+    return p, int(p.shape[0]), int(p.shape[1])
+
+
+class Lmot:
+    """One context = one sensor stream on one GPU (not thread-safe, like the reference's globals)."""
+
+    def __init__(self, params: Params | None = None, device: int = 0):
+        self.lib = load_library()
+        self.params = params if params is not None else default_params()
+        h = C.c_void_p()
+        st = self.lib.lmot_create(C.byref(h), C.byref(self.params), device)
+        if st != OK:
+            raise LmotError(st, self.lib.lmot_strerror(st).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lmot_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, st: int):
+        if st != OK:
+            raise LmotError(st, self.lib.lmot_strerror(st).decode() + " | " + self.lib.lmot_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream_handle: int | None):
+        self._chk(self.lib.lmot_set_stream(self.h, C.c_void_p(cuda_stream_handle or 0)))
+
+    def sync(self):
+        self._chk(self.lib.lmot_sync(self.h))
+
+    # ---- groundRemove ------------------------------------------------------------------------------------
+    def ground_remove(self, points):
+        """-> dict(labels (N,) u8, elevated (Ne,4) f32, ground (Ng,4) f32); clouds keep input order."""
+        p, n, s = _pts(points)
+        labels = np.zeros(max(n, 1), np.uint8)
+        elev = np.zeros((max(n, 1), 4), np.float32)
+        grnd = np.zeros((max(n, 1), 4), np.float32)
+        ne, ng = C.c_int(0), C.c_int(0)
+        self._chk(self.lib.lmot_ground_remove(self.h, _fp(p), n, s, labels.ctypes.data_as(C.POINTER(C.c_uint8)), _fp(elev),
+                                              C.byref(ne), _fp(grnd), C.byref(ng)))
+        return dict(labels=labels[:n], elevated=elev[: ne.value], ground=grnd[: ng.value])
+
+    def ground_remove_dev(self, d_ptr: int, n: int):
+        self._chk(self.lib.lmot_ground_remove_dev(self.h, C.c_void_p(d_ptr), n))
+
+    def debug_polar_grid(self):
+        names = ["minz", "height", "smoothed", "hdiff", "hground"]
+        arrs = [np.zeros(80 * 120, np.float32) for _ in names]
+        isg = np.zeros(80 * 120, np.uint8)
+        self._chk(self.lib.lmot_debug_polar_grid(self.h, *[_fp(a) for a in arrs], isg.ctypes.data_as(C.POINTER(C.c_uint8))))
+        d = {k: v.reshape(80, 120) for k, v in zip(names, arrs)}
+        d["isground"] = isg.reshape(80, 120)
+        return d
+
+    def debug_cell_index(self, n: int):
+        ch = np.zeros(max(n, 1), np.int32); b = np.zeros(max(n, 1), np.int32)
+        self._chk(self.lib.lmot_debug_cell_index(self.h, ch.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                 b.ctypes.data_as(C.POINTER(C.c_int32)), n))
+        return ch[:n], b[:n]
+
+
+def selftest_atan2f(y, x) -> np.ndarray:
+    """Host-side evaluation of the library's bit-exact atan2f restatement (no GPU needed)."""
+    lib = load_library()
+    y = np.ascontiguousarray(y, np.float32); x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(y)
+    st = lib.lmot_selftest_atan2f(_fp(y), _fp(x), int(y.size), _fp(out))
+    if st != OK:
+        raise LmotError(st, "selftest")
+    return out

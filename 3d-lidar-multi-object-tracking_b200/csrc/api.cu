@@ -1,0 +1,233 @@
+// api.cu -- the extern "C" boundary declared in include/lmot.h.  Host-side marshalling only: H2D/D2H copies,
+// stream ordering and capacity checks; every algorithmic step is a CUDA kernel in ground.cu / cluster.cu /
+// boxfit.cu / tracker.cu.  There is deliberately no CPU implementation of any stage here.
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "lmot_internal.cuh"
+#include "exact_math.cuh"
+
+using namespace lmot;
+
+struct lmot_ctx {
+  Ctx c;
+};
+
+namespace lmot {
+int ground_repack(Ctx* c, const float* d_in, int n, int stride);
+}
+
+namespace {
+
+// gaussKernel(samples=3, sigma=1.0) exactly as gaus_blur.cpp:26-49 evaluates it (host libm, double)
+void gauss_taps(double tap[3]) {
+  const int samples = 3;
+  const double sigma = 1.0;
+  const double mean = samples / 2;  // integer division, = 1 (gaus_blur.cpp:28)
+  double sum = 0.0;
+  for (int x = 0; x < samples; ++x) {
+    tap[x] = std::exp(-0.5 * (std::pow((x - mean) / sigma, 2.0))) / (2 * M_PI * sigma * sigma);
+    sum += tap[x];
+  }
+  for (int x = 0; x < samples; ++x) tap[x] /= sum;
+}
+
+int upload_points(Ctx* c, const float* points, int n, int stride) {
+  if (n < 0 || (n > 0 && !points) || stride < 3) return LMOT_ERR_INVALID;
+  if (n > c->max_points) return LMOT_ERR_CAPACITY;
+  if (n == 0) return LMOT_OK;
+  if (stride == 4) {
+    LMOT_CUDA(c, cudaMemcpyAsync(c->d_points, points, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    if (stride > 4) {  // wide host records: pack xyz on the host side of the copy
+      std::vector<float> tmp((size_t)n * 3);
+      for (int i = 0; i < n; ++i) { tmp[3*i] = points[(size_t)i*stride]; tmp[3*i+1] = points[(size_t)i*stride+1]; tmp[3*i+2] = points[(size_t)i*stride+2]; }
+      LMOT_CUDA(c, cudaMemcpyAsync(c->d_stage_in, tmp.data(), (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+      LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+      stride = 3;
+    } else {
+      LMOT_CUDA(c, cudaMemcpyAsync(c->d_stage_in, points, (size_t)n * stride * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    int rc = ground_repack(c, c->d_stage_in, n, stride);
+    if (rc) return rc;
+  }
+  return LMOT_OK;
+}
+
+int fetch_counters(Ctx* c) {
+  LMOT_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LMOT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lmot_default_params(lmot_params* p) {
+  if (!p) return LMOT_ERR_INVALID;
+  memset(p, 0, sizeof(*p));
+  p->r_min = 3.4f; p->r_max = 120.f; p->t_hmin = -2.0f; p->t_hmax = -0.4f; p->t_hdiff = 0.4f; p->h_sensor = 2.f;
+  p->ground_tolerance = 0.25;
+  p->roi_m = 50.f;
+  p->ram_points = 80; p->l_slope_dist = 1; p->l_num_points = 5; p->sensor_height = 2.f;
+  p->t_height_min = 0.8f; p->t_height_max = 2.6f; p->t_width_min = 0.2f; p->t_width_max = 3.5f;
+  p->t_len_min = 0.2f; p->t_len_max = 14.0f; p->t_area_max = 20.0f; p->t_ratio_min = 1.f; p->t_ratio_max = 8.0f;
+  p->min_len_ratio = 3.0f; p->t_pt_per_m3 = 8.f; p->min_cluster_points = 30;
+  p->rule_filter = LMOT_RULE_INTENDED;
+  p->oracle_compat_first_frame = 1;
+  p->max_points = 1 << 20; p->max_clusters = 4096; p->max_boxes = 1024; p->max_tracks = 8192;
+  return LMOT_OK;
+}
+
+const char* lmot_strerror(int s) {
+  switch (s) {
+    case LMOT_OK: return "ok";
+    case LMOT_ERR_INVALID: return "invalid argument";
+    case LMOT_ERR_CUDA: return "CUDA error (no CPU fallback exists)";
+    case LMOT_ERR_CAPACITY: return "capacity exceeded";
+    case LMOT_ERR_STATE: return "invalid call sequence / not available";
+    default: return "unknown status";
+  }
+}
+
+const char* lmot_build_info(void) { return "liblmot sm_100a, nvcc " __DATE__ " -fmad=false"; }
+
+const char* lmot_last_error(const lmot_ctx* ctx) { return ctx ? ctx->c.last_error.c_str() : ""; }
+
+int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
+  if (!out) return LMOT_ERR_INVALID;
+  *out = nullptr;
+  lmot_params p;
+  if (params) p = *params; else lmot_default_params(&p);
+  if (p.max_points <= 0 || p.max_clusters <= 0 || p.max_boxes <= 0 || p.max_tracks <= 0) return LMOT_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return LMOT_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return LMOT_ERR_CUDA;
+  lmot_ctx* h = new (std::nothrow) lmot_ctx();
+  if (!h) return LMOT_ERR_INVALID;
+  Ctx* c = &h->c;
+  c->prm = p;
+  c->device = device;
+  c->max_points = p.max_points;
+  c->gp.r_min = p.r_min; c->gp.r_max = p.r_max; c->gp.t_hmin = p.t_hmin; c->gp.t_hmax = p.t_hmax;
+  c->gp.t_hdiff = p.t_hdiff; c->gp.h_sensor = p.h_sensor;
+  { volatile float span = p.r_max - p.r_min; c->gp.r_span = span; }
+  c->gp.tol = p.ground_tolerance;
+  gauss_taps(c->gp.tap);
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return LMOT_ERR_CUDA; }
+  c->stream = c->own_stream;
+  int rc = ground_alloc(c);
+  if (rc == LMOT_OK) rc = (cudaStreamSynchronize(c->stream) == cudaSuccess) ? LMOT_OK : LMOT_ERR_CUDA;
+  if (rc != LMOT_OK) { lmot_destroy(h); return rc; }
+  for (int i = 0; i < 5; ++i) cudaEventCreate(&c->ev[i]);
+  *out = h;
+  return LMOT_OK;
+}
+
+void lmot_destroy(lmot_ctx* ctx) {
+  if (!ctx) return;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  ground_free(c);
+  for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete ctx;
+}
+
+int lmot_set_stream(lmot_ctx* ctx, void* s) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  ctx->c.stream = s ? (cudaStream_t)s : ctx->c.own_stream;
+  return LMOT_OK;
+}
+
+int lmot_sync(lmot_ctx* ctx) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  LMOT_CUDA(&ctx->c, cudaStreamSynchronize(ctx->c.stream));
+  return LMOT_OK;
+}
+
+int lmot_ground_remove_dev(lmot_ctx* ctx, const float* d_points, int n) {
+  if (!ctx || n < 0 || (n > 0 && !d_points)) return LMOT_ERR_INVALID;
+  if (n > ctx->c.max_points) return LMOT_ERR_CAPACITY;
+  return ground_launch(&ctx->c, reinterpret_cast<const float4*>(d_points), n);
+}
+
+int lmot_ground_remove(lmot_ctx* ctx, const float* points, int n, int stride, uint8_t* labels, float* elevated,
+                       int* n_elevated, float* ground, int* n_ground) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  int rc = upload_points(c, points, n, stride);
+  if (rc) return rc;
+  rc = ground_launch(c, c->d_points, n);
+  if (rc) return rc;
+  rc = fetch_counters(c);
+  if (rc) return rc;
+  const int ne = c->h_counters[CNT_N_ELEV], ng = c->h_counters[CNT_N_GROUND];
+  if (n_elevated) *n_elevated = ne;
+  if (n_ground) *n_ground = ng;
+  if (labels && n > 0) LMOT_CUDA(c, cudaMemcpyAsync(labels, c->d_labels, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  if (elevated && ne > 0) LMOT_CUDA(c, cudaMemcpyAsync(elevated, c->d_elev, (size_t)ne * 16, cudaMemcpyDeviceToHost, c->stream));
+  if (ground && ng > 0) LMOT_CUDA(c, cudaMemcpyAsync(ground, c->d_ground, (size_t)ng * 16, cudaMemcpyDeviceToHost, c->stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LMOT_OK;
+}
+
+int lmot_debug_polar_grid(lmot_ctx* ctx, float* minz, float* height, float* smoothed, float* hdiff, float* hground,
+                          uint8_t* isground) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  const size_t b = kPolarCells * sizeof(float);
+  if (minz) LMOT_CUDA(c, cudaMemcpyAsync(minz, c->d_minz, b, cudaMemcpyDeviceToHost, c->stream));
+  if (height) LMOT_CUDA(c, cudaMemcpyAsync(height, c->d_height, b, cudaMemcpyDeviceToHost, c->stream));
+  if (smoothed) LMOT_CUDA(c, cudaMemcpyAsync(smoothed, c->d_smoothed, b, cudaMemcpyDeviceToHost, c->stream));
+  if (hdiff) LMOT_CUDA(c, cudaMemcpyAsync(hdiff, c->d_hdiff, b, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<float> hg;
+  if (hground || isground) {
+    hg.resize(kPolarCells);
+    LMOT_CUDA(c, cudaMemcpyAsync(hg.data(), c->d_hg, b, cudaMemcpyDeviceToHost, c->stream));
+  }
+  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < kPolarCells && (hground || isground); ++k) {
+    const bool g = !(std::isinf(hg[k]) && hg[k] < 0);
+    if (hground) hground[k] = g ? hg[k] : 0.f;
+    if (isground) isground[k] = g ? 1 : 0;
+  }
+  return LMOT_OK;
+}
+
+int lmot_debug_cell_index(lmot_ctx* ctx, int32_t* ch, int32_t* bin, int n) {
+  if (!ctx || n < 0 || n > ctx->c.cur_n) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  std::vector<uint16_t> cell((size_t)n);
+  if (n) LMOT_CUDA(c, cudaMemcpyAsync(cell.data(), c->d_cell, (size_t)n * 2, cudaMemcpyDeviceToHost, c->stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < n; ++i) {
+    if (cell[i] == kNoCell) { ch[i] = -1; bin[i] = -1; }
+    else { ch[i] = cell[i] / kNumBin; bin[i] = cell[i] % kNumBin; }
+  }
+  return LMOT_OK;
+}
+
+int lmot_selftest_atan2f(const float* y, const float* x, int n, float* out) {
+  if (n < 0 || (n > 0 && (!y || !x || !out))) return LMOT_ERR_INVALID;
+  for (int i = 0; i < n; ++i) out[i] = atan2f_fdlibm(y[i], x[i]);
+  return LMOT_OK;
+}
+
+int lmot_enable_timing(lmot_ctx* ctx, int on) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  ctx->c.timing = on != 0;
+  return LMOT_OK;
+}
+
+int lmot_last_stage_ms(lmot_ctx* ctx, float ms[4]) {
+  if (!ctx || !ms) return LMOT_ERR_INVALID;
+  for (int i = 0; i < 4; ++i) ms[i] = ctx->c.stage_ms[i];
+  return LMOT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,311 @@
+// ground.cu -- slope-based polar-grid ground removal on sm_100a.
+//
+// Replaces groundRemove (/root/reference/object_tracking/src/groundremove/ground_removal.cpp:177-249) and
+// gaussSmoothen (src/groundremove/gaus_blur.cpp:52-68).  Three kernels per frame:
+//
+//   K1 polar_bin_kernel      N threads.  float4 XYZI load, range filter (:46-64), bit-exact point->cell
+//                            (:67-76, exact_math.cuh), warp-aggregated atomicMin of an order-preserving
+//                            key into the 80x120 min-z grid (:79-92).  Also stores the u16 cell id so the
+//                            classification pass does not repeat atan2f/sqrtf like the reference does.
+//   K2 polar_grid_kernel     ONE CTA, the whole 9,600-cell grid in shared memory: height clamp (:192-197),
+//                            3-tap blur in fp64 (gaus_blur.cpp), hDiff (:95-117), ground flag (:205-214),
+//                            median filter (:120-146, evaluated Jacobi-style -- provably order independent),
+//                            outlier filter (:149-174, sequential along bin, one lane per channel).
+//   K3 classify_partition_kernel  N threads.  ground / elevated decision (:221-247) + ORDER-PRESERVING
+//                            compaction of both output clouds with a single-pass decoupled look-back scan.
+//
+// Everything that decides a cell index or a label is IEEE round-to-nearest without FMA contraction, so the
+// results are bit-identical to the reference built for x86-64.
+#include "lmot_internal.cuh"
+#include "exact_math.cuh"
+
+namespace lmot {
+
+namespace {
+
+__device__ __forceinline__ unsigned fkey(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// ground_removal.cpp:46-64 (range filter) + :67-76 (getCellIndexFromPoints) + :89 (index guard)
+__device__ __forceinline__ uint16_t polar_cell(float x, float y, const GroundParams& p) {
+  const float d = fsqrt(fadd(fmul(x, x), fmul(y, y)));
+  if (d <= p.r_min || d >= p.r_max || d != d) return kNoCell;
+  const float a = atan2f_fdlibm(y, x);
+  const double chD = __ddiv_rn(__dadd_rn((double)a, 3.14159265358979323846), 6.28318530717958647692);
+  const float chP = (float)chD;
+  const float binP = fdiv(fsub(d, p.r_min), p.r_span);
+  const float chF = floorf(fmul(chP, (float)kNumChannel));
+  const float binF = floorf(fmul(binP, (float)kNumBin));
+  if (!(chF >= 0.f && chF < (float)kNumChannel && binF >= 0.f && binF < (float)kNumBin)) return kNoCell;
+  return (uint16_t)((int)chF * kNumBin + (int)binF);
+}
+
+__global__ void __launch_bounds__(256) polar_bin_kernel(const float4* __restrict__ pts, int n, GroundParams p,
+                                                        uint16_t* __restrict__ cell, unsigned* __restrict__ keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned c = kNoCell;
+  unsigned key = 0xFFFFFFFFu;
+  if (i < n) {
+    const float4 q = __ldg(&pts[i]);
+    c = polar_cell(q.x, q.y, p);
+    cell[i] = (uint16_t)c;
+    float z = q.z;
+    if (z == 0.f) z = 0.f;                       // -0 -> +0 (`z < minZ` does not order them either)
+    if (c != kNoCell && z == z) key = fkey(z);   // NaN z never wins `z < minZ` (ground_removal.cpp:41)
+  }
+  // consecutive HDL-64 returns fall into the same cell: one atomic per distinct cell per warp
+  const unsigned grp = __match_any_sync(0xFFFFFFFFu, c);
+  const unsigned kmin = __reduce_min_sync(grp, key);
+  const int lane = threadIdx.x & 31;
+  if (c != kNoCell && lane == __ffs(grp) - 1 && kmin != 0xFFFFFFFFu) atomicMin(&keys[c], kmin);
+}
+
+// generic-stride input -> float4 (the hot path is stride 4 and never runs this)
+__global__ void repack_kernel(const float* __restrict__ in, int n, int stride, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float4(in[(size_t)i * stride], in[(size_t)i * stride + 1], in[(size_t)i * stride + 2], 1.f);
+}
+
+constexpr int kGridThreads = 1024;
+
+__global__ void __launch_bounds__(kGridThreads, 1)
+polar_grid_kernel(GroundParams p, unsigned* __restrict__ keys, float* __restrict__ o_minz, float* __restrict__ o_height,
+                  float* __restrict__ o_smoothed, float* __restrict__ o_hdiff, float* __restrict__ o_hg,
+                  unsigned long long* __restrict__ tile_desc, int n_tiles, int* __restrict__ counters) {
+  extern __shared__ unsigned char smem_raw[];
+  float* H = reinterpret_cast<float*>(smem_raw);              // [9600] height
+  uint8_t* G = reinterpret_cast<uint8_t*>(H + kPolarCells);   // [9600] isGround
+  const int tid = threadIdx.x;
+  const unsigned init_key = fkey(1000.f);                     // Cell::Cell(): minZ = 1000 (ground_removal.cpp:35-38)
+
+  // housekeeping for the kernels that follow in this frame
+  for (int t = tid; t < n_tiles; t += kGridThreads) tile_desc[t] = 0ull;
+  if (tid == 0) { counters[CNT_TICKET_A] = 0; counters[CNT_N_ELEV] = 0; counters[CNT_N_GROUND] = 0; }
+
+  // (a4) height clamp, ground_removal.cpp:192-197
+  for (int k = tid; k < kPolarCells; k += kGridThreads) {
+    const float zi = fkey_inv(keys[k]);
+    keys[k] = init_key;                                       // ready for the next frame
+    o_minz[k] = zi;
+    float h;
+    if (zi > p.t_hmin && zi < p.t_hmax) h = zi;
+    else if (zi > p.t_hmax) h = p.h_sensor;
+    else h = p.t_hmin;
+    H[k] = h;
+  }
+  __syncthreads();
+
+  // (a5) blur, (a6) hDiff, (a7) ground flag -- per channel, neighbours along bin
+  for (int k = tid; k < kPolarCells; k += kGridThreads) {
+    const int b = k % kNumBin;
+    const float h = H[k];
+    double acc = 0.0;                                         // gaus_blur.cpp:58-65, order j = i-1, i, i+1
+    if (b > 0) acc = __dadd_rn(acc, __dmul_rn(p.tap[0], (double)H[k - 1]));
+    acc = __dadd_rn(acc, __dmul_rn(p.tap[1], (double)h));
+    if (b < kNumBin - 1) acc = __dadd_rn(acc, __dmul_rn(p.tap[2], (double)H[k + 1]));
+    const float sm = (float)acc;
+    float hd;                                                 // ground_removal.cpp:95-117
+    if (b == 0) hd = fsub(h, H[k + 1]);
+    else if (b == kNumBin - 1) hd = fsub(h, H[k - 1]);
+    else {
+      const float pre = fsub(h, H[k - 1]), post = fsub(h, H[k + 1]);
+      hd = (pre > post) ? pre : post;
+    }
+    o_smoothed[k] = sm;
+    o_hdiff[k] = hd;
+    G[k] = ((sm < p.t_hmax && hd < p.t_hdiff) || (h < p.t_hmax && hd < p.t_hdiff)) ? 1 : 0;  // :205-214
+  }
+  __syncthreads();
+
+  // (a8) applyMedianFilter, ground_removal.cpp:120-146.  A cell flips only if its four neighbours are ground
+  // already, and a neighbour that flips in this pass would have needed this cell to be ground: the in-place
+  // sequential pass and this two-phase (decide, then apply) pass are identical.
+  {
+    float newh[(kPolarCells + kGridThreads - 1) / kGridThreads];
+    unsigned flip = 0;
+    int j = 0;
+    for (int k = tid; k < kPolarCells; k += kGridThreads, ++j) {
+      const int ch = k / kNumBin, b = k % kNumBin;
+      if (ch >= 1 && ch < kNumChannel - 1 && b >= 1 && b < kNumBin - 1 && !G[k] && G[k + 1] && G[k - 1] &&
+          G[k + kNumBin] && G[k - kNumBin]) {
+        const float a = H[k + 1], bb = H[k - 1], c = H[k + kNumBin], d = H[k - kNumBin];
+        const float lo1 = fminf(a, bb), hi1 = fmaxf(a, bb), lo2 = fminf(c, d), hi2 = fmaxf(c, d);
+        const float m1 = fmaxf(lo1, lo2), m2 = fminf(hi1, hi2);  // the two middle values of the sorted four
+        newh[j] = fdiv(fadd(m1, m2), 2.f);
+        flip |= 1u << j;
+      }
+    }
+    __syncthreads();
+    j = 0;
+    for (int k = tid; k < kPolarCells; k += kGridThreads, ++j)
+      if (flip & (1u << j)) { H[k] = newh[j]; G[k] = 1; }
+  }
+  __syncthreads();
+
+  // (a8) outlierFilter, ground_removal.cpp:149-174: in place and order dependent along bin; channels independent
+  if (tid >= 1 && tid < kNumChannel - 1) {
+    float* Hc = H + tid * kNumBin;
+    const uint8_t* Gc = G + tid * kNumBin;
+    const float T = p.t_hmin;
+    for (int b = 1; b < kNumBin - 2; ++b) {
+      if (Gc[b] && Gc[b + 1] && Gc[b - 1] && Gc[b + 2]) {
+        const float h1 = Hc[b - 1], h2 = Hc[b], h3 = Hc[b + 1], h4 = Hc[b + 2];
+        if (h1 != T && h2 == T && h3 != T) Hc[b] = fdiv(fadd(h1, h3), 2.f);
+        else if (h1 != T && h2 == T && h3 == T && h4 != T) Hc[b] = fdiv(fadd(h1, h4), 2.f);
+      }
+    }
+  }
+  __syncthreads();
+
+  // hGround == height for every ground cell (updateGround() follows every height write of a ground cell)
+  for (int k = tid; k < kPolarCells; k += kGridThreads) {
+    o_height[k] = H[k];
+    o_hg[k] = G[k] ? H[k] : -INFINITY;
+  }
+}
+
+// status (2 bits) | elevated count (31 bits) | ground count (31 bits)
+__device__ __forceinline__ unsigned long long pack_desc(unsigned st, unsigned e, unsigned g) {
+  return ((unsigned long long)st << 62) | ((unsigned long long)e << 31) | (unsigned long long)g;
+}
+
+__global__ void __launch_bounds__(kScanTile)
+classify_partition_kernel(const float4* __restrict__ pts, int n, const uint16_t* __restrict__ cell,
+                          const float* __restrict__ hg, double tol, uint8_t* __restrict__ labels,
+                          float4* __restrict__ elev, float4* __restrict__ ground,
+                          unsigned long long* tile_desc, int* counters) {
+  __shared__ int s_tile;
+  __shared__ unsigned s_we[32], s_wg[32];
+  __shared__ unsigned s_base_e, s_base_g;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(&counters[CNT_TICKET_A], 1);
+  __syncthreads();
+  const int tile = s_tile;
+  const int i = tile * kScanTile + tid;
+
+  int lab = 0;
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n) {
+    q = __ldg(&pts[i]);
+    const unsigned c = cell[i];
+    if (c != kNoCell) {
+      const float h = __ldg(&hg[c]);                       // -inf for non-ground cells -> elevated
+      lab = ((double)q.z < __dadd_rn((double)h, tol)) ? 1 : 2;   // ground_removal.cpp:236-246
+    }
+    labels[i] = (uint8_t)lab;
+  }
+  const unsigned be = __ballot_sync(0xFFFFFFFFu, lab == 2);
+  const unsigned bg = __ballot_sync(0xFFFFFFFFu, lab == 1);
+  if (lane == 0) { s_we[warp] = __popc(be); s_wg[warp] = __popc(bg); }
+  __syncthreads();
+
+  if (warp == 0) {
+    const unsigned ve = s_we[lane], vg = s_wg[lane];
+    unsigned ie = ve, ig = vg;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned te = __shfl_up_sync(0xFFFFFFFFu, ie, o), tg = __shfl_up_sync(0xFFFFFFFFu, ig, o);
+      if (lane >= o) { ie += te; ig += tg; }
+    }
+    s_we[lane] = ie - ve;
+    s_wg[lane] = ig - vg;
+    const unsigned agg_e = __shfl_sync(0xFFFFFFFFu, ie, 31), agg_g = __shfl_sync(0xFFFFFFFFu, ig, 31);
+    volatile unsigned long long* desc = tile_desc;
+    if (lane == 0 && tile > 0) desc[tile] = pack_desc(1u, agg_e, agg_g);
+    // decoupled look-back, 32 predecessors per round
+    unsigned ex_e = 0, ex_g = 0;
+    int j = tile - 1 - lane;
+    while (true) {
+      unsigned long long d = (j >= 0) ? desc[j] : pack_desc(2u, 0u, 0u);
+      while (__any_sync(0xFFFFFFFFu, (d >> 62) == 0ull)) {
+        if ((d >> 62) == 0ull) d = desc[j];
+      }
+      const unsigned pm = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2ull);
+      const int first = pm ? (__ffs(pm) - 1) : 31;
+      unsigned ce = (lane <= first) ? (unsigned)((d >> 31) & 0x7FFFFFFFull) : 0u;
+      unsigned cg = (lane <= first) ? (unsigned)(d & 0x7FFFFFFFull) : 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { ce += __shfl_xor_sync(0xFFFFFFFFu, ce, o); cg += __shfl_xor_sync(0xFFFFFFFFu, cg, o); }
+      ex_e += ce; ex_g += cg;
+      if (pm) break;
+      j -= 32;
+    }
+    if (lane == 0) {
+      desc[tile] = pack_desc(2u, ex_e + agg_e, ex_g + agg_g);
+      s_base_e = ex_e; s_base_g = ex_g;
+      if (tile == (int)gridDim.x - 1) { counters[CNT_N_ELEV] = (int)(ex_e + agg_e); counters[CNT_N_GROUND] = (int)(ex_g + agg_g); }
+    }
+  }
+  __syncthreads();
+  const unsigned lt = (1u << lane) - 1u;
+  if (lab == 2) elev[s_base_e + s_we[warp] + __popc(be & lt)] = make_float4(q.x, q.y, q.z, 1.f);
+  else if (lab == 1) ground[s_base_g + s_wg[warp] + __popc(bg & lt)] = make_float4(q.x, q.y, q.z, 1.f);
+}
+
+__global__ void init_keys_kernel(unsigned* keys) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < kPolarCells) keys[k] = fkey(1000.f);
+}
+
+}  // namespace
+
+int ground_alloc(Ctx* c) {
+  const size_t np = (size_t)c->max_points;
+  c->max_tiles = (c->max_points + kScanTile - 1) / kScanTile;
+  LMOT_CUDA(c, cudaMalloc(&c->d_points, np * sizeof(float4)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_stage_in, np * 4 * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_cell, np * sizeof(uint16_t)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_polar_key, kPolarCells * sizeof(unsigned)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_minz, kPolarCells * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_height, kPolarCells * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_smoothed, kPolarCells * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_hdiff, kPolarCells * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_hg, kPolarCells * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_labels, np));
+  LMOT_CUDA(c, cudaMalloc(&c->d_elev, np * sizeof(float4)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_ground, np * sizeof(float4)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_tile_desc, (size_t)c->max_tiles * sizeof(unsigned long long)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_counters, CNT_COUNT * sizeof(int)));
+  LMOT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, CNT_COUNT * sizeof(int), c->stream));
+  LMOT_CUDA(c, cudaHostAlloc(&c->h_counters, CNT_COUNT * sizeof(int), cudaHostAllocDefault));
+  init_keys_kernel<<<(kPolarCells + 255) / 256, 256, 0, c->stream>>>(c->d_polar_key);
+  LMOT_CUDA(c, cudaGetLastError());
+  LMOT_CUDA(c, cudaFuncSetAttribute(polar_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kPolarCells * (int)(sizeof(float) + 1)));
+  return LMOT_OK;
+}
+
+void ground_free(Ctx* c) {
+  cudaFree(c->d_points); cudaFree(c->d_stage_in); cudaFree(c->d_cell); cudaFree(c->d_polar_key); cudaFree(c->d_minz);
+  cudaFree(c->d_height); cudaFree(c->d_smoothed); cudaFree(c->d_hdiff); cudaFree(c->d_hg); cudaFree(c->d_labels);
+  cudaFree(c->d_elev); cudaFree(c->d_ground); cudaFree(c->d_tile_desc); cudaFree(c->d_counters);
+  if (c->h_counters) cudaFreeHost(c->h_counters);
+}
+
+int ground_repack(Ctx* c, const float* d_in, int n, int stride) {
+  if (n > 0) repack_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_in, n, stride, c->d_points);
+  LMOT_CUDA(c, cudaGetLastError());
+  return LMOT_OK;
+}
+
+int ground_launch(Ctx* c, const float4* pts, int n) {
+  c->cur_points = pts;
+  c->cur_n = n;
+  const int n_tiles = (n + kScanTile - 1) / kScanTile;
+  if (n > 0) polar_bin_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(pts, n, c->gp, c->d_cell, c->d_polar_key);
+  polar_grid_kernel<<<1, kGridThreads, kPolarCells * (sizeof(float) + 1), c->stream>>>(
+      c->gp, c->d_polar_key, c->d_minz, c->d_height, c->d_smoothed, c->d_hdiff, c->d_hg, c->d_tile_desc, n_tiles,
+      c->d_counters);
+  if (n > 0)
+    classify_partition_kernel<<<n_tiles, kScanTile, 0, c->stream>>>(pts, n, c->d_cell, c->d_hg, c->gp.tol, c->d_labels,
+                                                                  c->d_elev, c->d_ground, c->d_tile_desc, c->d_counters);
+  LMOT_CUDA(c, cudaGetLastError());
+  return LMOT_OK;
+}
+
+}  // namespace lmot

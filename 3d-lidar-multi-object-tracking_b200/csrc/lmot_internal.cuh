@@ -1,0 +1,87 @@
+// lmot_internal.cuh -- context layout and launch prototypes shared by the stage translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include "../../include/lmot.h"
+
+namespace lmot {
+
+constexpr int kNumChannel = LMOT_NUM_CHANNEL;
+constexpr int kNumBin = LMOT_NUM_BIN;
+constexpr int kPolarCells = kNumChannel * kNumBin;  // 9600
+constexpr int kNumGrid = LMOT_NUM_GRID;
+constexpr int kCartCells = kNumGrid * kNumGrid;      // 62500
+constexpr uint16_t kNoCell = 0xFFFFu;
+constexpr int kScanTile = 1024;                      // points per tile of the stable-partition scan
+
+// device-side counters of one frame (one int each; written by kernels, read by later kernels and by fetch)
+enum Counter {
+  CNT_N_ELEV = 0, CNT_N_GROUND, CNT_NUM_CLUSTER, CNT_N_BOXES, CNT_N_CLUSTERED, CNT_ERROR, CNT_N_TRACKS, CNT_N_VIS,
+  CNT_TICKET_A, CNT_TICKET_B, CNT_COUNT = 16
+};
+
+struct GroundParams {
+  float r_min, r_max, t_hmin, t_hmax, t_hdiff, h_sensor;
+  float r_span;          // r_max - r_min evaluated in float (ground_removal.cpp:71)
+  double tol;            // 0.25
+  double tap[3];         // gaussKernel(3, 1.0) computed on the host with the host libm (gaus_blur.cpp:26-49)
+};
+
+struct Ctx {
+  lmot_params prm;
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  GroundParams gp;
+
+  // ---- capacities
+  int max_points = 0, max_tiles = 0;
+
+  // ---- frame input (host-buffer entry points copy here; *_dev entry points use the caller's pointer)
+  float4* d_points = nullptr;
+  float* d_stage_in = nullptr;  // raw staging for stride != 4 inputs
+  const float4* cur_points = nullptr;
+  int cur_n = 0;
+
+  // ---- ground removal
+  uint16_t* d_cell = nullptr;          // per point polar cell (ch*120+bin) or kNoCell
+  unsigned* d_polar_key = nullptr;     // [9600] order-preserving uint key of min z
+  float* d_minz = nullptr;             // [9600] debug / parity
+  float* d_height = nullptr;           // [9600]
+  float* d_smoothed = nullptr;         // [9600]
+  float* d_hdiff = nullptr;            // [9600]
+  float* d_hg = nullptr;               // [9600] hGround of ground cells, -inf for non-ground cells
+  uint8_t* d_labels = nullptr;         // per point 0/1/2
+  float4* d_elev = nullptr;            // compacted elevated cloud
+  float4* d_ground = nullptr;          // compacted ground cloud
+  unsigned long long* d_tile_desc = nullptr;  // decoupled look-back descriptors
+  int* d_counters = nullptr;           // [CNT_COUNT]
+  int* h_counters = nullptr;           // pinned mirror
+
+  // ---- timing
+  bool timing = false;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float stage_ms[4] = {0, 0, 0, 0};
+};
+
+// error helper: records the CUDA error text in the context and returns LMOT_ERR_CUDA
+#define LMOT_CUDA(ctx, call)                                                                     \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      (ctx)->last_error = std::string(#call) + ": " + cudaGetErrorString(e__);                   \
+      return LMOT_ERR_CUDA;                                                                      \
+    }                                                                                            \
+  } while (0)
+
+// ---- stage launchers (asynchronous on ctx->stream) ---------------------------------------------------
+int ground_alloc(Ctx* c);
+void ground_free(Ctx* c);
+// pts: device float4 array of n points
+int ground_launch(Ctx* c, const float4* pts, int n);
+int ground_repack(Ctx* c, const float* d_in, int n, int stride);
+
+}  // namespace lmot

@@ -1,0 +1,187 @@
+/* lmot.h -- C ABI of the B200-native LiDAR multi-object-tracking hot path (liblmot.so).
+ *
+ * Drop-in boundary.  The reference has no FFI; its boundary is four C++ free functions
+ * called from the three ROS node callbacks.  Each entry point below replaces one of them:
+ *
+ *   lmot_ground_remove      <- groundRemove         object_tracking/include/ground_removal.h:62-64
+ *                                                   (def. src/groundremove/ground_removal.cpp:177)
+ *   lmot_component_cluster  <- componentClustering  object_tracking/include/component_clustering.h:20-22
+ *                                                   (def. src/cluster/component_clustering.cpp:260)
+ *   lmot_box_fit            <- boxFitting           object_tracking/include/box_fitting.h:34-36
+ *                                                   (def. src/cluster/box_fitting.cpp:422)
+ *   lmot_track_step         <- getOriginPoints + immUkfJpdaf
+ *                                                   object_tracking/include/imm_ukf_jpda.h:15,19-22
+ *                                                   (def. tracking/imm_ukf_jpda.cpp:74,704)
+ *   lmot_frame              <- the four calls back to back, as object_tracking0/src/main.cpp:51-121 does in
+ *                              one callback (device-resident between stages, one H2D and one D2H per frame)
+ *
+ * Conventions: plain pointers and sizes, caller-owned buffers, no C++/torch types.  Every function returns
+ * LMOT_OK (0) or a negative lmot_status.  A context owns one CUDA device, one stream and all scratch memory;
+ * it is NOT thread-safe (the reference's functions are non-re-entrant too); use one context per sensor stream.
+ * There is no CPU fallback: without a usable CUDA device lmot_create fails with LMOT_ERR_CUDA.
+ *
+ * Point clouds are arrays of float with a caller-given stride in floats (3 = packed XYZ, 4 = XYZI or the
+ * 16-byte pcl::PointXYZ layout the reference's PCL containers use).  Clouds RETURNED by the library are
+ * always stride 4 (x, y, z, 1.0f) == pcl::PointXYZ, so a ROS shell can memcpy them into a PCL cloud.
+ */
+#ifndef LMOT_H
+#define LMOT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMOT_NUM_CHANNEL 80   /* ground_removal.h:16 */
+#define LMOT_NUM_BIN 120      /* ground_removal.h:17 */
+#define LMOT_NUM_GRID 250     /* component_clustering.h:13 */
+#define LMOT_TRACK_DUMP_DOUBLES 236
+
+typedef enum lmot_status {
+  LMOT_OK = 0,
+  LMOT_ERR_INVALID = -1,   /* bad argument */
+  LMOT_ERR_CUDA = -2,      /* CUDA runtime/driver error, or no device (there is no CPU fallback) */
+  LMOT_ERR_CAPACITY = -3,  /* input exceeds a capacity fixed at lmot_create (points, clusters, boxes, tracks) */
+  LMOT_ERR_STATE = -4      /* call sequence error (e.g. fetch before run) */
+} lmot_status;
+
+/* ruleBasedFilter (box_fitting.cpp:97-158) falls off its end without a return when a nested size check fails:
+ * undefined behaviour.  INTENDED = fall-through means `false`; GCC13_O2_COMPAT = what g++ 13 -O2 makes of the
+ * unmodified file (only the n>=30 test and the height window survive).  See SURVEY.md §8c. */
+typedef enum lmot_rule_filter { LMOT_RULE_INTENDED = 0, LMOT_RULE_GCC13_O2_COMPAT = 1 } lmot_rule_filter;
+
+/* Defaults (lmot_default_params) reproduce the reference's constants; citations are file:line under
+ * /root/reference/object_tracking. */
+typedef struct lmot_params {
+  /* ground removal -- src/groundremove/ground_removal.cpp:24-33,239 */
+  float r_min, r_max;        /* 3.4, 120 */
+  float t_hmin, t_hmax;      /* -2.0, -0.4 */
+  float t_hdiff;             /* 0.4 */
+  float h_sensor;            /* 2.0 ("hSeonsor") */
+  double ground_tolerance;   /* 0.25 */
+  /* clustering -- src/cluster/component_clustering.cpp:11 */
+  float roi_m;               /* 50 */
+  /* box fitting -- src/cluster/box_fitting.cpp:18-44,100,308 */
+  int ram_points;            /* 80 */
+  int l_slope_dist;          /* 1 */
+  int l_num_points;          /* 5 */
+  float sensor_height;       /* 2 */
+  float t_height_min, t_height_max;  /* 0.8, 2.6 */
+  float t_width_min, t_width_max;    /* 0.2, 3.5 */
+  float t_len_min, t_len_max;        /* 0.2, 14 */
+  float t_area_max;          /* 20 */
+  float t_ratio_min, t_ratio_max;    /* 1, 8 */
+  float min_len_ratio;       /* 3 */
+  float t_pt_per_m3;         /* 8 */
+  int min_cluster_points;    /* 30 (box_fitting.cpp:100) */
+  int rule_filter;           /* lmot_rule_filter, default LMOT_RULE_INTENDED */
+  /* tracker -- tracking/imm_ukf_jpda.cpp:26-51,70 ; first-frame quirk :741-760 */
+  int oracle_compat_first_frame; /* 1: first frame spawns ONE track from box #1 at the hard-coded (-1.5125,-8.975) */
+  /* capacities (the reference's std::vectors grow without bound; fixed here, LMOT_ERR_CAPACITY when exceeded) */
+  int max_points;            /* per frame, default 1<<20 */
+  int max_clusters;          /* default 4096 (a 250x250 grid with 3x3 dilation cannot hold more) */
+  int max_boxes;             /* default 1024 */
+  int max_tracks;            /* tracks ever created (dead ones keep their slot), default 8192 */
+} lmot_params;
+
+typedef struct lmot_ctx lmot_ctx;
+
+int lmot_default_params(lmot_params* p);
+int lmot_create(lmot_ctx** out, const lmot_params* params, int device);
+void lmot_destroy(lmot_ctx* ctx);
+const char* lmot_strerror(int status);
+const char* lmot_last_error(const lmot_ctx* ctx); /* text of the last CUDA error seen by this context */
+const char* lmot_build_info(void);
+
+/* Run every kernel of this context on an existing CUDA stream (cudaStream_t passed as void*), e.g. torch's
+ * current stream, instead of the context's own.  NULL restores the context's stream. */
+int lmot_set_stream(lmot_ctx* ctx, void* cuda_stream);
+
+/* ---- stage entry points, HOST buffers (synchronous: H2D, kernels, D2H, stream sync) -------------------- */
+
+/* groundRemove.  labels (nullable) gets one byte per input point: 0 = in neither output (range filter /
+ * cell index out of range, ground_removal.cpp:54,233), 1 = ground, 2 = elevated.  elevated / ground (nullable)
+ * receive the order-preserving output clouds, stride 4 floats, capacity n points each. */
+int lmot_ground_remove(lmot_ctx* ctx, const float* points, int n, int stride_floats, uint8_t* labels,
+                       float* elevated, int* n_elevated, float* ground, int* n_ground);
+
+/* componentClustering.  grid = int32[250*250], x-major like array<array<int,250>,250> (written entirely;
+ * the caller's zero-initialisation at src/cluster/main.cpp:72-73 is implied). */
+int lmot_component_cluster(lmot_ctx* ctx, const float* elevated, int n, int stride_floats, int32_t* grid,
+                           int* num_cluster);
+
+/* boxFitting.  boxes = float[max_boxes*8*3] (4 bottom corners z=-sensor_height, then 4 top corners z=maxZ,
+ * box_fitting.cpp:379-389), in cluster-id order.  markers (nullable) = float[max_boxes*6]: centroid xyz and
+ * AABB extent xyz of the cluster (mark_cluster, box_fitting.cpp:161-209). */
+int lmot_box_fit(lmot_ctx* ctx, const float* elevated, int n, int stride_floats, const int32_t* grid,
+                 int num_cluster, float* boxes, int max_boxes, int* n_boxes, float* markers);
+
+/* Outputs of immUkfJpdaf: one entry per track ever created (imm_ukf_jpda.cpp:995-1041).  All pointers are
+ * caller-owned with capacity `cap` entries (vis_bb: cap boxes); nullable ones are skipped. */
+typedef struct lmot_track_out {
+  int cap;
+  int n_tracks;        /* out */
+  int n_vis;           /* out: number of boxes in vis_bb */
+  float* targets;      /* [cap*3]  targetPoints (x, y, -1.73/2) */
+  double* vandyaw;     /* [cap*2]  targetVandYaw (v, yaw + ego yaw) */
+  int32_t* track_manage; /* [cap]  trackNumVec_ */
+  uint8_t* is_static;  /* [cap] */
+  uint8_t* is_vis;     /* [cap] */
+  float* vis_bb;       /* [cap*8*3] boxes of the tracks with is_vis, in track order */
+} lmot_track_out;
+
+/* getOriginPoints(timestamp, v_gps, yaw_gps) then immUkfJpdaf(boxes, timestamp, ...).  timestamp in
+ * microseconds (dt = (ts - ts_prev)/1e6, imm_ukf_jpda.cpp:807).  boxes = float[m*8*3]. */
+int lmot_track_step(lmot_ctx* ctx, const float* boxes, int m, double timestamp_us, double v_gps, double yaw_gps,
+                    lmot_track_out* out);
+
+typedef struct lmot_frame_out {
+  int n_elevated, n_ground, num_cluster, n_boxes; /* out */
+  float* boxes;        /* nullable, [max_boxes*8*3] */
+  int max_boxes;
+  lmot_track_out tracks;
+} lmot_frame_out;
+
+/* The whole hot path on one frame: one H2D of the XYZI frame, four device-resident stages, one D2H. */
+int lmot_frame(lmot_ctx* ctx, const float* points, int n, int stride_floats, double timestamp_us, double v_gps,
+               double yaw_gps, lmot_frame_out* out);
+
+/* ---- DEVICE-resident variants (asynchronous on the context's stream; no host copies) -------------------
+ * d_points: device pointer, stride 4 floats (16-byte aligned).  Results stay in the context's device buffers;
+ * lmot_frame_fetch copies the small artefacts (counts, boxes, track outputs) to the host and synchronises. */
+int lmot_frame_dev(lmot_ctx* ctx, const float* d_points, int n, double timestamp_us, double v_gps, double yaw_gps);
+int lmot_frame_fetch(lmot_ctx* ctx, lmot_frame_out* out);
+int lmot_ground_remove_dev(lmot_ctx* ctx, const float* d_points, int n);
+int lmot_detect_dev(lmot_ctx* ctx, const float* d_points, int n); /* ground + cluster + box, no tracker */
+int lmot_sync(lmot_ctx* ctx);
+
+/* ---- tracker state (checkpoint / teacher-forced parity tests) ------------------------------------------ */
+int lmot_tracker_reset(lmot_ctx* ctx);
+int lmot_tracker_num_tracks(lmot_ctx* ctx, int* n);
+/* dumps = double[n*LMOT_TRACK_DUMP_DOUBLES], layout documented in DESIGN.md (same as oracle/ref_harness.cpp) */
+int lmot_tracker_dump(lmot_ctx* ctx, double* dumps, int cap, int* n);
+int lmot_tracker_load(lmot_ctx* ctx, const double* dumps, int n, int init, double timestamp_us, double ego_velo,
+                      double ego_yaw, double ego_pre_yaw, double ego_point_yaw);
+
+/* ---- inspection of the last frame's device state (parity tests, debugging) ----------------------------- */
+/* polar grid after ground removal: each float[80*120] / uint8[80*120], nullable */
+int lmot_debug_polar_grid(lmot_ctx* ctx, float* minz, float* height, float* smoothed, float* hdiff, float* hground,
+                          uint8_t* isground);
+/* per-point polar cell of the last ground_remove: ch/bin int32[n]; -1/-1 for range-filtered points */
+int lmot_debug_cell_index(lmot_ctx* ctx, int32_t* ch, int32_t* bin, int n);
+/* label grid and per-elevated-point cluster id of the last clustering / box fitting */
+int lmot_debug_label_grid(lmot_ctx* ctx, int32_t* grid, int* num_cluster);
+
+/* host-side self test of the bit-exact atan2f restatement against the host libm (no GPU needed) */
+int lmot_selftest_atan2f(const float* y, const float* x, int n, float* out);
+
+/* Per-stage device time of the last lmot_frame / lmot_frame_dev in milliseconds (cudaEvent), for bench.py:
+ * ms[0] ground, ms[1] cluster, ms[2] box, ms[3] tracker.  Only recorded after lmot_enable_timing(ctx,1). */
+int lmot_enable_timing(lmot_ctx* ctx, int on);
+int lmot_last_stage_ms(lmot_ctx* ctx, float ms[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMOT_H */

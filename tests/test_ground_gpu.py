@@ -1,0 +1,93 @@
+"""GPU parity: lmot_ground_remove vs the reference's groundRemove (oracle/_ref, unmodified sources).
+
+Bar (BASELINE.json north_star): BIT-EXACT polar cell per point, ground/elevated label per point, and the
+order-preserving output clouds.  The 80x120 grid stages are compared bit-for-bit too.
+"""
+import numpy as np
+import pytest
+
+from oracle.ref import labels_from_clouds
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_frame(lm, ref, pts):
+    out = lm.ground_remove(pts)
+    e_ref, g_ref = ref.ground_remove(pts)
+    assert out["elevated"].shape[0] == e_ref.shape[0]
+    assert out["ground"].shape[0] == g_ref.shape[0]
+    assert np.array_equal(out["elevated"][:, :3].view(np.uint32), e_ref.view(np.uint32))
+    assert np.array_equal(out["ground"][:, :3].view(np.uint32), g_ref.view(np.uint32))
+    if len(out["elevated"]):
+        assert np.all(out["elevated"][:, 3] == 1.0)
+    lab_ref = labels_from_clouds(pts, e_ref, g_ref)
+    assert np.array_equal(out["labels"], lab_ref)
+    # point -> polar cell, bit exact (reference getCellIndexFromPoints on the range-filtered points)
+    n = len(pts)
+    ch, b = lm.debug_cell_index(n)
+    ch_r, b_r = ref.cell_index(pts)
+    d = np.hypot(pts[:, 0].astype(np.float32), pts[:, 1].astype(np.float32))
+    kept = ch >= 0
+    assert np.array_equal(ch[kept], ch_r[kept]) and np.array_equal(b[kept], b_r[kept])
+    # points the GPU dropped are exactly those the reference filters or cannot index
+    dropped_ref = (lab_ref == 0)
+    assert np.array_equal(~kept, dropped_ref)
+    # grid stages
+    g_gpu, g_r = lm.debug_polar_grid(), ref.polar_grid(pts)
+    for k in ("minz", "height", "smoothed", "hdiff"):
+        assert np.array_equal(g_gpu[k].view(np.uint32), g_r[k].view(np.uint32)), k
+    assert np.array_equal(g_gpu["isground"], g_r["isground"])
+    gm = g_r["isground"].astype(bool)
+    assert np.array_equal(g_gpu["hground"][gm].view(np.uint32), g_r["hground"][gm].view(np.uint32))
+    return out
+
+
+def test_hdl64_frames_bit_exact(lm, ref_intended, synth):
+    cfg = synth.SceneConfig(seed=3)
+    for ts, pts in synth.frames(cfg, 4):
+        out = _check_frame(lm, ref_intended, pts)
+        assert len(out["elevated"]) > 10000 and len(out["ground"]) > 10000
+
+
+def test_uniform_random_clouds_bit_exact(lm, ref_intended, synth):
+    for seed, n in ((1, 120000), (2, 50001), (3, 1000)):
+        _check_frame(lm, ref_intended, synth.uniform_cloud(n, seed))
+
+
+def test_grid_filters_stress(lm, ref_intended):
+    """Sparse clouds around the thresholds exercise applyMedianFilter / outlierFilter (tHmin runs of 1-2 cells)."""
+    rng = np.random.default_rng(7)
+    for it in range(6):
+        n = 40000
+        r = rng.uniform(3.5, 119.0, n).astype(np.float32)
+        a = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
+        z = rng.choice(np.array([-2.5, -2.0, -1.9, -1.7, -1.5, -0.41, -0.4, -0.39, 0.5], np.float32), n)
+        z = (z + rng.normal(0, 0.02, n) * (rng.random(n) < 0.5)).astype(np.float32)
+        pts = np.stack([r * np.cos(a), r * np.sin(a), z, np.zeros(n, np.float32)], 1).astype(np.float32)
+        _check_frame(lm, ref_intended, pts)
+
+
+def test_edge_cases(lm, ref_intended):
+    # empty cloud
+    out = lm.ground_remove(np.zeros((0, 4), np.float32))
+    assert len(out["elevated"]) == 0 and len(out["ground"]) == 0
+    # single point, points on the range limits, atan2 == +pi (chI == 80 -> dropped), zeros
+    pts = np.array([[10, 0, -1.7, 0], [-10, 0.0, -1.7, 0], [-10, -0.0, -1.7, 0], [3.4, 0, -1.7, 0], [0, 120, 0, 0],
+                    [0, 0, 0, 0], [3.4000001, 0, -1.7, 0], [0, -119.99999, -1.0, 0], [1e-20, -5, -1.8, 0]], np.float32)
+    _check_frame(lm, ref_intended, pts)
+    # stride 3 input gives the same answer as stride 4
+    cloud = np.random.default_rng(5).uniform(-30, 30, (5000, 3)).astype(np.float32)
+    cloud[:, 2] = np.random.default_rng(6).uniform(-2.5, 1, 5000)
+    a = lm.ground_remove(cloud)
+    b = lm.ground_remove(np.concatenate([cloud, np.ones((5000, 1), np.float32)], 1))
+    assert np.array_equal(a["labels"], b["labels"])
+    e_ref, g_ref = ref_intended.ground_remove(cloud)
+    assert np.array_equal(a["elevated"][:, :3], e_ref)
+
+
+def test_repeatable_and_stateless(lm, synth):
+    pts = synth.uniform_cloud(30000, 11)
+    a = lm.ground_remove(pts)
+    lm.ground_remove(synth.uniform_cloud(1000, 12))
+    b = lm.ground_remove(pts)
+    assert np.array_equal(a["labels"], b["labels"]) and np.array_equal(a["elevated"], b["elevated"])
