@@ -161,6 +161,39 @@ class Lmot:
     def ground_remove_dev(self, d_ptr: int, n: int):
         self._chk(self.lib.lmot_ground_remove_dev(self.h, C.c_void_p(d_ptr), n))
 
+    # ---- componentClustering ------------------------------------------------------------------------------
+    def component_cluster(self, elevated):
+        """-> (grid (250,250) int32 x-major, num_cluster)"""
+        if len(elevated) == 0:
+            p, n, s = np.zeros((1, 4), np.float32), 0, 4
+        else:
+            p, n, s = _pts(elevated)
+        grid = np.zeros(250 * 250, np.int32)
+        nc = C.c_int(0)
+        self._chk(self.lib.lmot_component_cluster(self.h, _fp(p), n, s, grid.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(nc)))
+        return grid.reshape(250, 250), nc.value
+
+    # ---- boxFitting ---------------------------------------------------------------------------------------
+    def box_fit(self, elevated, grid, num_cluster, max_boxes: int = 1024):
+        """-> (boxes (B,8,3) f32, markers (B,6) f32) in cluster-id order"""
+        if len(elevated) == 0:
+            p, n, s = np.zeros((1, 4), np.float32), 0, 4
+        else:
+            p, n, s = _pts(elevated)
+        g = np.ascontiguousarray(grid, np.int32).reshape(-1)
+        boxes = np.zeros((max_boxes, 8, 3), np.float32)
+        markers = np.zeros((max_boxes, 6), np.float32)
+        nb = C.c_int(0)
+        self._chk(self.lib.lmot_box_fit(self.h, _fp(p), n, s, g.ctypes.data_as(C.POINTER(C.c_int32)), int(num_cluster), _fp(boxes),
+                                        max_boxes, C.byref(nb), _fp(markers)))
+        return boxes[: nb.value].copy(), markers[: nb.value].copy()
+
+    def debug_label_grid(self):
+        grid = np.zeros(250 * 250, np.int32)
+        nc = C.c_int(0)
+        self._chk(self.lib.lmot_debug_label_grid(self.h, grid.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(nc)))
+        return grid.reshape(250, 250), nc.value
+
     def debug_polar_grid(self):
         names = ["minz", "height", "smoothed", "hdiff", "hground"]
         arrs = [np.zeros(80 * 120, np.float32) for _ in names]

@@ -14,9 +14,6 @@ struct lmot_ctx {
   Ctx c;
 };
 
-namespace lmot {
-int ground_repack(Ctx* c, const float* d_in, int n, int stride);
-}
 
 namespace {
 
@@ -33,12 +30,12 @@ void gauss_taps(double tap[3]) {
   for (int x = 0; x < samples; ++x) tap[x] /= sum;
 }
 
-int upload_points(Ctx* c, const float* points, int n, int stride) {
+int upload_points(Ctx* c, const float* points, int n, int stride, float4* d_dst) {
   if (n < 0 || (n > 0 && !points) || stride < 3) return LMOT_ERR_INVALID;
   if (n > c->max_points) return LMOT_ERR_CAPACITY;
   if (n == 0) return LMOT_OK;
   if (stride == 4) {
-    LMOT_CUDA(c, cudaMemcpyAsync(c->d_points, points, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    LMOT_CUDA(c, cudaMemcpyAsync(d_dst, points, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
   } else {
     if (stride > 4) {  // wide host records: pack xyz on the host side of the copy
       std::vector<float> tmp((size_t)n * 3);
@@ -49,7 +46,7 @@ int upload_points(Ctx* c, const float* points, int n, int stride) {
     } else {
       LMOT_CUDA(c, cudaMemcpyAsync(c->d_stage_in, points, (size_t)n * stride * 4, cudaMemcpyHostToDevice, c->stream));
     }
-    int rc = ground_repack(c, c->d_stage_in, n, stride);
+    int rc = ground_repack(c, c->d_stage_in, n, stride, d_dst);
     if (rc) return rc;
   }
   return LMOT_OK;
@@ -58,6 +55,23 @@ int upload_points(Ctx* c, const float* points, int n, int stride) {
 int fetch_counters(Ctx* c) {
   LMOT_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LMOT_OK;
+}
+
+// write host-known counts into the device counter block (stage entry points that start mid-pipeline)
+int set_counter(Ctx* c, int which, int value) {
+  c->h_set[which] = value;
+  LMOT_CUDA(c, cudaMemcpyAsync(c->d_counters + which, c->h_set + which, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  return LMOT_OK;
+}
+
+int check_device_error(Ctx* c) {
+  const int e = c->h_counters[CNT_ERROR];
+  if (e != 0) {
+    set_counter(c, CNT_ERROR, 0);
+    cudaStreamSynchronize(c->stream);
+    return e;
+  }
   return LMOT_OK;
 }
 
@@ -119,6 +133,8 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return LMOT_ERR_CUDA; }
   c->stream = c->own_stream;
   int rc = ground_alloc(c);
+  if (rc == LMOT_OK) rc = cluster_alloc(c);
+  if (rc == LMOT_OK) rc = boxfit_alloc(c);
   if (rc == LMOT_OK) rc = (cudaStreamSynchronize(c->stream) == cudaSuccess) ? LMOT_OK : LMOT_ERR_CUDA;
   if (rc != LMOT_OK) { lmot_destroy(h); return rc; }
   for (int i = 0; i < 5; ++i) cudaEventCreate(&c->ev[i]);
@@ -132,6 +148,8 @@ void lmot_destroy(lmot_ctx* ctx) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   ground_free(c);
+  cluster_free(c);
+  boxfit_free(c);
   for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete ctx;
@@ -160,7 +178,7 @@ int lmot_ground_remove(lmot_ctx* ctx, const float* points, int n, int stride, ui
   if (!ctx) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
   cudaSetDevice(c->device);
-  int rc = upload_points(c, points, n, stride);
+  int rc = upload_points(c, points, n, stride, c->d_points);
   if (rc) return rc;
   rc = ground_launch(c, c->d_points, n);
   if (rc) return rc;
@@ -174,6 +192,70 @@ int lmot_ground_remove(lmot_ctx* ctx, const float* points, int n, int stride, ui
   if (ground && ng > 0) LMOT_CUDA(c, cudaMemcpyAsync(ground, c->d_ground, (size_t)ng * 16, cudaMemcpyDeviceToHost, c->stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
   return LMOT_OK;
+}
+
+int lmot_component_cluster(lmot_ctx* ctx, const float* elevated, int n, int stride, int32_t* grid, int* num_cluster) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  int rc = upload_points(c, elevated, n, stride, c->d_elev);
+  if (rc) return rc;
+  if ((rc = set_counter(c, CNT_N_ELEV, n))) return rc;
+  if ((rc = cluster_launch(c, n))) return rc;
+  if ((rc = fetch_counters(c))) return rc;
+  if (num_cluster) *num_cluster = c->h_counters[CNT_NUM_CLUSTER];
+  if (grid) {
+    LMOT_CUDA(c, cudaMemcpyAsync(grid, c->d_label_grid, kCartCells * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return LMOT_OK;
+}
+
+int lmot_debug_label_grid(lmot_ctx* ctx, int32_t* grid, int* num_cluster) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  int rc = fetch_counters(c);
+  if (rc) return rc;
+  if (num_cluster) *num_cluster = c->h_counters[CNT_NUM_CLUSTER];
+  if (grid) {
+    LMOT_CUDA(c, cudaMemcpyAsync(grid, c->d_label_grid, kCartCells * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return LMOT_OK;
+}
+
+int lmot_box_fit(lmot_ctx* ctx, const float* elevated, int n, int stride, const int32_t* grid, int num_cluster,
+                 float* boxes, int max_boxes, int* n_boxes, float* markers) {
+  if (!ctx || !grid || num_cluster < 0 || max_boxes < 0) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  if (num_cluster > c->prm.max_clusters) return LMOT_ERR_CAPACITY;
+  int rc = upload_points(c, elevated, n, stride, c->d_elev);
+  if (rc) return rc;
+  LMOT_CUDA(c, cudaMemcpyAsync(c->d_label_grid, grid, kCartCells * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if ((rc = set_counter(c, CNT_N_ELEV, n))) return rc;
+  if ((rc = set_counter(c, CNT_NUM_CLUSTER, num_cluster))) return rc;
+  if ((rc = cluster_cells_only(c, n))) return rc;
+  if ((rc = boxfit_launch(c, n))) return rc;
+  if ((rc = fetch_counters(c))) return rc;
+  if ((rc = check_device_error(c))) return rc;
+  const int nb = c->h_counters[CNT_N_BOXES];
+  if (n_boxes) *n_boxes = nb;
+  const int ncopy = nb < max_boxes ? nb : max_boxes;
+  if (boxes && ncopy > 0) LMOT_CUDA(c, cudaMemcpyAsync(boxes, c->d_boxes, (size_t)ncopy * 24 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (markers && ncopy > 0) LMOT_CUDA(c, cudaMemcpyAsync(markers, c->d_markers, (size_t)ncopy * 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return nb > max_boxes ? LMOT_ERR_CAPACITY : LMOT_OK;
+}
+
+int lmot_detect_dev(lmot_ctx* ctx, const float* d_points, int n) {
+  if (!ctx || n < 0 || (n > 0 && !d_points)) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  if (n > c->max_points) return LMOT_ERR_CAPACITY;
+  int rc = ground_launch(c, reinterpret_cast<const float4*>(d_points), n);
+  if (rc) return rc;
+  if ((rc = cluster_launch(c, n))) return rc;
+  return boxfit_launch(c, n);
 }
 
 int lmot_debug_polar_grid(lmot_ctx* ctx, float* minz, float* height, float* smoothed, float* hdiff, float* hground,

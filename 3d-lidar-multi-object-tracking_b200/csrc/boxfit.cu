@@ -1,0 +1,537 @@
+// boxfit.cu -- per-cluster L-shape / minimum-area-rectangle box fitting on sm_100a.
+//
+// Replaces boxFitting (/root/reference/object_tracking/src/cluster/box_fitting.cpp:422-431):
+//   getClusteredPoints (:46-72)   gather the elevated points of every cluster IN CLOUD ORDER
+//   getBoundingBox (:212-418)     per cluster: pixelise @18 px/m around point #0, first-occurrence min/max
+//                                 slope points, max z (:239-293); L-shape fit from 80 seeded random samples
+//                                 (:296-356) or cv::minAreaRect (:358-365); ruleBasedFilter (:97-158);
+//                                 8-corner box (:379-389); mark_cluster centroid + AABB (:161-209)
+//
+// The reference's results depend on the order of the points inside a cluster (point #0, first-occurrence
+// ties, the random index picks the i-th point), so the gather is a STABLE counting sort by cluster id:
+//   B1 tile_hist_kernel    per 1024-point tile: cluster id of each point (label grid lookup through the u16 cell
+//                          id kept by clustering) + shared-memory histogram -> table[tile][cluster]
+//   B2 seg_offsets_kernel  exclusive scan over tiles per cluster, then over clusters -> segment starts
+//   B3 scatter_kernel      stable in-tile ranks (warp match_any, warps in order) -> sorted point indices
+//   B4 box_fit_kernel      one CTA per cluster (grid-stride), all of getBoundingBox; the last CTA to finish
+//                          compacts the accepted boxes in cluster-id order (:355,365 skip rejected clusters).
+//
+// cv::minAreaRect is third-party arithmetic that is not in /root/reference: it is implemented as the exact
+// integer contract documented in oracle/mar_contract.cpp / DESIGN.md (parity for that one call is UNPINNED
+// against OpenCV itself, bit-exact against the contract).
+#include <cfloat>
+#include <climits>
+#include <random>
+#include "lmot_internal.cuh"
+
+namespace lmot {
+
+namespace {
+
+constexpr int kTile = 1024;
+constexpr int kFitThreads = 256;
+constexpr int kCols = 1800;        // pixel columns a cluster can span: offsetX-450 = picX-initPicX in [-899,899]
+constexpr int kColShift = 899 - 450;
+constexpr int kHullCap = 2048;
+
+// ---------------------------------------------------------------------------------------------- B1
+__global__ void __launch_bounds__(kTile)
+tile_hist_kernel(const uint16_t* __restrict__ cart, const int* __restrict__ label_grid, const int* __restrict__ counters,
+                 uint16_t* __restrict__ pcid, int* __restrict__ table, int max_clusters) {
+  extern __shared__ int s_hist[];
+  const int n = counters[CNT_N_ELEV];
+  const int K = min(counters[CNT_NUM_CLUSTER], max_clusters);
+  const int tile = blockIdx.x;
+  if (tile * kTile >= n) return;
+  for (int k = threadIdx.x; k <= K; k += kTile) s_hist[k] = 0;
+  __syncthreads();
+  const int i = tile * kTile + threadIdx.x;
+  unsigned cid = 0;
+  if (i < n) {
+    const unsigned c = cart[i];
+    if (c != kNoCell) cid = (unsigned)__ldg(&label_grid[c]);
+    if (cid > (unsigned)K) cid = 0;                    // capacity overflow is reported by seg_offsets_kernel
+    pcid[i] = (uint16_t)cid;
+  }
+  const unsigned grp = __match_any_sync(0xFFFFFFFFu, cid);
+  if (cid != 0 && (threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&s_hist[cid], __popc(grp));
+  __syncthreads();
+  int* row = table + (size_t)tile * (max_clusters + 1);
+  for (int k = threadIdx.x; k <= K; k += kTile) row[k] = s_hist[k];
+}
+
+// ---------------------------------------------------------------------------------------------- B2
+__global__ void __launch_bounds__(1024)
+seg_offsets_kernel(int* __restrict__ table, int* counters,
+                   int* __restrict__ seg_start, int* __restrict__ seg_size, int max_clusters, int* __restrict__ done) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int n = counters[CNT_N_ELEV];
+  int K = counters[CNT_NUM_CLUSTER];
+  if (threadIdx.x == 0) {
+    s_carry = 0;
+    *done = 0;
+    if (K > max_clusters) counters[CNT_ERROR] = LMOT_ERR_CAPACITY;
+  }
+  K = min(K, max_clusters);
+  const int n_tiles = (n + kTile - 1) / kTile;
+  const int stride = max_clusters + 1;
+  __syncthreads();
+  for (int k0 = 1; k0 <= K; k0 += 1024) {
+    const int k = k0 + threadIdx.x;
+    int total = 0;
+    if (k <= K) {
+      for (int t = 0; t < n_tiles; ++t) {
+        const int v = table[(size_t)t * stride + k];
+        table[(size_t)t * stride + k] = total;
+        total += v;
+      }
+    }
+    // block exclusive scan of `total` (+ carry from previous chunks of 1024 clusters)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int v = s_warp[lane];
+      int wi = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += t; }
+      s_warp[lane] = wi - v;
+    }
+    __syncthreads();
+    const int excl = s_carry + s_warp[warp] + incl - total;
+    if (k <= K) { seg_start[k] = excl; seg_size[k] = total; }
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = excl + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counters[CNT_N_CLUSTERED] = s_carry;
+}
+
+// ---------------------------------------------------------------------------------------------- B3
+__global__ void __launch_bounds__(kTile)
+scatter_kernel(const uint16_t* __restrict__ pcid, const int* __restrict__ counters, const int* __restrict__ table,
+               const int* __restrict__ seg_start, int* __restrict__ sorted_idx, int max_clusters) {
+  extern __shared__ int s_cur[];
+  const int n = counters[CNT_N_ELEV];
+  const int K = min(counters[CNT_NUM_CLUSTER], max_clusters);
+  const int tile = blockIdx.x;
+  if (tile * kTile >= n) return;
+  const int* row = table + (size_t)tile * (max_clusters + 1);
+  for (int k = threadIdx.x + 1; k <= K; k += kTile) s_cur[k] = seg_start[k] + row[k];
+  __syncthreads();
+  const int i = tile * kTile + threadIdx.x;
+  const unsigned cid = (i < n) ? pcid[i] : 0u;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned grp = __match_any_sync(0xFFFFFFFFu, cid);
+  const int leader = __ffs(grp) - 1;
+  const int rank = __popc(grp & ((1u << lane) - 1u));
+  // warps take their turn in order so that ranks follow the cloud order
+  for (int w = 0; w < kTile / 32; ++w) {
+    if (warp == w) {
+      int base = 0;
+      if (cid != 0 && lane == leader) { base = s_cur[cid]; s_cur[cid] = base + __popc(grp); }
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      if (cid != 0) sorted_idx[base + rank] = i;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- B4
+struct BoxParams {
+  float roi, pic_scale, sensor_height;
+  int ram_points, l_slope_dist, l_num_points, min_points, rule_mode;
+  float t_height_min, t_height_max, t_width_min, t_width_max, t_len_min, t_len_max, t_area_max, t_ratio_min, t_ratio_max,
+      min_len_ratio, t_pt_per_m3;
+};
+
+__device__ __forceinline__ unsigned okey(float f) {   // order-preserving, -0 == +0
+  if (f == 0.f) f = 0.f;
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, Op op, T* s_buf) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+  __syncthreads();
+  if (lane == 0) s_buf[warp] = v;
+  __syncthreads();
+  T r = s_buf[0];
+  for (int w = 1; w < kFitThreads / 32; ++w) r = op(r, s_buf[w]);
+  return r;
+}
+
+struct MinU64 { __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a < b ? a : b; } };
+struct MaxU64 { __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a > b ? a : b; } };
+struct MaxF { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+struct MinF { __device__ float operator()(float a, float b) const { return fminf(a, b); } };
+struct AddD { __device__ double operator()(double a, double b) const { return a + b; } };
+struct MinI { __device__ int operator()(int a, int b) const { return a < b ? a : b; } };
+struct MaxI { __device__ int operator()(int a, int b) const { return a > b ? a : b; } };
+
+// ruleBasedFilter, box_fitting.cpp:97-158 (see lmot_rule_filter in lmot.h for the two modes)
+__device__ bool rule_filter(const float pc[4][2], float maxZ, int n, const BoxParams& P) {
+  if (n < P.min_points) return false;
+  const float x1 = pc[0][0], y1 = pc[0][1], x2 = pc[1][0], y2 = pc[1][1], x3 = pc[2][0], y3 = pc[2][1];
+  const float dist1 = sqrtf((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2));
+  const float dist2 = sqrtf((x3 - x2) * (x3 - x2) + (y3 - y2) * (y3 - y2));
+  float length, width;
+  if (dist1 > dist2) { length = dist1; width = dist2; } else { length = dist2; width = dist1; }
+  const float height = maxZ + P.sensor_height;
+  const float area = dist1 * dist2;
+  const float mass = area * height;
+  const float ratio = length / width;
+  if (height > P.t_height_min && height < P.t_height_max) {
+    if (P.rule_mode == LMOT_RULE_GCC13_O2_COMPAT) return true;
+    if (width > P.t_width_min && width < P.t_width_max)
+      if (length > P.t_len_min && length < P.t_len_max)
+        if (area < P.t_area_max)
+          if ((float)n > mass * P.t_pt_per_m3) {
+            if (length > P.min_len_ratio) { if (ratio > P.t_ratio_min && ratio < P.t_ratio_max) return true; }
+            else return true;
+          }
+    return false;   // INTENDED: the reference falls off the end here (undefined behaviour)
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(kFitThreads)
+box_fit_kernel(const float4* __restrict__ elev, const int* __restrict__ sorted_idx, const int* __restrict__ seg_start,
+               const int* __restrict__ seg_size, int* __restrict__ counters, BoxParams P,
+               const unsigned long long* __restrict__ mt_raw, int n_raw, int max_clusters, int max_boxes,
+               float* __restrict__ cl_box, float* __restrict__ cl_marker, uint8_t* __restrict__ cl_ok,
+               float* __restrict__ boxes, float* __restrict__ markers, int* __restrict__ done) {
+  __shared__ int s_lo[kCols], s_hi[kCols];
+  __shared__ short s_hx[kHullCap], s_hy[kHullCap];
+  __shared__ unsigned long long s_red64[kFitThreads / 32];
+  __shared__ float s_redf[kFitThreads / 32];
+  __shared__ double s_redd[kFitThreads / 32];
+  __shared__ int s_redi[kFitThreads / 32];
+  __shared__ int s_m;                        // hull size
+  __shared__ int s_best;                     // best edge
+  __shared__ unsigned long long s_bnum[kFitThreads / 32], s_bl[kFitThreads / 32];
+  __shared__ int s_bidx[kFitThreads / 32];
+  __shared__ float s_pc[4][2];
+  __shared__ int s_flag;
+  const int tid = threadIdx.x;
+  const int K = min(counters[CNT_NUM_CLUSTER], max_clusters);
+  const float half = P.roi / 2;
+  const float pic = P.pic_scale * P.roi;     // 900
+
+  for (int k = blockIdx.x + 1; k <= K; k += gridDim.x) {
+    const int n = seg_size[k];
+    const int* seg = sorted_idx + seg_start[k];
+    if (tid == 0) cl_ok[k] = 0;
+    if (n < P.min_points || n <= 0) continue;      // ruleBasedFilter's first test (:100) rejects it whatever the fit
+
+    // ---- point #0 and the pixel offsets (:218-225)
+    const float4 q0 = __ldg(&elev[seg[0]]);
+    const int initX = (int)floorf((q0.x + half) * P.pic_scale);
+    const int initY = (int)floorf((q0.y + half) * P.pic_scale);
+    const int initPicX = initX;
+    const int initPicY = (int)(pic - (float)initY);
+    const int offsetInitX = (int)(P.roi * P.pic_scale / 2 - (float)initPicX);
+    const int offsetInitY = (int)(P.roi * P.pic_scale / 2 - (float)initPicY);
+
+    // ---- per-point pass (:239-293): column extremes for the hull, slope extremes, max z, centroid, AABB
+    for (int c = tid; c < kCols; c += kFitThreads) { s_lo[c] = INT_MAX; s_hi[c] = INT_MIN; }
+    __syncthreads();
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    float maxZ = -99.f;
+    double sx = 0, sy = 0, sz = 0;
+    float mnx = FLT_MAX, mny = FLT_MAX, mnz = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX, mxz = -FLT_MAX;
+    for (int j = tid; j < n; j += kFitThreads) {
+      const float4 q = __ldg(&elev[seg[j]]);
+      const int x = (int)floorf((q.x + half) * P.pic_scale);
+      const int y = (int)floorf((q.y + half) * P.pic_scale);
+      const int picX = x, picY = (int)(pic - (float)y);
+      const int offX = picX + offsetInitX, offY = picY + offsetInitY;
+      const int col = offX + kColShift;
+      if (col >= 0 && col < kCols) { atomicMin(&s_lo[col], offY); atomicMax(&s_hi[col], offY); }
+      const float m = q.y / q.x;
+      if (m < 999.f) { const unsigned long long key = ((unsigned long long)okey(m) << 32) | (unsigned)j; kmin = kmin < key ? kmin : key; }
+      if (m > -999.f) { const unsigned long long key = ((unsigned long long)okey(m) << 32) | (0xFFFFFFFFu - (unsigned)j); kmax = kmax > key ? kmax : key; }
+      if (q.z > maxZ) maxZ = q.z;
+      sx += q.x; sy += q.y; sz += q.z;
+      mnx = fminf(mnx, q.x); mny = fminf(mny, q.y); mnz = fminf(mnz, q.z);
+      mxx = fmaxf(mxx, q.x); mxy = fmaxf(mxy, q.y); mxz = fmaxf(mxz, q.z);
+    }
+    kmin = block_reduce(kmin, MinU64(), s_red64);
+    kmax = block_reduce(kmax, MaxU64(), s_red64);
+    maxZ = block_reduce(maxZ, MaxF(), s_redf);
+    sx = block_reduce(sx, AddD(), s_redd); sy = block_reduce(sy, AddD(), s_redd); sz = block_reduce(sz, AddD(), s_redd);
+    mnx = block_reduce(mnx, MinF(), s_redf); mny = block_reduce(mny, MinF(), s_redf); mnz = block_reduce(mnz, MinF(), s_redf);
+    mxx = block_reduce(mxx, MaxF(), s_redf); mxy = block_reduce(mxy, MaxF(), s_redf); mxz = block_reduce(mxz, MaxF(), s_redf);
+
+    // first-occurrence min / max slope points (:268-280).  If no slope beats the 999 / -999 seeds the reference
+    // reads uninitialised floats; defined here as (0,0).
+    float minMx = 0.f, minMy = 0.f, maxMx = 0.f, maxMy = 0.f;
+    if (kmin != ~0ull) { const float4 q = __ldg(&elev[seg[(unsigned)(kmin & 0xFFFFFFFFull)]]); minMx = q.x; minMy = q.y; }
+    if (kmax != 0ull) { const float4 q = __ldg(&elev[seg[0xFFFFFFFFu - (unsigned)(kmax & 0xFFFFFFFFull)]]); maxMx = q.x; maxMy = q.y; }
+    const float xDist = maxMx - minMx, yDist = maxMy - minMy;
+    const float slopeDist = sqrtf(xDist * xDist + yDist * yDist);
+    const float slope = (maxMy - minMy) / (maxMx - minMx);
+
+    float pc[4][2];
+    if (slopeDist > (float)P.l_slope_dist && n > P.l_num_points && (maxMy > 8.f || maxMy < -5.f)) {
+      // ---- L-shape (:303-356): 80 draws of uniform_int_distribution<>(0,n-1) over mt19937_64(0), Lemire mapping
+      // (libstdc++ >= 11): idx = hi64(raw*n), redraw while lo64 < 2^64 mod n.  First strictly larger distance wins.
+      if (tid == 0) {
+        float maxDist = 0.f, maxDx = 0.f, maxDy = 0.f;   // maxDx/maxDy are uninitialised in the reference if no dist > 0
+        const float den = sqrtf(slope * slope + 1);
+        const unsigned long long un = (unsigned long long)n;
+        const unsigned long long thr = (0ull - un) % un;
+        int cur = 0;
+        for (int i = 0; i < P.ram_points; ++i) {
+          unsigned long long raw = mt_raw[cur % n_raw]; ++cur;
+          unsigned long long lo = raw * un;
+          while (lo < thr) { raw = mt_raw[cur % n_raw]; ++cur; lo = raw * un; }
+          const unsigned pInd = (unsigned)__umul64hi(raw, un);
+          const float4 q = __ldg(&elev[seg[pInd]]);
+          const float dist = fabsf(slope * q.x - 1 * q.y + maxMy - slope * maxMx) / den;
+          if (dist > maxDist) { maxDist = dist; maxDx = q.x; maxDy = q.y; }
+        }
+        const float maxMvecX = maxMx - maxDx, maxMvecY = maxMy - maxDy;
+        const float minMvecX = minMx - maxDx, minMvecY = minMy - maxDy;
+        s_pc[0][0] = minMx; s_pc[0][1] = minMy;
+        s_pc[1][0] = maxDx; s_pc[1][1] = maxDy;
+        s_pc[2][0] = maxMx; s_pc[2][1] = maxMy;
+        s_pc[3][0] = maxDx + maxMvecX + minMvecX; s_pc[3][1] = maxDy + maxMvecY + minMvecY;
+      }
+      __syncthreads();
+    } else {
+      // ---- MAR contract (oracle/mar_contract.cpp): strict hull of the pixel set from the column extremes
+      if (tid == 0) {
+        // Andrew's monotone chain exactly as oracle/mar_contract.cpp runs it, over the reduced sorted point list
+        // R = {(c, lo[c]), (c, hi[c]) if hi != lo : c ascending} (hull(R) == hull(all pixels), same canonical order)
+        int first = -1, last = -1, nR = 0;
+        for (int c = 0; c < kCols; ++c)
+          if (s_lo[c] != INT_MAX) { if (first < 0) first = c; last = c; nR += (s_hi[c] != s_lo[c]) ? 2 : 1; }
+        int m = 0;
+        auto push = [&](int px, int py, int floor_k) {
+          while (m >= floor_k) {
+            const long long cr = (long long)(s_hx[m - 1] - s_hx[m - 2]) * (py - s_hy[m - 2]) -
+                                 (long long)(s_hy[m - 1] - s_hy[m - 2]) * (px - s_hx[m - 2]);
+            if (cr <= 0) --m; else break;
+          }
+          if (m < kHullCap) { s_hx[m] = (short)px; s_hy[m] = (short)py; }
+          ++m;
+        };
+        if (nR <= 2) {
+          for (int c = first; c <= last && first >= 0; ++c) {
+            if (s_lo[c] == INT_MAX) continue;
+            s_hx[m] = (short)(c - kColShift); s_hy[m] = (short)s_lo[c]; ++m;
+            if (s_hi[c] != s_lo[c]) { s_hx[m] = (short)(c - kColShift); s_hy[m] = (short)s_hi[c]; ++m; }
+          }
+        } else {
+          for (int c = first; c <= last; ++c) {            // lower pass over R ascending
+            if (s_lo[c] == INT_MAX) continue;
+            push(c - kColShift, s_lo[c], 2);
+            if (s_hi[c] != s_lo[c]) push(c - kColShift, s_hi[c], 2);
+          }
+          const int t0 = m + 1;
+          bool skip = true;                                 // R's last element is already the end of the chain
+          for (int c = last; c >= first; --c) {             // upper pass over R descending
+            if (s_lo[c] == INT_MAX) continue;
+            if (s_hi[c] != s_lo[c]) { if (skip) skip = false; else push(c - kColShift, s_hi[c], t0); }
+            if (skip) skip = false; else push(c - kColShift, s_lo[c], t0);
+          }
+          --m;                                              // the start point was pushed again to close the chain
+        }
+        if (m > kHullCap) { counters[CNT_ERROR] = LMOT_ERR_CAPACITY; m = kHullCap; }
+        s_m = m;
+      }
+      __syncthreads();
+      const int m = s_m;
+      float rc[4][2];
+      if (m == 1) {
+        for (int c = 0; c < 4; ++c) { rc[c][0] = (float)s_hx[0]; rc[c][1] = (float)s_hy[0]; }
+      } else if (m == 2) {
+        rc[0][0] = rc[1][0] = (float)s_hx[0]; rc[0][1] = rc[1][1] = (float)s_hy[0];
+        rc[2][0] = rc[3][0] = (float)s_hx[1]; rc[2][1] = rc[3][1] = (float)s_hy[1];
+      } else {
+        // exact min-area edge: area_i = W*T/l compared as rationals, ties -> lowest edge index
+        unsigned long long bnum = 0, bl = 1; int bidx = INT_MAX;
+        for (int i = tid; i < m; i += kFitThreads) {
+          const int i1 = (i + 1 == m) ? 0 : i + 1;
+          const int dx = s_hx[i1] - s_hx[i], dy = s_hy[i1] - s_hy[i];
+          int smin = INT_MAX, smax = INT_MIN, tmin = INT_MAX, tmax = INT_MIN;
+          for (int j = 0; j < m; ++j) {
+            const int s = s_hx[j] * dx + s_hy[j] * dy, t = -s_hx[j] * dy + s_hy[j] * dx;
+            smin = min(smin, s); smax = max(smax, s); tmin = min(tmin, t); tmax = max(tmax, t);
+          }
+          const unsigned long long num = (unsigned long long)(smax - smin) * (unsigned long long)(tmax - tmin);
+          const unsigned long long l = (unsigned long long)((long long)dx * dx + (long long)dy * dy);
+          if (bidx == INT_MAX || num * bl < bnum * l) { bnum = num; bl = l; bidx = i; }   // i ascending per thread
+        }
+        // warp then block argmin with the same comparator (index breaks ties)
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long onum = __shfl_xor_sync(0xFFFFFFFFu, bnum, o), ol = __shfl_xor_sync(0xFFFFFFFFu, bl, o);
+          const int oidx = __shfl_xor_sync(0xFFFFFFFFu, bidx, o);
+          if (oidx != INT_MAX) {
+            const bool better = (bidx == INT_MAX) || (onum * bl < bnum * ol) || (onum * bl == bnum * ol && oidx < bidx);
+            if (better) { bnum = onum; bl = ol; bidx = oidx; }
+          }
+        }
+        if ((tid & 31) == 0) { s_bnum[tid >> 5] = bnum; s_bl[tid >> 5] = bl; s_bidx[tid >> 5] = bidx; }
+        __syncthreads();
+        if (tid == 0) {
+          for (int w = 1; w < kFitThreads / 32; ++w) {
+            if (s_bidx[w] == INT_MAX) continue;
+            const bool better = (bidx == INT_MAX) || (s_bnum[w] * bl < bnum * s_bl[w]) || (s_bnum[w] * bl == bnum * s_bl[w] && s_bidx[w] < bidx);
+            if (better) { bnum = s_bnum[w]; bl = s_bl[w]; bidx = s_bidx[w]; }
+          }
+          s_best = bidx;
+        }
+        __syncthreads();
+        const int best = s_best, b1 = (best + 1 == m) ? 0 : best + 1;
+        long long ux = s_hx[b1] - s_hx[best], uy = s_hy[b1] - s_hy[best];
+        for (int r = 0; r < 4 && !(ux >= 0 && uy < 0); ++r) { const long long t = ux; ux = -uy; uy = t; }
+        const long long l = ux * ux + uy * uy;
+        int smin = INT_MAX, smax = INT_MIN, tmin = INT_MAX, tmax = INT_MIN;
+        for (int j = tid; j < m; j += kFitThreads) {
+          const int s = (int)(s_hx[j] * ux + s_hy[j] * uy), t = (int)(-s_hx[j] * uy + s_hy[j] * ux);
+          smin = min(smin, s); smax = max(smax, s); tmin = min(tmin, t); tmax = max(tmax, t);
+        }
+        smin = block_reduce(smin, MinI(), s_redi); smax = block_reduce(smax, MaxI(), s_redi);
+        tmin = block_reduce(tmin, MinI(), s_redi); tmax = block_reduce(tmax, MaxI(), s_redi);
+        const long long S[4] = {smin, smin, smax, smax}, T[4] = {tmax, tmin, tmin, tmax};
+        for (int c = 0; c < 4; ++c) {
+          rc[c][0] = (float)((double)(S[c] * ux - T[c] * uy) / (double)l);
+          rc[c][1] = (float)((double)(S[c] * uy + T[c] * ux) / (double)l);
+        }
+      }
+      // getPointsInPcFrame (:75-95)
+      if (tid == 0) {
+        for (int c = 0; c < 4; ++c) {
+          const float rOffsetX = rc[c][0] - (float)offsetInitX, rOffsetY = rc[c][1] - (float)offsetInitY;
+          const float rX = rOffsetX, rY = P.pic_scale * P.roi - rOffsetY;
+          const float rmX = rX / P.pic_scale, rmY = rY / P.pic_scale;
+          s_pc[c][0] = rmX - P.roi / 2; s_pc[c][1] = rmY - P.roi / 2;
+        }
+      }
+      __syncthreads();
+    }
+    for (int c = 0; c < 4; ++c) { pc[c][0] = s_pc[c][0]; pc[c][1] = s_pc[c][1]; }
+    const bool ok = rule_filter(pc, maxZ, n, P);
+    if (tid == 0) {
+      cl_ok[k] = ok ? 1 : 0;
+      if (ok) {
+        float* b = cl_box + (size_t)k * 24;
+        for (int h = 0; h < 2; ++h)
+          for (int c = 0; c < 4; ++c) { b[(h * 4 + c) * 3] = pc[c][0]; b[(h * 4 + c) * 3 + 1] = pc[c][1]; b[(h * 4 + c) * 3 + 2] = h == 0 ? -P.sensor_height : maxZ; }
+        float* mk = cl_marker + (size_t)k * 6;      // mark_cluster (:161-209); zero extents become 0.1
+        mk[0] = (float)(sx / n); mk[1] = (float)(sy / n); mk[2] = (float)(sz / n);
+        float ex = mxx - mnx, ey = mxy - mny, ez = mxz - mnz;
+        mk[3] = ex == 0.f ? 0.1f : ex; mk[4] = ey == 0.f ? 0.1f : ey; mk[5] = ez == 0.f ? 0.1f : ez;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- the last CTA compacts the accepted boxes in cluster-id order
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_flag = (atomicAdd(done, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+  int carry = 0;
+  for (int k0 = 1; k0 <= K; k0 += kFitThreads) {
+    const int k = k0 + tid;
+    const int f = (k <= K) ? __ldcg((const unsigned char*)&cl_ok[k]) : 0;
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, f);
+    if ((tid & 31) == 0) s_redi[tid >> 5] = __popc(bal);
+    __syncthreads();
+    int wbase = 0, tot = 0;
+    for (int w = 0; w < kFitThreads / 32; ++w) { if (w < (tid >> 5)) wbase += s_redi[w]; tot += s_redi[w]; }
+    const int pos = carry + wbase + __popc(bal & ((1u << (tid & 31)) - 1u));
+    if (f) {
+      if (pos < max_boxes) {
+        for (int e = 0; e < 24; ++e) boxes[(size_t)pos * 24 + e] = __ldcg(&cl_box[(size_t)k * 24 + e]);
+        for (int e = 0; e < 6; ++e) markers[(size_t)pos * 6 + e] = __ldcg(&cl_marker[(size_t)k * 6 + e]);
+      }
+    }
+    carry += tot;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (carry > max_boxes) { counters[CNT_ERROR] = LMOT_ERR_CAPACITY; carry = max_boxes; }
+    counters[CNT_N_BOXES] = carry;
+  }
+}
+
+}  // namespace
+
+int boxfit_alloc(Ctx* c) {
+  const size_t np = (size_t)c->max_points;
+  const int K1 = c->prm.max_clusters + 1;
+  c->max_sort_tiles = (c->max_points + kTile - 1) / kTile;
+  LMOT_CUDA(c, cudaMalloc(&c->d_pcid, np * sizeof(uint16_t)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_table, (size_t)c->max_sort_tiles * K1 * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_seg_start, K1 * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_seg_size, K1 * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_sorted_idx, np * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_cl_box, (size_t)K1 * 24 * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_cl_marker, (size_t)K1 * 6 * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_cl_ok, K1));
+  LMOT_CUDA(c, cudaMalloc(&c->d_boxes, (size_t)c->prm.max_boxes * 24 * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_markers, (size_t)c->prm.max_boxes * 6 * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_done, sizeof(int)));
+  LMOT_CUDA(c, cudaMemsetAsync(c->d_done, 0, sizeof(int), c->stream));
+  // raw mt19937_64(0) stream (box_fitting.cpp:303 re-seeds per cluster, so every cluster sees the same draws)
+  constexpr int kRaw = 256;
+  std::mt19937_64 mt(0);
+  unsigned long long raw[kRaw];
+  for (int i = 0; i < kRaw; ++i) raw[i] = mt();
+  c->n_mt_raw = kRaw;
+  LMOT_CUDA(c, cudaMalloc(&c->d_mt_raw, sizeof(raw)));
+  LMOT_CUDA(c, cudaMemcpyAsync(c->d_mt_raw, raw, sizeof(raw), cudaMemcpyHostToDevice, c->stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LMOT_OK;
+}
+
+void boxfit_free(Ctx* c) {
+  cudaFree(c->d_pcid); cudaFree(c->d_table); cudaFree(c->d_seg_start); cudaFree(c->d_seg_size); cudaFree(c->d_sorted_idx);
+  cudaFree(c->d_cl_box); cudaFree(c->d_cl_marker); cudaFree(c->d_cl_ok); cudaFree(c->d_boxes); cudaFree(c->d_markers);
+  cudaFree(c->d_done); cudaFree(c->d_mt_raw);
+}
+
+// inputs: c->d_elev / CNT_N_ELEV, c->d_cart (from clustering), c->d_label_grid / CNT_NUM_CLUSTER
+int boxfit_launch(Ctx* c, int n_upper) {
+  const int K1 = c->prm.max_clusters + 1;
+  const int tiles = (n_upper + kTile - 1) / kTile;
+  const size_t sh = (size_t)K1 * sizeof(int);
+  if (tiles > 0)
+    tile_hist_kernel<<<tiles, kTile, sh, c->stream>>>(c->d_cart, c->d_label_grid, c->d_counters, c->d_pcid, c->d_table,
+                                                      c->prm.max_clusters);
+  seg_offsets_kernel<<<1, 1024, 0, c->stream>>>(c->d_table, c->d_counters, c->d_seg_start, c->d_seg_size,
+                                                c->prm.max_clusters, c->d_done);
+  if (tiles > 0)
+    scatter_kernel<<<tiles, kTile, sh, c->stream>>>(c->d_pcid, c->d_counters, c->d_table, c->d_seg_start, c->d_sorted_idx,
+                                                    c->prm.max_clusters);
+  BoxParams P;
+  const lmot_params& p = c->prm;
+  P.roi = p.roi_m;
+  { volatile float ps = 900 / p.roi_m; P.pic_scale = ps; }   // float picScale = 900/roiM (box_fitting.cpp:18)
+  P.sensor_height = p.sensor_height; P.ram_points = p.ram_points; P.l_slope_dist = p.l_slope_dist;
+  P.l_num_points = p.l_num_points; P.min_points = p.min_cluster_points; P.rule_mode = p.rule_filter;
+  P.t_height_min = p.t_height_min; P.t_height_max = p.t_height_max; P.t_width_min = p.t_width_min; P.t_width_max = p.t_width_max;
+  P.t_len_min = p.t_len_min; P.t_len_max = p.t_len_max; P.t_area_max = p.t_area_max; P.t_ratio_min = p.t_ratio_min;
+  P.t_ratio_max = p.t_ratio_max; P.min_len_ratio = p.min_len_ratio; P.t_pt_per_m3 = p.t_pt_per_m3;
+  box_fit_kernel<<<c->fit_ctas, kFitThreads, 0, c->stream>>>(c->d_elev, c->d_sorted_idx, c->d_seg_start, c->d_seg_size,
+                                                             c->d_counters, P, c->d_mt_raw, c->n_mt_raw, c->prm.max_clusters,
+                                                             c->prm.max_boxes, c->d_cl_box, c->d_cl_marker, c->d_cl_ok,
+                                                             c->d_boxes, c->d_markers, c->d_done);
+  LMOT_CUDA(c, cudaGetLastError());
+  return LMOT_OK;
+}
+
+}  // namespace lmot

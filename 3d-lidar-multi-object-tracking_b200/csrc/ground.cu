@@ -273,6 +273,7 @@ int ground_alloc(Ctx* c) {
   LMOT_CUDA(c, cudaMalloc(&c->d_counters, CNT_COUNT * sizeof(int)));
   LMOT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, CNT_COUNT * sizeof(int), c->stream));
   LMOT_CUDA(c, cudaHostAlloc(&c->h_counters, CNT_COUNT * sizeof(int), cudaHostAllocDefault));
+  LMOT_CUDA(c, cudaHostAlloc(&c->h_set, CNT_COUNT * sizeof(int), cudaHostAllocDefault));
   init_keys_kernel<<<(kPolarCells + 255) / 256, 256, 0, c->stream>>>(c->d_polar_key);
   LMOT_CUDA(c, cudaGetLastError());
   LMOT_CUDA(c, cudaFuncSetAttribute(polar_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -285,10 +286,11 @@ void ground_free(Ctx* c) {
   cudaFree(c->d_height); cudaFree(c->d_smoothed); cudaFree(c->d_hdiff); cudaFree(c->d_hg); cudaFree(c->d_labels);
   cudaFree(c->d_elev); cudaFree(c->d_ground); cudaFree(c->d_tile_desc); cudaFree(c->d_counters);
   if (c->h_counters) cudaFreeHost(c->h_counters);
+  if (c->h_set) cudaFreeHost(c->h_set);
 }
 
-int ground_repack(Ctx* c, const float* d_in, int n, int stride) {
-  if (n > 0) repack_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_in, n, stride, c->d_points);
+int ground_repack(Ctx* c, const float* d_in, int n, int stride, float4* d_out) {
+  if (n > 0) repack_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_in, n, stride, d_out);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }

@@ -60,6 +60,30 @@ struct Ctx {
   unsigned long long* d_tile_desc = nullptr;  // decoupled look-back descriptors
   int* d_counters = nullptr;           // [CNT_COUNT]
   int* h_counters = nullptr;           // pinned mirror
+  int* h_set = nullptr;                // pinned staging for host-written counters
+
+  // ---- clustering
+  uint16_t* d_cart = nullptr;          // per elevated point cartesian cell (x*250+y) or kNoCell
+  int* d_count = nullptr;              // [62500] points per cell (zeroed by the CCL kernel after use)
+  uint8_t* d_seed = nullptr;           // [62500] count > 1
+  int* d_parent = nullptr;             // [62500] union-find parent, -1 = empty
+  int* d_rid = nullptr;                // [62500] cluster id at root cells
+  int* d_label_grid = nullptr;         // [62500] final labels (0 = empty), x-major
+
+  // ---- box fitting
+  int max_sort_tiles = 0, fit_ctas = 296, n_mt_raw = 0;
+  uint16_t* d_pcid = nullptr;          // per elevated point cluster id (0 = none)
+  int* d_table = nullptr;              // [tiles][max_clusters+1] tile histograms -> exclusive tile offsets
+  int* d_seg_start = nullptr;          // [max_clusters+1] first slot of each cluster in d_sorted_idx
+  int* d_seg_size = nullptr;           // [max_clusters+1] points per cluster
+  int* d_sorted_idx = nullptr;         // elevated-point indices grouped by cluster, cloud order inside a cluster
+  float* d_cl_box = nullptr;           // [max_clusters+1][24] per-cluster box (valid where d_cl_ok)
+  float* d_cl_marker = nullptr;        // [max_clusters+1][6]
+  uint8_t* d_cl_ok = nullptr;          // [max_clusters+1] rule filter verdict
+  float* d_boxes = nullptr;            // [max_boxes][8][3] accepted boxes, cluster-id order
+  float* d_markers = nullptr;          // [max_boxes][6]
+  int* d_done = nullptr;               // last-CTA-done counter
+  unsigned long long* d_mt_raw = nullptr;  // raw mt19937_64(0) outputs
 
   // ---- timing
   bool timing = false;
@@ -82,6 +106,13 @@ int ground_alloc(Ctx* c);
 void ground_free(Ctx* c);
 // pts: device float4 array of n points
 int ground_launch(Ctx* c, const float4* pts, int n);
-int ground_repack(Ctx* c, const float* d_in, int n, int stride);
+int ground_repack(Ctx* c, const float* d_in, int n, int stride, float4* d_out);
+int cluster_alloc(Ctx* c);
+void cluster_free(Ctx* c);
+int cluster_launch(Ctx* c, int n_upper);
+int cluster_cells_only(Ctx* c, int n_upper);  // d_cart for an elevated cloud whose label grid comes from the caller
+int boxfit_alloc(Ctx* c);
+void boxfit_free(Ctx* c);
+int boxfit_launch(Ctx* c, int n_upper);
 
 }  // namespace lmot
