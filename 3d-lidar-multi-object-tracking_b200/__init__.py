@@ -188,6 +188,102 @@ class Lmot:
                                         max_boxes, C.byref(nb), _fp(markers)))
         return boxes[: nb.value].copy(), markers[: nb.value].copy()
 
+    # ---- getOriginPoints + immUkfJpdaf -------------------------------------------------------------------
+    def _track_out(self, cap):
+        bufs = dict(targets=np.zeros((cap, 3), np.float32), vandyaw=np.zeros((cap, 2), np.float64),
+                    track_manage=np.zeros(cap, np.int32), is_static=np.zeros(cap, np.uint8), is_vis=np.zeros(cap, np.uint8),
+                    vis_bb=np.zeros((cap, 8, 3), np.float32))
+        to = TrackOut()
+        to.cap = cap
+        to.targets = _fp(bufs["targets"]); to.vandyaw = bufs["vandyaw"].ctypes.data_as(C.POINTER(C.c_double))
+        to.track_manage = bufs["track_manage"].ctypes.data_as(C.POINTER(C.c_int32))
+        to.is_static = bufs["is_static"].ctypes.data_as(C.POINTER(C.c_uint8))
+        to.is_vis = bufs["is_vis"].ctypes.data_as(C.POINTER(C.c_uint8)); to.vis_bb = _fp(bufs["vis_bb"])
+        return to, bufs
+
+    @staticmethod
+    def _track_result(to, bufs):
+        t, v = to.n_tracks, to.n_vis
+        return dict(targets=bufs["targets"][:t].copy(), vandyaw=bufs["vandyaw"][:t].copy(),
+                    track_manage=bufs["track_manage"][:t].copy(), is_static=bufs["is_static"][:t].copy(),
+                    is_vis=bufs["is_vis"][:t].copy(), vis_bb=bufs["vis_bb"][:v].copy())
+
+    def track_step(self, boxes, timestamp_us, v_gps=0.0, yaw_gps=0.0, cap: int | None = None):
+        b = np.ascontiguousarray(boxes, np.float32).reshape(-1, 8, 3)
+        m = b.shape[0]
+        if m == 0:
+            b = np.zeros((1, 8, 3), np.float32)
+        cap = cap or self.params.max_tracks
+        to, bufs = self._track_out(cap)
+        self._chk(self.lib.lmot_track_step(self.h, _fp(b), m, C.c_double(timestamp_us), C.c_double(v_gps), C.c_double(yaw_gps), C.byref(to)))
+        return self._track_result(to, bufs)
+
+    def frame(self, points, timestamp_us, v_gps=0.0, yaw_gps=0.0, cap: int | None = None):
+        """The whole hot path on one host frame -> dict(n_elevated, n_ground, num_cluster, boxes, tracks...)."""
+        p, n, s = _pts(points)
+        cap = cap or self.params.max_tracks
+        fo = FrameOut()
+        boxes = np.zeros((self.params.max_boxes, 8, 3), np.float32)
+        fo.boxes = _fp(boxes); fo.max_boxes = self.params.max_boxes
+        to, bufs = self._track_out(cap)
+        fo.tracks = to
+        self._chk(self.lib.lmot_frame(self.h, _fp(p), n, s, C.c_double(timestamp_us), C.c_double(v_gps), C.c_double(yaw_gps), C.byref(fo)))
+        r = self._track_result(fo.tracks, bufs)
+        r.update(n_elevated=fo.n_elevated, n_ground=fo.n_ground, num_cluster=fo.num_cluster, boxes=boxes[: fo.n_boxes].copy())
+        return r
+
+    def frame_dev(self, d_ptr: int, n: int, timestamp_us, v_gps=0.0, yaw_gps=0.0):
+        """Asynchronous: device-resident XYZI frame (stride 4) through all four stages on the context's stream."""
+        self._chk(self.lib.lmot_frame_dev(self.h, C.c_void_p(d_ptr), n, C.c_double(timestamp_us), C.c_double(v_gps), C.c_double(yaw_gps)))
+
+    def detect_dev(self, d_ptr: int, n: int):
+        self._chk(self.lib.lmot_detect_dev(self.h, C.c_void_p(d_ptr), n))
+
+    def frame_fetch(self, cap: int | None = None, want_boxes: bool = True):
+        cap = cap or self.params.max_tracks
+        fo = FrameOut()
+        boxes = np.zeros((self.params.max_boxes, 8, 3), np.float32)
+        if want_boxes:
+            fo.boxes = _fp(boxes)
+        fo.max_boxes = self.params.max_boxes
+        to, bufs = self._track_out(cap)
+        fo.tracks = to
+        self._chk(self.lib.lmot_frame_fetch(self.h, C.byref(fo)))
+        r = self._track_result(fo.tracks, bufs)
+        r.update(n_elevated=fo.n_elevated, n_ground=fo.n_ground, num_cluster=fo.num_cluster, boxes=boxes[: fo.n_boxes].copy())
+        return r
+
+    def tracker_reset(self):
+        self._chk(self.lib.lmot_tracker_reset(self.h))
+
+    def tracker_num_tracks(self) -> int:
+        n = C.c_int(0)
+        self._chk(self.lib.lmot_tracker_num_tracks(self.h, C.byref(n)))
+        return n.value
+
+    def tracker_dump(self) -> np.ndarray:
+        t = self.tracker_num_tracks()
+        out = np.zeros((max(t, 1), TRACK_DUMP_DOUBLES), np.float64)
+        n = C.c_int(0)
+        self._chk(self.lib.lmot_tracker_dump(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), max(t, 1), C.byref(n)))
+        return out[: n.value]
+
+    def tracker_load(self, dumps, init, timestamp_us, ego_velo=0.0, ego_yaw=0.0, ego_pre_yaw=0.0, ego_point_yaw=-np.pi / 2):
+        d = np.ascontiguousarray(dumps, np.float64).reshape(-1, TRACK_DUMP_DOUBLES)
+        n = d.shape[0]
+        if n == 0:
+            d = np.zeros((1, TRACK_DUMP_DOUBLES), np.float64)
+        self._chk(self.lib.lmot_tracker_load(self.h, d.ctypes.data_as(C.POINTER(C.c_double)), n, int(init), C.c_double(timestamp_us),
+                                             C.c_double(ego_velo), C.c_double(ego_yaw), C.c_double(ego_pre_yaw), C.c_double(ego_point_yaw)))
+
+    def enable_timing(self, on: bool = True):
+        self._chk(self.lib.lmot_enable_timing(self.h, int(on)))
+
+    def last_stage_ms(self):
+        ms = (C.c_float * 4)()
+        self._chk(self.lib.lmot_last_stage_ms(self.h, ms))
+        return [float(x) for x in ms]
+
     def debug_label_grid(self):
         grid = np.zeros(250 * 250, np.int32)
         nc = C.c_int(0)

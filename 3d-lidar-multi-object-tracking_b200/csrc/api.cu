@@ -135,6 +135,7 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   int rc = ground_alloc(c);
   if (rc == LMOT_OK) rc = cluster_alloc(c);
   if (rc == LMOT_OK) rc = boxfit_alloc(c);
+  if (rc == LMOT_OK) rc = tracker_alloc(c);
   if (rc == LMOT_OK) rc = (cudaStreamSynchronize(c->stream) == cudaSuccess) ? LMOT_OK : LMOT_ERR_CUDA;
   if (rc != LMOT_OK) { lmot_destroy(h); return rc; }
   for (int i = 0; i < 5; ++i) cudaEventCreate(&c->ev[i]);
@@ -150,6 +151,7 @@ void lmot_destroy(lmot_ctx* ctx) {
   ground_free(c);
   cluster_free(c);
   boxfit_free(c);
+  tracker_free(c);
   for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete ctx;
@@ -256,6 +258,167 @@ int lmot_detect_dev(lmot_ctx* ctx, const float* d_points, int n) {
   if (rc) return rc;
   if ((rc = cluster_launch(c, n))) return rc;
   return boxfit_launch(c, n);
+}
+
+// ---------------------------------------------------------------------------------------------- tracker
+static int fetch_track_outputs(Ctx* c, lmot_track_out* out) {
+  // h_counters already holds this frame's counters
+  const int T = c->h_counters[CNT_N_TRACKS], nv = c->h_counters[CNT_N_VIS];
+  if (!out) return LMOT_OK;
+  out->n_tracks = T; out->n_vis = nv;
+  const int n = T < out->cap ? T : out->cap;
+  const int nvc = nv < out->cap ? nv : out->cap;
+  if (n > 0) {
+    if (out->targets) LMOT_CUDA(c, cudaMemcpyAsync(out->targets, c->d_out_targets, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (out->vandyaw) LMOT_CUDA(c, cudaMemcpyAsync(out->vandyaw, c->d_out_vandyaw, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (out->track_manage) LMOT_CUDA(c, cudaMemcpyAsync(out->track_manage, c->d_out_manage, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (out->is_static) LMOT_CUDA(c, cudaMemcpyAsync(out->is_static, c->d_out_static, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (out->is_vis) LMOT_CUDA(c, cudaMemcpyAsync(out->is_vis, c->d_out_vis, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (nvc > 0 && out->vis_bb) LMOT_CUDA(c, cudaMemcpyAsync(out->vis_bb, c->d_out_visbb, (size_t)nvc * 24 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return (T > out->cap) ? LMOT_ERR_CAPACITY : LMOT_OK;
+}
+
+int lmot_track_step(lmot_ctx* ctx, const float* boxes, int m, double timestamp_us, double v_gps, double yaw_gps,
+                    lmot_track_out* out) {
+  if (!ctx || m < 0 || (m > 0 && !boxes)) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  if (m > c->prm.max_boxes) return LMOT_ERR_CAPACITY;
+  if (m > 0) LMOT_CUDA(c, cudaMemcpyAsync(c->d_boxes_in, boxes, (size_t)m * 24 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  int rc = set_counter(c, CNT_N_BOXES, m);
+  if (rc) return rc;
+  if ((rc = tracker_launch(c, c->d_boxes_in, timestamp_us, v_gps, yaw_gps))) return rc;
+  if ((rc = fetch_counters(c))) return rc;
+  if ((rc = check_device_error(c))) return rc;
+  return fetch_track_outputs(c, out);
+}
+
+int lmot_frame_dev(lmot_ctx* ctx, const float* d_points, int n, double timestamp_us, double v_gps, double yaw_gps) {
+  if (!ctx || n < 0 || (n > 0 && !d_points)) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  if (n > c->max_points) return LMOT_ERR_CAPACITY;
+  int rc;
+  if (c->timing) cudaEventRecord(c->ev[0], c->stream);
+  if ((rc = ground_launch(c, reinterpret_cast<const float4*>(d_points), n))) return rc;
+  if (c->timing) cudaEventRecord(c->ev[1], c->stream);
+  if ((rc = cluster_launch(c, n))) return rc;
+  if (c->timing) cudaEventRecord(c->ev[2], c->stream);
+  if ((rc = boxfit_launch(c, n))) return rc;
+  if (c->timing) cudaEventRecord(c->ev[3], c->stream);
+  if ((rc = tracker_launch(c, c->d_boxes, timestamp_us, v_gps, yaw_gps))) return rc;
+  if (c->timing) cudaEventRecord(c->ev[4], c->stream);
+  return LMOT_OK;
+}
+
+int lmot_frame_fetch(lmot_ctx* ctx, lmot_frame_out* out) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  int rc = fetch_counters(c);
+  if (rc) return rc;
+  if (c->timing) for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
+  if ((rc = check_device_error(c))) return rc;
+  if (!out) return LMOT_OK;
+  out->n_elevated = c->h_counters[CNT_N_ELEV]; out->n_ground = c->h_counters[CNT_N_GROUND];
+  out->num_cluster = c->h_counters[CNT_NUM_CLUSTER]; out->n_boxes = c->h_counters[CNT_N_BOXES];
+  const int nb = out->n_boxes < out->max_boxes ? out->n_boxes : out->max_boxes;
+  if (out->boxes && nb > 0) LMOT_CUDA(c, cudaMemcpyAsync(out->boxes, c->d_boxes, (size_t)nb * 24 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  return fetch_track_outputs(c, &out->tracks);
+}
+
+int lmot_frame(lmot_ctx* ctx, const float* points, int n, int stride, double timestamp_us, double v_gps, double yaw_gps,
+               lmot_frame_out* out) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  int rc = upload_points(c, points, n, stride, c->d_points);
+  if (rc) return rc;
+  if ((rc = lmot_frame_dev(ctx, reinterpret_cast<const float*>(c->d_points), n, timestamp_us, v_gps, yaw_gps))) return rc;
+  return lmot_frame_fetch(ctx, out);
+}
+
+int lmot_tracker_reset(lmot_ctx* ctx) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  c->th = TrackerHost();
+  return set_counter(c, CNT_N_TRACKS, 0);
+}
+
+int lmot_tracker_num_tracks(lmot_ctx* ctx, int* n) {
+  if (!ctx || !n) return LMOT_ERR_INVALID;
+  int rc = fetch_counters(&ctx->c);
+  if (rc) return rc;
+  *n = ctx->c.h_counters[CNT_N_TRACKS];
+  return LMOT_OK;
+}
+
+// flat per-track dump, layout shared with oracle/ref_harness.cpp (documented in DESIGN.md)
+enum { D_TRACKNUM = 0, D_LIFETIME = 1, D_STATIC = 2, D_VIS = 3, D_X = 4, D_P = 24, D_MODE = 124, D_ZPRED = 127, D_S = 133,
+       D_K = 145, D_BESTYAW = 175, D_BBYAW = 176, D_BBAREA = 177, D_DISTINIT = 178, D_XMERGEYAW = 179, D_INITMEAS = 180,
+       D_VELON = 182, D_VELO = 183, D_BBN = 186, D_BB = 187, D_BESTBBN = 211, D_BESTBB = 212, D_TOTAL = LMOT_TRACK_DUMP_DOUBLES };
+
+int lmot_tracker_dump(lmot_ctx* ctx, double* dumps, int cap, int* n_out) {
+  if (!ctx || cap < 0) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  int rc = fetch_counters(c);
+  if (rc) return rc;
+  const int T = c->h_counters[CNT_N_TRACKS];
+  if (n_out) *n_out = T;
+  const int n = T < cap ? T : cap;
+  if (n == 0 || !dumps) return LMOT_OK;
+  std::vector<TrackState> h((size_t)n);
+  LMOT_CUDA(c, cudaMemcpyAsync(h.data(), c->d_tracks, (size_t)n * sizeof(TrackState), cudaMemcpyDeviceToHost, c->stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < n; ++i) {
+    const TrackState& t = h[i];
+    double* d = dumps + (size_t)i * D_TOTAL;
+    memset(d, 0, sizeof(double) * D_TOTAL);
+    d[D_TRACKNUM] = t.trackNum; d[D_LIFETIME] = t.lifetime; d[D_STATIC] = t.isStatic; d[D_VIS] = t.isVisBB;
+    for (int m = 0; m < 4; ++m) { memcpy(d + D_X + 5 * m, t.x[m], 5 * sizeof(double)); memcpy(d + D_P + 25 * m, t.P[m], 25 * sizeof(double)); }
+    for (int m = 0; m < 3; ++m) {
+      d[D_MODE + m] = t.modeProb[m]; d[D_ZPRED + 2 * m] = t.zPred[m][0]; d[D_ZPRED + 2 * m + 1] = t.zPred[m][1];
+      memcpy(d + D_S + 4 * m, t.S[m], 4 * sizeof(double)); memcpy(d + D_K + 10 * m, t.K[m], 10 * sizeof(double));
+    }
+    d[D_BESTYAW] = t.bestYaw; d[D_DISTINIT] = t.distFromInit; d[D_XMERGEYAW] = t.x_merge_yaw;
+    d[D_INITMEAS] = t.initMeas[0]; d[D_INITMEAS + 1] = t.initMeas[1];
+    d[D_VELON] = t.nVelo; for (int k = 0; k < t.nVelo && k < 3; ++k) d[D_VELO + k] = t.velo[k];
+    d[D_BBN] = t.nBBox; for (int p = 0; p < t.nBBox && p < 8; ++p) for (int q = 0; q < 3; ++q) d[D_BB + 3 * p + q] = t.BBox[p][q];
+    d[D_BESTBBN] = t.nBest; for (int p = 0; p < t.nBest && p < 8; ++p) for (int q = 0; q < 3; ++q) d[D_BESTBB + 3 * p + q] = t.bestBBox[p][q];
+  }
+  return T > cap ? LMOT_ERR_CAPACITY : LMOT_OK;
+}
+
+int lmot_tracker_load(lmot_ctx* ctx, const double* dumps, int n, int init, double timestamp_us, double ego_velo,
+                      double ego_yaw, double ego_pre_yaw, double ego_point_yaw) {
+  if (!ctx || n < 0 || (n > 0 && !dumps)) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  if (n > c->prm.max_tracks) return LMOT_ERR_CAPACITY;
+  std::vector<TrackState> h((size_t)(n > 0 ? n : 1));
+  for (int i = 0; i < n; ++i) {
+    TrackState& t = h[i];
+    memset(&t, 0, sizeof(t));
+    const double* d = dumps + (size_t)i * D_TOTAL;
+    t.trackNum = (int)d[D_TRACKNUM]; t.lifetime = (int)d[D_LIFETIME]; t.isStatic = d[D_STATIC] != 0; t.isVisBB = d[D_VIS] != 0;
+    for (int m = 0; m < 4; ++m) { memcpy(t.x[m], d + D_X + 5 * m, 5 * sizeof(double)); memcpy(t.P[m], d + D_P + 25 * m, 25 * sizeof(double)); }
+    for (int m = 0; m < 3; ++m) {
+      t.modeProb[m] = d[D_MODE + m]; t.zPred[m][0] = d[D_ZPRED + 2 * m]; t.zPred[m][1] = d[D_ZPRED + 2 * m + 1];
+      memcpy(t.S[m], d + D_S + 4 * m, 4 * sizeof(double)); memcpy(t.K[m], d + D_K + 10 * m, 10 * sizeof(double));
+    }
+    t.bestYaw = d[D_BESTYAW]; t.distFromInit = d[D_DISTINIT]; t.x_merge_yaw = d[D_XMERGEYAW];
+    t.initMeas[0] = d[D_INITMEAS]; t.initMeas[1] = d[D_INITMEAS + 1];
+    t.nVelo = (int)d[D_VELON]; for (int k = 0; k < t.nVelo && k < 3; ++k) t.velo[k] = d[D_VELO + k];
+    t.nBBox = (int)d[D_BBN]; for (int p = 0; p < t.nBBox && p < 8; ++p) for (int q = 0; q < 3; ++q) t.BBox[p][q] = (float)d[D_BB + 3 * p + q];
+    t.nBest = (int)d[D_BESTBBN]; for (int p = 0; p < t.nBest && p < 8; ++p) for (int q = 0; q < 3; ++q) t.bestBBox[p][q] = (float)d[D_BESTBB + 3 * p + q];
+  }
+  if (n > 0) {
+    LMOT_CUDA(c, cudaMemcpyAsync(c->d_tracks, h.data(), (size_t)n * sizeof(TrackState), cudaMemcpyHostToDevice, c->stream));
+    LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  c->th = TrackerHost();
+  c->th.init = init != 0; c->th.timestamp = timestamp_us; c->th.egoVelo = ego_velo; c->th.egoYaw = ego_yaw;
+  c->th.egoPreYaw = ego_pre_yaw; c->th.egoPoint[2] = ego_point_yaw;
+  return set_counter(c, CNT_N_TRACKS, n);
 }
 
 int lmot_debug_polar_grid(lmot_ctx* ctx, float* minz, float* height, float* smoothed, float* hdiff, float* hground,

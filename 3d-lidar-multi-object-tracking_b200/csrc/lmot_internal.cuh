@@ -29,6 +29,32 @@ struct GroundParams {
   double tap[3];         // gaussKernel(3, 1.0) computed on the host with the host libm (gaus_blur.cpp:26-49)
 };
 
+// one track == one UKF object of the reference (ukf.h:15-263) + its trackNumVec_ entry; x/P index 0 = merge,
+// 1 = cv, 2 = ctrv, 3 = rm.  Xsig_pred_* is transient (recomputed by every Prediction) and not stored.
+struct TrackState {
+  double x[4][5];
+  double P[4][25];
+  double modeProb[3];
+  double zPred[3][2];
+  double S[3][4];
+  double K[3][10];
+  double bestYaw, distFromInit, x_merge_yaw;
+  double initMeas[2];
+  double velo[3];
+  float BBox[8][3];
+  float bestBBox[8][3];
+  int trackNum, lifetime, nVelo, nBBox, nBest;
+  uint8_t isStatic, isVisBB;
+};
+
+// frame-level scalars of imm_ukf_jpda.cpp:19-24,56-58 (host side: a handful of doubles per frame)
+struct TrackerHost {
+  bool init = false;
+  double timestamp = 0, egoVelo = 0, egoYaw = 0, egoPreYaw = 0;
+  double egoPoint[3] = {0, 0, 0};
+  double fold[3] = {0, 0, -1.5707963267948966};
+};
+
 struct Ctx {
   lmot_params prm;
   int device = 0;
@@ -85,6 +111,19 @@ struct Ctx {
   int* d_done = nullptr;               // last-CTA-done counter
   unsigned long long* d_mt_raw = nullptr;  // raw mt19937_64(0) outputs
 
+  // ---- tracker
+  TrackerHost th;
+  int trk_ctas = 592, gate_words = 0;
+  TrackState* d_tracks = nullptr;      // [max_tracks] append-only table; dead tracks keep their slot
+  unsigned* d_gate = nullptr;          // [max_tracks][gate_words] chi-square gate bits per (track, box)
+  unsigned* d_setter = nullptr;        // [max_tracks][gate_words] boxes this track marks as matched
+  int* d_first_setter = nullptr;       // [max_boxes] lowest track index that matched the box (INT_MAX = unmatched)
+  uint8_t* d_skip = nullptr;           // [max_tracks] track did not reach measurementValidation this frame
+  int* d_new_num = nullptr;            // [max_tracks] staged mergeOverSegmentation writes
+  float* d_boxes_in = nullptr;         // staging for lmot_track_step's host boxes
+  float* d_out_targets = nullptr; double* d_out_vandyaw = nullptr; int* d_out_manage = nullptr;
+  uint8_t* d_out_static = nullptr; uint8_t* d_out_vis = nullptr; float* d_out_visbb = nullptr;
+
   // ---- timing
   bool timing = false;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -114,5 +153,8 @@ int cluster_cells_only(Ctx* c, int n_upper);  // d_cart for an elevated cloud wh
 int boxfit_alloc(Ctx* c);
 void boxfit_free(Ctx* c);
 int boxfit_launch(Ctx* c, int n_upper);
+int tracker_alloc(Ctx* c);
+void tracker_free(Ctx* c);
+int tracker_launch(Ctx* c, const float* d_boxes, double timestamp, double v_gps, double yaw_gps);
 
 }  // namespace lmot

@@ -1,0 +1,916 @@
+// tracker.cu -- batched IMM-UKF-PDA tracker on sm_100a.
+//
+// Replaces immUkfJpdaf (/root/reference/object_tracking/tracking/imm_ukf_jpda.cpp:704-1112) and class UKF
+// (tracking/ukf.cpp).  The reference walks its tracks sequentially; the only cross-track couplings are
+//   (a) the shared matchingVec / lifetime_ bookkeeping of measurementValidation (:205-257),
+//   (b) mergeOverSegmentation (:666-700), a last-writer-wins double loop, and
+//   (c) append-order spawning of new tracks (:972-989),
+// all deterministic functions of per-(track, box) predicates, so tracks run in parallel:
+//
+//   TA imm_predict_gate_kernel  3 warps per track (one per motion model CV/CTRV/RM): explosion guards (:826-831),
+//                               IMM mixing + interaction (ukf.cpp:439-500), 7-dim augmented sigma points with Eigen's
+//                               early-exit Cholesky (lane = sigma point), model propagation, weighted mean /
+//                               covariance (lane = matrix element), lidar S / K (ukf.cpp:778-902); then the chi-square
+//                               gate of every box against the max-det(S) model (:843-869) -> gate / setter bit
+//                               rows and first_setter[box] = min track index (atomicMin).
+//   TB imm_update_kernel        1 warp per track: lifetime_, measurement list, box association (:416-463), updateBB
+//                               (:565-653), secondInit (:882-921), track-number machine (:924-944), PDA update with
+//                               association likelihoods (:259-394), IMM mode-probability update and merge
+//                               (ukf.cpp:384-437).
+//   TC1 merge_overseg_kernel    1 warp per track k over all tracks i: the last write of the reference's (i,j) loop.
+//   TC2 spawn_output_kernel     one CTA: spawn a UKF per unmatched box in box order, per-track outputs, static flag.
+//
+// All state is fp64 like the reference (Eigen::MatrixXd); this file is compiled with -fmad=false so that the
+// operation sequence matches the x86-64 build of the reference except for libm (sin/cos/exp/pow/atan2 <= 2 ulp).
+#include <cfloat>
+#include <climits>
+#include <vector>
+#include "lmot_internal.cuh"
+#include "exact_math.cuh"
+
+namespace lmot {
+
+namespace {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double gammaG = 9.22, pG = 0.99, pD = 0.9;   // imm_ukf_jpda.cpp:26-34
+constexpr int lifeTimeThres = 3;                        // :42
+constexpr double distanceThres = 99;                    // :38
+constexpr double bbYawChangeThres = 0.2;                // :46
+
+__device__ __forceinline__ double wrap_pi(double a) {   // the reference's while loops; NaN falls through
+  // (beyond 1e4 rad the reference's loop would need thousands of iterations -- millions for a diverged filter --
+  //  so the bulk is removed in one step there; such a track is already past any parity claim)
+  if (fabs(a) > 1.0e4) a -= 2. * kPi * rint(a / (2. * kPi));
+  while (a > kPi) a -= 2. * kPi;
+  while (a < -kPi) a += 2. * kPi;
+  return a;
+}
+
+// Eigen dynamic determinant() == partialPivLu().determinant() (first-max pivoting, product of the diagonal)
+template <int N>
+__device__ double det_lu(const double* A) {
+  double lu[N * N];
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) lu[i] = A[i];
+  int sign = 1;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    int piv = k; double big = fabs(lu[k * N + k]);
+#pragma unroll
+    for (int r = k + 1; r < N; ++r) { const double v = fabs(lu[r * N + k]); if (v > big) { big = v; piv = r; } }
+    if (big != 0.0) {
+      if (piv != k) {
+#pragma unroll
+        for (int r = k + 1; r < N; ++r)
+          if (r == piv) {
+#pragma unroll
+            for (int c = 0; c < N; ++c) { const double t = lu[k * N + c]; lu[k * N + c] = lu[r * N + c]; lu[r * N + c] = t; }
+          }
+        sign = -sign;
+      }
+#pragma unroll
+      for (int r = k + 1; r < N; ++r) lu[r * N + k] /= lu[k * N + k];
+    }
+#pragma unroll
+    for (int r = k + 1; r < N; ++r)
+#pragma unroll
+      for (int c = k + 1; c < N; ++c) lu[r * N + c] -= lu[r * N + k] * lu[k * N + c];
+  }
+  double p = lu[0];
+#pragma unroll
+  for (int k = 1; k < N; ++k) p *= lu[k * N + k];
+  return (double)sign * p;
+}
+
+__device__ __forceinline__ double det2(const double* S) { return det_lu<2>(S); }
+
+// Eigen dynamic inverse() of a 2x2 == partialPivLu().solve(Identity)
+__device__ void inv2_lu(const double* A, double* R) {
+  double a00 = A[0], a01 = A[1], a10 = A[2], a11 = A[3];
+  const bool sw = fabs(a10) > fabs(a00);
+  if (sw) { double t = a00; a00 = a10; a10 = t; t = a01; a01 = a11; a11 = t; }
+  const double l10 = a10 / a00;
+  const double u11 = a11 - l10 * a01;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    double b0 = (c == 0) ? 1.0 : 0.0, b1 = (c == 1) ? 1.0 : 0.0;
+    if (sw) { const double t = b0; b0 = b1; b1 = t; }
+    const double y1 = b1 - l10 * b0;
+    const double x1 = y1 / u11;
+    const double x0 = (b0 - a01 * x1) / a00;
+    R[c] = x0; R[2 + c] = x1;
+  }
+}
+
+// getCpFromBbox, imm_ukf_jpda.cpp:465-479: float arithmetic inside S1/S2, double afterwards
+__device__ __forceinline__ void cp_from_corners(float p1x, float p1y, float p2x, float p2y, float p3x, float p3y, float p4x,
+                                                float p4y, double& cx, double& cy) {
+  const double S1 = ((p4x - p2x) * (p1y - p2y) - (p4y - p2y) * (p1x - p2x)) / 2;
+  const double S2 = ((p4x - p2x) * (p2y - p3y) - (p4y - p2y) * (p2x - p3x)) / 2;
+  cx = p1x + (p3x - p1x) * S1 / (S1 + S2);
+  cy = p1y + (p3y - p1y) * S1 / (S1 + S2);
+}
+__device__ __forceinline__ void cp_from_box(const float* b, double& cx, double& cy) {   // b = 8x3 floats
+  cp_from_corners(b[0], b[1], b[3], b[4], b[6], b[7], b[9], b[10], cx, cy);
+}
+
+__device__ void ukf_initialize(TrackState& t, double zx, double zy) {   // UKF::UKF + Initialize, ukf.cpp:20-322
+  const double x0[5] = {zx, zy, 0, 0, 0.1};
+  const double d[5] = {0.5, 0.5, 3, 10, 1};
+  for (int m = 0; m < 4; ++m) {
+    for (int i = 0; i < 5; ++i) t.x[m][i] = x0[i];
+    for (int e = 0; e < 25; ++e) t.P[m][e] = 0;
+    for (int i = 0; i < 5; ++i) t.P[m][i * 5 + i] = d[i];
+  }
+  for (int m = 0; m < 3; ++m) {
+    t.modeProb[m] = 0.33;
+    t.zPred[m][0] = zx; t.zPred[m][1] = zy;
+    t.S[m][0] = 1; t.S[m][1] = 0; t.S[m][2] = 0; t.S[m][3] = 1;
+    for (int e = 0; e < 10; ++e) t.K[m][e] = 0;
+  }
+  t.bestYaw = 0; t.distFromInit = 0; t.x_merge_yaw = 0; t.initMeas[0] = 0; t.initMeas[1] = 0;
+  t.velo[0] = t.velo[1] = t.velo[2] = 0;
+  for (int p = 0; p < 8; ++p) for (int c = 0; c < 3; ++c) { t.BBox[p][c] = 0; t.bestBBox[p][c] = 0; }
+  t.trackNum = 1; t.lifetime = 0; t.nVelo = 0; t.nBBox = 0; t.nBest = 0; t.isStatic = 0; t.isVisBB = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ TA
+constexpr int kTAThreads = 96;
+
+struct TAShared {
+  double xp[3][5];       // pre-interaction states of the three models
+  double Pp[3][25];
+  double L[3][49];       // per model: partial Cholesky factor of P_aug
+  double Xs[3][15][5];   // per model: predicted sigma points
+  double Pm[3][25];      // per model: mixed covariance
+  double S[3][4], Tc[3][10], zp[3][2];
+  int flag;              // 0 run, 1 skip
+};
+
+__device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
+
+__global__ void __launch_bounds__(kTAThreads)
+imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__ counters, const float* __restrict__ boxes,
+                        double dt, unsigned* __restrict__ gate, unsigned* __restrict__ setter, int* __restrict__ first_setter,
+                        uint8_t* __restrict__ skip, int words) {
+  __shared__ TAShared sh;
+  const int tid = threadIdx.x, lane = tid & 31, model = tid >> 5;
+  const int T = counters[CNT_N_TRACKS];
+  const int M = counters[CNT_N_BOXES];
+  const double kStdA = (model == 2) ? 3.0 : 2.0;       // std_a_{cv,ctrv,rm}_ ukf.cpp:68-70 (= std_*_yawdd_ :71-73)
+  const double lambda_aug = 3 - 7;
+  const double w0 = lambda_aug / (lambda_aug + 7), wi = 0.5 / (7 + lambda_aug);
+
+  for (int it = blockIdx.x; it < T; it += gridDim.x) {
+    TrackState& t = tracks[it];
+    __syncthreads();
+    if (tid == 0) {
+      t.isVisBB = 0;                                          // :814
+      int flag = 0;
+      if (t.trackNum == 0) flag = 1;                          // :826
+      else if (det_lu<5>(t.P[0]) > 10 || t.P[0][24] > 1000) { t.trackNum = 0; flag = 1; }   // :828-831
+      sh.flag = flag;
+      skip[it] = (uint8_t)flag;
+    }
+    // stage the pre-interaction states
+    for (int e = tid; e < 15; e += kTAThreads) sh.xp[e / 5][e % 5] = t.x[1 + e / 5][e % 5];
+    for (int e = tid; e < 75; e += kTAThreads) sh.Pp[e / 25][e % 25] = t.P[1 + e / 25][e % 25];
+    const double mp0 = t.modeProb[0], mp1 = t.modeProb[1], mp2 = t.modeProb[2];
+    __syncthreads();
+    if (sh.flag) continue;
+
+    // ---- MixingProbability (ukf.cpp:439-455) for this warp's model column j = model
+    const double pj0 = (model == 0) ? 0.9 : 0.05, pj1 = (model == 1) ? 0.9 : 0.05, pj2 = (model == 2) ? 0.9 : 0.05;
+    const double sumProb = mp0 * pj0 + mp1 * pj1 + mp2 * pj2;
+    const double mu0 = mp0 * pj0 / sumProb, mu1 = mp1 * pj1 / sumProb, mu2 = mp2 * pj2 / sumProb;
+    // ---- Interaction (:458-500)
+    double x[5];
+#pragma unroll
+    for (int e = 0; e < 5; ++e) x[e] = mu0 * sh.xp[0][e] + mu1 * sh.xp[1][e] + mu2 * sh.xp[2][e];
+    x[3] = wrap_pi(sh.xp[model][3]);
+    if (lane < 25) {
+      const int r = lane / 5, c = lane % 5;
+      const double t0 = mu0 * (sh.Pp[0][lane] + (sh.xp[0][r] - x[r]) * (sh.xp[0][c] - x[c]));
+      const double t1 = mu1 * (sh.Pp[1][lane] + (sh.xp[1][r] - x[r]) * (sh.xp[1][c] - x[c]));
+      const double t2 = mu2 * (sh.Pp[2][lane] + (sh.xp[2][r] - x[r]) * (sh.xp[2][c] - x[c]));
+      sh.Pm[model][lane] = t0 + t1 + t2;
+    }
+    __syncwarp();
+    // ---- Prediction (:630-772): P_aug.llt() with Eigen's early exit on a non-positive pivot (LLT.h:271-295)
+    if (lane == 0) {
+      double* L = sh.L[model];
+#pragma unroll 1
+      for (int e = 0; e < 49; ++e) L[e] = 0.0;
+      for (int r = 0; r < 5; ++r) for (int c = 0; c <= r; ++c) L[r * 7 + c] = sh.Pm[model][r * 5 + c];
+      L[5 * 7 + 5] = kStdA * kStdA;
+      L[6 * 7 + 6] = kStdA * kStdA;
+      for (int k = 0; k < 7; ++k) {
+        double xk = L[k * 7 + k];
+        if (k > 0) { double s = L[k * 7] * L[k * 7]; for (int j = 1; j < k; ++j) s += L[k * 7 + j] * L[k * 7 + j]; xk -= s; }
+        if (xk <= 0.0) break;
+        xk = sqrt(xk);
+        L[k * 7 + k] = xk;
+        for (int r = k + 1; r < 7; ++r) {
+          double acc = L[r * 7 + k];
+          for (int j = 0; j < k; ++j) acc -= L[r * 7 + j] * L[k * 7 + j];
+          L[r * 7 + k] = acc / xk;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane < 15) {      // one sigma point per lane (:682-735)
+      const double sq = sqrt(lambda_aug + 7);
+      double a[7];
+#pragma unroll
+      for (int e = 0; e < 5; ++e) a[e] = x[e];
+      a[5] = 0; a[6] = 0;
+      if (lane >= 1) {
+        const int col = (lane - 1) % 7;
+        const double* L = sh.L[model];
+#pragma unroll
+        for (int e = 0; e < 7; ++e) a[e] = (lane <= 7) ? a[e] + sq * L[e * 7 + col] : a[e] - sq * L[e * 7 + col];
+      }
+      const double p_x = a[0], p_y = a[1], v = a[2], yaw = a[3], yawd = a[4], nu_a = a[5], nu_yawdd = a[6];
+      double s0, s1, s2, s3, s4;
+      if (model == 2) { s0 = p_x; s1 = p_y; s2 = v; s3 = yaw; s4 = yawd; }      // randomMotion :589-606
+      else {
+        double px_p, py_p, yaw_p;
+        if (model == 0) {                                                         // Cv :564-588
+          px_p = p_x + v * cos(yaw) * dt;
+          py_p = p_y + v * sin(yaw) * dt;
+          yaw_p = yaw;
+        } else {                                                                  // Ctrv :539-563
+          if (fabs(yawd) > 0.001) {
+            px_p = p_x + v / yawd * (sin(yaw + yawd * dt) - sin(yaw));
+            py_p = p_y + v / yawd * (cos(yaw) - cos(yaw + yawd * dt));
+          } else {
+            px_p = p_x + v * dt * cos(yaw);
+            py_p = p_y + v * dt * sin(yaw);
+          }
+          yaw_p = yaw + yawd * dt;
+        }
+        double v_p = v, yawd_p = yawd;
+        px_p = px_p + 0.5 * nu_a * dt * dt * cos(yaw);
+        py_p = py_p + 0.5 * nu_a * dt * dt * sin(yaw);
+        v_p = v_p + nu_a * dt;
+        yaw_p = yaw_p + 0.5 * nu_yawdd * dt * dt;
+        yawd_p = yawd_p + nu_yawdd * dt;
+        s0 = px_p; s1 = py_p; s2 = v_p; s3 = yaw_p; s4 = yawd_p;
+      }
+      double* o = sh.Xs[model][lane];
+      o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3; o[4] = s4;
+    }
+    __syncwarp();
+    // predicted mean (:737-744), every lane sums in sigma-point order
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+      double acc = 0.0;
+      for (int i = 0; i < 15; ++i) acc = acc + ((i == 0) ? w0 : wi) * sh.Xs[model][i][e];
+      x[e] = acc;
+    }
+    x[3] = wrap_pi(x[3]);
+    double Pe = 0.0;      // predicted covariance element (:746-755)
+    if (lane < 25) {
+      const int r = lane / 5, c = lane % 5;
+      for (int i = 0; i < 15; ++i) {
+        double dr = sh.Xs[model][i][r] - x[r], dc = sh.Xs[model][i][c] - x[c];
+        if (r == 3) dr = wrap_pi(dr);
+        if (c == 3) dc = wrap_pi(dc);
+        Pe = Pe + (((i == 0) ? w0 : wi) * dr) * dc;
+      }
+    }
+    // ---- UpdateLidar (:778-902)
+    double zp0 = 0.0, zp1 = 0.0;
+    for (int i = 0; i < 15; ++i) { const double w = (i == 0) ? w0 : wi; zp0 = zp0 + w * sh.Xs[model][i][0]; zp1 = zp1 + w * sh.Xs[model][i][1]; }
+    if (lane < 4) {
+      const int r = lane >> 1, c = lane & 1;
+      double acc = 0.0;
+      for (int i = 0; i < 15; ++i) {
+        const double dzr = sh.Xs[model][i][r] - (r ? zp1 : zp0), dzc = sh.Xs[model][i][c] - (c ? zp1 : zp0);
+        acc = acc + (((i == 0) ? w0 : wi) * dzr) * dzc;
+      }
+      const double R = (r == c) ? 0.15 * 0.15 : 0.0;
+      sh.S[model][lane] = acc + R;
+    } else if (lane < 14) {
+      const int e = lane - 4, r = e >> 1, c = e & 1;
+      double acc = 0.0;
+      for (int i = 0; i < 15; ++i) {
+        const double xd = sh.Xs[model][i][r] - x[r], dz = sh.Xs[model][i][c] - (c ? zp1 : zp0);
+        acc = acc + (((i == 0) ? w0 : wi) * xd) * dz;
+      }
+      sh.Tc[model][e] = acc;
+    }
+    __syncwarp();
+    double Si[4];
+    inv2_lu(sh.S[model], Si);
+    // write back: x_, P_, zPred, S, K
+    if (lane < 5) t.x[1 + model][lane] = x[lane];
+    if (lane < 25) t.P[1 + model][lane] = Pe;
+    if (lane < 10) {
+      const int r = lane >> 1, c = lane & 1;
+      t.K[model][lane] = sh.Tc[model][r * 2] * Si[c] + sh.Tc[model][r * 2 + 1] * Si[2 + c];
+    }
+    if (lane < 4) t.S[model][lane] = sh.S[model][lane];
+    if (lane == 0) { t.zPred[model][0] = zp0; t.zPred[model][1] = zp1; sh.zp[model][0] = zp0; sh.zp[model][1] = zp1; }
+    __syncthreads();
+
+    // ---- findMaxZandS (:176-203), gate scale x4 and explosion guard (:843-851)
+    const double dcv = det2(sh.S[0]), dctrv = det2(sh.S[1]), drm = det2(sh.S[2]);
+    int mm;
+    if (dcv > dctrv) mm = (dcv > drm) ? 0 : 2; else mm = (dctrv > drm) ? 1 : 2;
+    double S4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) S4[e] = sh.S[mm][e] * 4;
+    const double detS = det2(S4);
+    const bool dead = isnan(detS) || detS > 10;
+    const int trackNum = t.trackNum;
+    __syncthreads();                      // everyone has read t.trackNum / sh before thread 0 may change it
+    if (dead) {
+      if (tid == 0) { t.trackNum = 0; skip[it] = 1; }
+      continue;
+    }
+    const double z0 = sh.zp[mm][0], z1 = sh.zp[mm][1];
+    inv2_lu(S4, Si);
+    const bool secondInit = (trackNum == 1);
+    // ---- measurementValidation (:205-257): gate bits for every box; warps take 32-box chunks round-robin
+    const int nchunk = (M + 31) >> 5;
+    if (!secondInit) {
+      for (int ch = model; ch < nchunk; ch += 3) {
+        const int b = ch * 32 + lane;
+        bool g = false;
+        if (b < M) {
+          double cx, cy;
+          cp_from_box(boxes + (size_t)b * 24, cx, cy);
+          const double d0 = cx - z0, d1 = cy - z1;
+          const double nis = (d0 * Si[0] + d1 * Si[2]) * d0 + (d0 * Si[1] + d1 * Si[3]) * d1;
+          g = nis < gammaG;
+        }
+        const unsigned bits = __ballot_sync(0xFFFFFFFFu, g);
+        if (lane == 0) { gate[(size_t)it * words + ch] = bits; setter[(size_t)it * words + ch] = bits; }
+        if (g) atomicMin(&first_setter[b], it);
+      }
+    } else if (model == 0) {
+      // secondInit (:238-246): every running minimum of the NIS marks its box; chunks in order with a carried minimum
+      double run = 999;
+      for (int ch = 0; ch < nchunk; ++ch) {
+        const int b = ch * 32 + lane;
+        bool g = false;
+        double nis = DBL_MAX;
+        if (b < M) {
+          double cx, cy;
+          cp_from_box(boxes + (size_t)b * 24, cx, cy);
+          const double d0 = cx - z0, d1 = cy - z1;
+          nis = (d0 * Si[0] + d1 * Si[2]) * d0 + (d0 * Si[1] + d1 * Si[3]) * d1;
+          g = nis < gammaG;
+        }
+        const double v = g ? nis : DBL_MAX;
+        double pm = v;     // inclusive prefix minimum over lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xFFFFFFFFu, pm, o); if (lane >= o) pm = fmin(pm, u); }
+        double ex = __shfl_up_sync(0xFFFFFFFFu, pm, 1);
+        if (lane == 0) ex = DBL_MAX;
+        ex = fmin(ex, run);
+        const bool s = g && (nis < ex);
+        const unsigned gb = __ballot_sync(0xFFFFFFFFu, g), sb = __ballot_sync(0xFFFFFFFFu, s);
+        if (lane == 0) { gate[(size_t)it * words + ch] = gb; setter[(size_t)it * words + ch] = sb; }
+        if (s) atomicMin(&first_setter[b], it);
+        run = fmin(run, __shfl_sync(0xFFFFFFFFu, pm, 31));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ TB
+constexpr int kTBWarps = 4;
+
+// getBboxArea :482-494 (float arithmetic, abs(float))
+__device__ double bbox_area(const float b[][3]) {
+  const float p1x = b[0][0], p1y = b[0][1], p2x = b[1][0], p2y = b[1][1], p3x = b[2][0], p3y = b[2][1], p4x = b[3][0], p4y = b[3][1];
+  const double tri1 = 0.5 * fabsf((p1x - p3x) * (p2y - p3y) - (p2x - p3x) * (p1y - p3y));
+  const double tri2 = 0.5 * fabsf((p1x - p4x) * (p3y - p4y) - (p3x - p4x) * (p1y - p4y));
+  return tri1 + tri2;
+}
+
+// getBBoxYaw :535-563 (float sqrt, float atan2 == host libm atan2f -> exact_math.cuh)
+__device__ double bbox_yaw(const float b[][3], double ukfYaw) {
+  const float p1x = b[0][0], p1y = b[0][1], p2x = b[1][0], p2y = b[1][1], p3x = b[2][0], p3y = b[2][1];
+  const double dist1 = sqrtf((p1x - p2x) * (p1x - p2x) + (p1y - p2y) * (p1y - p2y));
+  const double dist2 = sqrtf((p3x - p2x) * (p3x - p2x) + (p3y - p2y) * (p3y - p2y));
+  double yaw;
+  if (dist1 > dist2) yaw = atan2f_fdlibm(p1y - p2y, p1x - p2x);
+  else yaw = atan2f_fdlibm(p3y - p2y, p3x - p2x);
+  const double diffYaw = fabs(yaw - ukfYaw);
+  if (diffYaw < kPi * 0.5) return yaw;
+  yaw += kPi;
+  return wrap_pi(yaw);
+}
+
+__device__ void update_box_yaw(float bb[][3], int n, double cpx, double cpy, double dyaw) {   // updateBoxYaw :512-532
+  for (int i = 0; i < n; ++i) {
+    const double preX = bb[i][0], preY = bb[i][1];
+    bb[i][0] = (float)(cos(dyaw) * (preX - cpx) - sin(dyaw) * (preY - cpy) + cpx);
+    bb[i][1] = (float)(sin(dyaw) * (preX - cpx) + cos(dyaw) * (preY - cpy) + cpy);
+  }
+}
+
+// updateBB :565-653, executed by one lane
+__device__ void update_bb(TrackState& t) {
+  if (!t.isVisBB) return;
+  if (t.nBest == 0) {
+    for (int p = 0; p < 8; ++p) for (int c = 0; c < 3; ++c) t.bestBBox[p][c] = t.BBox[p][c];
+    t.nBest = t.nBBox;
+    t.bestYaw = bbox_yaw(t.BBox, t.x[0][3]);
+    return;
+  }
+  double cpx, cpy, bcx, bcy;
+  cp_from_corners(t.BBox[0][0], t.BBox[0][1], t.BBox[1][0], t.BBox[1][1], t.BBox[2][0], t.BBox[2][1], t.BBox[3][0], t.BBox[3][1], cpx, cpy);
+  cp_from_corners(t.bestBBox[0][0], t.bestBBox[0][1], t.bestBBox[1][0], t.bestBBox[1][1], t.bestBBox[2][0], t.bestBBox[2][1],
+                  t.bestBBox[3][0], t.bestBBox[3][1], bcx, bcy);
+  const double dtx = cpx - bcx, dty = cpy - bcy;
+  const double yaw = bbox_yaw(t.BBox, t.x[0][3]);
+  const double deltaArea = bbox_area(t.BBox) - bbox_area(t.bestBBox);
+  if (deltaArea < 0) {                         // updateVisBoxArea :496-510
+    for (int i = 0; i < t.nBBox; ++i) {
+      t.BBox[i][0] = (float)(t.bestBBox[i][0] + dtx);
+      t.BBox[i][1] = (float)(t.bestBBox[i][1] + dty);
+    }
+  } else if (deltaArea > 0) {
+    for (int p = 0; p < 8; ++p) for (int c = 0; c < 3; ++c) t.bestBBox[p][c] = t.BBox[p][c];
+    t.nBest = t.nBBox;
+  }
+  const double currentYaw = bbox_yaw(t.BBox, t.x[0][3]);
+  const double DiffYaw = yaw - currentYaw;
+  if (fabs(DiffYaw) > bbYawChangeThres) {
+  } else if (fabs(DiffYaw) < bbYawChangeThres) {
+    update_box_yaw(t.BBox, t.nBBox, cpx, cpy, DiffYaw);
+    update_box_yaw(t.bestBBox, t.nBBox, cpx, cpy, DiffYaw);
+    t.bestYaw = yaw;
+  }
+}
+
+__global__ void __launch_bounds__(kTBWarps * 32)
+imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ counters, const float* __restrict__ boxes,
+                  const unsigned* __restrict__ gate, const int* __restrict__ first_setter, const uint8_t* __restrict__ skip,
+                  int words) {
+  extern __shared__ unsigned short s_list_all[];          // per warp: indices of the gated boxes, in box order
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int T = counters[CNT_N_TRACKS];
+  const int M = counters[CNT_N_BOXES];
+  unsigned short* s_list = s_list_all + (size_t)warp * words * 32;
+  const int nchunk = (M + 31) >> 5;
+
+  for (int it = blockIdx.x * kTBWarps + warp; it < T; it += gridDim.x * kTBWarps) {
+    if (skip[it]) continue;
+    TrackState& t = tracks[it];
+    const int trackNum0 = t.trackNum;
+    const bool secondInit = (trackNum0 == 1);
+    // ---- lifetime_ (:232): a gated box counts unless an earlier track already matched it
+    int nmeas = 0, life = 0;
+    for (int ch = 0; ch < nchunk; ++ch) {
+      const unsigned g = gate[(size_t)it * words + ch];
+      const int b = ch * 32 + lane;
+      const bool cnt = ((g >> lane) & 1u) && (first_setter[b] >= it);
+      life += __popc(__ballot_sync(0xFFFFFFFFu, cnt));
+      if ((g >> lane) & 1u) s_list[nmeas + __popc(g & ((1u << lane) - 1u))] = (unsigned short)b;
+      nmeas += __popc(g);
+    }
+    __syncwarp();
+    const int lifetime = t.lifetime + life;
+
+    // measurement prediction used by the gate (same selection as TA)
+    const double dcv = det2(t.S[0]), dctrv = det2(t.S[1]), drm = det2(t.S[2]);
+    int mm;
+    if (dcv > dctrv) mm = (dcv > drm) ? 0 : 2; else mm = (dctrv > drm) ? 1 : 2;
+
+    int measCount = nmeas;     // measVec.size()
+    double sx = 0, sy = 0;     // the single measurement of a secondInit track
+    if (secondInit) {
+      // the last running minimum == first occurrence of the smallest NIS (:238-255)
+      double S4[4], Si[4];
+      for (int e = 0; e < 4; ++e) S4[e] = t.S[mm][e] * 4;
+      inv2_lu(S4, Si);
+      double best = DBL_MAX; int bi = INT_MAX; double bx = 0, by = 0;
+      for (int k = lane; k < nmeas; k += 32) {
+        double cx, cy;
+        cp_from_box(boxes + (size_t)s_list[k] * 24, cx, cy);
+        const double d0 = cx - t.zPred[mm][0], d1 = cy - t.zPred[mm][1];
+        const double nis = (d0 * Si[0] + d1 * Si[2]) * d0 + (d0 * Si[1] + d1 * Si[3]) * d1;
+        if (nis < best) { best = nis; bi = k; bx = cx; by = cy; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xFFFFFFFFu, best, o), ox = __shfl_xor_sync(0xFFFFFFFFu, bx, o), oy = __shfl_xor_sync(0xFFFFFFFFu, by, o);
+        const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; bx = ox; by = oy; }
+      }
+      measCount = (nmeas > 0) ? 1 : 0;
+      sx = bx; sy = by;
+    }
+
+    // ---- associateBB (:416-463) + getNearestEuclidBBox (:396-413): int minDist => first box with the smallest
+    // floor(distance); secondInit tracks have an empty bboxVec
+    int isVis = 0;
+    if (!secondInit && nmeas > 0 && trackNum0 == 5 && lifetime > lifeTimeThres) {
+      const double px = t.x[0][0], py = t.x[0][1];
+      long long key = LLONG_MAX;      // (floor(dist) << 32) | position
+      for (int k = lane; k < nmeas; k += 32) {
+        double cx, cy;
+        cp_from_box(boxes + (size_t)s_list[k] * 24, cx, cy);
+        const double dist = sqrt((px - cx) * (px - cx) + (py - cy) * (py - cy));
+        if (dist < 999) { const long long kk = ((long long)(int)dist << 32) | (unsigned)k; key = key < kk ? key : kk; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const long long ok = __shfl_xor_sync(0xFFFFFFFFu, key, o); key = key < ok ? key : ok; }
+      int minDist = 999, minInd = 0;
+      if (key != LLONG_MAX) { minDist = (int)(key >> 32); minInd = (int)(key & 0xFFFFFFFFll); }
+      if (minDist < distanceThres) {
+        const float* b = boxes + (size_t)s_list[minInd] * 24;
+        if (lane < 8) {
+          const int c = lane & 3;
+          t.BBox[lane][0] = b[c * 3]; t.BBox[lane][1] = b[c * 3 + 1];
+          t.BBox[lane][2] = (lane < 4) ? (float)-1.73 : 0.f;
+        }
+        isVis = 1;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      t.lifetime = lifetime;
+      if (isVis) { t.isVisBB = 1; t.nBBox = 8; }
+      update_bb(t);                                     // :877
+    }
+    __syncwarp();
+
+    if (secondInit) {                                   // :882-921
+      if (lane == 0) {
+        if (measCount == 0) t.trackNum = 0;
+        else {
+          t.initMeas[0] = t.x[0][0]; t.initMeas[1] = t.x[0][1];
+          const double dX = sx - t.x[0][0], dY = sy - t.x[0][1];
+          const double targetYaw = wrap_pi(atan2(dY, dX));
+          for (int m = 0; m < 4; ++m) { t.x[m][0] = sx; t.x[m][1] = sy; t.x[m][2] = 2; t.x[m][3] = targetYaw; }
+          t.trackNum = trackNum0 + 1;
+        }
+      }
+      continue;
+    }
+    int tn = trackNum0;                                 // :924-944
+    if (measCount > 0) {
+      if (tn < 3) tn++;
+      else if (tn == 3) tn = 5;
+      else if (tn >= 5) tn = 5;
+    } else {
+      if (tn < 5) tn = 0;
+      else if (tn >= 5 && tn < 10) tn++;
+      else tn = 0;                                      // `else if (trackNum = 10) trackNum = 0` (:941)
+    }
+    if (lane == 0) t.trackNum = tn;
+    if (tn == 0) continue;
+
+    // ---- filterPDA (:259-394): the three models in turn; scalars replicated on every lane
+    const double numMeas = (double)measCount;
+    const double bb = 2 * numMeas * (1 - pD * pG) / (gammaG * pD);
+    double eSum[3];
+    double xnew[3][5];      // updated model states (all lanes)
+    double Pnew[3];         // lane e < 25: updated covariance element of each model
+    for (int m = 0; m < 3; ++m) {
+      double Si[4];
+      inv2_lu(t.S[m], Si);
+      const double zp0 = t.zPred[m][0], zp1 = t.zPred[m][1];
+      double es = 0;
+      for (int k = 0; k < nmeas; ++k) {
+        double cx, cy;
+        cp_from_box(boxes + (size_t)s_list[k] * 24, cx, cy);
+        const double d0 = cx - zp0, d1 = cy - zp1;
+        const double t0 = -0.5 * d0, t1 = -0.5 * d1;
+        es += exp((t0 * Si[0] + t1 * Si[2]) * d0 + (t0 * Si[1] + t1 * Si[3]) * d1);
+      }
+      eSum[m] = es;
+      const double betaZero = bb / (bb + es);
+      double sX0 = 0, sX1 = 0;
+      for (int k = 0; k < nmeas; ++k) {
+        double cx, cy;
+        cp_from_box(boxes + (size_t)s_list[k] * 24, cx, cy);
+        const double d0 = cx - zp0, d1 = cy - zp1;
+        const double t0 = -0.5 * d0, t1 = -0.5 * d1;
+        const double beta = exp((t0 * Si[0] + t1 * Si[2]) * d0 + (t0 * Si[1] + t1 * Si[3]) * d1) / (bb + es);
+        sX0 += beta * d0; sX1 += beta * d1;
+      }
+      double sP[4] = {0, 0, 0, 0};
+      for (int k = 0; k < nmeas; ++k) {
+        double cx, cy;
+        cp_from_box(boxes + (size_t)s_list[k] * 24, cx, cy);
+        const double d[2] = {cx - zp0, cy - zp1};
+        const double t0 = -0.5 * d[0], t1 = -0.5 * d[1];
+        const double beta = exp((t0 * Si[0] + t1 * Si[2]) * d[0] + (t0 * Si[1] + t1 * Si[3]) * d[1]) / (bb + es);
+        const double sXv[2] = {sX0, sX1};
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) sP[r * 2 + c] += ((beta * d[r]) * d[c] - sXv[r] * sXv[c]);
+      }
+      const double* K = t.K[m];
+      const double* S = t.S[m];
+#pragma unroll
+      for (int r = 0; r < 5; ++r) xnew[m][r] = t.x[1 + m][r] + (K[r * 2] * sX0 + K[r * 2 + 1] * sX1);
+      xnew[m][3] = wrap_pi(xnew[m][3]);
+      double Pe = 0;
+      if (lane < 25) {
+        const int r = lane / 5, c = lane % 5;
+        const double KS0 = K[r * 2] * S[0] + K[r * 2 + 1] * S[2], KS1 = K[r * 2] * S[1] + K[r * 2 + 1] * S[3];
+        const double KP0 = K[r * 2] * sP[0] + K[r * 2 + 1] * sP[2], KP1 = K[r * 2] * sP[1] + K[r * 2 + 1] * sP[3];
+        const double KSK = KS0 * K[c * 2] + KS1 * K[c * 2 + 1], KPK = KP0 * K[c * 2] + KP1 * K[c * 2 + 1];
+        const double P = t.P[1 + m][lane];
+        if (numMeas != 0) Pe = betaZero * P + (1 - betaZero) * (P - KSK) + KPK;
+        else Pe = P - KSK;
+      }
+      Pnew[m] = Pe;
+    }
+    const double Vk = kPi * sqrt(gammaG * det2(t.S[mm]));     // S is untouched by the update, same max model
+    double lam[3];
+    for (int m = 0; m < 3; ++m) {
+      if (numMeas != 0)
+        lam[m] = (1 - pG * pD) / pow(Vk, numMeas) + pD * pow(Vk, 1 - numMeas) * eSum[m] / (numMeas * sqrt(2 * kPi * det2(t.S[m])));
+      else
+        lam[m] = (1 - pG * pD) / pow(Vk, numMeas);
+    }
+    // ---- PostProcessIMMUKF: UpdateModeProb (ukf.cpp:384-397), MergeEstimationAndCovariance (:419-437)
+    double mp[3] = {t.modeProb[0], t.modeProb[1], t.modeProb[2]};
+    const double sumG = lam[0] * mp[0] + lam[1] * mp[1] + lam[2] * mp[2];
+    for (int m = 0; m < 3; ++m) { mp[m] = (lam[m] * mp[m]) / sumG; }
+    for (int m = 0; m < 3; ++m) if (fabs(mp[m]) < 0.0001) mp[m] = 0.0001;
+    double xm[5];
+#pragma unroll
+    for (int e = 0; e < 5; ++e) xm[e] = mp[0] * xnew[0][e] + mp[1] * xnew[1][e] + mp[2] * xnew[2][e];
+    xm[3] = wrap_pi(xm[3]);
+    double myaw;
+    if (mp[0] > mp[1]) myaw = (mp[0] > mp[2]) ? xnew[0][3] : xnew[2][3];
+    else               myaw = (mp[1] > mp[2]) ? xnew[1][3] : xnew[2][3];
+    xm[3] = myaw;
+    __syncwarp();
+    if (lane < 25) {
+      const int r = lane / 5, c = lane % 5;
+      const double a0 = mp[0] * (Pnew[0] + (xnew[0][r] - xm[r]) * (xnew[0][c] - xm[c]));
+      const double a1 = mp[1] * (Pnew[1] + (xnew[1][r] - xm[r]) * (xnew[1][c] - xm[c]));
+      const double a2 = mp[2] * (Pnew[2] + (xnew[2][r] - xm[r]) * (xnew[2][c] - xm[c]));
+      t.P[0][lane] = a0 + a1 + a2;
+      t.P[1][lane] = Pnew[0]; t.P[2][lane] = Pnew[1]; t.P[3][lane] = Pnew[2];
+    }
+    if (lane < 5) { t.x[0][lane] = xm[lane]; t.x[1][lane] = xnew[0][lane]; t.x[2][lane] = xnew[1][lane]; t.x[3][lane] = xnew[2][lane]; }
+    if (lane == 0) {
+      t.modeProb[0] = mp[0]; t.modeProb[1] = mp[1]; t.modeProb[2] = mp[2];
+      t.x_merge_yaw = myaw;
+      int nv = t.nVelo;                                 // velo_history_ :955-959
+      if (nv == 3) { t.velo[0] = t.velo[1]; t.velo[1] = t.velo[2]; nv = 2; }
+      t.velo[nv] = xm[2];
+      t.nVelo = nv + 1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ TC1
+__device__ __forceinline__ double intersect_coef(double v1x, double v1y, double v2x, double v2y, double px, double py, double cpx, double cpy) {
+  return (((v1x - v2x) * (py - v1y) + (v1y - v2y) * (v1x - px)) * ((v1x - v2x) * (cpy - v1y) + (v1y - v2y) * (v1x - cpx)));
+}
+
+// does track `a` (visible box) contain the position of track `b`?  (:670-696)
+__device__ bool overseg_cond(const TrackState& a, double px, double py) {
+  const double v1x = a.BBox[0][0], v1y = a.BBox[0][1], v2x = a.BBox[1][0], v2y = a.BBox[1][1];
+  const double v3x = a.BBox[2][0], v3y = a.BBox[2][1], v4x = a.BBox[3][0], v4y = a.BBox[3][1];
+  const double cp1x = (v1x + v2x + v3x) / 3, cp1y = (v1y + v2y + v3y) / 3;
+  const double cp2x = (v1x + v4x + v3x) / 3, cp2y = (v1y + v4y + v3y) / 3;
+  const double c1 = intersect_coef(v1x, v1y, v2x, v2y, px, py, cp1x, cp1y);
+  const double c2 = intersect_coef(v1x, v1y, v3x, v3y, px, py, cp1x, cp1y);
+  const double c3 = intersect_coef(v3x, v3y, v2x, v2y, px, py, cp1x, cp1y);
+  const double c4 = intersect_coef(v1x, v1y, v4x, v4y, px, py, cp2x, cp2y);
+  const double c5 = intersect_coef(v1x, v1y, v3x, v3y, px, py, cp2x, cp2y);
+  const double c6 = intersect_coef(v3x, v3y, v4x, v4y, px, py, cp2x, cp2y);
+  return (c1 > 0 && c2 > 0 && c3 > 0) || (c4 > 0 && c5 > 0 && c6 > 0);
+}
+
+// mergeOverSegmentation (:666-700).  The sequential double loop writes trackNum[i]=5, trackNum[j]=0 for every hit
+// (i,j); the value that survives at index k is the write with the largest (i,j) key: 0 if some visible i > k
+// contains k, else 5 if k (visible) contains anybody, else unchanged.  Decisions are staged in new_num and
+// applied by spawn_output_kernel so that this kernel only reads the table.
+__global__ void __launch_bounds__(128)
+merge_overseg_kernel(const TrackState* __restrict__ tracks, const int* __restrict__ counters, int* __restrict__ new_num) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int T = counters[CNT_N_TRACKS];
+  for (int k = blockIdx.x * 4 + warp; k < T; k += gridDim.x * 4) {
+    const TrackState& tk = tracks[k];
+    const double kx = tk.x[0][0], ky = tk.x[0][1];
+    const bool kvis = tk.isVisBB != 0;
+    int imax = -1; bool has5 = false;
+    for (int i = lane; i < T; i += 32) {
+      if (i == k) continue;
+      const TrackState& ti = tracks[i];
+      if (ti.isVisBB && overseg_cond(ti, kx, ky)) imax = max(imax, i);
+      if (kvis && !has5 && overseg_cond(tk, ti.x[0][0], ti.x[0][1])) has5 = true;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) imax = max(imax, __shfl_xor_sync(0xFFFFFFFFu, imax, o));
+    has5 = __any_sync(0xFFFFFFFFu, has5);
+    if (lane == 0) {
+      int v = -1;                       // -1 = unchanged
+      if (imax >= 0 && (!has5 || imax > k)) v = 0;
+      else if (has5) v = 5;
+      new_num[k] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ TC2
+struct OutPtrs {
+  float* targets; double* vandyaw; int* track_manage; uint8_t* is_static; uint8_t* is_vis; float* vis_bb;
+};
+
+__global__ void __launch_bounds__(1024)
+spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ counters, const float* __restrict__ boxes,
+                    int* __restrict__ first_setter, const int* __restrict__ new_num, int first_frame, int compat_first,
+                    double ego_yaw, int max_tracks, OutPtrs o) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T0 = counters[CNT_N_TRACKS];
+  const int M = counters[CNT_N_BOXES];
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+
+  if (first_frame && compat_first) {
+    // :741-795 -- the first call spawns ONE track, from box #1, at a hard-coded position
+    if (tid == 0) {
+      int T = 0;
+      if (M >= 2) {
+        ukf_initialize(tracks[0], -1.5125, -8.975);
+        o.targets[0] = (float)-1.5125; o.targets[1] = (float)-8.975; o.targets[2] = (float)(-1.73 / 2);
+        o.vandyaw[0] = 0; o.vandyaw[1] = 0; o.is_static[0] = 0; o.is_vis[0] = 0; o.track_manage[0] = 1;
+        T = 1;
+      }
+      counters[CNT_N_TRACKS] = T; counters[CNT_N_VIS] = 0;
+    }
+    for (int b = tid; b < M; b += 1024) first_setter[b] = INT_MAX;
+    return;
+  }
+
+  // apply the staged mergeOverSegmentation writes (:968)
+  for (int k = tid; k < T0; k += 1024) { const int v = new_num[k]; if (v >= 0) tracks[k].trackNum = v; }
+
+  // spawn one UKF per unmatched box, in box order (:972-989)
+  for (int b0 = 0; b0 < M; b0 += 1024) {
+    const int b = b0 + tid;
+    const int un = (b < M && first_setter[b] == INT_MAX) ? 1 : 0;
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, un);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int wbase = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) { if (w < warp) wbase += s_warp[w]; tot += s_warp[w]; }
+    const int pos = T0 + s_carry + wbase + __popc(bal & ((1u << lane) - 1u));
+    if (un && pos < max_tracks) {
+      double cx, cy;
+      cp_from_box(boxes + (size_t)b * 24, cx, cy);
+      ukf_initialize(tracks[pos], cx, cy);
+    }
+    if (b < M) first_setter[b] = INT_MAX;        // ready for the next frame
+    __syncthreads();
+    if (tid == 0) s_carry += tot;
+    __syncthreads();
+  }
+  int T = T0 + s_carry;
+  if (T > max_tracks) { if (tid == 0) counters[CNT_ERROR] = LMOT_ERR_CAPACITY; T = max_tracks; }
+  __syncthreads();
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+
+  // outputs (:995-1081)
+  for (int i0 = 0; i0 < T; i0 += 1024) {
+    const int i = i0 + tid;
+    int vis = 0;
+    if (i < T) {
+      TrackState& t = tracks[i];
+      const double tx = t.x[0][0], ty = t.x[0][1];
+      const double mx = t.initMeas[0], my = t.initMeas[1];
+      t.distFromInit = sqrt((tx - mx) * (tx - mx) + (ty - my) * (ty - my));
+      double tyaw = t.x[0][3];
+      tyaw += ego_yaw;
+      tyaw = wrap_pi(tyaw);
+      o.targets[3 * i] = (float)tx; o.targets[3 * i + 1] = (float)ty; o.targets[3 * i + 2] = (float)(-1.73 / 2);
+      o.vandyaw[2 * i] = t.x[0][2]; o.vandyaw[2 * i + 1] = tyaw;
+      vis = t.isVisBB ? 1 : 0;
+      o.is_vis[i] = (uint8_t)vis;
+      int st = 0;
+      if (t.isStatic) st = 1;
+      else if (t.trackNum == 5 && t.lifetime > 8) {
+        if ((t.distFromInit < 3.0) && (t.modeProb[2] > t.modeProb[0] || t.modeProb[2] > t.modeProb[1])) { st = 1; t.isStatic = 1; }
+      }
+      o.is_static[i] = (uint8_t)st;
+      o.track_manage[i] = t.trackNum;
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, vis);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int wbase = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) { if (w < warp) wbase += s_warp[w]; tot += s_warp[w]; }
+    if (vis) {
+      const int pos = s_carry + wbase + __popc(bal & ((1u << lane) - 1u));
+      const TrackState& t = tracks[i];
+      for (int p = 0; p < 8; ++p) for (int c = 0; c < 3; ++c) o.vis_bb[(size_t)pos * 24 + p * 3 + c] = t.BBox[p][c];
+    }
+    __syncthreads();
+    if (tid == 0) s_carry += tot;
+    __syncthreads();
+  }
+  if (tid == 0) { counters[CNT_N_TRACKS] = T; counters[CNT_N_VIS] = s_carry; }
+}
+
+__global__ void fill_int_kernel(int* p, int n, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+int tracker_alloc(Ctx* c) {
+  const int TC = c->prm.max_tracks, MB = c->prm.max_boxes;
+  c->gate_words = (MB + 31) / 32;
+  LMOT_CUDA(c, cudaMalloc(&c->d_tracks, (size_t)TC * sizeof(TrackState)));
+  LMOT_CUDA(c, cudaMemsetAsync(c->d_tracks, 0, (size_t)TC * sizeof(TrackState), c->stream));
+  LMOT_CUDA(c, cudaMalloc(&c->d_gate, (size_t)TC * c->gate_words * sizeof(unsigned)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_setter, (size_t)TC * c->gate_words * sizeof(unsigned)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_first_setter, (size_t)MB * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_skip, TC));
+  LMOT_CUDA(c, cudaMalloc(&c->d_new_num, (size_t)TC * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_boxes_in, (size_t)MB * 24 * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_out_targets, (size_t)TC * 3 * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_out_vandyaw, (size_t)TC * 2 * sizeof(double)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_out_manage, (size_t)TC * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_out_static, TC));
+  LMOT_CUDA(c, cudaMalloc(&c->d_out_vis, TC));
+  LMOT_CUDA(c, cudaMalloc(&c->d_out_visbb, (size_t)TC * 24 * sizeof(float)));
+  fill_int_kernel<<<(MB + 255) / 256, 256, 0, c->stream>>>(c->d_first_setter, MB, INT_MAX);
+  LMOT_CUDA(c, cudaGetLastError());
+  const size_t sh = (size_t)kTBWarps * c->gate_words * 32 * sizeof(unsigned short);
+  LMOT_CUDA(c, cudaFuncSetAttribute(imm_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+  return LMOT_OK;
+}
+
+void tracker_free(Ctx* c) {
+  cudaFree(c->d_tracks); cudaFree(c->d_gate); cudaFree(c->d_setter); cudaFree(c->d_first_setter); cudaFree(c->d_skip);
+  cudaFree(c->d_new_num); cudaFree(c->d_boxes_in); cudaFree(c->d_out_targets); cudaFree(c->d_out_vandyaw);
+  cudaFree(c->d_out_manage); cudaFree(c->d_out_static); cudaFree(c->d_out_vis); cudaFree(c->d_out_visbb);
+}
+
+// getOriginPoints (imm_ukf_jpda.cpp:74-172) is scalar bookkeeping on three doubles per frame; it stays on the host.
+// The reference replays its whole delta history every call; the replay is a left fold, so carrying (x, y, yaw) is
+// bit-identical.
+static void origin_points_host(Ctx* c, double timestamp, double v_gps, double yaw_gps) {
+  TrackerHost& h = c->th;
+  const double firstEgoYawOffset = -0.63035 - M_PI / 2;
+  const double dt = (timestamp - h.timestamp) / 1000000.0;
+  h.egoVelo = v_gps;
+  h.egoYaw = yaw_gps;
+  h.egoYaw += firstEgoYawOffset;
+  if (!h.init) {
+    h.egoPoint[0] = 0; h.egoPoint[1] = 0; h.egoPoint[2] = h.egoYaw;
+    h.fold[0] = 0; h.fold[1] = 0; h.fold[2] = -M_PI / 2;
+    return;
+  }
+  const double diffYaw = h.egoYaw - h.egoPreYaw;
+  const double dX = dt * h.egoVelo * cos(diffYaw), dY = dt * h.egoVelo * sin(diffYaw);
+  double x = h.fold[0], y = h.fold[1], egoYaw = h.fold[2];
+  x -= dX; y -= dY;
+  const double preX = x, preY = y;
+  const double yaw = diffYaw * -1;
+  egoYaw += yaw;
+  x = cos(yaw) * preX - sin(yaw) * preY;
+  y = sin(yaw) * preX + cos(yaw) * preY;
+  h.fold[0] = x; h.fold[1] = y; h.fold[2] = egoYaw;
+  h.egoPoint[0] = x; h.egoPoint[1] = y; h.egoPoint[2] = egoYaw;
+}
+
+// boxes: device float[M][8][3] with M in d_counters[CNT_N_BOXES]
+int tracker_launch(Ctx* c, const float* d_boxes, double timestamp, double v_gps, double yaw_gps) {
+  origin_points_host(c, timestamp, v_gps, yaw_gps);
+  TrackerHost& h = c->th;
+  OutPtrs o{c->d_out_targets, c->d_out_vandyaw, c->d_out_manage, c->d_out_static, c->d_out_vis, c->d_out_visbb};
+  const int first = h.init ? 0 : 1;
+  const int compat = c->prm.oracle_compat_first_frame ? 1 : 0;
+  if (!(first && compat)) {
+    const double dt = first ? 0.0 : (timestamp - h.timestamp) / 1000000.0;     // :807
+    const size_t sh = (size_t)kTBWarps * c->gate_words * 32 * sizeof(unsigned short);
+    imm_predict_gate_kernel<<<c->trk_ctas, kTAThreads, 0, c->stream>>>(c->d_tracks, c->d_counters, d_boxes, dt, c->d_gate,
+                                                                        c->d_setter, c->d_first_setter, c->d_skip, c->gate_words);
+    imm_update_kernel<<<c->trk_ctas / kTBWarps + 1, kTBWarps * 32, sh, c->stream>>>(c->d_tracks, c->d_counters, d_boxes, c->d_gate,
+                                                                                  c->d_first_setter, c->d_skip, c->gate_words);
+    merge_overseg_kernel<<<c->trk_ctas / 4 + 1, 128, 0, c->stream>>>(c->d_tracks, c->d_counters, c->d_new_num);
+  }
+  spawn_output_kernel<<<1, 1024, 0, c->stream>>>(c->d_tracks, c->d_counters, d_boxes, c->d_first_setter, c->d_new_num,
+                                                 first, compat, h.egoPoint[2], c->prm.max_tracks, o);
+  LMOT_CUDA(c, cudaGetLastError());
+  h.timestamp = timestamp;
+  h.egoPreYaw = h.egoYaw;
+  h.init = true;
+  return LMOT_OK;
+}
+
+}  // namespace lmot
