@@ -11,7 +11,46 @@ enum { D_TRACKNUM = 0, D_LIFETIME = 1, D_STATIC = 2, D_VIS = 3, D_X = 4, D_P = 2
        D_K = 145, D_BESTYAW = 175, D_BBYAW = 176, D_BBAREA = 177, D_DISTINIT = 178, D_XMERGEYAW = 179, D_INITMEAS = 180,
        D_VELON = 182, D_VELO = 183, D_BBN = 186, D_BB = 187, D_BESTBBN = 211, D_BESTBB = 212, D_TOTAL = 236 };
 
+static int g_rule_mode = 0;
+
 extern "C" {
+
+void port_set_rule_mode(int mode) { g_rule_mode = mode; }
+
+void port_cell_index(const float* xy, int n, int stride, int* ch, int* bin) {
+  for (int i = 0; i < n; ++i) cell_index(xy[(size_t)i * stride], xy[(size_t)i * stride + 1], ch[i], bin[i]);
+}
+
+void port_ground_remove(const float* xyz, int n, int stride, float* elev, int* n_elev, float* ground, int* n_ground) {
+  std::vector<float> e, g;
+  ground_remove(xyz, n, stride, e, g, nullptr);
+  *n_elev = (int)e.size() / 3; *n_ground = (int)g.size() / 3;
+  memcpy(elev, e.data(), e.size() * sizeof(float)); memcpy(ground, g.data(), g.size() * sizeof(float));
+}
+
+void port_polar_grid(const float* xyz, int n, int stride, float* minz, float* height, float* smoothed, float* hdiff,
+                     float* hground, uint8_t* isground) {
+  std::vector<float> e, g;
+  GridDump d{minz, height, smoothed, hdiff, hground, isground};
+  ground_remove(xyz, n, stride, e, g, &d);
+}
+
+void port_component_clustering(const float* xyz, int n, int stride, int32_t* grid, int* num_cluster) {
+  int nc = 0;
+  component_clustering(xyz, n, stride, grid, nc);
+  *num_cluster = nc;
+}
+
+void port_box_fitting(const float* xyz, int n, int stride, const int32_t* grid, int num_cluster, int max_boxes, float* boxes,
+                      int* n_boxes, float* markers) {
+  std::vector<float> b, m;
+  box_fitting(xyz, n, stride, grid, num_cluster, g_rule_mode, b, m);
+  const int nb = (int)b.size() / 24;
+  *n_boxes = nb;
+  const int nc = nb < max_boxes ? nb : max_boxes;
+  memcpy(boxes, b.data(), (size_t)nc * 24 * sizeof(float));
+  if (markers) memcpy(markers, m.data(), (size_t)nc * 6 * sizeof(float));
+}
 
 void port_tracker_reset() { g_T = Tracker(); }
 int port_tracker_num_tracks() { return (int)g_T.targets.size(); }

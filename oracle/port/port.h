@@ -40,6 +40,12 @@ struct StepOut {
   void clear() { targets.clear(); vandyaw.clear(); track_manage.clear(); is_static.clear(); is_vis.clear(); vis_bb.clear(); }
 };
 
+struct GridDump { float *minz, *height, *smoothed, *hdiff, *hground; uint8_t* isground; };
+void cell_index(float x, float y, int& chI, int& binI);
+void ground_remove(const float* xyz, int n, int stride, std::vector<float>& elev, std::vector<float>& ground, GridDump* dump);
+void component_clustering(const float* xyz, int n, int stride, int* grid, int& numCluster);
+void box_fitting(const float* xyz, int n, int stride, const int* grid, int numCluster, int mode, std::vector<float>& boxes,
+                 std::vector<float>& markers);
 void ukf_initialize(Track& t, double zx, double zy);
 void get_origin_points(Tracker& T, double timestamp, double v_gps, double yaw_gps);
 void imm_ukf_jpdaf(Tracker& T, const float* boxes, int nb, double timestamp, StepOut& out);
