@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- HDL-64 frames/s of the LiDAR->tracks hot path (ground_removal -> component_clustering -> box_fitting ->
+imm_ukf_jpda) on B200, next to the reference's own CPU implementation timed on the same host.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]           # our CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]     # the reference's sources (oracle/_ref) on the host CPU
+    torchrun ... bench.py --gpus N ...                            # one rank per GPU, independent sensor streams (weak scaling)
+
+One "step" = one 120,000-point synthetic HDL-64 frame (64 rings x 1875 azimuths, ~64 live tracks) through all four
+stages, tracker state carried from frame to frame.  Frames are consecutive frames of ONE moving scene; every step reads
+a different frame (the ring of W+K frames is larger than the 126 MB L2, so inputs never sit in L2 from the previous step).
+
+Printed JSON (rank 0, one line):
+  value     whole-job frames/s with the frames already resident in HBM (CUDA events around K steps, max over ranks)
+  e2e       frames/s through the reference-facing C ABI call lmot_frame() on HOST buffers: every step copies the frame
+            H2D from pinned memory, runs the four stages and copies boxes + track outputs back, then synchronises
+  roofline  the ground-removal stage (polar_bin + polar_grid + classify_partition kernels, the only stage that
+            streams the whole frame): algorithmic bytes per frame / its CUDA-event duration, vs the measured HBM peak
+  cpu_baseline  the reference's own four entry points on a bounded sample of the same frames, one host thread
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "3d-lidar-multi-object-tracking_b200"
+
+WORKLOAD = "hdl64_120k_64trk_full_pipeline"
+SCENE = dict(n_objects=150, lattice_pitch=3.8, ped_fraction=0.65, seed=1)   # ~64 live tracks at steady state
+KERNELS_PER_FRAME = 13   # ground 3 + cluster 2 + box 4 + tracker 4
+
+
+def make_frames(synth, n_frames, seed_offset=0):
+    cfg = synth.SceneConfig(**{**SCENE, "seed": SCENE["seed"] + seed_offset})
+    ts, frames = [], []
+    for t, pts in synth.frames(cfg, n_frames):
+        ts.append(t)
+        frames.append(pts)
+    return ts, np.stack(frames)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_cpu_name():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, synth):
+    """The reference's own CPU implementation of the path (oracle/_ref = its unmodified sources, ruleBasedFilter in
+    INTENDED mode like the GPU arm), single thread like the reference's ROS nodes; bounded sample per step."""
+    from oracle import ref as oracle
+    if oracle.have_ref("intended"):
+        o, kind = oracle.RefOracle("intended"), "reference"
+    else:
+        o, kind = oracle.PortOracle("intended"), "port"
+    K, W = args.steps, args.warmup
+    ts, frames = make_frames(synth, W + K)
+    o.tracker_reset()
+    # The reference deploys as THREE single-threaded ROS nodes (ground | cluster | tracking) connected by topics, i.e. a
+    # 3-stage pipeline on three cores.  Same here: one thread per node, queues instead of TCPROS (ctypes drops the GIL).
+    import queue
+    q1, q2 = queue.Queue(maxsize=4), queue.Queue(maxsize=4)
+    stage = np.zeros(4)
+    marks = {}
+
+    def node_ground():
+        for i in range(W + K):
+            t0 = time.perf_counter()
+            e, g = o.ground_remove(frames[i])
+            if i >= W:
+                stage[0] += time.perf_counter() - t0
+            q1.put((i, e))
+        q1.put(None)
+
+    def node_cluster():
+        while True:
+            item = q1.get()
+            if item is None:
+                q2.put(None)
+                return
+            i, e = item
+            t0 = time.perf_counter()
+            grid, k = o.component_clustering(e); t1 = time.perf_counter()
+            boxes, _ = o.box_fitting(e, grid, k); t2 = time.perf_counter()
+            if i >= W:
+                stage[1] += t1 - t0; stage[2] += t2 - t1
+            q2.put((i, boxes))
+
+    def node_tracking():
+        while True:
+            item = q2.get()
+            if item is None:
+                return
+            i, boxes = item
+            if i == W:
+                marks["t0"] = time.perf_counter()
+            t0 = time.perf_counter()
+            o.tracker_step(boxes, ts[i])
+            if i >= W:
+                stage[3] += time.perf_counter() - t0
+            marks["t1"] = time.perf_counter()
+
+    threading.stack_size(256 * 1024 * 1024)   # the reference recurses per grid cell and passes 250 KB arrays by value
+    threads = [threading.Thread(target=f) for f in (node_ground, node_cluster, node_tracking)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    t_total = marks["t1"] - marks["t0"]
+    fps = K / t_total
+    line = {
+        "impl": "reference", "metric": "HDL-64 frames/sec (120K pts, 64 tracks)", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": K, "warmup": W, "ms_per_step": 1e3 * t_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 points / f64 tracker", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "points_per_frame": int(frames.shape[1]), "scene": SCENE, "rule_filter": "INTENDED"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 3, "kind": kind, "host_cpu": host_cpu_name(), "host_cores": os.cpu_count(),
+                         "sample": f"{K} consecutive frames of the workload after {W} warm-up frames; 3 threads = the reference's 3 ROS nodes pipelined; single-thread sum of stages = {1e3 * stage.sum() / K:.2f} ms/frame",
+                         "stage_ms": {n: 1e3 * v / K for n, v in zip(("ground", "cluster", "box", "tracker"), stage)}},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="lmot", choices=["lmot", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=60, help="frames of the CPU baseline sample (rank 0, N=1)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    synth = importlib.import_module(PKG + ".synth")
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args, synth)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lmot = importlib.import_module(PKG)
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---- inputs: W+K consecutive frames of this rank's sensor stream, resident in HBM and in pinned host memory
+    ts, frames = make_frames(synth, W + K, seed_offset=rank)
+    n_pts = int(frames.shape[1])
+    h_frames = torch.from_numpy(frames).pin_memory()
+    d_frames = h_frames.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+    ring_mb = d_frames.numel() * 4 / 2**20
+
+    ctx = lmot.Lmot(device=local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    frame_bytes = n_pts * 16
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- (1) device-resident throughput: `value`
+    ctx.tracker_reset()
+    for i in range(W):
+        ctx.frame_dev(d_frames[i].data_ptr(), n_pts, ts[i])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(W, W + K):
+        ctx.frame_dev(d_frames[i].data_ptr(), n_pts, ts[i])
+    e1.record(stream)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    res_dev = ctx.frame_fetch()
+    live_tracks = int((res_dev["track_manage"] > 0).sum())
+
+    # ---- (2) per-stage device time of the same frames (CUDA events on the launching stream): roofline numerator
+    ctx.tracker_reset()
+    ctx.enable_timing(True)
+    stage_ms = np.zeros(4)
+    n_elev_sum = 0
+    for i in range(W + K):
+        ctx.frame_dev(d_frames[i].data_ptr(), n_pts, ts[i])
+        r = ctx.frame_fetch(want_boxes=False)
+        if i >= W:
+            stage_ms += ctx.last_stage_ms()
+            n_elev_sum += r["n_elevated"] + r["n_ground"]
+    ctx.enable_timing(False)
+    stage_ms /= K
+    n_f = n_elev_sum / K                                         # points that survive the range filter, per frame
+    ground_bytes = 16 * n_pts + 16 * n_f + 9600 * 24             # read XYZI + write both clouds + grid
+    peak, peak_src = measured_peak_gbs()
+    achieved = ground_bytes / (stage_ms[0] * 1e-3) / 1e9
+
+    # ---- (3) end to end through the C ABI with host buffers: `e2e`
+    ctx.tracker_reset()
+    h_np = h_frames.numpy()
+    for i in range(W):
+        ctx.frame(h_np[i], ts[i])
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for i in range(W, W + K):
+        r = ctx.frame(h_np[i], ts[i])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    d2h = 16 * 4 + r["boxes"].size * 4 + len(r["track_manage"]) * (12 + 16 + 4 + 1 + 1) + r["vis_bb"].size * 4
+
+    # ---- aggregate over ranks (max time)
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    value = world * K / (dev_ms_max * 1e-3)
+    e2e = world * K / (e2e_ms_max * 1e-3)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and args.cpu_sample > 0:
+        from oracle import ref as oracle     # the checker / baseline, never the measured product
+        o = oracle.RefOracle("intended") if oracle.have_ref("intended") else oracle.PortOracle("intended")
+        kind = "reference" if isinstance(o, oracle.RefOracle) else "port"
+        S, Wc = args.cpu_sample, 10
+        o.tracker_reset()
+        tt = 0.0
+        for i in range(min(Wc + S, W + K)):
+            t0 = time.perf_counter()
+            e, g = o.ground_remove(frames[i]); grid, k = o.component_clustering(e); boxes, _ = o.box_fitting(e, grid, k)
+            o.tracker_step(boxes, ts[i])
+            if i >= Wc:
+                tt += time.perf_counter() - t0
+        ns = min(Wc + S, W + K) - Wc
+        cpu_baseline = {"value": ns / tt, "unit": "frames/s", "cores": 1, "kind": kind, "host_cpu": host_cpu_name(),
+                        "host_cores": os.cpu_count(),
+                        "sample": f"first {ns} frames of the same workload after {Wc} warm-up frames, single thread (the reference is single-threaded per node)"}
+
+    if rank == 0:
+        line = {
+            "metric": "HDL-64 frames/sec (120K pts, 64 tracks)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 points / f64 tracker", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "points_per_frame": n_pts, "scene": SCENE, "live_tracks_end": live_tracks,
+                       "tracks_in_table_end": int(len(res_dev["track_manage"])), "rule_filter": "INTENDED",
+                       "parallelism": f"{world} independent sensor stream(s), one per GPU, no collective on the data path",
+                       "l2_policy": f"every step reads a different frame of a {ring_mb:.0f} MiB ring (> 126 MB L2)"},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": KERNELS_PER_FRAME * K,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "ground_removal stage (polar_bin_kernel + polar_grid_kernel + classify_partition_kernel)",
+                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                         "algorithmic_bytes_per_launch": ground_bytes, "avg_launch_ms": float(stage_ms[0]), "traffic": None},
+            "stage_ms": {n: float(v) for n, v in zip(("ground", "cluster", "box", "tracker"), stage_ms)},
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -155,8 +155,18 @@ class RefOracle(_OracleBase):
 
 
 class PortOracle(_OracleBase):
-    def __init__(self):
+    def __init__(self, mode: str = "intended"):
         super().__init__(os.path.join(HERE, "liboracle_port.so"), "port_")
+        self.mode = mode
+        self.lib.port_set_rule_mode(0 if mode == "intended" else 1)
+
+    def box_fitting(self, elevated, grid, num_cluster, max_boxes: int = 4096):
+        self.lib.port_set_rule_mode(0 if self.mode == "intended" else 1)   # the mode is process-global in the port
+        return super().box_fitting(elevated, grid, num_cluster, max_boxes)
+
+
+def have_port() -> bool:
+    return os.path.exists(os.path.join(HERE, "liboracle_port.so"))
 
 
 def labels_from_clouds(points, elevated, ground) -> np.ndarray:
