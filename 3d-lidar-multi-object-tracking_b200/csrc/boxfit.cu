@@ -81,10 +81,13 @@ seg_offsets_kernel(int* __restrict__ table, int* counters,
     const int k = k0 + threadIdx.x;
     int total = 0;
     if (k <= K) {
-      for (int t = 0; t < n_tiles; ++t) {
-        const int v = table[(size_t)t * stride + k];
-        table[(size_t)t * stride + k] = total;
-        total += v;
+      for (int t0 = 0; t0 < n_tiles; t0 += 8) {        // 8 independent loads in flight, then the dependent prefix
+        int v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (t0 + u < n_tiles) ? table[(size_t)(t0 + u) * stride + k] : 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (t0 + u < n_tiles) { table[(size_t)(t0 + u) * stride + k] = total; total += v[u]; }
       }
     }
     // block exclusive scan of `total` (+ carry from previous chunks of 1024 clusters)
@@ -210,6 +213,8 @@ box_fit_kernel(const float4* __restrict__ elev, const int* __restrict__ sorted_i
                float* __restrict__ boxes, float* __restrict__ markers, int* __restrict__ done) {
   __shared__ int s_lo[kCols], s_hi[kCols];
   __shared__ short s_hx[kHullCap], s_hy[kHullCap];
+  __shared__ short s_cx[kCols], s_clo[kCols], s_chi[kCols];     // occupied pixel columns, compacted
+  __shared__ uint8_t s_flag8[kCols];
   __shared__ unsigned long long s_red64[kFitThreads / 32];
   __shared__ float s_redf[kFitThreads / 32];
   __shared__ double s_redd[kFitThreads / 32];
@@ -283,11 +288,30 @@ box_fit_kernel(const float4* __restrict__ elev, const int* __restrict__ sorted_i
     if (slopeDist > (float)P.l_slope_dist && n > P.l_num_points && (maxMy > 8.f || maxMy < -5.f)) {
       // ---- L-shape (:303-356): 80 draws of uniform_int_distribution<>(0,n-1) over mt19937_64(0), Lemire mapping
       // (libstdc++ >= 11): idx = hi64(raw*n), redraw while lo64 < 2^64 mod n.  First strictly larger distance wins.
-      if (tid == 0) {
-        float maxDist = 0.f, maxDx = 0.f, maxDy = 0.f;   // maxDx/maxDy are uninitialised in the reference if no dist > 0
-        const float den = sqrtf(slope * slope + 1);
-        const unsigned long long un = (unsigned long long)n;
-        const unsigned long long thr = (0ull - un) % un;
+      const float den = sqrtf(slope * slope + 1);
+      const unsigned long long un = (unsigned long long)n;
+      const unsigned long long thr = (0ull - un) % un;
+      // one draw per thread; a Lemire redraw (probability n / 2^64) shifts the stream, then thread 0 replays it in order
+      bool redraw = false;
+      unsigned long long key = 0ull;                       // (dist bits << 32) | (~draw index): max = first largest dist
+      float myx = 0.f, myy = 0.f;
+      if (tid < P.ram_points) {
+        const unsigned long long raw = mt_raw[tid % n_raw];
+        redraw = raw * un < thr;
+        const unsigned pInd = (unsigned)__umul64hi(raw, un);
+        const float4 q = __ldg(&elev[seg[pInd]]);
+        const float dist = fabsf(slope * q.x - 1 * q.y + maxMy - slope * maxMx) / den;
+        myx = q.x; myy = q.y;
+        if (dist > 0.f) key = ((unsigned long long)__float_as_uint(dist) << 32) | (0xFFFFFFFFu - (unsigned)tid);
+      }
+      const bool slow = __syncthreads_or(redraw) || P.ram_points > kFitThreads;
+      if (!slow) {
+        const unsigned long long best = block_reduce(key, MaxU64(), s_red64);
+        const unsigned win = 0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFull);
+        if (best == 0ull) { if (tid == 0) { s_pc[1][0] = 0.f; s_pc[1][1] = 0.f; } }   // no dist > 0: uninitialised in the reference
+        else if ((unsigned)tid == win) { s_pc[1][0] = myx; s_pc[1][1] = myy; }
+      } else if (tid == 0) {
+        float maxDist = 0.f, maxDx = 0.f, maxDy = 0.f;
         int cur = 0;
         for (int i = 0; i < P.ram_points; ++i) {
           unsigned long long raw = mt_raw[cur % n_raw]; ++cur;
@@ -298,52 +322,82 @@ box_fit_kernel(const float4* __restrict__ elev, const int* __restrict__ sorted_i
           const float dist = fabsf(slope * q.x - 1 * q.y + maxMy - slope * maxMx) / den;
           if (dist > maxDist) { maxDist = dist; maxDx = q.x; maxDy = q.y; }
         }
+        s_pc[1][0] = maxDx; s_pc[1][1] = maxDy;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        const float maxDx = s_pc[1][0], maxDy = s_pc[1][1];
         const float maxMvecX = maxMx - maxDx, maxMvecY = maxMy - maxDy;
         const float minMvecX = minMx - maxDx, minMvecY = minMy - maxDy;
         s_pc[0][0] = minMx; s_pc[0][1] = minMy;
-        s_pc[1][0] = maxDx; s_pc[1][1] = maxDy;
         s_pc[2][0] = maxMx; s_pc[2][1] = maxMy;
         s_pc[3][0] = maxDx + maxMvecX + minMvecX; s_pc[3][1] = maxDy + maxMvecY + minMvecY;
       }
       __syncthreads();
     } else {
       // ---- MAR contract (oracle/mar_contract.cpp): strict hull of the pixel set from the column extremes
+      // strict convex hull of the pixel set, same canonical sequence as Andrew's monotone chain in
+      // oracle/mar_contract.cpp (start = lexicographic minimum, lower chain left to right, upper chain right to left),
+      // computed in parallel from the per-column extremes:
+      //   (c, lo[c]) is a lower-hull vertex  <=>  max slope from any column on its left  <  min slope to any column on its right
+      //   (c, hi[c]) is an upper-hull vertex <=>  min slope from the left                >  max slope to the right
+      // (first / last occupied columns always are); slopes are compared exactly as integer cross products.
+      int W;
+      {
+        // compact the occupied columns: thread t owns columns [8t, 8t+8)
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int c = tid * 8 + u; if (c < kCols && s_lo[c] != INT_MAX) ++cnt; }
+        int incl = cnt;
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_redi[warp] = incl;
+        __syncthreads();
+        int wbase = 0, tot = 0;
+        for (int w = 0; w < kFitThreads / 32; ++w) { if (w < warp) wbase += s_redi[w]; tot += s_redi[w]; }
+        int pos = wbase + incl - cnt;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int c = tid * 8 + u;
+          if (c < kCols && s_lo[c] != INT_MAX) { s_cx[pos] = (short)(c - kColShift); s_clo[pos] = (short)s_lo[c]; s_chi[pos] = (short)s_hi[c]; ++pos; }
+        }
+        W = tot;
+        __syncthreads();
+      }
+      for (int i = tid; i < W; i += kFitThreads) {
+        const int xi = s_cx[i], li = s_clo[i], hi = s_chi[i];
+        bool lowv = true, upv = true;
+        if (i > 0 && i < W - 1) {
+          // left side: running extreme slopes as (dy, dx), dx > 0
+          int lmax_n = 0, lmax_d = 0, umin_n = 0, umin_d = 0;
+          for (int j = 0; j < i; ++j) {
+            const int dx = xi - s_cx[j];
+            const int dl = li - s_clo[j], du = hi - s_chi[j];
+            if (lmax_d == 0 || (long long)dl * lmax_d > (long long)lmax_n * dx) { lmax_n = dl; lmax_d = dx; }
+            if (umin_d == 0 || (long long)du * umin_d < (long long)umin_n * dx) { umin_n = du; umin_d = dx; }
+          }
+          for (int k = i + 1; k < W && (lowv || upv); ++k) {
+            const int dx = s_cx[k] - xi;
+            const int dl = s_clo[k] - li, du = s_chi[k] - hi;
+            if (!((long long)lmax_n * dx < (long long)dl * lmax_d)) lowv = false;   // need lmax < slope to k
+            if (!((long long)umin_n * dx > (long long)du * umin_d)) upv = false;    // need umin > slope to k
+          }
+        }
+        s_flag8[i] = (lowv ? 1 : 0) | (upv ? 2 : 0);
+      }
+      __syncthreads();
       if (tid == 0) {
-        // Andrew's monotone chain exactly as oracle/mar_contract.cpp runs it, over the reduced sorted point list
-        // R = {(c, lo[c]), (c, hi[c]) if hi != lo : c ascending} (hull(R) == hull(all pixels), same canonical order)
-        int first = -1, last = -1, nR = 0;
-        for (int c = 0; c < kCols; ++c)
-          if (s_lo[c] != INT_MAX) { if (first < 0) first = c; last = c; nR += (s_hi[c] != s_lo[c]) ? 2 : 1; }
         int m = 0;
-        auto push = [&](int px, int py, int floor_k) {
-          while (m >= floor_k) {
-            const long long cr = (long long)(s_hx[m - 1] - s_hx[m - 2]) * (py - s_hy[m - 2]) -
-                                 (long long)(s_hy[m - 1] - s_hy[m - 2]) * (px - s_hx[m - 2]);
-            if (cr <= 0) --m; else break;
-          }
-          if (m < kHullCap) { s_hx[m] = (short)px; s_hy[m] = (short)py; }
-          ++m;
-        };
-        if (nR <= 2) {
-          for (int c = first; c <= last && first >= 0; ++c) {
-            if (s_lo[c] == INT_MAX) continue;
-            s_hx[m] = (short)(c - kColShift); s_hy[m] = (short)s_lo[c]; ++m;
-            if (s_hi[c] != s_lo[c]) { s_hx[m] = (short)(c - kColShift); s_hy[m] = (short)s_hi[c]; ++m; }
-          }
+        if (W == 1) {
+          s_hx[0] = s_cx[0]; s_hy[0] = s_clo[0]; m = 1;
+          if (s_chi[0] != s_clo[0]) { s_hx[1] = s_cx[0]; s_hy[1] = s_chi[0]; m = 2; }
         } else {
-          for (int c = first; c <= last; ++c) {            // lower pass over R ascending
-            if (s_lo[c] == INT_MAX) continue;
-            push(c - kColShift, s_lo[c], 2);
-            if (s_hi[c] != s_lo[c]) push(c - kColShift, s_hi[c], 2);
-          }
-          const int t0 = m + 1;
-          bool skip = true;                                 // R's last element is already the end of the chain
-          for (int c = last; c >= first; --c) {             // upper pass over R descending
-            if (s_lo[c] == INT_MAX) continue;
-            if (s_hi[c] != s_lo[c]) { if (skip) skip = false; else push(c - kColShift, s_hi[c], t0); }
-            if (skip) skip = false; else push(c - kColShift, s_lo[c], t0);
-          }
-          --m;                                              // the start point was pushed again to close the chain
+          for (int i = 0; i < W; ++i)
+            if (s_flag8[i] & 1) { if (m < kHullCap) { s_hx[m] = s_cx[i]; s_hy[m] = s_clo[i]; } ++m; }
+          for (int i = W - 1; i >= 0; --i)
+            // the lo point of the first / last column already sits in the lower chain
+            if ((s_flag8[i] & 2) && !((i == 0 || i == W - 1) && s_chi[i] == s_clo[i])) { if (m < kHullCap) { s_hx[m] = s_cx[i]; s_hy[m] = s_chi[i]; } ++m; }
         }
         if (m > kHullCap) { counters[CNT_ERROR] = LMOT_ERR_CAPACITY; m = kHullCap; }
         s_m = m;

@@ -29,8 +29,7 @@ namespace {
 constexpr int kCclCtas = 8;
 constexpr int kCclThreads = 1024;
 constexpr int kCclAll = kCclCtas * kCclThreads;                       // 8192 threads per frame
-constexpr int kCclChunk = (kCartCells + kCclCtas - 1) / kCclCtas;     // 7813 cells per CTA (contiguous)
-constexpr int kCclPerThread = (kCclChunk + kCclThreads - 1) / kCclThreads;  // 8
+constexpr int kCclPerThread = 8;                                       // 32 rows x 250 cells / 1024 threads, rounded up
 
 // component_clustering.cpp:40-48
 __device__ __forceinline__ unsigned cart_cell(float x, float y, float roi) {
@@ -64,6 +63,7 @@ cart_cells_kernel(const float4* __restrict__ elev, const int* __restrict__ count
   if (i < counters[CNT_N_ELEV]) { const float4 q = __ldg(&elev[i]); cart[i] = (uint16_t)cart_cell(q.x, q.y, roi); }
 }
 
+// ---- union-find with root = smallest index (global-memory and shared-memory flavours) ----------------------
 __device__ __forceinline__ int uf_find(volatile int* L, int x) {
   int p = L[x];
   while (p != x) { x = p; p = L[x]; }
@@ -82,82 +82,132 @@ __device__ __forceinline__ void uf_union(volatile int* L, int* Lw, int a, int b)
   }
 }
 
+constexpr int kTileRows = 32;                  // 8 CTAs x 32 rows cover the 250 rows of the grid
+constexpr int kRowPitch = 256;                 // shared-memory row pitch (250 columns used)
+constexpr int kSeedRows = kTileRows + 3;       // rows ts-2 .. ts+32
+constexpr int kOccRows = kTileRows + 1;        // rows ts-1 .. ts+31
+constexpr int kCclSmem = kSeedRows * kRowPitch + kOccRows * kRowPitch + kTileRows * kRowPitch * (int)sizeof(int);
+
+// One thread-block cluster per frame; CTA r owns grid rows [32r, 32r+32).  Each CTA labels its tile entirely in shared
+// memory (pointer chasing at ~30 cycles instead of ~600 through L2), only the 7 tile borders are merged through
+// global memory, and the per-CTA root counts travel through distributed shared memory.
 __global__ void __cluster_dims__(kCclCtas, 1, 1) __launch_bounds__(kCclThreads, 1)
-ccl_cluster_kernel(int* __restrict__ count, uint8_t* __restrict__ seed, int* L, int* rid, int* __restrict__ out,
-                   int* __restrict__ counters) {
+ccl_cluster_kernel(int* __restrict__ count, int* G, int* rid, int* __restrict__ out, int* __restrict__ counters) {
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
-  const int tid = threadIdx.x;
-  const int gtid = crank * kCclThreads + tid;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  extern __shared__ unsigned char ccl_smem[];
+  uint8_t* s_seed = ccl_smem;                                         // [35][256] count > 1, rows ts-2..ts+32
+  uint8_t* s_occ = s_seed + kSeedRows * kRowPitch;                    // [33][256] dilated,   rows ts-1..ts+31
+  int* s_L = reinterpret_cast<int*>(s_occ + kOccRows * kRowPitch);    // [32][256] local parent (local index) or -1
   __shared__ int s_warp[32];
   __shared__ int s_tot[kCclCtas];
+  const int ts = crank * kTileRows;
+  const int rows = min(kTileRows, kNumGrid - ts);                     // 32, last tile 26
 
-  // P0: seed = count > 1 (component_clustering.cpp:136); the count grid is zeroed for the next frame
-  for (int k = gtid; k < kCartCells; k += kCclAll) {
-    seed[k] = count[k] > 1 ? 1 : 0;
-    count[k] = 0;
+  // A: seed = count > 1 (component_clustering.cpp:136) for the tile and its halo
+  for (int l = tid; l < kSeedRows * kRowPitch; l += kCclThreads) {
+    const int x = ts - 2 + (l >> 8), y = l & 255;
+    uint8_t sd = 0;
+    if (x >= 0 && x < kNumGrid && y < kNumGrid) sd = __ldcg(&count[x * kNumGrid + y]) > 1 ? 1 : 0;
+    s_seed[l] = sd;
   }
-  cluster.sync();
-
-  // P1: occupied = seed dilated 3x3, clipped at the border (:137-214); parent = self
-  for (int k = gtid; k < kCartCells; k += kCclAll) {
-    const int x = k / kNumGrid, y = k % kNumGrid;
-    int occ = 0;
-#pragma unroll
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int xx = x + dx;
-      if (xx < 0 || xx >= kNumGrid) continue;
-#pragma unroll
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int yy = y + dy;
-        if (yy < 0 || yy >= kNumGrid) continue;
-        occ |= __ldcg(&seed[xx * kNumGrid + yy]);
-      }
+  __syncthreads();
+  // B: occupied = seed dilated 3x3, clipped at the border (:137-214), rows ts-1 .. ts+31
+  for (int l = tid; l < kOccRows * kRowPitch; l += kCclThreads) {
+    const int orow = l >> 8, y = l & 255;
+    const int x = ts - 1 + orow;
+    uint8_t occ = 0;
+    if (x >= 0 && x < kNumGrid && y < kNumGrid) {
+      const uint8_t* c = s_seed + (orow + 1) * kRowPitch + y;         // seed row of x
+      const int ym = y > 0 ? -1 : 0, yp = y < kNumGrid - 1 ? 1 : 0;   // s_seed rows outside the grid are zero
+      occ = c[ym] | c[0] | c[yp] | c[-kRowPitch + ym] | c[-kRowPitch] | c[-kRowPitch + yp] | c[kRowPitch + ym] | c[kRowPitch] |
+            c[kRowPitch + yp];
     }
-    L[k] = occ ? k : -1;
+    s_occ[l] = occ;
   }
-  cluster.sync();
-
-  // P2: 8-connectivity (:228-244): union with the four neighbours that precede the cell in raster order
+  __syncthreads();
+  // C1: label = start of the horizontal run inside the 32-cell warp chunk
+  for (int task = warp; task < kTileRows * 8; task += kCclThreads / 32) {
+    const int lx = task >> 3, y = ((task & 7) << 5) + lane;
+    const bool o = lx < rows && s_occ[(lx + 1) * kRowPitch + y];
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, o);
+    const unsigned zb = ~mask & ((1u << lane) - 1u);                  // empty cells below this lane
+    const int start = zb ? (32 - __clz(zb)) : 0;
+    s_L[lx * kRowPitch + y] = o ? (lx * kRowPitch + (y - lane) + start) : -1;
+  }
+  __syncthreads();
+  // C2/C3: runs continuing across chunk boundaries, and 8-connectivity to the row above inside the tile.  A cell only
+  // needs the unions its left neighbour cannot have made: with N occupied, skip when W and NW are occupied too; with
+  // N empty, NW only if W is empty, NE always.
   {
-    volatile int* Lv = L;
-    for (int k = gtid; k < kCartCells; k += kCclAll) {
-      if (Lv[k] < 0) continue;
-      const int x = k / kNumGrid, y = k % kNumGrid;
-      if (y > 0 && Lv[k - 1] >= 0) uf_union(Lv, L, k, k - 1);
-      if (x > 0) {
-        const int u = k - kNumGrid;
-        if (Lv[u] >= 0) uf_union(Lv, L, k, u);
+    volatile int* Lv = s_L;
+    for (int l = tid; l < kTileRows * kRowPitch; l += kCclThreads) {
+      const int lx = l >> 8, y = l & 255;
+      if (lx >= rows || y >= kNumGrid || !s_occ[(lx + 1) * kRowPitch + y]) continue;
+      const uint8_t* o = s_occ + (lx + 1) * kRowPitch + y;
+      const bool W = y > 0 && o[-1];
+      if ((y & 31) == 0 && W) uf_union(Lv, s_L, l, l - 1);
+      if (lx > 0) {
+        const bool N = o[-kRowPitch], NW = y > 0 && o[-kRowPitch - 1], NE = y < kNumGrid - 1 && o[-kRowPitch + 1];
+        if (N) { if (!(W && NW)) uf_union(Lv, s_L, l, l - kRowPitch); }
         else {
-          // (x-1,y-1) and (x-1,y+1) are both adjacent to (x-1,y) when that one is occupied
-          if (y > 0 && Lv[u - 1] >= 0) uf_union(Lv, L, k, u - 1);
-          if (y < kNumGrid - 1 && Lv[u + 1] >= 0) uf_union(Lv, L, k, u + 1);
+          if (NW && !W) uf_union(Lv, s_L, l, l - kRowPitch - 1);
+          if (NE) uf_union(Lv, s_L, l, l - kRowPitch + 1);
         }
       }
     }
   }
+  __syncthreads();
+  // D: flatten inside the tile; publish the tile-local root as a GLOBAL linear index
+  {
+    volatile int* Lv = s_L;
+    for (int l = tid; l < kTileRows * kRowPitch; l += kCclThreads) {
+      const int lx = l >> 8, y = l & 255;
+      if (lx >= rows || y >= kNumGrid) continue;
+      int g = -1;
+      if (Lv[l] >= 0) { const int r = uf_find(Lv, l); g = (ts + (r >> 8)) * kNumGrid + (r & 255); }
+      G[(ts + lx) * kNumGrid + y] = g;
+    }
+  }
   cluster.sync();
-
-  // P3: flatten; count roots of this CTA's contiguous chunk, thread t owns kCclPerThread consecutive cells
-  const int cbeg = crank * kCclChunk, cend = min(cbeg + kCclChunk, kCartCells);
+  // every CTA has read its halo: zero this tile's counts for the next frame
+  for (int l = tid; l < rows * kNumGrid; l += kCclThreads) count[ts * kNumGrid + l] = 0;
+  // E: merge across the tile border (first row of the tile against the last row of the previous tile), same rule
+  if (crank > 0 && tid < kNumGrid) {
+    const int y = tid;
+    const uint8_t* o = s_occ + 1 * kRowPitch + y;                     // row ts
+    if (o[0]) {
+      volatile int* Gv = G;
+      const int k = ts * kNumGrid + y;
+      const bool W = y > 0 && o[-1];
+      const bool N = o[-kRowPitch], NW = y > 0 && o[-kRowPitch - 1], NE = y < kNumGrid - 1 && o[-kRowPitch + 1];
+      if (N) { if (!(W && NW)) uf_union(Gv, G, k, k - kNumGrid); }
+      else {
+        if (NW && !W) uf_union(Gv, G, k, k - kNumGrid - 1);
+        if (NE) uf_union(Gv, G, k, k - kNumGrid + 1);
+      }
+    }
+  }
+  cluster.sync();
+  // F: final flatten; roots of this tile in linear order, thread t owns kCclPerThread consecutive cells
+  const int cbeg = ts * kNumGrid, cend = cbeg + rows * kNumGrid;
   const int tbeg = cbeg + tid * kCclPerThread;
   int roots = 0;
   unsigned rootmask = 0;
   {
-    volatile int* Lv = L;
+    volatile int* Gv = G;
 #pragma unroll
     for (int j = 0; j < kCclPerThread; ++j) {
       const int k = tbeg + j;
-      if (k < cend && Lv[k] >= 0) {
-        const int r = uf_find(Lv, k);
-        Lv[k] = r;
+      if (k < cend && Gv[k] >= 0) {
+        const int r = uf_find(Gv, k);
+        Gv[k] = r;
         if (r == k) { ++roots; rootmask |= 1u << j; }
       }
     }
   }
-  // block exclusive scan of `roots`
   int incl = roots;
-  const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
   if (lane == 31) s_warp[warp] = incl;
@@ -168,10 +218,8 @@ ccl_cluster_kernel(int* __restrict__ count, uint8_t* __restrict__ seed, int* L, 
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += t; }
     s_warp[lane] = wi - v;
-    if (lane == 31) {
-      // publish this CTA's root count into every CTA's s_tot through distributed shared memory
+    if (lane == 31)       // publish this CTA's root count into every CTA's s_tot through distributed shared memory
       for (int r = 0; r < kCclCtas; ++r) cluster.map_shared_rank(s_tot, r)[crank] = wi;
-    }
   }
   __syncthreads();
   const int excl_in_cta = s_warp[warp] + incl - roots;
@@ -185,13 +233,12 @@ ccl_cluster_kernel(int* __restrict__ count, uint8_t* __restrict__ seed, int* L, 
     for (int j = 0; j < kCclPerThread; ++j)
       if (rootmask & (1u << j)) rid[tbeg + j] = ++rank;      // id = 1 + rank in raster order (:247-257)
   }
-  if (gtid == 0) counters[CNT_NUM_CLUSTER] = total;
+  if (crank == 0 && tid == 0) counters[CNT_NUM_CLUSTER] = total;
   cluster.sync();
-
-  // P4: label grid
-  for (int k = gtid; k < kCartCells; k += kCclAll) {
-    const int r = __ldcg(&L[k]);
-    out[k] = r >= 0 ? __ldcg(&rid[r]) : 0;
+  // G: label grid
+  for (int l = tid; l < rows * kNumGrid; l += kCclThreads) {
+    const int r = __ldcg(&G[cbeg + l]);
+    out[cbeg + l] = r >= 0 ? __ldcg(&rid[r]) : 0;
   }
 }
 
@@ -207,6 +254,7 @@ int cluster_alloc(Ctx* c) {
   LMOT_CUDA(c, cudaMalloc(&c->d_label_grid, kCartCells * sizeof(int)));
   LMOT_CUDA(c, cudaMemsetAsync(c->d_count, 0, kCartCells * sizeof(int), c->stream));
   LMOT_CUDA(c, cudaMemsetAsync(c->d_label_grid, 0, kCartCells * sizeof(int), c->stream));
+  LMOT_CUDA(c, cudaFuncSetAttribute(ccl_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCclSmem));
   return LMOT_OK;
 }
 
@@ -220,8 +268,8 @@ int cluster_launch(Ctx* c, int n_upper) {
   if (n_upper > 0)
     cart_count_kernel<<<(n_upper + 255) / 256, 256, 0, c->stream>>>(c->d_elev, c->d_counters, c->prm.roi_m, c->d_cart,
                                                                     c->d_count);
-  ccl_cluster_kernel<<<kCclCtas, kCclThreads, 0, c->stream>>>(c->d_count, c->d_seed, c->d_parent, c->d_rid,
-                                                              c->d_label_grid, c->d_counters);
+  ccl_cluster_kernel<<<kCclCtas, kCclThreads, kCclSmem, c->stream>>>(c->d_count, c->d_parent, c->d_rid, c->d_label_grid,
+                                                                     c->d_counters);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }
