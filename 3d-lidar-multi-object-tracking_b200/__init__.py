@@ -47,6 +47,7 @@ class Params(C.Structure):
         ("min_cluster_points", C.c_int), ("rule_filter", C.c_int),
         ("oracle_compat_first_frame", C.c_int),
         ("max_points", C.c_int), ("max_clusters", C.c_int), ("max_boxes", C.c_int), ("max_tracks", C.c_int),
+        ("pipeline_depth", C.c_int),
     ]
 
 
@@ -69,7 +70,8 @@ class FrameOut(C.Structure):
 ABI_SYMBOLS = [
     "lmot_default_params", "lmot_create", "lmot_destroy", "lmot_strerror", "lmot_last_error", "lmot_build_info",
     "lmot_set_stream", "lmot_ground_remove", "lmot_component_cluster", "lmot_box_fit", "lmot_track_step", "lmot_frame",
-    "lmot_frame_dev", "lmot_frame_fetch", "lmot_ground_remove_dev", "lmot_detect_dev", "lmot_sync",
+    "lmot_frame_dev", "lmot_frame_fetch", "lmot_frame_submit", "lmot_frame_collect", "lmot_frames_in_flight", "lmot_flush",
+    "lmot_ground_remove_dev", "lmot_detect_dev", "lmot_sync",
     "lmot_tracker_reset", "lmot_tracker_num_tracks", "lmot_tracker_dump", "lmot_tracker_load",
     "lmot_debug_polar_grid", "lmot_debug_cell_index", "lmot_debug_label_grid", "lmot_selftest_atan2f",
     "lmot_enable_timing", "lmot_last_stage_ms",
@@ -235,6 +237,35 @@ class Lmot:
     def frame_dev(self, d_ptr: int, n: int, timestamp_us, v_gps=0.0, yaw_gps=0.0):
         """Asynchronous: device-resident XYZI frame (stride 4) through all four stages on the context's stream."""
         self._chk(self.lib.lmot_frame_dev(self.h, C.c_void_p(d_ptr), n, C.c_double(timestamp_us), C.c_double(v_gps), C.c_double(yaw_gps)))
+
+    def flush(self):
+        """Device-side join: the caller stream waits for everything submitted so far."""
+        self._chk(self.lib.lmot_flush(self.h))
+
+    def frame_submit(self, points, timestamp_us, v_gps=0.0, yaw_gps=0.0):
+        """Asynchronous host frame (pinned memory recommended); collect results later with frame_collect()."""
+        p, n, s = _pts(points)
+        self._chk(self.lib.lmot_frame_submit(self.h, _fp(p), n, s, C.c_double(timestamp_us), C.c_double(v_gps), C.c_double(yaw_gps)))
+
+    def frame_collect(self, cap: int | None = None, want_boxes: bool = True):
+        """Results of the oldest submitted frame (blocks until it is done)."""
+        cap = cap or self.params.max_tracks
+        fo = FrameOut()
+        boxes = np.zeros((self.params.max_boxes, 8, 3), np.float32)
+        if want_boxes:
+            fo.boxes = _fp(boxes)
+        fo.max_boxes = self.params.max_boxes
+        to, bufs = self._track_out(cap)
+        fo.tracks = to
+        self._chk(self.lib.lmot_frame_collect(self.h, C.byref(fo)))
+        r = self._track_result(fo.tracks, bufs)
+        r.update(n_elevated=fo.n_elevated, n_ground=fo.n_ground, num_cluster=fo.num_cluster, boxes=boxes[: fo.n_boxes].copy())
+        return r
+
+    def frames_in_flight(self) -> int:
+        n = C.c_int(0)
+        self._chk(self.lib.lmot_frames_in_flight(self.h, C.byref(n)))
+        return n.value
 
     def detect_dev(self, d_ptr: int, n: int):
         self._chk(self.lib.lmot_detect_dev(self.h, C.c_void_p(d_ptr), n))

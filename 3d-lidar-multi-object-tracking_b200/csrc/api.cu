@@ -1,6 +1,11 @@
 // api.cu -- the extern "C" boundary declared in include/lmot.h.  Host-side marshalling only: H2D/D2H copies,
-// stream ordering and capacity checks; every algorithmic step is a CUDA kernel in ground.cu / cluster.cu /
-// boxfit.cu / tracker.cu.  There is deliberately no CPU implementation of any stage here.
+// stream/event ordering of the frame pipeline and capacity checks; every algorithmic step is a CUDA kernel in
+// ground.cu / cluster.cu / boxfit.cu / tracker.cu.  There is deliberately no CPU implementation of any stage here.
+//
+// Frame pipeline: a context owns `pipeline_depth` detection slots (own stream + own buffers each) and one tracker
+// stream.  Frame f runs ground -> cluster -> box on slot f % depth; the tracker stream waits for the slot's boxes,
+// folds them into the track table, and releases the slot.  Results (counts, boxes, per-track outputs) are stored by
+// the kernels straight into the slot's pinned, device-mapped host block; the host only waits on an event.
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -13,7 +18,6 @@ using namespace lmot;
 struct lmot_ctx {
   Ctx c;
 };
-
 
 namespace {
 
@@ -30,49 +34,184 @@ void gauss_taps(double tap[3]) {
   for (int x = 0; x < samples; ++x) tap[x] /= sum;
 }
 
-int upload_points(Ctx* c, const float* points, int n, int stride, float4* d_dst) {
+int upload_points(Ctx* c, Slot* s, cudaStream_t st, const float* points, int n, int stride, float4* d_dst) {
   if (n < 0 || (n > 0 && !points) || stride < 3) return LMOT_ERR_INVALID;
   if (n > c->max_points) return LMOT_ERR_CAPACITY;
   if (n == 0) return LMOT_OK;
   if (stride == 4) {
-    LMOT_CUDA(c, cudaMemcpyAsync(d_dst, points, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    LMOT_CUDA(c, cudaMemcpyAsync(d_dst, points, (size_t)n * 16, cudaMemcpyHostToDevice, st));
   } else {
     if (stride > 4) {  // wide host records: pack xyz on the host side of the copy
       std::vector<float> tmp((size_t)n * 3);
       for (int i = 0; i < n; ++i) { tmp[3*i] = points[(size_t)i*stride]; tmp[3*i+1] = points[(size_t)i*stride+1]; tmp[3*i+2] = points[(size_t)i*stride+2]; }
-      LMOT_CUDA(c, cudaMemcpyAsync(c->d_stage_in, tmp.data(), (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
-      LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+      LMOT_CUDA(c, cudaMemcpyAsync(s->d_stage_in, tmp.data(), (size_t)n * 12, cudaMemcpyHostToDevice, st));
+      LMOT_CUDA(c, cudaStreamSynchronize(st));
       stride = 3;
     } else {
-      LMOT_CUDA(c, cudaMemcpyAsync(c->d_stage_in, points, (size_t)n * stride * 4, cudaMemcpyHostToDevice, c->stream));
+      LMOT_CUDA(c, cudaMemcpyAsync(s->d_stage_in, points, (size_t)n * stride * 4, cudaMemcpyHostToDevice, st));
     }
-    int rc = ground_repack(c, c->d_stage_in, n, stride, d_dst);
+    int rc = ground_repack(c, st, s->d_stage_in, n, stride, d_dst);
     if (rc) return rc;
   }
   return LMOT_OK;
 }
 
-int fetch_counters(Ctx* c) {
-  LMOT_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+int fetch_counters(Ctx* c, Slot* s, cudaStream_t st) {
+  LMOT_CUDA(c, cudaMemcpyAsync(s->h_counters, s->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+  LMOT_CUDA(c, cudaStreamSynchronize(st));
   return LMOT_OK;
 }
 
-// write host-known counts into the device counter block (stage entry points that start mid-pipeline)
-int set_counter(Ctx* c, int which, int value) {
-  c->h_set[which] = value;
-  LMOT_CUDA(c, cudaMemcpyAsync(c->d_counters + which, c->h_set + which, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+// write a host-known count into the slot's device counter block (entry points that start mid-pipeline)
+int set_counter(Ctx* c, Slot* s, cudaStream_t st, int which, int value) {
+  s->h_set[which] = value;
+  LMOT_CUDA(c, cudaMemcpyAsync(s->d_counters + which, s->h_set + which, sizeof(int), cudaMemcpyHostToDevice, st));
   return LMOT_OK;
 }
 
-int check_device_error(Ctx* c) {
-  const int e = c->h_counters[CNT_ERROR];
+int check_device_error(Ctx* c, Slot* s, cudaStream_t st) {
+  const int e = s->h_counters[CNT_ERROR];
   if (e != 0) {
-    set_counter(c, CNT_ERROR, 0);
-    cudaStreamSynchronize(c->stream);
+    set_counter(c, s, st, CNT_ERROR, 0);
+    cudaStreamSynchronize(st);
     return e;
   }
   return LMOT_OK;
+}
+
+// wait until nothing of this context is running on the device and forget uncollected results
+int drain(Ctx* c) {
+  for (int i = 0; i < c->n_slots; ++i) LMOT_CUDA(c, cudaStreamSynchronize(c->slots[i].stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->trk_stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < c->n_slots; ++i) c->slots[i].in_flight = false;
+  c->n_in_flight = 0;
+  c->oldest = c->next_slot;
+  return LMOT_OK;
+}
+
+// next slot of the ring; an uncollected result that is still sitting in it is dropped
+Slot* acquire_slot(Ctx* c) {
+  Slot* s = &c->slots[c->next_slot];
+  if (s->in_flight) {
+    s->in_flight = false;
+    --c->n_in_flight;
+    c->oldest = (c->next_slot + 1) % c->n_slots;
+  }
+  c->last_slot = c->next_slot;
+  c->next_slot = (c->next_slot + 1) % c->n_slots;
+  return s;
+}
+
+// the asynchronous frame: detection on the slot stream, tracker on the tracker stream
+int submit(Ctx* c, Slot* s, const float4* d_pts, int n, bool with_tracker, double ts, double v, double yaw) {
+  int rc;
+  // the slot's previous boxes / counters / host block must have been consumed by the tracker
+  LMOT_CUDA(c, cudaStreamWaitEvent(s->stream, s->ev_trk_done, 0));
+  if (c->timing) cudaEventRecord(s->ev[0], s->stream);
+  if ((rc = ground_launch(c, s, s->stream, d_pts, n))) return rc;
+  if (c->timing) cudaEventRecord(s->ev[1], s->stream);
+  if ((rc = cluster_launch(c, s, s->stream, n))) return rc;
+  if (c->timing) cudaEventRecord(s->ev[2], s->stream);
+  if ((rc = boxfit_launch(c, s, s->stream, n))) return rc;
+  if (c->timing) cudaEventRecord(s->ev[3], s->stream);
+  LMOT_CUDA(c, cudaEventRecord(s->ev_det_done, s->stream));
+  if (with_tracker) {
+    LMOT_CUDA(c, cudaStreamWaitEvent(c->trk_stream, s->ev_det_done, 0));
+    if ((rc = tracker_launch(c, s, c->trk_stream, s->d_boxes, s->d_counters, ts, v, yaw))) return rc;
+    if (c->timing) cudaEventRecord(s->ev[4], c->trk_stream);
+    LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, c->trk_stream));
+  } else {
+    LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, s->stream));
+  }
+  s->has_tracks = with_tracker;
+  if (!s->in_flight) { s->in_flight = true; ++c->n_in_flight; }
+  return LMOT_OK;
+}
+
+int copy_track_outputs(const Slot* s, lmot_track_out* out) {
+  const int T = s->h_hdr[HDR_N_TRACKS], nv = s->h_hdr[HDR_N_VIS];
+  if (!out) return LMOT_OK;
+  out->n_tracks = T; out->n_vis = nv;
+  const int n = T < out->cap ? T : out->cap;
+  const int nvc = nv < out->cap ? nv : out->cap;
+  if (n > 0) {
+    if (out->targets) memcpy(out->targets, s->h_targets, (size_t)n * 3 * sizeof(float));
+    if (out->vandyaw) memcpy(out->vandyaw, s->h_vandyaw, (size_t)n * 2 * sizeof(double));
+    if (out->track_manage) memcpy(out->track_manage, s->h_manage, (size_t)n * sizeof(int));
+    if (out->is_static) memcpy(out->is_static, s->h_static, (size_t)n);
+    if (out->is_vis) memcpy(out->is_vis, s->h_vis, (size_t)n);
+  }
+  if (nvc > 0 && out->vis_bb) memcpy(out->vis_bb, s->h_visbb, (size_t)nvc * 24 * sizeof(float));
+  return (T > out->cap) ? LMOT_ERR_CAPACITY : LMOT_OK;
+}
+
+// results of a finished slot from its pinned host block
+int collect_slot(Ctx* c, Slot* s, lmot_frame_out* out) {
+  LMOT_CUDA(c, cudaEventSynchronize(s->ev_trk_done));
+  if (c->timing && s->has_tracks) for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&c->stage_ms[i], s->ev[i], s->ev[i + 1]);
+  if (!s->has_tracks) {   // detect only: no kernel wrote the header
+    int rc = fetch_counters(c, s, s->stream);
+    if (rc) return rc;
+    s->h_hdr[HDR_N_ELEV] = s->h_counters[CNT_N_ELEV]; s->h_hdr[HDR_N_GROUND] = s->h_counters[CNT_N_GROUND];
+    s->h_hdr[HDR_NUM_CLUSTER] = s->h_counters[CNT_NUM_CLUSTER]; s->h_hdr[HDR_N_BOXES] = s->h_counters[CNT_N_BOXES];
+    s->h_hdr[HDR_N_TRACKS] = 0; s->h_hdr[HDR_N_VIS] = 0; s->h_hdr[HDR_ERROR] = s->h_counters[CNT_ERROR];
+    if (s->h_counters[CNT_ERROR]) { set_counter(c, s, s->stream, CNT_ERROR, 0); cudaStreamSynchronize(s->stream); }
+  }
+  const int err = s->h_hdr[HDR_ERROR];
+  if (out) {
+    out->n_elevated = s->h_hdr[HDR_N_ELEV]; out->n_ground = s->h_hdr[HDR_N_GROUND];
+    out->num_cluster = s->h_hdr[HDR_NUM_CLUSTER]; out->n_boxes = s->h_hdr[HDR_N_BOXES];
+    const int nb = out->n_boxes < out->max_boxes ? out->n_boxes : out->max_boxes;
+    if (out->boxes && nb > 0) memcpy(out->boxes, s->h_boxes, (size_t)nb * 24 * sizeof(float));
+    const int rc = copy_track_outputs(s, &out->tracks);
+    if (rc && !err) return rc;
+  }
+  return err ? err : LMOT_OK;
+}
+
+int slot_create(Ctx* c, Slot* s, int index) {
+  s->index = index;
+  LMOT_CUDA(c, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  LMOT_CUDA(c, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+  LMOT_CUDA(c, cudaEventCreateWithFlags(&s->ev_det_done, cudaEventDisableTiming));
+  LMOT_CUDA(c, cudaEventCreateWithFlags(&s->ev_trk_done, cudaEventDisableTiming));
+  for (int i = 0; i < 5; ++i) LMOT_CUDA(c, cudaEventCreate(&s->ev[i]));
+  int rc = ground_alloc(c, s);
+  if (rc == LMOT_OK) rc = cluster_alloc(c, s);
+  if (rc == LMOT_OK) rc = boxfit_alloc(c, s);
+  if (rc) return rc;
+  const int TC = c->prm.max_tracks, MB = c->prm.max_boxes;
+  const unsigned fl = cudaHostAllocMapped;
+  LMOT_CUDA(c, cudaHostAlloc(&s->h_hdr, HDR_COUNT * sizeof(int), fl));
+  memset(s->h_hdr, 0, HDR_COUNT * sizeof(int));
+  LMOT_CUDA(c, cudaHostAlloc(&s->h_boxes, (size_t)MB * 24 * sizeof(float), fl));
+  LMOT_CUDA(c, cudaHostAlloc(&s->h_targets, (size_t)TC * 3 * sizeof(float), fl));
+  LMOT_CUDA(c, cudaHostAlloc(&s->h_vandyaw, (size_t)TC * 2 * sizeof(double), fl));
+  LMOT_CUDA(c, cudaHostAlloc(&s->h_manage, (size_t)TC * sizeof(int), fl));
+  LMOT_CUDA(c, cudaHostAlloc(&s->h_static, (size_t)TC, fl));
+  LMOT_CUDA(c, cudaHostAlloc(&s->h_vis, (size_t)TC, fl));
+  LMOT_CUDA(c, cudaHostAlloc(&s->h_visbb, (size_t)TC * 24 * sizeof(float), fl));
+  LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, s->stream));   // "free" from the start
+  LMOT_CUDA(c, cudaEventRecord(s->ev_det_done, s->stream));
+  return LMOT_OK;
+}
+
+void slot_destroy(Slot* s) {
+  ground_free(s); cluster_free(s); boxfit_free(s);
+  if (s->h_hdr) cudaFreeHost(s->h_hdr);
+  if (s->h_boxes) cudaFreeHost(s->h_boxes);
+  if (s->h_targets) cudaFreeHost(s->h_targets);
+  if (s->h_vandyaw) cudaFreeHost(s->h_vandyaw);
+  if (s->h_manage) cudaFreeHost(s->h_manage);
+  if (s->h_static) cudaFreeHost(s->h_static);
+  if (s->h_vis) cudaFreeHost(s->h_vis);
+  if (s->h_visbb) cudaFreeHost(s->h_visbb);
+  for (int i = 0; i < 5; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+  if (s->ev_det_done) cudaEventDestroy(s->ev_det_done);
+  if (s->ev_trk_done) cudaEventDestroy(s->ev_trk_done);
+  if (s->stream) cudaStreamDestroy(s->stream);
 }
 
 }  // namespace
@@ -92,6 +231,7 @@ int lmot_default_params(lmot_params* p) {
   p->rule_filter = LMOT_RULE_INTENDED;
   p->oracle_compat_first_frame = 1;
   p->max_points = 1 << 20; p->max_clusters = 4096; p->max_boxes = 1024; p->max_tracks = 8192;
+  p->pipeline_depth = 4;
   return LMOT_OK;
 }
 
@@ -116,6 +256,9 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   lmot_params p;
   if (params) p = *params; else lmot_default_params(&p);
   if (p.max_points <= 0 || p.max_clusters <= 0 || p.max_boxes <= 0 || p.max_tracks <= 0) return LMOT_ERR_INVALID;
+  if (p.max_clusters > 65534 || p.max_boxes > 65535) return LMOT_ERR_INVALID;   // u16 cluster ids / box indices
+  if (p.pipeline_depth < 1) p.pipeline_depth = 1;
+  if (p.pipeline_depth > kMaxSlots) p.pipeline_depth = kMaxSlots;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return LMOT_ERR_CUDA;
   if (cudaSetDevice(device) != cudaSuccess) return LMOT_ERR_CUDA;
@@ -125,20 +268,21 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   c->prm = p;
   c->device = device;
   c->max_points = p.max_points;
+  c->n_slots = p.pipeline_depth;
   c->gp.r_min = p.r_min; c->gp.r_max = p.r_max; c->gp.t_hmin = p.t_hmin; c->gp.t_hmax = p.t_hmax;
   c->gp.t_hdiff = p.t_hdiff; c->gp.h_sensor = p.h_sensor;
   { volatile float span = p.r_max - p.r_min; c->gp.r_span = span; }
   c->gp.tol = p.ground_tolerance;
   gauss_taps(c->gp.tap);
-  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return LMOT_ERR_CUDA; }
+  int rc = LMOT_OK;
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->trk_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return LMOT_ERR_CUDA; }
   c->stream = c->own_stream;
-  int rc = ground_alloc(c);
-  if (rc == LMOT_OK) rc = cluster_alloc(c);
-  if (rc == LMOT_OK) rc = boxfit_alloc(c);
+  rc = boxfit_alloc_shared(c);
+  for (int i = 0; i < c->n_slots && rc == LMOT_OK; ++i) rc = slot_create(c, &c->slots[i], i);
   if (rc == LMOT_OK) rc = tracker_alloc(c);
-  if (rc == LMOT_OK) rc = (cudaStreamSynchronize(c->stream) == cudaSuccess) ? LMOT_OK : LMOT_ERR_CUDA;
+  if (rc == LMOT_OK) rc = (cudaDeviceSynchronize() == cudaSuccess) ? LMOT_OK : LMOT_ERR_CUDA;
   if (rc != LMOT_OK) { lmot_destroy(h); return rc; }
-  for (int i = 0; i < 5; ++i) cudaEventCreate(&c->ev[i]);
   *out = h;
   return LMOT_OK;
 }
@@ -147,12 +291,11 @@ void lmot_destroy(lmot_ctx* ctx) {
   if (!ctx) return;
   Ctx* c = &ctx->c;
   cudaSetDevice(c->device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
-  ground_free(c);
-  cluster_free(c);
-  boxfit_free(c);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < c->n_slots; ++i) slot_destroy(&c->slots[i]);
   tracker_free(c);
-  for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  cudaFree(c->d_mt_raw);
+  if (c->trk_stream) cudaStreamDestroy(c->trk_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete ctx;
 }
@@ -165,14 +308,32 @@ int lmot_set_stream(lmot_ctx* ctx, void* s) {
 
 int lmot_sync(lmot_ctx* ctx) {
   if (!ctx) return LMOT_ERR_INVALID;
-  LMOT_CUDA(&ctx->c, cudaStreamSynchronize(ctx->c.stream));
+  Ctx* c = &ctx->c;
+  for (int i = 0; i < c->n_slots; ++i) LMOT_CUDA(c, cudaStreamSynchronize(c->slots[i].stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->trk_stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
   return LMOT_OK;
 }
 
+// make the caller's stream wait for everything submitted so far (so CUDA events recorded on it bracket the work)
+int lmot_flush(lmot_ctx* ctx) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  for (int i = 0; i < c->n_slots; ++i) {
+    LMOT_CUDA(c, cudaStreamWaitEvent(c->stream, c->slots[i].ev_det_done, 0));
+    LMOT_CUDA(c, cudaStreamWaitEvent(c->stream, c->slots[i].ev_trk_done, 0));
+  }
+  return LMOT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- stage entry points
 int lmot_ground_remove_dev(lmot_ctx* ctx, const float* d_points, int n) {
   if (!ctx || n < 0 || (n > 0 && !d_points)) return LMOT_ERR_INVALID;
-  if (n > ctx->c.max_points) return LMOT_ERR_CAPACITY;
-  return ground_launch(&ctx->c, reinterpret_cast<const float4*>(d_points), n);
+  Ctx* c = &ctx->c;
+  if (n > c->max_points) return LMOT_ERR_CAPACITY;
+  Slot* s = &c->slots[0];
+  c->last_slot = 0;
+  return ground_launch(c, s, c->stream, reinterpret_cast<const float4*>(d_points), n);
 }
 
 int lmot_ground_remove(lmot_ctx* ctx, const float* points, int n, int stride, uint8_t* labels, float* elevated,
@@ -180,19 +341,21 @@ int lmot_ground_remove(lmot_ctx* ctx, const float* points, int n, int stride, ui
   if (!ctx) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
   cudaSetDevice(c->device);
-  int rc = upload_points(c, points, n, stride, c->d_points);
+  int rc = drain(c);
   if (rc) return rc;
-  rc = ground_launch(c, c->d_points, n);
-  if (rc) return rc;
-  rc = fetch_counters(c);
-  if (rc) return rc;
-  const int ne = c->h_counters[CNT_N_ELEV], ng = c->h_counters[CNT_N_GROUND];
+  Slot* s = &c->slots[0];
+  c->last_slot = 0;
+  cudaStream_t st = c->stream;
+  if ((rc = upload_points(c, s, st, points, n, stride, s->d_points))) return rc;
+  if ((rc = ground_launch(c, s, st, s->d_points, n))) return rc;
+  if ((rc = fetch_counters(c, s, st))) return rc;
+  const int ne = s->h_counters[CNT_N_ELEV], ng = s->h_counters[CNT_N_GROUND];
   if (n_elevated) *n_elevated = ne;
   if (n_ground) *n_ground = ng;
-  if (labels && n > 0) LMOT_CUDA(c, cudaMemcpyAsync(labels, c->d_labels, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-  if (elevated && ne > 0) LMOT_CUDA(c, cudaMemcpyAsync(elevated, c->d_elev, (size_t)ne * 16, cudaMemcpyDeviceToHost, c->stream));
-  if (ground && ng > 0) LMOT_CUDA(c, cudaMemcpyAsync(ground, c->d_ground, (size_t)ng * 16, cudaMemcpyDeviceToHost, c->stream));
-  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (labels && n > 0) LMOT_CUDA(c, cudaMemcpyAsync(labels, s->d_labels, (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (elevated && ne > 0) LMOT_CUDA(c, cudaMemcpyAsync(elevated, s->d_elev, (size_t)ne * 16, cudaMemcpyDeviceToHost, st));
+  if (ground && ng > 0) LMOT_CUDA(c, cudaMemcpyAsync(ground, s->d_ground, (size_t)ng * 16, cudaMemcpyDeviceToHost, st));
+  LMOT_CUDA(c, cudaStreamSynchronize(st));
   return LMOT_OK;
 }
 
@@ -200,15 +363,19 @@ int lmot_component_cluster(lmot_ctx* ctx, const float* elevated, int n, int stri
   if (!ctx) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
   cudaSetDevice(c->device);
-  int rc = upload_points(c, elevated, n, stride, c->d_elev);
+  int rc = drain(c);
   if (rc) return rc;
-  if ((rc = set_counter(c, CNT_N_ELEV, n))) return rc;
-  if ((rc = cluster_launch(c, n))) return rc;
-  if ((rc = fetch_counters(c))) return rc;
-  if (num_cluster) *num_cluster = c->h_counters[CNT_NUM_CLUSTER];
+  Slot* s = &c->slots[0];
+  c->last_slot = 0;
+  cudaStream_t st = c->stream;
+  if ((rc = upload_points(c, s, st, elevated, n, stride, s->d_elev))) return rc;
+  if ((rc = set_counter(c, s, st, CNT_N_ELEV, n))) return rc;
+  if ((rc = cluster_launch(c, s, st, n))) return rc;
+  if ((rc = fetch_counters(c, s, st))) return rc;
+  if (num_cluster) *num_cluster = s->h_counters[CNT_NUM_CLUSTER];
   if (grid) {
-    LMOT_CUDA(c, cudaMemcpyAsync(grid, c->d_label_grid, kCartCells * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+    LMOT_CUDA(c, cudaMemcpyAsync(grid, s->d_label_grid, kCartCells * sizeof(int), cudaMemcpyDeviceToHost, st));
+    LMOT_CUDA(c, cudaStreamSynchronize(st));
   }
   return LMOT_OK;
 }
@@ -216,11 +383,13 @@ int lmot_component_cluster(lmot_ctx* ctx, const float* elevated, int n, int stri
 int lmot_debug_label_grid(lmot_ctx* ctx, int32_t* grid, int* num_cluster) {
   if (!ctx) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
-  int rc = fetch_counters(c);
+  int rc = lmot_sync(ctx);
   if (rc) return rc;
-  if (num_cluster) *num_cluster = c->h_counters[CNT_NUM_CLUSTER];
+  Slot* s = &c->slots[c->last_slot];
+  if ((rc = fetch_counters(c, s, c->stream))) return rc;
+  if (num_cluster) *num_cluster = s->h_counters[CNT_NUM_CLUSTER];
   if (grid) {
-    LMOT_CUDA(c, cudaMemcpyAsync(grid, c->d_label_grid, kCartCells * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LMOT_CUDA(c, cudaMemcpyAsync(grid, s->d_label_grid, kCartCells * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
   }
   return LMOT_OK;
@@ -232,52 +401,26 @@ int lmot_box_fit(lmot_ctx* ctx, const float* elevated, int n, int stride, const 
   Ctx* c = &ctx->c;
   cudaSetDevice(c->device);
   if (num_cluster > c->prm.max_clusters) return LMOT_ERR_CAPACITY;
-  int rc = upload_points(c, elevated, n, stride, c->d_elev);
+  int rc = drain(c);
   if (rc) return rc;
-  LMOT_CUDA(c, cudaMemcpyAsync(c->d_label_grid, grid, kCartCells * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  if ((rc = set_counter(c, CNT_N_ELEV, n))) return rc;
-  if ((rc = set_counter(c, CNT_NUM_CLUSTER, num_cluster))) return rc;
-  if ((rc = cluster_cells_only(c, n))) return rc;
-  if ((rc = boxfit_launch(c, n))) return rc;
-  if ((rc = fetch_counters(c))) return rc;
-  if ((rc = check_device_error(c))) return rc;
-  const int nb = c->h_counters[CNT_N_BOXES];
+  Slot* s = &c->slots[0];
+  c->last_slot = 0;
+  cudaStream_t st = c->stream;
+  if ((rc = upload_points(c, s, st, elevated, n, stride, s->d_elev))) return rc;
+  LMOT_CUDA(c, cudaMemcpyAsync(s->d_label_grid, grid, kCartCells * sizeof(int), cudaMemcpyHostToDevice, st));
+  if ((rc = set_counter(c, s, st, CNT_N_ELEV, n))) return rc;
+  if ((rc = set_counter(c, s, st, CNT_NUM_CLUSTER, num_cluster))) return rc;
+  if ((rc = cluster_cells_only(c, s, st, n))) return rc;
+  if ((rc = boxfit_launch(c, s, st, n))) return rc;
+  if ((rc = fetch_counters(c, s, st))) return rc;
+  if ((rc = check_device_error(c, s, st))) return rc;
+  const int nb = s->h_counters[CNT_N_BOXES];
   if (n_boxes) *n_boxes = nb;
   const int ncopy = nb < max_boxes ? nb : max_boxes;
-  if (boxes && ncopy > 0) LMOT_CUDA(c, cudaMemcpyAsync(boxes, c->d_boxes, (size_t)ncopy * 24 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  if (markers && ncopy > 0) LMOT_CUDA(c, cudaMemcpyAsync(markers, c->d_markers, (size_t)ncopy * 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (boxes && ncopy > 0) LMOT_CUDA(c, cudaMemcpyAsync(boxes, s->d_boxes, (size_t)ncopy * 24 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (markers && ncopy > 0) LMOT_CUDA(c, cudaMemcpyAsync(markers, s->d_markers, (size_t)ncopy * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  LMOT_CUDA(c, cudaStreamSynchronize(st));
   return nb > max_boxes ? LMOT_ERR_CAPACITY : LMOT_OK;
-}
-
-int lmot_detect_dev(lmot_ctx* ctx, const float* d_points, int n) {
-  if (!ctx || n < 0 || (n > 0 && !d_points)) return LMOT_ERR_INVALID;
-  Ctx* c = &ctx->c;
-  if (n > c->max_points) return LMOT_ERR_CAPACITY;
-  int rc = ground_launch(c, reinterpret_cast<const float4*>(d_points), n);
-  if (rc) return rc;
-  if ((rc = cluster_launch(c, n))) return rc;
-  return boxfit_launch(c, n);
-}
-
-// ---------------------------------------------------------------------------------------------- tracker
-static int fetch_track_outputs(Ctx* c, lmot_track_out* out) {
-  // h_counters already holds this frame's counters
-  const int T = c->h_counters[CNT_N_TRACKS], nv = c->h_counters[CNT_N_VIS];
-  if (!out) return LMOT_OK;
-  out->n_tracks = T; out->n_vis = nv;
-  const int n = T < out->cap ? T : out->cap;
-  const int nvc = nv < out->cap ? nv : out->cap;
-  if (n > 0) {
-    if (out->targets) LMOT_CUDA(c, cudaMemcpyAsync(out->targets, c->d_out_targets, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    if (out->vandyaw) LMOT_CUDA(c, cudaMemcpyAsync(out->vandyaw, c->d_out_vandyaw, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (out->track_manage) LMOT_CUDA(c, cudaMemcpyAsync(out->track_manage, c->d_out_manage, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    if (out->is_static) LMOT_CUDA(c, cudaMemcpyAsync(out->is_static, c->d_out_static, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-    if (out->is_vis) LMOT_CUDA(c, cudaMemcpyAsync(out->is_vis, c->d_out_vis, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-  }
-  if (nvc > 0 && out->vis_bb) LMOT_CUDA(c, cudaMemcpyAsync(out->vis_bb, c->d_out_visbb, (size_t)nvc * 24 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
-  return (T > out->cap) ? LMOT_ERR_CAPACITY : LMOT_OK;
 }
 
 int lmot_track_step(lmot_ctx* ctx, const float* boxes, int m, double timestamp_us, double v_gps, double yaw_gps,
@@ -286,70 +429,121 @@ int lmot_track_step(lmot_ctx* ctx, const float* boxes, int m, double timestamp_u
   Ctx* c = &ctx->c;
   cudaSetDevice(c->device);
   if (m > c->prm.max_boxes) return LMOT_ERR_CAPACITY;
-  if (m > 0) LMOT_CUDA(c, cudaMemcpyAsync(c->d_boxes_in, boxes, (size_t)m * 24 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  int rc = set_counter(c, CNT_N_BOXES, m);
+  int rc = drain(c);
   if (rc) return rc;
-  if ((rc = tracker_launch(c, c->d_boxes_in, timestamp_us, v_gps, yaw_gps))) return rc;
-  if ((rc = fetch_counters(c))) return rc;
-  if ((rc = check_device_error(c))) return rc;
-  return fetch_track_outputs(c, out);
+  Slot* s = &c->slots[0];
+  c->last_slot = 0;
+  cudaStream_t st = c->stream;
+  if (m > 0) LMOT_CUDA(c, cudaMemcpyAsync(s->d_boxes, boxes, (size_t)m * 24 * sizeof(float), cudaMemcpyHostToDevice, st));
+  if ((rc = set_counter(c, s, st, CNT_N_BOXES, m))) return rc;
+  if ((rc = tracker_launch(c, s, st, s->d_boxes, s->d_counters, timestamp_us, v_gps, yaw_gps))) return rc;
+  LMOT_CUDA(c, cudaStreamSynchronize(st));
+  const int err = s->h_hdr[HDR_ERROR];
+  rc = copy_track_outputs(s, out);
+  return err ? err : rc;
+}
+
+// ---------------------------------------------------------------------------------------------- frame pipeline
+int lmot_detect_dev(lmot_ctx* ctx, const float* d_points, int n) {
+  if (!ctx || n < 0 || (n > 0 && !d_points)) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  if (n > c->max_points) return LMOT_ERR_CAPACITY;
+  Slot* s = acquire_slot(c);
+  LMOT_CUDA(c, cudaEventRecord(s->ev_fork, c->stream));
+  LMOT_CUDA(c, cudaStreamWaitEvent(s->stream, s->ev_fork, 0));
+  return submit(c, s, reinterpret_cast<const float4*>(d_points), n, false, 0, 0, 0);
 }
 
 int lmot_frame_dev(lmot_ctx* ctx, const float* d_points, int n, double timestamp_us, double v_gps, double yaw_gps) {
   if (!ctx || n < 0 || (n > 0 && !d_points)) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
   if (n > c->max_points) return LMOT_ERR_CAPACITY;
-  int rc;
-  if (c->timing) cudaEventRecord(c->ev[0], c->stream);
-  if ((rc = ground_launch(c, reinterpret_cast<const float4*>(d_points), n))) return rc;
-  if (c->timing) cudaEventRecord(c->ev[1], c->stream);
-  if ((rc = cluster_launch(c, n))) return rc;
-  if (c->timing) cudaEventRecord(c->ev[2], c->stream);
-  if ((rc = boxfit_launch(c, n))) return rc;
-  if (c->timing) cudaEventRecord(c->ev[3], c->stream);
-  if ((rc = tracker_launch(c, c->d_boxes, timestamp_us, v_gps, yaw_gps))) return rc;
-  if (c->timing) cudaEventRecord(c->ev[4], c->stream);
+  Slot* s = acquire_slot(c);
+  LMOT_CUDA(c, cudaEventRecord(s->ev_fork, c->stream));          // the caller's stream produced d_points
+  LMOT_CUDA(c, cudaStreamWaitEvent(s->stream, s->ev_fork, 0));
+  return submit(c, s, reinterpret_cast<const float4*>(d_points), n, true, timestamp_us, v_gps, yaw_gps);
+}
+
+int lmot_frame_submit(lmot_ctx* ctx, const float* points, int n, int stride, double timestamp_us, double v_gps, double yaw_gps) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  if (c->n_in_flight >= c->n_slots) return LMOT_ERR_STATE;      // collect first: results would be overwritten
+  Slot* s = acquire_slot(c);
+  LMOT_CUDA(c, cudaStreamWaitEvent(s->stream, s->ev_trk_done, 0));
+  int rc = upload_points(c, s, s->stream, points, n, stride, s->d_points);
+  if (rc) return rc;
+  return submit(c, s, s->d_points, n, true, timestamp_us, v_gps, yaw_gps);
+}
+
+int lmot_frame_collect(lmot_ctx* ctx, lmot_frame_out* out) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  if (c->n_in_flight <= 0) return LMOT_ERR_STATE;
+  Slot* s = &c->slots[c->oldest];
+  int guard = 0;
+  while (!s->in_flight && guard++ < c->n_slots) { c->oldest = (c->oldest + 1) % c->n_slots; s = &c->slots[c->oldest]; }
+  if (!s->in_flight) return LMOT_ERR_STATE;
+  const int rc = collect_slot(c, s, out);
+  s->in_flight = false;
+  --c->n_in_flight;
+  c->oldest = (c->oldest + 1) % c->n_slots;
+  return rc;
+}
+
+int lmot_frames_in_flight(lmot_ctx* ctx, int* n) {
+  if (!ctx || !n) return LMOT_ERR_INVALID;
+  *n = ctx->c.n_in_flight;
   return LMOT_OK;
 }
 
+// results of the MOST RECENT submission; older uncollected ones are dropped
 int lmot_frame_fetch(lmot_ctx* ctx, lmot_frame_out* out) {
   if (!ctx) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
-  int rc = fetch_counters(c);
-  if (rc) return rc;
-  if (c->timing) for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
-  if ((rc = check_device_error(c))) return rc;
-  if (!out) return LMOT_OK;
-  out->n_elevated = c->h_counters[CNT_N_ELEV]; out->n_ground = c->h_counters[CNT_N_GROUND];
-  out->num_cluster = c->h_counters[CNT_NUM_CLUSTER]; out->n_boxes = c->h_counters[CNT_N_BOXES];
-  const int nb = out->n_boxes < out->max_boxes ? out->n_boxes : out->max_boxes;
-  if (out->boxes && nb > 0) LMOT_CUDA(c, cudaMemcpyAsync(out->boxes, c->d_boxes, (size_t)nb * 24 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  return fetch_track_outputs(c, &out->tracks);
+  Slot* s = &c->slots[c->last_slot];
+  const int rc = collect_slot(c, s, out);
+  for (int i = 0; i < c->n_slots; ++i) c->slots[i].in_flight = false;
+  c->n_in_flight = 0;
+  c->oldest = c->next_slot;
+  return rc;
 }
 
 int lmot_frame(lmot_ctx* ctx, const float* points, int n, int stride, double timestamp_us, double v_gps, double yaw_gps,
                lmot_frame_out* out) {
   if (!ctx) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
-  cudaSetDevice(c->device);
-  int rc = upload_points(c, points, n, stride, c->d_points);
+  if (c->n_in_flight > 0) { int rc = drain(c); if (rc) return rc; }
+  int rc = lmot_frame_submit(ctx, points, n, stride, timestamp_us, v_gps, yaw_gps);
   if (rc) return rc;
-  if ((rc = lmot_frame_dev(ctx, reinterpret_cast<const float*>(c->d_points), n, timestamp_us, v_gps, yaw_gps))) return rc;
-  return lmot_frame_fetch(ctx, out);
+  return lmot_frame_collect(ctx, out);
 }
 
+// ---------------------------------------------------------------------------------------------- tracker state
 int lmot_tracker_reset(lmot_ctx* ctx) {
   if (!ctx) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
+  int rc = drain(c);
+  if (rc) return rc;
   c->th = TrackerHost();
-  return set_counter(c, CNT_N_TRACKS, 0);
+  LMOT_CUDA(c, cudaMemsetAsync(c->d_trk_counters, 0, CNT_COUNT * sizeof(int), c->stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LMOT_OK;
+}
+
+static int fetch_trk_counters(Ctx* c) {
+  int rc = drain(c);
+  if (rc) return rc;
+  LMOT_CUDA(c, cudaMemcpyAsync(c->h_trk_counters, c->d_trk_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LMOT_OK;
 }
 
 int lmot_tracker_num_tracks(lmot_ctx* ctx, int* n) {
   if (!ctx || !n) return LMOT_ERR_INVALID;
-  int rc = fetch_counters(&ctx->c);
+  int rc = fetch_trk_counters(&ctx->c);
   if (rc) return rc;
-  *n = ctx->c.h_counters[CNT_N_TRACKS];
+  *n = ctx->c.h_trk_counters[CNT_N_TRACKS];
   return LMOT_OK;
 }
 
@@ -361,9 +555,9 @@ enum { D_TRACKNUM = 0, D_LIFETIME = 1, D_STATIC = 2, D_VIS = 3, D_X = 4, D_P = 2
 int lmot_tracker_dump(lmot_ctx* ctx, double* dumps, int cap, int* n_out) {
   if (!ctx || cap < 0) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
-  int rc = fetch_counters(c);
+  int rc = fetch_trk_counters(c);
   if (rc) return rc;
-  const int T = c->h_counters[CNT_N_TRACKS];
+  const int T = c->h_trk_counters[CNT_N_TRACKS];
   if (n_out) *n_out = T;
   const int n = T < cap ? T : cap;
   if (n == 0 || !dumps) return LMOT_OK;
@@ -394,6 +588,8 @@ int lmot_tracker_load(lmot_ctx* ctx, const double* dumps, int n, int init, doubl
   if (!ctx || n < 0 || (n > 0 && !dumps)) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
   if (n > c->prm.max_tracks) return LMOT_ERR_CAPACITY;
+  int rc = drain(c);
+  if (rc) return rc;
   std::vector<TrackState> h((size_t)(n > 0 ? n : 1));
   for (int i = 0; i < n; ++i) {
     TrackState& t = h[i];
@@ -411,31 +607,37 @@ int lmot_tracker_load(lmot_ctx* ctx, const double* dumps, int n, int init, doubl
     t.nBBox = (int)d[D_BBN]; for (int p = 0; p < t.nBBox && p < 8; ++p) for (int q = 0; q < 3; ++q) t.BBox[p][q] = (float)d[D_BB + 3 * p + q];
     t.nBest = (int)d[D_BESTBBN]; for (int p = 0; p < t.nBest && p < 8; ++p) for (int q = 0; q < 3; ++q) t.bestBBox[p][q] = (float)d[D_BESTBB + 3 * p + q];
   }
-  if (n > 0) {
-    LMOT_CUDA(c, cudaMemcpyAsync(c->d_tracks, h.data(), (size_t)n * sizeof(TrackState), cudaMemcpyHostToDevice, c->stream));
-    LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
-  }
+  if (n > 0) LMOT_CUDA(c, cudaMemcpyAsync(c->d_tracks, h.data(), (size_t)n * sizeof(TrackState), cudaMemcpyHostToDevice, c->stream));
+  c->h_trk_counters[CNT_N_TRACKS] = n;
+  LMOT_CUDA(c, cudaMemsetAsync(c->d_trk_counters, 0, CNT_COUNT * sizeof(int), c->stream));
+  LMOT_CUDA(c, cudaMemcpyAsync(c->d_trk_counters + CNT_N_TRACKS, c->h_trk_counters + CNT_N_TRACKS, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
   c->th = TrackerHost();
   c->th.init = init != 0; c->th.timestamp = timestamp_us; c->th.egoVelo = ego_velo; c->th.egoYaw = ego_yaw;
   c->th.egoPreYaw = ego_pre_yaw; c->th.egoPoint[2] = ego_point_yaw;
-  return set_counter(c, CNT_N_TRACKS, n);
+  return LMOT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- inspection
 int lmot_debug_polar_grid(lmot_ctx* ctx, float* minz, float* height, float* smoothed, float* hdiff, float* hground,
                           uint8_t* isground) {
   if (!ctx) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
+  int rc = lmot_sync(ctx);
+  if (rc) return rc;
+  Slot* s = &c->slots[c->last_slot];
+  cudaStream_t st = c->stream;
   const size_t b = kPolarCells * sizeof(float);
-  if (minz) LMOT_CUDA(c, cudaMemcpyAsync(minz, c->d_minz, b, cudaMemcpyDeviceToHost, c->stream));
-  if (height) LMOT_CUDA(c, cudaMemcpyAsync(height, c->d_height, b, cudaMemcpyDeviceToHost, c->stream));
-  if (smoothed) LMOT_CUDA(c, cudaMemcpyAsync(smoothed, c->d_smoothed, b, cudaMemcpyDeviceToHost, c->stream));
-  if (hdiff) LMOT_CUDA(c, cudaMemcpyAsync(hdiff, c->d_hdiff, b, cudaMemcpyDeviceToHost, c->stream));
+  if (minz) LMOT_CUDA(c, cudaMemcpyAsync(minz, s->d_minz, b, cudaMemcpyDeviceToHost, st));
+  if (height) LMOT_CUDA(c, cudaMemcpyAsync(height, s->d_height, b, cudaMemcpyDeviceToHost, st));
+  if (smoothed) LMOT_CUDA(c, cudaMemcpyAsync(smoothed, s->d_smoothed, b, cudaMemcpyDeviceToHost, st));
+  if (hdiff) LMOT_CUDA(c, cudaMemcpyAsync(hdiff, s->d_hdiff, b, cudaMemcpyDeviceToHost, st));
   std::vector<float> hg;
   if (hground || isground) {
     hg.resize(kPolarCells);
-    LMOT_CUDA(c, cudaMemcpyAsync(hg.data(), c->d_hg, b, cudaMemcpyDeviceToHost, c->stream));
+    LMOT_CUDA(c, cudaMemcpyAsync(hg.data(), s->d_hg, b, cudaMemcpyDeviceToHost, st));
   }
-  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(st));
   for (int k = 0; k < kPolarCells && (hground || isground); ++k) {
     const bool g = !(std::isinf(hg[k]) && hg[k] < 0);
     if (hground) hground[k] = g ? hg[k] : 0.f;
@@ -445,10 +647,14 @@ int lmot_debug_polar_grid(lmot_ctx* ctx, float* minz, float* height, float* smoo
 }
 
 int lmot_debug_cell_index(lmot_ctx* ctx, int32_t* ch, int32_t* bin, int n) {
-  if (!ctx || n < 0 || n > ctx->c.cur_n) return LMOT_ERR_INVALID;
+  if (!ctx || n < 0) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
+  int rc = lmot_sync(ctx);
+  if (rc) return rc;
+  Slot* s = &c->slots[c->last_slot];
+  if (n > s->cur_n) return LMOT_ERR_INVALID;
   std::vector<uint16_t> cell((size_t)n);
-  if (n) LMOT_CUDA(c, cudaMemcpyAsync(cell.data(), c->d_cell, (size_t)n * 2, cudaMemcpyDeviceToHost, c->stream));
+  if (n) LMOT_CUDA(c, cudaMemcpyAsync(cell.data(), s->d_cell, (size_t)n * 2, cudaMemcpyDeviceToHost, c->stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
   for (int i = 0; i < n; ++i) {
     if (cell[i] == kNoCell) { ch[i] = -1; bin[i] = -1; }

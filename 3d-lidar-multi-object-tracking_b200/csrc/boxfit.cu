@@ -210,7 +210,7 @@ box_fit_kernel(const float4* __restrict__ elev, const int* __restrict__ sorted_i
                const int* __restrict__ seg_size, int* __restrict__ counters, BoxParams P,
                const unsigned long long* __restrict__ mt_raw, int n_raw, int max_clusters, int max_boxes,
                float* __restrict__ cl_box, float* __restrict__ cl_marker, uint8_t* __restrict__ cl_ok,
-               float* __restrict__ boxes, float* __restrict__ markers, int* __restrict__ done) {
+               float* __restrict__ boxes, float* __restrict__ markers, float* __restrict__ h_boxes, int* __restrict__ done) {
   __shared__ int s_lo[kCols], s_hi[kCols];
   __shared__ short s_hx[kHullCap], s_hy[kHullCap];
   __shared__ short s_cx[kCols], s_clo[kCols], s_chi[kCols];     // occupied pixel columns, compacted
@@ -509,7 +509,7 @@ box_fit_kernel(const float4* __restrict__ elev, const int* __restrict__ sorted_i
     const int pos = carry + wbase + __popc(bal & ((1u << (tid & 31)) - 1u));
     if (f) {
       if (pos < max_boxes) {
-        for (int e = 0; e < 24; ++e) boxes[(size_t)pos * 24 + e] = __ldcg(&cl_box[(size_t)k * 24 + e]);
+        for (int e = 0; e < 24; ++e) { const float v = __ldcg(&cl_box[(size_t)k * 24 + e]); boxes[(size_t)pos * 24 + e] = v; h_boxes[(size_t)pos * 24 + e] = v; }
         for (int e = 0; e < 6; ++e) markers[(size_t)pos * 6 + e] = __ldcg(&cl_marker[(size_t)k * 6 + e]);
       }
     }
@@ -524,53 +524,53 @@ box_fit_kernel(const float4* __restrict__ elev, const int* __restrict__ sorted_i
 
 }  // namespace
 
-int boxfit_alloc(Ctx* c) {
-  const size_t np = (size_t)c->max_points;
-  const int K1 = c->prm.max_clusters + 1;
-  c->max_sort_tiles = (c->max_points + kTile - 1) / kTile;
-  LMOT_CUDA(c, cudaMalloc(&c->d_pcid, np * sizeof(uint16_t)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_table, (size_t)c->max_sort_tiles * K1 * sizeof(int)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_seg_start, K1 * sizeof(int)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_seg_size, K1 * sizeof(int)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_sorted_idx, np * sizeof(int)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_cl_box, (size_t)K1 * 24 * sizeof(float)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_cl_marker, (size_t)K1 * 6 * sizeof(float)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_cl_ok, K1));
-  LMOT_CUDA(c, cudaMalloc(&c->d_boxes, (size_t)c->prm.max_boxes * 24 * sizeof(float)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_markers, (size_t)c->prm.max_boxes * 6 * sizeof(float)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_done, sizeof(int)));
-  LMOT_CUDA(c, cudaMemsetAsync(c->d_done, 0, sizeof(int), c->stream));
+int boxfit_alloc_shared(Ctx* c) {
   // raw mt19937_64(0) stream (box_fitting.cpp:303 re-seeds per cluster, so every cluster sees the same draws)
   constexpr int kRaw = 256;
   std::mt19937_64 mt(0);
   unsigned long long raw[kRaw];
   for (int i = 0; i < kRaw; ++i) raw[i] = mt();
   c->n_mt_raw = kRaw;
+  c->max_sort_tiles = (c->max_points + kTile - 1) / kTile;
   LMOT_CUDA(c, cudaMalloc(&c->d_mt_raw, sizeof(raw)));
-  LMOT_CUDA(c, cudaMemcpyAsync(c->d_mt_raw, raw, sizeof(raw), cudaMemcpyHostToDevice, c->stream));
-  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  LMOT_CUDA(c, cudaMemcpy(c->d_mt_raw, raw, sizeof(raw), cudaMemcpyHostToDevice));
   return LMOT_OK;
 }
 
-void boxfit_free(Ctx* c) {
-  cudaFree(c->d_pcid); cudaFree(c->d_table); cudaFree(c->d_seg_start); cudaFree(c->d_seg_size); cudaFree(c->d_sorted_idx);
-  cudaFree(c->d_cl_box); cudaFree(c->d_cl_marker); cudaFree(c->d_cl_ok); cudaFree(c->d_boxes); cudaFree(c->d_markers);
-  cudaFree(c->d_done); cudaFree(c->d_mt_raw);
+int boxfit_alloc(Ctx* c, Slot* s) {
+  const size_t np = (size_t)c->max_points;
+  const int K1 = c->prm.max_clusters + 1;
+  LMOT_CUDA(c, cudaMalloc(&s->d_pcid, np * sizeof(uint16_t)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_table, (size_t)c->max_sort_tiles * K1 * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_seg_start, K1 * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_seg_size, K1 * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_sorted_idx, np * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_cl_box, (size_t)K1 * 24 * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_cl_marker, (size_t)K1 * 6 * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_cl_ok, K1));
+  LMOT_CUDA(c, cudaMalloc(&s->d_boxes, (size_t)c->prm.max_boxes * 24 * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_markers, (size_t)c->prm.max_boxes * 6 * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_done, sizeof(int)));
+  LMOT_CUDA(c, cudaMemsetAsync(s->d_done, 0, sizeof(int), s->stream));
+  return LMOT_OK;
 }
 
-// inputs: c->d_elev / CNT_N_ELEV, c->d_cart (from clustering), c->d_label_grid / CNT_NUM_CLUSTER
-int boxfit_launch(Ctx* c, int n_upper) {
+void boxfit_free(Slot* s) {
+  cudaFree(s->d_pcid); cudaFree(s->d_table); cudaFree(s->d_seg_start); cudaFree(s->d_seg_size); cudaFree(s->d_sorted_idx);
+  cudaFree(s->d_cl_box); cudaFree(s->d_cl_marker); cudaFree(s->d_cl_ok); cudaFree(s->d_boxes); cudaFree(s->d_markers);
+  cudaFree(s->d_done);
+}
+
+// inputs: s->d_elev / CNT_N_ELEV, s->d_cart (from clustering), s->d_label_grid / CNT_NUM_CLUSTER
+int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper) {
   const int K1 = c->prm.max_clusters + 1;
   const int tiles = (n_upper + kTile - 1) / kTile;
   const size_t sh = (size_t)K1 * sizeof(int);
   if (tiles > 0)
-    tile_hist_kernel<<<tiles, kTile, sh, c->stream>>>(c->d_cart, c->d_label_grid, c->d_counters, c->d_pcid, c->d_table,
-                                                      c->prm.max_clusters);
-  seg_offsets_kernel<<<1, 1024, 0, c->stream>>>(c->d_table, c->d_counters, c->d_seg_start, c->d_seg_size,
-                                                c->prm.max_clusters, c->d_done);
+    tile_hist_kernel<<<tiles, kTile, sh, st>>>(s->d_cart, s->d_label_grid, s->d_counters, s->d_pcid, s->d_table, c->prm.max_clusters);
+  seg_offsets_kernel<<<1, 1024, 0, st>>>(s->d_table, s->d_counters, s->d_seg_start, s->d_seg_size, c->prm.max_clusters, s->d_done);
   if (tiles > 0)
-    scatter_kernel<<<tiles, kTile, sh, c->stream>>>(c->d_pcid, c->d_counters, c->d_table, c->d_seg_start, c->d_sorted_idx,
-                                                    c->prm.max_clusters);
+    scatter_kernel<<<tiles, kTile, sh, st>>>(s->d_pcid, s->d_counters, s->d_table, s->d_seg_start, s->d_sorted_idx, c->prm.max_clusters);
   BoxParams P;
   const lmot_params& p = c->prm;
   P.roi = p.roi_m;
@@ -580,10 +580,9 @@ int boxfit_launch(Ctx* c, int n_upper) {
   P.t_height_min = p.t_height_min; P.t_height_max = p.t_height_max; P.t_width_min = p.t_width_min; P.t_width_max = p.t_width_max;
   P.t_len_min = p.t_len_min; P.t_len_max = p.t_len_max; P.t_area_max = p.t_area_max; P.t_ratio_min = p.t_ratio_min;
   P.t_ratio_max = p.t_ratio_max; P.min_len_ratio = p.min_len_ratio; P.t_pt_per_m3 = p.t_pt_per_m3;
-  box_fit_kernel<<<c->fit_ctas, kFitThreads, 0, c->stream>>>(c->d_elev, c->d_sorted_idx, c->d_seg_start, c->d_seg_size,
-                                                             c->d_counters, P, c->d_mt_raw, c->n_mt_raw, c->prm.max_clusters,
-                                                             c->prm.max_boxes, c->d_cl_box, c->d_cl_marker, c->d_cl_ok,
-                                                             c->d_boxes, c->d_markers, c->d_done);
+  box_fit_kernel<<<c->fit_ctas, kFitThreads, 0, st>>>(s->d_elev, s->d_sorted_idx, s->d_seg_start, s->d_seg_size, s->d_counters, P,
+                                                      c->d_mt_raw, c->n_mt_raw, c->prm.max_clusters, c->prm.max_boxes, s->d_cl_box,
+                                                      s->d_cl_marker, s->d_cl_ok, s->d_boxes, s->d_markers, s->h_boxes, s->d_done);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }

@@ -244,39 +244,35 @@ ccl_cluster_kernel(int* __restrict__ count, int* G, int* rid, int* __restrict__ 
 
 }  // namespace
 
-int cluster_alloc(Ctx* c) {
+int cluster_alloc(Ctx* c, Slot* s) {
   const size_t np = (size_t)c->max_points;
-  LMOT_CUDA(c, cudaMalloc(&c->d_cart, np * sizeof(uint16_t)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_count, kCartCells * sizeof(int)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_seed, kCartCells));
-  LMOT_CUDA(c, cudaMalloc(&c->d_parent, kCartCells * sizeof(int)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_rid, kCartCells * sizeof(int)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_label_grid, kCartCells * sizeof(int)));
-  LMOT_CUDA(c, cudaMemsetAsync(c->d_count, 0, kCartCells * sizeof(int), c->stream));
-  LMOT_CUDA(c, cudaMemsetAsync(c->d_label_grid, 0, kCartCells * sizeof(int), c->stream));
+  LMOT_CUDA(c, cudaMalloc(&s->d_cart, np * sizeof(uint16_t)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_count, kCartCells * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_parent, kCartCells * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_rid, kCartCells * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_label_grid, kCartCells * sizeof(int)));
+  LMOT_CUDA(c, cudaMemsetAsync(s->d_count, 0, kCartCells * sizeof(int), s->stream));
+  LMOT_CUDA(c, cudaMemsetAsync(s->d_label_grid, 0, kCartCells * sizeof(int), s->stream));
   LMOT_CUDA(c, cudaFuncSetAttribute(ccl_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCclSmem));
   return LMOT_OK;
 }
 
-void cluster_free(Ctx* c) {
-  cudaFree(c->d_cart); cudaFree(c->d_count); cudaFree(c->d_seed); cudaFree(c->d_parent); cudaFree(c->d_rid);
-  cudaFree(c->d_label_grid);
+void cluster_free(Slot* s) {
+  cudaFree(s->d_cart); cudaFree(s->d_count); cudaFree(s->d_parent); cudaFree(s->d_rid); cudaFree(s->d_label_grid);
 }
 
-// elevated cloud = c->d_elev with its length in d_counters[CNT_N_ELEV]; n_upper bounds that length on the host
-int cluster_launch(Ctx* c, int n_upper) {
+// elevated cloud = s->d_elev with its length in d_counters[CNT_N_ELEV]; n_upper bounds that length on the host
+int cluster_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper) {
   if (n_upper > 0)
-    cart_count_kernel<<<(n_upper + 255) / 256, 256, 0, c->stream>>>(c->d_elev, c->d_counters, c->prm.roi_m, c->d_cart,
-                                                                    c->d_count);
-  ccl_cluster_kernel<<<kCclCtas, kCclThreads, kCclSmem, c->stream>>>(c->d_count, c->d_parent, c->d_rid, c->d_label_grid,
-                                                                     c->d_counters);
+    cart_count_kernel<<<(n_upper + 255) / 256, 256, 0, st>>>(s->d_elev, s->d_counters, c->prm.roi_m, s->d_cart, s->d_count);
+  ccl_cluster_kernel<<<kCclCtas, kCclThreads, kCclSmem, st>>>(s->d_count, s->d_parent, s->d_rid, s->d_label_grid, s->d_counters);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }
 
-int cluster_cells_only(Ctx* c, int n_upper) {
+int cluster_cells_only(Ctx* c, Slot* s, cudaStream_t st, int n_upper) {
   if (n_upper > 0)
-    cart_cells_kernel<<<(n_upper + 255) / 256, 256, 0, c->stream>>>(c->d_elev, c->d_counters, c->prm.roi_m, c->d_cart);
+    cart_cells_kernel<<<(n_upper + 255) / 256, 256, 0, st>>>(s->d_elev, s->d_counters, c->prm.roi_m, s->d_cart);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }

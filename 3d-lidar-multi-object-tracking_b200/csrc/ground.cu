@@ -254,58 +254,58 @@ __global__ void init_keys_kernel(unsigned* keys) {
 
 }  // namespace
 
-int ground_alloc(Ctx* c) {
+int ground_alloc(Ctx* c, Slot* s) {
   const size_t np = (size_t)c->max_points;
   c->max_tiles = (c->max_points + kScanTile - 1) / kScanTile;
-  LMOT_CUDA(c, cudaMalloc(&c->d_points, np * sizeof(float4)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_stage_in, np * 4 * sizeof(float)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_cell, np * sizeof(uint16_t)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_polar_key, kPolarCells * sizeof(unsigned)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_minz, kPolarCells * sizeof(float)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_height, kPolarCells * sizeof(float)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_smoothed, kPolarCells * sizeof(float)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_hdiff, kPolarCells * sizeof(float)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_hg, kPolarCells * sizeof(float)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_labels, np));
-  LMOT_CUDA(c, cudaMalloc(&c->d_elev, np * sizeof(float4)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_ground, np * sizeof(float4)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_tile_desc, (size_t)c->max_tiles * sizeof(unsigned long long)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_counters, CNT_COUNT * sizeof(int)));
-  LMOT_CUDA(c, cudaMemsetAsync(c->d_counters, 0, CNT_COUNT * sizeof(int), c->stream));
-  LMOT_CUDA(c, cudaHostAlloc(&c->h_counters, CNT_COUNT * sizeof(int), cudaHostAllocDefault));
-  LMOT_CUDA(c, cudaHostAlloc(&c->h_set, CNT_COUNT * sizeof(int), cudaHostAllocDefault));
-  init_keys_kernel<<<(kPolarCells + 255) / 256, 256, 0, c->stream>>>(c->d_polar_key);
+  cudaStream_t st = s->stream;
+  LMOT_CUDA(c, cudaMalloc(&s->d_points, np * sizeof(float4)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_stage_in, np * 4 * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_cell, np * sizeof(uint16_t)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_polar_key, kPolarCells * sizeof(unsigned)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_minz, kPolarCells * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_height, kPolarCells * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_smoothed, kPolarCells * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_hdiff, kPolarCells * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_hg, kPolarCells * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_labels, np));
+  LMOT_CUDA(c, cudaMalloc(&s->d_elev, np * sizeof(float4)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_ground, np * sizeof(float4)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_tile_desc, (size_t)c->max_tiles * sizeof(unsigned long long)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_counters, CNT_COUNT * sizeof(int)));
+  LMOT_CUDA(c, cudaMemsetAsync(s->d_counters, 0, CNT_COUNT * sizeof(int), st));
+  LMOT_CUDA(c, cudaHostAlloc(&s->h_counters, CNT_COUNT * sizeof(int), cudaHostAllocDefault));
+  LMOT_CUDA(c, cudaHostAlloc(&s->h_set, CNT_COUNT * sizeof(int), cudaHostAllocDefault));
+  init_keys_kernel<<<(kPolarCells + 255) / 256, 256, 0, st>>>(s->d_polar_key);
   LMOT_CUDA(c, cudaGetLastError());
   LMOT_CUDA(c, cudaFuncSetAttribute(polar_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kPolarCells * (int)(sizeof(float) + 1)));
   return LMOT_OK;
 }
 
-void ground_free(Ctx* c) {
-  cudaFree(c->d_points); cudaFree(c->d_stage_in); cudaFree(c->d_cell); cudaFree(c->d_polar_key); cudaFree(c->d_minz);
-  cudaFree(c->d_height); cudaFree(c->d_smoothed); cudaFree(c->d_hdiff); cudaFree(c->d_hg); cudaFree(c->d_labels);
-  cudaFree(c->d_elev); cudaFree(c->d_ground); cudaFree(c->d_tile_desc); cudaFree(c->d_counters);
-  if (c->h_counters) cudaFreeHost(c->h_counters);
-  if (c->h_set) cudaFreeHost(c->h_set);
+void ground_free(Slot* s) {
+  cudaFree(s->d_points); cudaFree(s->d_stage_in); cudaFree(s->d_cell); cudaFree(s->d_polar_key); cudaFree(s->d_minz);
+  cudaFree(s->d_height); cudaFree(s->d_smoothed); cudaFree(s->d_hdiff); cudaFree(s->d_hg); cudaFree(s->d_labels);
+  cudaFree(s->d_elev); cudaFree(s->d_ground); cudaFree(s->d_tile_desc); cudaFree(s->d_counters);
+  if (s->h_counters) cudaFreeHost(s->h_counters);
+  if (s->h_set) cudaFreeHost(s->h_set);
 }
 
-int ground_repack(Ctx* c, const float* d_in, int n, int stride, float4* d_out) {
-  if (n > 0) repack_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_in, n, stride, d_out);
+int ground_repack(Ctx* c, cudaStream_t st, const float* d_in, int n, int stride, float4* d_out) {
+  if (n > 0) repack_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_in, n, stride, d_out);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }
 
-int ground_launch(Ctx* c, const float4* pts, int n) {
-  c->cur_points = pts;
-  c->cur_n = n;
+int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n) {
+  s->cur_points = pts;
+  s->cur_n = n;
   const int n_tiles = (n + kScanTile - 1) / kScanTile;
-  if (n > 0) polar_bin_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(pts, n, c->gp, c->d_cell, c->d_polar_key);
-  polar_grid_kernel<<<1, kGridThreads, kPolarCells * (sizeof(float) + 1), c->stream>>>(
-      c->gp, c->d_polar_key, c->d_minz, c->d_height, c->d_smoothed, c->d_hdiff, c->d_hg, c->d_tile_desc, n_tiles,
-      c->d_counters);
+  if (n > 0) polar_bin_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, c->gp, s->d_cell, s->d_polar_key);
+  polar_grid_kernel<<<1, kGridThreads, kPolarCells * (sizeof(float) + 1), st>>>(
+      c->gp, s->d_polar_key, s->d_minz, s->d_height, s->d_smoothed, s->d_hdiff, s->d_hg, s->d_tile_desc, n_tiles, s->d_counters);
   if (n > 0)
-    classify_partition_kernel<<<n_tiles, kScanTile, 0, c->stream>>>(pts, n, c->d_cell, c->d_hg, c->gp.tol, c->d_labels,
-                                                                  c->d_elev, c->d_ground, c->d_tile_desc, c->d_counters);
+    classify_partition_kernel<<<n_tiles, kScanTile, 0, st>>>(pts, n, s->d_cell, s->d_hg, c->gp.tol, s->d_labels, s->d_elev,
+                                                           s->d_ground, s->d_tile_desc, s->d_counters);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }

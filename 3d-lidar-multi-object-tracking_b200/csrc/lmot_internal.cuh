@@ -55,20 +55,21 @@ struct TrackerHost {
   double fold[3] = {0, 0, -1.5707963267948966};
 };
 
-struct Ctx {
-  lmot_params prm;
-  int device = 0;
-  cudaStream_t own_stream = nullptr;
+// Detection slot: every buffer the three detection stages (ground -> cluster -> box) touch for ONE frame, plus the
+// stream they run on.  A context owns `pipeline_depth` slots so the detection stages of frame f+1.. run while the
+// tracker (a sequential fold over frames, on its own stream) is still busy with frame f.
+struct Slot {
+  int index = 0;
   cudaStream_t stream = nullptr;
-  std::string last_error;
-  GroundParams gp;
-
-  // ---- capacities
-  int max_points = 0, max_tiles = 0;
+  cudaEvent_t ev_fork = nullptr;       // recorded on the caller's stream: the frame's input is ready
+  cudaEvent_t ev_det_done = nullptr;   // recorded on the slot stream after box fitting
+  cudaEvent_t ev_trk_done = nullptr;   // recorded on the tracker stream when the tracker has consumed the slot
+  bool in_flight = false;              // submitted and not yet collected / dropped
+  bool has_tracks = false;             // the last submission went through the tracker (frame) or not (detect only)
 
   // ---- frame input (host-buffer entry points copy here; *_dev entry points use the caller's pointer)
   float4* d_points = nullptr;
-  float* d_stage_in = nullptr;  // raw staging for stride != 4 inputs
+  float* d_stage_in = nullptr;         // raw staging for stride != 4 inputs
   const float4* cur_points = nullptr;
   int cur_n = 0;
 
@@ -91,13 +92,11 @@ struct Ctx {
   // ---- clustering
   uint16_t* d_cart = nullptr;          // per elevated point cartesian cell (x*250+y) or kNoCell
   int* d_count = nullptr;              // [62500] points per cell (zeroed by the CCL kernel after use)
-  uint8_t* d_seed = nullptr;           // [62500] count > 1
-  int* d_parent = nullptr;             // [62500] union-find parent, -1 = empty
+  int* d_parent = nullptr;             // [62500] union-find parent (global linear index), -1 = empty
   int* d_rid = nullptr;                // [62500] cluster id at root cells
   int* d_label_grid = nullptr;         // [62500] final labels (0 = empty), x-major
 
   // ---- box fitting
-  int max_sort_tiles = 0, fit_ctas = 296, n_mt_raw = 0;
   uint16_t* d_pcid = nullptr;          // per elevated point cluster id (0 = none)
   int* d_table = nullptr;              // [tiles][max_clusters+1] tile histograms -> exclusive tile offsets
   int* d_seg_start = nullptr;          // [max_clusters+1] first slot of each cluster in d_sorted_idx
@@ -109,24 +108,57 @@ struct Ctx {
   float* d_boxes = nullptr;            // [max_boxes][8][3] accepted boxes, cluster-id order
   float* d_markers = nullptr;          // [max_boxes][6]
   int* d_done = nullptr;               // last-CTA-done counter
-  unsigned long long* d_mt_raw = nullptr;  // raw mt19937_64(0) outputs
+
+  // ---- results of the frame in pinned, device-mapped host memory: written by the kernels themselves (box
+  // compaction, spawn_output_kernel), read by the host after ev_trk_done -- no sized D2H copies on the hot path
+  int* h_hdr = nullptr;                // [16] n_elev, n_ground, num_cluster, n_boxes, n_tracks, n_vis, error
+  float* h_boxes = nullptr;            // [max_boxes][24]
+  float* h_targets = nullptr; double* h_vandyaw = nullptr; int* h_manage = nullptr;
+  uint8_t* h_static = nullptr; uint8_t* h_vis = nullptr; float* h_visbb = nullptr;
+
+  // ---- timing
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+enum HostHdr { HDR_N_ELEV = 0, HDR_N_GROUND, HDR_NUM_CLUSTER, HDR_N_BOXES, HDR_N_TRACKS, HDR_N_VIS, HDR_ERROR, HDR_COUNT = 16 };
+
+constexpr int kMaxSlots = 8;
+
+struct Ctx {
+  lmot_params prm;
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;       // the caller's stream: stage-by-stage entry points, fork/join of the pipeline
+  std::string last_error;
+  GroundParams gp;
+
+  // ---- capacities
+  int max_points = 0, max_tiles = 0, max_sort_tiles = 0, fit_ctas = 296, n_mt_raw = 0;
+  unsigned long long* d_mt_raw = nullptr;  // raw mt19937_64(0) outputs (shared, read only)
+
+  // ---- detection slots
+  int n_slots = 1;
+  Slot slots[kMaxSlots];
+  int next_slot = 0;                   // slot of the next submission
+  int oldest = 0;                      // slot of the oldest in-flight submission
+  int n_in_flight = 0;
+  int last_slot = 0;                   // slot of the most recent submission (debug getters read it)
 
   // ---- tracker
   TrackerHost th;
+  cudaStream_t trk_stream = nullptr;
   int trk_ctas = 592, gate_words = 0;
   TrackState* d_tracks = nullptr;      // [max_tracks] append-only table; dead tracks keep their slot
+  int* d_trk_counters = nullptr;       // [CNT_COUNT] CNT_N_TRACKS / CNT_N_VIS / CNT_ERROR of the track table
+  int* h_trk_counters = nullptr;       // pinned mirror
   unsigned* d_gate = nullptr;          // [max_tracks][gate_words] chi-square gate bits per (track, box)
   unsigned* d_setter = nullptr;        // [max_tracks][gate_words] boxes this track marks as matched
   int* d_first_setter = nullptr;       // [max_boxes] lowest track index that matched the box (INT_MAX = unmatched)
   uint8_t* d_skip = nullptr;           // [max_tracks] track did not reach measurementValidation this frame
   int* d_new_num = nullptr;            // [max_tracks] staged mergeOverSegmentation writes
-  float* d_boxes_in = nullptr;         // staging for lmot_track_step's host boxes
-  float* d_out_targets = nullptr; double* d_out_vandyaw = nullptr; int* d_out_manage = nullptr;
-  uint8_t* d_out_static = nullptr; uint8_t* d_out_vis = nullptr; float* d_out_visbb = nullptr;
 
   // ---- timing
   bool timing = false;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float stage_ms[4] = {0, 0, 0, 0};
 };
 
@@ -140,21 +172,23 @@ struct Ctx {
     }                                                                                            \
   } while (0)
 
-// ---- stage launchers (asynchronous on ctx->stream) ---------------------------------------------------
-int ground_alloc(Ctx* c);
-void ground_free(Ctx* c);
-// pts: device float4 array of n points
-int ground_launch(Ctx* c, const float4* pts, int n);
-int ground_repack(Ctx* c, const float* d_in, int n, int stride, float4* d_out);
-int cluster_alloc(Ctx* c);
-void cluster_free(Ctx* c);
-int cluster_launch(Ctx* c, int n_upper);
-int cluster_cells_only(Ctx* c, int n_upper);  // d_cart for an elevated cloud whose label grid comes from the caller
-int boxfit_alloc(Ctx* c);
-void boxfit_free(Ctx* c);
-int boxfit_launch(Ctx* c, int n_upper);
+// ---- stage launchers (asynchronous on the given stream) -------------------------------------------------
+int ground_alloc(Ctx* c, Slot* s);
+void ground_free(Slot* s);
+int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n);   // pts: device float4 array of n points
+int ground_repack(Ctx* c, cudaStream_t st, const float* d_in, int n, int stride, float4* d_out);
+int cluster_alloc(Ctx* c, Slot* s);
+void cluster_free(Slot* s);
+int cluster_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper);
+int cluster_cells_only(Ctx* c, Slot* s, cudaStream_t st, int n_upper);  // d_cart for a cloud whose label grid comes from the caller
+int boxfit_alloc(Ctx* c, Slot* s);
+int boxfit_alloc_shared(Ctx* c);
+void boxfit_free(Slot* s);
+int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper);
 int tracker_alloc(Ctx* c);
 void tracker_free(Ctx* c);
-int tracker_launch(Ctx* c, const float* d_boxes, double timestamp, double v_gps, double yaw_gps);
+// boxes: device float[M][8][3] with M in det_counters[CNT_N_BOXES]; results into the slot's pinned host block
+int tracker_launch(Ctx* c, Slot* s, cudaStream_t st, const float* d_boxes, const int* det_counters, double timestamp, double v_gps,
+                   double yaw_gps);
 
 }  // namespace lmot

@@ -151,13 +151,13 @@ struct TAShared {
 __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
 
 __global__ void __launch_bounds__(kTAThreads)
-imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__ counters, const float* __restrict__ boxes,
+imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, const int* __restrict__ det, const float* __restrict__ boxes,
                         double dt, unsigned* __restrict__ gate, unsigned* __restrict__ setter, int* __restrict__ first_setter,
                         uint8_t* __restrict__ skip, int words) {
   __shared__ TAShared sh;
   const int tid = threadIdx.x, lane = tid & 31, model = tid >> 5;
-  const int T = counters[CNT_N_TRACKS];
-  const int M = counters[CNT_N_BOXES];
+  const int T = trk[CNT_N_TRACKS];
+  const int M = det[CNT_N_BOXES];
   const double kStdA = (model == 2) ? 3.0 : 2.0;       // std_a_{cv,ctrv,rm}_ ukf.cpp:68-70 (= std_*_yawdd_ :71-73)
   const double lambda_aug = 3 - 7;
   const double w0 = lambda_aug / (lambda_aug + 7), wi = 0.5 / (7 + lambda_aug);
@@ -450,13 +450,13 @@ __device__ void update_bb(TrackState& t) {
 }
 
 __global__ void __launch_bounds__(kTBWarps * 32)
-imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ counters, const float* __restrict__ boxes,
+imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, const int* __restrict__ det, const float* __restrict__ boxes,
                   const unsigned* __restrict__ gate, const int* __restrict__ first_setter, const uint8_t* __restrict__ skip,
                   int words) {
   extern __shared__ unsigned short s_list_all[];          // per warp: indices of the gated boxes, in box order
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int T = counters[CNT_N_TRACKS];
-  const int M = counters[CNT_N_BOXES];
+  const int T = trk[CNT_N_TRACKS];
+  const int M = det[CNT_N_BOXES];
   unsigned short* s_list = s_list_all + (size_t)warp * words * 32;
   const int nchunk = (M + 31) >> 5;
 
@@ -694,9 +694,9 @@ __device__ bool overseg_cond(const TrackState& a, double px, double py) {
 // contains k, else 5 if k (visible) contains anybody, else unchanged.  Decisions are staged in new_num and
 // applied by spawn_output_kernel so that this kernel only reads the table.
 __global__ void __launch_bounds__(128)
-merge_overseg_kernel(const TrackState* __restrict__ tracks, const int* __restrict__ counters, int* __restrict__ new_num) {
+merge_overseg_kernel(const TrackState* __restrict__ tracks, const int* __restrict__ trk, int* __restrict__ new_num) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int T = counters[CNT_N_TRACKS];
+  const int T = trk[CNT_N_TRACKS];
   for (int k = blockIdx.x * 4 + warp; k < T; k += gridDim.x * 4) {
     const TrackState& tk = tracks[k];
     const double kx = tk.x[0][0], ky = tk.x[0][1];
@@ -721,19 +721,19 @@ merge_overseg_kernel(const TrackState* __restrict__ tracks, const int* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ TC2
-struct OutPtrs {
-  float* targets; double* vandyaw; int* track_manage; uint8_t* is_static; uint8_t* is_vis; float* vis_bb;
+struct OutPtrs {   // pinned, device-mapped host memory of the slot: the kernel's stores ARE the D2H transfer
+  float* targets; double* vandyaw; int* track_manage; uint8_t* is_static; uint8_t* is_vis; float* vis_bb; int* hdr;
 };
 
 __global__ void __launch_bounds__(1024)
-spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ counters, const float* __restrict__ boxes,
+spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int* __restrict__ det, const float* __restrict__ boxes,
                     int* __restrict__ first_setter, const int* __restrict__ new_num, int first_frame, int compat_first,
                     double ego_yaw, int max_tracks, OutPtrs o) {
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int T0 = counters[CNT_N_TRACKS];
-  const int M = counters[CNT_N_BOXES];
+  const int T0 = trk[CNT_N_TRACKS];
+  const int M = det[CNT_N_BOXES];
   if (tid == 0) s_carry = 0;
   __syncthreads();
 
@@ -747,7 +747,10 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ counters,
         o.vandyaw[0] = 0; o.vandyaw[1] = 0; o.is_static[0] = 0; o.is_vis[0] = 0; o.track_manage[0] = 1;
         T = 1;
       }
-      counters[CNT_N_TRACKS] = T; counters[CNT_N_VIS] = 0;
+      trk[CNT_N_TRACKS] = T; trk[CNT_N_VIS] = 0;
+      o.hdr[HDR_N_ELEV] = det[CNT_N_ELEV]; o.hdr[HDR_N_GROUND] = det[CNT_N_GROUND]; o.hdr[HDR_NUM_CLUSTER] = det[CNT_NUM_CLUSTER];
+      o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = 0; o.hdr[HDR_ERROR] = det[CNT_ERROR];
+      det[CNT_ERROR] = 0;
     }
     for (int b = tid; b < M; b += 1024) first_setter[b] = INT_MAX;
     return;
@@ -777,7 +780,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ counters,
     __syncthreads();
   }
   int T = T0 + s_carry;
-  if (T > max_tracks) { if (tid == 0) counters[CNT_ERROR] = LMOT_ERR_CAPACITY; T = max_tracks; }
+  if (T > max_tracks) { if (tid == 0) det[CNT_ERROR] = LMOT_ERR_CAPACITY; T = max_tracks; }
   __syncthreads();
   if (tid == 0) s_carry = 0;
   __syncthreads();
@@ -820,7 +823,12 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ counters,
     if (tid == 0) s_carry += tot;
     __syncthreads();
   }
-  if (tid == 0) { counters[CNT_N_TRACKS] = T; counters[CNT_N_VIS] = s_carry; }
+  if (tid == 0) {
+    trk[CNT_N_TRACKS] = T; trk[CNT_N_VIS] = s_carry;
+    o.hdr[HDR_N_ELEV] = det[CNT_N_ELEV]; o.hdr[HDR_N_GROUND] = det[CNT_N_GROUND]; o.hdr[HDR_NUM_CLUSTER] = det[CNT_NUM_CLUSTER];
+    o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = s_carry; o.hdr[HDR_ERROR] = det[CNT_ERROR];
+    det[CNT_ERROR] = 0;
+  }
 }
 
 __global__ void fill_int_kernel(int* p, int n, int v) {
@@ -834,20 +842,16 @@ int tracker_alloc(Ctx* c) {
   const int TC = c->prm.max_tracks, MB = c->prm.max_boxes;
   c->gate_words = (MB + 31) / 32;
   LMOT_CUDA(c, cudaMalloc(&c->d_tracks, (size_t)TC * sizeof(TrackState)));
-  LMOT_CUDA(c, cudaMemsetAsync(c->d_tracks, 0, (size_t)TC * sizeof(TrackState), c->stream));
+  LMOT_CUDA(c, cudaMemsetAsync(c->d_tracks, 0, (size_t)TC * sizeof(TrackState), c->trk_stream));
+  LMOT_CUDA(c, cudaMalloc(&c->d_trk_counters, CNT_COUNT * sizeof(int)));
+  LMOT_CUDA(c, cudaMemsetAsync(c->d_trk_counters, 0, CNT_COUNT * sizeof(int), c->trk_stream));
+  LMOT_CUDA(c, cudaHostAlloc(&c->h_trk_counters, CNT_COUNT * sizeof(int), cudaHostAllocDefault));
   LMOT_CUDA(c, cudaMalloc(&c->d_gate, (size_t)TC * c->gate_words * sizeof(unsigned)));
   LMOT_CUDA(c, cudaMalloc(&c->d_setter, (size_t)TC * c->gate_words * sizeof(unsigned)));
   LMOT_CUDA(c, cudaMalloc(&c->d_first_setter, (size_t)MB * sizeof(int)));
   LMOT_CUDA(c, cudaMalloc(&c->d_skip, TC));
   LMOT_CUDA(c, cudaMalloc(&c->d_new_num, (size_t)TC * sizeof(int)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_boxes_in, (size_t)MB * 24 * sizeof(float)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_out_targets, (size_t)TC * 3 * sizeof(float)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_out_vandyaw, (size_t)TC * 2 * sizeof(double)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_out_manage, (size_t)TC * sizeof(int)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_out_static, TC));
-  LMOT_CUDA(c, cudaMalloc(&c->d_out_vis, TC));
-  LMOT_CUDA(c, cudaMalloc(&c->d_out_visbb, (size_t)TC * 24 * sizeof(float)));
-  fill_int_kernel<<<(MB + 255) / 256, 256, 0, c->stream>>>(c->d_first_setter, MB, INT_MAX);
+  fill_int_kernel<<<(MB + 255) / 256, 256, 0, c->trk_stream>>>(c->d_first_setter, MB, INT_MAX);
   LMOT_CUDA(c, cudaGetLastError());
   const size_t sh = (size_t)kTBWarps * c->gate_words * 32 * sizeof(unsigned short);
   LMOT_CUDA(c, cudaFuncSetAttribute(imm_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
@@ -855,9 +859,9 @@ int tracker_alloc(Ctx* c) {
 }
 
 void tracker_free(Ctx* c) {
-  cudaFree(c->d_tracks); cudaFree(c->d_gate); cudaFree(c->d_setter); cudaFree(c->d_first_setter); cudaFree(c->d_skip);
-  cudaFree(c->d_new_num); cudaFree(c->d_boxes_in); cudaFree(c->d_out_targets); cudaFree(c->d_out_vandyaw);
-  cudaFree(c->d_out_manage); cudaFree(c->d_out_static); cudaFree(c->d_out_vis); cudaFree(c->d_out_visbb);
+  cudaFree(c->d_tracks); cudaFree(c->d_trk_counters); cudaFree(c->d_gate); cudaFree(c->d_setter); cudaFree(c->d_first_setter);
+  cudaFree(c->d_skip); cudaFree(c->d_new_num);
+  if (c->h_trk_counters) cudaFreeHost(c->h_trk_counters);
 }
 
 // getOriginPoints (imm_ukf_jpda.cpp:74-172) is scalar bookkeeping on three doubles per frame; it stays on the host.
@@ -888,24 +892,26 @@ static void origin_points_host(Ctx* c, double timestamp, double v_gps, double ya
   h.egoPoint[0] = x; h.egoPoint[1] = y; h.egoPoint[2] = egoYaw;
 }
 
-// boxes: device float[M][8][3] with M in d_counters[CNT_N_BOXES]
-int tracker_launch(Ctx* c, const float* d_boxes, double timestamp, double v_gps, double yaw_gps) {
+// boxes: device float[M][8][3] with M in det_counters[CNT_N_BOXES]
+int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, const int* det_counters, double timestamp, double v_gps,
+                   double yaw_gps) {
   origin_points_host(c, timestamp, v_gps, yaw_gps);
   TrackerHost& h = c->th;
-  OutPtrs o{c->d_out_targets, c->d_out_vandyaw, c->d_out_manage, c->d_out_static, c->d_out_vis, c->d_out_visbb};
+  OutPtrs o{sl->h_targets, sl->h_vandyaw, sl->h_manage, sl->h_static, sl->h_vis, sl->h_visbb, sl->h_hdr};
+  int* det = const_cast<int*>(det_counters);
   const int first = h.init ? 0 : 1;
   const int compat = c->prm.oracle_compat_first_frame ? 1 : 0;
   if (!(first && compat)) {
     const double dt = first ? 0.0 : (timestamp - h.timestamp) / 1000000.0;     // :807
     const size_t sh = (size_t)kTBWarps * c->gate_words * 32 * sizeof(unsigned short);
-    imm_predict_gate_kernel<<<c->trk_ctas, kTAThreads, 0, c->stream>>>(c->d_tracks, c->d_counters, d_boxes, dt, c->d_gate,
-                                                                        c->d_setter, c->d_first_setter, c->d_skip, c->gate_words);
-    imm_update_kernel<<<c->trk_ctas / kTBWarps + 1, kTBWarps * 32, sh, c->stream>>>(c->d_tracks, c->d_counters, d_boxes, c->d_gate,
-                                                                                  c->d_first_setter, c->d_skip, c->gate_words);
-    merge_overseg_kernel<<<c->trk_ctas / 4 + 1, 128, 0, c->stream>>>(c->d_tracks, c->d_counters, c->d_new_num);
+    imm_predict_gate_kernel<<<c->trk_ctas, kTAThreads, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, dt, c->d_gate, c->d_setter,
+                                                                 c->d_first_setter, c->d_skip, c->gate_words);
+    imm_update_kernel<<<c->trk_ctas / kTBWarps + 1, kTBWarps * 32, sh, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_gate,
+                                                                           c->d_first_setter, c->d_skip, c->gate_words);
+    merge_overseg_kernel<<<c->trk_ctas / 4 + 1, 128, 0, st>>>(c->d_tracks, c->d_trk_counters, c->d_new_num);
   }
-  spawn_output_kernel<<<1, 1024, 0, c->stream>>>(c->d_tracks, c->d_counters, d_boxes, c->d_first_setter, c->d_new_num,
-                                                 first, compat, h.egoPoint[2], c->prm.max_tracks, o);
+  spawn_output_kernel<<<1, 1024, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_first_setter, c->d_new_num, first, compat,
+                                          h.egoPoint[2], c->prm.max_tracks, o);
   LMOT_CUDA(c, cudaGetLastError());
   h.timestamp = timestamp;
   h.egoPreYaw = h.egoYaw;

@@ -83,6 +83,8 @@ typedef struct lmot_params {
   int max_clusters;          /* default 4096 (a 250x250 grid with 3x3 dilation cannot hold more) */
   int max_boxes;             /* default 1024 */
   int max_tracks;            /* tracks ever created (dead ones keep their slot), default 8192 */
+  /* frames in flight inside one context: detection stages of frame f+1.. overlap the tracker of frame f (1..8, default 4) */
+  int pipeline_depth;
 } lmot_params;
 
 typedef struct lmot_ctx lmot_ctx;
@@ -147,11 +149,28 @@ typedef struct lmot_frame_out {
 int lmot_frame(lmot_ctx* ctx, const float* points, int n, int stride_floats, double timestamp_us, double v_gps,
                double yaw_gps, lmot_frame_out* out);
 
-/* ---- DEVICE-resident variants (asynchronous on the context's stream; no host copies) -------------------
- * d_points: device pointer, stride 4 floats (16-byte aligned).  Results stay in the context's device buffers;
- * lmot_frame_fetch copies the small artefacts (counts, boxes, track outputs) to the host and synchronises. */
+/* ---- pipelined frames (asynchronous) ----------------------------------------------------------------------
+ * A context keeps up to `pipeline_depth` frames in flight: the three detection stages of a frame run on one of
+ * `pipeline_depth` internal streams (own buffers each) while the tracker -- a sequential fold over frames -- runs on
+ * its own stream and consumes the box lists in submission order.  Results are identical to frame-at-a-time calls.
+ *
+ * lmot_frame_submit  : HOST frame (pinned memory recommended) -> H2D + all four stages, returns immediately.
+ *                      LMOT_ERR_STATE if pipeline_depth frames are already waiting to be collected.
+ * lmot_frame_collect : blocks until the OLDEST submitted frame is done and returns its results
+ *                      (the kernels wrote them into pinned host memory; no device copy is issued here).
+ * lmot_frame_dev     : like submit, but the frame is already on the device (stride 4 floats, 16-byte aligned); ordered
+ *                      after the work already queued on the context's caller stream (lmot_set_stream).  Uncollected
+ *                      results older than pipeline_depth submissions are dropped.
+ * lmot_frame_fetch   : waits for everything submitted so far and returns the results of the MOST RECENT frame.
+ * lmot_flush         : makes the caller stream wait (on the device, not the host) for everything submitted so far, so
+ *                      that CUDA events recorded on the caller stream bracket the work. */
+int lmot_frame_submit(lmot_ctx* ctx, const float* points, int n, int stride_floats, double timestamp_us, double v_gps,
+                      double yaw_gps);
+int lmot_frame_collect(lmot_ctx* ctx, lmot_frame_out* out);
+int lmot_frames_in_flight(lmot_ctx* ctx, int* n);
 int lmot_frame_dev(lmot_ctx* ctx, const float* d_points, int n, double timestamp_us, double v_gps, double yaw_gps);
 int lmot_frame_fetch(lmot_ctx* ctx, lmot_frame_out* out);
+int lmot_flush(lmot_ctx* ctx);
 int lmot_ground_remove_dev(lmot_ctx* ctx, const float* d_points, int n);
 int lmot_detect_dev(lmot_ctx* ctx, const float* d_points, int n); /* ground + cluster + box, no tracker */
 int lmot_sync(lmot_ctx* ctx);
