@@ -72,7 +72,7 @@ ABI_SYMBOLS = [
     "lmot_set_stream", "lmot_ground_remove", "lmot_component_cluster", "lmot_box_fit", "lmot_track_step", "lmot_frame",
     "lmot_frame_dev", "lmot_frame_fetch", "lmot_frame_submit", "lmot_frame_collect", "lmot_frames_in_flight", "lmot_flush",
     "lmot_ground_remove_dev", "lmot_detect_dev", "lmot_sync",
-    "lmot_tracker_reset", "lmot_tracker_num_tracks", "lmot_tracker_dump", "lmot_tracker_load",
+    "lmot_origin_points", "lmot_tracker_table", "lmot_tracker_set_num_tracks", "lmot_tracker_reset", "lmot_tracker_num_tracks", "lmot_tracker_dump", "lmot_tracker_load",
     "lmot_debug_polar_grid", "lmot_debug_cell_index", "lmot_debug_label_grid", "lmot_selftest_atan2f",
     "lmot_enable_timing", "lmot_last_stage_ms",
 ]
@@ -192,16 +192,32 @@ class Lmot:
 
     # ---- getOriginPoints + immUkfJpdaf -------------------------------------------------------------------
     def _track_out(self, cap):
-        bufs = dict(targets=np.zeros((cap, 3), np.float32), vandyaw=np.zeros((cap, 2), np.float64),
-                    track_manage=np.zeros(cap, np.int32), is_static=np.zeros(cap, np.uint8), is_vis=np.zeros(cap, np.uint8),
-                    vis_bb=np.zeros((cap, 8, 3), np.float32))
-        to = TrackOut()
-        to.cap = cap
-        to.targets = _fp(bufs["targets"]); to.vandyaw = bufs["vandyaw"].ctypes.data_as(C.POINTER(C.c_double))
-        to.track_manage = bufs["track_manage"].ctypes.data_as(C.POINTER(C.c_int32))
-        to.is_static = bufs["is_static"].ctypes.data_as(C.POINTER(C.c_uint8))
-        to.is_vis = bufs["is_vis"].ctypes.data_as(C.POINTER(C.c_uint8)); to.vis_bb = _fp(bufs["vis_bb"])
+        """Output buffers are allocated once per (context, cap) and reused: the hot loop must not allocate megabytes."""
+        cache = self.__dict__.setdefault("_out_cache", {})
+        if cap not in cache:
+            bufs = dict(targets=np.zeros((cap, 3), np.float32), vandyaw=np.zeros((cap, 2), np.float64),
+                        track_manage=np.zeros(cap, np.int32), is_static=np.zeros(cap, np.uint8), is_vis=np.zeros(cap, np.uint8),
+                        vis_bb=np.zeros((cap, 8, 3), np.float32), boxes=np.zeros((self.params.max_boxes, 8, 3), np.float32))
+            to = TrackOut()
+            to.cap = cap
+            to.targets = _fp(bufs["targets"]); to.vandyaw = bufs["vandyaw"].ctypes.data_as(C.POINTER(C.c_double))
+            to.track_manage = bufs["track_manage"].ctypes.data_as(C.POINTER(C.c_int32))
+            to.is_static = bufs["is_static"].ctypes.data_as(C.POINTER(C.c_uint8))
+            to.is_vis = bufs["is_vis"].ctypes.data_as(C.POINTER(C.c_uint8)); to.vis_bb = _fp(bufs["vis_bb"])
+            fo = FrameOut()
+            fo.boxes = _fp(bufs["boxes"]); fo.max_boxes = self.params.max_boxes
+            fo_nb = FrameOut()
+            fo_nb.max_boxes = self.params.max_boxes
+            cache[cap] = (to, bufs, fo, fo_nb)
+        to, bufs, _, _ = cache[cap]
         return to, bufs
+
+    def _frame_out(self, cap, want_boxes=True):
+        to, bufs = self._track_out(cap)
+        _, _, fo, fo_nb = self._out_cache[cap]
+        f = fo if want_boxes else fo_nb
+        f.tracks = to
+        return f, bufs
 
     @staticmethod
     def _track_result(to, bufs):
@@ -209,6 +225,13 @@ class Lmot:
         return dict(targets=bufs["targets"][:t].copy(), vandyaw=bufs["vandyaw"][:t].copy(),
                     track_manage=bufs["track_manage"][:t].copy(), is_static=bufs["is_static"][:t].copy(),
                     is_vis=bufs["is_vis"][:t].copy(), vis_bb=bufs["vis_bb"][:v].copy())
+
+    @staticmethod
+    def _frame_result(fo, bufs, want_boxes=True):
+        r = Lmot._track_result(fo.tracks, bufs)
+        r.update(n_elevated=fo.n_elevated, n_ground=fo.n_ground, num_cluster=fo.num_cluster,
+                 boxes=bufs["boxes"][: fo.n_boxes].copy() if want_boxes else bufs["boxes"][:0])
+        return r
 
     def track_step(self, boxes, timestamp_us, v_gps=0.0, yaw_gps=0.0, cap: int | None = None):
         b = np.ascontiguousarray(boxes, np.float32).reshape(-1, 8, 3)
@@ -223,16 +246,9 @@ class Lmot:
     def frame(self, points, timestamp_us, v_gps=0.0, yaw_gps=0.0, cap: int | None = None):
         """The whole hot path on one host frame -> dict(n_elevated, n_ground, num_cluster, boxes, tracks...)."""
         p, n, s = _pts(points)
-        cap = cap or self.params.max_tracks
-        fo = FrameOut()
-        boxes = np.zeros((self.params.max_boxes, 8, 3), np.float32)
-        fo.boxes = _fp(boxes); fo.max_boxes = self.params.max_boxes
-        to, bufs = self._track_out(cap)
-        fo.tracks = to
+        fo, bufs = self._frame_out(cap or self.params.max_tracks)
         self._chk(self.lib.lmot_frame(self.h, _fp(p), n, s, C.c_double(timestamp_us), C.c_double(v_gps), C.c_double(yaw_gps), C.byref(fo)))
-        r = self._track_result(fo.tracks, bufs)
-        r.update(n_elevated=fo.n_elevated, n_ground=fo.n_ground, num_cluster=fo.num_cluster, boxes=boxes[: fo.n_boxes].copy())
-        return r
+        return self._frame_result(fo, bufs)
 
     def frame_dev(self, d_ptr: int, n: int, timestamp_us, v_gps=0.0, yaw_gps=0.0):
         """Asynchronous: device-resident XYZI frame (stride 4) through all four stages on the context's stream."""
@@ -249,18 +265,9 @@ class Lmot:
 
     def frame_collect(self, cap: int | None = None, want_boxes: bool = True):
         """Results of the oldest submitted frame (blocks until it is done)."""
-        cap = cap or self.params.max_tracks
-        fo = FrameOut()
-        boxes = np.zeros((self.params.max_boxes, 8, 3), np.float32)
-        if want_boxes:
-            fo.boxes = _fp(boxes)
-        fo.max_boxes = self.params.max_boxes
-        to, bufs = self._track_out(cap)
-        fo.tracks = to
+        fo, bufs = self._frame_out(cap or self.params.max_tracks, want_boxes)
         self._chk(self.lib.lmot_frame_collect(self.h, C.byref(fo)))
-        r = self._track_result(fo.tracks, bufs)
-        r.update(n_elevated=fo.n_elevated, n_ground=fo.n_ground, num_cluster=fo.num_cluster, boxes=boxes[: fo.n_boxes].copy())
-        return r
+        return self._frame_result(fo, bufs, want_boxes)
 
     def frames_in_flight(self) -> int:
         n = C.c_int(0)
@@ -271,18 +278,9 @@ class Lmot:
         self._chk(self.lib.lmot_detect_dev(self.h, C.c_void_p(d_ptr), n))
 
     def frame_fetch(self, cap: int | None = None, want_boxes: bool = True):
-        cap = cap or self.params.max_tracks
-        fo = FrameOut()
-        boxes = np.zeros((self.params.max_boxes, 8, 3), np.float32)
-        if want_boxes:
-            fo.boxes = _fp(boxes)
-        fo.max_boxes = self.params.max_boxes
-        to, bufs = self._track_out(cap)
-        fo.tracks = to
+        fo, bufs = self._frame_out(cap or self.params.max_tracks, want_boxes)
         self._chk(self.lib.lmot_frame_fetch(self.h, C.byref(fo)))
-        r = self._track_result(fo.tracks, bufs)
-        r.update(n_elevated=fo.n_elevated, n_ground=fo.n_ground, num_cluster=fo.num_cluster, boxes=boxes[: fo.n_boxes].copy())
-        return r
+        return self._frame_result(fo, bufs, want_boxes)
 
     def tracker_reset(self):
         self._chk(self.lib.lmot_tracker_reset(self.h))
@@ -306,6 +304,15 @@ class Lmot:
             d = np.zeros((1, TRACK_DUMP_DOUBLES), np.float64)
         self._chk(self.lib.lmot_tracker_load(self.h, d.ctypes.data_as(C.POINTER(C.c_double)), n, int(init), C.c_double(timestamp_us),
                                              C.c_double(ego_velo), C.c_double(ego_yaw), C.c_double(ego_pre_yaw), C.c_double(ego_point_yaw)))
+
+    def tracker_table(self):
+        """-> (device pointer, bytes per track, capacity) of the track table (for NCCL broadcast, see shared_tracker.py)"""
+        ptr = C.c_void_p(); bpt = C.c_int(0); cap = C.c_int(0)
+        self._chk(self.lib.lmot_tracker_table(self.h, C.byref(ptr), C.byref(bpt), C.byref(cap)))
+        return int(ptr.value), bpt.value, cap.value
+
+    def tracker_set_num_tracks(self, n: int):
+        self._chk(self.lib.lmot_tracker_set_num_tracks(self.h, int(n)))
 
     def enable_timing(self, on: bool = True):
         self._chk(self.lib.lmot_enable_timing(self.h, int(on)))

@@ -109,9 +109,9 @@ int submit(Ctx* c, Slot* s, const float4* d_pts, int n, bool with_tracker, doubl
   // the slot's previous boxes / counters / host block must have been consumed by the tracker
   LMOT_CUDA(c, cudaStreamWaitEvent(s->stream, s->ev_trk_done, 0));
   if (c->timing) cudaEventRecord(s->ev[0], s->stream);
-  if ((rc = ground_launch(c, s, s->stream, d_pts, n))) return rc;
+  if ((rc = ground_launch(c, s, s->stream, d_pts, n, true))) return rc;
   if (c->timing) cudaEventRecord(s->ev[1], s->stream);
-  if ((rc = cluster_launch(c, s, s->stream, n))) return rc;
+  if ((rc = cluster_launch(c, s, s->stream, n, true))) return rc;
   if (c->timing) cudaEventRecord(s->ev[2], s->stream);
   if ((rc = boxfit_launch(c, s, s->stream, n))) return rc;
   if (c->timing) cudaEventRecord(s->ev[3], s->stream);
@@ -519,6 +519,15 @@ int lmot_frame(lmot_ctx* ctx, const float* points, int n, int stride, double tim
   return lmot_frame_collect(ctx, out);
 }
 
+int lmot_origin_points(lmot_ctx* ctx, double timestamp_us, double v_gps, double yaw_gps, double out6[6]) {
+  if (!ctx || !out6) return LMOT_ERR_INVALID;
+  TrackerHost h = ctx->c.th;                       // peek: fold on a copy
+  origin_points_fold(h, timestamp_us, v_gps, yaw_gps);
+  out6[0] = h.egoPoint[0]; out6[1] = h.egoPoint[1]; out6[2] = h.egoPoint[2];
+  out6[3] = h.egoPoint[0]; out6[4] = h.egoPoint[1]; out6[5] = h.egoPoint[2] + M_PI / 2;
+  return LMOT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- tracker state
 int lmot_tracker_reset(lmot_ctx* ctx) {
   if (!ctx) return LMOT_ERR_INVALID;
@@ -544,6 +553,25 @@ int lmot_tracker_num_tracks(lmot_ctx* ctx, int* n) {
   int rc = fetch_trk_counters(&ctx->c);
   if (rc) return rc;
   *n = ctx->c.h_trk_counters[CNT_N_TRACKS];
+  return LMOT_OK;
+}
+
+int lmot_tracker_table(lmot_ctx* ctx, void** dev_ptr, int* bytes_per_track, int* capacity) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  if (dev_ptr) *dev_ptr = ctx->c.d_tracks;
+  if (bytes_per_track) *bytes_per_track = (int)sizeof(TrackState);
+  if (capacity) *capacity = ctx->c.prm.max_tracks;
+  return LMOT_OK;
+}
+
+int lmot_tracker_set_num_tracks(lmot_ctx* ctx, int n) {
+  if (!ctx || n < 0 || n > ctx->c.prm.max_tracks) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  int rc = drain(c);
+  if (rc) return rc;
+  c->h_trk_counters[CNT_N_TRACKS] = n;
+  LMOT_CUDA(c, cudaMemcpyAsync(c->d_trk_counters + CNT_N_TRACKS, c->h_trk_counters + CNT_N_TRACKS, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
   return LMOT_OK;
 }
 

@@ -31,15 +31,7 @@ constexpr int kCclThreads = 1024;
 constexpr int kCclAll = kCclCtas * kCclThreads;                       // 8192 threads per frame
 constexpr int kCclPerThread = 8;                                       // 32 rows x 250 cells / 1024 threads, rounded up
 
-// component_clustering.cpp:40-48
-__device__ __forceinline__ unsigned cart_cell(float x, float y, float roi) {
-  const float half = fdiv(roi, 2.f);
-  const float xC = fadd(x, half), yC = fadd(y, half);
-  if (!(xC >= 0.f && xC < roi && yC >= 0.f && yC < roi)) return kNoCell;
-  const int xI = (int)floorf(fdiv(fmul((float)kNumGrid, xC), roi));
-  const int yI = (int)floorf(fdiv(fmul((float)kNumGrid, yC), roi));
-  return (unsigned)(xI * kNumGrid + yI);
-}
+__device__ __forceinline__ unsigned cart_cell(float x, float y, float roi) { return cart_cell_of(x, y, roi, kNumGrid); }
 
 __global__ void __launch_bounds__(256)
 cart_count_kernel(const float4* __restrict__ elev, const int* __restrict__ counters, float roi,
@@ -262,8 +254,8 @@ void cluster_free(Slot* s) {
 }
 
 // elevated cloud = s->d_elev with its length in d_counters[CNT_N_ELEV]; n_upper bounds that length on the host
-int cluster_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper) {
-  if (n_upper > 0)
+int cluster_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper, bool counted) {
+  if (n_upper > 0 && !counted)   // `counted`: classify_partition_kernel already binned the elevated points (fused frame path)
     cart_count_kernel<<<(n_upper + 255) / 256, 256, 0, st>>>(s->d_elev, s->d_counters, c->prm.roi_m, s->d_cart, s->d_count);
   ccl_cluster_kernel<<<kCclCtas, kCclThreads, kCclSmem, st>>>(s->d_count, s->d_parent, s->d_rid, s->d_label_grid, s->d_counters);
   LMOT_CUDA(c, cudaGetLastError());

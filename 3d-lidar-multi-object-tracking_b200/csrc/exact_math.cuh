@@ -11,6 +11,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <cmath>
 
 #if defined(__CUDACC__)
 #define LMOT_HD __host__ __device__ __forceinline__
@@ -156,6 +157,16 @@ LMOT_HD float atan2f_fdlibm(float y, float x) {
     case 2: return fsub(pi, fsub(z, pi_lo));
     default: return fsub(fsub(z, pi_lo), pi);
   }
+}
+
+// component_clustering.cpp:40-48: cartesian cell (x*250+y) of a point, 0xFFFF outside the ROI; fp32, no contraction
+LMOT_HD unsigned cart_cell_of(float x, float y, float roi, int num_grid) {
+  const float half = fdiv(roi, 2.f);
+  const float xC = fadd(x, half), yC = fadd(y, half);
+  if (!(xC >= 0.f && xC < roi && yC >= 0.f && yC < roi)) return 0xFFFFu;
+  const int xI = (int)floorf(fdiv(fmul((float)num_grid, xC), roi));
+  const int yI = (int)floorf(fdiv(fmul((float)num_grid, yC), roi));
+  return (unsigned)(xI * num_grid + yI);
 }
 
 }  // namespace lmot

@@ -72,6 +72,7 @@ __global__ void repack_kernel(const float* __restrict__ in, int n, int stride, f
 }
 
 constexpr int kGridThreads = 1024;
+constexpr int kCellsPerThread = (kPolarCells + kGridThreads - 1) / kGridThreads;   // 10
 
 __global__ void __launch_bounds__(kGridThreads, 1)
 polar_grid_kernel(GroundParams p, unsigned* __restrict__ keys, float* __restrict__ o_minz, float* __restrict__ o_height,
@@ -126,39 +127,64 @@ polar_grid_kernel(GroundParams p, unsigned* __restrict__ keys, float* __restrict
   // already, and a neighbour that flips in this pass would have needed this cell to be ground: the in-place
   // sequential pass and this two-phase (decide, then apply) pass are identical.
   {
-    float newh[(kPolarCells + kGridThreads - 1) / kGridThreads];
+    float newh[kCellsPerThread];
     unsigned flip = 0;
-    int j = 0;
-    for (int k = tid; k < kPolarCells; k += kGridThreads, ++j) {
-      const int ch = k / kNumBin, b = k % kNumBin;
-      if (ch >= 1 && ch < kNumChannel - 1 && b >= 1 && b < kNumBin - 1 && !G[k] && G[k + 1] && G[k - 1] &&
-          G[k + kNumBin] && G[k - kNumBin]) {
-        const float a = H[k + 1], bb = H[k - 1], c = H[k + kNumBin], d = H[k - kNumBin];
-        const float lo1 = fminf(a, bb), hi1 = fmaxf(a, bb), lo2 = fminf(c, d), hi2 = fmaxf(c, d);
-        const float m1 = fmaxf(lo1, lo2), m2 = fminf(hi1, hi2);  // the two middle values of the sorted four
-        newh[j] = fdiv(fadd(m1, m2), 2.f);
-        flip |= 1u << j;
+#pragma unroll
+    for (int j = 0; j < kCellsPerThread; ++j) {
+      const int k = tid + j * kGridThreads;
+      newh[j] = 0.f;
+      if (k < kPolarCells) {
+        const int ch = k / kNumBin, b = k - ch * kNumBin;
+        if (ch >= 1 && ch < kNumChannel - 1 && b >= 1 && b < kNumBin - 1 && !G[k] && G[k + 1] && G[k - 1] &&
+            G[k + kNumBin] && G[k - kNumBin]) {
+          const float a = H[k + 1], bb = H[k - 1], c = H[k + kNumBin], d = H[k - kNumBin];
+          const float lo1 = fminf(a, bb), hi1 = fmaxf(a, bb), lo2 = fminf(c, d), hi2 = fmaxf(c, d);
+          const float m1 = fmaxf(lo1, lo2), m2 = fminf(hi1, hi2);  // the two middle values of the sorted four
+          newh[j] = fdiv(fadd(m1, m2), 2.f);
+          flip |= 1u << j;
+        }
       }
     }
     __syncthreads();
-    j = 0;
-    for (int k = tid; k < kPolarCells; k += kGridThreads, ++j)
-      if (flip & (1u << j)) { H[k] = newh[j]; G[k] = 1; }
+#pragma unroll
+    for (int j = 0; j < kCellsPerThread; ++j)
+      if (flip & (1u << j)) { const int k = tid + j * kGridThreads; H[k] = newh[j]; G[k] = 1; }
   }
   __syncthreads();
 
-  // (a8) outlierFilter, ground_removal.cpp:149-174: in place and order dependent along bin; channels independent
-  if (tid >= 1 && tid < kNumChannel - 1) {
-    float* Hc = H + tid * kNumBin;
-    const uint8_t* Gc = G + tid * kNumBin;
+  // (a8) outlierFilter, ground_removal.cpp:149-174: in place along bin, so cell b sees the value written at b-1.
+  // With T = tHmin, a cell is rewritten iff  A(b): all of b-1..b+2 ground, H[b]==T and (H[b+1]!=T or H[b+2]!=T),
+  // and its left value is not T -- either originally, or because b-1 was itself rewritten.  Two consecutive rewrites
+  // force H[b-1]==H[b]==T and H[b+1]!=T, which rules out a rewrite at b-2 (its b+2 is H[b]==T, its b+1 is T): the chain
+  // is at most two cells long, so every cell's final value is a closed form of the ORIGINAL H[b-2..b+2], G[b-2..b+2].
+  {
     const float T = p.t_hmin;
-    for (int b = 1; b < kNumBin - 2; ++b) {
-      if (Gc[b] && Gc[b + 1] && Gc[b - 1] && Gc[b + 2]) {
-        const float h1 = Hc[b - 1], h2 = Hc[b], h3 = Hc[b + 1], h4 = Hc[b + 2];
-        if (h1 != T && h2 == T && h3 != T) Hc[b] = fdiv(fadd(h1, h3), 2.f);
-        else if (h1 != T && h2 == T && h3 == T && h4 != T) Hc[b] = fdiv(fadd(h1, h4), 2.f);
+    float newh[kCellsPerThread];
+    unsigned mod = 0;
+#pragma unroll
+    for (int j = 0; j < kCellsPerThread; ++j) {
+      const int k = tid + j * kGridThreads;
+      newh[j] = 0.f;
+      if (k < kPolarCells) {
+        const int ch = k / kNumBin, b = k - ch * kNumBin;
+        if (ch >= 1 && ch < kNumChannel - 1 && b >= 1 && b < kNumBin - 2 && G[k] && G[k + 1] && G[k - 1] && G[k + 2]) {
+          const float h1 = H[k - 1], h2 = H[k], h3 = H[k + 1], h4 = H[k + 2];
+          if (h2 == T && (h3 != T || h4 != T)) {                  // A(b)
+            float left = h1;
+            bool ok = (h1 != T);
+            if (!ok && b - 1 >= 1 && G[k - 2]) {                  // was b-1 rewritten?  A(b-1) with H[b]==T needs H[b+1]!=T
+              const float h0 = H[k - 2];                          // (flags of b-2..b+1 ground: G[k-2] here, others above)
+              if (h3 != T && h0 != T) { left = fdiv(fadd(h0, h3), 2.f); ok = true; }   // b-1 took its second branch
+            }
+            if (ok) { newh[j] = (h3 != T) ? fdiv(fadd(left, h3), 2.f) : fdiv(fadd(left, h4), 2.f); mod |= 1u << j; }
+          }
+        }
       }
     }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kCellsPerThread; ++j)
+      if (mod & (1u << j)) H[tid + j * kGridThreads] = newh[j];
   }
   __syncthreads();
 
@@ -178,7 +204,8 @@ __global__ void __launch_bounds__(kScanTile)
 classify_partition_kernel(const float4* __restrict__ pts, int n, const uint16_t* __restrict__ cell,
                           const float* __restrict__ hg, double tol, uint8_t* __restrict__ labels,
                           float4* __restrict__ elev, float4* __restrict__ ground,
-                          unsigned long long* tile_desc, int* counters) {
+                          unsigned long long* tile_desc, int* counters, float roi, uint16_t* __restrict__ cart,
+                          int* __restrict__ cart_count) {
   __shared__ int s_tile;
   __shared__ unsigned s_we[32], s_wg[32];
   __shared__ unsigned s_base_e, s_base_g;
@@ -243,8 +270,18 @@ classify_partition_kernel(const float4* __restrict__ pts, int n, const uint16_t*
   }
   __syncthreads();
   const unsigned lt = (1u << lane) - 1u;
-  if (lab == 2) elev[s_base_e + s_we[warp] + __popc(be & lt)] = make_float4(q.x, q.y, q.z, 1.f);
-  else if (lab == 1) ground[s_base_g + s_wg[warp] + __popc(bg & lt)] = make_float4(q.x, q.y, q.z, 1.f);
+  unsigned cc = kNoCell;
+  if (lab == 2) {
+    const unsigned pos = s_base_e + s_we[warp] + __popc(be & lt);
+    elev[pos] = make_float4(q.x, q.y, q.z, 1.f);
+    if (cart_count) { cc = cart_cell_of(q.x, q.y, roi, kNumGrid); cart[pos] = (uint16_t)cc; }
+  } else if (lab == 1) ground[s_base_g + s_wg[warp] + __popc(bg & lt)] = make_float4(q.x, q.y, q.z, 1.f);
+  // fused first pass of clustering (mapCartesianGrid, component_clustering.cpp:38-47): the elevated point is still in
+  // registers, so bin it now instead of re-reading the elevated cloud in a separate kernel
+  if (cart_count) {
+    const unsigned grp = __match_any_sync(0xFFFFFFFFu, cc);
+    if (cc != kNoCell && lane == __ffs(grp) - 1) atomicAdd(&cart_count[cc], __popc(grp));
+  }
 }
 
 __global__ void init_keys_kernel(unsigned* keys) {
@@ -296,7 +333,7 @@ int ground_repack(Ctx* c, cudaStream_t st, const float* d_in, int n, int stride,
   return LMOT_OK;
 }
 
-int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n) {
+int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count) {
   s->cur_points = pts;
   s->cur_n = n;
   const int n_tiles = (n + kScanTile - 1) / kScanTile;
@@ -305,7 +342,8 @@ int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n) {
       c->gp, s->d_polar_key, s->d_minz, s->d_height, s->d_smoothed, s->d_hdiff, s->d_hg, s->d_tile_desc, n_tiles, s->d_counters);
   if (n > 0)
     classify_partition_kernel<<<n_tiles, kScanTile, 0, st>>>(pts, n, s->d_cell, s->d_hg, c->gp.tol, s->d_labels, s->d_elev,
-                                                           s->d_ground, s->d_tile_desc, s->d_counters);
+                                                           s->d_ground, s->d_tile_desc, s->d_counters, c->prm.roi_m, s->d_cart,
+                                                           fuse_count ? s->d_count : nullptr);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }

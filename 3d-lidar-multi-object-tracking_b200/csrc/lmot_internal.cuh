@@ -175,16 +175,18 @@ struct Ctx {
 // ---- stage launchers (asynchronous on the given stream) -------------------------------------------------
 int ground_alloc(Ctx* c, Slot* s);
 void ground_free(Slot* s);
-int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n);   // pts: device float4 array of n points
+// pts: device float4 array of n points; fuse_count: also bin the elevated points into the slot's cartesian count grid
+int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count = false);
 int ground_repack(Ctx* c, cudaStream_t st, const float* d_in, int n, int stride, float4* d_out);
 int cluster_alloc(Ctx* c, Slot* s);
 void cluster_free(Slot* s);
-int cluster_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper);
+int cluster_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper, bool counted = false);
 int cluster_cells_only(Ctx* c, Slot* s, cudaStream_t st, int n_upper);  // d_cart for a cloud whose label grid comes from the caller
 int boxfit_alloc(Ctx* c, Slot* s);
 int boxfit_alloc_shared(Ctx* c);
 void boxfit_free(Slot* s);
 int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper);
+void origin_points_fold(TrackerHost& h, double timestamp, double v_gps, double yaw_gps);
 int tracker_alloc(Ctx* c);
 void tracker_free(Ctx* c);
 // boxes: device float[M][8][3] with M in det_counters[CNT_N_BOXES]; results into the slot's pinned host block

@@ -867,8 +867,7 @@ void tracker_free(Ctx* c) {
 // getOriginPoints (imm_ukf_jpda.cpp:74-172) is scalar bookkeeping on three doubles per frame; it stays on the host.
 // The reference replays its whole delta history every call; the replay is a left fold, so carrying (x, y, yaw) is
 // bit-identical.
-static void origin_points_host(Ctx* c, double timestamp, double v_gps, double yaw_gps) {
-  TrackerHost& h = c->th;
+void origin_points_fold(TrackerHost& h, double timestamp, double v_gps, double yaw_gps) {
   const double firstEgoYawOffset = -0.63035 - M_PI / 2;
   const double dt = (timestamp - h.timestamp) / 1000000.0;
   h.egoVelo = v_gps;
@@ -895,7 +894,7 @@ static void origin_points_host(Ctx* c, double timestamp, double v_gps, double ya
 // boxes: device float[M][8][3] with M in det_counters[CNT_N_BOXES]
 int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, const int* det_counters, double timestamp, double v_gps,
                    double yaw_gps) {
-  origin_points_host(c, timestamp, v_gps, yaw_gps);
+  origin_points_fold(c->th, timestamp, v_gps, yaw_gps);
   TrackerHost& h = c->th;
   OutPtrs o{sl->h_targets, sl->h_vandyaw, sl->h_manage, sl->h_static, sl->h_vis, sl->h_visbb, sl->h_hdr};
   int* det = const_cast<int*>(det_counters);

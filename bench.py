@@ -37,7 +37,7 @@ PKG = "3d-lidar-multi-object-tracking_b200"
 
 WORKLOAD = "hdl64_120k_64trk_full_pipeline"
 SCENE = dict(n_objects=150, lattice_pitch=3.8, ped_fraction=0.65, seed=1)   # ~64 live tracks at steady state
-KERNELS_PER_FRAME = 13   # ground 3 + cluster 2 + box 4 + tracker 4
+KERNELS_PER_FRAME = 12   # ground 3 (classify also bins the elevated points) + cluster 1 + box 4 + tracker 4
 
 
 def make_frames(synth, n_frames, seed_offset=0):

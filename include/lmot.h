@@ -138,6 +138,10 @@ typedef struct lmot_track_out {
 int lmot_track_step(lmot_ctx* ctx, const float* boxes, int m, double timestamp_us, double v_gps, double yaw_gps,
                     lmot_track_out* out);
 
+/* getOriginPoints (imm_ukf_jpda.cpp:74-172) on its own: what the ego origin points WOULD be for this frame, without
+ * advancing the tracker (lmot_track_step / lmot_frame do the same fold internally).  out6 = {x, y, yaw, x, y, yaw+pi/2}. */
+int lmot_origin_points(lmot_ctx* ctx, double timestamp_us, double v_gps, double yaw_gps, double out6[6]);
+
 typedef struct lmot_frame_out {
   int n_elevated, n_ground, num_cluster, n_boxes; /* out */
   float* boxes;        /* nullable, [max_boxes*8*3] */
@@ -182,6 +186,12 @@ int lmot_tracker_num_tracks(lmot_ctx* ctx, int* n);
 int lmot_tracker_dump(lmot_ctx* ctx, double* dumps, int cap, int* n);
 int lmot_tracker_load(lmot_ctx* ctx, const double* dumps, int n, int init, double timestamp_us, double ego_velo,
                       double ego_yaw, double ego_pre_yaw, double ego_point_yaw);
+
+/* Device view of the track table for multi-GPU use (several sensor streams feeding ONE tracker): the owner
+ * rank broadcasts `bytes_per_track * n` bytes from *dev_ptr with NCCL, the other ranks receive into their own table and
+ * then call lmot_tracker_set_num_tracks.  The pointer stays valid for the life of the context. */
+int lmot_tracker_table(lmot_ctx* ctx, void** dev_ptr, int* bytes_per_track, int* capacity);
+int lmot_tracker_set_num_tracks(lmot_ctx* ctx, int n);
 
 /* ---- inspection of the last frame's device state (parity tests, debugging) ----------------------------- */
 /* polar grid after ground removal: each float[80*120] / uint8[80*120], nullable */
