@@ -91,3 +91,31 @@ def test_repeatable_and_stateless(lm, synth):
     lm.ground_remove(synth.uniform_cloud(1000, 12))
     b = lm.ground_remove(pts)
     assert np.array_equal(a["labels"], b["labels"]) and np.array_equal(a["elevated"], b["elevated"])
+
+
+def test_channel_boundaries_fast_and_exact_paths_agree(lm, ref_intended):
+    """polar_bin_kernel takes a guarded fast path for the channel index (ground.cu, kChanGuard) and the exact fdlibm
+    restatement near channel boundaries: clouds that hug the 80 boundaries from both sides, from 1e-7 rad to 1e-3 rad,
+    must land in the reference's cells bit for bit."""
+    rng = np.random.default_rng(42)
+    n_per = 600
+    pts = []
+    for c in range(81):
+        theta0 = -np.pi + c * (2 * np.pi / 80)
+        off = np.concatenate([rng.uniform(-1e-3, 1e-3, n_per // 3), rng.uniform(-2e-5, 2e-5, n_per // 3), rng.uniform(-4e-7, 4e-7, n_per // 3)])
+        th = theta0 + off
+        r = rng.uniform(3.5, 119.0, len(th))
+        z = rng.uniform(-2.2, 0.5, len(th))
+        pts.append(np.stack([r * np.cos(th), r * np.sin(th), z, np.zeros_like(z)], 1))
+    pts = np.concatenate(pts).astype(np.float32)
+    pts = pts[rng.permutation(len(pts))]
+    out = lm.ground_remove(pts)
+    ch, b = lm.debug_cell_index(len(pts))
+    ch_r, b_r = ref_intended.cell_index(pts)
+    d = np.hypot(pts[:, 0], pts[:, 1])
+    kept = ch >= 0
+    assert kept.sum() > 0.9 * len(pts)
+    assert np.array_equal(ch[kept], ch_r[kept]) and np.array_equal(b[kept], b_r[kept])
+    e_ref, g_ref = ref_intended.ground_remove(pts)
+    assert np.array_equal(out["elevated"][:, :3].view(np.uint32), e_ref.view(np.uint32))
+    assert np.array_equal(out["ground"][:, :3].view(np.uint32), g_ref.view(np.uint32))
