@@ -331,6 +331,7 @@ int lmot_ground_remove_dev(lmot_ctx* ctx, const float* d_points, int n) {
   if (!ctx || n < 0 || (n > 0 && !d_points)) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
   if (n > c->max_points) return LMOT_ERR_CAPACITY;
+  if (c->n_in_flight > 0) { int rc = drain(c); if (rc) return rc; }     // slot 0 may still be busy with a pipelined frame
   Slot* s = &c->slots[0];
   c->last_slot = 0;
   return ground_launch(c, s, c->stream, reinterpret_cast<const float4*>(d_points), n);

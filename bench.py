@@ -202,6 +202,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="lmot", choices=["lmot", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=60, help="frames of the CPU baseline sample (rank 0, N=1)")
+    ap.add_argument("--dense-frames", type=int, default=10, help="1M-point frames for the dense roofline measurement (0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -278,6 +279,46 @@ def main():
     peak, peak_src = measured_peak_gbs()
     achieved = ground_bytes / (stage_ms[0] * 1e-3) / 1e9
 
+    # ---- (2b) the streaming stage on DENSE 1M-point frames (BASELINE.json configs[4] shape): the size at which an HBM
+    # roofline fraction is meaningful for ground removal (at 120 k points the stage is launch / latency bound)
+    dense = None
+    if args.dense_frames > 0:
+        dcfg = synth.dense_config(n_objects=SCENE["n_objects"], lattice_pitch=SCENE["lattice_pitch"], ped_fraction=SCENE["ped_fraction"], seed=7 + rank)
+        dfr = []
+        for _, p in synth.frames(dcfg, args.dense_frames):
+            dfr.append(p[:1_000_000])
+        d_dense = torch.from_numpy(np.stack(dfr)).cuda()
+        nd = int(d_dense.shape[1])
+        for i in range(3):
+            ctx.ground_remove_dev(d_dense[i % len(dfr)].data_ptr(), nd)
+        torch.cuda.synchronize()
+        reps = 3 * len(dfr)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for i in range(reps):
+            ctx.ground_remove_dev(d_dense[i % len(dfr)].data_ptr(), nd)
+        g1.record(stream)
+        torch.cuda.synchronize()
+        ms = g0.elapsed_time(g1) / reps
+        out = ctx.ground_remove(dfr[0])
+        nf_d = len(out["elevated"]) + len(out["ground"])
+        db = 16 * nd + 16 * nf_d + 9600 * 24
+        dense = {"workload": "ground_removal stage on dense 1M-point frames", "points_per_frame": nd, "frames_in_ring": len(dfr),
+                 "ring_mib": float(d_dense.numel() * 4 / 2**20), "avg_stage_ms": ms, "algorithmic_bytes_per_launch": db,
+                 "achieved": db / (ms * 1e-3) / 1e9, "unit": "GB/s", "peak": peak, "frac": db / (ms * 1e-3) / 1e9 / peak}
+        del d_dense
+
+    # ---- H2D bandwidth of this box (context for `e2e`: every step moves the 1.92 MB frame over PCIe)
+    hb0, hb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tmp_d = torch.empty_like(d_frames[:8])
+    hb0.record(stream)
+    for _ in range(8):
+        tmp_d.copy_(h_frames[:8], non_blocking=True)
+    hb1.record(stream)
+    torch.cuda.synchronize()
+    h2d_gbs = 8 * tmp_d.numel() * 4 / (hb0.elapsed_time(hb1) * 1e-3) / 1e9
+    del tmp_d
+
     # ---- (3) end to end through the C ABI with host buffers: `e2e`
     ctx.tracker_reset()
     h_np = h_frames.numpy()
@@ -337,13 +378,15 @@ def main():
                        "parallelism": f"{world} independent sensor stream(s), one per GPU, no collective on the data path",
                        "pipeline_depth": int(ctx.params.pipeline_depth),
                        "l2_policy": f"every step reads a different frame of a {ring_mb:.0f} MiB ring (> 126 MB L2)"},
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": int(d2h),
+                    "pinned_h2d_gbs_this_box": h2d_gbs, "pcie_bound_frames_per_s": h2d_gbs * 1e9 / frame_bytes},
             "gpu_launches": KERNELS_PER_FRAME * K,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "ground_removal stage (polar_bin_kernel + polar_grid_kernel + classify_partition_kernel)",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "algorithmic_bytes_per_launch": ground_bytes, "avg_launch_ms": float(stage_ms[0]), "traffic": None},
             "stage_ms": {n: float(v) for n, v in zip(("ground", "cluster", "box", "tracker"), stage_ms)},
+            "roofline_dense_1m": dense,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
