@@ -116,8 +116,8 @@ seg_offsets_kernel(int* __restrict__ table, int* counters,
 
 // ---------------------------------------------------------------------------------------------- B3
 __global__ void __launch_bounds__(kTile)
-scatter_kernel(const uint16_t* __restrict__ pcid, const int* __restrict__ counters, const int* __restrict__ table,
-               const int* __restrict__ seg_start, int* __restrict__ sorted_idx, int max_clusters) {
+scatter_kernel(const uint16_t* __restrict__ pcid, const float4* __restrict__ elev, const int* __restrict__ counters,
+               const int* __restrict__ table, const int* __restrict__ seg_start, float4* __restrict__ sorted_pts, int max_clusters) {
   extern __shared__ int s_cur[];
   const int n = counters[CNT_N_ELEV];
   const int K = min(counters[CNT_NUM_CLUSTER], max_clusters);
@@ -128,6 +128,8 @@ scatter_kernel(const uint16_t* __restrict__ pcid, const int* __restrict__ counte
   __syncthreads();
   const int i = tile * kTile + threadIdx.x;
   const unsigned cid = (i < n) ? pcid[i] : 0u;
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cid != 0) q = __ldg(&elev[i]);            // the point itself travels: box fitting then reads its cluster contiguously
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned grp = __match_any_sync(0xFFFFFFFFu, cid);
   const int leader = __ffs(grp) - 1;
@@ -138,7 +140,7 @@ scatter_kernel(const uint16_t* __restrict__ pcid, const int* __restrict__ counte
       int base = 0;
       if (cid != 0 && lane == leader) { base = s_cur[cid]; s_cur[cid] = base + __popc(grp); }
       base = __shfl_sync(0xFFFFFFFFu, base, leader);
-      if (cid != 0) sorted_idx[base + rank] = i;
+      if (cid != 0) sorted_pts[base + rank] = q;
     }
     __syncthreads();
   }
@@ -206,7 +208,7 @@ __device__ bool rule_filter(const float pc[4][2], float maxZ, int n, const BoxPa
 }
 
 __global__ void __launch_bounds__(kFitThreads)
-box_fit_kernel(const float4* __restrict__ elev, const int* __restrict__ sorted_idx, const int* __restrict__ seg_start,
+box_fit_kernel(const float4* __restrict__ sorted_pts, const int* __restrict__ seg_start,
                const int* __restrict__ seg_size, int* __restrict__ counters, BoxParams P,
                const unsigned long long* __restrict__ mt_raw, int n_raw, int max_clusters, int max_boxes,
                float* __restrict__ cl_box, float* __restrict__ cl_marker, uint8_t* __restrict__ cl_ok,
@@ -232,12 +234,12 @@ box_fit_kernel(const float4* __restrict__ elev, const int* __restrict__ sorted_i
 
   for (int k = blockIdx.x + 1; k <= K; k += gridDim.x) {
     const int n = seg_size[k];
-    const int* seg = sorted_idx + seg_start[k];
+    const float4* seg = sorted_pts + seg_start[k];          // the cluster's points, cloud order
     if (tid == 0) cl_ok[k] = 0;
     if (n < P.min_points || n <= 0) continue;      // ruleBasedFilter's first test (:100) rejects it whatever the fit
 
     // ---- point #0 and the pixel offsets (:218-225)
-    const float4 q0 = __ldg(&elev[seg[0]]);
+    const float4 q0 = __ldg(&seg[0]);
     const int initX = (int)floorf((q0.x + half) * P.pic_scale);
     const int initY = (int)floorf((q0.y + half) * P.pic_scale);
     const int initPicX = initX;
@@ -253,7 +255,7 @@ box_fit_kernel(const float4* __restrict__ elev, const int* __restrict__ sorted_i
     double sx = 0, sy = 0, sz = 0;
     float mnx = FLT_MAX, mny = FLT_MAX, mnz = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX, mxz = -FLT_MAX;
     for (int j = tid; j < n; j += kFitThreads) {
-      const float4 q = __ldg(&elev[seg[j]]);
+      const float4 q = __ldg(&seg[j]);
       const int x = (int)floorf((q.x + half) * P.pic_scale);
       const int y = (int)floorf((q.y + half) * P.pic_scale);
       const int picX = x, picY = (int)(pic - (float)y);
@@ -278,8 +280,8 @@ box_fit_kernel(const float4* __restrict__ elev, const int* __restrict__ sorted_i
     // first-occurrence min / max slope points (:268-280).  If no slope beats the 999 / -999 seeds the reference
     // reads uninitialised floats; defined here as (0,0).
     float minMx = 0.f, minMy = 0.f, maxMx = 0.f, maxMy = 0.f;
-    if (kmin != ~0ull) { const float4 q = __ldg(&elev[seg[(unsigned)(kmin & 0xFFFFFFFFull)]]); minMx = q.x; minMy = q.y; }
-    if (kmax != 0ull) { const float4 q = __ldg(&elev[seg[0xFFFFFFFFu - (unsigned)(kmax & 0xFFFFFFFFull)]]); maxMx = q.x; maxMy = q.y; }
+    if (kmin != ~0ull) { const float4 q = __ldg(&seg[(unsigned)(kmin & 0xFFFFFFFFull)]); minMx = q.x; minMy = q.y; }
+    if (kmax != 0ull) { const float4 q = __ldg(&seg[0xFFFFFFFFu - (unsigned)(kmax & 0xFFFFFFFFull)]); maxMx = q.x; maxMy = q.y; }
     const float xDist = maxMx - minMx, yDist = maxMy - minMy;
     const float slopeDist = sqrtf(xDist * xDist + yDist * yDist);
     const float slope = (maxMy - minMy) / (maxMx - minMx);
@@ -299,7 +301,7 @@ box_fit_kernel(const float4* __restrict__ elev, const int* __restrict__ sorted_i
         const unsigned long long raw = mt_raw[tid % n_raw];
         redraw = raw * un < thr;
         const unsigned pInd = (unsigned)__umul64hi(raw, un);
-        const float4 q = __ldg(&elev[seg[pInd]]);
+        const float4 q = __ldg(&seg[pInd]);
         const float dist = fabsf(slope * q.x - 1 * q.y + maxMy - slope * maxMx) / den;
         myx = q.x; myy = q.y;
         if (dist > 0.f) key = ((unsigned long long)__float_as_uint(dist) << 32) | (0xFFFFFFFFu - (unsigned)tid);
@@ -318,7 +320,7 @@ box_fit_kernel(const float4* __restrict__ elev, const int* __restrict__ sorted_i
           unsigned long long lo = raw * un;
           while (lo < thr) { raw = mt_raw[cur % n_raw]; ++cur; lo = raw * un; }
           const unsigned pInd = (unsigned)__umul64hi(raw, un);
-          const float4 q = __ldg(&elev[seg[pInd]]);
+          const float4 q = __ldg(&seg[pInd]);
           const float dist = fabsf(slope * q.x - 1 * q.y + maxMy - slope * maxMx) / den;
           if (dist > maxDist) { maxDist = dist; maxDx = q.x; maxDy = q.y; }
         }
@@ -544,7 +546,7 @@ int boxfit_alloc(Ctx* c, Slot* s) {
   LMOT_CUDA(c, cudaMalloc(&s->d_table, (size_t)c->max_sort_tiles * K1 * sizeof(int)));
   LMOT_CUDA(c, cudaMalloc(&s->d_seg_start, K1 * sizeof(int)));
   LMOT_CUDA(c, cudaMalloc(&s->d_seg_size, K1 * sizeof(int)));
-  LMOT_CUDA(c, cudaMalloc(&s->d_sorted_idx, np * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_sorted_pts, np * sizeof(float4)));
   LMOT_CUDA(c, cudaMalloc(&s->d_cl_box, (size_t)K1 * 24 * sizeof(float)));
   LMOT_CUDA(c, cudaMalloc(&s->d_cl_marker, (size_t)K1 * 6 * sizeof(float)));
   LMOT_CUDA(c, cudaMalloc(&s->d_cl_ok, K1));
@@ -556,7 +558,7 @@ int boxfit_alloc(Ctx* c, Slot* s) {
 }
 
 void boxfit_free(Slot* s) {
-  cudaFree(s->d_pcid); cudaFree(s->d_table); cudaFree(s->d_seg_start); cudaFree(s->d_seg_size); cudaFree(s->d_sorted_idx);
+  cudaFree(s->d_pcid); cudaFree(s->d_table); cudaFree(s->d_seg_start); cudaFree(s->d_seg_size); cudaFree(s->d_sorted_pts);
   cudaFree(s->d_cl_box); cudaFree(s->d_cl_marker); cudaFree(s->d_cl_ok); cudaFree(s->d_boxes); cudaFree(s->d_markers);
   cudaFree(s->d_done);
 }
@@ -570,7 +572,8 @@ int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper) {
     tile_hist_kernel<<<tiles, kTile, sh, st>>>(s->d_cart, s->d_label_grid, s->d_counters, s->d_pcid, s->d_table, c->prm.max_clusters);
   seg_offsets_kernel<<<1, 1024, 0, st>>>(s->d_table, s->d_counters, s->d_seg_start, s->d_seg_size, c->prm.max_clusters, s->d_done);
   if (tiles > 0)
-    scatter_kernel<<<tiles, kTile, sh, st>>>(s->d_pcid, s->d_counters, s->d_table, s->d_seg_start, s->d_sorted_idx, c->prm.max_clusters);
+    scatter_kernel<<<tiles, kTile, sh, st>>>(s->d_pcid, s->d_elev, s->d_counters, s->d_table, s->d_seg_start, s->d_sorted_pts,
+                                             c->prm.max_clusters);
   BoxParams P;
   const lmot_params& p = c->prm;
   P.roi = p.roi_m;
@@ -580,7 +583,7 @@ int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper) {
   P.t_height_min = p.t_height_min; P.t_height_max = p.t_height_max; P.t_width_min = p.t_width_min; P.t_width_max = p.t_width_max;
   P.t_len_min = p.t_len_min; P.t_len_max = p.t_len_max; P.t_area_max = p.t_area_max; P.t_ratio_min = p.t_ratio_min;
   P.t_ratio_max = p.t_ratio_max; P.min_len_ratio = p.min_len_ratio; P.t_pt_per_m3 = p.t_pt_per_m3;
-  box_fit_kernel<<<c->fit_ctas, kFitThreads, 0, st>>>(s->d_elev, s->d_sorted_idx, s->d_seg_start, s->d_seg_size, s->d_counters, P,
+  box_fit_kernel<<<c->fit_ctas, kFitThreads, 0, st>>>(s->d_sorted_pts, s->d_seg_start, s->d_seg_size, s->d_counters, P,
                                                       c->d_mt_raw, c->n_mt_raw, c->prm.max_clusters, c->prm.max_boxes, s->d_cl_box,
                                                       s->d_cl_marker, s->d_cl_ok, s->d_boxes, s->d_markers, s->h_boxes, s->d_done);
   LMOT_CUDA(c, cudaGetLastError());

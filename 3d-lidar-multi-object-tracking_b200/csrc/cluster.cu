@@ -78,7 +78,7 @@ constexpr int kTileRows = 32;                  // 8 CTAs x 32 rows cover the 250
 constexpr int kRowPitch = 256;                 // shared-memory row pitch (250 columns used)
 constexpr int kSeedRows = kTileRows + 3;       // rows ts-2 .. ts+32
 constexpr int kOccRows = kTileRows + 1;        // rows ts-1 .. ts+31
-constexpr int kCclSmem = kSeedRows * kRowPitch + kOccRows * kRowPitch + kTileRows * kRowPitch * (int)sizeof(int);
+constexpr int kCclSmem = kSeedRows * kRowPitch + kOccRows * kRowPitch + 2 * kTileRows * kRowPitch * (int)sizeof(int);
 
 // One thread-block cluster per frame; CTA r owns grid rows [32r, 32r+32).  Each CTA labels its tile entirely in shared
 // memory (pointer chasing at ~30 cycles instead of ~600 through L2), only the 7 tile borders are merged through
@@ -92,6 +92,7 @@ ccl_cluster_kernel(int* __restrict__ count, int* G, int* rid, int* __restrict__ 
   uint8_t* s_seed = ccl_smem;                                         // [35][256] count > 1, rows ts-2..ts+32
   uint8_t* s_occ = s_seed + kSeedRows * kRowPitch;                    // [33][256] dilated,   rows ts-1..ts+31
   int* s_L = reinterpret_cast<int*>(s_occ + kOccRows * kRowPitch);    // [32][256] local parent (local index) or -1
+  int* s_fin = s_L + kTileRows * kRowPitch;                           // [32][256] flattened local root
   __shared__ int s_warp[32];
   __shared__ int s_tot[kCclCtas];
   const int ts = crank * kTileRows;
@@ -151,16 +152,25 @@ ccl_cluster_kernel(int* __restrict__ count, int* G, int* rid, int* __restrict__ 
     }
   }
   __syncthreads();
-  // D: flatten inside the tile; publish the tile-local root as a GLOBAL linear index
+  // D: flatten inside the tile (shared memory only).  Global memory holds a union-find node only where another CTA
+  // can need one: at the tile-local ROOT cells and in the first / last row of the tile (the border merge looks the
+  // neighbour's root up through them).  Everything else stays in shared memory -- pointer chasing through L2 costs
+  // ~20x more per hop.
   {
     volatile int* Lv = s_L;
     for (int l = tid; l < kTileRows * kRowPitch; l += kCclThreads) {
       const int lx = l >> 8, y = l & 255;
-      if (lx >= rows || y >= kNumGrid) continue;
-      int g = -1;
-      if (Lv[l] >= 0) { const int r = uf_find(Lv, l); g = (ts + (r >> 8)) * kNumGrid + (r & 255); }
-      G[(ts + lx) * kNumGrid + y] = g;
+      if (lx >= rows || y >= kNumGrid || Lv[l] < 0) continue;
+      const int r = uf_find(Lv, l);
+      s_fin[l] = r;                                                   // flattened local root (separate array: no races)
     }
+  }
+  __syncthreads();
+  for (int l = tid; l < kTileRows * kRowPitch; l += kCclThreads) {
+    const int lx = l >> 8, y = l & 255;
+    if (lx >= rows || y >= kNumGrid || s_L[l] < 0) continue;
+    const int r = s_fin[l];
+    if (r == l || lx == 0 || lx == rows - 1) G[(ts + lx) * kNumGrid + y] = (ts + (r >> 8)) * kNumGrid + (r & 255);
   }
   cluster.sync();
   // every CTA has read its halo: zero this tile's counts for the next frame
@@ -182,20 +192,30 @@ ccl_cluster_kernel(int* __restrict__ count, int* G, int* rid, int* __restrict__ 
     }
   }
   cluster.sync();
-  // F: final flatten; roots of this tile in linear order, thread t owns kCclPerThread consecutive cells
+  // F: only the tile-local roots ask global memory for their final root; every other cell reads it from its root
+  // through shared memory
+  for (int l = tid; l < kTileRows * kRowPitch; l += kCclThreads) {
+    const int lx = l >> 8, y = l & 255;
+    if (lx >= rows || y >= kNumGrid || s_L[l] < 0 || s_fin[l] != l) continue;
+    volatile int* Gv = G;
+    s_L[l] = uf_find(Gv, (ts + lx) * kNumGrid + y);                   // s_L of a local root now holds the FINAL global root
+  }
+  __syncthreads();
+  // roots of this tile in linear order, thread t owns kCclPerThread consecutive cells
   const int cbeg = ts * kNumGrid, cend = cbeg + rows * kNumGrid;
   const int tbeg = cbeg + tid * kCclPerThread;
   int roots = 0;
   unsigned rootmask = 0;
-  {
-    volatile int* Gv = G;
+  int fin[kCclPerThread];
 #pragma unroll
-    for (int j = 0; j < kCclPerThread; ++j) {
-      const int k = tbeg + j;
-      if (k < cend && Gv[k] >= 0) {
-        const int r = uf_find(Gv, k);
-        Gv[k] = r;
-        if (r == k) { ++roots; rootmask |= 1u << j; }
+  for (int j = 0; j < kCclPerThread; ++j) {
+    const int k = tbeg + j;
+    fin[j] = -1;
+    if (k < cend) {
+      const int off = k - cbeg, l = (off / kNumGrid) * kRowPitch + off % kNumGrid;
+      if (s_L[l] >= 0) {
+        fin[j] = s_L[s_fin[l]];                                       // final global root of the cell
+        if (fin[j] == k) { ++roots; rootmask |= 1u << j; }
       }
     }
   }
@@ -227,11 +247,12 @@ ccl_cluster_kernel(int* __restrict__ count, int* G, int* rid, int* __restrict__ 
   }
   if (crank == 0 && tid == 0) counters[CNT_NUM_CLUSTER] = total;
   cluster.sync();
-  // G: label grid
-  for (int l = tid; l < rows * kNumGrid; l += kCclThreads) {
-    const int r = __ldcg(&G[cbeg + l]);
-    out[cbeg + l] = r >= 0 ? __ldcg(&rid[r]) : 0;
-  }
+  // G: label grid (the ids of roots that live in other tiles come through L2; the loads are independent)
+  int ids[kCclPerThread];
+#pragma unroll
+  for (int j = 0; j < kCclPerThread; ++j) ids[j] = fin[j] >= 0 ? __ldcg(&rid[fin[j]]) : 0;
+#pragma unroll
+  for (int j = 0; j < kCclPerThread; ++j) if (tbeg + j < cend) out[tbeg + j] = ids[j];
 }
 
 }  // namespace

@@ -90,73 +90,94 @@ __global__ void repack_kernel(const float* __restrict__ in, int n, int stride, f
   if (i < n) out[i] = make_float4(in[(size_t)i * stride], in[(size_t)i * stride + 1], in[(size_t)i * stride + 2], 1.f);
 }
 
-constexpr int kGridThreads = 1024;
-constexpr int kCellsPerThread = (kPolarCells + kGridThreads - 1) / kGridThreads;   // 10
+constexpr int kGridCtas = 8;                       // 10 channels per CTA (+1 halo channel each side, recomputed locally)
+constexpr int kChanPerCta = kNumChannel / kGridCtas;
+constexpr int kGridThreads = 512;
+constexpr int kLocChan = kChanPerCta + 2;
+constexpr int kLocCells = kLocChan * kNumBin;       // 1440
+constexpr int kCellsPerThread = (kLocCells + kGridThreads - 1) / kGridThreads;   // 3
 
+// The 80 channels are independent in every stage except the median filter, which looks one channel to each side:
+// each CTA owns 10 channels and recomputes the clamp / blur / hDiff / flag stages of one halo channel per side, so no
+// inter-CTA synchronisation is needed.  Keys are re-armed by classify_partition_kernel (a neighbour may still be
+// reading this CTA's boundary channel here).
 __global__ void __launch_bounds__(kGridThreads, 1)
-polar_grid_kernel(GroundParams p, unsigned* __restrict__ keys, float* __restrict__ o_minz, float* __restrict__ o_height,
+polar_grid_kernel(GroundParams p, const unsigned* __restrict__ keys, float* __restrict__ o_minz, float* __restrict__ o_height,
                   float* __restrict__ o_smoothed, float* __restrict__ o_hdiff, float* __restrict__ o_hg,
                   unsigned long long* __restrict__ tile_desc, int n_tiles, int* __restrict__ counters) {
-  extern __shared__ unsigned char smem_raw[];
-  float* H = reinterpret_cast<float*>(smem_raw);              // [9600] height
-  uint8_t* G = reinterpret_cast<uint8_t*>(H + kPolarCells);   // [9600] isGround
+  __shared__ float H[kLocCells];
+  __shared__ uint8_t G[kLocCells];
   const int tid = threadIdx.x;
-  const unsigned init_key = fkey(1000.f);                     // Cell::Cell(): minZ = 1000 (ground_removal.cpp:35-38)
+  const int ch0 = blockIdx.x * kChanPerCta - 1;              // global channel of local channel 0 (may be -1)
 
-  // housekeeping for the kernels that follow in this frame
-  for (int t = tid; t < n_tiles; t += kGridThreads) tile_desc[t] = 0ull;
-  if (tid == 0) { counters[CNT_TICKET_A] = 0; counters[CNT_N_ELEV] = 0; counters[CNT_N_GROUND] = 0; }
+  if (blockIdx.x == 0) {                                     // housekeeping for the kernels that follow in this frame
+    for (int t = tid; t < n_tiles; t += kGridThreads) tile_desc[t] = 0ull;
+    if (tid == 0) { counters[CNT_TICKET_A] = 0; counters[CNT_N_ELEV] = 0; counters[CNT_N_GROUND] = 0; }
+  }
 
   // (a4) height clamp, ground_removal.cpp:192-197
-  for (int k = tid; k < kPolarCells; k += kGridThreads) {
-    const float zi = fkey_inv(keys[k]);
-    keys[k] = init_key;                                       // ready for the next frame
-    o_minz[k] = zi;
-    float h;
-    if (zi > p.t_hmin && zi < p.t_hmax) h = zi;
-    else if (zi > p.t_hmax) h = p.h_sensor;
-    else h = p.t_hmin;
-    H[k] = h;
+#pragma unroll
+  for (int j = 0; j < kCellsPerThread; ++j) {
+    const int l = tid + j * kGridThreads;
+    if (l < kLocCells) {
+      const int lc = l / kNumBin, b = l - lc * kNumBin, ch = ch0 + lc;
+      float h = 0.f;
+      if (ch >= 0 && ch < kNumChannel) {
+        const float zi = fkey_inv(__ldg(&keys[ch * kNumBin + b]));
+        if (lc >= 1 && lc <= kChanPerCta) o_minz[ch * kNumBin + b] = zi;
+        if (zi > p.t_hmin && zi < p.t_hmax) h = zi;
+        else if (zi > p.t_hmax) h = p.h_sensor;
+        else h = p.t_hmin;
+      }
+      H[l] = h;
+    }
   }
   __syncthreads();
 
   // (a5) blur, (a6) hDiff, (a7) ground flag -- per channel, neighbours along bin
-  for (int k = tid; k < kPolarCells; k += kGridThreads) {
-    const int b = k % kNumBin;
-    const float h = H[k];
-    double acc = 0.0;                                         // gaus_blur.cpp:58-65, order j = i-1, i, i+1
-    if (b > 0) acc = __dadd_rn(acc, __dmul_rn(p.tap[0], (double)H[k - 1]));
-    acc = __dadd_rn(acc, __dmul_rn(p.tap[1], (double)h));
-    if (b < kNumBin - 1) acc = __dadd_rn(acc, __dmul_rn(p.tap[2], (double)H[k + 1]));
-    const float sm = (float)acc;
-    float hd;                                                 // ground_removal.cpp:95-117
-    if (b == 0) hd = fsub(h, H[k + 1]);
-    else if (b == kNumBin - 1) hd = fsub(h, H[k - 1]);
-    else {
-      const float pre = fsub(h, H[k - 1]), post = fsub(h, H[k + 1]);
-      hd = (pre > post) ? pre : post;
+#pragma unroll
+  for (int j = 0; j < kCellsPerThread; ++j) {
+    const int l = tid + j * kGridThreads;
+    if (l < kLocCells) {
+      const int lc = l / kNumBin, b = l - lc * kNumBin, ch = ch0 + lc;
+      uint8_t g = 0;
+      if (ch >= 0 && ch < kNumChannel) {
+        const float h = H[l];
+        double acc = 0.0;                                       // gaus_blur.cpp:58-65, order j = i-1, i, i+1
+        if (b > 0) acc = __dadd_rn(acc, __dmul_rn(p.tap[0], (double)H[l - 1]));
+        acc = __dadd_rn(acc, __dmul_rn(p.tap[1], (double)h));
+        if (b < kNumBin - 1) acc = __dadd_rn(acc, __dmul_rn(p.tap[2], (double)H[l + 1]));
+        const float sm = (float)acc;
+        float hd;                                               // ground_removal.cpp:95-117
+        if (b == 0) hd = fsub(h, H[l + 1]);
+        else if (b == kNumBin - 1) hd = fsub(h, H[l - 1]);
+        else {
+          const float pre = fsub(h, H[l - 1]), post = fsub(h, H[l + 1]);
+          hd = (pre > post) ? pre : post;
+        }
+        if (lc >= 1 && lc <= kChanPerCta) { o_smoothed[ch * kNumBin + b] = sm; o_hdiff[ch * kNumBin + b] = hd; }
+        g = ((sm < p.t_hmax && hd < p.t_hdiff) || (h < p.t_hmax && hd < p.t_hdiff)) ? 1 : 0;  // :205-214
+      }
+      G[l] = g;
     }
-    o_smoothed[k] = sm;
-    o_hdiff[k] = hd;
-    G[k] = ((sm < p.t_hmax && hd < p.t_hdiff) || (h < p.t_hmax && hd < p.t_hdiff)) ? 1 : 0;  // :205-214
   }
   __syncthreads();
 
   // (a8) applyMedianFilter, ground_removal.cpp:120-146.  A cell flips only if its four neighbours are ground
   // already, and a neighbour that flips in this pass would have needed this cell to be ground: the in-place
-  // sequential pass and this two-phase (decide, then apply) pass are identical.
+  // sequential pass and this two-phase (decide, then apply) pass are identical.  Own channels only.
   {
     float newh[kCellsPerThread];
     unsigned flip = 0;
 #pragma unroll
     for (int j = 0; j < kCellsPerThread; ++j) {
-      const int k = tid + j * kGridThreads;
+      const int l = tid + j * kGridThreads;
       newh[j] = 0.f;
-      if (k < kPolarCells) {
-        const int ch = k / kNumBin, b = k - ch * kNumBin;
-        if (ch >= 1 && ch < kNumChannel - 1 && b >= 1 && b < kNumBin - 1 && !G[k] && G[k + 1] && G[k - 1] &&
-            G[k + kNumBin] && G[k - kNumBin]) {
-          const float a = H[k + 1], bb = H[k - 1], c = H[k + kNumBin], d = H[k - kNumBin];
+      if (l < kLocCells) {
+        const int lc = l / kNumBin, b = l - lc * kNumBin, ch = ch0 + lc;
+        if (lc >= 1 && lc <= kChanPerCta && ch >= 1 && ch < kNumChannel - 1 && b >= 1 && b < kNumBin - 1 && !G[l] && G[l + 1] &&
+            G[l - 1] && G[l + kNumBin] && G[l - kNumBin]) {
+          const float a = H[l + 1], bb = H[l - 1], c = H[l + kNumBin], d = H[l - kNumBin];
           const float lo1 = fminf(a, bb), hi1 = fmaxf(a, bb), lo2 = fminf(c, d), hi2 = fmaxf(c, d);
           const float m1 = fmaxf(lo1, lo2), m2 = fminf(hi1, hi2);  // the two middle values of the sorted four
           newh[j] = fdiv(fadd(m1, m2), 2.f);
@@ -167,7 +188,7 @@ polar_grid_kernel(GroundParams p, unsigned* __restrict__ keys, float* __restrict
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kCellsPerThread; ++j)
-      if (flip & (1u << j)) { const int k = tid + j * kGridThreads; H[k] = newh[j]; G[k] = 1; }
+      if (flip & (1u << j)) { const int l = tid + j * kGridThreads; H[l] = newh[j]; G[l] = 1; }
   }
   __syncthreads();
 
@@ -182,17 +203,18 @@ polar_grid_kernel(GroundParams p, unsigned* __restrict__ keys, float* __restrict
     unsigned mod = 0;
 #pragma unroll
     for (int j = 0; j < kCellsPerThread; ++j) {
-      const int k = tid + j * kGridThreads;
+      const int l = tid + j * kGridThreads;
       newh[j] = 0.f;
-      if (k < kPolarCells) {
-        const int ch = k / kNumBin, b = k - ch * kNumBin;
-        if (ch >= 1 && ch < kNumChannel - 1 && b >= 1 && b < kNumBin - 2 && G[k] && G[k + 1] && G[k - 1] && G[k + 2]) {
-          const float h1 = H[k - 1], h2 = H[k], h3 = H[k + 1], h4 = H[k + 2];
+      if (l < kLocCells) {
+        const int lc = l / kNumBin, b = l - lc * kNumBin, ch = ch0 + lc;
+        if (lc >= 1 && lc <= kChanPerCta && ch >= 1 && ch < kNumChannel - 1 && b >= 1 && b < kNumBin - 2 && G[l] && G[l + 1] &&
+            G[l - 1] && G[l + 2]) {
+          const float h1 = H[l - 1], h2 = H[l], h3 = H[l + 1], h4 = H[l + 2];
           if (h2 == T && (h3 != T || h4 != T)) {                  // A(b)
             float left = h1;
             bool ok = (h1 != T);
-            if (!ok && b - 1 >= 1 && G[k - 2]) {                  // was b-1 rewritten?  A(b-1) with H[b]==T needs H[b+1]!=T
-              const float h0 = H[k - 2];                          // (flags of b-2..b+1 ground: G[k-2] here, others above)
+            if (!ok && b - 1 >= 1 && G[l - 2]) {                  // was b-1 rewritten?  A(b-1) with H[b]==T needs H[b+1]!=T
+              const float h0 = H[l - 2];
               if (h3 != T && h0 != T) { left = fdiv(fadd(h0, h3), 2.f); ok = true; }   // b-1 took its second branch
             }
             if (ok) { newh[j] = (h3 != T) ? fdiv(fadd(left, h3), 2.f) : fdiv(fadd(left, h4), 2.f); mod |= 1u << j; }
@@ -208,9 +230,16 @@ polar_grid_kernel(GroundParams p, unsigned* __restrict__ keys, float* __restrict
   __syncthreads();
 
   // hGround == height for every ground cell (updateGround() follows every height write of a ground cell)
-  for (int k = tid; k < kPolarCells; k += kGridThreads) {
-    o_height[k] = H[k];
-    o_hg[k] = G[k] ? H[k] : -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kCellsPerThread; ++j) {
+    const int l = tid + j * kGridThreads;
+    if (l < kLocCells) {
+      const int lc = l / kNumBin, b = l - lc * kNumBin, ch = ch0 + lc;
+      if (lc >= 1 && lc <= kChanPerCta) {
+        o_height[ch * kNumBin + b] = H[l];
+        o_hg[ch * kNumBin + b] = G[l] ? H[l] : -INFINITY;
+      }
+    }
   }
 }
 
@@ -224,11 +253,13 @@ classify_partition_kernel(const float4* __restrict__ pts, int n, const uint16_t*
                           const float* __restrict__ hg, double tol, uint8_t* __restrict__ labels,
                           float4* __restrict__ elev, float4* __restrict__ ground,
                           unsigned long long* tile_desc, int* counters, float roi, uint16_t* __restrict__ cart,
-                          int* __restrict__ cart_count) {
+                          int* __restrict__ cart_count, unsigned* __restrict__ keys) {
   __shared__ int s_tile;
   __shared__ unsigned s_we[32], s_wg[32];
   __shared__ unsigned s_base_e, s_base_g;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // re-arm the min-z grid for the next frame (Cell::Cell(): minZ = 1000); polar_grid_kernel has consumed it
+  for (int k = blockIdx.x * kScanTile + tid; k < kPolarCells; k += gridDim.x * kScanTile) keys[k] = fkey(1000.f);
   if (tid == 0) s_tile = atomicAdd(&counters[CNT_TICKET_A], 1);
   __syncthreads();
   const int tile = s_tile;
@@ -333,8 +364,6 @@ int ground_alloc(Ctx* c, Slot* s) {
   LMOT_CUDA(c, cudaHostAlloc(&s->h_set, CNT_COUNT * sizeof(int), cudaHostAllocDefault));
   init_keys_kernel<<<(kPolarCells + 255) / 256, 256, 0, st>>>(s->d_polar_key);
   LMOT_CUDA(c, cudaGetLastError());
-  LMOT_CUDA(c, cudaFuncSetAttribute(polar_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kPolarCells * (int)(sizeof(float) + 1)));
   return LMOT_OK;
 }
 
@@ -357,12 +386,12 @@ int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bo
   s->cur_n = n;
   const int n_tiles = (n + kScanTile - 1) / kScanTile;
   if (n > 0) polar_bin_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, c->gp, s->d_cell, s->d_polar_key);
-  polar_grid_kernel<<<1, kGridThreads, kPolarCells * (sizeof(float) + 1), st>>>(
+  polar_grid_kernel<<<kGridCtas, kGridThreads, 0, st>>>(
       c->gp, s->d_polar_key, s->d_minz, s->d_height, s->d_smoothed, s->d_hdiff, s->d_hg, s->d_tile_desc, n_tiles, s->d_counters);
   if (n > 0)
     classify_partition_kernel<<<n_tiles, kScanTile, 0, st>>>(pts, n, s->d_cell, s->d_hg, c->gp.tol, s->d_labels, s->d_elev,
                                                            s->d_ground, s->d_tile_desc, s->d_counters, c->prm.roi_m, s->d_cart,
-                                                           fuse_count ? s->d_count : nullptr);
+                                                           fuse_count ? s->d_count : nullptr, s->d_polar_key);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }

@@ -101,7 +101,7 @@ struct Slot {
   int* d_table = nullptr;              // [tiles][max_clusters+1] tile histograms -> exclusive tile offsets
   int* d_seg_start = nullptr;          // [max_clusters+1] first slot of each cluster in d_sorted_idx
   int* d_seg_size = nullptr;           // [max_clusters+1] points per cluster
-  int* d_sorted_idx = nullptr;         // elevated-point indices grouped by cluster, cloud order inside a cluster
+  float4* d_sorted_pts = nullptr;      // elevated points grouped by cluster, cloud order inside a cluster
   float* d_cl_box = nullptr;           // [max_clusters+1][24] per-cluster box (valid where d_cl_ok)
   float* d_cl_marker = nullptr;        // [max_clusters+1][6]
   uint8_t* d_cl_ok = nullptr;          // [max_clusters+1] rule filter verdict
