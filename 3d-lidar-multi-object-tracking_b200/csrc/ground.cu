@@ -18,6 +18,7 @@
 // results are bit-identical to the reference built for x86-64.
 #include "lmot_internal.cuh"
 #include "exact_math.cuh"
+#include "tma.cuh"
 
 namespace lmot {
 
@@ -64,24 +65,61 @@ __device__ __forceinline__ uint16_t polar_cell(float x, float y, const GroundPar
   return (uint16_t)((int)chF * kNumBin + (int)binF);
 }
 
-__global__ void __launch_bounds__(256) polar_bin_kernel(const float4* __restrict__ pts, int n, GroundParams p,
-                                                        uint16_t* __restrict__ cell, unsigned* __restrict__ keys) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned c = kNoCell;
-  unsigned key = 0xFFFFFFFFu;
-  if (i < n) {
-    const float4 q = __ldg(&pts[i]);
-    c = polar_cell(q.x, q.y, p);
-    cell[i] = (uint16_t)c;
-    float z = q.z;
-    if (z == 0.f) z = 0.f;                       // -0 -> +0 (`z < minZ` does not order them either)
-    if (c != kNoCell && z == z) key = fkey(z);   // NaN z never wins `z < minZ` (ground_removal.cpp:41)
+constexpr int kBinTile = 256;                      // points per TMA tile (4 KB), two tiles in flight per CTA
+
+// K1.  Persistent CTAs; the XYZI frame is staged through shared memory by the bulk async copy engine (TMA, UBLKCP in
+// SASS): one elected thread arms an mbarrier with the tile's byte count and issues a single 4 KB cp.async.bulk, the
+// other 255 threads never touch the LSU for input -- they pick their point up from shared memory when the barrier
+// flips, and the copy of tile t+2 overlaps the binning arithmetic of tile t.
+__global__ void __launch_bounds__(kBinTile) polar_bin_kernel(const float4* __restrict__ pts, int n, GroundParams p,
+                                                             uint16_t* __restrict__ cell, unsigned* __restrict__ keys) {
+  __shared__ alignas(128) float4 s_buf[2][kBinTile];
+  __shared__ alignas(8) uint64_t s_full[2];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n_tiles = (n + kBinTile - 1) / kBinTile;
+  if (tid == 0) { mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); fence_mbar_init(); }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int st = 0; st < 2; ++st) {
+      const int tile = blockIdx.x + st * gridDim.x;
+      if (tile < n_tiles) {
+        const uint32_t bytes = (uint32_t)min(kBinTile, n - tile * kBinTile) * 16u;
+        mbar_arrive_expect_tx(&s_full[st], bytes);
+        bulk_copy_g2s(s_buf[st], pts + (size_t)tile * kBinTile, bytes, &s_full[st]);
+      }
+    }
   }
-  // consecutive HDL-64 returns fall into the same cell: one atomic per distinct cell per warp
-  const unsigned grp = __match_any_sync(0xFFFFFFFFu, c);
-  const unsigned kmin = __reduce_min_sync(grp, key);
-  const int lane = threadIdx.x & 31;
-  if (c != kNoCell && lane == __ffs(grp) - 1 && kmin != 0xFFFFFFFFu) atomicMin(&keys[c], kmin);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int st = it & 1;
+    mbar_wait(&s_full[st], (uint32_t)(it >> 1) & 1u);
+    const int i = tile * kBinTile + tid;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) q = s_buf[st][tid];
+    __syncthreads();                                 // every thread holds its point: the stage can be refilled
+    if (tid == 0) {
+      const int next = tile + 2 * gridDim.x;
+      if (next < n_tiles) {
+        const uint32_t bytes = (uint32_t)min(kBinTile, n - next * kBinTile) * 16u;
+        mbar_arrive_expect_tx(&s_full[st], bytes);
+        bulk_copy_g2s(s_buf[st], pts + (size_t)next * kBinTile, bytes, &s_full[st]);
+      }
+    }
+    unsigned c = kNoCell;
+    unsigned key = 0xFFFFFFFFu;
+    if (i < n) {
+      c = polar_cell(q.x, q.y, p);
+      cell[i] = (uint16_t)c;
+      float z = q.z;
+      if (z == 0.f) z = 0.f;                       // -0 -> +0 (`z < minZ` does not order them either)
+      if (c != kNoCell && z == z) key = fkey(z);   // NaN z never wins `z < minZ` (ground_removal.cpp:41)
+    }
+    // consecutive HDL-64 returns fall into the same cell: one atomic per distinct cell per warp
+    const unsigned grp = __match_any_sync(0xFFFFFFFFu, c);
+    const unsigned kmin = __reduce_min_sync(grp, key);
+    if (c != kNoCell && lane == __ffs(grp) - 1 && kmin != 0xFFFFFFFFu) atomicMin(&keys[c], kmin);
+  }
 }
 
 // generic-stride input -> float4 (the hot path is stride 4 and never runs this)
@@ -385,7 +423,11 @@ int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bo
   s->cur_points = pts;
   s->cur_n = n;
   const int n_tiles = (n + kScanTile - 1) / kScanTile;
-  if (n > 0) polar_bin_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, c->gp, s->d_cell, s->d_polar_key);
+  if (n > 0) {
+    const int bin_tiles = (n + kBinTile - 1) / kBinTile;
+    const int bin_ctas = bin_tiles < c->bin_ctas ? bin_tiles : c->bin_ctas;     // persistent: <= 2 CTAs per SM
+    polar_bin_kernel<<<bin_ctas, kBinTile, 0, st>>>(pts, n, c->gp, s->d_cell, s->d_polar_key);
+  }
   polar_grid_kernel<<<kGridCtas, kGridThreads, 0, st>>>(
       c->gp, s->d_polar_key, s->d_minz, s->d_height, s->d_smoothed, s->d_hdiff, s->d_hg, s->d_tile_desc, n_tiles, s->d_counters);
   if (n > 0)

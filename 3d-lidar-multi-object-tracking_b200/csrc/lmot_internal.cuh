@@ -133,7 +133,7 @@ struct Ctx {
   GroundParams gp;
 
   // ---- capacities
-  int max_points = 0, max_tiles = 0, max_sort_tiles = 0, fit_ctas = 296, n_mt_raw = 0;
+  int max_points = 0, max_tiles = 0, max_sort_tiles = 0, fit_ctas = 296, bin_ctas = 296, n_mt_raw = 0;
   unsigned long long* d_mt_raw = nullptr;  // raw mt19937_64(0) outputs (shared, read only)
 
   // ---- detection slots

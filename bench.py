@@ -329,12 +329,17 @@ def main():
     t0 = time.perf_counter()
     d2h = 0
     collected = 0
+    t_submit = t_collect = 0.0
+    in_flight = 0
     for i in range(W, W + K):            # every step: H2D of its frame; every result is read back inside the region
-        if ctx.frames_in_flight() == depth:
-            r = ctx.frame_collect(); collected += 1
-        ctx.frame_submit(h_np[i], ts[i])
-    while ctx.frames_in_flight() > 0:
-        r = ctx.frame_collect(); collected += 1
+        if in_flight == depth:
+            tc = time.perf_counter(); r = ctx.frame_collect(); t_collect += time.perf_counter() - tc
+            collected += 1; in_flight -= 1
+        tc = time.perf_counter(); ctx.frame_submit(h_np[i], ts[i]); t_submit += time.perf_counter() - tc
+        in_flight += 1
+    while in_flight > 0:
+        tc = time.perf_counter(); r = ctx.frame_collect(); t_collect += time.perf_counter() - tc
+        collected += 1; in_flight -= 1
     barrier()
     e2e_s = time.perf_counter() - t0
     assert collected == K
@@ -379,7 +384,8 @@ def main():
                        "pipeline_depth": int(ctx.params.pipeline_depth),
                        "l2_policy": f"every step reads a different frame of a {ring_mb:.0f} MiB ring (> 126 MB L2)"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": int(d2h),
-                    "pinned_h2d_gbs_this_box": h2d_gbs, "pcie_bound_frames_per_s": h2d_gbs * 1e9 / frame_bytes},
+                    "pinned_h2d_gbs_this_box": h2d_gbs, "pcie_bound_frames_per_s": h2d_gbs * 1e9 / frame_bytes,
+                    "host_us_per_step": {"submit": 1e6 * t_submit / K, "collect_incl_wait": 1e6 * t_collect / K}},
             "gpu_launches": KERNELS_PER_FRAME * K,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "ground_removal stage (polar_bin_kernel + polar_grid_kernel + classify_partition_kernel)",
