@@ -74,7 +74,7 @@ ABI_SYMBOLS = [
     "lmot_ground_remove_dev", "lmot_detect_dev", "lmot_sync",
     "lmot_origin_points", "lmot_tracker_table", "lmot_tracker_set_num_tracks", "lmot_tracker_reset", "lmot_tracker_num_tracks", "lmot_tracker_dump", "lmot_tracker_load",
     "lmot_debug_polar_grid", "lmot_debug_cell_index", "lmot_debug_label_grid", "lmot_selftest_atan2f",
-    "lmot_enable_timing", "lmot_last_stage_ms",
+    "lmot_enable_timing", "lmot_last_stage_ms", "lmot_last_kernel_ms",
 ]
 
 _lib = None
@@ -321,6 +321,11 @@ class Lmot:
         ms = (C.c_float * 4)()
         self._chk(self.lib.lmot_last_stage_ms(self.h, ms))
         return [float(x) for x in ms]
+
+    def last_kernel_ms(self):
+        ms = (C.c_float * 32)(); n = C.c_int(0)
+        self._chk(self.lib.lmot_last_kernel_ms(self.h, ms, 32, C.byref(n)))
+        return [float(ms[i]) for i in range(min(n.value, 32))]
 
     def debug_label_grid(self):
         grid = np.zeros(250 * 250, np.int32)

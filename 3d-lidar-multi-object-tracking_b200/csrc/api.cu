@@ -108,6 +108,7 @@ int submit(Ctx* c, Slot* s, const float4* d_pts, int n, bool with_tracker, doubl
   int rc;
   // the slot's previous boxes / counters / host block must have been consumed by the tracker
   LMOT_CUDA(c, cudaStreamWaitEvent(s->stream, s->ev_trk_done, 0));
+  s->n_kev = 0;
   if (c->timing) cudaEventRecord(s->ev[0], s->stream);
   if ((rc = ground_launch(c, s, s->stream, d_pts, n, true))) return rc;
   if (c->timing) cudaEventRecord(s->ev[1], s->stream);
@@ -149,7 +150,11 @@ int copy_track_outputs(const Slot* s, lmot_track_out* out) {
 // results of a finished slot from its pinned host block
 int collect_slot(Ctx* c, Slot* s, lmot_frame_out* out) {
   LMOT_CUDA(c, cudaEventSynchronize(s->ev_trk_done));
-  if (c->timing && s->has_tracks) for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&c->stage_ms[i], s->ev[i], s->ev[i + 1]);
+  if (c->timing && s->has_tracks) {
+    for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&c->stage_ms[i], s->ev[i], s->ev[i + 1]);
+    c->n_kernel_ms = s->n_kev;
+    for (int i = 0; i < s->n_kev; ++i) cudaEventElapsedTime(&c->kernel_ms[i], i == 0 ? s->ev[0] : s->kev[i - 1], s->kev[i]);
+  }
   if (!s->has_tracks) {   // detect only: no kernel wrote the header
     int rc = fetch_counters(c, s, s->stream);
     if (rc) return rc;
@@ -177,6 +182,7 @@ int slot_create(Ctx* c, Slot* s, int index) {
   LMOT_CUDA(c, cudaEventCreateWithFlags(&s->ev_det_done, cudaEventDisableTiming));
   LMOT_CUDA(c, cudaEventCreateWithFlags(&s->ev_trk_done, cudaEventDisableTiming));
   for (int i = 0; i < 5; ++i) LMOT_CUDA(c, cudaEventCreate(&s->ev[i]));
+  for (int i = 0; i < kMaxKernelEvents; ++i) LMOT_CUDA(c, cudaEventCreate(&s->kev[i]));
   int rc = ground_alloc(c, s);
   if (rc == LMOT_OK) rc = cluster_alloc(c, s);
   if (rc == LMOT_OK) rc = boxfit_alloc(c, s);
@@ -208,6 +214,7 @@ void slot_destroy(Slot* s) {
   if (s->h_vis) cudaFreeHost(s->h_vis);
   if (s->h_visbb) cudaFreeHost(s->h_visbb);
   for (int i = 0; i < 5; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+  for (int i = 0; i < kMaxKernelEvents; ++i) if (s->kev[i]) cudaEventDestroy(s->kev[i]);
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
   if (s->ev_det_done) cudaEventDestroy(s->ev_det_done);
   if (s->ev_trk_done) cudaEventDestroy(s->ev_trk_done);
@@ -231,7 +238,7 @@ int lmot_default_params(lmot_params* p) {
   p->rule_filter = LMOT_RULE_INTENDED;
   p->oracle_compat_first_frame = 1;
   p->max_points = 1 << 20; p->max_clusters = 4096; p->max_boxes = 1024; p->max_tracks = 8192;
-  p->pipeline_depth = 4;
+  p->pipeline_depth = 8;
   return LMOT_OK;
 }
 
@@ -701,6 +708,13 @@ int lmot_selftest_atan2f(const float* y, const float* x, int n, float* out) {
 int lmot_enable_timing(lmot_ctx* ctx, int on) {
   if (!ctx) return LMOT_ERR_INVALID;
   ctx->c.timing = on != 0;
+  return LMOT_OK;
+}
+
+int lmot_last_kernel_ms(lmot_ctx* ctx, float* ms, int cap, int* n) {
+  if (!ctx || !ms || !n) return LMOT_ERR_INVALID;
+  *n = ctx->c.n_kernel_ms;
+  for (int i = 0; i < ctx->c.n_kernel_ms && i < cap; ++i) ms[i] = ctx->c.kernel_ms[i];
   return LMOT_OK;
 }
 

@@ -570,10 +570,13 @@ int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper) {
   const size_t sh = (size_t)K1 * sizeof(int);
   if (tiles > 0)
     tile_hist_kernel<<<tiles, kTile, sh, st>>>(s->d_cart, s->d_label_grid, s->d_counters, s->d_pcid, s->d_table, c->prm.max_clusters);
+  if (tiles > 0) kernel_mark(c, s, st);
   seg_offsets_kernel<<<1, 1024, 0, st>>>(s->d_table, s->d_counters, s->d_seg_start, s->d_seg_size, c->prm.max_clusters, s->d_done);
+  kernel_mark(c, s, st);
   if (tiles > 0)
     scatter_kernel<<<tiles, kTile, sh, st>>>(s->d_pcid, s->d_elev, s->d_counters, s->d_table, s->d_seg_start, s->d_sorted_pts,
                                              c->prm.max_clusters);
+  if (tiles > 0) kernel_mark(c, s, st);
   BoxParams P;
   const lmot_params& p = c->prm;
   P.roi = p.roi_m;

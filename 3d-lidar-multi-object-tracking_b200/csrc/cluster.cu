@@ -278,7 +278,9 @@ void cluster_free(Slot* s) {
 int cluster_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper, bool counted) {
   if (n_upper > 0 && !counted)   // `counted`: classify_partition_kernel already binned the elevated points (fused frame path)
     cart_count_kernel<<<(n_upper + 255) / 256, 256, 0, st>>>(s->d_elev, s->d_counters, c->prm.roi_m, s->d_cart, s->d_count);
+  if (n_upper > 0 && !counted) kernel_mark(c, s, st);
   ccl_cluster_kernel<<<kCclCtas, kCclThreads, kCclSmem, st>>>(s->d_count, s->d_parent, s->d_rid, s->d_label_grid, s->d_counters);
+  kernel_mark(c, s, st);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }

@@ -427,13 +427,16 @@ int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bo
     const int bin_tiles = (n + kBinTile - 1) / kBinTile;
     const int bin_ctas = bin_tiles < c->bin_ctas ? bin_tiles : c->bin_ctas;     // persistent: <= 2 CTAs per SM
     polar_bin_kernel<<<bin_ctas, kBinTile, 0, st>>>(pts, n, c->gp, s->d_cell, s->d_polar_key);
+    kernel_mark(c, s, st);
   }
   polar_grid_kernel<<<kGridCtas, kGridThreads, 0, st>>>(
       c->gp, s->d_polar_key, s->d_minz, s->d_height, s->d_smoothed, s->d_hdiff, s->d_hg, s->d_tile_desc, n_tiles, s->d_counters);
+  kernel_mark(c, s, st);
   if (n > 0)
     classify_partition_kernel<<<n_tiles, kScanTile, 0, st>>>(pts, n, s->d_cell, s->d_hg, c->gp.tol, s->d_labels, s->d_elev,
                                                            s->d_ground, s->d_tile_desc, s->d_counters, c->prm.roi_m, s->d_cart,
                                                            fuse_count ? s->d_count : nullptr, s->d_polar_key);
+  if (n > 0) kernel_mark(c, s, st);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }

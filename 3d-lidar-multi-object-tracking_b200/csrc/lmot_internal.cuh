@@ -55,6 +55,8 @@ struct TrackerHost {
   double fold[3] = {0, 0, -1.5707963267948966};
 };
 
+constexpr int kMaxKernelEvents = 20;
+
 // Detection slot: every buffer the three detection stages (ground -> cluster -> box) touch for ONE frame, plus the
 // stream they run on.  A context owns `pipeline_depth` slots so the detection stages of frame f+1.. run while the
 // tracker (a sequential fold over frames, on its own stream) is still busy with frame f.
@@ -116,8 +118,10 @@ struct Slot {
   float* h_targets = nullptr; double* h_vandyaw = nullptr; int* h_manage = nullptr;
   uint8_t* h_static = nullptr; uint8_t* h_vis = nullptr; float* h_visbb = nullptr;
 
-  // ---- timing
+  // ---- timing (lmot_enable_timing): stage boundaries and, finer, one event after every kernel
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t kev[kMaxKernelEvents] = {};
+  int n_kev = 0;
 };
 
 enum HostHdr { HDR_N_ELEV = 0, HDR_N_GROUND, HDR_NUM_CLUSTER, HDR_N_BOXES, HDR_N_TRACKS, HDR_N_VIS, HDR_ERROR, HDR_COUNT = 16 };
@@ -160,6 +164,8 @@ struct Ctx {
   // ---- timing
   bool timing = false;
   float stage_ms[4] = {0, 0, 0, 0};
+  float kernel_ms[kMaxKernelEvents] = {};
+  int n_kernel_ms = 0;
 };
 
 // error helper: records the CUDA error text in the context and returns LMOT_ERR_CUDA
@@ -171,6 +177,11 @@ struct Ctx {
       return LMOT_ERR_CUDA;                                                                      \
     }                                                                                            \
   } while (0)
+
+// timing mode only: mark the end of the kernel just launched on `st`
+inline void kernel_mark(Ctx* c, Slot* s, cudaStream_t st) {
+  if (c->timing && s->n_kev < kMaxKernelEvents) cudaEventRecord(s->kev[s->n_kev++], st);
+}
 
 // ---- stage launchers (asynchronous on the given stream) -------------------------------------------------
 int ground_alloc(Ctx* c, Slot* s);

@@ -905,12 +905,16 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
     const size_t sh = (size_t)kTBWarps * c->gate_words * 32 * sizeof(unsigned short);
     imm_predict_gate_kernel<<<c->trk_ctas, kTAThreads, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, dt, c->d_gate, c->d_setter,
                                                                  c->d_first_setter, c->d_skip, c->gate_words);
+    kernel_mark(c, sl, st);
     imm_update_kernel<<<c->trk_ctas / kTBWarps + 1, kTBWarps * 32, sh, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_gate,
                                                                            c->d_first_setter, c->d_skip, c->gate_words);
+    kernel_mark(c, sl, st);
     merge_overseg_kernel<<<c->trk_ctas / 4 + 1, 128, 0, st>>>(c->d_tracks, c->d_trk_counters, c->d_new_num);
+    kernel_mark(c, sl, st);
   }
   spawn_output_kernel<<<1, 1024, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_first_setter, c->d_new_num, first, compat,
                                           h.egoPoint[2], c->prm.max_tracks, o);
+  kernel_mark(c, sl, st);
   LMOT_CUDA(c, cudaGetLastError());
   h.timestamp = timestamp;
   h.egoPreYaw = h.egoYaw;

@@ -37,6 +37,8 @@ PKG = "3d-lidar-multi-object-tracking_b200"
 
 WORKLOAD = "hdl64_120k_64trk_full_pipeline"
 SCENE = dict(n_objects=150, lattice_pitch=3.8, ped_fraction=0.65, seed=1)   # ~64 live tracks at steady state
+KERNEL_NAMES = ("polar_bin", "polar_grid", "classify_partition", "ccl_cluster", "tile_hist", "seg_offsets", "scatter", "box_fit",
+                "imm_predict_gate", "imm_update", "merge_overseg", "spawn_output")
 KERNELS_PER_FRAME = 12   # ground 3 (classify also bins the elevated points) + cluster 1 + box 4 + tracker 4
 
 
@@ -265,12 +267,15 @@ def main():
     ctx.tracker_reset()
     ctx.enable_timing(True)
     stage_ms = np.zeros(4)
+    kern_ms = None
     n_elev_sum = 0
     for i in range(W + K):
         ctx.frame_dev(d_frames[i].data_ptr(), n_pts, ts[i])
         r = ctx.frame_fetch(want_boxes=False)
         if i >= W:
             stage_ms += ctx.last_stage_ms()
+            km = np.array(ctx.last_kernel_ms())
+            kern_ms = km if kern_ms is None or len(kern_ms) != len(km) else kern_ms + km
             n_elev_sum += r["n_elevated"] + r["n_ground"]
     ctx.enable_timing(False)
     stage_ms /= K
@@ -392,6 +397,7 @@ def main():
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "algorithmic_bytes_per_launch": ground_bytes, "avg_launch_ms": float(stage_ms[0]), "traffic": None},
             "stage_ms": {n: float(v) for n, v in zip(("ground", "cluster", "box", "tracker"), stage_ms)},
+            "kernel_us_warm": ({n: float(1e3 * v / K) for n, v in zip(KERNEL_NAMES, kern_ms)} if kern_ms is not None and len(kern_ms) == len(KERNEL_NAMES) else None),
             "roofline_dense_1m": dense,
             "cpu_baseline": cpu_baseline,
         }

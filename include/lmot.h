@@ -83,7 +83,7 @@ typedef struct lmot_params {
   int max_clusters;          /* default 4096 (a 250x250 grid with 3x3 dilation cannot hold more) */
   int max_boxes;             /* default 1024 */
   int max_tracks;            /* tracks ever created (dead ones keep their slot), default 8192 */
-  /* frames in flight inside one context: detection stages of frame f+1.. overlap the tracker of frame f (1..8, default 4) */
+  /* frames in flight inside one context: detection stages of frame f+1.. overlap the tracker of frame f (1..8, default 8) */
   int pipeline_depth;
 } lmot_params;
 
@@ -209,6 +209,10 @@ int lmot_selftest_atan2f(const float* y, const float* x, int n, float* out);
  * ms[0] ground, ms[1] cluster, ms[2] box, ms[3] tracker.  Only recorded after lmot_enable_timing(ctx,1). */
 int lmot_enable_timing(lmot_ctx* ctx, int on);
 int lmot_last_stage_ms(lmot_ctx* ctx, float ms[4]);
+/* finer: device time between consecutive kernels of the last timed frame, in launch order (12 kernels: polar_bin,
+ * polar_grid, classify_partition, ccl_cluster, tile_hist, seg_offsets, scatter, box_fit, imm_predict_gate, imm_update,
+ * merge_overseg, spawn_output) */
+int lmot_last_kernel_ms(lmot_ctx* ctx, float* ms, int cap, int* n);
 
 #ifdef __cplusplus
 }
