@@ -282,8 +282,12 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   c->gp.tol = p.ground_tolerance;
   gauss_taps(c->gp.tap);
   int rc = LMOT_OK;
+  // The tracker is the one sequential chain of the pipeline (frame f+1's tracker needs frame f's table): its CTAs get
+  // the highest stream priority so they are never queued behind the detection kernels of later frames.
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->trk_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return LMOT_ERR_CUDA; }
+      cudaStreamCreateWithPriority(&c->trk_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete h; return LMOT_ERR_CUDA; }
   c->stream = c->own_stream;
   rc = boxfit_alloc_shared(c);
   for (int i = 0; i < c->n_slots && rc == LMOT_OK; ++i) rc = slot_create(c, &c->slots[i], i);
