@@ -19,6 +19,10 @@ from __future__ import annotations
 import ctypes as C
 import os
 
+# The frame pipeline uses up to 8 detection streams + 1 tracker stream per context; with the default of 8 hardware
+# work queues streams alias and serialise each other.  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -74,7 +78,7 @@ ABI_SYMBOLS = [
     "lmot_ground_remove_dev", "lmot_detect_dev", "lmot_sync",
     "lmot_origin_points", "lmot_tracker_table", "lmot_tracker_set_num_tracks", "lmot_tracker_reset", "lmot_tracker_num_tracks", "lmot_tracker_dump", "lmot_tracker_load",
     "lmot_debug_polar_grid", "lmot_debug_cell_index", "lmot_debug_label_grid", "lmot_selftest_atan2f",
-    "lmot_enable_timing", "lmot_last_stage_ms", "lmot_last_kernel_ms",
+    "lmot_enable_timing", "lmot_last_stage_ms", "lmot_last_kernel_ms", "lmot_debug_host_ns",
 ]
 
 _lib = None
@@ -321,6 +325,11 @@ class Lmot:
         ms = (C.c_float * 4)()
         self._chk(self.lib.lmot_last_stage_ms(self.h, ms))
         return [float(x) for x in ms]
+
+    def debug_host_ns(self, reset=True):
+        ns = (C.c_double * 4)()
+        self._chk(self.lib.lmot_debug_host_ns(self.h, ns, int(reset)))
+        return [float(x) for x in ns]
 
     def last_kernel_ms(self):
         ms = (C.c_float * 32)(); n = C.c_int(0)

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstring>
 #include <new>
+#include <chrono>
 #include <vector>
 #include "lmot_internal.cuh"
 #include "exact_math.cuh"
@@ -20,6 +21,8 @@ struct lmot_ctx {
 };
 
 namespace {
+
+inline double now_ns() { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // gaussKernel(samples=3, sigma=1.0) exactly as gaus_blur.cpp:26-49 evaluates it (host libm, double)
 void gauss_taps(double tap[3]) {
@@ -106,6 +109,7 @@ Slot* acquire_slot(Ctx* c) {
 // the asynchronous frame: detection on the slot stream, tracker on the tracker stream
 int submit(Ctx* c, Slot* s, const float4* d_pts, int n, bool with_tracker, double ts, double v, double yaw) {
   int rc;
+  struct Tail { Ctx* c; double t0; ~Tail() { c->host_ns[0] += now_ns() - t0; } } tail{c, now_ns()};
   // the slot's previous boxes / counters / host block must have been consumed by the tracker
   LMOT_CUDA(c, cudaStreamWaitEvent(s->stream, s->ev_trk_done, 0));
   s->n_kev = 0;
@@ -149,7 +153,11 @@ int copy_track_outputs(const Slot* s, lmot_track_out* out) {
 
 // results of a finished slot from its pinned host block
 int collect_slot(Ctx* c, Slot* s, lmot_frame_out* out) {
+  const double t0 = now_ns();
   LMOT_CUDA(c, cudaEventSynchronize(s->ev_trk_done));
+  const double t1 = now_ns();
+  c->host_ns[1] += t1 - t0; c->host_ns[3] += 1;
+  struct Tail { Ctx* c; double t1; ~Tail() { c->host_ns[2] += now_ns() - t1; } } tail{c, t1};
   if (c->timing && s->has_tracks) {
     for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&c->stage_ms[i], s->ev[i], s->ev[i + 1]);
     c->n_kernel_ms = s->n_kev;
@@ -719,6 +727,12 @@ int lmot_last_kernel_ms(lmot_ctx* ctx, float* ms, int cap, int* n) {
   if (!ctx || !ms || !n) return LMOT_ERR_INVALID;
   *n = ctx->c.n_kernel_ms;
   for (int i = 0; i < ctx->c.n_kernel_ms && i < cap; ++i) ms[i] = ctx->c.kernel_ms[i];
+  return LMOT_OK;
+}
+
+int lmot_debug_host_ns(lmot_ctx* ctx, double ns[4], int reset) {
+  if (!ctx || !ns) return LMOT_ERR_INVALID;
+  for (int i = 0; i < 4; ++i) { ns[i] = ctx->c.host_ns[i]; if (reset) ctx->c.host_ns[i] = 0; }
   return LMOT_OK;
 }
 

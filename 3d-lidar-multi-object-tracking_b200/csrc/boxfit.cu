@@ -589,6 +589,7 @@ int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper) {
   box_fit_kernel<<<c->fit_ctas, kFitThreads, 0, st>>>(s->d_sorted_pts, s->d_seg_start, s->d_seg_size, s->d_counters, P,
                                                       c->d_mt_raw, c->n_mt_raw, c->prm.max_clusters, c->prm.max_boxes, s->d_cl_box,
                                                       s->d_cl_marker, s->d_cl_ok, s->d_boxes, s->d_markers, s->h_boxes, s->d_done);
+  kernel_mark(c, s, st);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }

@@ -166,6 +166,7 @@ struct Ctx {
   float stage_ms[4] = {0, 0, 0, 0};
   float kernel_ms[kMaxKernelEvents] = {};
   int n_kernel_ms = 0;
+  double host_ns[4] = {0, 0, 0, 0};    // accumulated host time: submit, collect: event wait, collect: copies, calls
 };
 
 // error helper: records the CUDA error text in the context and returns LMOT_ERR_CUDA

@@ -383,6 +383,8 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
 
 // ------------------------------------------------------------------------------------------------ TB
 constexpr int kTBWarps = 4;
+static_assert(sizeof(TrackState) % 8 == 0, "TrackState is copied as 8-byte words");
+constexpr int kTrackWords = (int)(sizeof(TrackState) / 8);
 
 // getBboxArea :482-494 (float arithmetic, abs(float))
 __device__ double bbox_area(const float b[][3]) {
@@ -454,6 +456,7 @@ imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, 
                   const unsigned* __restrict__ gate, const int* __restrict__ first_setter, const uint8_t* __restrict__ skip,
                   int words) {
   extern __shared__ unsigned short s_list_all[];          // per warp: indices of the gated boxes, in box order
+  __shared__ TrackState s_trk[kTBWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int T = trk[CNT_N_TRACKS];
   const int M = det[CNT_N_BOXES];
@@ -462,7 +465,16 @@ imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, 
 
   for (int it = blockIdx.x * kTBWarps + warp; it < T; it += gridDim.x * kTBWarps) {
     if (skip[it]) continue;
-    TrackState& t = tracks[it];
+    // stage the whole track (1.6 KB) in shared memory with coalesced 8-byte loads: the update below touches almost
+    // every field several times, and every one of those touches would otherwise be its own trip to L2 / HBM
+    {
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&tracks[it]);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_trk[warp]);
+      for (int w = lane; w < kTrackWords; w += 32) dst[w] = src[w];
+    }
+    __syncwarp();
+    TrackState& t = s_trk[warp];
+    do {
     const int trackNum0 = t.trackNum;
     const bool secondInit = (trackNum0 == 1);
     // ---- lifetime_ (:232): a gated box counts unless an earlier track already matched it
@@ -666,6 +678,14 @@ imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, 
       t.velo[nv] = xm[2];
       t.nVelo = nv + 1;
     }
+    } while (false);
+    __syncwarp();
+    {
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_trk[warp]);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(&tracks[it]);
+      for (int w = lane; w < kTrackWords; w += 32) dst[w] = src[w];
+    }
+    __syncwarp();
   }
 }
 

@@ -213,6 +213,9 @@ int lmot_last_stage_ms(lmot_ctx* ctx, float ms[4]);
  * polar_grid, classify_partition, ccl_cluster, tile_hist, seg_offsets, scatter, box_fit, imm_predict_gate, imm_update,
  * merge_overseg, spawn_output) */
 int lmot_last_kernel_ms(lmot_ctx* ctx, float* ms, int cap, int* n);
+/* accumulated host-side nanoseconds inside the library: [0] submit (launch calls), [1] collect: waiting for the frame's
+ * event, [2] collect: copying results out of the pinned block, [3] number of collects */
+int lmot_debug_host_ns(lmot_ctx* ctx, double ns[4], int reset);
 
 #ifdef __cplusplus
 }

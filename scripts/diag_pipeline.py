@@ -1,5 +1,6 @@
 """Diagnostic (not part of the bench contract): where does the frame pipeline spend its time?  Run on a GPU box."""
 import importlib, json, os, sys, time
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", os.environ.get("DIAG_CONN", "32"))
 import numpy as np
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -43,12 +44,14 @@ for depth in (1, 2, 4, 8):
     ctx.tracker_reset()
     for i in range(W): ctx.frame_dev(d[i].data_ptr(), n, ts[i])
     ctx.frame_fetch()
+    ctx.debug_host_ns()
     t0 = time.perf_counter(); inflight = 0
     for i in range(W, W + K):
         if inflight == depth: ctx.frame_collect(); inflight -= 1
         ctx.frame_dev(d[i].data_ptr(), n, ts[i]); inflight += 1
     while inflight: ctx.frame_collect(); inflight -= 1
-    res[f"C_dev_collect_depth{depth}"] = dict(fps=K / (time.perf_counter() - t0))
+    hn_ = ctx.debug_host_ns()
+    res[f"C_dev_collect_depth{depth}"] = dict(fps=K / (time.perf_counter() - t0), lib_submit_us=hn_[0] / 1e3 / K, lib_wait_us=hn_[1] / 1e3 / K, lib_copy_us=hn_[2] / 1e3 / K)
     # per-kernel warm times (synchronous frames)
     if depth == 1:
         ctx.tracker_reset(); ctx.enable_timing(True)
