@@ -51,7 +51,7 @@ class Params(C.Structure):
         ("min_cluster_points", C.c_int), ("rule_filter", C.c_int),
         ("oracle_compat_first_frame", C.c_int),
         ("max_points", C.c_int), ("max_clusters", C.c_int), ("max_boxes", C.c_int), ("max_tracks", C.c_int),
-        ("pipeline_depth", C.c_int),
+        ("pipeline_depth", C.c_int), ("result_ring", C.c_int),
     ]
 
 
@@ -74,7 +74,7 @@ class FrameOut(C.Structure):
 ABI_SYMBOLS = [
     "lmot_default_params", "lmot_create", "lmot_destroy", "lmot_strerror", "lmot_last_error", "lmot_build_info",
     "lmot_set_stream", "lmot_ground_remove", "lmot_component_cluster", "lmot_box_fit", "lmot_track_step", "lmot_frame",
-    "lmot_frame_dev", "lmot_frame_fetch", "lmot_frame_submit", "lmot_frame_collect", "lmot_frames_in_flight", "lmot_flush",
+    "lmot_frame_dev", "lmot_frame_fetch", "lmot_frame_submit", "lmot_frame_collect", "lmot_frames_in_flight", "lmot_frame_ready", "lmot_flush",
     "lmot_ground_remove_dev", "lmot_detect_dev", "lmot_sync",
     "lmot_origin_points", "lmot_tracker_table", "lmot_tracker_set_num_tracks", "lmot_tracker_reset", "lmot_tracker_num_tracks", "lmot_tracker_dump", "lmot_tracker_load",
     "lmot_debug_polar_grid", "lmot_debug_cell_index", "lmot_debug_label_grid", "lmot_selftest_atan2f",
@@ -272,6 +272,9 @@ class Lmot:
         fo, bufs = self._frame_out(cap or self.params.max_tracks, want_boxes)
         self._chk(self.lib.lmot_frame_collect(self.h, C.byref(fo)))
         return self._frame_result(fo, bufs, want_boxes)
+
+    def frame_ready(self) -> bool:
+        return self.lib.lmot_frame_ready(self.h) == 1
 
     def frames_in_flight(self) -> int:
         n = C.c_int(0)

@@ -87,54 +87,70 @@ int drain(Ctx* c) {
   for (int i = 0; i < c->n_slots; ++i) LMOT_CUDA(c, cudaStreamSynchronize(c->slots[i].stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->trk_stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
-  for (int i = 0; i < c->n_slots; ++i) c->slots[i].in_flight = false;
+  for (int i = 0; i < c->n_results; ++i) c->results[i].in_flight = false;
   c->n_in_flight = 0;
-  c->oldest = c->next_slot;
+  c->res_oldest = c->res_next;
   return LMOT_OK;
 }
 
-// next slot of the ring; an uncollected result that is still sitting in it is dropped
+// next detection slot of the ring (reuse is ordered on the device by the slot's ev_trk_done)
 Slot* acquire_slot(Ctx* c) {
   Slot* s = &c->slots[c->next_slot];
-  if (s->in_flight) {
-    s->in_flight = false;
-    --c->n_in_flight;
-    c->oldest = (c->next_slot + 1) % c->n_slots;
-  }
   c->last_slot = c->next_slot;
   c->next_slot = (c->next_slot + 1) % c->n_slots;
   return s;
 }
 
+// next result block of the ring; `drop_oldest`: an uncollected result still sitting in it is dropped, otherwise the
+// caller gets nullptr (ring full: collect first)
+Result* acquire_result(Ctx* c, bool drop_oldest) {
+  Result* r = &c->results[c->res_next];
+  if (r->in_flight) {
+    if (!drop_oldest) return nullptr;
+    cudaEventSynchronize(r->ev_done);            // its kernels may still be writing the block
+    r->in_flight = false;
+    --c->n_in_flight;
+    c->res_oldest = (c->res_next + 1) % c->n_results;
+  }
+  c->res_next = (c->res_next + 1) % c->n_results;
+  c->last_res = r;
+  return r;
+}
+
 // the asynchronous frame: detection on the slot stream, tracker on the tracker stream
-int submit(Ctx* c, Slot* s, const float4* d_pts, int n, bool with_tracker, double ts, double v, double yaw) {
+int submit(Ctx* c, Slot* s, Result* r, const float4* d_pts, int n, bool with_tracker, double ts, double v, double yaw) {
   int rc;
   struct Tail { Ctx* c; double t0; ~Tail() { c->host_ns[0] += now_ns() - t0; } } tail{c, now_ns()};
-  // the slot's previous boxes / counters / host block must have been consumed by the tracker
+  s->res = r;
+  r->n_kev = 0;
+  // the slot's previous boxes / counters must have been consumed by the tracker
   LMOT_CUDA(c, cudaStreamWaitEvent(s->stream, s->ev_trk_done, 0));
-  s->n_kev = 0;
-  if (c->timing) cudaEventRecord(s->ev[0], s->stream);
+  if (c->timing) cudaEventRecord(r->ev[0], s->stream);
   if ((rc = ground_launch(c, s, s->stream, d_pts, n, true))) return rc;
-  if (c->timing) cudaEventRecord(s->ev[1], s->stream);
+  if (c->timing) cudaEventRecord(r->ev[1], s->stream);
   if ((rc = cluster_launch(c, s, s->stream, n, true))) return rc;
-  if (c->timing) cudaEventRecord(s->ev[2], s->stream);
+  if (c->timing) cudaEventRecord(r->ev[2], s->stream);
   if ((rc = boxfit_launch(c, s, s->stream, n))) return rc;
-  if (c->timing) cudaEventRecord(s->ev[3], s->stream);
+  if (c->timing) cudaEventRecord(r->ev[3], s->stream);
+  if (!with_tracker)      // no spawn_output_kernel will snapshot the counters: copy them before the slot is reused
+    LMOT_CUDA(c, cudaMemcpyAsync(r->h_det, s->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   LMOT_CUDA(c, cudaEventRecord(s->ev_det_done, s->stream));
   if (with_tracker) {
     LMOT_CUDA(c, cudaStreamWaitEvent(c->trk_stream, s->ev_det_done, 0));
     if ((rc = tracker_launch(c, s, c->trk_stream, s->d_boxes, s->d_counters, ts, v, yaw))) return rc;
-    if (c->timing) cudaEventRecord(s->ev[4], c->trk_stream);
+    if (c->timing) cudaEventRecord(r->ev[4], c->trk_stream);
     LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, c->trk_stream));
+    LMOT_CUDA(c, cudaEventRecord(r->ev_done, c->trk_stream));
   } else {
     LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, s->stream));
+    LMOT_CUDA(c, cudaEventRecord(r->ev_done, s->stream));
   }
-  s->has_tracks = with_tracker;
-  if (!s->in_flight) { s->in_flight = true; ++c->n_in_flight; }
+  r->has_tracks = with_tracker;
+  if (!r->in_flight) { r->in_flight = true; ++c->n_in_flight; }
   return LMOT_OK;
 }
 
-int copy_track_outputs(const Slot* s, lmot_track_out* out) {
+int copy_track_outputs(const Result* s, lmot_track_out* out) {
   const int T = s->h_hdr[HDR_N_TRACKS], nv = s->h_hdr[HDR_N_VIS];
   if (!out) return LMOT_OK;
   out->n_tracks = T; out->n_vis = nv;
@@ -151,36 +167,69 @@ int copy_track_outputs(const Slot* s, lmot_track_out* out) {
   return (T > out->cap) ? LMOT_ERR_CAPACITY : LMOT_OK;
 }
 
-// results of a finished slot from its pinned host block
-int collect_slot(Ctx* c, Slot* s, lmot_frame_out* out) {
+// results of a finished frame from its pinned host block
+int collect_result(Ctx* c, Result* r, lmot_frame_out* out) {
   const double t0 = now_ns();
-  LMOT_CUDA(c, cudaEventSynchronize(s->ev_trk_done));
+  LMOT_CUDA(c, cudaEventSynchronize(r->ev_done));
   const double t1 = now_ns();
   c->host_ns[1] += t1 - t0; c->host_ns[3] += 1;
   struct Tail { Ctx* c; double t1; ~Tail() { c->host_ns[2] += now_ns() - t1; } } tail{c, t1};
-  if (c->timing && s->has_tracks) {
-    for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&c->stage_ms[i], s->ev[i], s->ev[i + 1]);
-    c->n_kernel_ms = s->n_kev;
-    for (int i = 0; i < s->n_kev; ++i) cudaEventElapsedTime(&c->kernel_ms[i], i == 0 ? s->ev[0] : s->kev[i - 1], s->kev[i]);
+  if (c->timing && r->has_tracks) {
+    for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&c->stage_ms[i], r->ev[i], r->ev[i + 1]);
+    c->n_kernel_ms = r->n_kev;
+    for (int i = 0; i < r->n_kev; ++i) cudaEventElapsedTime(&c->kernel_ms[i], i == 0 ? r->ev[0] : r->kev[i - 1], r->kev[i]);
   }
-  if (!s->has_tracks) {   // detect only: no kernel wrote the header
-    int rc = fetch_counters(c, s, s->stream);
-    if (rc) return rc;
-    s->h_hdr[HDR_N_ELEV] = s->h_counters[CNT_N_ELEV]; s->h_hdr[HDR_N_GROUND] = s->h_counters[CNT_N_GROUND];
-    s->h_hdr[HDR_NUM_CLUSTER] = s->h_counters[CNT_NUM_CLUSTER]; s->h_hdr[HDR_N_BOXES] = s->h_counters[CNT_N_BOXES];
-    s->h_hdr[HDR_N_TRACKS] = 0; s->h_hdr[HDR_N_VIS] = 0; s->h_hdr[HDR_ERROR] = s->h_counters[CNT_ERROR];
-    if (s->h_counters[CNT_ERROR]) { set_counter(c, s, s->stream, CNT_ERROR, 0); cudaStreamSynchronize(s->stream); }
+  if (!r->has_tracks) {   // detect only: no kernel wrote the header
+    r->h_hdr[HDR_N_ELEV] = r->h_det[CNT_N_ELEV]; r->h_hdr[HDR_N_GROUND] = r->h_det[CNT_N_GROUND];
+    r->h_hdr[HDR_NUM_CLUSTER] = r->h_det[CNT_NUM_CLUSTER]; r->h_hdr[HDR_N_BOXES] = r->h_det[CNT_N_BOXES];
+    r->h_hdr[HDR_N_TRACKS] = 0; r->h_hdr[HDR_N_VIS] = 0; r->h_hdr[HDR_ERROR] = r->h_det[CNT_ERROR];
   }
-  const int err = s->h_hdr[HDR_ERROR];
+  const int err = r->h_hdr[HDR_ERROR];
   if (out) {
-    out->n_elevated = s->h_hdr[HDR_N_ELEV]; out->n_ground = s->h_hdr[HDR_N_GROUND];
-    out->num_cluster = s->h_hdr[HDR_NUM_CLUSTER]; out->n_boxes = s->h_hdr[HDR_N_BOXES];
+    out->n_elevated = r->h_hdr[HDR_N_ELEV]; out->n_ground = r->h_hdr[HDR_N_GROUND];
+    out->num_cluster = r->h_hdr[HDR_NUM_CLUSTER]; out->n_boxes = r->h_hdr[HDR_N_BOXES];
     const int nb = out->n_boxes < out->max_boxes ? out->n_boxes : out->max_boxes;
-    if (out->boxes && nb > 0) memcpy(out->boxes, s->h_boxes, (size_t)nb * 24 * sizeof(float));
-    const int rc = copy_track_outputs(s, &out->tracks);
+    if (out->boxes && nb > 0) memcpy(out->boxes, r->h_boxes, (size_t)nb * 24 * sizeof(float));
+    const int rc = copy_track_outputs(r, &out->tracks);
     if (rc && !err) return rc;
   }
   return err ? err : LMOT_OK;
+}
+
+int result_create(Ctx* c, Result* r) {
+  const int TC = c->prm.max_tracks, MB = c->prm.max_boxes;
+  const unsigned fl = cudaHostAllocMapped;
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_hdr, HDR_COUNT * sizeof(int), fl));
+  memset(r->h_hdr, 0, HDR_COUNT * sizeof(int));
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_det, CNT_COUNT * sizeof(int), fl));
+  memset(r->h_det, 0, CNT_COUNT * sizeof(int));
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_boxes, (size_t)MB * 24 * sizeof(float), fl));
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_targets, (size_t)TC * 3 * sizeof(float), fl));
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_vandyaw, (size_t)TC * 2 * sizeof(double), fl));
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_manage, (size_t)TC * sizeof(int), fl));
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_static, (size_t)TC, fl));
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_vis, (size_t)TC, fl));
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_visbb, (size_t)TC * 24 * sizeof(float), fl));
+  LMOT_CUDA(c, cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming));
+  LMOT_CUDA(c, cudaEventRecord(r->ev_done, c->stream));
+  for (int i = 0; i < 5; ++i) LMOT_CUDA(c, cudaEventCreate(&r->ev[i]));
+  for (int i = 0; i < kMaxKernelEvents; ++i) LMOT_CUDA(c, cudaEventCreate(&r->kev[i]));
+  return LMOT_OK;
+}
+
+void result_destroy(Result* r) {
+  if (r->h_hdr) cudaFreeHost(r->h_hdr);
+  if (r->h_det) cudaFreeHost(r->h_det);
+  if (r->h_boxes) cudaFreeHost(r->h_boxes);
+  if (r->h_targets) cudaFreeHost(r->h_targets);
+  if (r->h_vandyaw) cudaFreeHost(r->h_vandyaw);
+  if (r->h_manage) cudaFreeHost(r->h_manage);
+  if (r->h_static) cudaFreeHost(r->h_static);
+  if (r->h_vis) cudaFreeHost(r->h_vis);
+  if (r->h_visbb) cudaFreeHost(r->h_visbb);
+  if (r->ev_done) cudaEventDestroy(r->ev_done);
+  for (int i = 0; i < 5; ++i) if (r->ev[i]) cudaEventDestroy(r->ev[i]);
+  for (int i = 0; i < kMaxKernelEvents; ++i) if (r->kev[i]) cudaEventDestroy(r->kev[i]);
 }
 
 int slot_create(Ctx* c, Slot* s, int index) {
@@ -189,40 +238,18 @@ int slot_create(Ctx* c, Slot* s, int index) {
   LMOT_CUDA(c, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
   LMOT_CUDA(c, cudaEventCreateWithFlags(&s->ev_det_done, cudaEventDisableTiming));
   LMOT_CUDA(c, cudaEventCreateWithFlags(&s->ev_trk_done, cudaEventDisableTiming));
-  for (int i = 0; i < 5; ++i) LMOT_CUDA(c, cudaEventCreate(&s->ev[i]));
-  for (int i = 0; i < kMaxKernelEvents; ++i) LMOT_CUDA(c, cudaEventCreate(&s->kev[i]));
   int rc = ground_alloc(c, s);
   if (rc == LMOT_OK) rc = cluster_alloc(c, s);
   if (rc == LMOT_OK) rc = boxfit_alloc(c, s);
   if (rc) return rc;
-  const int TC = c->prm.max_tracks, MB = c->prm.max_boxes;
-  const unsigned fl = cudaHostAllocMapped;
-  LMOT_CUDA(c, cudaHostAlloc(&s->h_hdr, HDR_COUNT * sizeof(int), fl));
-  memset(s->h_hdr, 0, HDR_COUNT * sizeof(int));
-  LMOT_CUDA(c, cudaHostAlloc(&s->h_boxes, (size_t)MB * 24 * sizeof(float), fl));
-  LMOT_CUDA(c, cudaHostAlloc(&s->h_targets, (size_t)TC * 3 * sizeof(float), fl));
-  LMOT_CUDA(c, cudaHostAlloc(&s->h_vandyaw, (size_t)TC * 2 * sizeof(double), fl));
-  LMOT_CUDA(c, cudaHostAlloc(&s->h_manage, (size_t)TC * sizeof(int), fl));
-  LMOT_CUDA(c, cudaHostAlloc(&s->h_static, (size_t)TC, fl));
-  LMOT_CUDA(c, cudaHostAlloc(&s->h_vis, (size_t)TC, fl));
-  LMOT_CUDA(c, cudaHostAlloc(&s->h_visbb, (size_t)TC * 24 * sizeof(float), fl));
   LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, s->stream));   // "free" from the start
   LMOT_CUDA(c, cudaEventRecord(s->ev_det_done, s->stream));
+  s->res = &c->results[0];
   return LMOT_OK;
 }
 
 void slot_destroy(Slot* s) {
   ground_free(s); cluster_free(s); boxfit_free(s);
-  if (s->h_hdr) cudaFreeHost(s->h_hdr);
-  if (s->h_boxes) cudaFreeHost(s->h_boxes);
-  if (s->h_targets) cudaFreeHost(s->h_targets);
-  if (s->h_vandyaw) cudaFreeHost(s->h_vandyaw);
-  if (s->h_manage) cudaFreeHost(s->h_manage);
-  if (s->h_static) cudaFreeHost(s->h_static);
-  if (s->h_vis) cudaFreeHost(s->h_vis);
-  if (s->h_visbb) cudaFreeHost(s->h_visbb);
-  for (int i = 0; i < 5; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
-  for (int i = 0; i < kMaxKernelEvents; ++i) if (s->kev[i]) cudaEventDestroy(s->kev[i]);
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
   if (s->ev_det_done) cudaEventDestroy(s->ev_det_done);
   if (s->ev_trk_done) cudaEventDestroy(s->ev_trk_done);
@@ -246,7 +273,8 @@ int lmot_default_params(lmot_params* p) {
   p->rule_filter = LMOT_RULE_INTENDED;
   p->oracle_compat_first_frame = 1;
   p->max_points = 1 << 20; p->max_clusters = 4096; p->max_boxes = 1024; p->max_tracks = 8192;
-  p->pipeline_depth = 8;
+  p->pipeline_depth = 4;
+  p->result_ring = 32;
   return LMOT_OK;
 }
 
@@ -274,6 +302,8 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   if (p.max_clusters > 65534 || p.max_boxes > 65535) return LMOT_ERR_INVALID;   // u16 cluster ids / box indices
   if (p.pipeline_depth < 1) p.pipeline_depth = 1;
   if (p.pipeline_depth > kMaxSlots) p.pipeline_depth = kMaxSlots;
+  if (p.result_ring < 1) p.result_ring = 1;
+  if (p.result_ring > kMaxResults) p.result_ring = kMaxResults;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return LMOT_ERR_CUDA;
   if (cudaSetDevice(device) != cudaSuccess) return LMOT_ERR_CUDA;
@@ -284,6 +314,7 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   c->device = device;
   c->max_points = p.max_points;
   c->n_slots = p.pipeline_depth;
+  c->n_results = p.result_ring;
   c->gp.r_min = p.r_min; c->gp.r_max = p.r_max; c->gp.t_hmin = p.t_hmin; c->gp.t_hmax = p.t_hmax;
   c->gp.t_hdiff = p.t_hdiff; c->gp.h_sensor = p.h_sensor;
   { volatile float span = p.r_max - p.r_min; c->gp.r_span = span; }
@@ -298,7 +329,9 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
       cudaStreamCreateWithPriority(&c->trk_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete h; return LMOT_ERR_CUDA; }
   c->stream = c->own_stream;
   rc = boxfit_alloc_shared(c);
+  for (int i = 0; i < c->n_results && rc == LMOT_OK; ++i) rc = result_create(c, &c->results[i]);
   for (int i = 0; i < c->n_slots && rc == LMOT_OK; ++i) rc = slot_create(c, &c->slots[i], i);
+  c->last_res = &c->results[0];
   if (rc == LMOT_OK) rc = tracker_alloc(c);
   if (rc == LMOT_OK) rc = (cudaDeviceSynchronize() == cudaSuccess) ? LMOT_OK : LMOT_ERR_CUDA;
   if (rc != LMOT_OK) { lmot_destroy(h); return rc; }
@@ -312,6 +345,7 @@ void lmot_destroy(lmot_ctx* ctx) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (int i = 0; i < c->n_slots; ++i) slot_destroy(&c->slots[i]);
+  for (int i = 0; i < c->n_results; ++i) result_destroy(&c->results[i]);
   tracker_free(c);
   cudaFree(c->d_mt_raw);
   if (c->trk_stream) cudaStreamDestroy(c->trk_stream);
@@ -430,6 +464,8 @@ int lmot_box_fit(lmot_ctx* ctx, const float* elevated, int n, int stride, const 
   LMOT_CUDA(c, cudaMemcpyAsync(s->d_label_grid, grid, kCartCells * sizeof(int), cudaMemcpyHostToDevice, st));
   if ((rc = set_counter(c, s, st, CNT_N_ELEV, n))) return rc;
   if ((rc = set_counter(c, s, st, CNT_NUM_CLUSTER, num_cluster))) return rc;
+  s->res = &c->results[0];
+  s->res->n_kev = 0;
   if ((rc = cluster_cells_only(c, s, st, n))) return rc;
   if ((rc = boxfit_launch(c, s, st, n))) return rc;
   if ((rc = fetch_counters(c, s, st))) return rc;
@@ -453,13 +489,16 @@ int lmot_track_step(lmot_ctx* ctx, const float* boxes, int m, double timestamp_u
   if (rc) return rc;
   Slot* s = &c->slots[0];
   c->last_slot = 0;
+  s->res = &c->results[0];
+  c->last_res = s->res;
+  s->res->n_kev = 0;
   cudaStream_t st = c->stream;
   if (m > 0) LMOT_CUDA(c, cudaMemcpyAsync(s->d_boxes, boxes, (size_t)m * 24 * sizeof(float), cudaMemcpyHostToDevice, st));
   if ((rc = set_counter(c, s, st, CNT_N_BOXES, m))) return rc;
   if ((rc = tracker_launch(c, s, st, s->d_boxes, s->d_counters, timestamp_us, v_gps, yaw_gps))) return rc;
   LMOT_CUDA(c, cudaStreamSynchronize(st));
-  const int err = s->h_hdr[HDR_ERROR];
-  rc = copy_track_outputs(s, out);
+  const int err = s->res->h_hdr[HDR_ERROR];
+  rc = copy_track_outputs(s->res, out);
   return err ? err : rc;
 }
 
@@ -469,9 +508,10 @@ int lmot_detect_dev(lmot_ctx* ctx, const float* d_points, int n) {
   Ctx* c = &ctx->c;
   if (n > c->max_points) return LMOT_ERR_CAPACITY;
   Slot* s = acquire_slot(c);
+  Result* r = acquire_result(c, true);
   LMOT_CUDA(c, cudaEventRecord(s->ev_fork, c->stream));
   LMOT_CUDA(c, cudaStreamWaitEvent(s->stream, s->ev_fork, 0));
-  return submit(c, s, reinterpret_cast<const float4*>(d_points), n, false, 0, 0, 0);
+  return submit(c, s, r, reinterpret_cast<const float4*>(d_points), n, false, 0, 0, 0);
 }
 
 int lmot_frame_dev(lmot_ctx* ctx, const float* d_points, int n, double timestamp_us, double v_gps, double yaw_gps) {
@@ -479,35 +519,38 @@ int lmot_frame_dev(lmot_ctx* ctx, const float* d_points, int n, double timestamp
   Ctx* c = &ctx->c;
   if (n > c->max_points) return LMOT_ERR_CAPACITY;
   Slot* s = acquire_slot(c);
+  Result* r = acquire_result(c, true);
   LMOT_CUDA(c, cudaEventRecord(s->ev_fork, c->stream));          // the caller's stream produced d_points
   LMOT_CUDA(c, cudaStreamWaitEvent(s->stream, s->ev_fork, 0));
-  return submit(c, s, reinterpret_cast<const float4*>(d_points), n, true, timestamp_us, v_gps, yaw_gps);
+  return submit(c, s, r, reinterpret_cast<const float4*>(d_points), n, true, timestamp_us, v_gps, yaw_gps);
 }
 
 int lmot_frame_submit(lmot_ctx* ctx, const float* points, int n, int stride, double timestamp_us, double v_gps, double yaw_gps) {
   if (!ctx) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
   cudaSetDevice(c->device);
-  if (c->n_in_flight >= c->n_slots) return LMOT_ERR_STATE;      // collect first: results would be overwritten
+  if (c->n_in_flight >= c->n_results) return LMOT_ERR_STATE;    // result ring full: collect first
   Slot* s = acquire_slot(c);
+  Result* r = acquire_result(c, false);
+  if (!r) return LMOT_ERR_STATE;
   LMOT_CUDA(c, cudaStreamWaitEvent(s->stream, s->ev_trk_done, 0));
   int rc = upload_points(c, s, s->stream, points, n, stride, s->d_points);
   if (rc) return rc;
-  return submit(c, s, s->d_points, n, true, timestamp_us, v_gps, yaw_gps);
+  return submit(c, s, r, s->d_points, n, true, timestamp_us, v_gps, yaw_gps);
 }
 
 int lmot_frame_collect(lmot_ctx* ctx, lmot_frame_out* out) {
   if (!ctx) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
   if (c->n_in_flight <= 0) return LMOT_ERR_STATE;
-  Slot* s = &c->slots[c->oldest];
+  Result* r = &c->results[c->res_oldest];
   int guard = 0;
-  while (!s->in_flight && guard++ < c->n_slots) { c->oldest = (c->oldest + 1) % c->n_slots; s = &c->slots[c->oldest]; }
-  if (!s->in_flight) return LMOT_ERR_STATE;
-  const int rc = collect_slot(c, s, out);
-  s->in_flight = false;
+  while (!r->in_flight && guard++ < c->n_results) { c->res_oldest = (c->res_oldest + 1) % c->n_results; r = &c->results[c->res_oldest]; }
+  if (!r->in_flight) return LMOT_ERR_STATE;
+  const int rc = collect_result(c, r, out);
+  r->in_flight = false;
   --c->n_in_flight;
-  c->oldest = (c->oldest + 1) % c->n_slots;
+  c->res_oldest = (c->res_oldest + 1) % c->n_results;
   return rc;
 }
 
@@ -517,15 +560,25 @@ int lmot_frames_in_flight(lmot_ctx* ctx, int* n) {
   return LMOT_OK;
 }
 
+// 1 if the oldest submitted frame has finished (lmot_frame_collect would not block), 0 if not, <0 on error
+int lmot_frame_ready(lmot_ctx* ctx) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  if (c->n_in_flight <= 0) return 0;
+  Result* r = &c->results[c->res_oldest];
+  if (!r->in_flight) return 0;
+  return cudaEventQuery(r->ev_done) == cudaSuccess ? 1 : 0;
+}
+
 // results of the MOST RECENT submission; older uncollected ones are dropped
 int lmot_frame_fetch(lmot_ctx* ctx, lmot_frame_out* out) {
   if (!ctx) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
-  Slot* s = &c->slots[c->last_slot];
-  const int rc = collect_slot(c, s, out);
-  for (int i = 0; i < c->n_slots; ++i) c->slots[i].in_flight = false;
+  Result* r = c->last_res;
+  const int rc = collect_result(c, r, out);
+  for (int i = 0; i < c->n_results; ++i) c->results[i].in_flight = false;
   c->n_in_flight = 0;
-  c->oldest = c->next_slot;
+  c->res_oldest = c->res_next;
   return rc;
 }
 

@@ -588,7 +588,7 @@ int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper) {
   P.t_ratio_max = p.t_ratio_max; P.min_len_ratio = p.min_len_ratio; P.t_pt_per_m3 = p.t_pt_per_m3;
   box_fit_kernel<<<c->fit_ctas, kFitThreads, 0, st>>>(s->d_sorted_pts, s->d_seg_start, s->d_seg_size, s->d_counters, P,
                                                       c->d_mt_raw, c->n_mt_raw, c->prm.max_clusters, c->prm.max_boxes, s->d_cl_box,
-                                                      s->d_cl_marker, s->d_cl_ok, s->d_boxes, s->d_markers, s->h_boxes, s->d_done);
+                                                      s->d_cl_marker, s->d_cl_ok, s->d_boxes, s->d_markers, s->res->h_boxes, s->d_done);
   kernel_mark(c, s, st);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;

@@ -57,6 +57,24 @@ struct TrackerHost {
 
 constexpr int kMaxKernelEvents = 20;
 
+// Result block: where one frame's results land.  Pinned, device-mapped host memory written by the kernels themselves
+// (box compaction, spawn_output_kernel) -- the stores ARE the D2H transfer; the host waits on ev_done and reads.
+// The ring of result blocks is independent of the detection slots, so the host can run many frames ahead of the GPU.
+struct Result {
+  int* h_hdr = nullptr;                // [16] n_elev, n_ground, num_cluster, n_boxes, n_tracks, n_vis, error
+  int* h_det = nullptr;                // [CNT_COUNT] raw detection counters (detect-only submissions)
+  float* h_boxes = nullptr;            // [max_boxes][24]
+  float* h_targets = nullptr; double* h_vandyaw = nullptr; int* h_manage = nullptr;
+  uint8_t* h_static = nullptr; uint8_t* h_vis = nullptr; float* h_visbb = nullptr;
+  cudaEvent_t ev_done = nullptr;
+  bool in_flight = false;              // submitted and not yet collected / dropped
+  bool has_tracks = false;             // went through the tracker (frame) or not (detect only)
+  // timing (lmot_enable_timing): stage boundaries and one event after every kernel
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t kev[kMaxKernelEvents] = {};
+  int n_kev = 0;
+};
+
 // Detection slot: every buffer the three detection stages (ground -> cluster -> box) touch for ONE frame, plus the
 // stream they run on.  A context owns `pipeline_depth` slots so the detection stages of frame f+1.. run while the
 // tracker (a sequential fold over frames, on its own stream) is still busy with frame f.
@@ -66,8 +84,6 @@ struct Slot {
   cudaEvent_t ev_fork = nullptr;       // recorded on the caller's stream: the frame's input is ready
   cudaEvent_t ev_det_done = nullptr;   // recorded on the slot stream after box fitting
   cudaEvent_t ev_trk_done = nullptr;   // recorded on the tracker stream when the tracker has consumed the slot
-  bool in_flight = false;              // submitted and not yet collected / dropped
-  bool has_tracks = false;             // the last submission went through the tracker (frame) or not (detect only)
 
   // ---- frame input (host-buffer entry points copy here; *_dev entry points use the caller's pointer)
   float4* d_points = nullptr;
@@ -111,22 +127,13 @@ struct Slot {
   float* d_markers = nullptr;          // [max_boxes][6]
   int* d_done = nullptr;               // last-CTA-done counter
 
-  // ---- results of the frame in pinned, device-mapped host memory: written by the kernels themselves (box
-  // compaction, spawn_output_kernel), read by the host after ev_trk_done -- no sized D2H copies on the hot path
-  int* h_hdr = nullptr;                // [16] n_elev, n_ground, num_cluster, n_boxes, n_tracks, n_vis, error
-  float* h_boxes = nullptr;            // [max_boxes][24]
-  float* h_targets = nullptr; double* h_vandyaw = nullptr; int* h_manage = nullptr;
-  uint8_t* h_static = nullptr; uint8_t* h_vis = nullptr; float* h_visbb = nullptr;
-
-  // ---- timing (lmot_enable_timing): stage boundaries and, finer, one event after every kernel
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t kev[kMaxKernelEvents] = {};
-  int n_kev = 0;
+  struct Result* res = nullptr;        // result block of the frame currently (or last) processed on this slot
 };
 
 enum HostHdr { HDR_N_ELEV = 0, HDR_N_GROUND, HDR_NUM_CLUSTER, HDR_N_BOXES, HDR_N_TRACKS, HDR_N_VIS, HDR_ERROR, HDR_COUNT = 16 };
 
 constexpr int kMaxSlots = 8;
+constexpr int kMaxResults = 64;
 
 struct Ctx {
   lmot_params prm;
@@ -144,9 +151,13 @@ struct Ctx {
   int n_slots = 1;
   Slot slots[kMaxSlots];
   int next_slot = 0;                   // slot of the next submission
-  int oldest = 0;                      // slot of the oldest in-flight submission
-  int n_in_flight = 0;
   int last_slot = 0;                   // slot of the most recent submission (debug getters read it)
+
+  // ---- result ring
+  int n_results = 1;
+  Result results[kMaxResults];
+  int res_next = 0, res_oldest = 0, n_in_flight = 0;
+  Result* last_res = nullptr;
 
   // ---- tracker
   TrackerHost th;
@@ -181,7 +192,7 @@ struct Ctx {
 
 // timing mode only: mark the end of the kernel just launched on `st`
 inline void kernel_mark(Ctx* c, Slot* s, cudaStream_t st) {
-  if (c->timing && s->n_kev < kMaxKernelEvents) cudaEventRecord(s->kev[s->n_kev++], st);
+  if (c->timing && s->res && s->res->n_kev < kMaxKernelEvents) cudaEventRecord(s->res->kev[s->res->n_kev++], st);
 }
 
 // ---- stage launchers (asynchronous on the given stream) -------------------------------------------------

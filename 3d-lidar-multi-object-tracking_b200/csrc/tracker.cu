@@ -916,7 +916,8 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
                    double yaw_gps) {
   origin_points_fold(c->th, timestamp, v_gps, yaw_gps);
   TrackerHost& h = c->th;
-  OutPtrs o{sl->h_targets, sl->h_vandyaw, sl->h_manage, sl->h_static, sl->h_vis, sl->h_visbb, sl->h_hdr};
+  Result* r = sl->res;
+  OutPtrs o{r->h_targets, r->h_vandyaw, r->h_manage, r->h_static, r->h_vis, r->h_visbb, r->h_hdr};
   int* det = const_cast<int*>(det_counters);
   const int first = h.init ? 0 : 1;
   const int compat = c->prm.oracle_compat_first_frame ? 1 : 0;

@@ -329,7 +329,7 @@ def main():
     # ---- (3) end to end through the C ABI with host buffers: `e2e`
     ctx.tracker_reset()
     h_np = h_frames.numpy()
-    depth = int(ctx.params.pipeline_depth)
+    depth = int(ctx.params.result_ring) - 1     # frames the host may be ahead of the results it has read back
     for i in range(W):
         ctx.frame(h_np[i], ts[i])
     barrier()
@@ -388,7 +388,7 @@ def main():
             "config": {"workload": WORKLOAD, "points_per_frame": n_pts, "scene": SCENE, "live_tracks_end": live_tracks,
                        "tracks_in_table_end": int(len(res_dev["track_manage"])), "rule_filter": "INTENDED",
                        "parallelism": f"{world} independent sensor stream(s), one per GPU, no collective on the data path",
-                       "pipeline_depth": int(ctx.params.pipeline_depth),
+                       "pipeline_depth": int(ctx.params.pipeline_depth), "result_ring": int(ctx.params.result_ring),
                        "l2_policy": f"every step reads a different frame of a {ring_mb:.0f} MiB ring (> 126 MB L2)"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": int(d2h),
                     "pinned_h2d_gbs_this_box": h2d_gbs, "pcie_bound_frames_per_s": h2d_gbs * 1e9 / frame_bytes,

@@ -83,8 +83,10 @@ typedef struct lmot_params {
   int max_clusters;          /* default 4096 (a 250x250 grid with 3x3 dilation cannot hold more) */
   int max_boxes;             /* default 1024 */
   int max_tracks;            /* tracks ever created (dead ones keep their slot), default 8192 */
-  /* frames in flight inside one context: detection stages of frame f+1.. overlap the tracker of frame f (1..8, default 8) */
+  /* frames in flight inside one context: detection stages of frame f+1.. overlap the tracker of frame f (1..8, default 4) */
   int pipeline_depth;
+  /* result blocks (pinned host memory) = how many submitted frames may wait to be collected (1..64, default 32) */
+  int result_ring;
 } lmot_params;
 
 typedef struct lmot_ctx lmot_ctx;
@@ -159,12 +161,13 @@ int lmot_frame(lmot_ctx* ctx, const float* points, int n, int stride_floats, dou
  * its own stream and consumes the box lists in submission order.  Results are identical to frame-at-a-time calls.
  *
  * lmot_frame_submit  : HOST frame (pinned memory recommended) -> H2D + all four stages, returns immediately.
- *                      LMOT_ERR_STATE if pipeline_depth frames are already waiting to be collected.
+ *                      LMOT_ERR_STATE if result_ring frames are already waiting to be collected (the result ring is
+ *                      independent of pipeline_depth, so the host may run far ahead of the GPU).
  * lmot_frame_collect : blocks until the OLDEST submitted frame is done and returns its results
  *                      (the kernels wrote them into pinned host memory; no device copy is issued here).
  * lmot_frame_dev     : like submit, but the frame is already on the device (stride 4 floats, 16-byte aligned); ordered
  *                      after the work already queued on the context's caller stream (lmot_set_stream).  Uncollected
- *                      results older than pipeline_depth submissions are dropped.
+ *                      results older than result_ring submissions are dropped.
  * lmot_frame_fetch   : waits for everything submitted so far and returns the results of the MOST RECENT frame.
  * lmot_flush         : makes the caller stream wait (on the device, not the host) for everything submitted so far, so
  *                      that CUDA events recorded on the caller stream bracket the work. */
@@ -172,6 +175,8 @@ int lmot_frame_submit(lmot_ctx* ctx, const float* points, int n, int stride_floa
                       double yaw_gps);
 int lmot_frame_collect(lmot_ctx* ctx, lmot_frame_out* out);
 int lmot_frames_in_flight(lmot_ctx* ctx, int* n);
+/* 1 if lmot_frame_collect would return without waiting, 0 if the oldest frame is still running or nothing is in flight */
+int lmot_frame_ready(lmot_ctx* ctx);
 int lmot_frame_dev(lmot_ctx* ctx, const float* d_points, int n, double timestamp_us, double v_gps, double yaw_gps);
 int lmot_frame_fetch(lmot_ctx* ctx, lmot_frame_out* out);
 int lmot_flush(lmot_ctx* ctx);

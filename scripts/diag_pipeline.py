@@ -16,7 +16,7 @@ h = torch.from_numpy(frames).pin_memory(); d = h.cuda(); hn = h.numpy()
 torch.cuda.synchronize()
 res = {}
 for depth in (1, 2, 4, 8):
-    prm = lmot.default_params(); prm.pipeline_depth = depth
+    prm = lmot.default_params(); prm.pipeline_depth = depth; prm.result_ring = int(os.environ.get('DIAG_RING', '32'))
     ctx = lmot.Lmot(prm)
     st = torch.cuda.current_stream(); ctx.set_stream(st.cuda_stream)
     # A: device-resident, host never blocks
@@ -35,7 +35,7 @@ for depth in (1, 2, 4, 8):
     for i in range(W): ctx.frame(hn[i], ts[i])
     t0 = time.perf_counter(); inflight = 0; tsub = tcol = 0.0
     for i in range(W, W + K):
-        if inflight == depth:
+        if inflight == prm.result_ring - 1:
             a = time.perf_counter(); ctx.frame_collect(); tcol += time.perf_counter() - a; inflight -= 1
         a = time.perf_counter(); ctx.frame_submit(hn[i], ts[i]); tsub += time.perf_counter() - a; inflight += 1
     while inflight: ctx.frame_collect(); inflight -= 1
@@ -47,7 +47,7 @@ for depth in (1, 2, 4, 8):
     ctx.debug_host_ns()
     t0 = time.perf_counter(); inflight = 0
     for i in range(W, W + K):
-        if inflight == depth: ctx.frame_collect(); inflight -= 1
+        if inflight == prm.result_ring - 1: ctx.frame_collect(); inflight -= 1
         ctx.frame_dev(d[i].data_ptr(), n, ts[i]); inflight += 1
     while inflight: ctx.frame_collect(); inflight -= 1
     hn_ = ctx.debug_host_ns()

@@ -28,10 +28,12 @@ def _same(a, b):
 def test_submit_collect_equals_frame_at_a_time(pkg, synth):
     frames = list(synth.frames(synth.SceneConfig(seed=13, n_objects=90, lattice_pitch=4.5), 14))
     base = _run_sync(pkg, frames, 1)
-    for depth in (2, 4):
+    for depth, ring in ((2, 2), (4, 3), (4, 32)):
         prm = pkg.default_params()
         prm.pipeline_depth = depth
+        prm.result_ring = ring
         ctx = pkg.Lmot(prm)
+        depth = ring
         try:
             got = []
             for ts, p in frames:
