@@ -136,7 +136,7 @@ __device__ void ukf_initialize(TrackState& t, double zx, double zy) {   // UKF::
 }
 
 // ------------------------------------------------------------------------------------------------ TA
-constexpr int kTAThreads = 96;
+constexpr int kTAThreads = 128;     // warps 0-2: one motion model each; warp 3: explosion guard, then helps gating
 
 struct TAShared {
   double xp[3][5];       // pre-interaction states of the three models
@@ -145,7 +145,8 @@ struct TAShared {
   double Xs[3][15][5];   // per model: predicted sigma points
   double Pm[3][25];      // per model: mixed covariance
   double S[3][4], Tc[3][10], zp[3][2];
-  int flag;              // 0 run, 1 skip
+  int flag;              // 0 run, 1 skip (dead track)
+  int explode;           // det(P_merge) > 10 or P_merge(4,4) > 1000 (:828-831), computed by warp 3 while warps 0-2 predict
 };
 
 __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
@@ -167,9 +168,7 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
     __syncthreads();
     if (tid == 0) {
       t.isVisBB = 0;                                          // :814
-      int flag = 0;
-      if (t.trackNum == 0) flag = 1;                          // :826
-      else if (det_lu<5>(t.P[0]) > 10 || t.P[0][24] > 1000) { t.trackNum = 0; flag = 1; }   // :828-831
+      const int flag = (t.trackNum == 0) ? 1 : 0;             // :826
       sh.flag = flag;
       skip[it] = (uint8_t)flag;
     }
@@ -179,13 +178,17 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
     const double mp0 = t.modeProb[0], mp1 = t.modeProb[1], mp2 = t.modeProb[2];
     __syncthreads();
     if (sh.flag) continue;
-
+    // guard :828-831 on the side: the serial 5x5 LU no longer sits in front of the prediction
+    if (tid == 96) sh.explode = (det_lu<5>(t.P[0]) > 10 || t.P[0][24] > 1000) ? 1 : 0;
+    double x[5] = {0, 0, 0, 0, 0};
+    double Pe = 0.0, zp0 = 0.0, zp1 = 0.0;
+    double Si[4] = {0, 0, 0, 0};
+    if (model < 3) {
     // ---- MixingProbability (ukf.cpp:439-455) for this warp's model column j = model
     const double pj0 = (model == 0) ? 0.9 : 0.05, pj1 = (model == 1) ? 0.9 : 0.05, pj2 = (model == 2) ? 0.9 : 0.05;
     const double sumProb = mp0 * pj0 + mp1 * pj1 + mp2 * pj2;
     const double mu0 = mp0 * pj0 / sumProb, mu1 = mp1 * pj1 / sumProb, mu2 = mp2 * pj2 / sumProb;
     // ---- Interaction (:458-500)
-    double x[5];
 #pragma unroll
     for (int e = 0; e < 5; ++e) x[e] = mu0 * sh.xp[0][e] + mu1 * sh.xp[1][e] + mu2 * sh.xp[2][e];
     x[3] = wrap_pi(sh.xp[model][3]);
@@ -270,8 +273,7 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
       x[e] = acc;
     }
     x[3] = wrap_pi(x[3]);
-    double Pe = 0.0;      // predicted covariance element (:746-755)
-    if (lane < 25) {
+    if (lane < 25) {      // predicted covariance element (:746-755)
       const int r = lane / 5, c = lane % 5;
       for (int i = 0; i < 15; ++i) {
         double dr = sh.Xs[model][i][r] - x[r], dc = sh.Xs[model][i][c] - x[c];
@@ -281,7 +283,6 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
       }
     }
     // ---- UpdateLidar (:778-902)
-    double zp0 = 0.0, zp1 = 0.0;
     for (int i = 0; i < 15; ++i) { const double w = (i == 0) ? w0 : wi; zp0 = zp0 + w * sh.Xs[model][i][0]; zp1 = zp1 + w * sh.Xs[model][i][1]; }
     if (lane < 4) {
       const int r = lane >> 1, c = lane & 1;
@@ -302,8 +303,14 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
       sh.Tc[model][e] = acc;
     }
     __syncwarp();
-    double Si[4];
     inv2_lu(sh.S[model], Si);
+    }   // model < 3
+    __syncthreads();                      // the guard's verdict is in
+    if (sh.explode) {
+      if (tid == 0) { t.trackNum = 0; skip[it] = 1; }
+      continue;
+    }
+    if (model < 3) {
     // write back: x_, P_, zPred, S, K
     if (lane < 5) t.x[1 + model][lane] = x[lane];
     if (lane < 25) t.P[1 + model][lane] = Pe;
@@ -313,6 +320,7 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
     }
     if (lane < 4) t.S[model][lane] = sh.S[model][lane];
     if (lane == 0) { t.zPred[model][0] = zp0; t.zPred[model][1] = zp1; sh.zp[model][0] = zp0; sh.zp[model][1] = zp1; }
+    }   // model < 3
     __syncthreads();
 
     // ---- findMaxZandS (:176-203), gate scale x4 and explosion guard (:843-851)
@@ -336,7 +344,7 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
     // ---- measurementValidation (:205-257): gate bits for every box; warps take 32-box chunks round-robin
     const int nchunk = (M + 31) >> 5;
     if (!secondInit) {
-      for (int ch = model; ch < nchunk; ch += 3) {
+      for (int ch = model; ch < nchunk; ch += 4) {
         const int b = ch * 32 + lane;
         bool g = false;
         if (b < M) {

@@ -238,7 +238,11 @@ def main():
     ring_mb = d_frames.numel() * 4 / 2**20
 
     ctx = lmot.Lmot(device=local_rank)
-    stream = torch.cuda.current_stream()
+    # a REAL stream: torch's default stream has handle 0, which lmot_set_stream reads as "use the context's own stream" --
+    # CUDA events recorded on stream 0 would then not be ordered with the pipeline at all
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     frame_bytes = n_pts * 16
 

@@ -98,8 +98,10 @@ const char* lmot_strerror(int status);
 const char* lmot_last_error(const lmot_ctx* ctx); /* text of the last CUDA error seen by this context */
 const char* lmot_build_info(void);
 
-/* Run every kernel of this context on an existing CUDA stream (cudaStream_t passed as void*), e.g. torch's
- * current stream, instead of the context's own.  NULL restores the context's stream. */
+/* Caller stream (cudaStream_t passed as void*): stage-by-stage entry points run on it, and the frame pipeline forks from /
+ * joins into it (lmot_frame_dev orders a frame after the work already queued on it; lmot_flush makes it wait for the
+ * pipeline).  NULL restores the context's own stream -- the legacy default stream (handle 0) cannot be selected, create a
+ * stream instead (CUDA events recorded on stream 0 are not ordered with the pipeline's non-blocking streams). */
 int lmot_set_stream(lmot_ctx* ctx, void* cuda_stream);
 
 /* ---- stage entry points, HOST buffers (synchronous: H2D, kernels, D2H, stream sync) -------------------- */

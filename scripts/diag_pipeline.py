@@ -18,7 +18,7 @@ res = {}
 for depth in (1, 2, 4, 8):
     prm = lmot.default_params(); prm.pipeline_depth = depth; prm.result_ring = int(os.environ.get('DIAG_RING', '32'))
     ctx = lmot.Lmot(prm)
-    st = torch.cuda.current_stream(); ctx.set_stream(st.cuda_stream)
+    st = torch.cuda.Stream(); torch.cuda.set_stream(st); ctx.set_stream(st.cuda_stream)
     # A: device-resident, host never blocks
     ctx.tracker_reset()
     for i in range(W): ctx.frame_dev(d[i].data_ptr(), n, ts[i])

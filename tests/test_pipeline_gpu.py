@@ -57,7 +57,8 @@ def test_frame_dev_async_matches(pkg, synth):
     base = _run_sync(pkg, frames, 1)
     ctx = pkg.Lmot()
     try:
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        st = torch.cuda.Stream()
+        ctx.set_stream(st.cuda_stream)
         dev = [torch.from_numpy(p).cuda() for _, p in frames]
         torch.cuda.synchronize()
         for (ts, p), d in zip(frames, dev):
