@@ -47,6 +47,12 @@ __device__ __forceinline__ double wrap_pi(double a) {   // the reference's while
   return a;
 }
 
+// a / b, bit-identical to IEEE division, but a zero numerator over a finite non-zero denominator (covariances are full of
+// exact zeros) does not go through the slow-path subroutine of the software fp64 divide: 0 * b has the same signed zero
+__device__ __forceinline__ double qdiv(double a, double b) {
+  return (a == 0.0 && b != 0.0 && fabs(b) <= DBL_MAX) ? a * b : a / b;
+}
+
 // Eigen dynamic determinant() == partialPivLu().determinant() (first-max pivoting, product of the diagonal)
 template <int N>
 __device__ double det_lu(const double* A) {
@@ -70,7 +76,7 @@ __device__ double det_lu(const double* A) {
         sign = -sign;
       }
 #pragma unroll
-      for (int r = k + 1; r < N; ++r) lu[r * N + k] /= lu[k * N + k];
+      for (int r = k + 1; r < N; ++r) lu[r * N + k] = qdiv(lu[r * N + k], lu[k * N + k]);
     }
 #pragma unroll
     for (int r = k + 1; r < N; ++r)
@@ -85,20 +91,21 @@ __device__ double det_lu(const double* A) {
 
 __device__ __forceinline__ double det2(const double* S) { return det_lu<2>(S); }
 
+
 // Eigen dynamic inverse() of a 2x2 == partialPivLu().solve(Identity)
 __device__ void inv2_lu(const double* A, double* R) {
   double a00 = A[0], a01 = A[1], a10 = A[2], a11 = A[3];
   const bool sw = fabs(a10) > fabs(a00);
   if (sw) { double t = a00; a00 = a10; a10 = t; t = a01; a01 = a11; a11 = t; }
-  const double l10 = a10 / a00;
+  const double l10 = qdiv(a10, a00);
   const double u11 = a11 - l10 * a01;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     double b0 = (c == 0) ? 1.0 : 0.0, b1 = (c == 1) ? 1.0 : 0.0;
     if (sw) { const double t = b0; b0 = b1; b1 = t; }
     const double y1 = b1 - l10 * b0;
-    const double x1 = y1 / u11;
-    const double x0 = (b0 - a01 * x1) / a00;
+    const double x1 = qdiv(y1, u11);
+    const double x0 = qdiv(b0 - a01 * x1, a00);
     R[c] = x0; R[2 + c] = x1;
   }
 }
@@ -194,32 +201,56 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
     x[3] = wrap_pi(sh.xp[model][3]);
     if (lane < 25) {
       const int r = lane / 5, c = lane % 5;
-      const double t0 = mu0 * (sh.Pp[0][lane] + (sh.xp[0][r] - x[r]) * (sh.xp[0][c] - x[c]));
-      const double t1 = mu1 * (sh.Pp[1][lane] + (sh.xp[1][r] - x[r]) * (sh.xp[1][c] - x[c]));
-      const double t2 = mu2 * (sh.Pp[2][lane] + (sh.xp[2][r] - x[r]) * (sh.xp[2][c] - x[c]));
+      const double xr = (r == 0) ? x[0] : (r == 1) ? x[1] : (r == 2) ? x[2] : (r == 3) ? x[3] : x[4];
+      const double xc = (c == 0) ? x[0] : (c == 1) ? x[1] : (c == 2) ? x[2] : (c == 3) ? x[3] : x[4];
+      const double t0 = mu0 * (sh.Pp[0][lane] + (sh.xp[0][r] - xr) * (sh.xp[0][c] - xc));
+      const double t1 = mu1 * (sh.Pp[1][lane] + (sh.xp[1][r] - xr) * (sh.xp[1][c] - xc));
+      const double t2 = mu2 * (sh.Pp[2][lane] + (sh.xp[2][r] - xr) * (sh.xp[2][c] - xc));
       sh.Pm[model][lane] = t0 + t1 + t2;
     }
     __syncwarp();
     // ---- Prediction (:630-772): P_aug.llt() with Eigen's early exit on a non-positive pivot (LLT.h:271-295)
     if (lane == 0) {
-      double* L = sh.L[model];
-#pragma unroll 1
-      for (int e = 0; e < 49; ++e) L[e] = 0.0;
-      for (int r = 0; r < 5; ++r) for (int c = 0; c <= r; ++c) L[r * 7 + c] = sh.Pm[model][r * 5 + c];
-      L[5 * 7 + 5] = kStdA * kStdA;
-      L[6 * 7 + 6] = kStdA * kStdA;
-      for (int k = 0; k < 7; ++k) {
-        double xk = L[k * 7 + k];
-        if (k > 0) { double s = L[k * 7] * L[k * 7]; for (int j = 1; j < k; ++j) s += L[k * 7 + j] * L[k * 7 + j]; xk -= s; }
-        if (xk <= 0.0) break;
-        xk = sqrt(xk);
-        L[k * 7 + k] = xk;
-        for (int r = k + 1; r < 7; ++r) {
-          double acc = L[r * 7 + k];
-          for (int j = 0; j < k; ++j) acc -= L[r * 7 + j] * L[k * 7 + j];
-          L[r * 7 + k] = acc / xk;
+      // 5x5 block in registers, fully unrolled (packed lower triangle); the two augmentation rows are diagonal
+      double a[15];
+#pragma unroll
+      for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) a[r * (r + 1) / 2 + c] = sh.Pm[model][r * 5 + c];
+      bool stop = false;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        if (!stop) {
+          double xk = a[k * (k + 1) / 2 + k];
+          if (k > 0) {
+            double sq = a[k * (k + 1) / 2] * a[k * (k + 1) / 2];
+#pragma unroll
+            for (int j = 1; j < k; ++j) sq += a[k * (k + 1) / 2 + j] * a[k * (k + 1) / 2 + j];
+            xk -= sq;
+          }
+          if (xk <= 0.0) stop = true;                        // Eigen returns here; the rest stays unfactored
+          else {
+            xk = sqrt(xk);
+            a[k * (k + 1) / 2 + k] = xk;
+#pragma unroll
+            for (int r = k + 1; r < 5; ++r) {
+              double acc = a[r * (r + 1) / 2 + k];
+#pragma unroll
+              for (int j = 0; j < k; ++j) acc -= a[r * (r + 1) / 2 + j] * a[k * (k + 1) / 2 + j];
+              a[r * (r + 1) / 2 + k] = qdiv(acc, xk);
+            }
+          }
         }
       }
+      double* L = sh.L[model];
+#pragma unroll
+      for (int r = 0; r < 7; ++r)
+#pragma unroll
+        for (int c = 0; c < 7; ++c) L[r * 7 + c] = (r < 5 && c <= r) ? a[r * (r + 1) / 2 + c] : 0.0;
+      // columns 5 and 6: pivot = sigma^2 - 0 > 0 -> sqrt, unless the factorisation stopped earlier (then raw sigma^2)
+      const double s2 = kStdA * kStdA;
+      L[5 * 7 + 5] = stop ? s2 : sqrt(s2);
+      L[6 * 7 + 6] = stop ? s2 : sqrt(s2);
     }
     __syncwarp();
     if (lane < 15) {      // one sigma point per lane (:682-735)
@@ -269,24 +300,30 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
 #pragma unroll
     for (int e = 0; e < 5; ++e) {
       double acc = 0.0;
+#pragma unroll
       for (int i = 0; i < 15; ++i) acc = acc + ((i == 0) ? w0 : wi) * sh.Xs[model][i][e];
       x[e] = acc;
     }
     x[3] = wrap_pi(x[3]);
     if (lane < 25) {      // predicted covariance element (:746-755)
       const int r = lane / 5, c = lane % 5;
+      const double xr = (r == 0) ? x[0] : (r == 1) ? x[1] : (r == 2) ? x[2] : (r == 3) ? x[3] : x[4];
+      const double xc = (c == 0) ? x[0] : (c == 1) ? x[1] : (c == 2) ? x[2] : (c == 3) ? x[3] : x[4];
+#pragma unroll
       for (int i = 0; i < 15; ++i) {
-        double dr = sh.Xs[model][i][r] - x[r], dc = sh.Xs[model][i][c] - x[c];
+        double dr = sh.Xs[model][i][r] - xr, dc = sh.Xs[model][i][c] - xc;
         if (r == 3) dr = wrap_pi(dr);
         if (c == 3) dc = wrap_pi(dc);
         Pe = Pe + (((i == 0) ? w0 : wi) * dr) * dc;
       }
     }
     // ---- UpdateLidar (:778-902)
+#pragma unroll
     for (int i = 0; i < 15; ++i) { const double w = (i == 0) ? w0 : wi; zp0 = zp0 + w * sh.Xs[model][i][0]; zp1 = zp1 + w * sh.Xs[model][i][1]; }
     if (lane < 4) {
       const int r = lane >> 1, c = lane & 1;
       double acc = 0.0;
+#pragma unroll
       for (int i = 0; i < 15; ++i) {
         const double dzr = sh.Xs[model][i][r] - (r ? zp1 : zp0), dzc = sh.Xs[model][i][c] - (c ? zp1 : zp0);
         acc = acc + (((i == 0) ? w0 : wi) * dzr) * dzc;
@@ -295,9 +332,11 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
       sh.S[model][lane] = acc + R;
     } else if (lane < 14) {
       const int e = lane - 4, r = e >> 1, c = e & 1;
+      const double xr = (r == 0) ? x[0] : (r == 1) ? x[1] : (r == 2) ? x[2] : (r == 3) ? x[3] : x[4];
       double acc = 0.0;
+#pragma unroll
       for (int i = 0; i < 15; ++i) {
-        const double xd = sh.Xs[model][i][r] - x[r], dz = sh.Xs[model][i][c] - (c ? zp1 : zp0);
+        const double xd = sh.Xs[model][i][r] - xr, dz = sh.Xs[model][i][c] - (c ? zp1 : zp0);
         acc = acc + (((i == 0) ? w0 : wi) * xd) * dz;
       }
       sh.Tc[model][e] = acc;
@@ -594,36 +633,42 @@ imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, 
     double eSum[3];
     double xnew[3][5];      // updated model states (all lanes)
     double Pnew[3];         // lane e < 25: updated covariance element of each model
+    // centre point of every gated box once (lane k <-> measurement k; beyond 32 measurements recomputed on the fly):
+    // the reference re-derives it in each of its nine loops
+    double mcx = 0, mcy = 0;
+    if (lane < nmeas) cp_from_box(boxes + (size_t)s_list[lane] * 24, mcx, mcy);
     for (int m = 0; m < 3; ++m) {
       double Si[4];
       inv2_lu(t.S[m], Si);
       const double zp0 = t.zPred[m][0], zp1 = t.zPred[m][1];
+      // per-lane innovation and Gaussian kernel of "its" measurement
+      const double ld0 = mcx - zp0, ld1 = mcy - zp1;
+      double le = 0;
+      if (lane < nmeas) { const double t0 = -0.5 * ld0, t1 = -0.5 * ld1; le = exp((t0 * Si[0] + t1 * Si[2]) * ld0 + (t0 * Si[1] + t1 * Si[3]) * ld1); }
+      auto meas = [&](int k, double& d0, double& d1, double& e) {        // k is warp-uniform
+        if (k < 32) { d0 = __shfl_sync(0xFFFFFFFFu, ld0, k); d1 = __shfl_sync(0xFFFFFFFFu, ld1, k); e = __shfl_sync(0xFFFFFFFFu, le, k); }
+        else {
+          double cx, cy;
+          cp_from_box(boxes + (size_t)s_list[k] * 24, cx, cy);
+          d0 = cx - zp0; d1 = cy - zp1;
+          const double t0 = -0.5 * d0, t1 = -0.5 * d1;
+          e = exp((t0 * Si[0] + t1 * Si[2]) * d0 + (t0 * Si[1] + t1 * Si[3]) * d1);
+        }
+      };
       double es = 0;
-      for (int k = 0; k < nmeas; ++k) {
-        double cx, cy;
-        cp_from_box(boxes + (size_t)s_list[k] * 24, cx, cy);
-        const double d0 = cx - zp0, d1 = cy - zp1;
-        const double t0 = -0.5 * d0, t1 = -0.5 * d1;
-        es += exp((t0 * Si[0] + t1 * Si[2]) * d0 + (t0 * Si[1] + t1 * Si[3]) * d1);
-      }
+      for (int k = 0; k < nmeas; ++k) { double d0, d1, e; meas(k, d0, d1, e); es += e; }
       eSum[m] = es;
       const double betaZero = bb / (bb + es);
       double sX0 = 0, sX1 = 0;
       for (int k = 0; k < nmeas; ++k) {
-        double cx, cy;
-        cp_from_box(boxes + (size_t)s_list[k] * 24, cx, cy);
-        const double d0 = cx - zp0, d1 = cy - zp1;
-        const double t0 = -0.5 * d0, t1 = -0.5 * d1;
-        const double beta = exp((t0 * Si[0] + t1 * Si[2]) * d0 + (t0 * Si[1] + t1 * Si[3]) * d1) / (bb + es);
+        double d0, d1, e; meas(k, d0, d1, e);
+        const double beta = e / (bb + es);
         sX0 += beta * d0; sX1 += beta * d1;
       }
       double sP[4] = {0, 0, 0, 0};
       for (int k = 0; k < nmeas; ++k) {
-        double cx, cy;
-        cp_from_box(boxes + (size_t)s_list[k] * 24, cx, cy);
-        const double d[2] = {cx - zp0, cy - zp1};
-        const double t0 = -0.5 * d[0], t1 = -0.5 * d[1];
-        const double beta = exp((t0 * Si[0] + t1 * Si[2]) * d[0] + (t0 * Si[1] + t1 * Si[3]) * d[1]) / (bb + es);
+        double d[2], e; meas(k, d[0], d[1], e);
+        const double beta = e / (bb + es);
         const double sXv[2] = {sX0, sX1};
 #pragma unroll
         for (int r = 0; r < 2; ++r)
