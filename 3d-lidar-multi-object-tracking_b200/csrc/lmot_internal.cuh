@@ -170,7 +170,9 @@ struct Ctx {
   unsigned* d_setter = nullptr;        // [max_tracks][gate_words] boxes this track marks as matched
   int* d_first_setter = nullptr;       // [max_boxes] lowest track index that matched the box (INT_MAX = unmatched)
   uint8_t* d_skip = nullptr;           // [max_tracks] track did not reach measurementValidation this frame
-  int* d_new_num = nullptr;            // [max_tracks] staged mergeOverSegmentation writes
+  int* d_new_num = nullptr;            // [max_tracks] mergeOverSegmentation: largest visible container index per live track
+  int* d_live_list = nullptr;          // [max_tracks] scratch: indices of live tracks
+  int* d_vis_list = nullptr;           // [max_tracks] scratch: indices of tracks with a visible box
 
   // ---- timing
   bool timing = false;

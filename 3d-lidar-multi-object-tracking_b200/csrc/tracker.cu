@@ -17,8 +17,9 @@
 //                               (:565-653), secondInit (:882-921), track-number machine (:924-944), PDA update with
 //                               association likelihoods (:259-394), IMM mode-probability update and merge
 //                               (ukf.cpp:384-437).
-//   TC1 merge_overseg_kernel    1 warp per track k over all tracks i: the last write of the reference's (i,j) loop.
-//   TC2 spawn_output_kernel     one CTA: spawn a UKF per unmatched box in box order, per-track outputs, static flag.
+//   TC spawn_output_kernel      one CTA: mergeOverSegmentation as "the last write of the reference's (i,j) loop" over
+//                               (live x visible) and (visible x all) pairs, then spawn a UKF per unmatched box in box
+//                               order, per-track outputs, static flag.
 //
 // All state is fp64 like the reference (Eigen::MatrixXd); this file is compiled with -fmad=false so that the
 // operation sequence matches the x86-64 build of the reference except for libm (sin/cos/exp/pow/atan2 <= 2 ulp).
@@ -742,7 +743,7 @@ imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, 
   }
 }
 
-// ------------------------------------------------------------------------------------------------ TC1
+// ------------------------------------------------------------------------------------------------ TC: over-segmentation test
 __device__ __forceinline__ double intersect_coef(double v1x, double v1y, double v2x, double v2y, double px, double py, double cpx, double cpy) {
   return (((v1x - v2x) * (py - v1y) + (v1y - v2y) * (v1x - px)) * ((v1x - v2x) * (cpy - v1y) + (v1y - v2y) * (v1x - cpx)));
 }
@@ -762,37 +763,6 @@ __device__ bool overseg_cond(const TrackState& a, double px, double py) {
   return (c1 > 0 && c2 > 0 && c3 > 0) || (c4 > 0 && c5 > 0 && c6 > 0);
 }
 
-// mergeOverSegmentation (:666-700).  The sequential double loop writes trackNum[i]=5, trackNum[j]=0 for every hit
-// (i,j); the value that survives at index k is the write with the largest (i,j) key: 0 if some visible i > k
-// contains k, else 5 if k (visible) contains anybody, else unchanged.  Decisions are staged in new_num and
-// applied by spawn_output_kernel so that this kernel only reads the table.
-__global__ void __launch_bounds__(128)
-merge_overseg_kernel(const TrackState* __restrict__ tracks, const int* __restrict__ trk, int* __restrict__ new_num) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int T = trk[CNT_N_TRACKS];
-  for (int k = blockIdx.x * 4 + warp; k < T; k += gridDim.x * 4) {
-    const TrackState& tk = tracks[k];
-    const double kx = tk.x[0][0], ky = tk.x[0][1];
-    const bool kvis = tk.isVisBB != 0;
-    int imax = -1; bool has5 = false;
-    for (int i = lane; i < T; i += 32) {
-      if (i == k) continue;
-      const TrackState& ti = tracks[i];
-      if (ti.isVisBB && overseg_cond(ti, kx, ky)) imax = max(imax, i);
-      if (kvis && !has5 && overseg_cond(tk, ti.x[0][0], ti.x[0][1])) has5 = true;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) imax = max(imax, __shfl_xor_sync(0xFFFFFFFFu, imax, o));
-    has5 = __any_sync(0xFFFFFFFFu, has5);
-    if (lane == 0) {
-      int v = -1;                       // -1 = unchanged
-      if (imax >= 0 && (!has5 || imax > k)) v = 0;
-      else if (has5) v = 5;
-      new_num[k] = v;
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ TC2
 struct OutPtrs {   // pinned, device-mapped host memory of the slot: the kernel's stores ARE the D2H transfer
   float* targets; double* vandyaw; int* track_manage; uint8_t* is_static; uint8_t* is_vis; float* vis_bb; int* hdr;
@@ -800,8 +770,8 @@ struct OutPtrs {   // pinned, device-mapped host memory of the slot: the kernel'
 
 __global__ void __launch_bounds__(1024)
 spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int* __restrict__ det, const float* __restrict__ boxes,
-                    int* __restrict__ first_setter, const int* __restrict__ new_num, int first_frame, int compat_first,
-                    double ego_yaw, int max_tracks, OutPtrs o) {
+                    int* __restrict__ first_setter, int* __restrict__ imax_arr, int* __restrict__ live_list, int* __restrict__ vis_list,
+                    uint8_t* __restrict__ has5_arr, int first_frame, int compat_first, double ego_yaw, int max_tracks, OutPtrs o) {
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -829,8 +799,42 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
     return;
   }
 
-  // apply the staged mergeOverSegmentation writes (:968)
-  for (int k = tid; k < T0; k += 1024) { const int v = new_num[k]; if (v >= 0) tracks[k].trackNum = v; }
+  // ---- mergeOverSegmentation (:666-700), folded into this kernel.  The sequential double loop writes trackNum[i]=5,
+  // trackNum[j]=0 for every hit (i,j) with i visible; the value that survives at index k is the write with the largest
+  // (i,j) key: 0 if some visible i > k contains k, else 5 if k (visible) contains anybody, else unchanged.  Only live k can
+  // change (0 -> 0 is a no-op, 5 needs a visible, hence live, k), containers are the few visible tracks.
+  {
+    __shared__ int s_nlive, s_nvis;
+    if (tid == 0) { s_nlive = 0; s_nvis = 0; }
+    __syncthreads();
+    for (int k0 = 0; k0 < T0; k0 += 1024) {            // lists of live / visible tracks (order is irrelevant here)
+      const int k = k0 + tid;
+      if (k < T0) {
+        const TrackState& t = tracks[k];
+        if (t.trackNum != 0) { const int p = atomicAdd(&s_nlive, 1); live_list[p] = k; imax_arr[k] = -1; has5_arr[k] = 0; }
+        if (t.isVisBB) { const int p = atomicAdd(&s_nvis, 1); vis_list[p] = k; }
+      }
+    }
+    __syncthreads();
+    const int nl = s_nlive, nv = s_nvis;
+    for (int p = tid; p < nl * nv; p += 1024) {         // does visible i contain live k ?
+      const int k = live_list[p / nv], i = vis_list[p % nv];
+      if (i != k && overseg_cond(tracks[i], tracks[k].x[0][0], tracks[k].x[0][1])) atomicMax(&imax_arr[k], i);
+    }
+    for (int p = tid; p < nv * T0; p += 1024) {         // does visible k contain anybody (dead tracks included) ?
+      const int k = vis_list[p / T0], j = p % T0;
+      if (j != k && !has5_arr[k] && overseg_cond(tracks[k], tracks[j].x[0][0], tracks[j].x[0][1])) has5_arr[k] = 1;
+    }
+    __syncthreads();
+    for (int p = tid; p < nl; p += 1024) {
+      const int k = live_list[p];
+      const int imax = imax_arr[k];
+      const bool has5 = has5_arr[k] != 0;
+      if (imax >= 0 && (!has5 || imax > k)) tracks[k].trackNum = 0;
+      else if (has5) tracks[k].trackNum = 5;
+    }
+    __syncthreads();
+  }
 
   // spawn one UKF per unmatched box, in box order (:972-989)
   for (int b0 = 0; b0 < M; b0 += 1024) {
@@ -924,6 +928,8 @@ int tracker_alloc(Ctx* c) {
   LMOT_CUDA(c, cudaMalloc(&c->d_first_setter, (size_t)MB * sizeof(int)));
   LMOT_CUDA(c, cudaMalloc(&c->d_skip, TC));
   LMOT_CUDA(c, cudaMalloc(&c->d_new_num, (size_t)TC * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_live_list, (size_t)TC * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_vis_list, (size_t)TC * sizeof(int)));
   fill_int_kernel<<<(MB + 255) / 256, 256, 0, c->trk_stream>>>(c->d_first_setter, MB, INT_MAX);
   LMOT_CUDA(c, cudaGetLastError());
   const size_t sh = (size_t)kTBWarps * c->gate_words * 32 * sizeof(unsigned short);
@@ -933,7 +939,7 @@ int tracker_alloc(Ctx* c) {
 
 void tracker_free(Ctx* c) {
   cudaFree(c->d_tracks); cudaFree(c->d_trk_counters); cudaFree(c->d_gate); cudaFree(c->d_setter); cudaFree(c->d_first_setter);
-  cudaFree(c->d_skip); cudaFree(c->d_new_num);
+  cudaFree(c->d_skip); cudaFree(c->d_new_num); cudaFree(c->d_live_list); cudaFree(c->d_vis_list);
   if (c->h_trk_counters) cudaFreeHost(c->h_trk_counters);
 }
 
@@ -983,11 +989,9 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
     imm_update_kernel<<<c->trk_ctas / kTBWarps + 1, kTBWarps * 32, sh, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_gate,
                                                                            c->d_first_setter, c->d_skip, c->gate_words);
     kernel_mark(c, sl, st);
-    merge_overseg_kernel<<<c->trk_ctas / 4 + 1, 128, 0, st>>>(c->d_tracks, c->d_trk_counters, c->d_new_num);
-    kernel_mark(c, sl, st);
   }
-  spawn_output_kernel<<<1, 1024, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_first_setter, c->d_new_num, first, compat,
-                                          h.egoPoint[2], c->prm.max_tracks, o);
+  spawn_output_kernel<<<1, 1024, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_first_setter, c->d_new_num, c->d_live_list,
+                                          c->d_vis_list, c->d_skip, first, compat, h.egoPoint[2], c->prm.max_tracks, o);
   kernel_mark(c, sl, st);
   LMOT_CUDA(c, cudaGetLastError());
   h.timestamp = timestamp;

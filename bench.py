@@ -40,8 +40,8 @@ PKG = "3d-lidar-multi-object-tracking_b200"
 WORKLOAD = "hdl64_120k_64trk_full_pipeline"
 SCENE = dict(n_objects=150, lattice_pitch=3.8, ped_fraction=0.65, seed=1)   # ~64 live tracks at steady state
 KERNEL_NAMES = ("polar_bin", "polar_grid", "classify_partition", "ccl_cluster", "tile_hist", "seg_offsets", "scatter", "box_fit",
-                "imm_predict_gate", "imm_update", "merge_overseg", "spawn_output")
-KERNELS_PER_FRAME = 12   # ground 3 (classify also bins the elevated points) + cluster 1 + box 4 + tracker 4
+                "imm_predict_gate", "imm_update", "spawn_output")
+KERNELS_PER_FRAME = 11   # ground 3 (classify also bins the elevated points) + cluster 1 + box 4 + tracker 3
 
 
 def make_frames(synth, n_frames, seed_offset=0):

@@ -59,7 +59,7 @@ for depth in (1, 2, 4, 8):
         for i in range(W + 100):
             ctx.frame_dev(d[i].data_ptr(), n, ts[i]); ctx.frame_fetch(want_boxes=False)
             km = np.array(ctx.last_kernel_ms())
-            if i >= W and len(km) == 12: acc = km if acc is None else acc + km
+            if i >= W and len(km) == len(bench.KERNEL_NAMES): acc = km if acc is None else acc + km
         ctx.enable_timing(False)
         res["kernel_us_warm"] = None if acc is None else {k: float(1e3 * v / 100) for k, v in zip(bench.KERNEL_NAMES, acc)}
         res["n_kernel_events_last"] = len(km)
