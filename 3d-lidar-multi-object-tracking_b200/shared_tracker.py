@@ -54,13 +54,25 @@ class SharedTracker:
         allb = torch.cat([bufs[r][: counts[r]] for r in range(self.world)], 0) if sum(counts) else pad[:0]
         return allb.cpu().numpy(), counts
 
-    def step(self, boxes: np.ndarray, timestamp_us: float, v_gps: float = 0.0, yaw_gps: float = 0.0):
-        """One tick of the shared tracker.  Every rank gets the same per-track outputs."""
+    def step(self, boxes: np.ndarray, timestamp_us: float, v_gps: float = 0.0, yaw_gps: float = 0.0, frame_sharded: bool = False,
+             frame_dt_us: float = 1.0e5):
+        """One tick of the shared tracker.  Every rank gets the same per-track outputs.
+
+        frame_sharded=False: the ranks are different SENSORS observed at the same instant; their boxes are concatenated in
+        rank order into ONE tracker step (BASELINE.json configs[3]).
+        frame_sharded=True: the ranks hold CONSECUTIVE FRAMES of one sensor (rank r has frame t*world + r, configs[4]); the
+        owner folds them into the table in frame order, one tracker step per rank, timestamps timestamp_us + r*frame_dt_us."""
         allb, counts = self.gather_boxes(boxes)
         hdr = torch.zeros(2, dtype=torch.int64, device=self.device)
         out = None
         if self.rank == self.owner:
-            out = self.backend.track_step(allb, timestamp_us, v_gps, yaw_gps)
+            if frame_sharded:
+                off = 0
+                for r in range(self.world):
+                    out = self.backend.track_step(allb[off: off + counts[r]], timestamp_us + r * frame_dt_us, v_gps, yaw_gps)
+                    off += counts[r]
+            else:
+                out = self.backend.track_step(allb, timestamp_us, v_gps, yaw_gps)
             hdr[0] = len(out["track_manage"]); hdr[1] = len(out["vis_bb"])
         dist.broadcast(hdr, src=self.owner, group=self.group)
         T, V = int(hdr[0].item()), int(hdr[1].item())

@@ -198,6 +198,44 @@ def run_reference(args, synth):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------- shared track table (N > 1)
+def run_shared_tracker(args, lmot, ctx, d_frames, ts, n_pts, rank, world, local_rank, stream):
+    """All ranks detect on their own frame, then feed ONE track table owned by rank 0 (the only exchange step of the path)."""
+    import torch
+    import torch.distributed as dist
+    st_mod = importlib.import_module(PKG + ".shared_tracker")
+    K, W = args.steps, max(args.warmup, 3)
+    st = st_mod.SharedTracker(ctx, owner=0, max_boxes=int(ctx.params.max_boxes), device=torch.device("cuda", local_rank))
+    sharded = args.shared_tracker == "frames"
+    ctx.tracker_reset()
+
+    def tick(i):
+        ctx.detect_dev(d_frames[i].data_ptr(), n_pts)
+        r = ctx.frame_fetch()
+        base_ts = ts[i] * world if sharded else ts[i]
+        return st.step(r["boxes"], base_ts, frame_sharded=sharded)
+
+    for i in range(W):
+        tick(i)
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(W, W + K):
+        out = tick(i)
+    dist.barrier(); torch.cuda.synchronize()
+    sec = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        fps = world * K / float(sec[0])
+        print(json.dumps({
+            "metric": "HDL-64 frames/sec (120K pts, shared track table)", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * float(sec[0]) / K, "higher_is_better": True, "scaling": "weak" if not sharded else "strong", "vs_baseline": None,
+            "dtype": "f32 points / f64 tracker", "data": "synthetic",
+            "config": {"workload": "hdl64_120k_shared_tracker_" + args.shared_tracker, "points_per_frame": n_pts, "scene": SCENE,
+                       "tracks_in_table_end": int(len(out["track_manage"])), "live_tracks_end": int((out["track_manage"] > 0).sum()),
+                       "parallelism": f"detection on {world} GPUs, one track table on rank 0, NCCL all_gather(boxes) + broadcast(outputs, table)"},
+            "gpu_launches": 11 * K}))
+
+
 # ------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -207,6 +245,10 @@ def main():
     ap.add_argument("--impl", default="lmot", choices=["lmot", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=60, help="frames of the CPU baseline sample (rank 0, N=1)")
     ap.add_argument("--dense-frames", type=int, default=10, help="1M-point frames for the dense roofline measurement (0 = skip)")
+    ap.add_argument("--shared-tracker", choices=["off", "streams", "frames"], default="off",
+                    help="N>1 only: all ranks feed ONE track table (NCCL all_gather of boxes, tracker on rank 0, NCCL broadcast of the "
+                         "outputs and of the table): 'streams' = N sensors per tick (configs[3]), 'frames' = one sensor, frames sharded "
+                         "round-robin over the ranks (configs[4]).  Default: N independent streams, no collective.")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -253,6 +295,12 @@ def main():
 
     sampler = ClockSampler(local_rank)      # nvidia-smi samples every 100 ms across all three timed passes below
     sampler.start()
+    if args.shared_tracker != "off" and world > 1:
+        run_shared_tracker(args, lmot, ctx, d_frames, ts, n_pts, rank, world, local_rank, stream)
+        ctx.close()
+        dist.destroy_process_group()
+        return
+
     # ---- (1) device-resident throughput: `value`
     ctx.tracker_reset()
     for i in range(W):

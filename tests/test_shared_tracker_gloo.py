@@ -34,6 +34,22 @@ def _boxes_for(rank, frame):
     return out
 
 
+def _worker_sharded(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    st_mod = importlib.import_module("3d-lidar-multi-object-tracking_b200.shared_tracker")
+    backend = _PortBackend() if rank == 0 else object()
+    st = st_mod.SharedTracker(backend, owner=0, max_boxes=64, device="cpu")
+    results = []
+    for t in range(5):                      # tick t: rank r holds frame t*world + r of ONE sensor
+        f = t * world + rank
+        r = st.step(_boxes_for(0, f), (t * world + 1) * 1e5, frame_sharded=True, frame_dt_us=1e5)
+        results.append((r["track_manage"].copy(), r["targets"].copy()))
+    q.put((rank, results))
+    dist.destroy_process_group()
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -74,3 +90,29 @@ def test_two_streams_one_tracker_gloo():
             assert counts == [3, 5]
             assert np.array_equal(tm, want["track_manage"])
             assert np.array_equal(tg, want["targets"])
+
+
+def test_frame_sharded_one_sensor_gloo():
+    """configs[4] shape: consecutive frames of one sensor live on different ranks; the owner folds them in frame order."""
+    from oracle import ref as oracle
+    if not oracle.have_port():
+        pytest.skip("oracle port not built")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_sharded, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o = oracle.PortOracle("intended")
+    o.tracker_reset()
+    for t in range(5):
+        for r in range(2):
+            f = t * 2 + r
+            want = o.tracker_step(_boxes_for(0, f), (f + 1) * 1e5)
+        for rank in (0, 1):
+            tm, tg = got[rank][t]
+            assert np.array_equal(tm, want["track_manage"]) and np.array_equal(tg, want["targets"])
