@@ -8,6 +8,7 @@
 // the kernels straight into the slot's pinned, device-mapped host block; the host only waits on an event.
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <chrono>
 #include <vector>
@@ -126,7 +127,7 @@ int submit(Ctx* c, Slot* s, Result* r, const float4* d_pts, int n, bool with_tra
   // the slot's previous boxes / counters must have been consumed by the tracker
   LMOT_CUDA(c, cudaStreamWaitEvent(s->stream, s->ev_trk_done, 0));
   if (c->timing) cudaEventRecord(r->ev[0], s->stream);
-  if ((rc = ground_launch(c, s, s->stream, d_pts, n, true))) return rc;
+  if ((rc = ground_launch(c, s, s->stream, d_pts, n, true, false))) return rc;
   if (c->timing) cudaEventRecord(r->ev[1], s->stream);
   if ((rc = cluster_launch(c, s, s->stream, n, true))) return rc;
   if (c->timing) cudaEventRecord(r->ev[2], s->stream);
@@ -320,6 +321,7 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   { volatile float span = p.r_max - p.r_min; c->gp.r_span = span; }
   c->gp.tol = p.ground_tolerance;
   gauss_taps(c->gp.tap);
+  if (const char* e = getenv("LMOT_PTS_PER_CTA")) { const int v = atoi(e); if (v >= 256 && v <= 16384) c->pts_per_cta = v; }
   int rc = LMOT_OK;
   // The tracker is the one sequential chain of the pipeline (frame f+1's tracker needs frame f's table): its CTAs get
   // the highest stream priority so they are never queued behind the detection kernels of later frames.
@@ -755,6 +757,7 @@ int lmot_debug_cell_index(lmot_ctx* ctx, int32_t* ch, int32_t* bin, int n) {
   Slot* s = &c->slots[c->last_slot];
   if (n > s->cur_n) return LMOT_ERR_INVALID;
   std::vector<uint16_t> cell((size_t)n);
+  if ((rc = ground_cells_debug(c, s, c->stream))) return rc;   // the fused kernel keeps the ids in shared memory: recompute them
   if (n) LMOT_CUDA(c, cudaMemcpyAsync(cell.data(), s->d_cell, (size_t)n * 2, cudaMemcpyDeviceToHost, c->stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
   for (int i = 0; i < n; ++i) {

@@ -1,18 +1,23 @@
 // ground.cu -- slope-based polar-grid ground removal on sm_100a.
 //
 // Replaces groundRemove (/root/reference/object_tracking/src/groundremove/ground_removal.cpp:177-249) and
-// gaussSmoothen (src/groundremove/gaus_blur.cpp:52-68).  Three kernels per frame:
+// gaussSmoothen (src/groundremove/gaus_blur.cpp:52-68) with ONE cooperative kernel per frame, ground_fused_kernel:
 //
-//   K1 polar_bin_kernel      N threads.  float4 XYZI load, range filter (:46-64), bit-exact point->cell
-//                            (:67-76, exact_math.cuh), warp-aggregated atomicMin of an order-preserving
-//                            key into the 80x120 min-z grid (:79-92).  Also stores the u16 cell id so the
-//                            classification pass does not repeat atan2f/sqrtf like the reference does.
-//   K2 polar_grid_kernel     ONE CTA, the whole 9,600-cell grid in shared memory: height clamp (:192-197),
-//                            3-tap blur in fp64 (gaus_blur.cpp), hDiff (:95-117), ground flag (:205-214),
-//                            median filter (:120-146, evaluated Jacobi-style -- provably order independent),
-//                            outlier filter (:149-174, sequential along bin, one lane per channel).
-//   K3 classify_partition_kernel  N threads.  ground / elevated decision (:221-247) + ORDER-PRESERVING
-//                            compaction of both output clouds with a single-pass decoupled look-back scan.
+//   phase 1  every CTA owns a contiguous chunk of the XYZI frame and pulls it into shared memory with the bulk async
+//            copy engine (TMA, one cp.async.bulk per 16 KB tile); range filter (:46-64), bit-exact point->cell
+//            (:67-76, exact_math.cuh), warp-aggregated atomicMin of an order-preserving key into the 80x120
+//            min-z grid (:79-92).  The points and their u16 cell ids STAY in shared memory.
+//   -- grid barrier --
+//   phase 2  the 80 channels are split over the first min(G,80) CTAs (one halo channel per side recomputed locally):
+//            height clamp (:192-197), 3-tap blur in fp64 (gaus_blur.cpp), hDiff (:95-117), ground flag (:205-214),
+//            median filter (:120-146, Jacobi -- provably order independent), outlier filter (:149-174, closed form).
+//   -- grid barrier --
+//   phase 3  ground / elevated decision (:221-247) from shared memory + ORDER-PRESERVING compaction of both output
+//            clouds (per-CTA totals published once, every CTA sums its predecessors), fused with the first pass of
+//            clustering (cartesian cell + occupancy of every elevated point, component_clustering.cpp:38-47).
+//
+// HBM traffic is the compulsory minimum: every input point is read once (16 B) and every surviving point written
+// once (16 B); the reference, and a kernel-per-stage design, read the frame twice and round-trip the cell ids.
 //
 // Everything that decides a cell index or a label is IEEE round-to-nearest without FMA contraction, so the
 // results are bit-identical to the reference built for x86-64.
@@ -65,104 +70,41 @@ __device__ __forceinline__ uint16_t polar_cell(float x, float y, const GroundPar
   return (uint16_t)((int)chF * kNumBin + (int)binF);
 }
 
-constexpr int kBinTile = 256;                      // points per TMA tile (4 KB), two tiles in flight per CTA
-
-// K1.  Persistent CTAs; the XYZI frame is staged through shared memory by the bulk async copy engine (TMA, UBLKCP in
-// SASS): one elected thread arms an mbarrier with the tile's byte count and issues a single 4 KB cp.async.bulk, the
-// other 255 threads never touch the LSU for input -- they pick their point up from shared memory when the barrier
-// flips, and the copy of tile t+2 overlaps the binning arithmetic of tile t.
-__global__ void __launch_bounds__(kBinTile) polar_bin_kernel(const float4* __restrict__ pts, int n, GroundParams p,
-                                                             uint16_t* __restrict__ cell, unsigned* __restrict__ keys) {
-  __shared__ alignas(128) float4 s_buf[2][kBinTile];
-  __shared__ alignas(8) uint64_t s_full[2];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int n_tiles = (n + kBinTile - 1) / kBinTile;
-  if (tid == 0) { mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); fence_mbar_init(); }
-  __syncthreads();
-  if (tid == 0) {
-#pragma unroll
-    for (int st = 0; st < 2; ++st) {
-      const int tile = blockIdx.x + st * gridDim.x;
-      if (tile < n_tiles) {
-        const uint32_t bytes = (uint32_t)min(kBinTile, n - tile * kBinTile) * 16u;
-        mbar_arrive_expect_tx(&s_full[st], bytes);
-        bulk_copy_g2s(s_buf[st], pts + (size_t)tile * kBinTile, bytes, &s_full[st]);
-      }
-    }
-  }
-  int it = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int st = it & 1;
-    mbar_wait(&s_full[st], (uint32_t)(it >> 1) & 1u);
-    const int i = tile * kBinTile + tid;
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < n) q = s_buf[st][tid];
-    __syncthreads();                                 // every thread holds its point: the stage can be refilled
-    if (tid == 0) {
-      const int next = tile + 2 * gridDim.x;
-      if (next < n_tiles) {
-        const uint32_t bytes = (uint32_t)min(kBinTile, n - next * kBinTile) * 16u;
-        mbar_arrive_expect_tx(&s_full[st], bytes);
-        bulk_copy_g2s(s_buf[st], pts + (size_t)next * kBinTile, bytes, &s_full[st]);
-      }
-    }
-    unsigned c = kNoCell;
-    unsigned key = 0xFFFFFFFFu;
-    if (i < n) {
-      c = polar_cell(q.x, q.y, p);
-      cell[i] = (uint16_t)c;
-      float z = q.z;
-      if (z == 0.f) z = 0.f;                       // -0 -> +0 (`z < minZ` does not order them either)
-      if (c != kNoCell && z == z) key = fkey(z);   // NaN z never wins `z < minZ` (ground_removal.cpp:41)
-    }
-    // consecutive HDL-64 returns fall into the same cell: one atomic per distinct cell per warp
-    const unsigned grp = __match_any_sync(0xFFFFFFFFu, c);
-    const unsigned kmin = __reduce_min_sync(grp, key);
-    if (c != kNoCell && lane == __ffs(grp) - 1 && kmin != 0xFFFFFFFFu) atomicMin(&keys[c], kmin);
-  }
-}
-
 // generic-stride input -> float4 (the hot path is stride 4 and never runs this)
 __global__ void repack_kernel(const float* __restrict__ in, int n, int stride, float4* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = make_float4(in[(size_t)i * stride], in[(size_t)i * stride + 1], in[(size_t)i * stride + 2], 1.f);
 }
 
-constexpr int kGridCtas = 8;                       // 10 channels per CTA (+1 halo channel each side, recomputed locally)
-constexpr int kChanPerCta = kNumChannel / kGridCtas;
-constexpr int kGridThreads = 512;
-constexpr int kLocChan = kChanPerCta + 2;
-constexpr int kLocCells = kLocChan * kNumBin;       // 1440
-constexpr int kCellsPerThread = (kLocCells + kGridThreads - 1) / kGridThreads;   // 3
+// ---------------------------------------------------------------------------------------------------------------
+// polar-grid stages for a window of channels.  H / G: shared-memory height and ground flag of the window's cells,
+// window = the CTA's own channels [own0, own0 + n_own) plus one halo channel on each side (the 80 channels are
+// independent in every stage except the median filter, which looks one channel to each side; the halo's clamp / blur /
+// hDiff / flag stages are recomputed locally, so the CTAs never exchange grid data).
+constexpr int kFusedThreads = 1024;                 // threads per CTA == points per tile
+constexpr int kMinCtas = 8;                         // => at most 10 own + 2 halo channels per CTA
+constexpr int kMaxLocChan = kNumChannel / kMinCtas + 2;
+constexpr int kMaxLocCells = kMaxLocChan * kNumBin;  // 1440
+constexpr int kCellsPerThread = (kMaxLocCells + kFusedThreads - 1) / kFusedThreads;   // 2
 
-// The 80 channels are independent in every stage except the median filter, which looks one channel to each side:
-// each CTA owns 10 channels and recomputes the clamp / blur / hDiff / flag stages of one halo channel per side, so no
-// inter-CTA synchronisation is needed.  Keys are re-armed by classify_partition_kernel (a neighbour may still be
-// reading this CTA's boundary channel here).
-__global__ void __launch_bounds__(kGridThreads, 1)
-polar_grid_kernel(GroundParams p, const unsigned* __restrict__ keys, float* __restrict__ o_minz, float* __restrict__ o_height,
-                  float* __restrict__ o_smoothed, float* __restrict__ o_hdiff, float* __restrict__ o_hg,
-                  unsigned long long* __restrict__ tile_desc, int n_tiles, int* __restrict__ counters) {
-  __shared__ float H[kLocCells];
-  __shared__ uint8_t G[kLocCells];
+__device__ __forceinline__ void polar_grid_slice(const GroundParams& p, const unsigned* __restrict__ keys, int own0, int n_own,
+                                                 float* H, uint8_t* G, float* __restrict__ o_minz, float* __restrict__ o_height,
+                                                 float* __restrict__ o_smoothed, float* __restrict__ o_hdiff,
+                                                 float* __restrict__ o_hg) {
   const int tid = threadIdx.x;
-  const int ch0 = blockIdx.x * kChanPerCta - 1;              // global channel of local channel 0 (may be -1)
-
-  if (blockIdx.x == 0) {                                     // housekeeping for the kernels that follow in this frame
-    for (int t = tid; t < n_tiles; t += kGridThreads) tile_desc[t] = 0ull;
-    if (tid == 0) { counters[CNT_TICKET_A] = 0; counters[CNT_N_ELEV] = 0; counters[CNT_N_GROUND] = 0; }
-  }
+  const int ch0 = own0 - 1;                                   // global channel of local channel 0 (may be -1)
+  const int n_cells = (n_own + 2) * kNumBin;
 
   // (a4) height clamp, ground_removal.cpp:192-197
 #pragma unroll
   for (int j = 0; j < kCellsPerThread; ++j) {
-    const int l = tid + j * kGridThreads;
-    if (l < kLocCells) {
+    const int l = tid + j * kFusedThreads;
+    if (l < n_cells) {
       const int lc = l / kNumBin, b = l - lc * kNumBin, ch = ch0 + lc;
       float h = 0.f;
       if (ch >= 0 && ch < kNumChannel) {
-        const float zi = fkey_inv(__ldg(&keys[ch * kNumBin + b]));
-        if (lc >= 1 && lc <= kChanPerCta) o_minz[ch * kNumBin + b] = zi;
+        const float zi = fkey_inv(__ldcg(&keys[ch * kNumBin + b]));
+        if (lc >= 1 && lc <= n_own) o_minz[ch * kNumBin + b] = zi;
         if (zi > p.t_hmin && zi < p.t_hmax) h = zi;
         else if (zi > p.t_hmax) h = p.h_sensor;
         else h = p.t_hmin;
@@ -175,8 +117,8 @@ polar_grid_kernel(GroundParams p, const unsigned* __restrict__ keys, float* __re
   // (a5) blur, (a6) hDiff, (a7) ground flag -- per channel, neighbours along bin
 #pragma unroll
   for (int j = 0; j < kCellsPerThread; ++j) {
-    const int l = tid + j * kGridThreads;
-    if (l < kLocCells) {
+    const int l = tid + j * kFusedThreads;
+    if (l < n_cells) {
       const int lc = l / kNumBin, b = l - lc * kNumBin, ch = ch0 + lc;
       uint8_t g = 0;
       if (ch >= 0 && ch < kNumChannel) {
@@ -193,7 +135,7 @@ polar_grid_kernel(GroundParams p, const unsigned* __restrict__ keys, float* __re
           const float pre = fsub(h, H[l - 1]), post = fsub(h, H[l + 1]);
           hd = (pre > post) ? pre : post;
         }
-        if (lc >= 1 && lc <= kChanPerCta) { o_smoothed[ch * kNumBin + b] = sm; o_hdiff[ch * kNumBin + b] = hd; }
+        if (lc >= 1 && lc <= n_own) { o_smoothed[ch * kNumBin + b] = sm; o_hdiff[ch * kNumBin + b] = hd; }
         g = ((sm < p.t_hmax && hd < p.t_hdiff) || (h < p.t_hmax && hd < p.t_hdiff)) ? 1 : 0;  // :205-214
       }
       G[l] = g;
@@ -209,11 +151,11 @@ polar_grid_kernel(GroundParams p, const unsigned* __restrict__ keys, float* __re
     unsigned flip = 0;
 #pragma unroll
     for (int j = 0; j < kCellsPerThread; ++j) {
-      const int l = tid + j * kGridThreads;
+      const int l = tid + j * kFusedThreads;
       newh[j] = 0.f;
-      if (l < kLocCells) {
+      if (l < n_cells) {
         const int lc = l / kNumBin, b = l - lc * kNumBin, ch = ch0 + lc;
-        if (lc >= 1 && lc <= kChanPerCta && ch >= 1 && ch < kNumChannel - 1 && b >= 1 && b < kNumBin - 1 && !G[l] && G[l + 1] &&
+        if (lc >= 1 && lc <= n_own && ch >= 1 && ch < kNumChannel - 1 && b >= 1 && b < kNumBin - 1 && !G[l] && G[l + 1] &&
             G[l - 1] && G[l + kNumBin] && G[l - kNumBin]) {
           const float a = H[l + 1], bb = H[l - 1], c = H[l + kNumBin], d = H[l - kNumBin];
           const float lo1 = fminf(a, bb), hi1 = fmaxf(a, bb), lo2 = fminf(c, d), hi2 = fmaxf(c, d);
@@ -226,7 +168,7 @@ polar_grid_kernel(GroundParams p, const unsigned* __restrict__ keys, float* __re
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kCellsPerThread; ++j)
-      if (flip & (1u << j)) { const int l = tid + j * kGridThreads; H[l] = newh[j]; G[l] = 1; }
+      if (flip & (1u << j)) { const int l = tid + j * kFusedThreads; H[l] = newh[j]; G[l] = 1; }
   }
   __syncthreads();
 
@@ -241,11 +183,11 @@ polar_grid_kernel(GroundParams p, const unsigned* __restrict__ keys, float* __re
     unsigned mod = 0;
 #pragma unroll
     for (int j = 0; j < kCellsPerThread; ++j) {
-      const int l = tid + j * kGridThreads;
+      const int l = tid + j * kFusedThreads;
       newh[j] = 0.f;
-      if (l < kLocCells) {
+      if (l < n_cells) {
         const int lc = l / kNumBin, b = l - lc * kNumBin, ch = ch0 + lc;
-        if (lc >= 1 && lc <= kChanPerCta && ch >= 1 && ch < kNumChannel - 1 && b >= 1 && b < kNumBin - 2 && G[l] && G[l + 1] &&
+        if (lc >= 1 && lc <= n_own && ch >= 1 && ch < kNumChannel - 1 && b >= 1 && b < kNumBin - 2 && G[l] && G[l + 1] &&
             G[l - 1] && G[l + 2]) {
           const float h1 = H[l - 1], h2 = H[l], h3 = H[l + 1], h4 = H[l + 2];
           if (h2 == T && (h3 != T || h4 != T)) {                  // A(b)
@@ -263,17 +205,17 @@ polar_grid_kernel(GroundParams p, const unsigned* __restrict__ keys, float* __re
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kCellsPerThread; ++j)
-      if (mod & (1u << j)) H[tid + j * kGridThreads] = newh[j];
+      if (mod & (1u << j)) H[tid + j * kFusedThreads] = newh[j];
   }
   __syncthreads();
 
   // hGround == height for every ground cell (updateGround() follows every height write of a ground cell)
 #pragma unroll
   for (int j = 0; j < kCellsPerThread; ++j) {
-    const int l = tid + j * kGridThreads;
-    if (l < kLocCells) {
+    const int l = tid + j * kFusedThreads;
+    if (l < n_cells) {
       const int lc = l / kNumBin, b = l - lc * kNumBin, ch = ch0 + lc;
-      if (lc >= 1 && lc <= kChanPerCta) {
+      if (lc >= 1 && lc <= n_own) {
         o_height[ch * kNumBin + b] = H[l];
         o_hg[ch * kNumBin + b] = G[l] ? H[l] : -INFINITY;
       }
@@ -281,112 +223,247 @@ polar_grid_kernel(GroundParams p, const unsigned* __restrict__ keys, float* __re
   }
 }
 
-// status (2 bits) | elevated count (31 bits) | ground count (31 bits)
-__device__ __forceinline__ unsigned long long pack_desc(unsigned st, unsigned e, unsigned g) {
-  return ((unsigned long long)st << 62) | ((unsigned long long)e << 31) | (unsigned long long)g;
+// ---------------------------------------------------------------------------------------------------------------
+// grid-wide barrier of a cooperative launch (all CTAs co-resident).  The counter is never reset: launch k of a slot
+// waits for `target` = arrivals of all earlier launches + the arrivals this barrier needs (host-side bookkeeping).
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned spin = 0;
+    while ((int)(ld_acquire_u32(bar) - target) < 0)
+      if (++spin > (1u << 22)) __trap();           // a lost CTA must not hang the GPU
+    __threadfence();
+  }
+  __syncthreads();
 }
 
-__global__ void __launch_bounds__(kScanTile)
-classify_partition_kernel(const float4* __restrict__ pts, int n, const uint16_t* __restrict__ cell,
-                          const float* __restrict__ hg, double tol, uint8_t* __restrict__ labels,
-                          float4* __restrict__ elev, float4* __restrict__ ground,
-                          unsigned long long* tile_desc, int* counters, float roi, uint16_t* __restrict__ cart,
-                          int* __restrict__ cart_count, unsigned* __restrict__ keys) {
-  __shared__ int s_tile;
-  __shared__ unsigned s_we[32], s_wg[32];
-  __shared__ unsigned s_base_e, s_base_g;
+constexpr int kTilePts = kFusedThreads;             // 1024 points = 16 KB per TMA tile
+constexpr int kMaxResTiles = 7;                     // tiles of a CTA's chunk that stay in shared memory (112 KB)
+constexpr int kMaxTiles = 16;                       // tiles per chunk (labels of a thread's points: 2 bits each in one register)
+// dynamic shared memory layout (bytes)
+constexpr int kOffBar = 0;                                                  // [7] mbarriers
+constexpr int kOffPts = 128;                                                // [7][1024] float4
+constexpr int kOffCell = kOffPts + kMaxResTiles * kTilePts * 16;            // [16][1024] u16
+constexpr int kOffH = kOffCell + kMaxTiles * kTilePts * 2;                  // [1440] float
+constexpr int kOffCnt = kOffH + kMaxLocCells * 4;                           // [16][32] u32 elevated | ground << 16 per warp
+constexpr int kOffWex = kOffCnt + kMaxTiles * 32 * 4;                       // [16][32] u32 exclusive inside the tile
+constexpr int kOffTtot = kOffWex + kMaxTiles * 32 * 4;                      // [16] u32 tile totals
+constexpr int kOffBase = kOffTtot + kMaxTiles * 4;                          // [2] u32 chunk base (elevated, ground)
+constexpr int kOffG = kOffBase + 16;                                        // [1440] u8
+constexpr int kFusedSmem = kOffG + ((kMaxLocCells + 15) & ~15);
+
+struct FusedOut {
+  uint8_t* labels;          // nullable
+  float4* elev;
+  float4* ground;
+  uint16_t* cart;           // nullable: cartesian cell of every elevated point (fused first pass of clustering)
+  int* cart_count;          // nullable
+  int* counters;
+};
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundParams p, unsigned* __restrict__ keys,
+                    unsigned* __restrict__ keys_next, float* __restrict__ o_minz, float* __restrict__ o_height,
+                    float* __restrict__ o_smoothed, float* __restrict__ o_hdiff, float* __restrict__ o_hg, unsigned* bar,
+                    unsigned bar_base, unsigned long long* desc, unsigned epoch, FusedOut out, float roi) {
+  extern __shared__ __align__(128) unsigned char fsm[];
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(fsm + kOffBar);
+  float4* s_pts = reinterpret_cast<float4*>(fsm + kOffPts);
+  uint16_t* s_cell = reinterpret_cast<uint16_t*>(fsm + kOffCell);
+  float* s_H = reinterpret_cast<float*>(fsm + kOffH);
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(fsm + kOffCnt);
+  unsigned* s_wex = reinterpret_cast<unsigned*>(fsm + kOffWex);
+  unsigned* s_ttot = reinterpret_cast<unsigned*>(fsm + kOffTtot);
+  unsigned* s_base = reinterpret_cast<unsigned*>(fsm + kOffBase);
+  uint8_t* s_G = fsm + kOffG;
+
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // re-arm the min-z grid for the next frame (Cell::Cell(): minZ = 1000); polar_grid_kernel has consumed it
-  for (int k = blockIdx.x * kScanTile + tid; k < kPolarCells; k += gridDim.x * kScanTile) keys[k] = fkey(1000.f);
-  if (tid == 0) s_tile = atomicAdd(&counters[CNT_TICKET_A], 1);
-  __syncthreads();
-  const int tile = s_tile;
-  const int i = tile * kScanTile + tid;
+  const int cta = blockIdx.x, G = gridDim.x;
+  const long long beg_ll = (long long)cta * chunk;
+  const int beg = beg_ll < n ? (int)beg_ll : n;
+  const int end = min(n, beg + chunk);
+  const int cnt = end - beg;
+  const int T = (cnt + kTilePts - 1) / kTilePts;
 
-  int lab = 0;
-  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (i < n) {
-    q = __ldg(&pts[i]);
-    const unsigned c = cell[i];
-    if (c != kNoCell) {
-      const float h = __ldg(&hg[c]);                       // -inf for non-ground cells -> elevated
-      lab = ((double)q.z < __dadd_rn((double)h, tol)) ? 1 : 2;   // ground_removal.cpp:236-246
+  // ---- phase 0: arm the TMA copies of the resident tiles; re-arm the OTHER key grid for the next frame
+  if (tid == 0) {
+    for (int t = 0; t < kMaxResTiles; ++t) mbar_init(&s_full[t], 1);
+    fence_mbar_init();
+    for (int t = 0; t < T && t < kMaxResTiles; ++t) {
+      const uint32_t bytes = (uint32_t)min(kTilePts, cnt - t * kTilePts) * 16u;
+      mbar_arrive_expect_tx(&s_full[t], bytes);
+      bulk_copy_g2s(s_pts + t * kTilePts, pts + beg + t * kTilePts, bytes, &s_full[t]);
     }
-    labels[i] = (uint8_t)lab;
   }
-  const unsigned be = __ballot_sync(0xFFFFFFFFu, lab == 2);
-  const unsigned bg = __ballot_sync(0xFFFFFFFFu, lab == 1);
-  if (lane == 0) { s_we[warp] = __popc(be); s_wg[warp] = __popc(bg); }
+  for (int k = cta * kFusedThreads + tid; k < kPolarCells; k += G * kFusedThreads) keys_next[k] = fkey(1000.f);  // Cell::Cell(): minZ = 1000
   __syncthreads();
 
-  if (warp == 0) {
-    const unsigned ve = s_we[lane], vg = s_wg[lane];
-    unsigned ie = ve, ig = vg;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned te = __shfl_up_sync(0xFFFFFFFFu, ie, o), tg = __shfl_up_sync(0xFFFFFFFFu, ig, o);
-      if (lane >= o) { ie += te; ig += tg; }
+  // ---- phase 1: point -> polar cell, min z per cell
+  for (int t = 0; t < T; ++t) {
+    const int li = t * kTilePts + tid;
+    const bool valid = li < cnt;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < kMaxResTiles) {
+      mbar_wait(&s_full[t], 0u);
+      if (valid) q = s_pts[li];
+    } else if (valid) q = __ldg(&pts[beg + li]);
+    unsigned c = kNoCell;
+    unsigned key = 0xFFFFFFFFu;
+    if (valid) {
+      c = polar_cell(q.x, q.y, p);
+      float z = q.z;
+      if (z == 0.f) z = 0.f;                       // -0 -> +0 (`z < minZ` does not order them either)
+      if (c != kNoCell && z == z) key = fkey(z);   // NaN z never wins `z < minZ` (ground_removal.cpp:41)
     }
-    s_we[lane] = ie - ve;
-    s_wg[lane] = ig - vg;
-    const unsigned agg_e = __shfl_sync(0xFFFFFFFFu, ie, 31), agg_g = __shfl_sync(0xFFFFFFFFu, ig, 31);
-    volatile unsigned long long* desc = tile_desc;
-    if (lane == 0 && tile > 0) desc[tile] = pack_desc(1u, agg_e, agg_g);
-    // decoupled look-back, 32 predecessors per round
-    unsigned ex_e = 0, ex_g = 0;
-    int j = tile - 1 - lane;
-    while (true) {
-      unsigned long long d = (j >= 0) ? desc[j] : pack_desc(2u, 0u, 0u);
-      while (__any_sync(0xFFFFFFFFu, (d >> 62) == 0ull)) {
-        if ((d >> 62) == 0ull) d = desc[j];
+    s_cell[li] = (uint16_t)c;
+    // consecutive HDL-64 returns fall into the same cell: one atomic per distinct cell per warp
+    const unsigned grp = __match_any_sync(0xFFFFFFFFu, c);
+    const unsigned kmin = __reduce_min_sync(grp, key);
+    if (c != kNoCell && lane == __ffs(grp) - 1 && kmin != 0xFFFFFFFFu) atomicMin(&keys[c], kmin);
+  }
+  grid_barrier(bar, bar_base + (unsigned)G);
+
+  // ---- phase 2: the polar grid, channels split over the first min(G, 80) CTAs
+  {
+    const int gc = G < kNumChannel ? G : kNumChannel;
+    if (cta < gc) {
+      const int own0 = cta * kNumChannel / gc, own1 = (cta + 1) * kNumChannel / gc;
+      polar_grid_slice(p, keys, own0, own1 - own0, s_H, s_G, o_minz, o_height, o_smoothed, o_hdiff, o_hg);
+    }
+  }
+  grid_barrier(bar, bar_base + 2u * (unsigned)G);
+
+  // ---- phase 3: labels (ground_removal.cpp:221-247), per-warp counts
+  unsigned labs = 0;                                // 2 bits per tile: 0 dropped, 1 ground, 2 elevated
+  for (int t = 0; t < T; ++t) {
+    const int li = t * kTilePts + tid;
+    int lab = 0;
+    if (li < cnt) {
+      const unsigned c = s_cell[li];
+      if (c != kNoCell) {
+        const float z = (t < kMaxResTiles) ? s_pts[li].z : __ldg(&pts[beg + li]).z;
+        const float h = __ldcg(&o_hg[c]);                       // -inf for non-ground cells -> elevated
+        lab = ((double)z < __dadd_rn((double)h, p.tol)) ? 1 : 2;   // :236-246
       }
-      const unsigned pm = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2ull);
-      const int first = pm ? (__ffs(pm) - 1) : 31;
-      unsigned ce = (lane <= first) ? (unsigned)((d >> 31) & 0x7FFFFFFFull) : 0u;
-      unsigned cg = (lane <= first) ? (unsigned)(d & 0x7FFFFFFFull) : 0u;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { ce += __shfl_xor_sync(0xFFFFFFFFu, ce, o); cg += __shfl_xor_sync(0xFFFFFFFFu, cg, o); }
-      ex_e += ce; ex_g += cg;
-      if (pm) break;
-      j -= 32;
     }
+    labs |= (unsigned)lab << (2 * t);
+    const unsigned be = __ballot_sync(0xFFFFFFFFu, lab == 2);
+    const unsigned bg = __ballot_sync(0xFFFFFFFFu, lab == 1);
+    if (lane == 0) s_cnt[t * 32 + warp] = (unsigned)__popc(be) | ((unsigned)__popc(bg) << 16);
+  }
+  __syncthreads();
+  if (warp < T) {                                   // warp w scans the 32 warp counts of tile w
+    const unsigned v = s_cnt[warp * 32 + lane];
+    unsigned inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += u; }
+    s_wex[warp * 32 + lane] = inc - v;
+    if (lane == 31) s_ttot[warp] = inc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // chunk totals -> published once; every CTA sums the totals of its predecessors (all CTAs are co-resident)
+    unsigned te = 0, tg = 0;
+    if (lane < T) { const unsigned v = s_ttot[lane]; te = v & 0xFFFFu; tg = v >> 16; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { te += __shfl_xor_sync(0xFFFFFFFFu, te, o); tg += __shfl_xor_sync(0xFFFFFFFFu, tg, o); }
+    volatile unsigned long long* d = desc;
     if (lane == 0) {
-      desc[tile] = pack_desc(2u, ex_e + agg_e, ex_g + agg_g);
-      s_base_e = ex_e; s_base_g = ex_g;
-      if (tile == (int)gridDim.x - 1) { counters[CNT_N_ELEV] = (int)(ex_e + agg_e); counters[CNT_N_GROUND] = (int)(ex_g + agg_g); }
+      d[2 * cta] = ((unsigned long long)epoch << 32) | te;
+      d[2 * cta + 1] = ((unsigned long long)epoch << 32) | tg;
+    }
+    unsigned se = 0, sg = 0;
+    for (int j = lane; j < cta; j += 32) {
+      unsigned long long a = d[2 * j], b = d[2 * j + 1];
+      unsigned spin = 0;
+      while ((unsigned)(a >> 32) != epoch || (unsigned)(b >> 32) != epoch) {
+        a = d[2 * j]; b = d[2 * j + 1];
+        if (++spin > (1u << 22)) __trap();
+      }
+      se += (unsigned)a; sg += (unsigned)b;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { se += __shfl_xor_sync(0xFFFFFFFFu, se, o); sg += __shfl_xor_sync(0xFFFFFFFFu, sg, o); }
+    if (lane == 0) {
+      s_base[0] = se; s_base[1] = sg;
+      if (cta == G - 1) { out.counters[CNT_N_ELEV] = (int)(se + te); out.counters[CNT_N_GROUND] = (int)(sg + tg); }
     }
   }
   __syncthreads();
+
+  // ---- phase 3b: order-preserving output clouds + the first pass of clustering on the elevated points
+  unsigned run_e = s_base[0], run_g = s_base[1];
   const unsigned lt = (1u << lane) - 1u;
-  unsigned cc = kNoCell;
-  if (lab == 2) {
-    const unsigned pos = s_base_e + s_we[warp] + __popc(be & lt);
-    elev[pos] = make_float4(q.x, q.y, q.z, 1.f);
-    if (cart_count) { cc = cart_cell_of(q.x, q.y, roi, kNumGrid); cart[pos] = (uint16_t)cc; }
-  } else if (lab == 1) ground[s_base_g + s_wg[warp] + __popc(bg & lt)] = make_float4(q.x, q.y, q.z, 1.f);
-  // fused first pass of clustering (mapCartesianGrid, component_clustering.cpp:38-47): the elevated point is still in
-  // registers, so bin it now instead of re-reading the elevated cloud in a separate kernel
-  if (cart_count) {
-    const unsigned grp = __match_any_sync(0xFFFFFFFFu, cc);
-    if (cc != kNoCell && lane == __ffs(grp) - 1) atomicAdd(&cart_count[cc], __popc(grp));
+  for (int t = 0; t < T; ++t) {
+    const int li = t * kTilePts + tid;
+    const int lab = (int)((labs >> (2 * t)) & 3u);
+    const unsigned be = __ballot_sync(0xFFFFFFFFu, lab == 2);
+    const unsigned bg = __ballot_sync(0xFFFFFFFFu, lab == 1);
+    const unsigned wex = s_wex[t * 32 + warp];
+    unsigned cc = kNoCell;
+    if (li < cnt) {
+      if (out.labels) out.labels[beg + li] = (uint8_t)lab;
+      if (lab) {
+        const float4 q = (t < kMaxResTiles) ? s_pts[li] : __ldg(&pts[beg + li]);
+        if (lab == 2) {
+          const unsigned pos = run_e + (wex & 0xFFFFu) + __popc(be & lt);
+          out.elev[pos] = make_float4(q.x, q.y, q.z, 1.f);
+          if (out.cart) { cc = cart_cell_of(q.x, q.y, roi, kNumGrid); out.cart[pos] = (uint16_t)cc; }
+        } else {
+          out.ground[run_g + (wex >> 16) + __popc(bg & lt)] = make_float4(q.x, q.y, q.z, 1.f);
+        }
+      }
+    }
+    if (out.cart_count) {      // mapCartesianGrid, component_clustering.cpp:38-47: one atomic per distinct cell per warp
+      const unsigned grp = __match_any_sync(0xFFFFFFFFu, cc);
+      if (cc != kNoCell && lane == __ffs(grp) - 1) atomicAdd(&out.cart_count[cc], __popc(grp));
+    }
+    const unsigned tt = s_ttot[t];
+    run_e += tt & 0xFFFFu; run_g += tt >> 16;
   }
 }
 
-__global__ void init_keys_kernel(unsigned* keys) {
+// inspection only (lmot_debug_cell_index): the fused kernel keeps the cell ids in shared memory
+__global__ void polar_cells_kernel(const float4* __restrict__ pts, int n, GroundParams p, uint16_t* __restrict__ cell) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float4 q = __ldg(&pts[i]); cell[i] = polar_cell(q.x, q.y, p); }
+}
+
+__global__ void init_keys_kernel(unsigned* keys, int n) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < kPolarCells) keys[k] = fkey(1000.f);
+  if (k < n) keys[k] = fkey(1000.f);
 }
 
 }  // namespace
 
 int ground_alloc(Ctx* c, Slot* s) {
   const size_t np = (size_t)c->max_points;
-  c->max_tiles = (c->max_points + kScanTile - 1) / kScanTile;
   cudaStream_t st = s->stream;
+  // co-residency limit of the cooperative kernel on this device (1 CTA per SM at this shared-memory size)
+  if (c->fused_max_ctas == 0) {
+    LMOT_CUDA(c, cudaFuncSetAttribute(ground_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
+    int sms = 0, per_sm = 0, coop = 0;
+    LMOT_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    LMOT_CUDA(c, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+    LMOT_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ground_fused_kernel, kFusedThreads, kFusedSmem));
+    if (!coop || per_sm < 1 || sms * per_sm < kMinCtas) { c->last_error = "device cannot run the cooperative ground kernel"; return LMOT_ERR_CUDA; }
+    c->fused_max_ctas = sms * per_sm;
+    if ((long long)c->fused_max_ctas * kMaxTiles * kTilePts < (long long)c->max_points) {
+      c->last_error = "max_points exceeds what one cooperative launch covers on this device";
+      return LMOT_ERR_CAPACITY;
+    }
+  }
   LMOT_CUDA(c, cudaMalloc(&s->d_points, np * sizeof(float4)));
   LMOT_CUDA(c, cudaMalloc(&s->d_stage_in, np * 4 * sizeof(float)));
   LMOT_CUDA(c, cudaMalloc(&s->d_cell, np * sizeof(uint16_t)));
-  LMOT_CUDA(c, cudaMalloc(&s->d_polar_key, kPolarCells * sizeof(unsigned)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_polar_key, 2 * kPolarCells * sizeof(unsigned)));
   LMOT_CUDA(c, cudaMalloc(&s->d_minz, kPolarCells * sizeof(float)));
   LMOT_CUDA(c, cudaMalloc(&s->d_height, kPolarCells * sizeof(float)));
   LMOT_CUDA(c, cudaMalloc(&s->d_smoothed, kPolarCells * sizeof(float)));
@@ -395,12 +472,16 @@ int ground_alloc(Ctx* c, Slot* s) {
   LMOT_CUDA(c, cudaMalloc(&s->d_labels, np));
   LMOT_CUDA(c, cudaMalloc(&s->d_elev, np * sizeof(float4)));
   LMOT_CUDA(c, cudaMalloc(&s->d_ground, np * sizeof(float4)));
-  LMOT_CUDA(c, cudaMalloc(&s->d_tile_desc, (size_t)c->max_tiles * sizeof(unsigned long long)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_gdesc, (size_t)2 * c->fused_max_ctas * sizeof(unsigned long long)));
+  LMOT_CUDA(c, cudaMemsetAsync(s->d_gdesc, 0, (size_t)2 * c->fused_max_ctas * sizeof(unsigned long long), st));
+  LMOT_CUDA(c, cudaMalloc(&s->d_gbar, sizeof(unsigned)));
+  LMOT_CUDA(c, cudaMemsetAsync(s->d_gbar, 0, sizeof(unsigned), st));
+  s->bar_base = 0; s->epoch = 0;
   LMOT_CUDA(c, cudaMalloc(&s->d_counters, CNT_COUNT * sizeof(int)));
   LMOT_CUDA(c, cudaMemsetAsync(s->d_counters, 0, CNT_COUNT * sizeof(int), st));
   LMOT_CUDA(c, cudaHostAlloc(&s->h_counters, CNT_COUNT * sizeof(int), cudaHostAllocDefault));
   LMOT_CUDA(c, cudaHostAlloc(&s->h_set, CNT_COUNT * sizeof(int), cudaHostAllocDefault));
-  init_keys_kernel<<<(kPolarCells + 255) / 256, 256, 0, st>>>(s->d_polar_key);
+  init_keys_kernel<<<(2 * kPolarCells + 255) / 256, 256, 0, st>>>(s->d_polar_key, 2 * kPolarCells);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }
@@ -408,7 +489,7 @@ int ground_alloc(Ctx* c, Slot* s) {
 void ground_free(Slot* s) {
   cudaFree(s->d_points); cudaFree(s->d_stage_in); cudaFree(s->d_cell); cudaFree(s->d_polar_key); cudaFree(s->d_minz);
   cudaFree(s->d_height); cudaFree(s->d_smoothed); cudaFree(s->d_hdiff); cudaFree(s->d_hg); cudaFree(s->d_labels);
-  cudaFree(s->d_elev); cudaFree(s->d_ground); cudaFree(s->d_tile_desc); cudaFree(s->d_counters);
+  cudaFree(s->d_elev); cudaFree(s->d_ground); cudaFree(s->d_gdesc); cudaFree(s->d_gbar); cudaFree(s->d_counters);
   if (s->h_counters) cudaFreeHost(s->h_counters);
   if (s->h_set) cudaFreeHost(s->h_set);
 }
@@ -419,25 +500,42 @@ int ground_repack(Ctx* c, cudaStream_t st, const float* d_in, int n, int stride,
   return LMOT_OK;
 }
 
-int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count) {
+// per-point polar cell ids of the slot's current frame, recomputed with the same device function (inspection only)
+int ground_cells_debug(Ctx* c, Slot* s, cudaStream_t st) {
+  if (s->cur_n > 0) polar_cells_kernel<<<(s->cur_n + 255) / 256, 256, 0, st>>>(s->cur_points, s->cur_n, c->gp, s->d_cell);
+  LMOT_CUDA(c, cudaGetLastError());
+  return LMOT_OK;
+}
+
+int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count, bool want_labels) {
   s->cur_points = pts;
   s->cur_n = n;
-  const int n_tiles = (n + kScanTile - 1) / kScanTile;
-  if (n > 0) {
-    const int bin_tiles = (n + kBinTile - 1) / kBinTile;
-    const int bin_ctas = bin_tiles < c->bin_ctas ? bin_tiles : c->bin_ctas;     // persistent: <= 2 CTAs per SM
-    polar_bin_kernel<<<bin_ctas, kBinTile, 0, st>>>(pts, n, c->gp, s->d_cell, s->d_polar_key);
-    kernel_mark(c, s, st);
-  }
-  polar_grid_kernel<<<kGridCtas, kGridThreads, 0, st>>>(
-      c->gp, s->d_polar_key, s->d_minz, s->d_height, s->d_smoothed, s->d_hdiff, s->d_hg, s->d_tile_desc, n_tiles, s->d_counters);
+  // CTAs: enough that a chunk is a handful of 16 KB tiles, never fewer than kMinCtas (channel split of phase 2),
+  // never more than can be co-resident
+  int G = (n + c->pts_per_cta - 1) / c->pts_per_cta;
+  if (G < kMinCtas) G = kMinCtas;
+  if (G > c->fused_max_ctas) G = c->fused_max_ctas;
+  int chunk = (n + G - 1) / G;
+  if (chunk > kMaxTiles * kTilePts) return LMOT_ERR_CAPACITY;
+  const int parity = (int)(s->epoch & 1u);
+  s->epoch += 1;
+  unsigned* keys = s->d_polar_key + parity * kPolarCells;
+  unsigned* keys_next = s->d_polar_key + (1 - parity) * kPolarCells;
+  FusedOut out;
+  out.labels = want_labels ? s->d_labels : nullptr;
+  out.elev = s->d_elev; out.ground = s->d_ground;
+  out.cart = fuse_count ? s->d_cart : nullptr;
+  out.cart_count = fuse_count ? s->d_count : nullptr;
+  out.counters = s->d_counters;
+  unsigned bar_base = s->bar_base, epoch = s->epoch;
+  float roi = c->prm.roi_m;
+  GroundParams gp = c->gp;
+  void* args[] = {(void*)&pts, (void*)&n, (void*)&chunk, (void*)&gp, (void*)&keys, (void*)&keys_next, (void*)&s->d_minz,
+                  (void*)&s->d_height, (void*)&s->d_smoothed, (void*)&s->d_hdiff, (void*)&s->d_hg, (void*)&s->d_gbar,
+                  (void*)&bar_base, (void*)&s->d_gdesc, (void*)&epoch, (void*)&out, (void*)&roi};
+  LMOT_CUDA(c, cudaLaunchCooperativeKernel((const void*)ground_fused_kernel, dim3(G), dim3(kFusedThreads), args, kFusedSmem, st));
+  s->bar_base += 2u * (unsigned)G;
   kernel_mark(c, s, st);
-  if (n > 0)
-    classify_partition_kernel<<<n_tiles, kScanTile, 0, st>>>(pts, n, s->d_cell, s->d_hg, c->gp.tol, s->d_labels, s->d_elev,
-                                                           s->d_ground, s->d_tile_desc, s->d_counters, c->prm.roi_m, s->d_cart,
-                                                           fuse_count ? s->d_count : nullptr, s->d_polar_key);
-  if (n > 0) kernel_mark(c, s, st);
-  LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }
 

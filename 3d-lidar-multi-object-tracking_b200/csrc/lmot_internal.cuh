@@ -93,7 +93,7 @@ struct Slot {
 
   // ---- ground removal
   uint16_t* d_cell = nullptr;          // per point polar cell (ch*120+bin) or kNoCell
-  unsigned* d_polar_key = nullptr;     // [9600] order-preserving uint key of min z
+  unsigned* d_polar_key = nullptr;     // [2][9600] order-preserving uint key of min z; frame k uses grid k&1 and re-arms the other
   float* d_minz = nullptr;             // [9600] debug / parity
   float* d_height = nullptr;           // [9600]
   float* d_smoothed = nullptr;         // [9600]
@@ -102,7 +102,10 @@ struct Slot {
   uint8_t* d_labels = nullptr;         // per point 0/1/2
   float4* d_elev = nullptr;            // compacted elevated cloud
   float4* d_ground = nullptr;          // compacted ground cloud
-  unsigned long long* d_tile_desc = nullptr;  // decoupled look-back descriptors
+  unsigned long long* d_gdesc = nullptr;  // [2*CTAs] epoch-tagged per-CTA output counts of the fused ground kernel
+  unsigned* d_gbar = nullptr;          // grid-barrier arrival counter of the fused ground kernel (never reset)
+  unsigned bar_base = 0;               // host: arrivals of all earlier launches on this slot
+  unsigned epoch = 0;                  // host: launches so far on this slot (tag of d_gdesc, parity of d_polar_key)
   int* d_counters = nullptr;           // [CNT_COUNT]
   int* h_counters = nullptr;           // pinned mirror
   int* h_set = nullptr;                // pinned staging for host-written counters
@@ -144,7 +147,9 @@ struct Ctx {
   GroundParams gp;
 
   // ---- capacities
-  int max_points = 0, max_tiles = 0, max_sort_tiles = 0, fit_ctas = 296, bin_ctas = 296, n_mt_raw = 0;
+  int max_points = 0, max_sort_tiles = 0, fit_ctas = 296, n_mt_raw = 0;
+  int fused_max_ctas = 0;              // co-residency limit of the cooperative ground kernel on this device
+  int pts_per_cta = 4096;              // target chunk of the fused ground kernel (LMOT_PTS_PER_CTA overrides, tuning only)
   unsigned long long* d_mt_raw = nullptr;  // raw mt19937_64(0) outputs (shared, read only)
 
   // ---- detection slots
@@ -201,7 +206,9 @@ inline void kernel_mark(Ctx* c, Slot* s, cudaStream_t st) {
 int ground_alloc(Ctx* c, Slot* s);
 void ground_free(Slot* s);
 // pts: device float4 array of n points; fuse_count: also bin the elevated points into the slot's cartesian count grid
-int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count = false);
+// want_labels: also write the per-point u8 label array (stage entry point); the frame pipeline skips it
+int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count = false, bool want_labels = true);
+int ground_cells_debug(Ctx* c, Slot* s, cudaStream_t st);
 int ground_repack(Ctx* c, cudaStream_t st, const float* d_in, int n, int stride, float4* d_out);
 int cluster_alloc(Ctx* c, Slot* s);
 void cluster_free(Slot* s);

@@ -14,8 +14,8 @@ Printed JSON (rank 0, one line):
   value     whole-job frames/s with the frames already resident in HBM (CUDA events around K steps, max over ranks)
   e2e       frames/s through the reference-facing C ABI call lmot_frame() on HOST buffers: every step copies the frame
             H2D from pinned memory, runs the four stages and copies boxes + track outputs back, then synchronises
-  roofline  the ground-removal stage (polar_bin + polar_grid + classify_partition kernels, the only stage that
-            streams the whole frame): algorithmic bytes per frame / its CUDA-event duration, vs the measured HBM peak
+  roofline  ground_fused_kernel (the whole ground-removal stage in one cooperative launch, the only stage that streams
+            the whole frame): algorithmic bytes per frame / its CUDA-event duration, vs the measured HBM peak
   cpu_baseline  the reference's own four entry points on a bounded sample of the same frames, one host thread
 """
 from __future__ import annotations
@@ -39,9 +39,9 @@ PKG = "3d-lidar-multi-object-tracking_b200"
 
 WORKLOAD = "hdl64_120k_64trk_full_pipeline"
 SCENE = dict(n_objects=150, lattice_pitch=3.8, ped_fraction=0.65, seed=1)   # ~64 live tracks at steady state
-KERNEL_NAMES = ("polar_bin", "polar_grid", "classify_partition", "ccl_cluster", "tile_hist", "seg_offsets", "scatter", "box_fit",
+KERNEL_NAMES = ("ground_fused", "ccl_cluster", "tile_hist", "seg_offsets", "scatter", "box_fit",
                 "imm_predict_gate", "imm_update", "spawn_output")
-KERNELS_PER_FRAME = 11   # ground 3 (classify also bins the elevated points) + cluster 1 + box 4 + tracker 3
+KERNELS_PER_FRAME = len(KERNEL_NAMES)   # ground 1 (cooperative; also bins the elevated points) + cluster 1 + box 4 + tracker 3
 
 
 def make_frames(synth, n_frames, seed_offset=0):
@@ -233,7 +233,7 @@ def run_shared_tracker(args, lmot, ctx, d_frames, ts, n_pts, rank, world, local_
             "config": {"workload": "hdl64_120k_shared_tracker_" + args.shared_tracker, "points_per_frame": n_pts, "scene": SCENE,
                        "tracks_in_table_end": int(len(out["track_manage"])), "live_tracks_end": int((out["track_manage"] > 0).sum()),
                        "parallelism": f"detection on {world} GPUs, one track table on rank 0, NCCL all_gather(boxes) + broadcast(outputs, table)"},
-            "gpu_launches": 11 * K}))
+            "gpu_launches": KERNELS_PER_FRAME * K}))
 
 
 # ------------------------------------------------------------------------------------------- our arm
@@ -447,7 +447,7 @@ def main():
                     "host_us_per_step": {"submit": 1e6 * t_submit / K, "collect_incl_wait": 1e6 * t_collect / K}},
             "gpu_launches": KERNELS_PER_FRAME * K,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "ground_removal stage (polar_bin_kernel + polar_grid_kernel + classify_partition_kernel)",
+            "roofline": {"bound": "hbm", "kernel": "ground_fused_kernel (the whole ground_removal stage: bin + polar grid + classify/partition, one cooperative launch)",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "algorithmic_bytes_per_launch": ground_bytes, "avg_launch_ms": float(stage_ms[0]), "traffic": None},
             "stage_ms": {n: float(v) for n, v in zip(("ground", "cluster", "box", "tracker"), stage_ms)},

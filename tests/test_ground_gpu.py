@@ -119,3 +119,48 @@ def test_channel_boundaries_fast_and_exact_paths_agree(lm, ref_intended):
     e_ref, g_ref = ref_intended.ground_remove(pts)
     assert np.array_equal(out["elevated"][:, :3].view(np.uint32), e_ref.view(np.uint32))
     assert np.array_equal(out["ground"][:, :3].view(np.uint32), g_ref.view(np.uint32))
+
+
+def _ctx_with(pkg_mod, pts_per_cta, max_points=None):
+    import os
+    old = os.environ.get("LMOT_PTS_PER_CTA")
+    os.environ["LMOT_PTS_PER_CTA"] = str(pts_per_cta)
+    try:
+        p = pkg_mod.default_params()
+        if max_points:
+            p.max_points = max_points
+        p.pipeline_depth = 1
+        return pkg_mod.Lmot(p, device=0)
+    finally:
+        if old is None:
+            del os.environ["LMOT_PTS_PER_CTA"]
+        else:
+            os.environ["LMOT_PTS_PER_CTA"] = old
+
+
+def test_fused_kernel_chunkings_bit_exact(pkg, ref_intended, synth):
+    """ground_fused_kernel splits the frame into per-CTA chunks of 16 KB tiles: the result must not depend on the split.
+    256 points per CTA = every SM gets a partial tile; 16384 = the minimum of 8 CTAs with multi-tile chunks."""
+    pts = synth.uniform_cloud(120000, 21)
+    for ppc in (256, 1000, 16384):
+        ctx = _ctx_with(pkg, ppc)
+        try:
+            _check_frame(ctx, ref_intended, pts)
+            _check_frame(ctx, ref_intended, pts[:777])
+        finally:
+            ctx.close()
+
+
+def test_fused_kernel_tiles_beyond_shared_memory_bit_exact(pkg, ref_intended, synth):
+    """Chunks longer than the 7 shared-memory-resident tiles (frames > ~1.06 M points on 148 SMs) re-read their tail from
+    global memory in the classification phase: 1.6 M points, bit-exact against the reference."""
+    pts = synth.uniform_cloud(1_600_000, 22)
+    ctx = _ctx_with(pkg, 16384, max_points=1_600_000)
+    try:
+        out = ctx.ground_remove(pts)
+        e_ref, g_ref = ref_intended.ground_remove(pts)
+        assert np.array_equal(out["elevated"][:, :3].view(np.uint32), e_ref.view(np.uint32))
+        assert np.array_equal(out["ground"][:, :3].view(np.uint32), g_ref.view(np.uint32))
+        assert np.array_equal(out["labels"], labels_from_clouds(pts, e_ref, g_ref))
+    finally:
+        ctx.close()
