@@ -349,6 +349,7 @@ void lmot_destroy(lmot_ctx* ctx) {
   for (int i = 0; i < c->n_slots; ++i) slot_destroy(&c->slots[i]);
   for (int i = 0; i < c->n_results; ++i) result_destroy(&c->results[i]);
   tracker_free(c);
+  cudaFree(c->d_phase_clock);
   cudaFree(c->d_mt_raw);
   if (c->trk_stream) cudaStreamDestroy(c->trk_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -464,6 +465,7 @@ int lmot_box_fit(lmot_ctx* ctx, const float* elevated, int n, int stride, const 
   cudaStream_t st = c->stream;
   if ((rc = upload_points(c, s, st, elevated, n, stride, s->d_elev))) return rc;
   LMOT_CUDA(c, cudaMemcpyAsync(s->d_label_grid, grid, kCartCells * sizeof(int), cudaMemcpyHostToDevice, st));
+  s->label_grid_foreign = true;
   if ((rc = set_counter(c, s, st, CNT_N_ELEV, n))) return rc;
   if ((rc = set_counter(c, s, st, CNT_NUM_CLUSTER, num_cluster))) return rc;
   s->res = &c->results[0];
@@ -764,6 +766,24 @@ int lmot_debug_cell_index(lmot_ctx* ctx, int32_t* ch, int32_t* bin, int n) {
     if (cell[i] == kNoCell) { ch[i] = -1; bin[i] = -1; }
     else { ch[i] = cell[i] / kNumBin; bin[i] = cell[i] % kNumBin; }
   }
+  return LMOT_OK;
+}
+
+// diagnostic: switch the phase clock of ground_fused_kernel on (allocates [CTAs][8] u64) and read the last launch's stamps
+int lmot_debug_phase_clock(lmot_ctx* ctx, unsigned long long* out, int cap_ctas, int* n_ctas) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  int rc = lmot_sync(ctx);
+  if (rc) return rc;
+  if (!c->d_phase_clock) {
+    LMOT_CUDA(c, cudaMalloc(&c->d_phase_clock, (size_t)c->fused_max_ctas * 8 * sizeof(unsigned long long)));
+    LMOT_CUDA(c, cudaMemset(c->d_phase_clock, 0, (size_t)c->fused_max_ctas * 8 * sizeof(unsigned long long)));
+    if (n_ctas) *n_ctas = 0;
+    return LMOT_OK;
+  }
+  const int g = c->last_ground_ctas < cap_ctas ? c->last_ground_ctas : cap_ctas;
+  if (out && g > 0) LMOT_CUDA(c, cudaMemcpy(out, c->d_phase_clock, (size_t)g * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (n_ctas) *n_ctas = g;
   return LMOT_OK;
 }
 

@@ -6,56 +6,57 @@
 //   findComponent/search (:228-257)  raster scan (x outer, y inner); each unlabelled occupied cell starts
 //                               id = ++numCluster and a recursive 8-connected flood fill
 //
-// B200 design: two launches per frame.
-//   C1 cart_count_kernel   one thread per elevated point: fp32 binning exactly as :43-48, u16 cell id kept for
-//                          box fitting, warp-aggregated atomicAdd (one atomic per distinct cell per warp).
-//   C2 ccl_cluster_kernel  ONE thread-block cluster (8 CTAs x 1024 threads, cluster.sync between phases, the
-//                          per-CTA root counts exchanged through distributed shared memory):
-//                            seed = count>1 -> occupied = dilate3x3(seed) -> lock-free union-find with
-//                            atomicMin (root = smallest linear index of the component) -> flatten ->
-//                            id = 1 + rank of the root among all roots in linear (raster) order.
-//                          The recursive fill labels components in the order the raster scan first meets
-//                          them, which is exactly the order of their smallest linear index: identical ids.
-#include <cooperative_groups.h>
+// B200 design: the grid is 250 rows of 250 BITS (8 words per row, 8 KB in all), not 62,500 counters.
+//   * "count > 1" needs no counter: two bit planes, `once` and `twice`.  A point sets its cell's bit in `once`; if it
+//     was set already (or two points of one warp share the cell) it sets the bit in `twice`.  seed == twice.
+//     (cart_mark(), called by ground_fused_kernel for every elevated point while it is still in registers, or by
+//     cart_mark_kernel for the stand-alone entry point.)
+//   * ccl_bitmap_kernel, ONE CTA, everything in shared memory:
+//       dilate3x3 on words  ->  "pieces" (maximal runs of 1-bits inside a word; <= 16 per word, node id = word*16 + k,
+//       monotone in the raster index of the piece's first cell)  ->  union-find over pieces (atomicMin, root = smallest
+//       id): a piece joins the previous word's last piece when the run continues across the word boundary, and every
+//       piece of the row above that touches its 1-cell halo  ->  path flattening  ->  id = 1 + rank of the root among
+//       the roots in node order.  The recursive fill labels components in the order the raster scan first meets them,
+//       i.e. by their smallest linear index == smallest node id: identical ids.
+//       The 250x250 int label grid (the reference's only carrier of labels) is updated SPARSELY: cells occupied in the
+//       previous frame are cleared, cells occupied now get their id (one coalesced 128 B store per touched word).
 #include "lmot_internal.cuh"
 #include "exact_math.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace lmot {
 
 namespace {
 
-constexpr int kCclCtas = 8;
+constexpr int kRowWords = 8;                                   // 250 bits per row
+constexpr int kBitWords = kNumGrid * kRowWords;                // 2000
+constexpr unsigned kLastWordMask = (1u << (kNumGrid - 32 * (kRowWords - 1))) - 1u;   // bits 0..25 of word 7
+constexpr int kPiecesPerWord = 16;
+constexpr int kNodes = kBitWords * kPiecesPerWord;             // 32000
 constexpr int kCclThreads = 1024;
-constexpr int kCclAll = kCclCtas * kCclThreads;                       // 8192 threads per frame
-constexpr int kCclPerThread = 8;                                       // 32 rows x 250 cells / 1024 threads, rounded up
-
-__device__ __forceinline__ unsigned cart_cell(float x, float y, float roi) { return cart_cell_of(x, y, roi, kNumGrid); }
+constexpr int kCclSmem = kNodes * 4 + 3 * kBitWords * 4 + 64 * 4;
 
 __global__ void __launch_bounds__(256)
-cart_count_kernel(const float4* __restrict__ elev, const int* __restrict__ counters, float roi,
-                  uint16_t* __restrict__ cart, int* __restrict__ count) {
+cart_mark_kernel(const float4* __restrict__ elev, const int* __restrict__ counters, float roi, uint16_t* __restrict__ cart,
+                 unsigned* __restrict__ once, unsigned* __restrict__ twice) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = counters[CNT_N_ELEV];
   if (blockIdx.x * blockDim.x >= n) return;      // whole block past the end (launch is sized for the input cloud)
   unsigned c = kNoCell;
   if (i < n) {
     const float4 q = __ldg(&elev[i]);
-    c = cart_cell(q.x, q.y, roi);
+    c = cart_cell_of(q.x, q.y, roi, kNumGrid);
     cart[i] = (uint16_t)c;
   }
-  const unsigned grp = __match_any_sync(0xFFFFFFFFu, c);
-  if (c != kNoCell && (threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&count[c], __popc(grp));
+  cart_mark(c, once, twice);
 }
 
 __global__ void __launch_bounds__(256)
 cart_cells_kernel(const float4* __restrict__ elev, const int* __restrict__ counters, float roi, uint16_t* __restrict__ cart) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < counters[CNT_N_ELEV]) { const float4 q = __ldg(&elev[i]); cart[i] = (uint16_t)cart_cell(q.x, q.y, roi); }
+  if (i < counters[CNT_N_ELEV]) { const float4 q = __ldg(&elev[i]); cart[i] = (uint16_t)cart_cell_of(q.x, q.y, roi, kNumGrid); }
 }
 
-// ---- union-find with root = smallest index (global-memory and shared-memory flavours) ----------------------
+// ---- union-find over shared-memory nodes, root = smallest id -------------------------------------------------
 __device__ __forceinline__ int uf_find(volatile int* L, int x) {
   int p = L[x];
   while (p != x) { x = p; p = L[x]; }
@@ -74,149 +75,117 @@ __device__ __forceinline__ void uf_union(volatile int* L, int* Lw, int a, int b)
   }
 }
 
-constexpr int kTileRows = 32;                  // 8 CTAs x 32 rows cover the 250 rows of the grid
-constexpr int kRowPitch = 256;                 // shared-memory row pitch (250 columns used)
-constexpr int kSeedRows = kTileRows + 3;       // rows ts-2 .. ts+32
-constexpr int kOccRows = kTileRows + 1;        // rows ts-1 .. ts+31
-constexpr int kCclSmem = kSeedRows * kRowPitch + kOccRows * kRowPitch + 2 * kTileRows * kRowPitch * (int)sizeof(int);
+// horizontal 3-tap dilation of one word of a row (neighbour words supply the carry bits)
+__device__ __forceinline__ unsigned hdil(const unsigned* row, int k) {
+  const unsigned s = row[k];
+  unsigned d = s | (s << 1) | (s >> 1);
+  if (k > 0) d |= row[k - 1] >> 31;
+  if (k < kRowWords - 1) d |= row[k + 1] << 31;
+  return d;
+}
 
-// One thread-block cluster per frame; CTA r owns grid rows [32r, 32r+32).  Each CTA labels its tile entirely in shared
-// memory (pointer chasing at ~30 cycles instead of ~600 through L2), only the 7 tile borders are merged through
-// global memory, and the per-CTA root counts travel through distributed shared memory.
-__global__ void __cluster_dims__(kCclCtas, 1, 1) __launch_bounds__(kCclThreads, 1)
-ccl_cluster_kernel(int* __restrict__ count, int* G, int* rid, int* __restrict__ out, int* __restrict__ counters) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int crank = (int)cluster.block_rank();
+__device__ __forceinline__ unsigned piece_starts(unsigned m) { return m & ~(m << 1); }
+// index (inside its word) of the piece that contains set bit p of word m
+__device__ __forceinline__ int piece_of(unsigned m, int p) { return __popc(piece_starts(m) & ((2u << p) - 1u)) - 1; }
+
+__global__ void __launch_bounds__(kCclThreads, 1)
+ccl_bitmap_kernel(unsigned* __restrict__ once, unsigned* __restrict__ twice, unsigned* __restrict__ prev_occ, int* __restrict__ out,
+                  int* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char ccl_smem[];
+  int* s_par = reinterpret_cast<int*>(ccl_smem);                       // [32000] parent node, later -(cluster id) at roots
+  unsigned* s_seed = reinterpret_cast<unsigned*>(s_par + kNodes);       // [2000]
+  unsigned* s_occ = s_seed + kBitWords;                                 // [2000]
+  unsigned* s_prev = s_occ + kBitWords;                                 // [2000]
+  int* s_warp = reinterpret_cast<int*>(s_prev + kBitWords);             // [32] + total
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  extern __shared__ unsigned char ccl_smem[];
-  uint8_t* s_seed = ccl_smem;                                         // [35][256] count > 1, rows ts-2..ts+32
-  uint8_t* s_occ = s_seed + kSeedRows * kRowPitch;                    // [33][256] dilated,   rows ts-1..ts+31
-  int* s_L = reinterpret_cast<int*>(s_occ + kOccRows * kRowPitch);    // [32][256] local parent (local index) or -1
-  int* s_fin = s_L + kTileRows * kRowPitch;                           // [32][256] flattened local root
-  __shared__ int s_warp[32];
-  __shared__ int s_tot[kCclCtas];
-  const int ts = crank * kTileRows;
-  const int rows = min(kTileRows, kNumGrid - ts);                     // 32, last tile 26
 
-  // A: seed = count > 1 (component_clustering.cpp:136) for the tile and its halo
-  for (int l = tid; l < kSeedRows * kRowPitch; l += kCclThreads) {
-    const int x = ts - 2 + (l >> 8), y = l & 255;
-    uint8_t sd = 0;
-    if (x >= 0 && x < kNumGrid && y < kNumGrid) sd = __ldcg(&count[x * kNumGrid + y]) > 1 ? 1 : 0;
-    s_seed[l] = sd;
+  // A: seed = cells with more than one point (component_clustering.cpp:136); the bit planes are re-armed for the next frame
+  for (int w = tid; w < kBitWords; w += kCclThreads) {
+    s_seed[w] = __ldcg(&twice[w]);
+    s_prev[w] = __ldcg(&prev_occ[w]);
+    once[w] = 0u; twice[w] = 0u;
   }
   __syncthreads();
-  // B: occupied = seed dilated 3x3, clipped at the border (:137-214), rows ts-1 .. ts+31
-  for (int l = tid; l < kOccRows * kRowPitch; l += kCclThreads) {
-    const int orow = l >> 8, y = l & 255;
-    const int x = ts - 1 + orow;
-    uint8_t occ = 0;
-    if (x >= 0 && x < kNumGrid && y < kNumGrid) {
-      const uint8_t* c = s_seed + (orow + 1) * kRowPitch + y;         // seed row of x
-      const int ym = y > 0 ? -1 : 0, yp = y < kNumGrid - 1 ? 1 : 0;   // s_seed rows outside the grid are zero
-      occ = c[ym] | c[0] | c[yp] | c[-kRowPitch + ym] | c[-kRowPitch] | c[-kRowPitch + yp] | c[kRowPitch + ym] | c[kRowPitch] |
-            c[kRowPitch + yp];
+  // B: occupied = seed dilated 3x3, clipped at the border (:137-214)
+  for (int w = tid; w < kBitWords; w += kCclThreads) {
+    const int x = w >> 3, k = w & 7;
+    unsigned o = hdil(s_seed + x * kRowWords, k);
+    if (x > 0) o |= hdil(s_seed + (x - 1) * kRowWords, k);
+    if (x < kNumGrid - 1) o |= hdil(s_seed + (x + 1) * kRowWords, k);
+    if (k == kRowWords - 1) o &= kLastWordMask;
+    s_occ[w] = o;
+    prev_occ[w] = o;
+  }
+  __syncthreads();
+  // C: one node per piece; a piece that continues the previous word's run starts as its child
+  for (int w = tid; w < kBitWords; w += kCclThreads) {
+    const unsigned m = s_occ[w];
+    if (!m) continue;
+    const int np = __popc(piece_starts(m));
+    const int k = w & 7;
+    for (int j = 0; j < np; ++j) s_par[w * kPiecesPerWord + j] = w * kPiecesPerWord + j;
+    if ((m & 1u) && k > 0) {
+      const unsigned l = s_occ[w - 1];
+      if (l >> 31) s_par[w * kPiecesPerWord] = (w - 1) * kPiecesPerWord + __popc(piece_starts(l)) - 1;
     }
-    s_occ[l] = occ;
   }
   __syncthreads();
-  // C1: label = start of the horizontal run inside the 32-cell warp chunk
-  for (int task = warp; task < kTileRows * 8; task += kCclThreads / 32) {
-    const int lx = task >> 3, y = ((task & 7) << 5) + lane;
-    const bool o = lx < rows && s_occ[(lx + 1) * kRowPitch + y];
-    const unsigned mask = __ballot_sync(0xFFFFFFFFu, o);
-    const unsigned zb = ~mask & ((1u << lane) - 1u);                  // empty cells below this lane
-    const int start = zb ? (32 - __clz(zb)) : 0;
-    s_L[lx * kRowPitch + y] = o ? (lx * kRowPitch + (y - lane) + start) : -1;
-  }
-  __syncthreads();
-  // C2/C3: runs continuing across chunk boundaries, and 8-connectivity to the row above inside the tile.  A cell only
-  // needs the unions its left neighbour cannot have made: with N occupied, skip when W and NW are occupied too; with
-  // N empty, NW only if W is empty, NE always.
+  // D: 8-connectivity to the row above: every piece of row x-1 that intersects [a-1, b+1]
   {
-    volatile int* Lv = s_L;
-    for (int l = tid; l < kTileRows * kRowPitch; l += kCclThreads) {
-      const int lx = l >> 8, y = l & 255;
-      if (lx >= rows || y >= kNumGrid || !s_occ[(lx + 1) * kRowPitch + y]) continue;
-      const uint8_t* o = s_occ + (lx + 1) * kRowPitch + y;
-      const bool W = y > 0 && o[-1];
-      if ((y & 31) == 0 && W) uf_union(Lv, s_L, l, l - 1);
-      if (lx > 0) {
-        const bool N = o[-kRowPitch], NW = y > 0 && o[-kRowPitch - 1], NE = y < kNumGrid - 1 && o[-kRowPitch + 1];
-        if (N) { if (!(W && NW)) uf_union(Lv, s_L, l, l - kRowPitch); }
-        else {
-          if (NW && !W) uf_union(Lv, s_L, l, l - kRowPitch - 1);
-          if (NE) uf_union(Lv, s_L, l, l - kRowPitch + 1);
+    volatile int* Lv = s_par;
+    for (int w = tid; w < kBitWords; w += kCclThreads) {
+      const unsigned m = s_occ[w];
+      const int x = w >> 3, k = w & 7;
+      if (!m || x == 0) continue;
+      const unsigned up = s_occ[w - kRowWords];
+      const unsigned upl = k > 0 ? s_occ[w - kRowWords - 1] : 0u;
+      const unsigned upr = k < kRowWords - 1 ? s_occ[w - kRowWords + 1] : 0u;
+      unsigned rest = m;
+      int j = 0;
+      while (rest) {
+        const int a = __ffs(rest) - 1;
+        const unsigned t = ~(rest >> a);                       // first zero above a ends the piece
+        const int len = t ? __ffs(t) - 1 : 32;
+        const unsigned pm = (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << a;
+        rest &= ~pm;
+        const int me = w * kPiecesPerWord + j;
+        ++j;
+        unsigned touched = up & (pm | (pm << 1) | (pm >> 1));
+        while (touched) {
+          const int p = __ffs(touched) - 1;
+          uf_union(Lv, s_par, me, (w - kRowWords) * kPiecesPerWord + piece_of(up, p));
+          const unsigned tu = ~(up >> p);
+          const int lu = tu ? __ffs(tu) - 1 : 32;
+          touched &= ~((lu >= 32 ? 0xFFFFFFFFu : ((1u << lu) - 1u)) << p);
         }
+        if (a == 0 && (upl >> 31)) uf_union(Lv, s_par, me, (w - kRowWords - 1) * kPiecesPerWord + __popc(piece_starts(upl)) - 1);
+        if (a + len == 32 && (upr & 1u)) uf_union(Lv, s_par, me, (w - kRowWords + 1) * kPiecesPerWord);
       }
     }
   }
   __syncthreads();
-  // D: flatten inside the tile (shared memory only).  Global memory holds a union-find node only where another CTA
-  // can need one: at the tile-local ROOT cells and in the first / last row of the tile (the border merge looks the
-  // neighbour's root up through them).  Everything else stays in shared memory -- pointer chasing through L2 costs
-  // ~20x more per hop.
+  // E: flatten (parents only ever move to smaller ancestors, so compressing in place is safe against concurrent finds)
   {
-    volatile int* Lv = s_L;
-    for (int l = tid; l < kTileRows * kRowPitch; l += kCclThreads) {
-      const int lx = l >> 8, y = l & 255;
-      if (lx >= rows || y >= kNumGrid || Lv[l] < 0) continue;
-      const int r = uf_find(Lv, l);
-      s_fin[l] = r;                                                   // flattened local root (separate array: no races)
+    volatile int* Lv = s_par;
+    for (int w = tid; w < kBitWords; w += kCclThreads) {
+      const unsigned m = s_occ[w];
+      if (!m) continue;
+      const int np = __popc(piece_starts(m));
+      for (int j = 0; j < np; ++j) { const int nd = w * kPiecesPerWord + j; Lv[nd] = uf_find(Lv, nd); }
     }
   }
   __syncthreads();
-  for (int l = tid; l < kTileRows * kRowPitch; l += kCclThreads) {
-    const int lx = l >> 8, y = l & 255;
-    if (lx >= rows || y >= kNumGrid || s_L[l] < 0) continue;
-    const int r = s_fin[l];
-    if (r == l || lx == 0 || lx == rows - 1) G[(ts + lx) * kNumGrid + y] = (ts + (r >> 8)) * kNumGrid + (r & 255);
-  }
-  cluster.sync();
-  // every CTA has read its halo: zero this tile's counts for the next frame
-  for (int l = tid; l < rows * kNumGrid; l += kCclThreads) count[ts * kNumGrid + l] = 0;
-  // E: merge across the tile border (first row of the tile against the last row of the previous tile), same rule
-  if (crank > 0 && tid < kNumGrid) {
-    const int y = tid;
-    const uint8_t* o = s_occ + 1 * kRowPitch + y;                     // row ts
-    if (o[0]) {
-      volatile int* Gv = G;
-      const int k = ts * kNumGrid + y;
-      const bool W = y > 0 && o[-1];
-      const bool N = o[-kRowPitch], NW = y > 0 && o[-kRowPitch - 1], NE = y < kNumGrid - 1 && o[-kRowPitch + 1];
-      if (N) { if (!(W && NW)) uf_union(Gv, G, k, k - kNumGrid); }
-      else {
-        if (NW && !W) uf_union(Gv, G, k, k - kNumGrid - 1);
-        if (NE) uf_union(Gv, G, k, k - kNumGrid + 1);
-      }
-    }
-  }
-  cluster.sync();
-  // F: only the tile-local roots ask global memory for their final root; every other cell reads it from its root
-  // through shared memory
-  for (int l = tid; l < kTileRows * kRowPitch; l += kCclThreads) {
-    const int lx = l >> 8, y = l & 255;
-    if (lx >= rows || y >= kNumGrid || s_L[l] < 0 || s_fin[l] != l) continue;
-    volatile int* Gv = G;
-    s_L[l] = uf_find(Gv, (ts + lx) * kNumGrid + y);                   // s_L of a local root now holds the FINAL global root
-  }
-  __syncthreads();
-  // roots of this tile in linear order, thread t owns kCclPerThread consecutive cells
-  const int cbeg = ts * kNumGrid, cend = cbeg + rows * kNumGrid;
-  const int tbeg = cbeg + tid * kCclPerThread;
+  // F: id = 1 + rank of the root among all roots in node (= raster) order (:247-257).  Thread t owns words 2t, 2t+1.
   int roots = 0;
-  unsigned rootmask = 0;
-  int fin[kCclPerThread];
+  unsigned rootmask[2] = {0u, 0u};
+  if (tid < kBitWords / 2) {
 #pragma unroll
-  for (int j = 0; j < kCclPerThread; ++j) {
-    const int k = tbeg + j;
-    fin[j] = -1;
-    if (k < cend) {
-      const int off = k - cbeg, l = (off / kNumGrid) * kRowPitch + off % kNumGrid;
-      if (s_L[l] >= 0) {
-        fin[j] = s_L[s_fin[l]];                                       // final global root of the cell
-        if (fin[j] == k) { ++roots; rootmask |= 1u << j; }
-      }
+    for (int h = 0; h < 2; ++h) {
+      const int w = 2 * tid + h;
+      const unsigned m = s_occ[w];
+      const int np = m ? __popc(piece_starts(m)) : 0;
+      for (int j = 0; j < np; ++j)
+        if (s_par[w * kPiecesPerWord + j] == w * kPiecesPerWord + j) { ++roots; rootmask[h] |= 1u << j; }
     }
   }
   int incl = roots;
@@ -230,29 +199,36 @@ ccl_cluster_kernel(int* __restrict__ count, int* G, int* rid, int* __restrict__ 
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += t; }
     s_warp[lane] = wi - v;
-    if (lane == 31)       // publish this CTA's root count into every CTA's s_tot through distributed shared memory
-      for (int r = 0; r < kCclCtas; ++r) cluster.map_shared_rank(s_tot, r)[crank] = wi;
+    if (lane == 31) { s_warp[32] = wi; counters[CNT_NUM_CLUSTER] = wi; }
   }
   __syncthreads();
-  const int excl_in_cta = s_warp[warp] + incl - roots;
-  cluster.sync();
-  int base = 0, total = 0;
-#pragma unroll
-  for (int r = 0; r < kCclCtas; ++r) { if (r < crank) base += s_tot[r]; total += s_tot[r]; }
   {
-    int rank = base + excl_in_cta;
+    int rank = s_warp[warp] + incl - roots;
 #pragma unroll
-    for (int j = 0; j < kCclPerThread; ++j)
-      if (rootmask & (1u << j)) rid[tbeg + j] = ++rank;      // id = 1 + rank in raster order (:247-257)
+    for (int h = 0; h < 2; ++h) {
+      unsigned rm = rootmask[h];
+      while (rm) { const int j = __ffs(rm) - 1; rm &= rm - 1; s_par[(2 * tid + h) * kPiecesPerWord + j] = -(++rank); }
+    }
   }
-  if (crank == 0 && tid == 0) counters[CNT_NUM_CLUSTER] = total;
-  cluster.sync();
-  // G: label grid (the ids of roots that live in other tiles come through L2; the loads are independent)
-  int ids[kCclPerThread];
-#pragma unroll
-  for (int j = 0; j < kCclPerThread; ++j) ids[j] = fin[j] >= 0 ? __ldcg(&rid[fin[j]]) : 0;
-#pragma unroll
-  for (int j = 0; j < kCclPerThread; ++j) if (tbeg + j < cend) out[tbeg + j] = ids[j];
+  __syncthreads();
+  // G: label grid, sparse: one warp per word that is occupied now or was in the previous frame, lane = cell
+  for (int w = warp; w < kBitWords; w += kCclThreads / 32) {
+    const unsigned m = s_occ[w], pv = s_prev[w];
+    if (!(m | pv)) continue;
+    if (!((m | pv) >> lane & 1u)) continue;
+    int id = 0;
+    if (m >> lane & 1u) {
+      int r = s_par[w * kPiecesPerWord + piece_of(m, lane)];
+      if (r >= 0) r = s_par[r];                                 // non-root: its root holds -(id)
+      id = -r;
+    }
+    out[(w >> 3) * kNumGrid + (w & 7) * 32 + lane] = id;
+  }
+}
+
+__global__ void zero_u32_kernel(unsigned* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0u;
 }
 
 }  // namespace
@@ -260,26 +236,30 @@ ccl_cluster_kernel(int* __restrict__ count, int* G, int* rid, int* __restrict__ 
 int cluster_alloc(Ctx* c, Slot* s) {
   const size_t np = (size_t)c->max_points;
   LMOT_CUDA(c, cudaMalloc(&s->d_cart, np * sizeof(uint16_t)));
-  LMOT_CUDA(c, cudaMalloc(&s->d_count, kCartCells * sizeof(int)));
-  LMOT_CUDA(c, cudaMalloc(&s->d_parent, kCartCells * sizeof(int)));
-  LMOT_CUDA(c, cudaMalloc(&s->d_rid, kCartCells * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_cart_bits, 3 * kBitWords * sizeof(unsigned)));      // once | twice | occupancy of the previous frame
   LMOT_CUDA(c, cudaMalloc(&s->d_label_grid, kCartCells * sizeof(int)));
-  LMOT_CUDA(c, cudaMemsetAsync(s->d_count, 0, kCartCells * sizeof(int), s->stream));
+  LMOT_CUDA(c, cudaMemsetAsync(s->d_cart_bits, 0, 3 * kBitWords * sizeof(unsigned), s->stream));
   LMOT_CUDA(c, cudaMemsetAsync(s->d_label_grid, 0, kCartCells * sizeof(int), s->stream));
-  LMOT_CUDA(c, cudaFuncSetAttribute(ccl_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCclSmem));
+  s->label_grid_foreign = false;
+  LMOT_CUDA(c, cudaFuncSetAttribute(ccl_bitmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCclSmem));
   return LMOT_OK;
 }
 
-void cluster_free(Slot* s) {
-  cudaFree(s->d_cart); cudaFree(s->d_count); cudaFree(s->d_parent); cudaFree(s->d_rid); cudaFree(s->d_label_grid);
-}
+void cluster_free(Slot* s) { cudaFree(s->d_cart); cudaFree(s->d_cart_bits); cudaFree(s->d_label_grid); }
 
 // elevated cloud = s->d_elev with its length in d_counters[CNT_N_ELEV]; n_upper bounds that length on the host
 int cluster_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper, bool counted) {
-  if (n_upper > 0 && !counted)   // `counted`: classify_partition_kernel already binned the elevated points (fused frame path)
-    cart_count_kernel<<<(n_upper + 255) / 256, 256, 0, st>>>(s->d_elev, s->d_counters, c->prm.roi_m, s->d_cart, s->d_count);
-  if (n_upper > 0 && !counted) kernel_mark(c, s, st);
-  ccl_cluster_kernel<<<kCclCtas, kCclThreads, kCclSmem, st>>>(s->d_count, s->d_parent, s->d_rid, s->d_label_grid, s->d_counters);
+  unsigned* once = s->d_cart_bits, *twice = once + kBitWords, *prev = twice + kBitWords;
+  if (s->label_grid_foreign) {   // the caller uploaded its own label grid (lmot_box_fit): the sparse update needs a clean slate
+    LMOT_CUDA(c, cudaMemsetAsync(s->d_label_grid, 0, kCartCells * sizeof(int), st));
+    LMOT_CUDA(c, cudaMemsetAsync(prev, 0, kBitWords * sizeof(unsigned), st));
+    s->label_grid_foreign = false;
+  }
+  if (n_upper > 0 && !counted) {   // `counted`: ground_fused_kernel already marked the elevated points (fused frame path)
+    cart_mark_kernel<<<(n_upper + 255) / 256, 256, 0, st>>>(s->d_elev, s->d_counters, c->prm.roi_m, s->d_cart, once, twice);
+    kernel_mark(c, s, st);
+  }
+  ccl_bitmap_kernel<<<1, kCclThreads, kCclSmem, st>>>(once, twice, prev, s->d_label_grid, s->d_counters);
   kernel_mark(c, s, st);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;

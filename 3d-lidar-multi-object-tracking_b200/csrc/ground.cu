@@ -231,6 +231,15 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// diagnostic (scripts/ground_phases.py): %globaltimer of thread 0 at the phase boundaries, [CTA][8]; nullptr in production
+__device__ __forceinline__ void phase_mark(unsigned long long* clk, int slot) {
+  if (clk && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    clk[blockIdx.x * 8 + slot] = t;
+  }
+}
+
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -264,7 +273,8 @@ struct FusedOut {
   float4* elev;
   float4* ground;
   uint16_t* cart;           // nullable: cartesian cell of every elevated point (fused first pass of clustering)
-  int* cart_count;          // nullable
+  unsigned* cart_once;      // nullable: bit planes of the cartesian grid (cluster.cu)
+  unsigned* cart_twice;
   int* counters;
 };
 
@@ -272,7 +282,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
 ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundParams p, unsigned* __restrict__ keys,
                     unsigned* __restrict__ keys_next, float* __restrict__ o_minz, float* __restrict__ o_height,
                     float* __restrict__ o_smoothed, float* __restrict__ o_hdiff, float* __restrict__ o_hg, unsigned* bar,
-                    unsigned bar_base, unsigned long long* desc, unsigned epoch, FusedOut out, float roi) {
+                    unsigned bar_base, unsigned long long* desc, unsigned epoch, FusedOut out, float roi,
+                    unsigned long long* __restrict__ phase_clock) {
   extern __shared__ __align__(128) unsigned char fsm[];
   uint64_t* s_full = reinterpret_cast<uint64_t*>(fsm + kOffBar);
   float4* s_pts = reinterpret_cast<float4*>(fsm + kOffPts);
@@ -292,6 +303,7 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
   const int cnt = end - beg;
   const int T = (cnt + kTilePts - 1) / kTilePts;
 
+  phase_mark(phase_clock, 0);
   // ---- phase 0: arm the TMA copies of the resident tiles; re-arm the OTHER key grid for the next frame
   if (tid == 0) {
     for (int t = 0; t < kMaxResTiles; ++t) mbar_init(&s_full[t], 1);
@@ -328,7 +340,9 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
     const unsigned kmin = __reduce_min_sync(grp, key);
     if (c != kNoCell && lane == __ffs(grp) - 1 && kmin != 0xFFFFFFFFu) atomicMin(&keys[c], kmin);
   }
+  phase_mark(phase_clock, 1);
   grid_barrier(bar, bar_base + (unsigned)G);
+  phase_mark(phase_clock, 2);
 
   // ---- phase 2: the polar grid, channels split over the first min(G, 80) CTAs
   {
@@ -338,7 +352,9 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
       polar_grid_slice(p, keys, own0, own1 - own0, s_H, s_G, o_minz, o_height, o_smoothed, o_hdiff, o_hg);
     }
   }
+  phase_mark(phase_clock, 3);
   grid_barrier(bar, bar_base + 2u * (unsigned)G);
+  phase_mark(phase_clock, 4);
 
   // ---- phase 3: labels (ground_removal.cpp:221-247), per-warp counts
   unsigned labs = 0;                                // 2 bits per tile: 0 dropped, 1 ground, 2 elevated
@@ -359,6 +375,7 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
     if (lane == 0) s_cnt[t * 32 + warp] = (unsigned)__popc(be) | ((unsigned)__popc(bg) << 16);
   }
   __syncthreads();
+  phase_mark(phase_clock, 5);
   if (warp < T) {                                   // warp w scans the 32 warp counts of tile w
     const unsigned v = s_cnt[warp * 32 + lane];
     unsigned inc = v;
@@ -398,6 +415,7 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
   }
   __syncthreads();
 
+  phase_mark(phase_clock, 6);
   // ---- phase 3b: order-preserving output clouds + the first pass of clustering on the elevated points
   unsigned run_e = s_base[0], run_g = s_base[1];
   const unsigned lt = (1u << lane) - 1u;
@@ -421,13 +439,11 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
         }
       }
     }
-    if (out.cart_count) {      // mapCartesianGrid, component_clustering.cpp:38-47: one atomic per distinct cell per warp
-      const unsigned grp = __match_any_sync(0xFFFFFFFFu, cc);
-      if (cc != kNoCell && lane == __ffs(grp) - 1) atomicAdd(&out.cart_count[cc], __popc(grp));
-    }
+    if (out.cart_once) cart_mark(cc, out.cart_once, out.cart_twice);   // one atomic per distinct cell per warp
     const unsigned tt = s_ttot[t];
     run_e += tt & 0xFFFFu; run_g += tt >> 16;
   }
+  phase_mark(phase_clock, 7);
 }
 
 // inspection only (lmot_debug_cell_index): the fused kernel keeps the cell ids in shared memory
@@ -525,16 +541,18 @@ int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bo
   out.labels = want_labels ? s->d_labels : nullptr;
   out.elev = s->d_elev; out.ground = s->d_ground;
   out.cart = fuse_count ? s->d_cart : nullptr;
-  out.cart_count = fuse_count ? s->d_count : nullptr;
+  out.cart_once = fuse_count ? s->d_cart_bits : nullptr;
+  out.cart_twice = fuse_count ? s->d_cart_bits + 2000 : nullptr;
   out.counters = s->d_counters;
   unsigned bar_base = s->bar_base, epoch = s->epoch;
   float roi = c->prm.roi_m;
   GroundParams gp = c->gp;
   void* args[] = {(void*)&pts, (void*)&n, (void*)&chunk, (void*)&gp, (void*)&keys, (void*)&keys_next, (void*)&s->d_minz,
                   (void*)&s->d_height, (void*)&s->d_smoothed, (void*)&s->d_hdiff, (void*)&s->d_hg, (void*)&s->d_gbar,
-                  (void*)&bar_base, (void*)&s->d_gdesc, (void*)&epoch, (void*)&out, (void*)&roi};
+                  (void*)&bar_base, (void*)&s->d_gdesc, (void*)&epoch, (void*)&out, (void*)&roi, (void*)&c->d_phase_clock};
   LMOT_CUDA(c, cudaLaunchCooperativeKernel((const void*)ground_fused_kernel, dim3(G), dim3(kFusedThreads), args, kFusedSmem, st));
   s->bar_base += 2u * (unsigned)G;
+  c->last_ground_ctas = G;
   kernel_mark(c, s, st);
   return LMOT_OK;
 }

@@ -112,10 +112,10 @@ struct Slot {
 
   // ---- clustering
   uint16_t* d_cart = nullptr;          // per elevated point cartesian cell (x*250+y) or kNoCell
-  int* d_count = nullptr;              // [62500] points per cell (zeroed by the CCL kernel after use)
-  int* d_parent = nullptr;             // [62500] union-find parent (global linear index), -1 = empty
-  int* d_rid = nullptr;                // [62500] cluster id at root cells
-  int* d_label_grid = nullptr;         // [62500] final labels (0 = empty), x-major
+  unsigned* d_cart_bits = nullptr;     // [3][2000] bit planes of the 250x250 grid (8 words per row): cells seen once | cells
+                                       // seen more than once (re-armed by the CCL kernel) | occupancy of the previous frame
+  int* d_label_grid = nullptr;         // [62500] final labels (0 = empty), x-major; updated sparsely from frame to frame
+  bool label_grid_foreign = false;     // the caller uploaded its own grid (lmot_box_fit): next clustering starts from zero
 
   // ---- box fitting
   uint16_t* d_pcid = nullptr;          // per elevated point cluster id (0 = none)
@@ -149,7 +149,9 @@ struct Ctx {
   // ---- capacities
   int max_points = 0, max_sort_tiles = 0, fit_ctas = 296, n_mt_raw = 0;
   int fused_max_ctas = 0;              // co-residency limit of the cooperative ground kernel on this device
-  int pts_per_cta = 4096;              // target chunk of the fused ground kernel (LMOT_PTS_PER_CTA overrides, tuning only)
+  unsigned long long* d_phase_clock = nullptr;   // diagnostic: [CTAs][8] %globaltimer stamps of the last ground launch (lmot_debug_phase_clock)
+  int last_ground_ctas = 0;
+  int pts_per_cta = 1024;              // target chunk of the fused ground kernel (LMOT_PTS_PER_CTA overrides, tuning only)
   unsigned long long* d_mt_raw = nullptr;  // raw mt19937_64(0) outputs (shared, read only)
 
   // ---- detection slots
@@ -201,6 +203,20 @@ struct Ctx {
 inline void kernel_mark(Ctx* c, Slot* s, cudaStream_t st) {
   if (c->timing && s->res && s->res->n_kev < kMaxKernelEvents) cudaEventRecord(s->res->kev[s->res->n_kev++], st);
 }
+
+#ifdef __CUDACC__
+// mapCartesianGrid (component_clustering.cpp:38-47) + the "more than one point" test (:136) without a counter: bit planes
+// `once` / `twice` of the 250x250 grid, 8 words per row.  c = x*250+y or 0xFFFF; ALL 32 lanes of the warp must call.
+__device__ __forceinline__ void cart_mark(unsigned c, unsigned* __restrict__ once, unsigned* __restrict__ twice) {
+  const unsigned grp = __match_any_sync(0xFFFFFFFFu, c);
+  if (c != 0xFFFFu && (int)(threadIdx.x & 31) == __ffs(grp) - 1) {
+    const unsigned x = c / (unsigned)kNumGrid, y = c - x * (unsigned)kNumGrid;
+    const unsigned w = x * 8u + (y >> 5), bit = 1u << (y & 31u);
+    if (__popc(grp) > 1) atomicOr(&twice[w], bit);
+    else if (atomicOr(&once[w], bit) & bit) atomicOr(&twice[w], bit);
+  }
+}
+#endif
 
 // ---- stage launchers (asynchronous on the given stream) -------------------------------------------------
 int ground_alloc(Ctx* c, Slot* s);

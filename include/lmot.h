@@ -209,6 +209,10 @@ int lmot_debug_cell_index(lmot_ctx* ctx, int32_t* ch, int32_t* bin, int n);
 /* label grid and per-elevated-point cluster id of the last clustering / box fitting */
 int lmot_debug_label_grid(lmot_ctx* ctx, int32_t* grid, int* num_cluster);
 
+/* diagnostic: first call switches on the phase clock of ground_fused_kernel; later calls return the %globaltimer stamps
+ * (ns) thread 0 of every CTA took at its 8 phase boundaries during the last launch: out[n_ctas][8] */
+int lmot_debug_phase_clock(lmot_ctx* ctx, unsigned long long* out, int cap_ctas, int* n_ctas);
+
 /* host-side self test of the bit-exact atan2f restatement against the host libm (no GPU needed) */
 int lmot_selftest_atan2f(const float* y, const float* x, int n, float* out);
 
@@ -216,9 +220,8 @@ int lmot_selftest_atan2f(const float* y, const float* x, int n, float* out);
  * ms[0] ground, ms[1] cluster, ms[2] box, ms[3] tracker.  Only recorded after lmot_enable_timing(ctx,1). */
 int lmot_enable_timing(lmot_ctx* ctx, int on);
 int lmot_last_stage_ms(lmot_ctx* ctx, float ms[4]);
-/* finer: device time between consecutive kernels of the last timed frame, in launch order (12 kernels: polar_bin,
- * polar_grid, classify_partition, ccl_cluster, tile_hist, seg_offsets, scatter, box_fit, imm_predict_gate, imm_update,
- * merge_overseg, spawn_output) */
+/* finer: device time between consecutive kernels of the last timed frame, in launch order (9 kernels: ground_fused,
+ * ccl_bitmap, tile_hist, seg_offsets, scatter, box_fit, imm_predict_gate, imm_update, spawn_output) */
 int lmot_last_kernel_ms(lmot_ctx* ctx, float* ms, int cap, int* n);
 /* accumulated host-side nanoseconds inside the library: [0] submit (launch calls), [1] collect: waiting for the frame's
  * event, [2] collect: copying results out of the pinned block, [3] number of collects */
