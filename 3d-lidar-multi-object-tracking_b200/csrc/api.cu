@@ -205,11 +205,12 @@ int result_create(Ctx* c, Result* r) {
   LMOT_CUDA(c, cudaHostAlloc(&r->h_det, CNT_COUNT * sizeof(int), fl));
   memset(r->h_det, 0, CNT_COUNT * sizeof(int));
   LMOT_CUDA(c, cudaHostAlloc(&r->h_boxes, (size_t)MB * 24 * sizeof(float), fl));
-  LMOT_CUDA(c, cudaHostAlloc(&r->h_targets, (size_t)TC * 3 * sizeof(float), fl));
-  LMOT_CUDA(c, cudaHostAlloc(&r->h_vandyaw, (size_t)TC * 2 * sizeof(double), fl));
-  LMOT_CUDA(c, cudaHostAlloc(&r->h_manage, (size_t)TC * sizeof(int), fl));
-  LMOT_CUDA(c, cudaHostAlloc(&r->h_static, (size_t)TC, fl));
-  LMOT_CUDA(c, cudaHostAlloc(&r->h_vis, (size_t)TC, fl));
+  // + 16 bytes: spawn_output_kernel writes whole 16-byte words
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_targets, (size_t)TC * 3 * sizeof(float) + 16, fl));
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_vandyaw, (size_t)TC * 2 * sizeof(double) + 16, fl));
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_manage, (size_t)TC * sizeof(int) + 16, fl));
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_static, (size_t)TC + 16, fl));
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_vis, (size_t)TC + 16, fl));
   LMOT_CUDA(c, cudaHostAlloc(&r->h_visbb, (size_t)TC * 24 * sizeof(float), fl));
   LMOT_CUDA(c, cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming));
   LMOT_CUDA(c, cudaEventRecord(r->ev_done, c->stream));
@@ -319,6 +320,7 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   c->gp.r_min = p.r_min; c->gp.r_max = p.r_max; c->gp.t_hmin = p.t_hmin; c->gp.t_hmax = p.t_hmax;
   c->gp.t_hdiff = p.t_hdiff; c->gp.h_sensor = p.h_sensor;
   { volatile float span = p.r_max - p.r_min; c->gp.r_span = span; }
+  c->gp.bin_scale = (float)((double)LMOT_NUM_BIN / (double)c->gp.r_span);
   c->gp.tol = p.ground_tolerance;
   gauss_taps(c->gp.tap);
   if (const char* e = getenv("LMOT_PTS_PER_CTA")) { const int v = atoi(e); if (v >= 256 && v <= 16384) c->pts_per_cta = v; }

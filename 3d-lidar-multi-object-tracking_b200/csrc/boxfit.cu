@@ -227,6 +227,7 @@ box_fit_kernel(const float4* __restrict__ sorted_pts, const int* __restrict__ se
   __shared__ int s_bidx[kFitThreads / 32];
   __shared__ float s_pc[4][2];
   __shared__ int s_flag;
+  __shared__ int s_src[kFitThreads];         // compaction: cluster id of the j-th accepted box of the current batch
   const int tid = threadIdx.x;
   const int K = min(counters[CNT_NUM_CLUSTER], max_clusters);
   const float half = P.roi / 2;
@@ -509,11 +510,19 @@ box_fit_kernel(const float4* __restrict__ sorted_pts, const int* __restrict__ se
     int wbase = 0, tot = 0;
     for (int w = 0; w < kFitThreads / 32; ++w) { if (w < (tid >> 5)) wbase += s_redi[w]; tot += s_redi[w]; }
     const int pos = carry + wbase + __popc(bal & ((1u << (tid & 31)) - 1u));
-    if (f) {
-      if (pos < max_boxes) {
-        for (int e = 0; e < 24; ++e) { const float v = __ldcg(&cl_box[(size_t)k * 24 + e]); boxes[(size_t)pos * 24 + e] = v; h_boxes[(size_t)pos * 24 + e] = v; }
-        for (int e = 0; e < 6; ++e) markers[(size_t)pos * 6 + e] = __ldcg(&cl_marker[(size_t)k * 6 + e]);
-      }
+    if (f && pos < max_boxes) s_src[pos - carry] = k;
+    __syncthreads();
+    // cooperative copy: consecutive threads move consecutive floats, so the stores into the device list AND into the
+    // pinned host block (h_boxes is mapped host memory: these stores are the D2H transfer) are full 128-byte lines
+    const int nacc = min(tot, max_boxes - carry);
+    for (int e = tid; e < nacc * 24; e += kFitThreads) {
+      const int j = e / 24, w = e - j * 24;
+      const float v = __ldcg(&cl_box[(size_t)s_src[j] * 24 + w]);
+      boxes[(size_t)(carry + j) * 24 + w] = v; h_boxes[(size_t)(carry + j) * 24 + w] = v;
+    }
+    for (int e = tid; e < nacc * 6; e += kFitThreads) {
+      const int j = e / 6, w = e - j * 6;
+      markers[(size_t)(carry + j) * 6 + w] = __ldcg(&cl_marker[(size_t)s_src[j] * 6 + w]);
     }
     carry += tot;
     __syncthreads();

@@ -37,37 +37,59 @@ __device__ __forceinline__ float fkey_inv(unsigned k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// ground_removal.cpp:46-64 (range filter) + :67-76 (getCellIndexFromPoints) + :89 (index guard)
-//
-// The channel index must equal floor(fl(fl((atan2f_glibc(y,x) + pi) / 2pi) * 80)) bit for bit.  Evaluating the exact
-// fdlibm restatement (two IEEE divisions + an 11-term polynomial without FMA, ~150 instructions) for every point makes
-// this kernel instruction-bound, so it is only used where it can matter: CUDA's own atan2f (<= 2 ulp) and glibc's
-// (<= 2 ulp) differ by < 1e-6 rad, i.e. < 1.3e-5 channel widths, and the reference's float roundings of the scaled angle
-// move it by < 1e-5 more.  A point whose fast scaled angle lies further than kChanGuard = 2e-4 channel widths from
-// every integer therefore has the same floor() under both evaluations; the rest (about 4 points in 10,000) take the
-// exact path.  The result is identical to the exact path for every point (tests/test_ground_gpu.py compares cells of
-// random, HDL-64 and boundary-hugging clouds against the reference bit for bit).
-constexpr float kChanGuard = 2.0e-4f;
-
-__device__ __forceinline__ uint16_t polar_cell(float x, float y, const GroundParams& p) {
+// ground_removal.cpp:46-64 (range filter) + :67-76 (getCellIndexFromPoints) + :89 (index guard), evaluated exactly as the
+// reference does: IEEE sqrt and divisions, glibc's atan2f (fdlibm restatement, exact_math.cuh), the double add / divide.
+__device__ __noinline__ uint16_t polar_cell_exact(float x, float y, const GroundParams& p) {
   const float d = fsqrt(fadd(fmul(x, x), fmul(y, y)));
   if (d <= p.r_min || d >= p.r_max || d != d) return kNoCell;
   const float binP = fdiv(fsub(d, p.r_min), p.r_span);
   const float binF = floorf(fmul(binP, (float)kNumBin));
   if (!(binF >= 0.f && binF < (float)kNumBin)) return kNoCell;
-  // fast path
-  const float t = (atan2f(y, x) + 3.14159265358979323846f) * (float)(kNumChannel / 6.28318530717958647692);
-  const float tf = floorf(t);
-  const float fr = t - tf;
-  float chF = tf;
-  if (!(fr > kChanGuard && fr < 1.0f - kChanGuard)) {
-    // exact path: glibc's atan2f, double add / divide, narrowing, float multiply, floor -- as the reference evaluates it
-    const float a = atan2f_fdlibm(y, x);
-    const double chD = __ddiv_rn(__dadd_rn((double)a, 3.14159265358979323846), 6.28318530717958647692);
-    chF = floorf(fmul((float)chD, (float)kNumChannel));
-  }
+  const float a = atan2f_fdlibm(y, x);
+  const double chD = __ddiv_rn(__dadd_rn((double)a, 3.14159265358979323846), 6.28318530717958647692);
+  const float chF = floorf(fmul((float)chD, (float)kNumChannel));
   if (!(chF >= 0.f && chF < (float)kNumChannel)) return kNoCell;
   return (uint16_t)((int)chF * kNumBin + (int)binF);
+}
+
+// The cell index must equal the exact evaluation above bit for bit, but ~170 instructions per point (two IEEE divisions,
+// an IEEE square root, an 11-term polynomial without FMA, an fp64 divide) make the kernel instruction-bound.  The exact
+// path is only needed where it can matter.  Fast path: d ~ d2 * rsqrt(d2) (MUFU, <= 2 ulp), the scaled bin coordinate
+// t = (d - rMin) * 120/(rMax - rMin), the angle from a degree-6 minimax polynomial of atan on [0,1] with octant folding
+// (|error| < 6e-7 rad), scaled to channel units.  Measured against the exact evaluation over 2e7 points (random, tiny
+// and huge |y/x|): the fast coordinates differ from the reference's by < 1.6e-5 channel widths and < 6.2e-5 bin
+// widths.  A point whose fast coordinates lie further than kChanGuard = 2e-4 / kBinGuard = 6e-4 (>= 10x those bounds)
+// from every integer has the same floor() under both evaluations, and the range filter `rMin < d < rMax` is the same
+// statement as 0 < t < 120; every other point (about 1.6 in 1000; NaN/Inf/zero-radius inputs fail the comparisons and
+// land there too) is re-evaluated exactly.  tests/test_ground_gpu.py compares cells of random, HDL-64 and
+// boundary-hugging clouds (down to 1e-7 rad / 1e-6 m from the boundaries) against the reference bit for bit.
+constexpr float kChanGuard = 2.0e-4f;
+constexpr float kBinGuard = 6.0e-4f;
+
+__device__ __forceinline__ uint16_t polar_cell(float x, float y, const GroundParams& p) {
+  const float d2 = fadd(fmul(x, x), fmul(y, y));
+  const float t = __fmaf_rn(d2, rsqrtf(d2), -p.r_min) * p.bin_scale;
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float z = __fdividef(mn, mx);
+  const float u = z * z;
+  float a = 0.00782548263669014f;
+  a = __fmaf_rn(a, u, -0.03689862787723541f);
+  a = __fmaf_rn(a, u, 0.08374155312776566f);
+  a = __fmaf_rn(a, u, -0.13480405509471893f);
+  a = __fmaf_rn(a, u, 0.19879871606826782f);
+  a = __fmaf_rn(a, u, -0.3332637548446655f);
+  a = __fmaf_rn(a, u, 0.9999993443489075f);
+  a = a * z;
+  if (ay > ax) a = 1.57079632679489661923f - a;
+  if (x < 0.f) a = 3.14159265358979323846f - a;
+  if (y < 0.f) a = -a;
+  const float sc = __fmaf_rn(a, (float)(kNumChannel / 6.28318530717958647692), (float)(kNumChannel / 2));
+  if (t < -kBinGuard || t > (float)kNumBin + kBinGuard) return kNoCell;      // certainly outside (rMin, rMax)
+  const float tf = floorf(t), cf = floorf(sc);
+  const float tr = t - tf, cr = sc - cf;
+  if (!(tr > kBinGuard && tr < 1.0f - kBinGuard && cr > kChanGuard && cr < 1.0f - kChanGuard)) return polar_cell_exact(x, y, p);
+  return (uint16_t)((int)cf * kNumBin + (int)tf);
 }
 
 // generic-stride input -> float4 (the hot path is stride 4 and never runs this)
@@ -226,47 +248,41 @@ __device__ __forceinline__ void polar_grid_slice(const GroundParams& p, const un
 // ---------------------------------------------------------------------------------------------------------------
 // grid-wide barrier of a cooperative launch (all CTAs co-resident).  The counter is never reset: launch k of a slot
 // waits for `target` = arrivals of all earlier launches + the arrivals this barrier needs (host-side bookkeeping).
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// diagnostic (scripts/ground_phases.py): %globaltimer of thread 0 at the phase boundaries, [CTA][8]; nullptr in production
-__device__ __forceinline__ void phase_mark(unsigned long long* clk, int slot) {
-  if (clk && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    clk[blockIdx.x * 8 + slot] = t;
-  }
-}
-
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
+    // release: the CTA's writes (ordered before this thread by the barrier above) become visible before the arrival
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
     unsigned spin = 0;
-    while ((int)(ld_acquire_u32(bar) - target) < 0)
+    while ((int)(ld_relaxed_u32(bar) - target) < 0)
       if (++spin > (1u << 22)) __trap();           // a lost CTA must not hang the GPU
-    __threadfence();
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire: the other CTAs' writes are visible to this CTA from here on
   }
   __syncthreads();
 }
 
 constexpr int kTilePts = kFusedThreads;             // 1024 points = 16 KB per TMA tile
 constexpr int kMaxResTiles = 7;                     // tiles of a CTA's chunk that stay in shared memory (112 KB)
+constexpr int kLookBatch = 5;                       // 5 x 32 >= 148 CTAs: all predecessors in one batch of loads
 constexpr int kMaxTiles = 16;                       // tiles per chunk (labels of a thread's points: 2 bits each in one register)
-// dynamic shared memory layout (bytes)
+// dynamic shared memory layout (bytes): fixed part, then the resident tiles, then the cell ids of every tile of the chunk.
+// The launch allocates only what its chunk length needs (a 120 k-point frame on 148 CTAs: one tile, 26 KB), so the
+// ground kernels of several frames in flight (pipeline slots, other sensor streams) can be co-resident on an SM.
 constexpr int kOffBar = 0;                                                  // [7] mbarriers
-constexpr int kOffPts = 128;                                                // [7][1024] float4
-constexpr int kOffCell = kOffPts + kMaxResTiles * kTilePts * 16;            // [16][1024] u16
-constexpr int kOffH = kOffCell + kMaxTiles * kTilePts * 2;                  // [1440] float
+constexpr int kOffH = 128;                                                  // [1440] float
 constexpr int kOffCnt = kOffH + kMaxLocCells * 4;                           // [16][32] u32 elevated | ground << 16 per warp
 constexpr int kOffWex = kOffCnt + kMaxTiles * 32 * 4;                       // [16][32] u32 exclusive inside the tile
 constexpr int kOffTtot = kOffWex + kMaxTiles * 32 * 4;                      // [16] u32 tile totals
 constexpr int kOffBase = kOffTtot + kMaxTiles * 4;                          // [2] u32 chunk base (elevated, ground)
 constexpr int kOffG = kOffBase + 16;                                        // [1440] u8
-constexpr int kFusedSmem = kOffG + ((kMaxLocCells + 15) & ~15);
+constexpr int kOffPts = (kOffG + kMaxLocCells + 127) & ~127;                // [res_tiles][1024] float4, then [tiles][1024] u16
+__host__ __device__ constexpr int fused_smem_bytes(int res_tiles, int tiles) { return kOffPts + res_tiles * kTilePts * 16 + tiles * kTilePts * 2; }
+constexpr int kFusedSmem = fused_smem_bytes(kMaxResTiles, kMaxTiles);
 
 struct FusedOut {
   uint8_t* labels;          // nullable
@@ -285,15 +301,17 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
                     unsigned bar_base, unsigned long long* desc, unsigned epoch, FusedOut out, float roi,
                     unsigned long long* __restrict__ phase_clock) {
   extern __shared__ __align__(128) unsigned char fsm[];
+  const int T_max = (chunk + kTilePts - 1) / kTilePts;                     // tiles of a full chunk (what the launch allocated for)
+  const int res_tiles = T_max < kMaxResTiles ? T_max : kMaxResTiles;
   uint64_t* s_full = reinterpret_cast<uint64_t*>(fsm + kOffBar);
-  float4* s_pts = reinterpret_cast<float4*>(fsm + kOffPts);
-  uint16_t* s_cell = reinterpret_cast<uint16_t*>(fsm + kOffCell);
   float* s_H = reinterpret_cast<float*>(fsm + kOffH);
   unsigned* s_cnt = reinterpret_cast<unsigned*>(fsm + kOffCnt);
   unsigned* s_wex = reinterpret_cast<unsigned*>(fsm + kOffWex);
   unsigned* s_ttot = reinterpret_cast<unsigned*>(fsm + kOffTtot);
   unsigned* s_base = reinterpret_cast<unsigned*>(fsm + kOffBase);
   uint8_t* s_G = fsm + kOffG;
+  float4* s_pts = reinterpret_cast<float4*>(fsm + kOffPts);
+  uint16_t* s_cell = reinterpret_cast<uint16_t*>(fsm + kOffPts + res_tiles * kTilePts * 16);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x, G = gridDim.x;
@@ -308,7 +326,7 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
   if (tid == 0) {
     for (int t = 0; t < kMaxResTiles; ++t) mbar_init(&s_full[t], 1);
     fence_mbar_init();
-    for (int t = 0; t < T && t < kMaxResTiles; ++t) {
+    for (int t = 0; t < T && t < res_tiles; ++t) {
       const uint32_t bytes = (uint32_t)min(kTilePts, cnt - t * kTilePts) * 16u;
       mbar_arrive_expect_tx(&s_full[t], bytes);
       bulk_copy_g2s(s_pts + t * kTilePts, pts + beg + t * kTilePts, bytes, &s_full[t]);
@@ -322,7 +340,7 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
     const int li = t * kTilePts + tid;
     const bool valid = li < cnt;
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t < kMaxResTiles) {
+    if (t < res_tiles) {
       mbar_wait(&s_full[t], 0u);
       if (valid) q = s_pts[li];
     } else if (valid) q = __ldg(&pts[beg + li]);
@@ -364,7 +382,7 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
     if (li < cnt) {
       const unsigned c = s_cell[li];
       if (c != kNoCell) {
-        const float z = (t < kMaxResTiles) ? s_pts[li].z : __ldg(&pts[beg + li]).z;
+        const float z = (t < res_tiles) ? s_pts[li].z : __ldg(&pts[beg + li]).z;
         const float h = __ldcg(&o_hg[c]);                       // -inf for non-ground cells -> elevated
         lab = ((double)z < __dadd_rn((double)h, p.tol)) ? 1 : 2;   // :236-246
       }
@@ -391,20 +409,24 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
     if (lane < T) { const unsigned v = s_ttot[lane]; te = v & 0xFFFFu; tg = v >> 16; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { te += __shfl_xor_sync(0xFFFFFFFFu, te, o); tg += __shfl_xor_sync(0xFFFFFFFFu, tg, o); }
+    // one word per CTA: launch tag (32) | elevated (16) | ground (16); a chunk holds at most 16384 points
     volatile unsigned long long* d = desc;
-    if (lane == 0) {
-      d[2 * cta] = ((unsigned long long)epoch << 32) | te;
-      d[2 * cta + 1] = ((unsigned long long)epoch << 32) | tg;
-    }
+    if (lane == 0) d[cta] = ((unsigned long long)epoch << 32) | ((unsigned long long)te << 16) | tg;
     unsigned se = 0, sg = 0;
-    for (int j = lane; j < cta; j += 32) {
-      unsigned long long a = d[2 * j], b = d[2 * j + 1];
-      unsigned spin = 0;
-      while ((unsigned)(a >> 32) != epoch || (unsigned)(b >> 32) != epoch) {
-        a = d[2 * j]; b = d[2 * j + 1];
-        if (++spin > (1u << 22)) __trap();
+    for (int j0 = 0; j0 < cta; j0 += 32 * kLookBatch) {      // kLookBatch independent loads in flight per lane: one L2 round trip
+      unsigned long long v[kLookBatch];
+#pragma unroll
+      for (int q = 0; q < kLookBatch; ++q) { const int j = j0 + q * 32 + lane; v[q] = (j < cta) ? d[j] : ((unsigned long long)epoch << 32); }
+#pragma unroll
+      for (int q = 0; q < kLookBatch; ++q) {
+        const int j = j0 + q * 32 + lane;
+        unsigned spin = 0;
+        while ((unsigned)(v[q] >> 32) != epoch) {
+          v[q] = d[j];
+          if (++spin > (1u << 22)) __trap();
+        }
+        se += (unsigned)(v[q] >> 16) & 0xFFFFu; sg += (unsigned)v[q] & 0xFFFFu;
       }
-      se += (unsigned)a; sg += (unsigned)b;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { se += __shfl_xor_sync(0xFFFFFFFFu, se, o); sg += __shfl_xor_sync(0xFFFFFFFFu, sg, o); }
@@ -429,7 +451,7 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
     if (li < cnt) {
       if (out.labels) out.labels[beg + li] = (uint8_t)lab;
       if (lab) {
-        const float4 q = (t < kMaxResTiles) ? s_pts[li] : __ldg(&pts[beg + li]);
+        const float4 q = (t < res_tiles) ? s_pts[li] : __ldg(&pts[beg + li]);
         if (lab == 2) {
           const unsigned pos = run_e + (wex & 0xFFFFu) + __popc(be & lt);
           out.elev[pos] = make_float4(q.x, q.y, q.z, 1.f);
@@ -550,7 +572,9 @@ int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bo
   void* args[] = {(void*)&pts, (void*)&n, (void*)&chunk, (void*)&gp, (void*)&keys, (void*)&keys_next, (void*)&s->d_minz,
                   (void*)&s->d_height, (void*)&s->d_smoothed, (void*)&s->d_hdiff, (void*)&s->d_hg, (void*)&s->d_gbar,
                   (void*)&bar_base, (void*)&s->d_gdesc, (void*)&epoch, (void*)&out, (void*)&roi, (void*)&c->d_phase_clock};
-  LMOT_CUDA(c, cudaLaunchCooperativeKernel((const void*)ground_fused_kernel, dim3(G), dim3(kFusedThreads), args, kFusedSmem, st));
+  const int tiles = (chunk + kTilePts - 1) / kTilePts;
+  const size_t smem = (size_t)fused_smem_bytes(tiles < kMaxResTiles ? tiles : kMaxResTiles, tiles > 0 ? tiles : 1);
+  LMOT_CUDA(c, cudaLaunchCooperativeKernel((const void*)ground_fused_kernel, dim3(G), dim3(kFusedThreads), args, smem, st));
   s->bar_base += 2u * (unsigned)G;
   c->last_ground_ctas = G;
   kernel_mark(c, s, st);

@@ -25,6 +25,7 @@ enum Counter {
 struct GroundParams {
   float r_min, r_max, t_hmin, t_hmax, t_hdiff, h_sensor;
   float r_span;          // r_max - r_min evaluated in float (ground_removal.cpp:71)
+  float bin_scale;       // 120 / r_span: bins per metre of the guarded fast path (ground.cu polar_cell)
   double tol;            // 0.25
   double tap[3];         // gaussKernel(3, 1.0) computed on the host with the host libm (gaus_blur.cpp:26-49)
 };
@@ -151,7 +152,7 @@ struct Ctx {
   int fused_max_ctas = 0;              // co-residency limit of the cooperative ground kernel on this device
   unsigned long long* d_phase_clock = nullptr;   // diagnostic: [CTAs][8] %globaltimer stamps of the last ground launch (lmot_debug_phase_clock)
   int last_ground_ctas = 0;
-  int pts_per_cta = 1024;              // target chunk of the fused ground kernel (LMOT_PTS_PER_CTA overrides, tuning only)
+  int pts_per_cta = 768;               // target chunk of the fused ground kernel (LMOT_PTS_PER_CTA overrides, tuning only)
   unsigned long long* d_mt_raw = nullptr;  // raw mt19937_64(0) outputs (shared, read only)
 
   // ---- detection slots

@@ -750,8 +750,18 @@ __device__ __forceinline__ double intersect_coef(double v1x, double v1y, double 
 
 // does track `a` (visible box) contain the position of track `b`?  (:670-696)
 __device__ bool overseg_cond(const TrackState& a, double px, double py) {
-  const double v1x = a.BBox[0][0], v1y = a.BBox[0][1], v2x = a.BBox[1][0], v2y = a.BBox[1][1];
-  const double v3x = a.BBox[2][0], v3y = a.BBox[2][1], v4x = a.BBox[3][0], v4y = a.BBox[3][1];
+  const float f1x = a.BBox[0][0], f1y = a.BBox[0][1], f2x = a.BBox[1][0], f2y = a.BBox[1][1];
+  const float f3x = a.BBox[2][0], f3y = a.BBox[2][1], f4x = a.BBox[3][0], f4y = a.BBox[3][1];
+  // Cheap exact-safe rejection: all three products of a triangle test are > 0 only for a point strictly inside that
+  // triangle (up to rounding of the cross products, ~1e-13 m here), hence inside the box's axis-aligned bounds.  The
+  // bounds are widened by 1 cm + 1e-9 of the coordinate, orders of magnitude beyond that rounding, so a rejected point
+  // fails the full test too; NaN coordinates are not rejected and fall through to it.  ~95 % of the (visible, track)
+  // pairs stop here instead of running ~120 fp64 operations.
+  const float mnx = fminf(fminf(f1x, f2x), fminf(f3x, f4x)), mxx = fmaxf(fmaxf(f1x, f2x), fmaxf(f3x, f4x));
+  const float mny = fminf(fminf(f1y, f2y), fminf(f3y, f4y)), mxy = fmaxf(fmaxf(f1y, f2y), fmaxf(f3y, f4y));
+  const double mg = 0.01 + 1.0e-9 * (fabs(px) + fabs(py));
+  if (px < (double)mnx - mg || px > (double)mxx + mg || py < (double)mny - mg || py > (double)mxy + mg) return false;
+  const double v1x = f1x, v1y = f1y, v2x = f2x, v2y = f2y, v3x = f3x, v3y = f3y, v4x = f4x, v4y = f4y;
   const double cp1x = (v1x + v2x + v3x) / 3, cp1y = (v1y + v2y + v3y) / 3;
   const double cp2x = (v1x + v4x + v3x) / 3, cp2y = (v1y + v4y + v3y) / 3;
   const double c1 = intersect_coef(v1x, v1y, v2x, v2y, px, py, cp1x, cp1y);
@@ -862,9 +872,19 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   if (tid == 0) s_carry = 0;
   __syncthreads();
 
-  // outputs (:995-1081)
+  // outputs (:995-1081).  The destination is pinned, device-mapped HOST memory (the stores are the D2H transfer), where
+  // every partially written 32-byte sector becomes its own PCIe write: the per-track values are staged in shared memory
+  // tile by tile and leave the SM as full 16-byte-per-lane, 512-byte-per-warp stores.
+  __shared__ __align__(16) float s_tg[1024 * 3];
+  __shared__ __align__(16) double s_vy[1024 * 2];
+  __shared__ __align__(16) int s_mg[1024];
+  __shared__ __align__(16) uint8_t s_st[1024];
+  __shared__ __align__(16) uint8_t s_vs[1024];
+  __shared__ int s_vlist[1024];
+  __shared__ __align__(16) int s_hdr[HDR_COUNT];
   for (int i0 = 0; i0 < T; i0 += 1024) {
     const int i = i0 + tid;
+    const int nt = min(1024, T - i0);
     int vis = 0;
     if (i < T) {
       TrackState& t = tracks[i];
@@ -874,27 +894,46 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
       double tyaw = t.x[0][3];
       tyaw += ego_yaw;
       tyaw = wrap_pi(tyaw);
-      o.targets[3 * i] = (float)tx; o.targets[3 * i + 1] = (float)ty; o.targets[3 * i + 2] = (float)(-1.73 / 2);
-      o.vandyaw[2 * i] = t.x[0][2]; o.vandyaw[2 * i + 1] = tyaw;
+      s_tg[3 * tid] = (float)tx; s_tg[3 * tid + 1] = (float)ty; s_tg[3 * tid + 2] = (float)(-1.73 / 2);
+      s_vy[2 * tid] = t.x[0][2]; s_vy[2 * tid + 1] = tyaw;
       vis = t.isVisBB ? 1 : 0;
-      o.is_vis[i] = (uint8_t)vis;
+      s_vs[tid] = (uint8_t)vis;
       int st = 0;
       if (t.isStatic) st = 1;
       else if (t.trackNum == 5 && t.lifetime > 8) {
         if ((t.distFromInit < 3.0) && (t.modeProb[2] > t.modeProb[0] || t.modeProb[2] > t.modeProb[1])) { st = 1; t.isStatic = 1; }
       }
-      o.is_static[i] = (uint8_t)st;
-      o.track_manage[i] = t.trackNum;
+      s_st[tid] = (uint8_t)st;
+      s_mg[tid] = t.trackNum;
     }
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, vis);
     if (lane == 0) s_warp[warp] = __popc(bal);
     __syncthreads();
     int wbase = 0, tot = 0;
     for (int w = 0; w < 32; ++w) { if (w < warp) wbase += s_warp[w]; tot += s_warp[w]; }
-    if (vis) {
-      const int pos = s_carry + wbase + __popc(bal & ((1u << lane) - 1u));
-      const TrackState& t = tracks[i];
-      for (int p = 0; p < 8; ++p) for (int c = 0; c < 3; ++c) o.vis_bb[(size_t)pos * 24 + p * 3 + c] = t.BBox[p][c];
+    if (vis) s_vlist[wbase + __popc(bal & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    // flush the tile: 16 bytes per thread, consecutive threads -> consecutive addresses (buffers have 16 bytes of slack)
+    {
+      const uint4* q;
+      uint4* d;
+      q = reinterpret_cast<const uint4*>(s_tg); d = reinterpret_cast<uint4*>(o.targets + 3 * (size_t)i0);
+      for (int e = tid; e < (nt * 12 + 15) / 16; e += 1024) d[e] = q[e];
+      q = reinterpret_cast<const uint4*>(s_vy); d = reinterpret_cast<uint4*>(o.vandyaw + 2 * (size_t)i0);
+      for (int e = tid; e < nt; e += 1024) d[e] = q[e];
+      q = reinterpret_cast<const uint4*>(s_mg); d = reinterpret_cast<uint4*>(o.track_manage + i0);
+      for (int e = tid; e < (nt * 4 + 15) / 16; e += 1024) d[e] = q[e];
+      q = reinterpret_cast<const uint4*>(s_st); d = reinterpret_cast<uint4*>(o.is_static + i0);
+      for (int e = tid; e < (nt + 15) / 16; e += 1024) d[e] = q[e];
+      q = reinterpret_cast<const uint4*>(s_vs); d = reinterpret_cast<uint4*>(o.is_vis + i0);
+      for (int e = tid; e < (nt + 15) / 16; e += 1024) d[e] = q[e];
+      // boxes of the visible tracks, in track order: 12 threads x 8 bytes per box
+      const int carry = s_carry;
+      for (int e = tid; e < tot * 12; e += 1024) {
+        const int v = e / 12, part = e - v * 12;
+        const float2* src = reinterpret_cast<const float2*>(&tracks[s_vlist[v]].BBox[0][0]) + part;
+        reinterpret_cast<float2*>(o.vis_bb + (size_t)(carry + v) * 24)[part] = *src;
+      }
     }
     __syncthreads();
     if (tid == 0) s_carry += tot;
@@ -902,10 +941,13 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   }
   if (tid == 0) {
     trk[CNT_N_TRACKS] = T; trk[CNT_N_VIS] = s_carry;
-    o.hdr[HDR_N_ELEV] = det[CNT_N_ELEV]; o.hdr[HDR_N_GROUND] = det[CNT_N_GROUND]; o.hdr[HDR_NUM_CLUSTER] = det[CNT_NUM_CLUSTER];
-    o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = s_carry; o.hdr[HDR_ERROR] = det[CNT_ERROR];
+    for (int e = 0; e < HDR_COUNT; ++e) s_hdr[e] = 0;
+    s_hdr[HDR_N_ELEV] = det[CNT_N_ELEV]; s_hdr[HDR_N_GROUND] = det[CNT_N_GROUND]; s_hdr[HDR_NUM_CLUSTER] = det[CNT_NUM_CLUSTER];
+    s_hdr[HDR_N_BOXES] = M; s_hdr[HDR_N_TRACKS] = T; s_hdr[HDR_N_VIS] = s_carry; s_hdr[HDR_ERROR] = det[CNT_ERROR];
     det[CNT_ERROR] = 0;
   }
+  __syncthreads();
+  if (tid < HDR_COUNT / 4) reinterpret_cast<uint4*>(o.hdr)[tid] = reinterpret_cast<const uint4*>(s_hdr)[tid];   // one 64-byte write
 }
 
 __global__ void fill_int_kernel(int* p, int n, int v) {
