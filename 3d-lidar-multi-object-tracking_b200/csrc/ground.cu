@@ -248,6 +248,15 @@ __device__ __forceinline__ void polar_grid_slice(const GroundParams& p, const un
 // ---------------------------------------------------------------------------------------------------------------
 // grid-wide barrier of a cooperative launch (all CTAs co-resident).  The counter is never reset: launch k of a slot
 // waits for `target` = arrivals of all earlier launches + the arrivals this barrier needs (host-side bookkeeping).
+// diagnostic (scripts/ground_phases.py): %globaltimer of thread 0 at the phase boundaries, [CTA][8]; nullptr in production
+__device__ __forceinline__ void phase_mark(unsigned long long* clk, int slot) {
+  if (clk && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    clk[blockIdx.x * 8 + slot] = t;
+  }
+}
+
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
