@@ -19,7 +19,7 @@
 //       the roots in node order.  The recursive fill labels components in the order the raster scan first meets them,
 //       i.e. by their smallest linear index == smallest node id: identical ids.
 //       The 250x250 int label grid (the reference's only carrier of labels) is updated SPARSELY: cells occupied in the
-//       previous frame are cleared, cells occupied now get their id (one coalesced 128 B store per touched word).
+//       previous frame are cleared, cells occupied now get their id (stores only where something is or was).
 #include "lmot_internal.cuh"
 #include "exact_math.cuh"
 
@@ -57,9 +57,16 @@ cart_cells_kernel(const float4* __restrict__ elev, const int* __restrict__ count
 }
 
 // ---- union-find over shared-memory nodes, root = smallest id -------------------------------------------------
+// find with path halving: every visited node is re-pointed at its grandparent.  Parents only ever move to an ancestor
+// (a smaller id), so concurrent finds / unions by other threads stay correct, and the chains that the row-by-row links
+// would otherwise build (one hop per grid row of a tall component) collapse while the unions are still being made.
 __device__ __forceinline__ int uf_find(volatile int* L, int x) {
   int p = L[x];
-  while (p != x) { x = p; p = L[x]; }
+  while (p != x) {
+    const int g = L[p];
+    if (g != p) L[x] = g;
+    x = p; p = g;
+  }
   return x;
 }
 
@@ -99,47 +106,63 @@ ccl_bitmap_kernel(unsigned* __restrict__ once, unsigned* __restrict__ twice, uns
   int* s_warp = reinterpret_cast<int*>(s_prev + kBitWords);             // [32] + total
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+  // Thread t owns the two consecutive words 2t, 2t+1 (t < 1000) in every step.
+  const int w0 = 2 * tid;
+  const bool own = tid < kBitWords / 2;
   // A: seed = cells with more than one point (component_clustering.cpp:136); the bit planes are re-armed for the next frame
-  for (int w = tid; w < kBitWords; w += kCclThreads) {
-    s_seed[w] = __ldcg(&twice[w]);
-    s_prev[w] = __ldcg(&prev_occ[w]);
-    once[w] = 0u; twice[w] = 0u;
+  if (own) {
+    const uint2 tw = __ldcg(reinterpret_cast<const uint2*>(twice) + tid);
+    const uint2 pv = __ldcg(reinterpret_cast<const uint2*>(prev_occ) + tid);
+    s_seed[w0] = tw.x; s_seed[w0 + 1] = tw.y;
+    s_prev[w0] = pv.x; s_prev[w0 + 1] = pv.y;
+    reinterpret_cast<uint2*>(once)[tid] = make_uint2(0u, 0u);
+    reinterpret_cast<uint2*>(twice)[tid] = make_uint2(0u, 0u);
   }
   __syncthreads();
   // B: occupied = seed dilated 3x3, clipped at the border (:137-214)
-  for (int w = tid; w < kBitWords; w += kCclThreads) {
-    const int x = w >> 3, k = w & 7;
-    unsigned o = hdil(s_seed + x * kRowWords, k);
-    if (x > 0) o |= hdil(s_seed + (x - 1) * kRowWords, k);
-    if (x < kNumGrid - 1) o |= hdil(s_seed + (x + 1) * kRowWords, k);
-    if (k == kRowWords - 1) o &= kLastWordMask;
-    s_occ[w] = o;
-    prev_occ[w] = o;
+  unsigned occ[2] = {0u, 0u};
+  if (own) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int w = w0 + h, x = w >> 3, k = w & 7;
+      unsigned o = hdil(s_seed + x * kRowWords, k);
+      if (x > 0) o |= hdil(s_seed + (x - 1) * kRowWords, k);
+      if (x < kNumGrid - 1) o |= hdil(s_seed + (x + 1) * kRowWords, k);
+      if (k == kRowWords - 1) o &= kLastWordMask;
+      occ[h] = o;
+      s_occ[w] = o;
+    }
+    reinterpret_cast<uint2*>(prev_occ)[tid] = make_uint2(occ[0], occ[1]);
   }
   __syncthreads();
   // C: one node per piece; a piece that continues the previous word's run starts as its child
-  for (int w = tid; w < kBitWords; w += kCclThreads) {
-    const unsigned m = s_occ[w];
-    if (!m) continue;
-    const int np = __popc(piece_starts(m));
-    const int k = w & 7;
-    for (int j = 0; j < np; ++j) s_par[w * kPiecesPerWord + j] = w * kPiecesPerWord + j;
-    if ((m & 1u) && k > 0) {
-      const unsigned l = s_occ[w - 1];
-      if (l >> 31) s_par[w * kPiecesPerWord] = (w - 1) * kPiecesPerWord + __popc(piece_starts(l)) - 1;
+  if (own) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const unsigned m = occ[h];
+      if (!m) continue;
+      const int w = w0 + h, k = w & 7;
+      const int np = __popc(piece_starts(m));
+      for (int j = 0; j < np; ++j) s_par[w * kPiecesPerWord + j] = w * kPiecesPerWord + j;
+      if ((m & 1u) && k > 0) {
+        const unsigned l = (h == 1) ? occ[0] : s_occ[w - 1];
+        if (l >> 31) s_par[w * kPiecesPerWord] = (w - 1) * kPiecesPerWord + __popc(piece_starts(l)) - 1;
+      }
     }
   }
   __syncthreads();
   // D: 8-connectivity to the row above: every piece of row x-1 that intersects [a-1, b+1]
-  {
+  if (own) {
     volatile int* Lv = s_par;
-    for (int w = tid; w < kBitWords; w += kCclThreads) {
-      const unsigned m = s_occ[w];
-      const int x = w >> 3, k = w & 7;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const unsigned m = occ[h];
+      const int w = w0 + h, x = w >> 3, k = w & 7;
       if (!m || x == 0) continue;
       const unsigned up = s_occ[w - kRowWords];
       const unsigned upl = k > 0 ? s_occ[w - kRowWords - 1] : 0u;
       const unsigned upr = k < kRowWords - 1 ? s_occ[w - kRowWords + 1] : 0u;
+      if (!(up | (upl >> 31) | (upr & 1u))) continue;
       unsigned rest = m;
       int j = 0;
       while (rest) {
@@ -164,30 +187,26 @@ ccl_bitmap_kernel(unsigned* __restrict__ once, unsigned* __restrict__ twice, uns
     }
   }
   __syncthreads();
-  // E: flatten (parents only ever move to smaller ancestors, so compressing in place is safe against concurrent finds)
-  {
-    volatile int* Lv = s_par;
-    for (int w = tid; w < kBitWords; w += kCclThreads) {
-      const unsigned m = s_occ[w];
-      if (!m) continue;
-      const int np = __popc(piece_starts(m));
-      for (int j = 0; j < np; ++j) { const int nd = w * kPiecesPerWord + j; Lv[nd] = uf_find(Lv, nd); }
-    }
-  }
-  __syncthreads();
-  // F: id = 1 + rank of the root among all roots in node (= raster) order (:247-257).  Thread t owns words 2t, 2t+1.
+  // E: flatten (parents only ever move to smaller ancestors, so compressing in place is safe against concurrent finds),
+  // F: roots of the thread's words
   int roots = 0;
   unsigned rootmask[2] = {0u, 0u};
-  if (tid < kBitWords / 2) {
+  if (own) {
+    volatile int* Lv = s_par;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int w = 2 * tid + h;
-      const unsigned m = s_occ[w];
-      const int np = m ? __popc(piece_starts(m)) : 0;
-      for (int j = 0; j < np; ++j)
-        if (s_par[w * kPiecesPerWord + j] == w * kPiecesPerWord + j) { ++roots; rootmask[h] |= 1u << j; }
+      const unsigned m = occ[h];
+      if (!m) continue;
+      const int np = __popc(piece_starts(m));
+      for (int j = 0; j < np; ++j) {
+        const int nd = (w0 + h) * kPiecesPerWord + j;
+        const int r = uf_find(Lv, nd);
+        Lv[nd] = r;
+        if (r == nd) { ++roots; rootmask[h] |= 1u << j; }
+      }
     }
   }
+  // id = 1 + rank of the root among all roots in node (= raster) order (:247-257)
   int incl = roots;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
@@ -199,7 +218,7 @@ ccl_bitmap_kernel(unsigned* __restrict__ once, unsigned* __restrict__ twice, uns
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += t; }
     s_warp[lane] = wi - v;
-    if (lane == 31) { s_warp[32] = wi; counters[CNT_NUM_CLUSTER] = wi; }
+    if (lane == 31) counters[CNT_NUM_CLUSTER] = wi;
   }
   __syncthreads();
   {
@@ -207,22 +226,32 @@ ccl_bitmap_kernel(unsigned* __restrict__ once, unsigned* __restrict__ twice, uns
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       unsigned rm = rootmask[h];
-      while (rm) { const int j = __ffs(rm) - 1; rm &= rm - 1; s_par[(2 * tid + h) * kPiecesPerWord + j] = -(++rank); }
+      while (rm) { const int j = __ffs(rm) - 1; rm &= rm - 1; s_par[(w0 + h) * kPiecesPerWord + j] = -(++rank); }
     }
   }
   __syncthreads();
-  // G: label grid, sparse: one warp per word that is occupied now or was in the previous frame, lane = cell
-  for (int w = warp; w < kBitWords; w += kCclThreads / 32) {
-    const unsigned m = s_occ[w], pv = s_prev[w];
-    if (!(m | pv)) continue;
-    if (!((m | pv) >> lane & 1u)) continue;
-    int id = 0;
-    if (m >> lane & 1u) {
-      int r = s_par[w * kPiecesPerWord + piece_of(m, lane)];
-      if (r >= 0) r = s_par[r];                                 // non-root: its root holds -(id)
-      id = -r;
+  // G: label grid, sparse: cells occupied now get their id, cells occupied only in the previous frame are cleared
+  if (own) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int w = w0 + h;
+      const unsigned m = occ[h];
+      int* o = out + (w >> 3) * kNumGrid + (w & 7) * 32;
+      unsigned gone = s_prev[w] & ~m;
+      while (gone) { const int b = __ffs(gone) - 1; gone &= gone - 1; o[b] = 0; }
+      unsigned rest = m;
+      int j = 0;
+      while (rest) {
+        const int a = __ffs(rest) - 1;
+        const unsigned t = ~(rest >> a);
+        const int len = t ? __ffs(t) - 1 : 32;
+        rest &= ~((len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << a);
+        int r = s_par[w * kPiecesPerWord + j];
+        ++j;
+        if (r >= 0) r = s_par[r];                               // non-root: its root holds -(id)
+        for (int b = a; b < a + len; ++b) o[b] = -r;
+      }
     }
-    out[(w >> 3) * kNumGrid + (w & 7) * 32 + lane] = id;
   }
 }
 

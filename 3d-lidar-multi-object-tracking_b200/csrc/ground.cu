@@ -277,6 +277,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
 
 constexpr int kTilePts = kFusedThreads;             // 1024 points = 16 KB per TMA tile
 constexpr int kMaxResTiles = 7;                     // tiles of a CTA's chunk that stay in shared memory (112 KB)
+constexpr int kDescStride = 16;                     // u64 words between two CTAs' count descriptors (128 bytes)
 constexpr int kLookBatch = 5;                       // 5 x 32 >= 148 CTAs: all predecessors in one batch of loads
 constexpr int kMaxTiles = 16;                       // tiles per chunk (labels of a thread's points: 2 bits each in one register)
 // dynamic shared memory layout (bytes): fixed part, then the resident tiles, then the cell ids of every tile of the chunk.
@@ -418,20 +419,22 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
     if (lane < T) { const unsigned v = s_ttot[lane]; te = v & 0xFFFFu; tg = v >> 16; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { te += __shfl_xor_sync(0xFFFFFFFFu, te, o); tg += __shfl_xor_sync(0xFFFFFFFFu, tg, o); }
-    // one word per CTA: launch tag (32) | elevated (16) | ground (16); a chunk holds at most 16384 points
+    // one word per CTA: launch tag (32) | elevated (16) | ground (16); a chunk holds at most 16384 points.  The words sit
+    // kDescStride apart (one 128-byte line each): with all of them in ten adjacent lines, 148 CTAs polling the same
+    // L2 slices serialised the whole exchange (measured: 4-6 us instead of one L2 round trip)
     volatile unsigned long long* d = desc;
-    if (lane == 0) d[cta] = ((unsigned long long)epoch << 32) | ((unsigned long long)te << 16) | tg;
+    if (lane == 0) d[cta * kDescStride] = ((unsigned long long)epoch << 32) | ((unsigned long long)te << 16) | tg;
     unsigned se = 0, sg = 0;
     for (int j0 = 0; j0 < cta; j0 += 32 * kLookBatch) {      // kLookBatch independent loads in flight per lane: one L2 round trip
       unsigned long long v[kLookBatch];
 #pragma unroll
-      for (int q = 0; q < kLookBatch; ++q) { const int j = j0 + q * 32 + lane; v[q] = (j < cta) ? d[j] : ((unsigned long long)epoch << 32); }
+      for (int q = 0; q < kLookBatch; ++q) { const int j = j0 + q * 32 + lane; v[q] = (j < cta) ? d[j * kDescStride] : ((unsigned long long)epoch << 32); }
 #pragma unroll
       for (int q = 0; q < kLookBatch; ++q) {
         const int j = j0 + q * 32 + lane;
         unsigned spin = 0;
         while ((unsigned)(v[q] >> 32) != epoch) {
-          v[q] = d[j];
+          v[q] = d[j * kDescStride];
           if (++spin > (1u << 22)) __trap();
         }
         se += (unsigned)(v[q] >> 16) & 0xFFFFu; sg += (unsigned)v[q] & 0xFFFFu;
@@ -519,8 +522,8 @@ int ground_alloc(Ctx* c, Slot* s) {
   LMOT_CUDA(c, cudaMalloc(&s->d_labels, np));
   LMOT_CUDA(c, cudaMalloc(&s->d_elev, np * sizeof(float4)));
   LMOT_CUDA(c, cudaMalloc(&s->d_ground, np * sizeof(float4)));
-  LMOT_CUDA(c, cudaMalloc(&s->d_gdesc, (size_t)2 * c->fused_max_ctas * sizeof(unsigned long long)));
-  LMOT_CUDA(c, cudaMemsetAsync(s->d_gdesc, 0, (size_t)2 * c->fused_max_ctas * sizeof(unsigned long long), st));
+  LMOT_CUDA(c, cudaMalloc(&s->d_gdesc, (size_t)kDescStride * c->fused_max_ctas * sizeof(unsigned long long)));
+  LMOT_CUDA(c, cudaMemsetAsync(s->d_gdesc, 0, (size_t)kDescStride * c->fused_max_ctas * sizeof(unsigned long long), st));
   LMOT_CUDA(c, cudaMalloc(&s->d_gbar, sizeof(unsigned)));
   LMOT_CUDA(c, cudaMemsetAsync(s->d_gbar, 0, sizeof(unsigned), st));
   s->bar_base = 0; s->epoch = 0;
