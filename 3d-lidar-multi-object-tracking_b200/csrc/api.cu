@@ -87,6 +87,7 @@ int check_device_error(Ctx* c, Slot* s, cudaStream_t st) {
 int drain(Ctx* c) {
   for (int i = 0; i < c->n_slots; ++i) LMOT_CUDA(c, cudaStreamSynchronize(c->slots[i].stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->trk_stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->pub_stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
   for (int i = 0; i < c->n_results; ++i) c->results[i].in_flight = false;
   c->n_in_flight = 0;
@@ -133,16 +134,21 @@ int submit(Ctx* c, Slot* s, Result* r, const float4* d_pts, int n, bool with_tra
   if (c->timing) cudaEventRecord(r->ev[2], s->stream);
   if ((rc = boxfit_launch(c, s, s->stream, n))) return rc;
   if (c->timing) cudaEventRecord(r->ev[3], s->stream);
-  if (!with_tracker)      // no spawn_output_kernel will snapshot the counters: copy them before the slot is reused
-    LMOT_CUDA(c, cudaMemcpyAsync(r->h_det, s->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   LMOT_CUDA(c, cudaEventRecord(s->ev_det_done, s->stream));
   if (with_tracker) {
     LMOT_CUDA(c, cudaStreamWaitEvent(c->trk_stream, s->ev_det_done, 0));
     if ((rc = tracker_launch(c, s, c->trk_stream, s->d_boxes, s->d_counters, ts, v, yaw))) return rc;
     if (c->timing) cudaEventRecord(r->ev[4], c->trk_stream);
-    LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, c->trk_stream));
-    LMOT_CUDA(c, cudaEventRecord(r->ev_done, c->trk_stream));
+    LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, c->trk_stream));      // the slot is free: its boxes / counters were consumed
+    LMOT_CUDA(c, cudaEventRecord(r->ev_tc, c->trk_stream));
+    // device block -> pinned host block, off the tracker's sequential chain
+    LMOT_CUDA(c, cudaStreamWaitEvent(c->pub_stream, r->ev_tc, 0));
+    if ((rc = tracker_publish(c, r, c->pub_stream))) return rc;
+    LMOT_CUDA(c, cudaEventRecord(r->ev_done, c->pub_stream));
   } else {
+    // no spawn_output_kernel will snapshot the counters / boxes: copy them before the slot is reused
+    LMOT_CUDA(c, cudaMemcpyAsync(r->h_det, s->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    if ((rc = boxes_publish(c, s, r, s->stream))) return rc;
     LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, s->stream));
     LMOT_CUDA(c, cudaEventRecord(r->ev_done, s->stream));
   }
@@ -200,18 +206,32 @@ int collect_result(Ctx* c, Result* r, lmot_frame_out* out) {
 int result_create(Ctx* c, Result* r) {
   const int TC = c->prm.max_tracks, MB = c->prm.max_boxes;
   const unsigned fl = cudaHostAllocMapped;
-  LMOT_CUDA(c, cudaHostAlloc(&r->h_hdr, HDR_COUNT * sizeof(int), fl));
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_hdr, HDR_COUNT * sizeof(int) + 16, fl));
   memset(r->h_hdr, 0, HDR_COUNT * sizeof(int));
   LMOT_CUDA(c, cudaHostAlloc(&r->h_det, CNT_COUNT * sizeof(int), fl));
   memset(r->h_det, 0, CNT_COUNT * sizeof(int));
-  LMOT_CUDA(c, cudaHostAlloc(&r->h_boxes, (size_t)MB * 24 * sizeof(float), fl));
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_boxes, (size_t)MB * 24 * sizeof(float) + 16, fl));
   // + 16 bytes: spawn_output_kernel writes whole 16-byte words
   LMOT_CUDA(c, cudaHostAlloc(&r->h_targets, (size_t)TC * 3 * sizeof(float) + 16, fl));
   LMOT_CUDA(c, cudaHostAlloc(&r->h_vandyaw, (size_t)TC * 2 * sizeof(double) + 16, fl));
   LMOT_CUDA(c, cudaHostAlloc(&r->h_manage, (size_t)TC * sizeof(int) + 16, fl));
   LMOT_CUDA(c, cudaHostAlloc(&r->h_static, (size_t)TC + 16, fl));
   LMOT_CUDA(c, cudaHostAlloc(&r->h_vis, (size_t)TC + 16, fl));
-  LMOT_CUDA(c, cudaHostAlloc(&r->h_visbb, (size_t)TC * 24 * sizeof(float), fl));
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_visbb, (size_t)TC * 24 * sizeof(float) + 16, fl));
+  {   // device copy of the block, one allocation, every array 256-byte aligned with 16 bytes of slack
+    auto al = [](size_t b) { return (b + 16 + 255) & ~(size_t)255; };
+    const size_t sz[8] = {al(HDR_COUNT * sizeof(int)), al((size_t)MB * 96), al((size_t)TC * 12), al((size_t)TC * 16), al((size_t)TC * 4),
+                          al((size_t)TC), al((size_t)TC), al((size_t)TC * 96)};
+    size_t tot = 0;
+    for (size_t b : sz) tot += b;
+    LMOT_CUDA(c, cudaMalloc(&r->d_block, tot));
+    LMOT_CUDA(c, cudaMemsetAsync(r->d_block, 0, tot, c->stream));
+    unsigned char* p = r->d_block;
+    r->d_hdr = (int*)p; p += sz[0]; r->d_boxes = (float*)p; p += sz[1]; r->d_targets = (float*)p; p += sz[2];
+    r->d_vandyaw = (double*)p; p += sz[3]; r->d_manage = (int*)p; p += sz[4]; r->d_static = p; p += sz[5]; r->d_vis = p; p += sz[6];
+    r->d_visbb = (float*)p;
+  }
+  LMOT_CUDA(c, cudaEventCreateWithFlags(&r->ev_tc, cudaEventDisableTiming));
   LMOT_CUDA(c, cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming));
   LMOT_CUDA(c, cudaEventRecord(r->ev_done, c->stream));
   for (int i = 0; i < 5; ++i) LMOT_CUDA(c, cudaEventCreate(&r->ev[i]));
@@ -229,6 +249,8 @@ void result_destroy(Result* r) {
   if (r->h_static) cudaFreeHost(r->h_static);
   if (r->h_vis) cudaFreeHost(r->h_vis);
   if (r->h_visbb) cudaFreeHost(r->h_visbb);
+  if (r->d_block) cudaFree(r->d_block);
+  if (r->ev_tc) cudaEventDestroy(r->ev_tc);
   if (r->ev_done) cudaEventDestroy(r->ev_done);
   for (int i = 0; i < 5; ++i) if (r->ev[i]) cudaEventDestroy(r->ev[i]);
   for (int i = 0; i < kMaxKernelEvents; ++i) if (r->kev[i]) cudaEventDestroy(r->kev[i]);
@@ -330,7 +352,8 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithPriority(&c->trk_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete h; return LMOT_ERR_CUDA; }
+      cudaStreamCreateWithPriority(&c->trk_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->pub_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return LMOT_ERR_CUDA; }
   c->stream = c->own_stream;
   rc = boxfit_alloc_shared(c);
   for (int i = 0; i < c->n_results && rc == LMOT_OK; ++i) rc = result_create(c, &c->results[i]);
@@ -354,6 +377,7 @@ void lmot_destroy(lmot_ctx* ctx) {
   cudaFree(c->d_phase_clock);
   cudaFree(c->d_mt_raw);
   if (c->trk_stream) cudaStreamDestroy(c->trk_stream);
+  if (c->pub_stream) cudaStreamDestroy(c->pub_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete ctx;
 }
@@ -369,6 +393,7 @@ int lmot_sync(lmot_ctx* ctx) {
   Ctx* c = &ctx->c;
   for (int i = 0; i < c->n_slots; ++i) LMOT_CUDA(c, cudaStreamSynchronize(c->slots[i].stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->trk_stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->pub_stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
   return LMOT_OK;
 }
@@ -381,6 +406,7 @@ int lmot_flush(lmot_ctx* ctx) {
     LMOT_CUDA(c, cudaStreamWaitEvent(c->stream, c->slots[i].ev_det_done, 0));
     LMOT_CUDA(c, cudaStreamWaitEvent(c->stream, c->slots[i].ev_trk_done, 0));
   }
+  if (c->last_res && c->last_res->ev_done) LMOT_CUDA(c, cudaStreamWaitEvent(c->stream, c->last_res->ev_done, 0));   // publication is in order
   return LMOT_OK;
 }
 
@@ -502,6 +528,7 @@ int lmot_track_step(lmot_ctx* ctx, const float* boxes, int m, double timestamp_u
   if (m > 0) LMOT_CUDA(c, cudaMemcpyAsync(s->d_boxes, boxes, (size_t)m * 24 * sizeof(float), cudaMemcpyHostToDevice, st));
   if ((rc = set_counter(c, s, st, CNT_N_BOXES, m))) return rc;
   if ((rc = tracker_launch(c, s, st, s->d_boxes, s->d_counters, timestamp_us, v_gps, yaw_gps))) return rc;
+  if ((rc = tracker_publish(c, s->res, st))) return rc;
   LMOT_CUDA(c, cudaStreamSynchronize(st));
   const int err = s->res->h_hdr[HDR_ERROR];
   rc = copy_track_outputs(s->res, out);
@@ -614,6 +641,7 @@ int lmot_tracker_reset(lmot_ctx* ctx) {
   int rc = drain(c);
   if (rc) return rc;
   c->th = TrackerHost();
+  c->act_valid = false;
   LMOT_CUDA(c, cudaMemsetAsync(c->d_trk_counters, 0, CNT_COUNT * sizeof(int), c->stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
   return LMOT_OK;
@@ -649,6 +677,7 @@ int lmot_tracker_set_num_tracks(lmot_ctx* ctx, int n) {
   int rc = drain(c);
   if (rc) return rc;
   c->h_trk_counters[CNT_N_TRACKS] = n;
+  c->act_valid = false;
   LMOT_CUDA(c, cudaMemcpyAsync(c->d_trk_counters + CNT_N_TRACKS, c->h_trk_counters + CNT_N_TRACKS, sizeof(int), cudaMemcpyHostToDevice, c->stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
   return LMOT_OK;
@@ -719,6 +748,7 @@ int lmot_tracker_load(lmot_ctx* ctx, const double* dumps, int n, int init, doubl
   LMOT_CUDA(c, cudaMemsetAsync(c->d_trk_counters, 0, CNT_COUNT * sizeof(int), c->stream));
   LMOT_CUDA(c, cudaMemcpyAsync(c->d_trk_counters + CNT_N_TRACKS, c->h_trk_counters + CNT_N_TRACKS, sizeof(int), cudaMemcpyHostToDevice, c->stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->act_valid = false;
   c->th = TrackerHost();
   c->th.init = init != 0; c->th.timestamp = timestamp_us; c->th.egoVelo = ego_velo; c->th.egoYaw = ego_yaw;
   c->th.egoPreYaw = ego_pre_yaw; c->th.egoPoint[2] = ego_point_yaw;

@@ -212,7 +212,7 @@ box_fit_kernel(const float4* __restrict__ sorted_pts, const int* __restrict__ se
                const int* __restrict__ seg_size, int* __restrict__ counters, BoxParams P,
                const unsigned long long* __restrict__ mt_raw, int n_raw, int max_clusters, int max_boxes,
                float* __restrict__ cl_box, float* __restrict__ cl_marker, uint8_t* __restrict__ cl_ok,
-               float* __restrict__ boxes, float* __restrict__ markers, float* __restrict__ h_boxes, int* __restrict__ done) {
+               float* __restrict__ boxes, float* __restrict__ markers, int* __restrict__ done) {
   __shared__ int s_lo[kCols], s_hi[kCols];
   __shared__ short s_hx[kHullCap], s_hy[kHullCap];
   __shared__ short s_cx[kCols], s_clo[kCols], s_chi[kCols];     // occupied pixel columns, compacted
@@ -512,13 +512,12 @@ box_fit_kernel(const float4* __restrict__ sorted_pts, const int* __restrict__ se
     const int pos = carry + wbase + __popc(bal & ((1u << (tid & 31)) - 1u));
     if (f && pos < max_boxes) s_src[pos - carry] = k;
     __syncthreads();
-    // cooperative copy: consecutive threads move consecutive floats, so the stores into the device list AND into the
-    // pinned host block (h_boxes is mapped host memory: these stores are the D2H transfer) are full 128-byte lines
+    // cooperative copy: consecutive threads move consecutive floats
     const int nacc = min(tot, max_boxes - carry);
     for (int e = tid; e < nacc * 24; e += kFitThreads) {
       const int j = e / 24, w = e - j * 24;
       const float v = __ldcg(&cl_box[(size_t)s_src[j] * 24 + w]);
-      boxes[(size_t)(carry + j) * 24 + w] = v; h_boxes[(size_t)(carry + j) * 24 + w] = v;
+      boxes[(size_t)(carry + j) * 24 + w] = v;
     }
     for (int e = tid; e < nacc * 6; e += kFitThreads) {
       const int j = e / 6, w = e - j * 6;
@@ -597,7 +596,7 @@ int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper) {
   P.t_ratio_max = p.t_ratio_max; P.min_len_ratio = p.min_len_ratio; P.t_pt_per_m3 = p.t_pt_per_m3;
   box_fit_kernel<<<c->fit_ctas, kFitThreads, 0, st>>>(s->d_sorted_pts, s->d_seg_start, s->d_seg_size, s->d_counters, P,
                                                       c->d_mt_raw, c->n_mt_raw, c->prm.max_clusters, c->prm.max_boxes, s->d_cl_box,
-                                                      s->d_cl_marker, s->d_cl_ok, s->d_boxes, s->d_markers, s->res->h_boxes, s->d_done);
+                                                      s->d_cl_marker, s->d_cl_ok, s->d_boxes, s->d_markers, s->d_done);
   kernel_mark(c, s, st);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;

@@ -19,7 +19,8 @@ constexpr int kScanTile = 1024;                      // points per tile of the s
 // device-side counters of one frame (one int each; written by kernels, read by later kernels and by fetch)
 enum Counter {
   CNT_N_ELEV = 0, CNT_N_GROUND, CNT_NUM_CLUSTER, CNT_N_BOXES, CNT_N_CLUSTERED, CNT_ERROR, CNT_N_TRACKS, CNT_N_VIS,
-  CNT_TICKET_A, CNT_TICKET_B, CNT_COUNT = 16
+  CNT_N_ACT,        // tracks the next frame has to visit (live, or dead with a stale isVisBB_ flag): length of d_act_list
+  CNT_COUNT = 16
 };
 
 struct GroundParams {
@@ -67,6 +68,12 @@ struct Result {
   float* h_boxes = nullptr;            // [max_boxes][24]
   float* h_targets = nullptr; double* h_vandyaw = nullptr; int* h_manage = nullptr;
   uint8_t* h_static = nullptr; uint8_t* h_vis = nullptr; float* h_visbb = nullptr;
+  // device copy of the same block: written by spawn_output_kernel on the tracker stream, moved to the host block by
+  // publish_kernel on the publish stream (off the tracker's sequential chain)
+  unsigned char* d_block = nullptr;
+  int* d_hdr = nullptr; float* d_boxes = nullptr; float* d_targets = nullptr; double* d_vandyaw = nullptr; int* d_manage = nullptr;
+  uint8_t* d_static = nullptr; uint8_t* d_vis = nullptr; float* d_visbb = nullptr;
+  cudaEvent_t ev_tc = nullptr;         // recorded on the tracker stream after spawn_output_kernel
   cudaEvent_t ev_done = nullptr;
   bool in_flight = false;              // submitted and not yet collected / dropped
   bool has_tracks = false;             // went through the tracker (frame) or not (detect only)
@@ -170,6 +177,9 @@ struct Ctx {
   // ---- tracker
   TrackerHost th;
   cudaStream_t trk_stream = nullptr;
+  cudaStream_t pub_stream = nullptr;   // device -> host publication of finished frames
+  int* d_act_list = nullptr;           // [max_tracks] tracks to visit next frame (built by spawn_output_kernel)
+  bool act_valid = false;              // false after the table was written from the host: rebuilt before the next step
   int trk_ctas = 592, gate_words = 0;
   TrackState* d_tracks = nullptr;      // [max_tracks] append-only table; dead tracks keep their slot
   int* d_trk_counters = nullptr;       // [CNT_COUNT] CNT_N_TRACKS / CNT_N_VIS / CNT_ERROR of the track table
@@ -241,5 +251,7 @@ void tracker_free(Ctx* c);
 // boxes: device float[M][8][3] with M in det_counters[CNT_N_BOXES]; results into the slot's pinned host block
 int tracker_launch(Ctx* c, Slot* s, cudaStream_t st, const float* d_boxes, const int* det_counters, double timestamp, double v_gps,
                    double yaw_gps);
+int tracker_publish(Ctx* c, Result* r, cudaStream_t st);            // device block of r -> pinned host block
+int boxes_publish(Ctx* c, Slot* s, Result* r, cudaStream_t st);     // detection-only: slot box list -> pinned host block
 
 }  // namespace lmot

@@ -162,16 +162,20 @@ __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(
 __global__ void __launch_bounds__(kTAThreads)
 imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, const int* __restrict__ det, const float* __restrict__ boxes,
                         double dt, unsigned* __restrict__ gate, unsigned* __restrict__ setter, int* __restrict__ first_setter,
-                        uint8_t* __restrict__ skip, int words) {
+                        uint8_t* __restrict__ skip, int words, const int* __restrict__ act_list) {
   __shared__ TAShared sh;
   const int tid = threadIdx.x, lane = tid & 31, model = tid >> 5;
-  const int T = trk[CNT_N_TRACKS];
+  const int n_act = trk[CNT_N_ACT];
   const int M = det[CNT_N_BOXES];
   const double kStdA = (model == 2) ? 3.0 : 2.0;       // std_a_{cv,ctrv,rm}_ ukf.cpp:68-70 (= std_*_yawdd_ :71-73)
   const double lambda_aug = 3 - 7;
   const double w0 = lambda_aug / (lambda_aug + 7), wi = 0.5 / (7 + lambda_aug);
 
-  for (int it = blockIdx.x; it < T; it += gridDim.x) {
+  // Only the ACTIVE tracks are visited: live ones, plus dead ones whose isVisBB_ flag is still set from the frame they died
+  // in (the reference clears it for every track at :814).  The table is append-only like targets_ -- dead tracks keep their
+  // slot forever -- so walking all of it would put several tracks on one CTA once it outgrows the grid.
+  for (int q = blockIdx.x; q < n_act; q += gridDim.x) {
+    const int it = act_list[q];
     TrackState& t = tracks[it];
     __syncthreads();
     if (tid == 0) {
@@ -505,16 +509,17 @@ __device__ void update_bb(TrackState& t) {
 __global__ void __launch_bounds__(kTBWarps * 32)
 imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, const int* __restrict__ det, const float* __restrict__ boxes,
                   const unsigned* __restrict__ gate, const int* __restrict__ first_setter, const uint8_t* __restrict__ skip,
-                  int words) {
+                  int words, const int* __restrict__ act_list) {
   extern __shared__ unsigned short s_list_all[];          // per warp: indices of the gated boxes, in box order
   __shared__ TrackState s_trk[kTBWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int T = trk[CNT_N_TRACKS];
+  const int n_act = trk[CNT_N_ACT];
   const int M = det[CNT_N_BOXES];
   unsigned short* s_list = s_list_all + (size_t)warp * words * 32;
   const int nchunk = (M + 31) >> 5;
 
-  for (int it = blockIdx.x * kTBWarps + warp; it < T; it += gridDim.x * kTBWarps) {
+  for (int q = blockIdx.x * kTBWarps + warp; q < n_act; q += gridDim.x * kTBWarps) {
+    const int it = act_list[q];
     if (skip[it]) continue;
     // stage the whole track (1.6 KB) in shared memory with coalesced 8-byte loads: the update below touches almost
     // every field several times, and every one of those touches would otherwise be its own trip to L2 / HBM
@@ -778,14 +783,18 @@ __device__ bool overseg_cond(const TrackState& a, double px, double py) {
 }
 
 // ------------------------------------------------------------------------------------------------ TC2
-struct OutPtrs {   // pinned, device-mapped host memory of the slot: the kernel's stores ARE the D2H transfer
-  float* targets; double* vandyaw; int* track_manage; uint8_t* is_static; uint8_t* is_vis; float* vis_bb; int* hdr;
+// One frame's results.  spawn_output_kernel fills the DEVICE copy (the tracker is the sequential chain of the pipeline:
+// nothing slow may sit on it); publish_kernel, on its own stream and off that chain, moves it into the pinned,
+// device-mapped host block -- its stores are the D2H transfer, sized by the counts only the device knows.
+struct OutPtrs {
+  float* targets; double* vandyaw; int* track_manage; uint8_t* is_static; uint8_t* is_vis; float* vis_bb; int* hdr; float* boxes;
 };
 
 __global__ void __launch_bounds__(1024)
 spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int* __restrict__ det, const float* __restrict__ boxes,
                     int* __restrict__ first_setter, int* __restrict__ imax_arr, int* __restrict__ live_list, int* __restrict__ vis_list,
-                    uint8_t* __restrict__ has5_arr, int first_frame, int compat_first, double ego_yaw, int max_tracks, OutPtrs o) {
+                    uint8_t* __restrict__ has5_arr, int first_frame, int compat_first, double ego_yaw, int max_tracks, OutPtrs o,
+                    int* __restrict__ act_list) {
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -804,14 +813,16 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
         o.vandyaw[0] = 0; o.vandyaw[1] = 0; o.is_static[0] = 0; o.is_vis[0] = 0; o.track_manage[0] = 1;
         T = 1;
       }
-      trk[CNT_N_TRACKS] = T; trk[CNT_N_VIS] = 0;
+      trk[CNT_N_TRACKS] = T; trk[CNT_N_VIS] = 0; trk[CNT_N_ACT] = T; act_list[0] = 0;
       o.hdr[HDR_N_ELEV] = det[CNT_N_ELEV]; o.hdr[HDR_N_GROUND] = det[CNT_N_GROUND]; o.hdr[HDR_NUM_CLUSTER] = det[CNT_NUM_CLUSTER];
       o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = 0; o.hdr[HDR_ERROR] = det[CNT_ERROR];
       det[CNT_ERROR] = 0;
     }
     for (int b = tid; b < M; b += 1024) first_setter[b] = INT_MAX;
+    for (int e = tid; e < M * 24; e += 1024) o.boxes[e] = boxes[e];
     return;
   }
+  for (int e = tid; e < M * 24; e += 1024) o.boxes[e] = boxes[e];     // the frame's box list travels with its results
 
   // ---- mergeOverSegmentation (:666-700), folded into this kernel.  The sequential double loop writes trackNum[i]=5,
   // trackNum[j]=0 for every hit (i,j) with i visible; the value that survives at index k is the write with the largest
@@ -876,20 +887,14 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   if (tid == 0) s_carry = 0;
   __syncthreads();
 
-  // outputs (:995-1081).  The destination is pinned, device-mapped HOST memory (the stores are the D2H transfer), where
-  // every partially written 32-byte sector becomes its own PCIe write: the per-track values are staged in shared memory
-  // tile by tile and leave the SM as full 16-byte-per-lane, 512-byte-per-warp stores.
-  __shared__ __align__(16) float s_tg[1024 * 3];
-  __shared__ __align__(16) double s_vy[1024 * 2];
-  __shared__ __align__(16) int s_mg[1024];
-  __shared__ __align__(16) uint8_t s_st[1024];
-  __shared__ __align__(16) uint8_t s_vs[1024];
-  __shared__ int s_vlist[1024];
-  __shared__ __align__(16) int s_hdr[HDR_COUNT];
+  // outputs (:995-1081), one coalesced pass over the table; the list of tracks the next frame has to visit falls out of it
+  __shared__ int s_warp2[32];
+  __shared__ int s_carry2;
+  if (tid == 0) s_carry2 = 0;
+  __syncthreads();
   for (int i0 = 0; i0 < T; i0 += 1024) {
     const int i = i0 + tid;
-    const int nt = min(1024, T - i0);
-    int vis = 0;
+    int vis = 0, act = 0;
     if (i < T) {
       TrackState& t = tracks[i];
       const double tx = t.x[0][0], ty = t.x[0][1];
@@ -898,60 +903,77 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
       double tyaw = t.x[0][3];
       tyaw += ego_yaw;
       tyaw = wrap_pi(tyaw);
-      s_tg[3 * tid] = (float)tx; s_tg[3 * tid + 1] = (float)ty; s_tg[3 * tid + 2] = (float)(-1.73 / 2);
-      s_vy[2 * tid] = t.x[0][2]; s_vy[2 * tid + 1] = tyaw;
+      o.targets[3 * i] = (float)tx; o.targets[3 * i + 1] = (float)ty; o.targets[3 * i + 2] = (float)(-1.73 / 2);
+      o.vandyaw[2 * i] = t.x[0][2]; o.vandyaw[2 * i + 1] = tyaw;
       vis = t.isVisBB ? 1 : 0;
-      s_vs[tid] = (uint8_t)vis;
+      o.is_vis[i] = (uint8_t)vis;
       int st = 0;
       if (t.isStatic) st = 1;
       else if (t.trackNum == 5 && t.lifetime > 8) {
         if ((t.distFromInit < 3.0) && (t.modeProb[2] > t.modeProb[0] || t.modeProb[2] > t.modeProb[1])) { st = 1; t.isStatic = 1; }
       }
-      s_st[tid] = (uint8_t)st;
-      s_mg[tid] = t.trackNum;
+      o.is_static[i] = (uint8_t)st;
+      o.track_manage[i] = t.trackNum;
+      act = (t.trackNum != 0 || vis) ? 1 : 0;
     }
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, vis);
-    if (lane == 0) s_warp[warp] = __popc(bal);
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, vis), bala = __ballot_sync(0xFFFFFFFFu, act);
+    if (lane == 0) { s_warp[warp] = __popc(bal); s_warp2[warp] = __popc(bala); }
     __syncthreads();
-    int wbase = 0, tot = 0;
-    for (int w = 0; w < 32; ++w) { if (w < warp) wbase += s_warp[w]; tot += s_warp[w]; }
-    if (vis) s_vlist[wbase + __popc(bal & ((1u << lane) - 1u))] = i;
-    __syncthreads();
-    // flush the tile: 16 bytes per thread, consecutive threads -> consecutive addresses (buffers have 16 bytes of slack)
-    {
-      const uint4* q;
-      uint4* d;
-      q = reinterpret_cast<const uint4*>(s_tg); d = reinterpret_cast<uint4*>(o.targets + 3 * (size_t)i0);
-      for (int e = tid; e < (nt * 12 + 15) / 16; e += 1024) d[e] = q[e];
-      q = reinterpret_cast<const uint4*>(s_vy); d = reinterpret_cast<uint4*>(o.vandyaw + 2 * (size_t)i0);
-      for (int e = tid; e < nt; e += 1024) d[e] = q[e];
-      q = reinterpret_cast<const uint4*>(s_mg); d = reinterpret_cast<uint4*>(o.track_manage + i0);
-      for (int e = tid; e < (nt * 4 + 15) / 16; e += 1024) d[e] = q[e];
-      q = reinterpret_cast<const uint4*>(s_st); d = reinterpret_cast<uint4*>(o.is_static + i0);
-      for (int e = tid; e < (nt + 15) / 16; e += 1024) d[e] = q[e];
-      q = reinterpret_cast<const uint4*>(s_vs); d = reinterpret_cast<uint4*>(o.is_vis + i0);
-      for (int e = tid; e < (nt + 15) / 16; e += 1024) d[e] = q[e];
-      // boxes of the visible tracks, in track order: 12 threads x 8 bytes per box
-      const int carry = s_carry;
-      for (int e = tid; e < tot * 12; e += 1024) {
-        const int v = e / 12, part = e - v * 12;
-        const float2* src = reinterpret_cast<const float2*>(&tracks[s_vlist[v]].BBox[0][0]) + part;
-        reinterpret_cast<float2*>(o.vis_bb + (size_t)(carry + v) * 24)[part] = *src;
-      }
+    int wbase = 0, tot = 0, wbase2 = 0, tot2 = 0;
+    for (int w = 0; w < 32; ++w) { if (w < warp) { wbase += s_warp[w]; wbase2 += s_warp2[w]; } tot += s_warp[w]; tot2 += s_warp2[w]; }
+    if (act) act_list[s_carry2 + wbase2 + __popc(bala & ((1u << lane) - 1u))] = i;
+    if (vis) {      // boxes of the visible tracks, in track order
+      const int pos = s_carry + wbase + __popc(bal & ((1u << lane) - 1u));
+      const float2* src = reinterpret_cast<const float2*>(&tracks[i].BBox[0][0]);
+      float2* dst = reinterpret_cast<float2*>(o.vis_bb + (size_t)pos * 24);
+#pragma unroll
+      for (int e = 0; e < 12; ++e) dst[e] = src[e];
     }
     __syncthreads();
-    if (tid == 0) s_carry += tot;
+    if (tid == 0) { s_carry += tot; s_carry2 += tot2; }
     __syncthreads();
   }
   if (tid == 0) {
-    trk[CNT_N_TRACKS] = T; trk[CNT_N_VIS] = s_carry;
-    for (int e = 0; e < HDR_COUNT; ++e) s_hdr[e] = 0;
-    s_hdr[HDR_N_ELEV] = det[CNT_N_ELEV]; s_hdr[HDR_N_GROUND] = det[CNT_N_GROUND]; s_hdr[HDR_NUM_CLUSTER] = det[CNT_NUM_CLUSTER];
-    s_hdr[HDR_N_BOXES] = M; s_hdr[HDR_N_TRACKS] = T; s_hdr[HDR_N_VIS] = s_carry; s_hdr[HDR_ERROR] = det[CNT_ERROR];
+    trk[CNT_N_TRACKS] = T; trk[CNT_N_VIS] = s_carry; trk[CNT_N_ACT] = s_carry2;
+    o.hdr[HDR_N_ELEV] = det[CNT_N_ELEV]; o.hdr[HDR_N_GROUND] = det[CNT_N_GROUND]; o.hdr[HDR_NUM_CLUSTER] = det[CNT_NUM_CLUSTER];
+    o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = s_carry; o.hdr[HDR_ERROR] = det[CNT_ERROR];
     det[CNT_ERROR] = 0;
   }
-  __syncthreads();
-  if (tid < HDR_COUNT / 4) reinterpret_cast<uint4*>(o.hdr)[tid] = reinterpret_cast<const uint4*>(s_hdr)[tid];   // one 64-byte write
+}
+
+// device copy of a frame's results -> pinned, device-mapped host block.  16 bytes per thread, consecutive threads ->
+// consecutive addresses: every store instruction of a warp is four full 128-byte lines on the PCIe side.
+__device__ __forceinline__ void copy16(void* dst, const void* src, size_t bytes, int tid, int nthreads) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  const size_t n16 = (bytes + 15) / 16;                 // the blocks have 16 bytes of slack
+  for (size_t e = tid; e < n16; e += nthreads) d[e] = s[e];
+}
+
+__global__ void __launch_bounds__(1024)
+publish_kernel(OutPtrs d, OutPtrs h) {
+  const int tid = threadIdx.x;
+  const int T = d.hdr[HDR_N_TRACKS], V = d.hdr[HDR_N_VIS], M = d.hdr[HDR_N_BOXES];
+  copy16(h.boxes, d.boxes, (size_t)M * 96, tid, 1024);
+  copy16(h.targets, d.targets, (size_t)T * 12, tid, 1024);
+  copy16(h.vandyaw, d.vandyaw, (size_t)T * 16, tid, 1024);
+  copy16(h.track_manage, d.track_manage, (size_t)T * 4, tid, 1024);
+  copy16(h.is_static, d.is_static, (size_t)T, tid, 1024);
+  copy16(h.is_vis, d.is_vis, (size_t)T, tid, 1024);
+  copy16(h.vis_bb, d.vis_bb, (size_t)V * 96, tid, 1024);
+  copy16(h.hdr, d.hdr, HDR_COUNT * sizeof(int), tid, 1024);
+}
+
+// detection-only submissions: the box list of the slot -> the result's host block
+__global__ void __launch_bounds__(256)
+publish_boxes_kernel(const float* __restrict__ d_boxes, const int* __restrict__ det, float* __restrict__ h_boxes) {
+  copy16(h_boxes, d_boxes, (size_t)det[CNT_N_BOXES] * 96, threadIdx.x, 256);
+}
+
+// rebuilds the active-track list after the table was written from the host (load / reset / broadcast from another rank)
+__global__ void build_active_kernel(const TrackState* __restrict__ tracks, int* __restrict__ trk, int* __restrict__ act_list) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < trk[CNT_N_TRACKS] && (tracks[k].trackNum != 0 || tracks[k].isVisBB)) act_list[atomicAdd(&trk[CNT_N_ACT], 1)] = k;
 }
 
 __global__ void fill_int_kernel(int* p, int n, int v) {
@@ -976,6 +998,8 @@ int tracker_alloc(Ctx* c) {
   LMOT_CUDA(c, cudaMalloc(&c->d_new_num, (size_t)TC * sizeof(int)));
   LMOT_CUDA(c, cudaMalloc(&c->d_live_list, (size_t)TC * sizeof(int)));
   LMOT_CUDA(c, cudaMalloc(&c->d_vis_list, (size_t)TC * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_act_list, (size_t)TC * sizeof(int)));
+  c->act_valid = false;
   fill_int_kernel<<<(MB + 255) / 256, 256, 0, c->trk_stream>>>(c->d_first_setter, MB, INT_MAX);
   LMOT_CUDA(c, cudaGetLastError());
   const size_t sh = (size_t)kTBWarps * c->gate_words * 32 * sizeof(unsigned short);
@@ -985,7 +1009,7 @@ int tracker_alloc(Ctx* c) {
 
 void tracker_free(Ctx* c) {
   cudaFree(c->d_tracks); cudaFree(c->d_trk_counters); cudaFree(c->d_gate); cudaFree(c->d_setter); cudaFree(c->d_first_setter);
-  cudaFree(c->d_skip); cudaFree(c->d_new_num); cudaFree(c->d_live_list); cudaFree(c->d_vis_list);
+  cudaFree(c->d_skip); cudaFree(c->d_new_num); cudaFree(c->d_live_list); cudaFree(c->d_vis_list); cudaFree(c->d_act_list);
   if (c->h_trk_counters) cudaFreeHost(c->h_trk_counters);
 }
 
@@ -1016,33 +1040,53 @@ void origin_points_fold(TrackerHost& h, double timestamp, double v_gps, double y
   h.egoPoint[0] = x; h.egoPoint[1] = y; h.egoPoint[2] = egoYaw;
 }
 
-// boxes: device float[M][8][3] with M in det_counters[CNT_N_BOXES]
+// boxes: device float[M][8][3] with M in det_counters[CNT_N_BOXES]; results into the DEVICE block of sl->res
 int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, const int* det_counters, double timestamp, double v_gps,
                    double yaw_gps) {
   origin_points_fold(c->th, timestamp, v_gps, yaw_gps);
   TrackerHost& h = c->th;
   Result* r = sl->res;
-  OutPtrs o{r->h_targets, r->h_vandyaw, r->h_manage, r->h_static, r->h_vis, r->h_visbb, r->h_hdr};
+  OutPtrs o{r->d_targets, r->d_vandyaw, r->d_manage, r->d_static, r->d_vis, r->d_visbb, r->d_hdr, r->d_boxes};
   int* det = const_cast<int*>(det_counters);
   const int first = h.init ? 0 : 1;
   const int compat = c->prm.oracle_compat_first_frame ? 1 : 0;
+  if (!c->act_valid) {      // the table was written from the host since the last frame
+    LMOT_CUDA(c, cudaMemsetAsync(c->d_trk_counters + CNT_N_ACT, 0, sizeof(int), st));
+    build_active_kernel<<<(c->prm.max_tracks + 255) / 256, 256, 0, st>>>(c->d_tracks, c->d_trk_counters, c->d_act_list);
+    c->act_valid = true;
+  }
   if (!(first && compat)) {
     const double dt = first ? 0.0 : (timestamp - h.timestamp) / 1000000.0;     // :807
     const size_t sh = (size_t)kTBWarps * c->gate_words * 32 * sizeof(unsigned short);
     imm_predict_gate_kernel<<<c->trk_ctas, kTAThreads, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, dt, c->d_gate, c->d_setter,
-                                                                 c->d_first_setter, c->d_skip, c->gate_words);
+                                                                 c->d_first_setter, c->d_skip, c->gate_words, c->d_act_list);
     kernel_mark(c, sl, st);
     imm_update_kernel<<<c->trk_ctas / kTBWarps + 1, kTBWarps * 32, sh, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_gate,
-                                                                           c->d_first_setter, c->d_skip, c->gate_words);
+                                                                           c->d_first_setter, c->d_skip, c->gate_words, c->d_act_list);
     kernel_mark(c, sl, st);
   }
   spawn_output_kernel<<<1, 1024, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_first_setter, c->d_new_num, c->d_live_list,
-                                          c->d_vis_list, c->d_skip, first, compat, h.egoPoint[2], c->prm.max_tracks, o);
+                                          c->d_vis_list, c->d_skip, first, compat, h.egoPoint[2], c->prm.max_tracks, o, c->d_act_list);
   kernel_mark(c, sl, st);
   LMOT_CUDA(c, cudaGetLastError());
   h.timestamp = timestamp;
   h.egoPreYaw = h.egoYaw;
   h.init = true;
+  return LMOT_OK;
+}
+
+// device block of `r` -> its pinned host block (asynchronous on st)
+int tracker_publish(Ctx* c, Result* r, cudaStream_t st) {
+  OutPtrs d{r->d_targets, r->d_vandyaw, r->d_manage, r->d_static, r->d_vis, r->d_visbb, r->d_hdr, r->d_boxes};
+  OutPtrs h{r->h_targets, r->h_vandyaw, r->h_manage, r->h_static, r->h_vis, r->h_visbb, r->h_hdr, r->h_boxes};
+  publish_kernel<<<1, 1024, 0, st>>>(d, h);
+  LMOT_CUDA(c, cudaGetLastError());
+  return LMOT_OK;
+}
+
+int boxes_publish(Ctx* c, Slot* s, Result* r, cudaStream_t st) {
+  publish_boxes_kernel<<<1, 256, 0, st>>>(s->d_boxes, s->d_counters, r->h_boxes);
+  LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }
 
