@@ -527,9 +527,17 @@ int lmot_track_step(lmot_ctx* ctx, const float* boxes, int m, double timestamp_u
   cudaStream_t st = c->stream;
   if (m > 0) LMOT_CUDA(c, cudaMemcpyAsync(s->d_boxes, boxes, (size_t)m * 24 * sizeof(float), cudaMemcpyHostToDevice, st));
   if ((rc = set_counter(c, s, st, CNT_N_BOXES, m))) return rc;
+  if (c->timing) cudaEventRecord(s->res->ev[3], st);
   if ((rc = tracker_launch(c, s, st, s->d_boxes, s->d_counters, timestamp_us, v_gps, yaw_gps))) return rc;
+  if (c->timing) cudaEventRecord(s->res->ev[4], st);
   if ((rc = tracker_publish(c, s->res, st))) return rc;
   LMOT_CUDA(c, cudaStreamSynchronize(st));
+  if (c->timing) {    // tracker stage only: stage_ms[3], kernel_ms[0..] = predict+gate, update, spawn/output
+    c->stage_ms[0] = c->stage_ms[1] = c->stage_ms[2] = 0.f;
+    cudaEventElapsedTime(&c->stage_ms[3], s->res->ev[3], s->res->ev[4]);
+    c->n_kernel_ms = s->res->n_kev;
+    for (int i = 0; i < s->res->n_kev; ++i) cudaEventElapsedTime(&c->kernel_ms[i], i == 0 ? s->res->ev[3] : s->res->kev[i - 1], s->res->kev[i]);
+  }
   const int err = s->res->h_hdr[HDR_ERROR];
   rc = copy_track_outputs(s->res, out);
   return err ? err : rc;

@@ -70,6 +70,14 @@ __device__ __forceinline__ int uf_find(volatile int* L, int x) {
   return x;
 }
 
+// read-only find for the flattening pass: there, the only writes are final roots (a halving store by another thread could
+// land after the owner's flattening store and point the node back at an intermediate ancestor)
+__device__ __forceinline__ int uf_root(const volatile int* L, int x) {
+  int p = L[x];
+  while (p != x) { x = p; p = L[x]; }
+  return x;
+}
+
 __device__ __forceinline__ void uf_union(volatile int* L, int* Lw, int a, int b) {
   while (true) {
     a = uf_find(L, a);
@@ -187,7 +195,7 @@ ccl_bitmap_kernel(unsigned* __restrict__ once, unsigned* __restrict__ twice, uns
     }
   }
   __syncthreads();
-  // E: flatten (parents only ever move to smaller ancestors, so compressing in place is safe against concurrent finds),
+  // E: flatten (read-only walks; every store of this pass is a final root, so concurrent walks stay correct),
   // F: roots of the thread's words
   int roots = 0;
   unsigned rootmask[2] = {0u, 0u};
@@ -200,7 +208,7 @@ ccl_bitmap_kernel(unsigned* __restrict__ once, unsigned* __restrict__ twice, uns
       const int np = __popc(piece_starts(m));
       for (int j = 0; j < np; ++j) {
         const int nd = (w0 + h) * kPiecesPerWord + j;
-        const int r = uf_find(Lv, nd);
+        const int r = uf_root(Lv, nd);
         Lv[nd] = r;
         if (r == nd) { ++roots; rootmask[h] |= 1u << j; }
       }

@@ -757,20 +757,16 @@ __device__ __forceinline__ double intersect_coef(double v1x, double v1y, double 
   return (((v1x - v2x) * (py - v1y) + (v1y - v2y) * (v1x - px)) * ((v1x - v2x) * (cpy - v1y) + (v1y - v2y) * (v1x - cpx)));
 }
 
-// does track `a` (visible box) contain the position of track `b`?  (:670-696)
-__device__ bool overseg_cond(const TrackState& a, double px, double py) {
-  const float f1x = a.BBox[0][0], f1y = a.BBox[0][1], f2x = a.BBox[1][0], f2y = a.BBox[1][1];
-  const float f3x = a.BBox[2][0], f3y = a.BBox[2][1], f4x = a.BBox[3][0], f4y = a.BBox[3][1];
-  // Cheap exact-safe rejection: all three products of a triangle test are > 0 only for a point strictly inside that
-  // triangle (up to rounding of the cross products, ~1e-13 m here), hence inside the box's axis-aligned bounds.  The
-  // bounds are widened by 1 cm + 1e-9 of the coordinate, orders of magnitude beyond that rounding, so a rejected point
-  // fails the full test too; NaN coordinates are not rejected and fall through to it.  ~95 % of the (visible, track)
-  // pairs stop here instead of running ~120 fp64 operations.
-  const float mnx = fminf(fminf(f1x, f2x), fminf(f3x, f4x)), mxx = fmaxf(fmaxf(f1x, f2x), fmaxf(f3x, f4x));
-  const float mny = fminf(fminf(f1y, f2y), fminf(f3y, f4y)), mxy = fmaxf(fmaxf(f1y, f2y), fmaxf(f3y, f4y));
+// does the visible box with corners c[0..7] = (x1,y1,..,x4,y4) contain the position (px,py)?  (:670-696)
+// ab = its axis-aligned bounds (min x, max x, min y, max y).  Cheap exact-safe rejection first: all three products of a
+// triangle test are > 0 only for a point strictly inside that triangle (up to rounding of the cross products, ~1e-13 m
+// here), hence inside the box's bounds.  The bounds are widened by 1 cm + 1e-9 of the coordinate, orders of magnitude
+// beyond that rounding, so a rejected point fails the full test too; NaN coordinates are not rejected and fall through
+// to it.  ~99 % of the (visible box, track) pairs stop here instead of running ~120 fp64 operations.
+__device__ __forceinline__ bool overseg_cond(const float* c, const float* ab, double px, double py) {
   const double mg = 0.01 + 1.0e-9 * (fabs(px) + fabs(py));
-  if (px < (double)mnx - mg || px > (double)mxx + mg || py < (double)mny - mg || py > (double)mxy + mg) return false;
-  const double v1x = f1x, v1y = f1y, v2x = f2x, v2y = f2y, v3x = f3x, v3y = f3y, v4x = f4x, v4y = f4y;
+  if (px < (double)ab[0] - mg || px > (double)ab[1] + mg || py < (double)ab[2] - mg || py > (double)ab[3] + mg) return false;
+  const double v1x = c[0], v1y = c[1], v2x = c[2], v2y = c[3], v3x = c[4], v3y = c[5], v4x = c[6], v4y = c[7];
   const double cp1x = (v1x + v2x + v3x) / 3, cp1y = (v1y + v2y + v3y) / 3;
   const double cp2x = (v1x + v4x + v3x) / 3, cp2y = (v1y + v4y + v3y) / 3;
   const double c1 = intersect_coef(v1x, v1y, v2x, v2y, px, py, cp1x, cp1y);
@@ -781,6 +777,8 @@ __device__ bool overseg_cond(const TrackState& a, double px, double py) {
   const double c6 = intersect_coef(v3x, v3y, v4x, v4y, px, py, cp2x, cp2y);
   return (c1 > 0 && c2 > 0 && c3 > 0) || (c4 > 0 && c5 > 0 && c6 > 0);
 }
+
+constexpr int kVisChunk = 256;       // visible boxes staged in shared memory per pass
 
 // ------------------------------------------------------------------------------------------------ TC2
 // One frame's results.  spawn_output_kernel fills the DEVICE copy (the tracker is the sequential chain of the pipeline:
@@ -826,37 +824,60 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
 
   // ---- mergeOverSegmentation (:666-700), folded into this kernel.  The sequential double loop writes trackNum[i]=5,
   // trackNum[j]=0 for every hit (i,j) with i visible; the value that survives at index k is the write with the largest
-  // (i,j) key: 0 if some visible i > k contains k, else 5 if k (visible) contains anybody, else unchanged.  Only live k can
-  // change (0 -> 0 is a no-op, 5 needs a visible, hence live, k), containers are the few visible tracks.
+  // (i,j) key: 0 if some visible i > k contains k, else 5 if k (visible) contains anybody, else unchanged.  Both facts come
+  // from ONE predicate, "visible box i contains the position of track j" (dead j included, like the reference): thread =
+  // track j, the visible boxes (a few dozen) are staged in shared memory with their bounds and read as broadcasts.
   {
-    __shared__ int s_nlive, s_nvis;
-    if (tid == 0) { s_nlive = 0; s_nvis = 0; }
+    __shared__ int s_nvis;
+    __shared__ __align__(16) float s_bx[kVisChunk][8];
+    __shared__ __align__(16) float s_ab[kVisChunk][4];
+    __shared__ int s_vid[kVisChunk];
+    __shared__ unsigned char s_h5[kVisChunk];
+    if (tid == 0) s_nvis = 0;
     __syncthreads();
-    for (int k0 = 0; k0 < T0; k0 += 1024) {            // lists of live / visible tracks (order is irrelevant here)
+    for (int k0 = 0; k0 < T0; k0 += 1024) {            // list of visible tracks (order is irrelevant here)
       const int k = k0 + tid;
-      if (k < T0) {
-        const TrackState& t = tracks[k];
-        if (t.trackNum != 0) { const int p = atomicAdd(&s_nlive, 1); live_list[p] = k; imax_arr[k] = -1; has5_arr[k] = 0; }
-        if (t.isVisBB) { const int p = atomicAdd(&s_nvis, 1); vis_list[p] = k; }
+      if (k < T0 && tracks[k].isVisBB) vis_list[atomicAdd(&s_nvis, 1)] = k;
+    }
+    __syncthreads();
+    const int nv = s_nvis;
+    for (int v0 = 0; v0 < nv; v0 += kVisChunk) {
+      const int nc = min(kVisChunk, nv - v0);
+      for (int e = tid; e < nc * 8; e += 1024) { const int v = e >> 3, q = e & 7; s_bx[v][q] = tracks[vis_list[v0 + v]].BBox[q >> 1][q & 1]; }
+      __syncthreads();
+      for (int v = tid; v < nc; v += 1024) {
+        const float* c = s_bx[v];
+        s_ab[v][0] = fminf(fminf(c[0], c[2]), fminf(c[4], c[6])); s_ab[v][1] = fmaxf(fmaxf(c[0], c[2]), fmaxf(c[4], c[6]));
+        s_ab[v][2] = fminf(fminf(c[1], c[3]), fminf(c[5], c[7])); s_ab[v][3] = fmaxf(fmaxf(c[1], c[3]), fmaxf(c[5], c[7]));
+        s_vid[v] = vis_list[v0 + v]; s_h5[v] = 0;
       }
+      __syncthreads();
+      for (int j0 = 0; j0 < T0; j0 += 1024) {
+        const int j = j0 + tid;
+        if (j < T0) {
+          const double px = tracks[j].x[0][0], py = tracks[j].x[0][1];
+          int imax = (v0 == 0) ? -1 : imax_arr[j];
+          for (int v = 0; v < nc; ++v) {
+            const int i = s_vid[v];
+            if (i != j && overseg_cond(s_bx[v], s_ab[v], px, py)) { s_h5[v] = 1; imax = max(imax, i); }
+          }
+          imax_arr[j] = imax;
+        }
+      }
+      __syncthreads();
+      for (int v = tid; v < nc; v += 1024) has5_arr[s_vid[v]] = s_h5[v];
+      __syncthreads();
     }
-    __syncthreads();
-    const int nl = s_nlive, nv = s_nvis;
-    for (int p = tid; p < nl * nv; p += 1024) {         // does visible i contain live k ?
-      const int k = live_list[p / nv], i = vis_list[p % nv];
-      if (i != k && overseg_cond(tracks[i], tracks[k].x[0][0], tracks[k].x[0][1])) atomicMax(&imax_arr[k], i);
-    }
-    for (int p = tid; p < nv * T0; p += 1024) {         // does visible k contain anybody (dead tracks included) ?
-      const int k = vis_list[p / T0], j = p % T0;
-      if (j != k && !has5_arr[k] && overseg_cond(tracks[k], tracks[j].x[0][0], tracks[j].x[0][1])) has5_arr[k] = 1;
-    }
-    __syncthreads();
-    for (int p = tid; p < nl; p += 1024) {
-      const int k = live_list[p];
-      const int imax = imax_arr[k];
-      const bool has5 = has5_arr[k] != 0;
-      if (imax >= 0 && (!has5 || imax > k)) tracks[k].trackNum = 0;
-      else if (has5) tracks[k].trackNum = 5;
+    if (nv > 0) {
+      for (int k0 = 0; k0 < T0; k0 += 1024) {
+        const int k = k0 + tid;
+        if (k < T0 && tracks[k].trackNum != 0) {
+          const int imax = imax_arr[k];
+          const bool has5 = tracks[k].isVisBB && has5_arr[k] != 0;
+          if (imax >= 0 && (!has5 || imax > k)) tracks[k].trackNum = 0;
+          else if (has5) tracks[k].trackNum = 5;
+        }
+      }
     }
     __syncthreads();
   }

@@ -236,6 +236,53 @@ def run_shared_tracker(args, lmot, ctx, d_frames, ts, n_pts, rank, world, local_
             "gpu_launches": KERNELS_PER_FRAME * K}))
 
 
+# ------------------------------------------------------------------------------------------- tracker in isolation (configs[2])
+def tracker_stress(ctx, steps=40, warm=5):
+    """BASELINE.json configs[2]: 1024 mature tracks (32x32 lattice, 8 m pitch) x 256 noisy detections, the tracker stage in
+    isolation through lmot_track_step.  Every timed step starts from the SAME 1024-track table (re-loaded, untimed), so each
+    step is exactly that workload; device time = CUDA events around the three tracker kernels."""
+    rng = np.random.default_rng(0)
+    T, M = 1024, 256
+    gx, gy = np.meshgrid(np.arange(32) * 8.0 - 124.0, np.arange(32) * 8.0 - 124.0, indexing="ij")
+    pos = np.stack([gx.ravel(), gy.ravel()], 1)
+    half = np.array([[-1.0, -0.5], [-1.0, 0.5], [1.0, 0.5], [1.0, -0.5]])
+
+    def boxes_at(p, noise):
+        c = p + rng.normal(0, noise, p.shape)
+        out = np.zeros((len(c), 8, 3), np.float32)
+        for k in range(4):
+            out[:, k, :2] = c + half[k]; out[:, k, 2] = -2.0
+            out[:, 4 + k, :2] = c + half[k]; out[:, 4 + k, 2] = 0.0
+        return out
+
+    off = -0.63035 - np.pi / 2
+    ctx.tracker_reset()
+    ts = 0.0
+    for _ in range(8):                      # frame 1 spawns, then every lattice site is observed until the tracks are mature
+        ts += 1e5
+        ctx.track_step(boxes_at(pos, 0.02), ts)
+    state = ctx.tracker_dump()
+    mature = int((state[:, 0] == 5).sum())
+    det = boxes_at(pos[np.sort(rng.choice(T, M, replace=False))], 0.15)
+    ctx.enable_timing(True)
+    dev, host, kern = [], [], []
+    for i in range(warm + steps):
+        ctx.tracker_load(state, 1, ts, 0.0, off, off, -np.pi / 2)
+        t0 = time.perf_counter()
+        out = ctx.track_step(det, ts + 1e5)
+        t1 = time.perf_counter()
+        if i >= warm:
+            dev.append(ctx.last_stage_ms()[3]); host.append(1e3 * (t1 - t0)); kern.append(ctx.last_kernel_ms()[:3])
+    ctx.enable_timing(False)
+    ctx.tracker_reset()
+    dev_ms, host_ms = float(np.mean(dev)), float(np.mean(host))
+    return {"workload": "imm_ukf_jpda stress: 1024 tracks x 256 detections, tracker stage in isolation (configs[2])",
+            "tracks_in_table": int(len(state)), "mature_tracks": mature, "detections": M, "steps": steps,
+            "device_ms_per_step": dev_ms, "track_updates_per_s_device": len(state) / (dev_ms * 1e-3),
+            "host_call_ms_per_step": host_ms, "steps_per_s_through_c_abi": 1e3 / host_ms,
+            "kernel_us": {n: float(1e3 * v) for n, v in zip(("imm_predict_gate", "imm_update", "spawn_output"), np.mean(np.array(kern), 0))}}
+
+
 # ------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -244,6 +291,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="lmot", choices=["lmot", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=60, help="frames of the CPU baseline sample (rank 0, N=1)")
+    ap.add_argument("--tracker-stress", type=int, default=40, help="timed steps of the 1024x256 tracker-only workload (0 = skip; rank 0, N=1)")
     ap.add_argument("--dense-frames", type=int, default=10, help="1M-point frames for the dense roofline measurement (0 = skip)")
     ap.add_argument("--shared-tracker", choices=["off", "streams", "frames"], default="off",
                     help="N>1 only: all ranks feed ONE track table (NCCL all_gather of boxes, tracker on rank 0, NCCL broadcast of the "
@@ -432,6 +480,10 @@ def main():
                         "host_cores": os.cpu_count(),
                         "sample": f"first {ns} frames of the same workload after {Wc} warm-up frames, single thread (the reference is single-threaded per node)"}
 
+    stress = None
+    if rank == 0 and world == 1 and args.tracker_stress > 0:
+        stress = tracker_stress(ctx, steps=args.tracker_stress)
+
     if rank == 0:
         line = {
             "metric": "HDL-64 frames/sec (120K pts, 64 tracks)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -453,6 +505,7 @@ def main():
             "stage_ms": {n: float(v) for n, v in zip(("ground", "cluster", "box", "tracker"), stage_ms)},
             "kernel_us_warm": ({n: float(1e3 * v / K) for n, v in zip(KERNEL_NAMES, kern_ms)} if kern_ms is not None and len(kern_ms) == len(KERNEL_NAMES) else None),
             "roofline_dense_1m": dense,
+            "tracker_stress_1024x256": stress,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
