@@ -51,6 +51,8 @@ class Params(C.Structure):
         ("min_cluster_points", C.c_int), ("rule_filter", C.c_int),
         ("oracle_compat_first_frame", C.c_int),
         ("max_points", C.c_int), ("max_clusters", C.c_int), ("max_boxes", C.c_int), ("max_tracks", C.c_int),
+        ("node_prefilter", C.c_int), ("filter_z_min", C.c_float), ("filter_z_max", C.c_float),
+        ("filter_x_min", C.c_float), ("filter_x_max", C.c_float), ("filter_y_min", C.c_float), ("filter_y_max", C.c_float),
         ("pipeline_depth", C.c_int), ("result_ring", C.c_int),
     ]
 

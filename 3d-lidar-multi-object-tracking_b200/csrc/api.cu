@@ -297,6 +297,8 @@ int lmot_default_params(lmot_params* p) {
   p->rule_filter = LMOT_RULE_INTENDED;
   p->oracle_compat_first_frame = 1;
   p->max_points = 1 << 20; p->max_clusters = 4096; p->max_boxes = 1024; p->max_tracks = 8192;
+  p->node_prefilter = 0; p->filter_z_min = -3.0f; p->filter_z_max = 1.0f;
+  p->filter_x_min = -15.f; p->filter_x_max = 5.f; p->filter_y_min = -50.f; p->filter_y_max = 50.f;
   p->pipeline_depth = 4;
   p->result_ring = 32;
   return LMOT_OK;
@@ -342,9 +344,14 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   c->gp.r_min = p.r_min; c->gp.r_max = p.r_max; c->gp.t_hmin = p.t_hmin; c->gp.t_hmax = p.t_hmax;
   c->gp.t_hdiff = p.t_hdiff; c->gp.h_sensor = p.h_sensor;
   { volatile float span = p.r_max - p.r_min; c->gp.r_span = span; }
+  c->gp.prefilter = p.node_prefilter ? 1 : 0;
+  c->gp.fz0 = p.filter_z_min; c->gp.fz1 = p.filter_z_max; c->gp.fx0 = p.filter_x_min; c->gp.fx1 = p.filter_x_max;
+  c->gp.fy0 = p.filter_y_min; c->gp.fy1 = p.filter_y_max;
   c->gp.bin_scale = (float)((double)LMOT_NUM_BIN / (double)c->gp.r_span);
   c->gp.tol = p.ground_tolerance;
   gauss_taps(c->gp.tap);
+  if (const char* e = getenv("LMOT_TRK_CTAS")) { const int v = atoi(e); if (v >= 8 && v <= 4096) c->trk_ctas = v; }     // tuning only
+  if (const char* e = getenv("LMOT_FIT_CTAS")) { const int v = atoi(e); if (v >= 8 && v <= 4096) c->fit_ctas = v; }
   if (const char* e = getenv("LMOT_PTS_PER_CTA")) { const int v = atoi(e); if (v >= 256 && v <= 16384) c->pts_per_cta = v; }
   int rc = LMOT_OK;
   // The tracker is the one sequential chain of the pipeline (frame f+1's tracker needs frame f's table): its CTAs get

@@ -356,13 +356,17 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
     } else if (valid) q = __ldg(&pts[beg + li]);
     unsigned c = kNoCell;
     unsigned key = 0xFFFFFFFFu;
-    if (valid) {
+    bool pre = false;                              // removed by the node's pre-filters (src/groundremove/main.cpp:104-112)
+    if (valid && p.prefilter)
+      pre = !(isfinite(q.x) && isfinite(q.y) && isfinite(q.z) && q.z >= p.fz0 && q.z <= p.fz1 &&   // PassThrough: inclusive
+              q.x > p.fx0 && q.x < p.fx1 && q.y > p.fy0 && q.y < p.fy1);                            // ConditionalRemoval: strict
+    if (valid && !pre) {
       c = polar_cell(q.x, q.y, p);
       float z = q.z;
       if (z == 0.f) z = 0.f;                       // -0 -> +0 (`z < minZ` does not order them either)
       if (c != kNoCell && z == z) key = fkey(z);   // NaN z never wins `z < minZ` (ground_removal.cpp:41)
     }
-    s_cell[li] = (uint16_t)c;
+    s_cell[li] = pre ? kPreFiltered : (uint16_t)c;
     // consecutive HDL-64 returns fall into the same cell: one atomic per distinct cell per warp
     const unsigned grp = __match_any_sync(0xFFFFFFFFu, c);
     const unsigned kmin = __reduce_min_sync(grp, key);
@@ -391,7 +395,8 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
     int lab = 0;
     if (li < cnt) {
       const unsigned c = s_cell[li];
-      if (c != kNoCell) {
+      if (c == kNoCell) lab = p.prefilter ? 3 : 0;      // in neither output; with the node pre-filters on: still an aux point
+      else if (c != kPreFiltered) {
         const float z = (t < res_tiles) ? s_pts[li].z : __ldg(&pts[beg + li]).z;
         const float h = __ldcg(&o_hg[c]);                       // -inf for non-ground cells -> elevated
         lab = ((double)z < __dadd_rn((double)h, p.tol)) ? 1 : 2;   // :236-246
@@ -462,7 +467,7 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
     unsigned cc = kNoCell;
     if (li < cnt) {
       if (out.labels) out.labels[beg + li] = (uint8_t)lab;
-      if (lab) {
+      if (lab == 1 || lab == 2) {
         const float4 q = (t < res_tiles) ? s_pts[li] : __ldg(&pts[beg + li]);
         if (lab == 2) {
           const unsigned pos = run_e + (wex & 0xFFFFu) + __popc(be & lt);
@@ -483,7 +488,12 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
 // inspection only (lmot_debug_cell_index): the fused kernel keeps the cell ids in shared memory
 __global__ void polar_cells_kernel(const float4* __restrict__ pts, int n, GroundParams p, uint16_t* __restrict__ cell) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { const float4 q = __ldg(&pts[i]); cell[i] = polar_cell(q.x, q.y, p); }
+  if (i < n) {
+    const float4 q = __ldg(&pts[i]);
+    const bool pre = p.prefilter && !(isfinite(q.x) && isfinite(q.y) && isfinite(q.z) && q.z >= p.fz0 && q.z <= p.fz1 &&
+                                      q.x > p.fx0 && q.x < p.fx1 && q.y > p.fy0 && q.y < p.fy1);
+    cell[i] = pre ? kNoCell : polar_cell(q.x, q.y, p);
+  }
 }
 
 __global__ void init_keys_kernel(unsigned* keys, int n) {

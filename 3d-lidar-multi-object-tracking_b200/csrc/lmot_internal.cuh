@@ -14,6 +14,7 @@ constexpr int kPolarCells = kNumChannel * kNumBin;  // 9600
 constexpr int kNumGrid = LMOT_NUM_GRID;
 constexpr int kCartCells = kNumGrid * kNumGrid;      // 62500
 constexpr uint16_t kNoCell = 0xFFFFu;
+constexpr uint16_t kPreFiltered = 0xFFFEu;           // removed by the ground node's pre-filters (never reaches groundRemove)
 constexpr int kScanTile = 1024;                      // points per tile of the stable-partition scan
 
 // device-side counters of one frame (one int each; written by kernels, read by later kernels and by fetch)
@@ -27,6 +28,8 @@ struct GroundParams {
   float r_min, r_max, t_hmin, t_hmax, t_hdiff, h_sensor;
   float r_span;          // r_max - r_min evaluated in float (ground_removal.cpp:71)
   float bin_scale;       // 120 / r_span: bins per metre of the guarded fast path (ground.cu polar_cell)
+  int prefilter;         // the `ground` node's PassThrough(z) + ConditionalRemoval(x, y) in front of groundRemove
+  float fz0, fz1, fx0, fx1, fy0, fy1;
   double tol;            // 0.25
   double tap[3];         // gaussKernel(3, 1.0) computed on the host with the host libm (gaus_blur.cpp:26-49)
 };

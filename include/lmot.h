@@ -83,6 +83,13 @@ typedef struct lmot_params {
   int max_clusters;          /* default 4096 (a 250x250 grid with 3x3 dilation cannot hold more) */
   int max_boxes;             /* default 1024 */
   int max_tracks;            /* tracks ever created (dead ones keep their slot), default 8192 */
+  /* pre-filters of the reference's `ground` ROS node, applied BEFORE groundRemove (src/groundremove/main.cpp:56-89,104-112):
+   * pcl::PassThrough on z (limits inclusive, non-finite points removed) then pcl::ConditionalRemoval x in (x_min,x_max) AND
+   * y in (y_min,y_max) (strict).  Off by default: the hot path is groundRemove itself.  Fused into the first load. */
+  int node_prefilter;        /* 0 */
+  float filter_z_min, filter_z_max;   /* -3.0, 1.0  (ROS params filter_z_min / filter_z_max, main.cpp:147-148) */
+  float filter_x_min, filter_x_max;   /* -15, 5     (main.cpp:68-71) */
+  float filter_y_min, filter_y_max;   /* -50, 50    (main.cpp:73-76) */
   /* frames in flight inside one context: detection stages of frame f+1.. overlap the tracker of frame f (1..8, default 4) */
   int pipeline_depth;
   /* result blocks (pinned host memory) = how many submitted frames may wait to be collected (1..64, default 32) */
@@ -107,7 +114,9 @@ int lmot_set_stream(lmot_ctx* ctx, void* cuda_stream);
 /* ---- stage entry points, HOST buffers (synchronous: H2D, kernels, D2H, stream sync) -------------------- */
 
 /* groundRemove.  labels (nullable) gets one byte per input point: 0 = in neither output (range filter /
- * cell index out of range, ground_removal.cpp:54,233), 1 = ground, 2 = elevated.  elevated / ground (nullable)
+ * cell index out of range, ground_removal.cpp:54,233), 1 = ground, 2 = elevated.  With node_prefilter on, 0 = removed by
+ * the node's pre-filters and 3 = survived them (i.e. belongs to the node's `aux_points` cloud, as 1 and 2 do) but in neither
+ * output of groundRemove.  elevated / ground (nullable)
  * receive the order-preserving output clouds, stride 4 floats, capacity n points each. */
 int lmot_ground_remove(lmot_ctx* ctx, const float* points, int n, int stride_floats, uint8_t* labels,
                        float* elevated, int* n_elevated, float* ground, int* n_ground);

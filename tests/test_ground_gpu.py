@@ -164,3 +164,35 @@ def test_fused_kernel_tiles_beyond_shared_memory_bit_exact(pkg, ref_intended, sy
         assert np.array_equal(out["labels"], labels_from_clouds(pts, e_ref, g_ref))
     finally:
         ctx.close()
+
+
+def test_node_prefilter_matches_filter_then_ground_remove(pkg, ref_intended, synth):
+    """SURVEY.md §8(f)2: the `ground` ROS node runs pcl::PassThrough (z in [-3, 1], inclusive, non-finite removed) and
+    pcl::ConditionalRemoval (x in (-15, 5), y in (-50, 50), strict) in front of groundRemove
+    (/root/reference/object_tracking/src/groundremove/main.cpp:56-89,104-112).  With node_prefilter on, the fused kernel must give
+    what groundRemove gives on the pre-filtered cloud, and label 3 / 1 / 2 must mark exactly the node's aux_points cloud."""
+    p = pkg.default_params()
+    p.node_prefilter = 1
+    p.pipeline_depth = 1
+    ctx = pkg.Lmot(p, device=0)
+    try:
+        for seed in (4, 5):
+            pts = next(iter(synth.frames(synth.SceneConfig(seed=seed), 1)))[1].copy()
+            rng = np.random.default_rng(seed)
+            # points exactly on the limits, and a few non-finite ones
+            pts[:6, :3] = [[-15.0, 0, -1.7], [5.0, 0, -1.7], [1, -50.0, -1.7], [1, 50.0, -1.7], [1, 1, -3.0], [1, 8, 1.0]]
+            pts[6, 0] = np.nan; pts[7, 2] = np.inf; pts[8, 1] = -np.inf
+            x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+            with np.errstate(invalid="ignore"):
+                keep = np.isfinite(x) & np.isfinite(y) & np.isfinite(z) & (z >= -3.0) & (z <= 1.0) & (x > -15) & (x < 5) & (y > -50) & (y < 50)
+            aux = pts[keep]
+            e_ref, g_ref = ref_intended.ground_remove(aux)
+            out = ctx.ground_remove(pts)
+            assert np.array_equal(out["elevated"][:, :3].view(np.uint32), e_ref.view(np.uint32))
+            assert np.array_equal(out["ground"][:, :3].view(np.uint32), g_ref.view(np.uint32))
+            assert np.array_equal(out["labels"] != 0, keep)
+            lab_aux = labels_from_clouds(aux, e_ref, g_ref)
+            assert np.array_equal(out["labels"][keep] % 3, lab_aux)      # 3 = aux point in neither output
+            assert keep[4] and keep[5] and not keep[:4].any() and not keep[6:9].any()
+    finally:
+        ctx.close()
