@@ -350,6 +350,7 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   c->gp.bin_scale = (float)((double)LMOT_NUM_BIN / (double)c->gp.r_span);
   c->gp.tol = p.ground_tolerance;
   gauss_taps(c->gp.tap);
+  if (const char* e = getenv("LMOT_COOP")) c->coop_launch = atoi(e) != 0;
   if (const char* e = getenv("LMOT_TRK_CTAS")) { const int v = atoi(e); if (v >= 8 && v <= 4096) c->trk_ctas = v; }     // tuning only
   if (const char* e = getenv("LMOT_FIT_CTAS")) { const int v = atoi(e); if (v >= 8 && v <= 4096) c->fit_ctas = v; }
   if (const char* e = getenv("LMOT_PTS_PER_CTA")) { const int v = atoi(e); if (v >= 256 && v <= 16384) c->pts_per_cta = v; }

@@ -21,6 +21,7 @@
 //
 // Everything that decides a cell index or a label is IEEE round-to-nearest without FMA contraction, so the
 // results are bit-identical to the reference built for x86-64.
+#include <mutex>
 #include "lmot_internal.cuh"
 #include "exact_math.cuh"
 #include "tma.cuh"
@@ -28,6 +29,9 @@
 namespace lmot {
 
 namespace {
+
+std::mutex g_ground_mutex;                 // one ground kernel in flight per device (see ground_launch)
+cudaEvent_t g_ground_done[64] = {};
 
 __device__ __forceinline__ unsigned fkey(float f) {
   const unsigned u = __float_as_uint(f);
@@ -596,7 +600,23 @@ int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bo
                   (void*)&bar_base, (void*)&s->d_gdesc, (void*)&epoch, (void*)&out, (void*)&roi, (void*)&c->d_phase_clock};
   const int tiles = (chunk + kTilePts - 1) / kTilePts;
   const size_t smem = (size_t)fused_smem_bytes(tiles < kMaxResTiles ? tiles : kMaxResTiles, tiles > 0 ? tiles : 1);
-  LMOT_CUDA(c, cudaLaunchCooperativeKernel((const void*)ground_fused_kernel, dim3(G), dim3(kFusedThreads), args, smem, st));
+  if (c->coop_launch) {
+    LMOT_CUDA(c, cudaLaunchCooperativeKernel((const void*)ground_fused_kernel, dim3(G), dim3(kFusedThreads), args, smem, st));
+  } else {
+    // Ordinary launch + the guarantee a cooperative launch would give, obtained differently.  A cooperative launch makes
+    // the driver wait for an idle device, i.e. it serialises the frame pipeline's streams (measured: the detection stages of
+    // different frames stopped overlapping).  The kernel's grid barrier only needs all G CTAs to BECOME resident: G <= one
+    // CTA per SM (fused_max_ctas), every other kernel on the device terminates without waiting for this one, and ground
+    // kernels never wait for each other because they are chained through one per-device event -- at most one is in flight,
+    // so no two partially resident grids can starve each other.  (Several PROCESSES sharing the GPU through MPS are outside
+    // this guarantee; the barrier then traps after ~2 s instead of hanging.)
+    std::lock_guard<std::mutex> lk(g_ground_mutex);
+    cudaEvent_t& ev = g_ground_done[c->device & 63];
+    if (!ev) LMOT_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    else LMOT_CUDA(c, cudaStreamWaitEvent(st, ev, 0));
+    LMOT_CUDA(c, cudaLaunchKernel((const void*)ground_fused_kernel, dim3(G), dim3(kFusedThreads), args, smem, st));
+    LMOT_CUDA(c, cudaEventRecord(ev, st));
+  }
   s->bar_base += 2u * (unsigned)G;
   c->last_ground_ctas = G;
   kernel_mark(c, s, st);

@@ -159,6 +159,7 @@ struct Ctx {
 
   // ---- capacities
   int max_points = 0, max_sort_tiles = 0, fit_ctas = 296, n_mt_raw = 0;
+  bool coop_launch = false;            // LMOT_COOP=1: cudaLaunchCooperativeKernel for the ground kernel (A/B diagnostics)
   int fused_max_ctas = 0;              // co-residency limit of the cooperative ground kernel on this device
   unsigned long long* d_phase_clock = nullptr;   // diagnostic: [CTAs][8] %globaltimer stamps of the last ground launch (lmot_debug_phase_clock)
   int last_ground_ctas = 0;

@@ -14,8 +14,8 @@ ts, frames = bench.make_frames(synth, W + K)
 n = frames.shape[1]
 d = torch.from_numpy(frames).cuda()
 torch.cuda.synchronize()
-for trk, fit in ((592, 296), (148, 296), (148, 148), (96, 96), (592, 148)):
-    os.environ["LMOT_TRK_CTAS"] = str(trk); os.environ["LMOT_FIT_CTAS"] = str(fit)
+for coop, trk, fit in ((1, 592, 296), (0, 592, 296), (0, 148, 148)):
+    os.environ["LMOT_TRK_CTAS"] = str(trk); os.environ["LMOT_FIT_CTAS"] = str(fit); os.environ["LMOT_COOP"] = str(coop)
     for depth in (1, 2, 4, 8):
         prm = lmot.default_params(); prm.pipeline_depth = depth
         ctx = lmot.Lmot(prm)
@@ -28,5 +28,5 @@ for trk, fit in ((592, 296), (148, 296), (148, 148), (96, 96), (592, 148)):
         for i in range(W, W + K): ctx.frame_dev(d[i].data_ptr(), n, ts[i])
         th = time.perf_counter() - t0
         ctx.flush(); e1.record(st); torch.cuda.synchronize()
-        print(json.dumps(dict(trk_ctas=trk, fit_ctas=fit, depth=depth, fps=K / (e0.elapsed_time(e1) * 1e-3), host_submit_us=1e6 * th / K)), flush=True)
+        print(json.dumps(dict(coop=coop, trk_ctas=trk, fit_ctas=fit, depth=depth, fps=K / (e0.elapsed_time(e1) * 1e-3), host_submit_us=1e6 * th / K)), flush=True)
         ctx.frame_fetch(); ctx.close()
