@@ -79,7 +79,7 @@ ABI_SYMBOLS = [
     "lmot_frame_dev", "lmot_frame_fetch", "lmot_frame_submit", "lmot_frame_collect", "lmot_frames_in_flight", "lmot_frame_ready", "lmot_flush",
     "lmot_ground_remove_dev", "lmot_detect_dev", "lmot_sync",
     "lmot_origin_points", "lmot_tracker_table", "lmot_tracker_set_num_tracks", "lmot_tracker_reset", "lmot_tracker_num_tracks", "lmot_tracker_dump", "lmot_tracker_load",
-    "lmot_debug_polar_grid", "lmot_debug_cell_index", "lmot_debug_label_grid", "lmot_debug_phase_clock", "lmot_selftest_atan2f",
+    "lmot_debug_polar_grid", "lmot_debug_cell_index", "lmot_debug_label_grid", "lmot_debug_phase_clock", "lmot_debug_timeline", "lmot_selftest_atan2f",
     "lmot_enable_timing", "lmot_last_stage_ms", "lmot_last_kernel_ms", "lmot_debug_host_ns",
 ]
 
@@ -346,6 +346,14 @@ class Lmot:
         nc = C.c_int(0)
         self._chk(self.lib.lmot_debug_label_grid(self.h, grid.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(nc)))
         return grid.reshape(250, 250), nc.value
+
+    def debug_timeline(self):
+        """(frames, 5 + kernels) float32 ms: completion of the stage boundaries and kernels of the frames still in the result ring."""
+        buf = np.full((64, 64), -1.0, np.float32)
+        n = C.c_int(0); stride = C.c_int(0)
+        self._chk(self.lib.lmot_debug_timeline(self.h, buf.ctypes.data_as(C.POINTER(C.c_float)), 64, C.byref(n), C.byref(stride)))
+        flat = buf.reshape(-1)[: n.value * stride.value].reshape(n.value, stride.value) if n.value else buf[:0]
+        return flat
 
     def debug_phase_clock(self):
         """First call arms the phase clock of ground_fused_kernel; later calls -> (n_ctas, 8) uint64 ns stamps of the last launch."""

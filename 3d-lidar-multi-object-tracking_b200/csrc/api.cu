@@ -817,6 +817,32 @@ int lmot_debug_cell_index(lmot_ctx* ctx, int32_t* ch, int32_t* bin, int n) {
   return LMOT_OK;
 }
 
+// diagnostic: completion times (ms, relative to the oldest frame's start) of the stage boundaries and of every kernel of the
+// frames still in the result ring, pipelined submissions included.  out[frame][0..4] = ev[0..4] (start, ground, cluster, box,
+// tracker), out[frame][5..5+n) = the kernels in launch order; row stride 5 + kMaxKernelEvents floats; -1 = not recorded.
+int lmot_debug_timeline(lmot_ctx* ctx, float* out, int cap_frames, int* n_frames, int* row_stride) {
+  if (!ctx || !out) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  int rc = lmot_sync(ctx);
+  if (rc) return rc;
+  const int stride = 5 + kMaxKernelEvents;
+  if (row_stride) *row_stride = stride;
+  int n = 0;
+  Result* base = nullptr;
+  for (int k = 0; k < c->n_results && n < cap_frames; ++k) {
+    Result* r = &c->results[(c->res_next + k) % c->n_results];      // oldest first
+    if (!r->has_tracks || r->n_kev == 0) continue;
+    if (!base) base = r;
+    float* o = out + (size_t)n * stride;
+    for (int i = 0; i < stride; ++i) o[i] = -1.f;
+    for (int i = 0; i < 5; ++i) if (cudaEventElapsedTime(&o[i], base->ev[0], r->ev[i]) != cudaSuccess) { o[i] = -1.f; cudaGetLastError(); }
+    for (int i = 0; i < r->n_kev; ++i) if (cudaEventElapsedTime(&o[5 + i], base->ev[0], r->kev[i]) != cudaSuccess) { o[5 + i] = -1.f; cudaGetLastError(); }
+    ++n;
+  }
+  if (n_frames) *n_frames = n;
+  return LMOT_OK;
+}
+
 // diagnostic: switch the phase clock of ground_fused_kernel on (allocates [CTAs][8] u64) and read the last launch's stamps
 int lmot_debug_phase_clock(lmot_ctx* ctx, unsigned long long* out, int cap_ctas, int* n_ctas) {
   if (!ctx) return LMOT_ERR_INVALID;

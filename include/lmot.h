@@ -218,6 +218,10 @@ int lmot_debug_cell_index(lmot_ctx* ctx, int32_t* ch, int32_t* bin, int n);
 /* label grid and per-elevated-point cluster id of the last clustering / box fitting */
 int lmot_debug_label_grid(lmot_ctx* ctx, int32_t* grid, int* num_cluster);
 
+/* diagnostic (after lmot_enable_timing): completion times in ms, relative to the start of the oldest frame still in the result
+ * ring, of the stage boundaries [0..4] and of every kernel [5..] of each of those frames -- pipelined submissions included */
+int lmot_debug_timeline(lmot_ctx* ctx, float* out, int cap_frames, int* n_frames, int* row_stride);
+
 /* diagnostic: first call switches on the phase clock of ground_fused_kernel; later calls return the %globaltimer stamps
  * (ns) thread 0 of every CTA took at its 8 phase boundaries during the last launch: out[n_ctas][8] */
 int lmot_debug_phase_clock(lmot_ctx* ctx, unsigned long long* out, int cap_ctas, int* n_ctas);

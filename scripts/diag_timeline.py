@@ -1,0 +1,32 @@
+"""Diagnostic: GPU timeline of the pipelined frames (completion time of every kernel of the last frames), device-resident input."""
+import importlib, os, sys
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+lmot = importlib.import_module("3d-lidar-multi-object-tracking_b200")
+synth = importlib.import_module("3d-lidar-multi-object-tracking_b200.synth")
+import bench
+K, W = 120, 20
+ts, frames = bench.make_frames(synth, W + K)
+n = frames.shape[1]
+d = torch.from_numpy(frames).cuda()
+torch.cuda.synchronize()
+for depth in (1, 4):
+    prm = lmot.default_params(); prm.pipeline_depth = depth
+    ctx = lmot.Lmot(prm)
+    st = torch.cuda.Stream(); torch.cuda.set_stream(st); ctx.set_stream(st.cuda_stream)
+    ctx.tracker_reset(); ctx.enable_timing(True)
+    for i in range(W + K): ctx.frame_dev(d[i].data_ptr(), n, ts[i])
+    ctx.sync()
+    tl = ctx.debug_timeline() * 1e3          # us
+    names = ["start", "ground", "cluster", "box", "tracker"] + list(bench.KERNEL_NAMES)
+    print(f"--- pipeline_depth {depth}: {len(tl)} frames; columns = completion time (us) relative to the oldest frame's start")
+    print("frame " + " ".join(f"{x[:9]:>9s}" for x in names))
+    for f, row in enumerate(tl[-14:]):
+        print(f"{f:5d} " + " ".join(f"{v:9.1f}" for v in row[: len(names)]))
+    if len(tl) > 4:
+        per = (tl[-1, 4] - tl[-11, 4]) / 10
+        print(f"tracker completion to tracker completion: {per:.1f} us per frame")
+    ctx.enable_timing(False); ctx.close()
