@@ -183,6 +183,8 @@ struct Ctx {
   cudaStream_t trk_stream = nullptr;
   cudaStream_t pub_stream = nullptr;   // device -> host publication of finished frames
   int* d_act_list = nullptr;           // [max_tracks] tracks to visit next frame (built by spawn_output_kernel)
+  double2* d_pos = nullptr;            // [max_tracks] packed (x, y) of every track's merged state, for mergeOverSegmentation
+  Result* last_trk_res = nullptr;      // result block of the previous tracker step (its device copy seeds the next one)
   bool act_valid = false;              // false after the table was written from the host: rebuilt before the next step
   int trk_ctas = 592, gate_words = 0;
   TrackState* d_tracks = nullptr;      // [max_tracks] append-only table; dead tracks keep their slot

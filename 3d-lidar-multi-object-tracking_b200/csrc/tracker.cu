@@ -788,17 +788,53 @@ struct OutPtrs {
   float* targets; double* vandyaw; int* track_manage; uint8_t* is_static; uint8_t* is_vis; float* vis_bb; int* hdr; float* boxes;
 };
 
+// per-track outputs of one track (:995-1041) + static flag (:1045-1081) into the frame's result block; returns isVisBB
+__device__ __forceinline__ int emit_track(TrackState& t, int i, double ego_yaw, const OutPtrs& o, double2* __restrict__ pos) {
+  const double tx = t.x[0][0], ty = t.x[0][1];
+  const double mx = t.initMeas[0], my = t.initMeas[1];
+  t.distFromInit = sqrt((tx - mx) * (tx - mx) + (ty - my) * (ty - my));
+  double tyaw = t.x[0][3];
+  tyaw += ego_yaw;
+  tyaw = wrap_pi(tyaw);
+  o.targets[3 * i] = (float)tx; o.targets[3 * i + 1] = (float)ty; o.targets[3 * i + 2] = (float)(-1.73 / 2);
+  o.vandyaw[2 * i] = t.x[0][2]; o.vandyaw[2 * i + 1] = tyaw;
+  const int vis = t.isVisBB ? 1 : 0;
+  o.is_vis[i] = (uint8_t)vis;
+  int st = 0;
+  if (t.isStatic) st = 1;
+  else if (t.trackNum == 5 && t.lifetime > 8) {
+    if ((t.distFromInit < 3.0) && (t.modeProb[2] > t.modeProb[0] || t.modeProb[2] > t.modeProb[1])) { st = 1; t.isStatic = 1; }
+  }
+  o.is_static[i] = (uint8_t)st;
+  o.track_manage[i] = t.trackNum;
+  pos[i] = make_double2(tx, ty);
+  return vis;
+}
+
+// TC.  The track table only ever grows (dead tracks keep their slot, like targets_), and the reference re-emits every track
+// every frame.  Everything here that walks the table does so through coalesced side arrays; everything that touches the
+// 1.6 KB TrackState records is limited to the ACTIVE tracks:
+//   * the per-track outputs of a dead track never change, so the frame's result block starts as a copy of the previous
+//     frame's block (device to device, 34 B per track, coalesced) and only active / new tracks are re-emitted;
+//   * mergeOverSegmentation needs the position of EVERY track (dead ones included, like the reference): `pos`, a packed
+//     double2 per track, refreshed for the active tracks only.
+// `full` (first step after the table was written from the host): everything is rebuilt from the records.
 __global__ void __launch_bounds__(1024)
 spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int* __restrict__ det, const float* __restrict__ boxes,
-                    int* __restrict__ first_setter, int* __restrict__ imax_arr, int* __restrict__ live_list, int* __restrict__ vis_list,
+                    int* __restrict__ first_setter, int* __restrict__ imax_arr, int* __restrict__ vis_list,
                     uint8_t* __restrict__ has5_arr, int first_frame, int compat_first, double ego_yaw, int max_tracks, OutPtrs o,
-                    int* __restrict__ act_list) {
-  __shared__ int s_warp[32];
-  __shared__ int s_carry;
+                    OutPtrs prev, int full, int* __restrict__ act_list, double2* __restrict__ pos) {
+  __shared__ int s_warp[32], s_warp2[32];
+  __shared__ int s_carry, s_carry2, s_nvis;
+  __shared__ __align__(16) float s_bx[kVisChunk][8];
+  __shared__ __align__(16) float s_ab[kVisChunk][4];
+  __shared__ int s_vid[kVisChunk];
+  __shared__ unsigned char s_h5[kVisChunk];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T0 = trk[CNT_N_TRACKS];
+  const int n_act0 = trk[CNT_N_ACT];
   const int M = det[CNT_N_BOXES];
-  if (tid == 0) s_carry = 0;
+  if (tid == 0) { s_carry = 0; s_carry2 = 0; s_nvis = 0; }
   __syncthreads();
 
   if (first_frame && compat_first) {
@@ -809,6 +845,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
         ukf_initialize(tracks[0], -1.5125, -8.975);
         o.targets[0] = (float)-1.5125; o.targets[1] = (float)-8.975; o.targets[2] = (float)(-1.73 / 2);
         o.vandyaw[0] = 0; o.vandyaw[1] = 0; o.is_static[0] = 0; o.is_vis[0] = 0; o.track_manage[0] = 1;
+        pos[0] = make_double2(-1.5125, -8.975);
         T = 1;
       }
       trk[CNT_N_TRACKS] = T; trk[CNT_N_VIS] = 0; trk[CNT_N_ACT] = T; act_list[0] = 0;
@@ -822,56 +859,78 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   }
   for (int e = tid; e < M * 24; e += 1024) o.boxes[e] = boxes[e];     // the frame's box list travels with its results
 
+  // ---- start the frame's result block from the previous one (dead tracks: unchanged), refresh the positions of the
+  // active tracks, collect the visible ones (a subset of the active list, which is sorted by track index)
+  if (!full && prev.targets != o.targets) {
+    for (int e = tid; e < (T0 * 12 + 15) / 16; e += 1024) reinterpret_cast<uint4*>(o.targets)[e] = reinterpret_cast<const uint4*>(prev.targets)[e];
+    for (int e = tid; e < T0; e += 1024) reinterpret_cast<uint4*>(o.vandyaw)[e] = reinterpret_cast<const uint4*>(prev.vandyaw)[e];
+    for (int e = tid; e < (T0 * 4 + 15) / 16; e += 1024) reinterpret_cast<uint4*>(o.track_manage)[e] = reinterpret_cast<const uint4*>(prev.track_manage)[e];
+    for (int e = tid; e < (T0 + 15) / 16; e += 1024) {
+      reinterpret_cast<uint4*>(o.is_static)[e] = reinterpret_cast<const uint4*>(prev.is_static)[e];
+      reinterpret_cast<uint4*>(o.is_vis)[e] = reinterpret_cast<const uint4*>(prev.is_vis)[e];
+    }
+  }
+  const int n_scan = full ? T0 : n_act0;       // entries to visit: the whole table, or the active list
+  for (int q0 = 0; q0 < n_scan; q0 += 1024) {
+    const int q = q0 + tid;
+    int vis = 0, k = 0;
+    if (q < n_scan) {
+      k = full ? q : act_list[q];
+      const TrackState& t = tracks[k];
+      pos[k] = make_double2(t.x[0][0], t.x[0][1]);
+      vis = t.isVisBB ? 1 : 0;
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, vis);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int wbase = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) { if (w < warp) wbase += s_warp[w]; tot += s_warp[w]; }
+    if (vis) vis_list[s_nvis + wbase + __popc(bal & ((1u << lane) - 1u))] = k;
+    __syncthreads();
+    if (tid == 0) s_nvis += tot;
+    __syncthreads();
+  }
+  const int nv = s_nvis;
+
   // ---- mergeOverSegmentation (:666-700), folded into this kernel.  The sequential double loop writes trackNum[i]=5,
   // trackNum[j]=0 for every hit (i,j) with i visible; the value that survives at index k is the write with the largest
   // (i,j) key: 0 if some visible i > k contains k, else 5 if k (visible) contains anybody, else unchanged.  Both facts come
   // from ONE predicate, "visible box i contains the position of track j" (dead j included, like the reference): thread =
-  // track j, the visible boxes (a few dozen) are staged in shared memory with their bounds and read as broadcasts.
-  {
-    __shared__ int s_nvis;
-    __shared__ __align__(16) float s_bx[kVisChunk][8];
-    __shared__ __align__(16) float s_ab[kVisChunk][4];
-    __shared__ int s_vid[kVisChunk];
-    __shared__ unsigned char s_h5[kVisChunk];
-    if (tid == 0) s_nvis = 0;
+  // track j (its position from the packed array), the visible boxes (a few dozen) are staged in shared memory with their
+  // bounds and read as broadcasts.
+  for (int v0 = 0; v0 < nv; v0 += kVisChunk) {
+    const int nc = min(kVisChunk, nv - v0);
+    for (int e = tid; e < nc * 8; e += 1024) { const int v = e >> 3, q = e & 7; s_bx[v][q] = tracks[vis_list[v0 + v]].BBox[q >> 1][q & 1]; }
     __syncthreads();
-    for (int k0 = 0; k0 < T0; k0 += 1024) {            // list of visible tracks (order is irrelevant here)
-      const int k = k0 + tid;
-      if (k < T0 && tracks[k].isVisBB) vis_list[atomicAdd(&s_nvis, 1)] = k;
+    for (int v = tid; v < nc; v += 1024) {
+      const float* c = s_bx[v];
+      s_ab[v][0] = fminf(fminf(c[0], c[2]), fminf(c[4], c[6])); s_ab[v][1] = fmaxf(fmaxf(c[0], c[2]), fmaxf(c[4], c[6]));
+      s_ab[v][2] = fminf(fminf(c[1], c[3]), fminf(c[5], c[7])); s_ab[v][3] = fmaxf(fmaxf(c[1], c[3]), fmaxf(c[5], c[7]));
+      s_vid[v] = vis_list[v0 + v]; s_h5[v] = 0;
     }
     __syncthreads();
-    const int nv = s_nvis;
-    for (int v0 = 0; v0 < nv; v0 += kVisChunk) {
-      const int nc = min(kVisChunk, nv - v0);
-      for (int e = tid; e < nc * 8; e += 1024) { const int v = e >> 3, q = e & 7; s_bx[v][q] = tracks[vis_list[v0 + v]].BBox[q >> 1][q & 1]; }
-      __syncthreads();
-      for (int v = tid; v < nc; v += 1024) {
-        const float* c = s_bx[v];
-        s_ab[v][0] = fminf(fminf(c[0], c[2]), fminf(c[4], c[6])); s_ab[v][1] = fmaxf(fmaxf(c[0], c[2]), fmaxf(c[4], c[6]));
-        s_ab[v][2] = fminf(fminf(c[1], c[3]), fminf(c[5], c[7])); s_ab[v][3] = fmaxf(fmaxf(c[1], c[3]), fmaxf(c[5], c[7]));
-        s_vid[v] = vis_list[v0 + v]; s_h5[v] = 0;
-      }
-      __syncthreads();
-      for (int j0 = 0; j0 < T0; j0 += 1024) {
-        const int j = j0 + tid;
-        if (j < T0) {
-          const double px = tracks[j].x[0][0], py = tracks[j].x[0][1];
-          int imax = (v0 == 0) ? -1 : imax_arr[j];
-          for (int v = 0; v < nc; ++v) {
-            const int i = s_vid[v];
-            if (i != j && overseg_cond(s_bx[v], s_ab[v], px, py)) { s_h5[v] = 1; imax = max(imax, i); }
-          }
-          imax_arr[j] = imax;
+    for (int j0 = 0; j0 < T0; j0 += 1024) {
+      const int j = j0 + tid;
+      if (j < T0) {
+        const double2 pj = pos[j];
+        int imax = (v0 == 0) ? -1 : imax_arr[j];
+        for (int v = 0; v < nc; ++v) {
+          const int i = s_vid[v];
+          if (i != j && overseg_cond(s_bx[v], s_ab[v], pj.x, pj.y)) { s_h5[v] = 1; imax = max(imax, i); }
         }
+        imax_arr[j] = imax;
       }
-      __syncthreads();
-      for (int v = tid; v < nc; v += 1024) has5_arr[s_vid[v]] = s_h5[v];
-      __syncthreads();
     }
-    if (nv > 0) {
-      for (int k0 = 0; k0 < T0; k0 += 1024) {
-        const int k = k0 + tid;
-        if (k < T0 && tracks[k].trackNum != 0) {
+    __syncthreads();
+    for (int v = tid; v < nc; v += 1024) has5_arr[s_vid[v]] = s_h5[v];
+    __syncthreads();
+  }
+  if (nv > 0) {       // only live tracks can change (0 -> 0 is a no-op, 5 needs a visible, hence live, track)
+    for (int q0 = 0; q0 < n_scan; q0 += 1024) {
+      const int q = q0 + tid;
+      if (q < n_scan) {
+        const int k = full ? q : act_list[q];
+        if (tracks[k].trackNum != 0) {
           const int imax = imax_arr[k];
           const bool has5 = tracks[k].isVisBB && has5_arr[k] != 0;
           if (imax >= 0 && (!has5 || imax > k)) tracks[k].trackNum = 0;
@@ -879,10 +938,10 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
         }
       }
     }
-    __syncthreads();
   }
+  __syncthreads();
 
-  // spawn one UKF per unmatched box, in box order (:972-989)
+  // ---- spawn one UKF per unmatched box, in box order (:972-989)
   for (int b0 = 0; b0 < M; b0 += 1024) {
     const int b = b0 + tid;
     const int un = (b < M && first_setter[b] == INT_MAX) ? 1 : 0;
@@ -891,11 +950,11 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
     __syncthreads();
     int wbase = 0, tot = 0;
     for (int w = 0; w < 32; ++w) { if (w < warp) wbase += s_warp[w]; tot += s_warp[w]; }
-    const int pos = T0 + s_carry + wbase + __popc(bal & ((1u << lane) - 1u));
-    if (un && pos < max_tracks) {
+    const int p = T0 + s_carry + wbase + __popc(bal & ((1u << lane) - 1u));
+    if (un && p < max_tracks) {
       double cx, cy;
       cp_from_box(boxes + (size_t)b * 24, cx, cy);
-      ukf_initialize(tracks[pos], cx, cy);
+      ukf_initialize(tracks[p], cx, cy);
     }
     if (b < M) first_setter[b] = INT_MAX;        // ready for the next frame
     __syncthreads();
@@ -908,33 +967,17 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   if (tid == 0) s_carry = 0;
   __syncthreads();
 
-  // outputs (:995-1081), one coalesced pass over the table; the list of tracks the next frame has to visit falls out of it
-  __shared__ int s_warp2[32];
-  __shared__ int s_carry2;
-  if (tid == 0) s_carry2 = 0;
-  __syncthreads();
-  for (int i0 = 0; i0 < T; i0 += 1024) {
-    const int i = i0 + tid;
-    int vis = 0, act = 0;
-    if (i < T) {
+  // ---- outputs (:995-1081) of the active and the new tracks, visible boxes in track order, next frame's active list
+  // (stable in-place compaction: a tile is read completely before anything at or below its range is written)
+  const int n_new = T - T0;
+  const int n_emit = n_scan + n_new;
+  for (int q0 = 0; q0 < n_emit; q0 += 1024) {
+    const int q = q0 + tid;
+    int vis = 0, act = 0, i = 0;
+    if (q < n_emit) {
+      i = (q < n_scan) ? (full ? q : act_list[q]) : T0 + (q - n_scan);
       TrackState& t = tracks[i];
-      const double tx = t.x[0][0], ty = t.x[0][1];
-      const double mx = t.initMeas[0], my = t.initMeas[1];
-      t.distFromInit = sqrt((tx - mx) * (tx - mx) + (ty - my) * (ty - my));
-      double tyaw = t.x[0][3];
-      tyaw += ego_yaw;
-      tyaw = wrap_pi(tyaw);
-      o.targets[3 * i] = (float)tx; o.targets[3 * i + 1] = (float)ty; o.targets[3 * i + 2] = (float)(-1.73 / 2);
-      o.vandyaw[2 * i] = t.x[0][2]; o.vandyaw[2 * i + 1] = tyaw;
-      vis = t.isVisBB ? 1 : 0;
-      o.is_vis[i] = (uint8_t)vis;
-      int st = 0;
-      if (t.isStatic) st = 1;
-      else if (t.trackNum == 5 && t.lifetime > 8) {
-        if ((t.distFromInit < 3.0) && (t.modeProb[2] > t.modeProb[0] || t.modeProb[2] > t.modeProb[1])) { st = 1; t.isStatic = 1; }
-      }
-      o.is_static[i] = (uint8_t)st;
-      o.track_manage[i] = t.trackNum;
+      vis = emit_track(t, i, ego_yaw, o, pos);
       act = (t.trackNum != 0 || vis) ? 1 : 0;
     }
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, vis), bala = __ballot_sync(0xFFFFFFFFu, act);
@@ -943,10 +986,10 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
     int wbase = 0, tot = 0, wbase2 = 0, tot2 = 0;
     for (int w = 0; w < 32; ++w) { if (w < warp) { wbase += s_warp[w]; wbase2 += s_warp2[w]; } tot += s_warp[w]; tot2 += s_warp2[w]; }
     if (act) act_list[s_carry2 + wbase2 + __popc(bala & ((1u << lane) - 1u))] = i;
-    if (vis) {      // boxes of the visible tracks, in track order
-      const int pos = s_carry + wbase + __popc(bal & ((1u << lane) - 1u));
+    if (vis) {
+      const int p = s_carry + wbase + __popc(bal & ((1u << lane) - 1u));
       const float2* src = reinterpret_cast<const float2*>(&tracks[i].BBox[0][0]);
-      float2* dst = reinterpret_cast<float2*>(o.vis_bb + (size_t)pos * 24);
+      float2* dst = reinterpret_cast<float2*>(o.vis_bb + (size_t)p * 24);
 #pragma unroll
       for (int e = 0; e < 12; ++e) dst[e] = src[e];
     }
@@ -1020,6 +1063,9 @@ int tracker_alloc(Ctx* c) {
   LMOT_CUDA(c, cudaMalloc(&c->d_live_list, (size_t)TC * sizeof(int)));
   LMOT_CUDA(c, cudaMalloc(&c->d_vis_list, (size_t)TC * sizeof(int)));
   LMOT_CUDA(c, cudaMalloc(&c->d_act_list, (size_t)TC * sizeof(int)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_pos, (size_t)TC * sizeof(double2)));
+  LMOT_CUDA(c, cudaMemsetAsync(c->d_pos, 0, (size_t)TC * sizeof(double2), c->trk_stream));
+  c->last_trk_res = nullptr;
   c->act_valid = false;
   fill_int_kernel<<<(MB + 255) / 256, 256, 0, c->trk_stream>>>(c->d_first_setter, MB, INT_MAX);
   LMOT_CUDA(c, cudaGetLastError());
@@ -1030,7 +1076,7 @@ int tracker_alloc(Ctx* c) {
 
 void tracker_free(Ctx* c) {
   cudaFree(c->d_tracks); cudaFree(c->d_trk_counters); cudaFree(c->d_gate); cudaFree(c->d_setter); cudaFree(c->d_first_setter);
-  cudaFree(c->d_skip); cudaFree(c->d_new_num); cudaFree(c->d_live_list); cudaFree(c->d_vis_list); cudaFree(c->d_act_list);
+  cudaFree(c->d_skip); cudaFree(c->d_new_num); cudaFree(c->d_live_list); cudaFree(c->d_vis_list); cudaFree(c->d_act_list); cudaFree(c->d_pos);
   if (c->h_trk_counters) cudaFreeHost(c->h_trk_counters);
 }
 
@@ -1071,11 +1117,15 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
   int* det = const_cast<int*>(det_counters);
   const int first = h.init ? 0 : 1;
   const int compat = c->prm.oracle_compat_first_frame ? 1 : 0;
-  if (!c->act_valid) {      // the table was written from the host since the last frame
+  const int full = c->act_valid ? 0 : 1;   // the table was written from the host since the last frame: rebuild the side arrays
+  if (full) {
     LMOT_CUDA(c, cudaMemsetAsync(c->d_trk_counters + CNT_N_ACT, 0, sizeof(int), st));
     build_active_kernel<<<(c->prm.max_tracks + 255) / 256, 256, 0, st>>>(c->d_tracks, c->d_trk_counters, c->d_act_list);
     c->act_valid = true;
   }
+  Result* pr = (full || !c->last_trk_res) ? r : c->last_trk_res;
+  OutPtrs po{pr->d_targets, pr->d_vandyaw, pr->d_manage, pr->d_static, pr->d_vis, pr->d_visbb, pr->d_hdr, pr->d_boxes};
+  c->last_trk_res = r;
   if (!(first && compat)) {
     const double dt = first ? 0.0 : (timestamp - h.timestamp) / 1000000.0;     // :807
     const size_t sh = (size_t)kTBWarps * c->gate_words * 32 * sizeof(unsigned short);
@@ -1086,8 +1136,8 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
                                                                            c->d_first_setter, c->d_skip, c->gate_words, c->d_act_list);
     kernel_mark(c, sl, st);
   }
-  spawn_output_kernel<<<1, 1024, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_first_setter, c->d_new_num, c->d_live_list,
-                                          c->d_vis_list, c->d_skip, first, compat, h.egoPoint[2], c->prm.max_tracks, o, c->d_act_list);
+  spawn_output_kernel<<<1, 1024, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_first_setter, c->d_new_num, c->d_vis_list,
+                                          c->d_skip, first, compat, h.egoPoint[2], c->prm.max_tracks, o, po, full, c->d_act_list, c->d_pos);
   kernel_mark(c, sl, st);
   LMOT_CUDA(c, cudaGetLastError());
   h.timestamp = timestamp;
