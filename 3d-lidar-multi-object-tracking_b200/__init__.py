@@ -75,7 +75,7 @@ class FrameOut(C.Structure):
 # every symbol include/lmot.h declares (tests assert the library exports all of them)
 ABI_SYMBOLS = [
     "lmot_default_params", "lmot_create", "lmot_destroy", "lmot_strerror", "lmot_last_error", "lmot_build_info",
-    "lmot_set_stream", "lmot_ground_remove", "lmot_component_cluster", "lmot_box_fit", "lmot_track_step", "lmot_frame",
+    "lmot_set_stream", "lmot_ground_remove", "lmot_component_cluster", "lmot_cluster_outputs", "lmot_box_fit", "lmot_track_step", "lmot_frame",
     "lmot_frame_dev", "lmot_frame_fetch", "lmot_frame_submit", "lmot_frame_collect", "lmot_frames_in_flight", "lmot_frame_ready", "lmot_flush",
     "lmot_ground_remove_dev", "lmot_detect_dev", "lmot_sync",
     "lmot_origin_points", "lmot_tracker_table", "lmot_tracker_set_num_tracks", "lmot_tracker_reset", "lmot_tracker_num_tracks", "lmot_tracker_dump", "lmot_tracker_load",
@@ -168,6 +168,15 @@ class Lmot:
 
     def ground_remove_dev(self, d_ptr: int, n: int):
         self._chk(self.lib.lmot_ground_remove_dev(self.h, C.c_void_p(d_ptr), n))
+
+    def cluster_outputs(self, cap: int | None = None):
+        """Side outputs of the cluster node for the last clustering: (clustered (n,4), obstacles (m,4) [x,y,z,cluster], cost_map (50,50))"""
+        cap = cap or int(self.params.max_points)
+        cl = np.zeros((cap, 4), np.float32); ob = np.zeros((62500, 4), np.float32); cm = np.zeros(2500, np.int32)
+        ncl = C.c_int(0); nob = C.c_int(0)
+        self._chk(self.lib.lmot_cluster_outputs(self.h, _fp(cl), cap, C.byref(ncl), _fp(ob), 62500, C.byref(nob),
+                                                cm.ctypes.data_as(C.POINTER(C.c_int32))))
+        return cl[: ncl.value].copy(), ob[: nob.value].copy(), cm.reshape(50, 50)
 
     # ---- componentClustering ------------------------------------------------------------------------------
     def component_cluster(self, elevated):

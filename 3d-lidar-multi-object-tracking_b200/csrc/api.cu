@@ -473,6 +473,30 @@ int lmot_component_cluster(lmot_ctx* ctx, const float* elevated, int n, int stri
   return LMOT_OK;
 }
 
+// the cluster node's side outputs for the elevated cloud + label grid of the most recent clustering of this context
+int lmot_cluster_outputs(lmot_ctx* ctx, float* clustered, int cap_clustered, int* n_clustered, float* obstacles, int cap_obstacles,
+                         int* n_obstacles, int32_t* cost_map) {
+  if (!ctx || cap_clustered < 0 || cap_obstacles < 0) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  int rc = lmot_sync(ctx);
+  if (rc) return rc;
+  Slot* s = &c->slots[c->last_slot];
+  cudaStream_t st = c->stream;
+  if ((rc = cluster_outputs_launch(c, s, st))) return rc;
+  int cnt[2] = {0, 0};
+  LMOT_CUDA(c, cudaMemcpyAsync(cnt, s->d_cost_map + 2500, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (cost_map) LMOT_CUDA(c, cudaMemcpyAsync(cost_map, s->d_cost_map, 2500 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  LMOT_CUDA(c, cudaStreamSynchronize(st));
+  if (n_clustered) *n_clustered = cnt[0];
+  if (n_obstacles) *n_obstacles = cnt[1];
+  const int nc = cnt[0] < cap_clustered ? cnt[0] : cap_clustered, no = cnt[1] < cap_obstacles ? cnt[1] : cap_obstacles;
+  if (clustered && nc > 0) LMOT_CUDA(c, cudaMemcpyAsync(clustered, s->d_clustered, (size_t)nc * 16, cudaMemcpyDeviceToHost, st));
+  if (obstacles && no > 0) LMOT_CUDA(c, cudaMemcpyAsync(obstacles, s->d_obstacles, (size_t)no * 16, cudaMemcpyDeviceToHost, st));
+  LMOT_CUDA(c, cudaStreamSynchronize(st));
+  return (cnt[0] > cap_clustered && clustered) || (cnt[1] > cap_obstacles && obstacles) ? LMOT_ERR_CAPACITY : LMOT_OK;
+}
+
 int lmot_debug_label_grid(lmot_ctx* ctx, int32_t* grid, int* num_cluster) {
   if (!ctx) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;

@@ -126,6 +126,11 @@ struct Slot {
   unsigned* d_cart_bits = nullptr;     // [3][2000] bit planes of the 250x250 grid (8 words per row): cells seen once | cells
                                        // seen more than once (re-armed by the CCL kernel) | occupancy of the previous frame
   int* d_label_grid = nullptr;         // [62500] final labels (0 = empty), x-major; updated sparsely from frame to frame
+  // side outputs of the cluster node (allocated on first use by lmot_cluster_outputs)
+  int* d_first_idx = nullptr;          // [62500] scratch: first point of each labelled cell, INT_MAX at rest
+  float4* d_clustered = nullptr;       // makeClusteredCloud
+  float4* d_obstacles = nullptr;       // setObsMsg: x, y, z, cluster id
+  int* d_cost_map = nullptr;           // [2500] createCostMap, then the two output counts
   bool label_grid_foreign = false;     // the caller uploaded its own grid (lmot_box_fit): next clustering starts from zero
 
   // ---- box fitting
@@ -183,7 +188,7 @@ struct Ctx {
   cudaStream_t trk_stream = nullptr;
   cudaStream_t pub_stream = nullptr;   // device -> host publication of finished frames
   int* d_act_list = nullptr;           // [max_tracks] tracks to visit next frame (built by spawn_output_kernel)
-  double2* d_pos = nullptr;            // [max_tracks] packed (x, y) of every track's merged state, for mergeOverSegmentation
+  double4* d_pos = nullptr;            // [max_tracks] packed (x, y, yaw, -) of every track's merged state
   Result* last_trk_res = nullptr;      // result block of the previous tracker step (its device copy seeds the next one)
   bool act_valid = false;              // false after the table was written from the host: rebuilt before the next step
   int trk_ctas = 592, gate_words = 0;
@@ -246,7 +251,8 @@ int ground_repack(Ctx* c, cudaStream_t st, const float* d_in, int n, int stride,
 int cluster_alloc(Ctx* c, Slot* s);
 void cluster_free(Slot* s);
 int cluster_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper, bool counted = false);
-int cluster_cells_only(Ctx* c, Slot* s, cudaStream_t st, int n_upper);  // d_cart for a cloud whose label grid comes from the caller
+int cluster_cells_only(Ctx* c, Slot* s, cudaStream_t st, int n_upper);
+int cluster_outputs_launch(Ctx* c, Slot* s, cudaStream_t st);      // makeClusteredCloud / setObsMsg / createCostMap  // d_cart for a cloud whose label grid comes from the caller
 int boxfit_alloc(Ctx* c, Slot* s);
 int boxfit_alloc_shared(Ctx* c);
 void boxfit_free(Slot* s);

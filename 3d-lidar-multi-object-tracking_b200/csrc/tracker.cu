@@ -789,7 +789,7 @@ struct OutPtrs {
 };
 
 // per-track outputs of one track (:995-1041) + static flag (:1045-1081) into the frame's result block; returns isVisBB
-__device__ __forceinline__ int emit_track(TrackState& t, int i, double ego_yaw, const OutPtrs& o, double2* __restrict__ pos) {
+__device__ __forceinline__ int emit_track(TrackState& t, int i, double ego_yaw, const OutPtrs& o, double4* __restrict__ pos) {
   const double tx = t.x[0][0], ty = t.x[0][1];
   const double mx = t.initMeas[0], my = t.initMeas[1];
   t.distFromInit = sqrt((tx - mx) * (tx - mx) + (ty - my) * (ty - my));
@@ -807,7 +807,7 @@ __device__ __forceinline__ int emit_track(TrackState& t, int i, double ego_yaw, 
   }
   o.is_static[i] = (uint8_t)st;
   o.track_manage[i] = t.trackNum;
-  pos[i] = make_double2(tx, ty);
+  pos[i] = make_double4(tx, ty, t.x[0][3], 0.0);
   return vis;
 }
 
@@ -816,14 +816,16 @@ __device__ __forceinline__ int emit_track(TrackState& t, int i, double ego_yaw, 
 // 1.6 KB TrackState records is limited to the ACTIVE tracks:
 //   * the per-track outputs of a dead track never change, so the frame's result block starts as a copy of the previous
 //     frame's block (device to device, 34 B per track, coalesced) and only active / new tracks are re-emitted;
-//   * mergeOverSegmentation needs the position of EVERY track (dead ones included, like the reference): `pos`, a packed
-//     double2 per track, refreshed for the active tracks only.
+//   * mergeOverSegmentation needs the position of EVERY track (dead ones included, like the reference), and the output yaw
+//     of every track is its state's yaw plus THIS frame's ego yaw: `pos`, a packed (x, y, yaw) per track, refreshed for the
+//     active tracks only.
 // `full` (first step after the table was written from the host): everything is rebuilt from the records.
 __global__ void __launch_bounds__(1024)
 spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int* __restrict__ det, const float* __restrict__ boxes,
                     int* __restrict__ first_setter, int* __restrict__ imax_arr, int* __restrict__ vis_list,
                     uint8_t* __restrict__ has5_arr, int first_frame, int compat_first, double ego_yaw, int max_tracks, OutPtrs o,
-                    OutPtrs prev, int full, int* __restrict__ act_list, double2* __restrict__ pos) {
+                    OutPtrs prev, int full, int* __restrict__ act_list, double4* __restrict__ pos, unsigned long long* __restrict__ trace) {
+  if (trace && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[0] = t; }
   __shared__ int s_warp[32], s_warp2[32];
   __shared__ int s_carry, s_carry2, s_nvis;
   __shared__ __align__(16) float s_bx[kVisChunk][8];
@@ -845,7 +847,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
         ukf_initialize(tracks[0], -1.5125, -8.975);
         o.targets[0] = (float)-1.5125; o.targets[1] = (float)-8.975; o.targets[2] = (float)(-1.73 / 2);
         o.vandyaw[0] = 0; o.vandyaw[1] = 0; o.is_static[0] = 0; o.is_vis[0] = 0; o.track_manage[0] = 1;
-        pos[0] = make_double2(-1.5125, -8.975);
+        pos[0] = make_double4(-1.5125, -8.975, 0.0, 0.0);
         T = 1;
       }
       trk[CNT_N_TRACKS] = T; trk[CNT_N_VIS] = 0; trk[CNT_N_ACT] = T; act_list[0] = 0;
@@ -863,7 +865,10 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   // active tracks, collect the visible ones (a subset of the active list, which is sorted by track index)
   if (!full && prev.targets != o.targets) {
     for (int e = tid; e < (T0 * 12 + 15) / 16; e += 1024) reinterpret_cast<uint4*>(o.targets)[e] = reinterpret_cast<const uint4*>(prev.targets)[e];
-    for (int e = tid; e < T0; e += 1024) reinterpret_cast<uint4*>(o.vandyaw)[e] = reinterpret_cast<const uint4*>(prev.vandyaw)[e];
+    for (int e = tid; e < T0; e += 1024) {      // v is the state's; the yaw is re-offset by THIS frame's ego yaw for every track (:1004-1008)
+      o.vandyaw[2 * e] = prev.vandyaw[2 * e];
+      o.vandyaw[2 * e + 1] = wrap_pi(pos[e].z + ego_yaw);
+    }
     for (int e = tid; e < (T0 * 4 + 15) / 16; e += 1024) reinterpret_cast<uint4*>(o.track_manage)[e] = reinterpret_cast<const uint4*>(prev.track_manage)[e];
     for (int e = tid; e < (T0 + 15) / 16; e += 1024) {
       reinterpret_cast<uint4*>(o.is_static)[e] = reinterpret_cast<const uint4*>(prev.is_static)[e];
@@ -877,7 +882,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
     if (q < n_scan) {
       k = full ? q : act_list[q];
       const TrackState& t = tracks[k];
-      pos[k] = make_double2(t.x[0][0], t.x[0][1]);
+      pos[k] = make_double4(t.x[0][0], t.x[0][1], t.x[0][3], 0.0);
       vis = t.isVisBB ? 1 : 0;
     }
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, vis);
@@ -912,7 +917,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
     for (int j0 = 0; j0 < T0; j0 += 1024) {
       const int j = j0 + tid;
       if (j < T0) {
-        const double2 pj = pos[j];
+        const double4 pj = pos[j];
         int imax = (v0 == 0) ? -1 : imax_arr[j];
         for (int v = 0; v < nc; ++v) {
           const int i = s_vid[v];
@@ -1002,6 +1007,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
     o.hdr[HDR_N_ELEV] = det[CNT_N_ELEV]; o.hdr[HDR_N_GROUND] = det[CNT_N_GROUND]; o.hdr[HDR_NUM_CLUSTER] = det[CNT_NUM_CLUSTER];
     o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = s_carry; o.hdr[HDR_ERROR] = det[CNT_ERROR];
     det[CNT_ERROR] = 0;
+    if (trace) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[1] = t; trace[2] = (unsigned long long)T; trace[3] = (unsigned long long)nv; }
   }
 }
 
@@ -1063,8 +1069,8 @@ int tracker_alloc(Ctx* c) {
   LMOT_CUDA(c, cudaMalloc(&c->d_live_list, (size_t)TC * sizeof(int)));
   LMOT_CUDA(c, cudaMalloc(&c->d_vis_list, (size_t)TC * sizeof(int)));
   LMOT_CUDA(c, cudaMalloc(&c->d_act_list, (size_t)TC * sizeof(int)));
-  LMOT_CUDA(c, cudaMalloc(&c->d_pos, (size_t)TC * sizeof(double2)));
-  LMOT_CUDA(c, cudaMemsetAsync(c->d_pos, 0, (size_t)TC * sizeof(double2), c->trk_stream));
+  LMOT_CUDA(c, cudaMalloc(&c->d_pos, (size_t)TC * sizeof(double4)));
+  LMOT_CUDA(c, cudaMemsetAsync(c->d_pos, 0, (size_t)TC * sizeof(double4), c->trk_stream));
   c->last_trk_res = nullptr;
   c->act_valid = false;
   fill_int_kernel<<<(MB + 255) / 256, 256, 0, c->trk_stream>>>(c->d_first_setter, MB, INT_MAX);
@@ -1137,7 +1143,7 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
     kernel_mark(c, sl, st);
   }
   spawn_output_kernel<<<1, 1024, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_first_setter, c->d_new_num, c->d_vis_list,
-                                          c->d_skip, first, compat, h.egoPoint[2], c->prm.max_tracks, o, po, full, c->d_act_list, c->d_pos);
+                                          c->d_skip, first, compat, h.egoPoint[2], c->prm.max_tracks, o, po, full, c->d_act_list, c->d_pos, c->d_phase_clock);
   kernel_mark(c, sl, st);
   LMOT_CUDA(c, cudaGetLastError());
   h.timestamp = timestamp;

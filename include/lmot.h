@@ -126,6 +126,16 @@ int lmot_ground_remove(lmot_ctx* ctx, const float* points, int n, int stride_flo
 int lmot_component_cluster(lmot_ctx* ctx, const float* elevated, int n, int stride_floats, int32_t* grid,
                            int* num_cluster);
 
+/* The cluster node's side outputs (src/cluster/main.cpp:62-99) for the elevated cloud and label grid of the most recent
+ * lmot_component_cluster / lmot_frame of this context (synchronous; call it before submitting further frames):
+ *   clustered  <- makeClusteredCloud  component_clustering.cpp:308-335   float[cap][4] (cell centre x, y, -1, 1), cloud order
+ *   obstacles  <- setObsMsg           component_clustering.cpp:337-375   float[cap][4] (cell centre x, y, -1, cluster id):
+ *                                      ONE obstacle per labelled cell that holds a point, in order of its first point
+ *   cost_map   <- createCostMap       component_clustering.cpp:425-454   int32[50*50], row = y cell, column = x cell
+ * all nullable; LMOT_ERR_CAPACITY if a requested list does not fit (the counts are still returned). */
+int lmot_cluster_outputs(lmot_ctx* ctx, float* clustered, int cap_clustered, int* n_clustered, float* obstacles, int cap_obstacles,
+                         int* n_obstacles, int32_t* cost_map);
+
 /* boxFitting.  boxes = float[max_boxes*8*3] (4 bottom corners z=-sensor_height, then 4 top corners z=maxZ,
  * box_fitting.cpp:379-389), in cluster-id order.  markers (nullable) = float[max_boxes*6]: centroid xyz and
  * AABB extent xyz of the cluster (mark_cluster, box_fitting.cpp:161-209). */

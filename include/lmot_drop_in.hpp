@@ -12,6 +12,7 @@
 //
 //   groundRemove         object_tracking/include/ground_removal.h:62-64
 //   componentClustering  object_tracking/include/component_clustering.h:20-22
+//   makeClusteredCloud / setObsMsg / createCostMap   object_tracking/include/component_clustering.h:27-37
 //   boxFitting           object_tracking/include/box_fitting.h:34-36
 //   getOriginPoints      object_tracking/include/imm_ukf_jpda.h:15
 //   immUkfJpdaf          object_tracking/include/imm_ukf_jpda.h:19-22
@@ -80,6 +81,41 @@ void componentClustering(CloudPtr elevatedCloud, CartesianGrid& cartesianData, i
   static_assert(sizeof(CartesianGrid) == sizeof(int) * numGrid * numGrid, "grid layout");
   check(lmot_component_cluster(context(), detail::data(*elevatedCloud), (int)elevatedCloud->points.size(), 4,
                                reinterpret_cast<int32_t*>(&cartesianData[0][0]), &numCluster), "lmot_component_cluster");
+}
+
+// The cluster node's other topics (src/cluster/main.cpp:62-99).  All three work on the elevated cloud and label grid the
+// context still holds from the componentClustering call just above them in the callback (the arguments are the reference's
+// and must be that cloud / that grid; they are not uploaded again).
+// void makeClusteredCloud(Ptr& elevatedCloud, array<...> cartesianData, Ptr& clusterCloud)   component_clustering.h:27-29
+template <class CloudPtr>
+void makeClusteredCloud(CloudPtr& elevatedCloud, const CartesianGrid&, CloudPtr& clusterCloud) {
+  const int cap = (int)elevatedCloud->points.size();
+  std::vector<float> cl((size_t)(cap > 0 ? cap : 1) * 4);
+  int n = 0;
+  check(lmot_cluster_outputs(context(), cl.data(), cap, &n, nullptr, 0, nullptr, nullptr), "lmot_cluster_outputs");
+  detail::append(*clusterCloud, cl.data(), n);
+}
+// void setObsMsg(Ptr& elevatedCloud, array<...> cartesianData, object_tracking::ObstacleList& clu_obs)   component_clustering.h:35-37
+// ObstacleList: anything with cellLength, cellWidth and `obstacles` (push_back) of elements with x, y, z, cluster
+template <class CloudPtr, class ObstacleList>
+void setObsMsg(CloudPtr& elevatedCloud, const CartesianGrid&, ObstacleList& clu_obs) {
+  std::vector<float> ob((size_t)numGrid * numGrid * 4);
+  int n = 0;
+  check(lmot_cluster_outputs(context(), nullptr, 0, nullptr, ob.data(), numGrid * numGrid, &n, nullptr), "lmot_cluster_outputs");
+  (void)elevatedCloud;
+  for (int i = 0; i < n; ++i) {
+    typename std::remove_reference<decltype(clu_obs.obstacles[0])>::type o{};
+    o.x = ob[4 * i]; o.y = ob[4 * i + 1]; o.z = ob[4 * i + 2]; o.cluster = (int)ob[4 * i + 3];
+    clu_obs.cellLength = 0.2f; clu_obs.cellWidth = 0.2f;       // grid_size, component_clustering.h:15
+    clu_obs.obstacles.push_back(o);
+  }
+}
+// std::vector<int> createCostMap(const pcl::PointCloud<pcl::PointXYZ>& scan)   component_clustering.h:33
+template <class Cloud>
+std::vector<int> createCostMap(const Cloud&) {
+  std::vector<int32_t> cm(50 * 50);
+  check(lmot_cluster_outputs(context(), nullptr, 0, nullptr, nullptr, 0, nullptr, cm.data()), "lmot_cluster_outputs");
+  return std::vector<int>(cm.begin(), cm.end());
 }
 
 // vector<PointCloud<PointXYZ>> boxFitting(Ptr elevatedCloud, array<...> cartesianData, int numCluster, MarkerArray& ma)

@@ -49,6 +49,9 @@ class _OracleBase:
         self._pg = getattr(L, p + "polar_grid"); self._pg.argtypes = [_f32p, C.c_int, C.c_int] + [_f32p] * 5 + [_u8p]
         self._cc = getattr(L, p + "component_clustering"); self._cc.argtypes = [_f32p, C.c_int, C.c_int, _i32p, C.POINTER(C.c_int)]
         self._bf = getattr(L, p + "box_fitting"); self._bf.argtypes = [_f32p, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int), _f32p]
+        self._co = getattr(L, p + "cluster_outputs", None)      # the cluster node's side outputs (reference build only)
+        if self._co is not None:
+            self._co.argtypes = [_f32p, C.c_int, C.c_int, _i32p, C.c_int, _f32p, C.POINTER(C.c_int), _f64p, C.POINTER(C.c_int), _i32p]
         self._tr = getattr(L, p + "tracker_reset"); self._tr.argtypes = []
         self._tn = getattr(L, p + "tracker_num_tracks"); self._tn.restype = C.c_int
         self._ts = getattr(L, p + "tracker_step")
@@ -95,6 +98,17 @@ class _OracleBase:
         boxes = np.zeros((max_boxes, 8, 3), np.float32); markers = np.zeros((max_boxes, 6), np.float32); nb = C.c_int(0)
         self._bf(p, n, s, np.ascontiguousarray(grid, np.int32).reshape(-1), int(num_cluster), max_boxes, boxes, C.byref(nb), markers)
         return boxes[: nb.value].copy(), markers[: nb.value].copy()
+
+    def cluster_outputs(self, elevated, grid):
+        """makeClusteredCloud, setObsMsg, createCostMap -> (clustered (n,3) f32, obstacles (m,4) f64 [x,y,z,cluster], cost_map (50,50) i32)"""
+        if self._co is None:
+            raise RuntimeError("cluster_outputs is only available from the compiled reference (oracle/_ref)")
+        p, n, s = _as_pts(elevated) if len(elevated) else (np.zeros((1, 3), np.float32), 0, 3)
+        cap = max(n, 1)
+        cl = np.zeros((cap, 3), np.float32); ob = np.zeros((cap, 4), np.float64); cm = np.zeros(2500, np.int32)
+        ncl = C.c_int(0); nob = C.c_int(0)
+        self._co(p, n, s, np.ascontiguousarray(grid, np.int32).reshape(-1), cap, cl, C.byref(ncl), ob, C.byref(nob), cm)
+        return cl[: ncl.value].copy(), ob[: nob.value].copy(), cm.reshape(50, 50)
 
     # -- tracker --------------------------------------------------------------------------------
     def tracker_reset(self):

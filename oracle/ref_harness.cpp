@@ -126,6 +126,29 @@ void ref_component_clustering(const float* xyz, int n, int stride, int32_t* grid
   for (int x = 0; x < numGrid; ++x) for (int y = 0; y < numGrid; ++y) grid[x * numGrid + y] = cart[x][y];
 }
 
+// component_clustering.cpp:308-335 makeClusteredCloud, :337-375 setObsMsg, :425-454 createCostMap -- the cluster node's
+// side outputs (src/cluster/main.cpp:62-99).  clustered = float[cap*3]; obstacles = double[cap*4] (x, y, z, cluster);
+// cost_map = int32[50*50].
+void ref_cluster_outputs(const float* xyz, int n, int stride, const int32_t* grid, int cap, float* clustered, int* n_clustered,
+                         double* obstacles, int* n_obstacles, int32_t* cost_map) {
+  Quiet q;
+  PointCloud<PointXYZ>::Ptr cloud = make_cloud(xyz, n, stride);
+  static array<array<int, numGrid>, numGrid> cart;
+  for (int x = 0; x < numGrid; ++x) for (int y = 0; y < numGrid; ++y) cart[x][y] = grid[x * numGrid + y];
+  PointCloud<PointXYZ>::Ptr cc(new PointCloud<PointXYZ>());
+  makeClusteredCloud(cloud, cart, cc);
+  *n_clustered = (int)cc->points.size();
+  for (int i = 0; i < *n_clustered && i < cap; ++i) { clustered[3*i] = cc->points[i].x; clustered[3*i+1] = cc->points[i].y; clustered[3*i+2] = cc->points[i].z; }
+  object_tracking::ObstacleList ol;
+  setObsMsg(cloud, cart, ol);
+  *n_obstacles = (int)ol.obstacles.size();
+  for (int i = 0; i < *n_obstacles && i < cap; ++i) {
+    obstacles[4*i] = ol.obstacles[i].x; obstacles[4*i+1] = ol.obstacles[i].y; obstacles[4*i+2] = ol.obstacles[i].z; obstacles[4*i+3] = ol.obstacles[i].cluster;
+  }
+  std::vector<int> cm = createCostMap(*cloud);
+  for (size_t i = 0; i < cm.size() && i < 2500; ++i) cost_map[i] = cm[i];
+}
+
 // box_fitting.cpp:422 boxFitting.  boxes = float[n_boxes*8*3]; markers = float[n_boxes*6] (centroid xyz, scale xyz)
 void ref_box_fitting(const float* xyz, int n, int stride, const int32_t* grid, int num_cluster, int max_boxes,
                      float* boxes, int* n_boxes, float* markers) {

@@ -17,7 +17,7 @@ for depth in (1, 4):
     prm = lmot.default_params(); prm.pipeline_depth = depth
     ctx = lmot.Lmot(prm)
     st = torch.cuda.Stream(); torch.cuda.set_stream(st); ctx.set_stream(st.cuda_stream)
-    ctx.tracker_reset(); ctx.enable_timing(True)
+    ctx.tracker_reset(); ctx.enable_timing(True); ctx.debug_phase_clock()
     for i in range(W + K): ctx.frame_dev(d[i].data_ptr(), n, ts[i])
     ctx.sync()
     tl = ctx.debug_timeline() * 1e3          # us
@@ -29,4 +29,7 @@ for depth in (1, 4):
     if len(tl) > 4:
         per = (tl[-1, 4] - tl[-11, 4]) / 10
         print(f"tracker completion to tracker completion: {per:.1f} us per frame")
+    tr = ctx.debug_phase_clock()
+    if len(tr): print(f"last frame: ground kernel span {(tr[:, 7].max() - tr[:, 0].min()) / 1e3:.2f} us (CTA stamps); "
+                      f"spawn_output start->end by %globaltimer: {(int(tr[0, 1]) - int(tr[0, 0])) / 1e3:.2f} us, T = {int(tr[0, 2])}, visible = {int(tr[0, 3])}")
     ctx.enable_timing(False); ctx.close()

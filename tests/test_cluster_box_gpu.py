@@ -134,3 +134,24 @@ def test_boxes_random_blobs(lm, ref_intended):
 def test_box_fit_empty(lm):
     b, m = lm.box_fit(np.zeros((0, 3), np.float32), np.zeros((250, 250), np.int32), 0)
     assert b.shape == (0, 8, 3)
+
+
+def test_cluster_node_side_outputs_bit_exact(lm, ref_intended, synth):
+    """makeClusteredCloud / setObsMsg / createCostMap (the cluster node's other topics) from the label grid."""
+    rng = np.random.default_rng(3)
+    for seed in (2, 9):
+        for ts, pts in synth.frames(synth.SceneConfig(seed=seed), 2):
+            e = _elevated(ref_intended, pts)
+            e = np.concatenate([e, rng.uniform(-30, 30, (500, 3)).astype(np.float32) * [1, 1, 0.05]]).astype(np.float32)   # points outside the ROI / near the car
+            g_ref, k_ref = ref_intended.component_clustering(e)
+            cl_r, ob_r, cm_r = ref_intended.cluster_outputs(e, g_ref)
+            g, k = lm.component_cluster(e)
+            assert k == k_ref and np.array_equal(g, g_ref)
+            cl, ob, cm = lm.cluster_outputs()
+            assert cl.shape[0] == cl_r.shape[0] and np.array_equal(cl[:, :3].view(np.uint32), cl_r.view(np.uint32))
+            assert ob.shape[0] == ob_r.shape[0] and ob.shape[0] > 100
+            assert np.array_equal(ob[:, :3].astype(np.float64), ob_r[:, :3]) and np.array_equal(ob[:, 3].astype(np.int64), ob_r[:, 3].astype(np.int64))
+            assert np.array_equal(cm, cm_r) and cm.max() == 100
+    # twice in a row: the scratch grid is back at rest
+    cl2, ob2, cm2 = lm.cluster_outputs()
+    assert np.array_equal(cl2, cl) and np.array_equal(ob2, ob) and np.array_equal(cm2, cm)
