@@ -779,6 +779,7 @@ __device__ __forceinline__ bool overseg_cond(const float* c, const float* ab, do
 }
 
 constexpr int kVisChunk = 256;       // visible boxes staged in shared memory per pass
+constexpr int kCandCap = 4096;       // (box, track) pairs that pass the bounds pre-test, per pass
 
 // ------------------------------------------------------------------------------------------------ TC2
 // One frame's results.  spawn_output_kernel fills the DEVICE copy (the tracker is the sequential chain of the pipeline:
@@ -787,6 +788,27 @@ constexpr int kVisChunk = 256;       // visible boxes staged in shared memory pe
 struct OutPtrs {
   float* targets; double* vandyaw; int* track_manage; uint8_t* is_static; uint8_t* is_vis; float* vis_bb; int* hdr; float* boxes;
 };
+
+// Block-wide exclusive offsets of up to two 0/1 flags per thread (packed a | b << 16): ballot inside the warp, one shuffle scan
+// of the 32 warp totals by warp 0.  s_w = int[33] scratch; returns (exclusive offset, block total), both packed the same way.
+__device__ __forceinline__ void block_offsets(int a, int b, int* s_w, int& excl, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned ba = __ballot_sync(0xFFFFFFFFu, a), bb = __ballot_sync(0xFFFFFFFFu, b);
+  if (lane == 0) s_w[warp] = __popc(ba) | (__popc(bb) << 16);
+  __syncthreads();
+  if (warp == 0) {
+    const int c = s_w[lane];
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += u; }
+    s_w[lane] = inc - c;
+    if (lane == 31) s_w[32] = inc;
+  }
+  __syncthreads();
+  const unsigned lt = (1u << lane) - 1u;
+  excl = s_w[warp] + (__popc(ba & lt) | (__popc(bb & lt) << 16));
+  total = s_w[32];
+}
 
 // per-track outputs of one track (:995-1041) + static flag (:1045-1081) into the frame's result block; returns isVisBB
 __device__ __forceinline__ int emit_track(TrackState& t, int i, double ego_yaw, const OutPtrs& o, double4* __restrict__ pos) {
@@ -826,12 +848,13 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
                     uint8_t* __restrict__ has5_arr, int first_frame, int compat_first, double ego_yaw, int max_tracks, OutPtrs o,
                     OutPtrs prev, int full, int* __restrict__ act_list, double4* __restrict__ pos, unsigned long long* __restrict__ trace) {
   if (trace && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[0] = t; }
-  __shared__ int s_warp[32], s_warp2[32];
-  __shared__ int s_carry, s_carry2, s_nvis;
+  __shared__ int s_w[33];
+  __shared__ int s_carry, s_carry2, s_nvis, s_ncand;
   __shared__ __align__(16) float s_bx[kVisChunk][8];
-  __shared__ __align__(16) float s_ab[kVisChunk][4];
+  __shared__ __align__(16) float4 s_ab[kVisChunk];     // bounds of the box: min x, max x, min y, max y
   __shared__ int s_vid[kVisChunk];
   __shared__ unsigned char s_h5[kVisChunk];
+  __shared__ unsigned s_cand[kCandCap];                 // (visible slot << 24) | track index
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T0 = trk[CNT_N_TRACKS];
   const int n_act0 = trk[CNT_N_ACT];
@@ -863,16 +886,19 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
 
   // ---- start the frame's result block from the previous one (dead tracks: unchanged), refresh the positions of the
   // active tracks, collect the visible ones (a subset of the active list, which is sorted by track index)
-  if (!full && prev.targets != o.targets) {
-    for (int e = tid; e < (T0 * 12 + 15) / 16; e += 1024) reinterpret_cast<uint4*>(o.targets)[e] = reinterpret_cast<const uint4*>(prev.targets)[e];
-    for (int e = tid; e < T0; e += 1024) {      // v is the state's; the yaw is re-offset by THIS frame's ego yaw for every track (:1004-1008)
-      o.vandyaw[2 * e] = prev.vandyaw[2 * e];
-      o.vandyaw[2 * e + 1] = wrap_pi(pos[e].z + ego_yaw);
+  if (!full) {
+    const bool cp = prev.targets != o.targets;   // same block (result_ring == 1, or the synchronous entry points): patch in place
+    if (cp) {
+      for (int e = tid; e < (T0 * 12 + 15) / 16; e += 1024) reinterpret_cast<uint4*>(o.targets)[e] = reinterpret_cast<const uint4*>(prev.targets)[e];
+      for (int e = tid; e < (T0 * 4 + 15) / 16; e += 1024) reinterpret_cast<uint4*>(o.track_manage)[e] = reinterpret_cast<const uint4*>(prev.track_manage)[e];
+      for (int e = tid; e < (T0 + 15) / 16; e += 1024) {
+        reinterpret_cast<uint4*>(o.is_static)[e] = reinterpret_cast<const uint4*>(prev.is_static)[e];
+        reinterpret_cast<uint4*>(o.is_vis)[e] = reinterpret_cast<const uint4*>(prev.is_vis)[e];
+      }
     }
-    for (int e = tid; e < (T0 * 4 + 15) / 16; e += 1024) reinterpret_cast<uint4*>(o.track_manage)[e] = reinterpret_cast<const uint4*>(prev.track_manage)[e];
-    for (int e = tid; e < (T0 + 15) / 16; e += 1024) {
-      reinterpret_cast<uint4*>(o.is_static)[e] = reinterpret_cast<const uint4*>(prev.is_static)[e];
-      reinterpret_cast<uint4*>(o.is_vis)[e] = reinterpret_cast<const uint4*>(prev.is_vis)[e];
+    for (int e = tid; e < T0; e += 1024) {      // v is the state's; the yaw is re-offset by THIS frame's ego yaw for every track (:1004-1008)
+      if (cp) o.vandyaw[2 * e] = prev.vandyaw[2 * e];
+      o.vandyaw[2 * e + 1] = wrap_pi(pos[e].z + ego_yaw);
     }
   }
   const int n_scan = full ? T0 : n_act0;       // entries to visit: the whole table, or the active list
@@ -885,12 +911,9 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
       pos[k] = make_double4(t.x[0][0], t.x[0][1], t.x[0][3], 0.0);
       vis = t.isVisBB ? 1 : 0;
     }
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, vis);
-    if (lane == 0) s_warp[warp] = __popc(bal);
-    __syncthreads();
-    int wbase = 0, tot = 0;
-    for (int w = 0; w < 32; ++w) { if (w < warp) wbase += s_warp[w]; tot += s_warp[w]; }
-    if (vis) vis_list[s_nvis + wbase + __popc(bal & ((1u << lane) - 1u))] = k;
+    int ex, tot;
+    block_offsets(vis, 0, s_w, ex, tot);
+    if (vis) vis_list[s_nvis + ex] = k;
     __syncthreads();
     if (tid == 0) s_nvis += tot;
     __syncthreads();
@@ -906,25 +929,42 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   for (int v0 = 0; v0 < nv; v0 += kVisChunk) {
     const int nc = min(kVisChunk, nv - v0);
     for (int e = tid; e < nc * 8; e += 1024) { const int v = e >> 3, q = e & 7; s_bx[v][q] = tracks[vis_list[v0 + v]].BBox[q >> 1][q & 1]; }
+    if (tid == 0) s_ncand = 0;
     __syncthreads();
     for (int v = tid; v < nc; v += 1024) {
       const float* c = s_bx[v];
-      s_ab[v][0] = fminf(fminf(c[0], c[2]), fminf(c[4], c[6])); s_ab[v][1] = fmaxf(fmaxf(c[0], c[2]), fmaxf(c[4], c[6]));
-      s_ab[v][2] = fminf(fminf(c[1], c[3]), fminf(c[5], c[7])); s_ab[v][3] = fmaxf(fmaxf(c[1], c[3]), fmaxf(c[5], c[7]));
+      s_ab[v] = make_float4(fminf(fminf(c[0], c[2]), fminf(c[4], c[6])), fmaxf(fmaxf(c[0], c[2]), fmaxf(c[4], c[6])),
+                            fminf(fminf(c[1], c[3]), fminf(c[5], c[7])), fmaxf(fmaxf(c[1], c[3]), fmaxf(c[5], c[7])));
       s_vid[v] = vis_list[v0 + v]; s_h5[v] = 0;
     }
     __syncthreads();
+    // pass 1, thread = track: single-precision bounds pre-test against every staged box (the margin covers the rounding of
+    // the position to float); the few pairs that survive are queued so that pass 2 runs them one per THREAD -- inline, the
+    // ~150 dependent fp64 operations of the exact test would serialise on whichever warp happens to own a crowded spot
     for (int j0 = 0; j0 < T0; j0 += 1024) {
       const int j = j0 + tid;
       if (j < T0) {
         const double4 pj = pos[j];
-        int imax = (v0 == 0) ? -1 : imax_arr[j];
+        const float px = (float)pj.x, py = (float)pj.y;
+        const float mg = 0.011f + 2.0e-7f * (fabsf(px) + fabsf(py));
+        if (v0 == 0) imax_arr[j] = -1;
         for (int v = 0; v < nc; ++v) {
-          const int i = s_vid[v];
-          if (i != j && overseg_cond(s_bx[v], s_ab[v], pj.x, pj.y)) { s_h5[v] = 1; imax = max(imax, i); }
+          const float4 ab = s_ab[v];
+          if (!(px < ab.x - mg || px > ab.y + mg || py < ab.z - mg || py > ab.w + mg) && s_vid[v] != j) {
+            const int slot = atomicAdd(&s_ncand, 1);
+            if (slot < kCandCap) s_cand[slot] = ((unsigned)v << 24) | (unsigned)j;
+            else if (overseg_cond(s_bx[v], reinterpret_cast<const float*>(&s_ab[v]), pj.x, pj.y)) { s_h5[v] = 1; atomicMax(&imax_arr[j], s_vid[v]); }
+          }
         }
-        imax_arr[j] = imax;
       }
+    }
+    __syncthreads();
+    // pass 2, thread = candidate pair: the exact test
+    const int ncand = min(s_ncand, kCandCap);
+    for (int e = tid; e < ncand; e += 1024) {
+      const int v = (int)(s_cand[e] >> 24), j = (int)(s_cand[e] & 0xFFFFFFu);
+      const double4 pj = pos[j];
+      if (overseg_cond(s_bx[v], reinterpret_cast<const float*>(&s_ab[v]), pj.x, pj.y)) { s_h5[v] = 1; atomicMax(&imax_arr[j], s_vid[v]); }
     }
     __syncthreads();
     for (int v = tid; v < nc; v += 1024) has5_arr[s_vid[v]] = s_h5[v];
@@ -950,12 +990,9 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   for (int b0 = 0; b0 < M; b0 += 1024) {
     const int b = b0 + tid;
     const int un = (b < M && first_setter[b] == INT_MAX) ? 1 : 0;
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, un);
-    if (lane == 0) s_warp[warp] = __popc(bal);
-    __syncthreads();
-    int wbase = 0, tot = 0;
-    for (int w = 0; w < 32; ++w) { if (w < warp) wbase += s_warp[w]; tot += s_warp[w]; }
-    const int p = T0 + s_carry + wbase + __popc(bal & ((1u << lane) - 1u));
+    int ex, tot;
+    block_offsets(un, 0, s_w, ex, tot);
+    const int p = T0 + s_carry + ex;
     if (un && p < max_tracks) {
       double cx, cy;
       cp_from_box(boxes + (size_t)b * 24, cx, cy);
@@ -985,21 +1022,18 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
       vis = emit_track(t, i, ego_yaw, o, pos);
       act = (t.trackNum != 0 || vis) ? 1 : 0;
     }
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, vis), bala = __ballot_sync(0xFFFFFFFFu, act);
-    if (lane == 0) { s_warp[warp] = __popc(bal); s_warp2[warp] = __popc(bala); }
-    __syncthreads();
-    int wbase = 0, tot = 0, wbase2 = 0, tot2 = 0;
-    for (int w = 0; w < 32; ++w) { if (w < warp) { wbase += s_warp[w]; wbase2 += s_warp2[w]; } tot += s_warp[w]; tot2 += s_warp2[w]; }
-    if (act) act_list[s_carry2 + wbase2 + __popc(bala & ((1u << lane) - 1u))] = i;
+    int ex, tot;
+    block_offsets(vis, act, s_w, ex, tot);
+    if (act) act_list[s_carry2 + (ex >> 16)] = i;
     if (vis) {
-      const int p = s_carry + wbase + __popc(bal & ((1u << lane) - 1u));
+      const int p = s_carry + (ex & 0xFFFF);
       const float2* src = reinterpret_cast<const float2*>(&tracks[i].BBox[0][0]);
       float2* dst = reinterpret_cast<float2*>(o.vis_bb + (size_t)p * 24);
 #pragma unroll
       for (int e = 0; e < 12; ++e) dst[e] = src[e];
     }
     __syncthreads();
-    if (tid == 0) { s_carry += tot; s_carry2 += tot2; }
+    if (tid == 0) { s_carry += tot & 0xFFFF; s_carry2 += tot >> 16; }
     __syncthreads();
   }
   if (tid == 0) {

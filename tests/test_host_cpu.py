@@ -6,6 +6,8 @@ import os
 
 import numpy as np
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def test_library_exports_every_declared_symbol(pkg):
     lib = pkg.load_library()
@@ -54,3 +56,23 @@ def test_no_cuda_device_is_a_loud_failure(pkg):
         assert e.status == pkg.ERR_CUDA
     else:
         raise AssertionError("lmot_create succeeded without a CUDA device")
+
+
+def test_ros_codecs_cpu():
+    """ros/include/lmot_ros_codec.hpp (PointCloud2 layout / zero-copy test, trackbox pack + unpack, box edges) against plain structs."""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "cpp", "ros_codec_test")
+    subprocess.run(["g++", "-std=c++14", "-O1", "-Wall", os.path.join(ROOT, "tests", "cpp", "ros_codec_test.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "ros codec ok" in out
+
+
+def test_ros_node_shells_compile():
+    """The three node shells (ros/src) need ROS to link; here they are type-checked against API-shaped stand-ins of the ROS headers
+    (tests/cpp/ros_stubs) and the real include/lmot.h + ros/include/lmot_ros_codec.hpp."""
+    import subprocess
+    for node in ("ground", "cluster", "tracking"):
+        r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-w", "-I", os.path.join(ROOT, "tests", "cpp", "ros_stubs"), "-I",
+                            os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "ros", "include"),
+                            os.path.join(ROOT, "ros", "src", node + "_node.cpp")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
