@@ -153,6 +153,8 @@ struct TAShared {
   double Xs[3][15][5];   // per model: predicted sigma points
   double Pm[3][25];      // per model: mixed covariance
   double S[3][4], Tc[3][10], zp[3][2];
+  double dyaw[3][15];    // per model: wrapped yaw residual of every sigma point against the predicted mean
+  double detS[3];        // per model: det(S), computed by the model's own warp
   int flag;              // 0 run, 1 skip (dead track)
   int explode;           // det(P_merge) > 10 or P_merge(4,4) > 1000 (:828-831), computed by warp 3 while warps 0-2 predict
 };
@@ -310,15 +312,18 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
       x[e] = acc;
     }
     x[3] = wrap_pi(x[3]);
+    // the yaw residual of sigma point i is wrapped once (lane = sigma point) instead of inside the 15-term sums of the
+    // nine covariance elements that use it: same operands, same operations, same bits
+    if (lane < 15) sh.dyaw[model][lane] = wrap_pi(sh.Xs[model][lane][3] - x[3]);
+    __syncwarp();
     if (lane < 25) {      // predicted covariance element (:746-755)
       const int r = lane / 5, c = lane % 5;
       const double xr = (r == 0) ? x[0] : (r == 1) ? x[1] : (r == 2) ? x[2] : (r == 3) ? x[3] : x[4];
       const double xc = (c == 0) ? x[0] : (c == 1) ? x[1] : (c == 2) ? x[2] : (c == 3) ? x[3] : x[4];
 #pragma unroll
       for (int i = 0; i < 15; ++i) {
-        double dr = sh.Xs[model][i][r] - xr, dc = sh.Xs[model][i][c] - xc;
-        if (r == 3) dr = wrap_pi(dr);
-        if (c == 3) dc = wrap_pi(dc);
+        const double dr = (r == 3) ? sh.dyaw[model][i] : sh.Xs[model][i][r] - xr;
+        const double dc = (c == 3) ? sh.dyaw[model][i] : sh.Xs[model][i][c] - xc;
         Pe = Pe + (((i == 0) ? w0 : wi) * dr) * dc;
       }
     }
@@ -348,6 +353,7 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
     }
     __syncwarp();
     inv2_lu(sh.S[model], Si);
+    if (lane == 0) sh.detS[model] = det2(sh.S[model]);     // for findMaxZandS below: each warp its own model, not every warp all three
     }   // model < 3
     __syncthreads();                      // the guard's verdict is in
     if (sh.explode) {
@@ -368,7 +374,7 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
     __syncthreads();
 
     // ---- findMaxZandS (:176-203), gate scale x4 and explosion guard (:843-851)
-    const double dcv = det2(sh.S[0]), dctrv = det2(sh.S[1]), drm = det2(sh.S[2]);
+    const double dcv = sh.detS[0], dctrv = sh.detS[1], drm = sh.detS[2];
     int mm;
     if (dcv > dctrv) mm = (dcv > drm) ? 0 : 2; else mm = (dctrv > drm) ? 1 : 2;
     double S4[4];
@@ -849,7 +855,8 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
                     OutPtrs prev, int full, int* __restrict__ act_list, double4* __restrict__ pos, unsigned long long* __restrict__ trace) {
   if (trace && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[0] = t; }
   __shared__ int s_w[33];
-  __shared__ int s_carry, s_carry2, s_nvis, s_ncand;
+  __shared__ int s_carry, s_carry2, s_nvis, s_ncand, s_ncont;
+  __shared__ unsigned char s_cont[kVisChunk];           // visible boxes that sit inside another visible box
   __shared__ __align__(16) float s_bx[kVisChunk][8];
   __shared__ __align__(16) float4 s_ab[kVisChunk];     // bounds of the box: min x, max x, min y, max y
   __shared__ int s_vid[kVisChunk];
@@ -921,15 +928,19 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   const int nv = s_nvis;
 
   // ---- mergeOverSegmentation (:666-700), folded into this kernel.  The sequential double loop writes trackNum[i]=5,
-  // trackNum[j]=0 for every hit (i,j) with i visible; the value that survives at index k is the write with the largest
-  // (i,j) key: 0 if some visible i > k contains k, else 5 if k (visible) contains anybody, else unchanged.  Both facts come
-  // from ONE predicate, "visible box i contains the position of track j" (dead j included, like the reference): thread =
-  // track j (its position from the packed array), the visible boxes (a few dozen) are staged in shared memory with their
-  // bounds and read as broadcasts.
-  for (int v0 = 0; v0 < nv; v0 += kVisChunk) {
-    const int nc = min(kVisChunk, nv - v0);
+  // trackNum[j]=0 for every hit (i,j) with i visible ("box i contains the position of track j"); the value that survives at
+  // index k is the write with the largest (i,j) key: 0 if some visible i > k contains k, else 5 if k (visible) contains
+  // anybody, else unchanged.  Only LIVE k can change (0 -> 0 is a no-op), and a visible track already has trackNum 5 when it
+  // gets here (associateBB requires 5, a validated measurement keeps it), so "k contains anybody" (has5) only matters for a
+  // visible k that is itself inside another visible box.  Hence:
+  //   pass A  imax[j] = largest visible i containing j, for the LIVE tracks j only (active list x visible boxes);
+  //   pass B  has5[k] for the rare visible k with imax[k] >= 0: those alone are tested against EVERY track, dead ones
+  //           included like the reference (positions from the packed array, coalesced).
+  // Visible boxes + bounds are staged in shared memory; a single-precision bounds pre-test (the margin covers the rounding
+  // of the position to float) selects the few pairs that get the exact fp64 test, queued so that they run one per THREAD.
+  auto stage_boxes = [&](int v0, int nc) {
     for (int e = tid; e < nc * 8; e += 1024) { const int v = e >> 3, q = e & 7; s_bx[v][q] = tracks[vis_list[v0 + v]].BBox[q >> 1][q & 1]; }
-    if (tid == 0) s_ncand = 0;
+    if (tid == 0) { s_ncand = 0; s_ncont = 0; }
     __syncthreads();
     for (int v = tid; v < nc; v += 1024) {
       const float* c = s_bx[v];
@@ -938,33 +949,54 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
       s_vid[v] = vis_list[v0 + v]; s_h5[v] = 0;
     }
     __syncthreads();
-    // pass 1, thread = track: single-precision bounds pre-test against every staged box (the margin covers the rounding of
-    // the position to float); the few pairs that survive are queued so that pass 2 runs them one per THREAD -- inline, the
-    // ~150 dependent fp64 operations of the exact test would serialise on whichever warp happens to own a crowded spot
-    for (int j0 = 0; j0 < T0; j0 += 1024) {
-      const int j = j0 + tid;
-      if (j < T0) {
-        const double4 pj = pos[j];
-        const float px = (float)pj.x, py = (float)pj.y;
-        const float mg = 0.011f + 2.0e-7f * (fabsf(px) + fabsf(py));
-        if (v0 == 0) imax_arr[j] = -1;
-        for (int v = 0; v < nc; ++v) {
-          const float4 ab = s_ab[v];
-          if (!(px < ab.x - mg || px > ab.y + mg || py < ab.z - mg || py > ab.w + mg) && s_vid[v] != j) {
-            const int slot = atomicAdd(&s_ncand, 1);
-            if (slot < kCandCap) s_cand[slot] = ((unsigned)v << 24) | (unsigned)j;
-            else if (overseg_cond(s_bx[v], reinterpret_cast<const float*>(&s_ab[v]), pj.x, pj.y)) { s_h5[v] = 1; atomicMax(&imax_arr[j], s_vid[v]); }
-          }
+  };
+  if (nv > 0)
+    for (int q = tid; q < n_scan; q += 1024) imax_arr[full ? q : act_list[q]] = -1;
+  __syncthreads();
+  for (int v0 = 0; v0 < nv; v0 += kVisChunk) {                 // pass A
+    const int nc = min(kVisChunk, nv - v0);
+    stage_boxes(v0, nc);
+    for (int q = tid; q < n_scan; q += 1024) {
+      const int j = full ? q : act_list[q];
+      if (tracks[j].trackNum == 0) continue;                    // dead (stale-visible entry of the list): cannot change
+      const double4 pj = pos[j];
+      const float px = (float)pj.x, py = (float)pj.y;
+      const float mg = 0.011f + 2.0e-7f * (fabsf(px) + fabsf(py));
+      for (int v = 0; v < nc; ++v) {
+        const float4 ab = s_ab[v];
+        if (!(px < ab.x - mg || px > ab.y + mg || py < ab.z - mg || py > ab.w + mg) && s_vid[v] != j) {
+          const int slot = atomicAdd(&s_ncand, 1);
+          if (slot < kCandCap) s_cand[slot] = ((unsigned)v << 24) | (unsigned)j;
+          else if (overseg_cond(s_bx[v], reinterpret_cast<const float*>(&s_ab[v]), pj.x, pj.y)) atomicMax(&imax_arr[j], s_vid[v]);
         }
       }
     }
     __syncthreads();
-    // pass 2, thread = candidate pair: the exact test
     const int ncand = min(s_ncand, kCandCap);
     for (int e = tid; e < ncand; e += 1024) {
       const int v = (int)(s_cand[e] >> 24), j = (int)(s_cand[e] & 0xFFFFFFu);
       const double4 pj = pos[j];
-      if (overseg_cond(s_bx[v], reinterpret_cast<const float*>(&s_ab[v]), pj.x, pj.y)) { s_h5[v] = 1; atomicMax(&imax_arr[j], s_vid[v]); }
+      if (overseg_cond(s_bx[v], reinterpret_cast<const float*>(&s_ab[v]), pj.x, pj.y)) atomicMax(&imax_arr[j], s_vid[v]);
+    }
+    __syncthreads();
+  }
+  for (int v0 = 0; v0 < nv; v0 += kVisChunk) {                 // pass B
+    const int nc = min(kVisChunk, nv - v0);
+    if (nv > kVisChunk) stage_boxes(v0, nc);                    // otherwise the only chunk is still staged
+    for (int v = tid; v < nc; v += 1024)
+      if (imax_arr[s_vid[v]] >= 0) s_cont[atomicAdd(&s_ncont, 1)] = (unsigned char)v;
+    __syncthreads();
+    const int ncont = s_ncont;
+    for (int cidx = 0; cidx < ncont; ++cidx) {
+      const int v = s_cont[cidx], k = s_vid[v];
+      const float4 ab = s_ab[v];
+      for (int j = tid; j < T0; j += 1024) {
+        const double4 pj = pos[j];
+        const float px = (float)pj.x, py = (float)pj.y;
+        const float mg = 0.011f + 2.0e-7f * (fabsf(px) + fabsf(py));
+        if (j != k && !(px < ab.x - mg || px > ab.y + mg || py < ab.z - mg || py > ab.w + mg) &&
+            overseg_cond(s_bx[v], reinterpret_cast<const float*>(&s_ab[v]), pj.x, pj.y)) s_h5[v] = 1;
+      }
     }
     __syncthreads();
     for (int v = tid; v < nc; v += 1024) has5_arr[s_vid[v]] = s_h5[v];
