@@ -161,7 +161,7 @@ struct TAShared {
 
 __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
 
-__global__ void __launch_bounds__(kTAThreads)
+__global__ void __launch_bounds__(kTAThreads, 4)     // <= 128 registers: a CTA (16 K registers) fits on an SM next to a ground-kernel CTA (47 K)
 imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, const int* __restrict__ det, const float* __restrict__ boxes,
                         double dt, unsigned* __restrict__ gate, unsigned* __restrict__ setter, int* __restrict__ first_setter,
                         uint8_t* __restrict__ skip, int words, const int* __restrict__ act_list) {
@@ -784,6 +784,8 @@ __device__ __forceinline__ bool overseg_cond(const float* c, const float* ab, do
   return (c1 > 0 && c2 > 0 && c3 > 0) || (c4 > 0 && c5 > 0 && c6 > 0);
 }
 
+constexpr int kTCThreads = 256;      // ONE small CTA: 16 K registers, so it starts on any SM next to the resident detection kernels
+                                     // instead of waiting for a whole SM to drain (a 1024-thread CTA needs the full register file)
 constexpr int kVisChunk = 256;       // visible boxes staged in shared memory per pass
 constexpr int kCandCap = 4096;       // (box, track) pairs that pass the bounds pre-test, per pass
 
@@ -803,7 +805,7 @@ __device__ __forceinline__ void block_offsets(int a, int b, int* s_w, int& excl,
   if (lane == 0) s_w[warp] = __popc(ba) | (__popc(bb) << 16);
   __syncthreads();
   if (warp == 0) {
-    const int c = s_w[lane];
+    const int c = lane < (int)(blockDim.x >> 5) ? s_w[lane] : 0;
     int inc = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += u; }
@@ -848,7 +850,7 @@ __device__ __forceinline__ int emit_track(TrackState& t, int i, double ego_yaw, 
 //     of every track is its state's yaw plus THIS frame's ego yaw: `pos`, a packed (x, y, yaw) per track, refreshed for the
 //     active tracks only.
 // `full` (first step after the table was written from the host): everything is rebuilt from the records.
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(kTCThreads)
 spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int* __restrict__ det, const float* __restrict__ boxes,
                     int* __restrict__ first_setter, int* __restrict__ imax_arr, int* __restrict__ vis_list,
                     uint8_t* __restrict__ has5_arr, int first_frame, int compat_first, double ego_yaw, int max_tracks, OutPtrs o,
@@ -885,31 +887,31 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
       o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = 0; o.hdr[HDR_ERROR] = det[CNT_ERROR];
       det[CNT_ERROR] = 0;
     }
-    for (int b = tid; b < M; b += 1024) first_setter[b] = INT_MAX;
-    for (int e = tid; e < M * 24; e += 1024) o.boxes[e] = boxes[e];
+    for (int b = tid; b < M; b += kTCThreads) first_setter[b] = INT_MAX;
+    for (int e = tid; e < M * 24; e += kTCThreads) o.boxes[e] = boxes[e];
     return;
   }
-  for (int e = tid; e < M * 24; e += 1024) o.boxes[e] = boxes[e];     // the frame's box list travels with its results
+  for (int e = tid; e < M * 24; e += kTCThreads) o.boxes[e] = boxes[e];     // the frame's box list travels with its results
 
   // ---- start the frame's result block from the previous one (dead tracks: unchanged), refresh the positions of the
   // active tracks, collect the visible ones (a subset of the active list, which is sorted by track index)
   if (!full) {
     const bool cp = prev.targets != o.targets;   // same block (result_ring == 1, or the synchronous entry points): patch in place
     if (cp) {
-      for (int e = tid; e < (T0 * 12 + 15) / 16; e += 1024) reinterpret_cast<uint4*>(o.targets)[e] = reinterpret_cast<const uint4*>(prev.targets)[e];
-      for (int e = tid; e < (T0 * 4 + 15) / 16; e += 1024) reinterpret_cast<uint4*>(o.track_manage)[e] = reinterpret_cast<const uint4*>(prev.track_manage)[e];
-      for (int e = tid; e < (T0 + 15) / 16; e += 1024) {
+      for (int e = tid; e < (T0 * 12 + 15) / 16; e += kTCThreads) reinterpret_cast<uint4*>(o.targets)[e] = reinterpret_cast<const uint4*>(prev.targets)[e];
+      for (int e = tid; e < (T0 * 4 + 15) / 16; e += kTCThreads) reinterpret_cast<uint4*>(o.track_manage)[e] = reinterpret_cast<const uint4*>(prev.track_manage)[e];
+      for (int e = tid; e < (T0 + 15) / 16; e += kTCThreads) {
         reinterpret_cast<uint4*>(o.is_static)[e] = reinterpret_cast<const uint4*>(prev.is_static)[e];
         reinterpret_cast<uint4*>(o.is_vis)[e] = reinterpret_cast<const uint4*>(prev.is_vis)[e];
       }
     }
-    for (int e = tid; e < T0; e += 1024) {      // v is the state's; the yaw is re-offset by THIS frame's ego yaw for every track (:1004-1008)
+    for (int e = tid; e < T0; e += kTCThreads) {      // v is the state's; the yaw is re-offset by THIS frame's ego yaw for every track (:1004-1008)
       if (cp) o.vandyaw[2 * e] = prev.vandyaw[2 * e];
       o.vandyaw[2 * e + 1] = wrap_pi(pos[e].z + ego_yaw);
     }
   }
   const int n_scan = full ? T0 : n_act0;       // entries to visit: the whole table, or the active list
-  for (int q0 = 0; q0 < n_scan; q0 += 1024) {
+  for (int q0 = 0; q0 < n_scan; q0 += kTCThreads) {
     const int q = q0 + tid;
     int vis = 0, k = 0;
     if (q < n_scan) {
@@ -939,10 +941,10 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   // Visible boxes + bounds are staged in shared memory; a single-precision bounds pre-test (the margin covers the rounding
   // of the position to float) selects the few pairs that get the exact fp64 test, queued so that they run one per THREAD.
   auto stage_boxes = [&](int v0, int nc) {
-    for (int e = tid; e < nc * 8; e += 1024) { const int v = e >> 3, q = e & 7; s_bx[v][q] = tracks[vis_list[v0 + v]].BBox[q >> 1][q & 1]; }
+    for (int e = tid; e < nc * 8; e += kTCThreads) { const int v = e >> 3, q = e & 7; s_bx[v][q] = tracks[vis_list[v0 + v]].BBox[q >> 1][q & 1]; }
     if (tid == 0) { s_ncand = 0; s_ncont = 0; }
     __syncthreads();
-    for (int v = tid; v < nc; v += 1024) {
+    for (int v = tid; v < nc; v += kTCThreads) {
       const float* c = s_bx[v];
       s_ab[v] = make_float4(fminf(fminf(c[0], c[2]), fminf(c[4], c[6])), fmaxf(fmaxf(c[0], c[2]), fmaxf(c[4], c[6])),
                             fminf(fminf(c[1], c[3]), fminf(c[5], c[7])), fmaxf(fmaxf(c[1], c[3]), fmaxf(c[5], c[7])));
@@ -951,12 +953,12 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
     __syncthreads();
   };
   if (nv > 0)
-    for (int q = tid; q < n_scan; q += 1024) imax_arr[full ? q : act_list[q]] = -1;
+    for (int q = tid; q < n_scan; q += kTCThreads) imax_arr[full ? q : act_list[q]] = -1;
   __syncthreads();
   for (int v0 = 0; v0 < nv; v0 += kVisChunk) {                 // pass A
     const int nc = min(kVisChunk, nv - v0);
     stage_boxes(v0, nc);
-    for (int q = tid; q < n_scan; q += 1024) {
+    for (int q = tid; q < n_scan; q += kTCThreads) {
       const int j = full ? q : act_list[q];
       if (tracks[j].trackNum == 0) continue;                    // dead (stale-visible entry of the list): cannot change
       const double4 pj = pos[j];
@@ -973,7 +975,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
     }
     __syncthreads();
     const int ncand = min(s_ncand, kCandCap);
-    for (int e = tid; e < ncand; e += 1024) {
+    for (int e = tid; e < ncand; e += kTCThreads) {
       const int v = (int)(s_cand[e] >> 24), j = (int)(s_cand[e] & 0xFFFFFFu);
       const double4 pj = pos[j];
       if (overseg_cond(s_bx[v], reinterpret_cast<const float*>(&s_ab[v]), pj.x, pj.y)) atomicMax(&imax_arr[j], s_vid[v]);
@@ -983,14 +985,14 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   for (int v0 = 0; v0 < nv; v0 += kVisChunk) {                 // pass B
     const int nc = min(kVisChunk, nv - v0);
     if (nv > kVisChunk) stage_boxes(v0, nc);                    // otherwise the only chunk is still staged
-    for (int v = tid; v < nc; v += 1024)
+    for (int v = tid; v < nc; v += kTCThreads)
       if (imax_arr[s_vid[v]] >= 0) s_cont[atomicAdd(&s_ncont, 1)] = (unsigned char)v;
     __syncthreads();
     const int ncont = s_ncont;
     for (int cidx = 0; cidx < ncont; ++cidx) {
       const int v = s_cont[cidx], k = s_vid[v];
       const float4 ab = s_ab[v];
-      for (int j = tid; j < T0; j += 1024) {
+      for (int j = tid; j < T0; j += kTCThreads) {
         const double4 pj = pos[j];
         const float px = (float)pj.x, py = (float)pj.y;
         const float mg = 0.011f + 2.0e-7f * (fabsf(px) + fabsf(py));
@@ -999,11 +1001,11 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
       }
     }
     __syncthreads();
-    for (int v = tid; v < nc; v += 1024) has5_arr[s_vid[v]] = s_h5[v];
+    for (int v = tid; v < nc; v += kTCThreads) has5_arr[s_vid[v]] = s_h5[v];
     __syncthreads();
   }
   if (nv > 0) {       // only live tracks can change (0 -> 0 is a no-op, 5 needs a visible, hence live, track)
-    for (int q0 = 0; q0 < n_scan; q0 += 1024) {
+    for (int q0 = 0; q0 < n_scan; q0 += kTCThreads) {
       const int q = q0 + tid;
       if (q < n_scan) {
         const int k = full ? q : act_list[q];
@@ -1019,7 +1021,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   __syncthreads();
 
   // ---- spawn one UKF per unmatched box, in box order (:972-989)
-  for (int b0 = 0; b0 < M; b0 += 1024) {
+  for (int b0 = 0; b0 < M; b0 += kTCThreads) {
     const int b = b0 + tid;
     const int un = (b < M && first_setter[b] == INT_MAX) ? 1 : 0;
     int ex, tot;
@@ -1045,7 +1047,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   // (stable in-place compaction: a tile is read completely before anything at or below its range is written)
   const int n_new = T - T0;
   const int n_emit = n_scan + n_new;
-  for (int q0 = 0; q0 < n_emit; q0 += 1024) {
+  for (int q0 = 0; q0 < n_emit; q0 += kTCThreads) {
     const int q = q0 + tid;
     int vis = 0, act = 0, i = 0;
     if (q < n_emit) {
@@ -1208,7 +1210,7 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
                                                                            c->d_first_setter, c->d_skip, c->gate_words, c->d_act_list);
     kernel_mark(c, sl, st);
   }
-  spawn_output_kernel<<<1, 1024, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_first_setter, c->d_new_num, c->d_vis_list,
+  spawn_output_kernel<<<1, kTCThreads, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_first_setter, c->d_new_num, c->d_vis_list,
                                           c->d_skip, first, compat, h.egoPoint[2], c->prm.max_tracks, o, po, full, c->d_act_list, c->d_pos, c->d_phase_clock);
   kernel_mark(c, sl, st);
   LMOT_CUDA(c, cudaGetLastError());

@@ -41,6 +41,9 @@ WORKLOAD = "hdl64_120k_64trk_full_pipeline"
 SCENE = dict(n_objects=150, lattice_pitch=3.8, ped_fraction=0.65, seed=1)   # ~64 live tracks at steady state
 KERNEL_NAMES = ("ground_fused", "ccl_cluster", "tile_hist", "seg_offsets", "scatter", "box_fit",
                 "imm_predict_gate", "imm_update", "spawn_output")
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE ground_fused_kernel launch at the bench workload, from the committed
+# `ncu --set full` capture named in profiles/README.md (None until that capture exists for the current kernel)
+TRAFFIC_NCU = None
 KERNELS_PER_FRAME = len(KERNEL_NAMES)   # ground 1 (cooperative; also bins the elevated points) + cluster 1 + box 4 + tracker 3
 
 
@@ -384,7 +387,19 @@ def main():
     n_f = n_elev_sum / K                                         # points that survive the range filter, per frame
     ground_bytes = 16 * n_pts + 16 * n_f + 9600 * 24             # read XYZI + write both clouds + grid
     peak, peak_src = measured_peak_gbs()
-    achieved = ground_bytes / (stage_ms[0] * 1e-3) / 1e9
+    # roofline of the dominant streaming kernel at the bench workload: ground_fused_kernel launched back to back over the
+    # K timed frames of the ring (each launch reads a different frame; ring > L2), CUDA events on the launching stream
+    for i in range(W):
+        ctx.ground_remove_dev(d_frames[i].data_ptr(), n_pts)
+    torch.cuda.synchronize()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record(stream)
+    for i in range(W, W + K):
+        ctx.ground_remove_dev(d_frames[i].data_ptr(), n_pts)
+    r1.record(stream)
+    torch.cuda.synchronize()
+    ground_launch_ms = r0.elapsed_time(r1) / K
+    achieved = ground_bytes / (ground_launch_ms * 1e-3) / 1e9
 
     # ---- (2b) the streaming stage on DENSE 1M-point frames (BASELINE.json configs[4] shape): the size at which an HBM
     # roofline fraction is meaningful for ground removal (at 120 k points the stage is launch / latency bound)
@@ -501,7 +516,9 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "ground_fused_kernel (the whole ground_removal stage: bin + polar grid + classify/partition, one cooperative launch)",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "algorithmic_bytes_per_launch": ground_bytes, "avg_launch_ms": float(stage_ms[0]), "traffic": None},
+                         "algorithmic_bytes_per_launch": ground_bytes, "avg_launch_ms": float(ground_launch_ms),
+                         "launches_timed": K, "traffic": TRAFFIC_NCU,
+                         "note": "latency bound at 120 k points: 3.84 MB is 0.6 us of HBM time, the kernel needs two grid-wide barriers and one count exchange; see roofline_dense_1m"},
             "stage_ms": {n: float(v) for n, v in zip(("ground", "cluster", "box", "tracker"), stage_ms)},
             "kernel_us_warm": ({n: float(1e3 * v / K) for n, v in zip(KERNEL_NAMES, kern_ms)} if kern_ms is not None and len(kern_ms) == len(KERNEL_NAMES) else None),
             "roofline_dense_1m": dense,
