@@ -280,6 +280,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
 }
 
 constexpr int kTilePts = kFusedThreads;             // 1024 points = 16 KB per TMA tile
+
 constexpr int kMaxResTiles = 7;                     // tiles of a CTA's chunk that stay in shared memory (112 KB)
 constexpr int kDescStride = 16;                     // u64 words between two CTAs' count descriptors (128 bytes)
 constexpr int kLookBatch = 5;                       // 5 x 32 >= 148 CTAs: all predecessors in one batch of loads
@@ -371,10 +372,17 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
       if (c != kNoCell && z == z) key = fkey(z);   // NaN z never wins `z < minZ` (ground_removal.cpp:41)
     }
     s_cell[li] = pre ? kPreFiltered : (uint16_t)c;
-    // consecutive HDL-64 returns fall into the same cell: one atomic per distinct cell per warp
-    const unsigned grp = __match_any_sync(0xFFFFFFFFu, c);
-    const unsigned kmin = __reduce_min_sync(grp, key);
-    if (c != kNoCell && lane == __ffs(grp) - 1 && kmin != 0xFFFFFFFFu) atomicMin(&keys[c], kmin);
+    // consecutive HDL-64 returns fall into the same cell: one atomic per distinct cell per warp.  Most warps hold a single
+    // cell (32 returns of one ring span 1.5 degrees, a channel 4.5): they skip the match and reduce over the whole warp.
+    const unsigned c0 = __shfl_sync(0xFFFFFFFFu, c, 0);
+    if (__all_sync(0xFFFFFFFFu, c == c0)) {
+      const unsigned kmin = __reduce_min_sync(0xFFFFFFFFu, key);
+      if (lane == 0 && c0 != kNoCell && kmin != 0xFFFFFFFFu) atomicMin(&keys[c0], kmin);
+    } else {
+      const unsigned grp = __match_any_sync(0xFFFFFFFFu, c);
+      const unsigned kmin = __reduce_min_sync(grp, key);
+      if (c != kNoCell && lane == __ffs(grp) - 1 && kmin != 0xFFFFFFFFu) atomicMin(&keys[c], kmin);
+    }
   }
   phase_mark(phase_clock, 1);
   grid_barrier(bar, bar_base + (unsigned)G);
@@ -394,6 +402,15 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
 
   // ---- phase 3: labels (ground_removal.cpp:221-247), per-warp counts
   unsigned labs = 0;                                // 2 bits per tile: 0 dropped, 1 ground, 2 elevated
+  // hGround of this thread's points in the resident tiles: all loads issued before the first is used (one L2 round trip for
+  // the whole chunk instead of one per tile)
+  float hv[kMaxResTiles];
+#pragma unroll
+  for (int t = 0; t < kMaxResTiles; ++t) {
+    hv[t] = 0.f;
+    const int li = t * kTilePts + tid;
+    if (t < T && li < cnt) { const unsigned c = s_cell[li]; if (c < kPreFiltered) hv[t] = __ldcg(&o_hg[c]); }
+  }
   for (int t = 0; t < T; ++t) {
     const int li = t * kTilePts + tid;
     int lab = 0;
@@ -402,7 +419,12 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
       if (c == kNoCell) lab = p.prefilter ? 3 : 0;      // in neither output; with the node pre-filters on: still an aux point
       else if (c != kPreFiltered) {
         const float z = (t < res_tiles) ? s_pts[li].z : __ldg(&pts[beg + li]).z;
-        const float h = __ldcg(&o_hg[c]);                       // -inf for non-ground cells -> elevated
+        float h;                                                // -inf for non-ground cells -> elevated
+        switch (t) {                                            // (register array: constant indices only)
+          case 0: h = hv[0]; break; case 1: h = hv[1]; break; case 2: h = hv[2]; break; case 3: h = hv[3]; break;
+          case 4: h = hv[4]; break; case 5: h = hv[5]; break; case 6: h = hv[6]; break;
+          default: h = __ldcg(&o_hg[c]);
+        }
         lab = ((double)z < __dadd_rn((double)h, p.tol)) ? 1 : 2;   // :236-246
       }
     }

@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 lmot = importlib.import_module("3d-lidar-multi-object-tracking_b200")
 synth = importlib.import_module("3d-lidar-multi-object-tracking_b200.synth")
 import bench
-K, W = 120, 20
+K, W = int(os.environ.get("DIAG_K", "120")), 20
 ts, frames = bench.make_frames(synth, W + K)
 n = frames.shape[1]
 d = torch.from_numpy(frames).cuda()
@@ -26,10 +26,27 @@ for depth in (1, 4):
     print("frame " + " ".join(f"{x[:9]:>9s}" for x in names))
     for f, row in enumerate(tl[-14:]):
         print(f"{f:5d} " + " ".join(f"{v:9.1f}" for v in row[: len(names)]))
-    if len(tl) > 4:
+    if len(tl) > 12:
         per = (tl[-1, 4] - tl[-11, 4]) / 10
         print(f"tracker completion to tracker completion: {per:.1f} us per frame")
+        ta = tl[-10:, 11] - tl[-11:-1, 4]; tb = tl[-10:, 12] - tl[-10:, 11]; tc = tl[-10:, 13] - tl[-10:, 12]; tail = tl[-10:, 4] - tl[-10:, 13]
+        print(f"  mean over the last 10 frames: prev tracker done -> TA done {ta.mean():.1f}, TA -> TB {tb.mean():.1f}, TB -> TC {tc.mean():.1f}, TC -> stage event {tail.mean():.1f} us")
+        det = tl[-10:, 10] - tl[-10:, 0]
+        print(f"  detection start -> box_fit done {det.mean():.1f} us; box_fit done -> TA done {(tl[-10:, 11] - tl[-10:, 10]).mean():.1f} us")
     tr = ctx.debug_phase_clock()
     if len(tr): print(f"last frame: ground kernel span {(tr[:, 7].max() - tr[:, 0].min()) / 1e3:.2f} us (CTA stamps); "
                       f"spawn_output start->end by %globaltimer: {(int(tr[0, 1]) - int(tr[0, 0])) / 1e3:.2f} us, T = {int(tr[0, 2])}, visible = {int(tr[0, 3])}")
-    ctx.enable_timing(False); ctx.close()
+    ctx.enable_timing(False)
+    # the same loop without timing events: frames/s as bench.py measures `value`
+    ctx.tracker_reset()
+    for i in range(W): ctx.frame_dev(d[i].data_ptr(), n, ts[i])
+    torch.cuda.synchronize(); ctx.sync()
+    import time
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter(); e0.record(st)
+    for i in range(W, W + K): ctx.frame_dev(d[i].data_ptr(), n, ts[i])
+    th = time.perf_counter() - t0
+    ctx.flush(); e1.record(st); torch.cuda.synchronize()
+    hn = ctx.debug_host_ns()
+    print(f"  no timing events: {K / (e0.elapsed_time(e1) * 1e-3):.0f} frames/s ({1e3 * e0.elapsed_time(e1) / K:.1f} us/frame); python loop {1e6 * th / K:.1f} us/frame, inside the library {hn[0] / 1e3 / (W + K):.1f} us/frame")
+    ctx.close()
