@@ -786,8 +786,8 @@ __device__ __forceinline__ bool overseg_cond(const float* c, const float* ab, do
 
 constexpr int kTCThreads = 256;      // ONE small CTA: 16 K registers, so it starts on any SM next to the resident detection kernels
                                      // instead of waiting for a whole SM to drain (a 1024-thread CTA needs the full register file)
-constexpr int kVisChunk = 256;       // visible boxes staged in shared memory per pass
-constexpr int kCandCap = 4096;       // (box, track) pairs that pass the bounds pre-test, per pass
+constexpr int kVisChunk = 128;       // visible boxes staged in shared memory per pass
+constexpr int kCandCap = 1024;       // (box, track) pairs that pass the bounds pre-test, per pass (more: tested inline)
 
 // ------------------------------------------------------------------------------------------------ TC2
 // One frame's results.  spawn_output_kernel fills the DEVICE copy (the tracker is the sequential chain of the pipeline:
@@ -1145,6 +1145,13 @@ int tracker_alloc(Ctx* c) {
   LMOT_CUDA(c, cudaGetLastError());
   const size_t sh = (size_t)kTBWarps * c->gate_words * 32 * sizeof(unsigned short);
   LMOT_CUDA(c, cudaFuncSetAttribute(imm_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+  // the three kernels of the chain (and the publisher) ask for the same shared-memory carve-out, so that an SM does not have to
+  // re-partition its L1 / shared memory between two consecutive kernels of the sequential chain
+  const int carve = 25;     // percent of the maximum (~57 KB): enough for every one of them
+  LMOT_CUDA(c, cudaFuncSetAttribute(imm_predict_gate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+  LMOT_CUDA(c, cudaFuncSetAttribute(imm_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+  LMOT_CUDA(c, cudaFuncSetAttribute(spawn_output_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+  LMOT_CUDA(c, cudaFuncSetAttribute(publish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   return LMOT_OK;
 }
 

@@ -92,3 +92,40 @@ def test_stage_calls_interleave_with_pipeline(pkg, synth, ref_intended):
             assert np.array_equal(r["track_manage"], base[i]["track_manage"])
     finally:
         ctx.close()
+
+
+def test_detect_only_submissions_between_tracked_frames(pkg, synth):
+    """Detection-only submissions take result blocks from the same ring as tracked frames; the tracker's incremental outputs
+    (each frame's block is seeded from the previous TRACKED frame's block) must not notice them.  Small ring -> wraps."""
+    import torch
+    frames = list(synth.frames(synth.SceneConfig(seed=16, n_objects=70, lattice_pitch=4.2), 16))
+    base = _run_sync(pkg, frames, 1)
+    prm = pkg.default_params()
+    prm.pipeline_depth = 3
+    prm.result_ring = 3
+    ctx = pkg.Lmot(prm)
+    try:
+        st = torch.cuda.Stream()
+        ctx.set_stream(st.cuda_stream)
+        dev = [torch.from_numpy(p).cuda() for _, p in frames]
+        torch.cuda.synchronize()
+        for i, ((ts, p), d) in enumerate(zip(frames, dev)):
+            ctx.frame_dev(d.data_ptr(), len(p), ts, 2.0 + 0.1 * i, 0.01 * i)
+            if i % 3 == 1:
+                ctx.detect_dev(dev[(i + 5) % len(dev)].data_ptr(), len(p))
+            if i in (6, 15):
+                ctx.frame_dev(d.data_ptr(), len(p), ts + 1, 2.0 + 0.1 * i, 0.01 * i)   # undo below: compare against a matching baseline
+        last = ctx.frame_fetch()
+    finally:
+        ctx.close()
+    # baseline with the same call sequence, frame at a time
+    ctx = pkg.Lmot()
+    try:
+        for i, (ts, p) in enumerate(frames):
+            want = ctx.frame(p, ts, 2.0 + 0.1 * i, 0.01 * i)
+            if i in (6, 15):
+                want = ctx.frame(p, ts + 1, 2.0 + 0.1 * i, 0.01 * i)
+    finally:
+        ctx.close()
+    _same(last, want)
+    assert len(base) == len(frames)
