@@ -39,6 +39,13 @@ constexpr int lifeTimeThres = 3;                        // :42
 constexpr double distanceThres = 99;                    // :38
 constexpr double bbYawChangeThres = 0.2;                // :46
 
+// Programmatic dependent launch (sm_90+): the three kernels of the tracker chain are launched back to back on one stream.
+// A kernel calls pdl_launch_dependents() at its start so that the NEXT kernel's CTAs may already become resident and run up to
+// their pdl_wait(), which returns once the whole preceding grid has finished and its writes are visible -- the dependent
+// kernel's launch latency leaves the sequential chain.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ double wrap_pi(double a) {   // the reference's while loops; NaN falls through
   // (beyond 1e4 rad the reference's loop would need thousands of iterations -- millions for a diverged filter --
   //  so the bulk is removed in one step there; such a track is already past any parity claim)
@@ -166,6 +173,7 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
                         double dt, unsigned* __restrict__ gate, unsigned* __restrict__ setter, int* __restrict__ first_setter,
                         uint8_t* __restrict__ skip, int words, const int* __restrict__ act_list) {
   __shared__ TAShared sh;
+  pdl_launch_dependents();                 // TB's CTAs may line up behind this grid
   const int tid = threadIdx.x, lane = tid & 31, model = tid >> 5;
   const int n_act = trk[CNT_N_ACT];
   const int M = det[CNT_N_BOXES];
@@ -519,6 +527,8 @@ imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, 
   extern __shared__ unsigned short s_list_all[];          // per warp: indices of the gated boxes, in box order
   __shared__ TrackState s_trk[kTBWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_wait();                              // TA has finished (gate rows, first_setter, predicted states are visible)
+  pdl_launch_dependents();                 // TC's CTA may line up behind this grid
   const int n_act = trk[CNT_N_ACT];
   const int M = det[CNT_N_BOXES];
   unsigned short* s_list = s_list_all + (size_t)warp * words * 32;
@@ -855,6 +865,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
                     int* __restrict__ first_setter, int* __restrict__ imax_arr, int* __restrict__ vis_list,
                     uint8_t* __restrict__ has5_arr, int first_frame, int compat_first, double ego_yaw, int max_tracks, OutPtrs o,
                     OutPtrs prev, int full, int* __restrict__ act_list, double4* __restrict__ pos, unsigned long long* __restrict__ trace) {
+  pdl_wait();                              // TB has finished
   if (trace && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[0] = t; }
   __shared__ int s_w[33];
   __shared__ int s_carry, s_carry2, s_nvis, s_ncand, s_ncont;
@@ -1145,13 +1156,6 @@ int tracker_alloc(Ctx* c) {
   LMOT_CUDA(c, cudaGetLastError());
   const size_t sh = (size_t)kTBWarps * c->gate_words * 32 * sizeof(unsigned short);
   LMOT_CUDA(c, cudaFuncSetAttribute(imm_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-  // the three kernels of the chain (and the publisher) ask for the same shared-memory carve-out, so that an SM does not have to
-  // re-partition its L1 / shared memory between two consecutive kernels of the sequential chain
-  const int carve = 25;     // percent of the maximum (~57 KB): enough for every one of them
-  LMOT_CUDA(c, cudaFuncSetAttribute(imm_predict_gate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-  LMOT_CUDA(c, cudaFuncSetAttribute(imm_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-  LMOT_CUDA(c, cudaFuncSetAttribute(spawn_output_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-  LMOT_CUDA(c, cudaFuncSetAttribute(publish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   return LMOT_OK;
 }
 
@@ -1213,12 +1217,30 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
     imm_predict_gate_kernel<<<c->trk_ctas, kTAThreads, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, dt, c->d_gate, c->d_setter,
                                                                  c->d_first_setter, c->d_skip, c->gate_words, c->d_act_list);
     kernel_mark(c, sl, st);
-    imm_update_kernel<<<c->trk_ctas / kTBWarps + 1, kTBWarps * 32, sh, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_gate,
-                                                                           c->d_first_setter, c->d_skip, c->gate_words, c->d_act_list);
+    // TB and TC: programmatic dependent launches (their CTAs wait on the device for the preceding grid, see pdl_wait); timing
+    // mode records an event between the kernels, which needs the ordinary full serialisation
+    cudaLaunchAttribute pdl;
+    pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl.val.programmaticStreamSerializationAllowed = c->timing ? 0 : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(c->trk_ctas / kTBWarps + 1); cfg.blockDim = dim3(kTBWarps * 32); cfg.dynamicSmemBytes = sh; cfg.stream = st;
+    cfg.attrs = &pdl; cfg.numAttrs = 1;
+    LMOT_CUDA(c, cudaLaunchKernelEx(&cfg, imm_update_kernel, c->d_tracks, (const int*)c->d_trk_counters, (const int*)det, d_boxes,
+                                    (const unsigned*)c->d_gate, (const int*)c->d_first_setter, (const uint8_t*)c->d_skip, c->gate_words,
+                                    (const int*)c->d_act_list));
     kernel_mark(c, sl, st);
   }
-  spawn_output_kernel<<<1, kTCThreads, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_first_setter, c->d_new_num, c->d_vis_list,
-                                          c->d_skip, first, compat, h.egoPoint[2], c->prm.max_tracks, o, po, full, c->d_act_list, c->d_pos, c->d_phase_clock);
+  {
+    cudaLaunchAttribute pdl;
+    pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl.val.programmaticStreamSerializationAllowed = (c->timing || (first && compat)) ? 0 : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(kTCThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cfg.attrs = &pdl; cfg.numAttrs = 1;
+    LMOT_CUDA(c, cudaLaunchKernelEx(&cfg, spawn_output_kernel, c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_first_setter, c->d_new_num,
+                                    c->d_vis_list, c->d_skip, first, compat, h.egoPoint[2], c->prm.max_tracks, o, po, full, c->d_act_list,
+                                    c->d_pos, c->d_phase_clock));
+  }
   kernel_mark(c, sl, st);
   LMOT_CUDA(c, cudaGetLastError());
   h.timestamp = timestamp;
