@@ -79,7 +79,7 @@ ABI_SYMBOLS = [
     "lmot_frame_dev", "lmot_frame_fetch", "lmot_frame_submit", "lmot_frame_collect", "lmot_frames_in_flight", "lmot_frame_ready", "lmot_flush",
     "lmot_ground_remove_dev", "lmot_detect_dev", "lmot_sync",
     "lmot_origin_points", "lmot_tracker_table", "lmot_tracker_set_num_tracks", "lmot_tracker_reset", "lmot_tracker_num_tracks", "lmot_tracker_dump", "lmot_tracker_load",
-    "lmot_debug_polar_grid", "lmot_debug_cell_index", "lmot_debug_label_grid", "lmot_debug_phase_clock", "lmot_debug_timeline", "lmot_selftest_atan2f",
+    "lmot_debug_polar_grid", "lmot_debug_cell_index", "lmot_debug_label_grid", "lmot_debug_phase_clock", "lmot_debug_timeline", "lmot_debug_tracker_trace", "lmot_selftest_atan2f",
     "lmot_enable_timing", "lmot_last_stage_ms", "lmot_last_kernel_ms", "lmot_debug_host_ns",
 ]
 
@@ -363,6 +363,14 @@ class Lmot:
         self._chk(self.lib.lmot_debug_timeline(self.h, buf.ctypes.data_as(C.POINTER(C.c_float)), 64, C.byref(n), C.byref(stride)))
         flat = buf.reshape(-1)[: n.value * stride.value].reshape(n.value, stride.value) if n.value else buf[:0]
         return flat
+
+    def debug_tracker_trace(self):
+        """(32, 8) uint64 ns, oldest step first: TA start, TA end, TB start, TB end, TC start, TC end, tracks, visible."""
+        buf = np.zeros((32, 8), np.uint64); nxt = C.c_int(0)
+        self._chk(self.lib.lmot_debug_tracker_trace(self.h, buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), C.byref(nxt)))
+        for k in (0, 2, 4):
+            buf[:, k] = ~buf[:, k]        # starts are stored complemented (see trace_start in tracker.cu)
+        return np.roll(buf, -nxt.value, axis=0)
 
     def debug_phase_clock(self):
         """First call arms the phase clock of ground_fused_kernel; later calls -> (n_ctas, 8) uint64 ns stamps of the last launch."""

@@ -382,7 +382,7 @@ void lmot_destroy(lmot_ctx* ctx) {
   for (int i = 0; i < c->n_slots; ++i) slot_destroy(&c->slots[i]);
   for (int i = 0; i < c->n_results; ++i) result_destroy(&c->results[i]);
   tracker_free(c);
-  cudaFree(c->d_phase_clock);
+  cudaFree(c->d_phase_clock); cudaFree(c->d_trk_trace);
   cudaFree(c->d_mt_raw);
   if (c->trk_stream) cudaStreamDestroy(c->trk_stream);
   if (c->pub_stream) cudaStreamDestroy(c->pub_stream);
@@ -867,6 +867,19 @@ int lmot_debug_timeline(lmot_ctx* ctx, float* out, int cap_frames, int* n_frames
   return LMOT_OK;
 }
 
+// diagnostic: %globaltimer spans (ns) of the tracker kernels of the last 32 tracker steps: out[32][8] = TA first start, TA last end,
+// TB start, TB end, TC start, TC end, tracks in the table, visible tracks; *next = ring position of the NEXT step (oldest entry)
+int lmot_debug_tracker_trace(lmot_ctx* ctx, unsigned long long* out, int* next) {
+  if (!ctx || !out) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  int rc = lmot_sync(ctx);
+  if (rc) return rc;
+  if (!c->d_trk_trace) return LMOT_ERR_STATE;
+  LMOT_CUDA(c, cudaMemcpy(out, c->d_trk_trace, 32 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (next) *next = (int)(c->trk_frames % 32);
+  return LMOT_OK;
+}
+
 // diagnostic: switch the phase clock of ground_fused_kernel on (allocates [CTAs][8] u64) and read the last launch's stamps
 int lmot_debug_phase_clock(lmot_ctx* ctx, unsigned long long* out, int cap_ctas, int* n_ctas) {
   if (!ctx) return LMOT_ERR_INVALID;
@@ -876,6 +889,8 @@ int lmot_debug_phase_clock(lmot_ctx* ctx, unsigned long long* out, int cap_ctas,
   if (!c->d_phase_clock) {
     LMOT_CUDA(c, cudaMalloc(&c->d_phase_clock, (size_t)c->fused_max_ctas * 8 * sizeof(unsigned long long)));
     LMOT_CUDA(c, cudaMemset(c->d_phase_clock, 0, (size_t)c->fused_max_ctas * 8 * sizeof(unsigned long long)));
+    LMOT_CUDA(c, cudaMalloc(&c->d_trk_trace, 32 * 8 * sizeof(unsigned long long)));
+    LMOT_CUDA(c, cudaMemset(c->d_trk_trace, 0, 32 * 8 * sizeof(unsigned long long)));
     if (n_ctas) *n_ctas = 0;
     return LMOT_OK;
   }

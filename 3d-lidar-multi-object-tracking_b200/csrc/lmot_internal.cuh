@@ -166,6 +166,8 @@ struct Ctx {
   int max_points = 0, max_sort_tiles = 0, fit_ctas = 296, n_mt_raw = 0;
   bool coop_launch = false;            // LMOT_COOP=1: cudaLaunchCooperativeKernel for the ground kernel (A/B diagnostics)
   int fused_max_ctas = 0;              // co-residency limit of the cooperative ground kernel on this device
+  unsigned long long* d_trk_trace = nullptr;     // diagnostic: [32][8] per-frame kernel spans of the tracker chain (same switch)
+  unsigned long long trk_frames = 0;
   unsigned long long* d_phase_clock = nullptr;   // diagnostic: [CTAs][8] %globaltimer stamps of the last ground launch (lmot_debug_phase_clock)
   int last_ground_ctas = 0;
   int pts_per_cta = 768;               // target chunk of the fused ground kernel (LMOT_PTS_PER_CTA overrides, tuning only)

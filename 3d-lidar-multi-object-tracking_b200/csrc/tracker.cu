@@ -46,6 +46,14 @@ constexpr double bbYawChangeThres = 0.2;                // :46
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// diagnostic (scripts/diag_timeline.py): first start / last end of a kernel's CTAs by %globaltimer; trace == nullptr in production
+__device__ __forceinline__ void trace_start(unsigned long long* trace, int k) {
+  if (trace && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(&trace[2 * k], ~t); }   // max of ~t == ~(earliest start): every entry rests at 0
+}
+__device__ __forceinline__ void trace_end(unsigned long long* trace, int k) {
+  if (trace && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(&trace[2 * k + 1], t); }
+}
+
 __device__ __forceinline__ double wrap_pi(double a) {   // the reference's while loops; NaN falls through
   // (beyond 1e4 rad the reference's loop would need thousands of iterations -- millions for a diverged filter --
   //  so the bulk is removed in one step there; such a track is already past any parity claim)
@@ -171,9 +179,11 @@ __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(
 __global__ void __launch_bounds__(kTAThreads, 4)     // <= 128 registers: a CTA (16 K registers) fits on an SM next to a ground-kernel CTA (47 K)
 imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, const int* __restrict__ det, const float* __restrict__ boxes,
                         double dt, unsigned* __restrict__ gate, unsigned* __restrict__ setter, int* __restrict__ first_setter,
-                        uint8_t* __restrict__ skip, int words, const int* __restrict__ act_list) {
+                        uint8_t* __restrict__ skip, int words, const int* __restrict__ act_list, unsigned long long* trace) {
   __shared__ TAShared sh;
   pdl_launch_dependents();                 // TB's CTAs may line up behind this grid
+  trace_start(trace, 0);
+  struct TraceEnd { unsigned long long* t; __device__ ~TraceEnd() { __syncthreads(); trace_end(t, 0); } } trace_at_exit{trace};
   const int tid = threadIdx.x, lane = tid & 31, model = tid >> 5;
   const int n_act = trk[CNT_N_ACT];
   const int M = det[CNT_N_BOXES];
@@ -523,12 +533,14 @@ __device__ void update_bb(TrackState& t) {
 __global__ void __launch_bounds__(kTBWarps * 32)
 imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, const int* __restrict__ det, const float* __restrict__ boxes,
                   const unsigned* __restrict__ gate, const int* __restrict__ first_setter, const uint8_t* __restrict__ skip,
-                  int words, const int* __restrict__ act_list) {
+                  int words, const int* __restrict__ act_list, unsigned long long* trace) {
   extern __shared__ unsigned short s_list_all[];          // per warp: indices of the gated boxes, in box order
   __shared__ TrackState s_trk[kTBWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   pdl_wait();                              // TA has finished (gate rows, first_setter, predicted states are visible)
   pdl_launch_dependents();                 // TC's CTA may line up behind this grid
+  trace_start(trace, 1);
+  struct TraceEnd { unsigned long long* t; __device__ ~TraceEnd() { __syncthreads(); trace_end(t, 1); } } trace_at_exit{trace};
   const int n_act = trk[CNT_N_ACT];
   const int M = det[CNT_N_BOXES];
   unsigned short* s_list = s_list_all + (size_t)warp * words * 32;
@@ -866,7 +878,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
                     uint8_t* __restrict__ has5_arr, int first_frame, int compat_first, double ego_yaw, int max_tracks, OutPtrs o,
                     OutPtrs prev, int full, int* __restrict__ act_list, double4* __restrict__ pos, unsigned long long* __restrict__ trace) {
   pdl_wait();                              // TB has finished
-  if (trace && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[0] = t; }
+  trace_start(trace, 2);
   __shared__ int s_w[33];
   __shared__ int s_carry, s_carry2, s_nvis, s_ncand, s_ncont;
   __shared__ unsigned char s_cont[kVisChunk];           // visible boxes that sit inside another visible box
@@ -1086,7 +1098,8 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
     o.hdr[HDR_N_ELEV] = det[CNT_N_ELEV]; o.hdr[HDR_N_GROUND] = det[CNT_N_GROUND]; o.hdr[HDR_NUM_CLUSTER] = det[CNT_NUM_CLUSTER];
     o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = s_carry; o.hdr[HDR_ERROR] = det[CNT_ERROR];
     det[CNT_ERROR] = 0;
-    if (trace) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[1] = t; trace[2] = (unsigned long long)T; trace[3] = (unsigned long long)nv; }
+    trace_end(trace, 2);
+    if (trace) { trace[6] = (unsigned long long)T; trace[7] = (unsigned long long)nv; }
   }
 }
 
@@ -1202,6 +1215,12 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
   int* det = const_cast<int*>(det_counters);
   const int first = h.init ? 0 : 1;
   const int compat = c->prm.oracle_compat_first_frame ? 1 : 0;
+  unsigned long long* trace = nullptr;     // diagnostic: [32 frames][8] first start / last end of TA, TB, TC
+  if (c->d_trk_trace) {
+    trace = c->d_trk_trace + (size_t)(c->trk_frames % 32) * 8;
+    LMOT_CUDA(c, cudaMemsetAsync(trace, 0, 64, st));
+  }
+  ++c->trk_frames;
   const int full = c->act_valid ? 0 : 1;   // the table was written from the host since the last frame: rebuild the side arrays
   if (full) {
     LMOT_CUDA(c, cudaMemsetAsync(c->d_trk_counters + CNT_N_ACT, 0, sizeof(int), st));
@@ -1215,7 +1234,7 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
     const double dt = first ? 0.0 : (timestamp - h.timestamp) / 1000000.0;     // :807
     const size_t sh = (size_t)kTBWarps * c->gate_words * 32 * sizeof(unsigned short);
     imm_predict_gate_kernel<<<c->trk_ctas, kTAThreads, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, dt, c->d_gate, c->d_setter,
-                                                                 c->d_first_setter, c->d_skip, c->gate_words, c->d_act_list);
+                                                                 c->d_first_setter, c->d_skip, c->gate_words, c->d_act_list, trace);
     kernel_mark(c, sl, st);
     // TB and TC: programmatic dependent launches (their CTAs wait on the device for the preceding grid, see pdl_wait); timing
     // mode records an event between the kernels, which needs the ordinary full serialisation
@@ -1227,7 +1246,7 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
     cfg.attrs = &pdl; cfg.numAttrs = 1;
     LMOT_CUDA(c, cudaLaunchKernelEx(&cfg, imm_update_kernel, c->d_tracks, (const int*)c->d_trk_counters, (const int*)det, d_boxes,
                                     (const unsigned*)c->d_gate, (const int*)c->d_first_setter, (const uint8_t*)c->d_skip, c->gate_words,
-                                    (const int*)c->d_act_list));
+                                    (const int*)c->d_act_list, trace));
     kernel_mark(c, sl, st);
   }
   {
@@ -1239,7 +1258,7 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
     cfg.attrs = &pdl; cfg.numAttrs = 1;
     LMOT_CUDA(c, cudaLaunchKernelEx(&cfg, spawn_output_kernel, c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_first_setter, c->d_new_num,
                                     c->d_vis_list, c->d_skip, first, compat, h.egoPoint[2], c->prm.max_tracks, o, po, full, c->d_act_list,
-                                    c->d_pos, c->d_phase_clock));
+                                    c->d_pos, trace));
   }
   kernel_mark(c, sl, st);
   LMOT_CUDA(c, cudaGetLastError());

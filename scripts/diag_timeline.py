@@ -48,5 +48,11 @@ for depth in (1, 4):
     th = time.perf_counter() - t0
     ctx.flush(); e1.record(st); torch.cuda.synchronize()
     hn = ctx.debug_host_ns()
+    tt = ctx.debug_tracker_trace().astype(np.int64)[-12:]
+    ta, tb, tc = (tt[:, 1] - tt[:, 0]) / 1e3, (tt[:, 3] - tt[:, 2]) / 1e3, (tt[:, 5] - tt[:, 4]) / 1e3
+    g1, g2, g3 = (tt[:, 2] - tt[:, 1]) / 1e3, (tt[:, 4] - tt[:, 3]) / 1e3, (tt[1:, 0] - tt[:-1, 5]) / 1e3
+    print(f"  tracker chain by %globaltimer, no events in the streams (mean of the last 12 steps, us): TA {ta.mean():.1f} | gap {g1.mean():.1f} | "
+          f"TB {tb.mean():.1f} | gap {g2.mean():.1f} | TC {tc.mean():.1f} | gap to the next frame's TA {g3.mean():.1f}  "
+          f"(TA start to next TA start {((tt[1:, 0] - tt[:-1, 0]) / 1e3).mean():.1f})")
     print(f"  no timing events: {K / (e0.elapsed_time(e1) * 1e-3):.0f} frames/s ({1e3 * e0.elapsed_time(e1) / K:.1f} us/frame); python loop {1e6 * th / K:.1f} us/frame, inside the library {hn[0] / 1e3 / (W + K):.1f} us/frame")
     ctx.close()
