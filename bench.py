@@ -42,8 +42,9 @@ SCENE = dict(n_objects=150, lattice_pitch=3.8, ped_fraction=0.65, seed=1)   # ~6
 KERNEL_NAMES = ("ground_fused", "ccl_cluster", "tile_hist", "seg_offsets", "scatter", "box_fit",
                 "imm_predict_gate", "imm_update", "spawn_output")
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE ground_fused_kernel launch at the bench workload, from the committed
-# `ncu --set full` capture named in profiles/README.md (None until that capture exists for the current kernel)
-TRAFFIC_NCU = None
+# `ncu --set full` capture profiles/r1z_ncu_full_ground.csv (2.040 MB read: the frame once, plus the polar grid; 8-11 KB
+# written: the 3.9 MB of output clouds stay in the 126 MB L2 within the measured launch)
+TRAFFIC_NCU = 2.05e6
 KERNELS_PER_FRAME = len(KERNEL_NAMES)   # ground 1 (cooperative; also bins the elevated points) + cluster 1 + box 4 + tracker 3
 
 
