@@ -365,9 +365,12 @@ class Lmot:
         return flat
 
     def debug_tracker_trace(self):
-        """(32, 8) uint64 ns, oldest step first: TA start, TA end, TB start, TB end, TC start, TC end, tracks, visible."""
-        buf = np.zeros((32, 8), np.uint64); nxt = C.c_int(0)
-        self._chk(self.lib.lmot_debug_tracker_trace(self.h, buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), C.byref(nxt)))
+        """(32, 8) uint64 ns, oldest step first: TA start, TA end, TB start, TB end, TC start, TC end, latest start of a working TA CTA, same for TB."""
+        raw = np.zeros(32 * 8 + 32, np.uint64); nxt = C.c_int(0)
+        self._chk(self.lib.lmot_debug_tracker_trace(self.h, raw.ctypes.data_as(C.POINTER(C.c_ulonglong)), C.byref(nxt)))
+        buf = raw[:256].reshape(32, 8).copy()
+        self.last_tc_phases = raw[256:272].copy()
+        self.last_tb_phases = raw[272:].copy()        # same for the first track's warp of imm_update_kernel       # %globaltimer stamps inside the last spawn_output_kernel (fast path)
         for k in (0, 2, 4):
             buf[:, k] = ~buf[:, k]        # starts are stored complemented (see trace_start in tracker.cu)
         return np.roll(buf, -nxt.value, axis=0)

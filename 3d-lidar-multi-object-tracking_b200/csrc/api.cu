@@ -353,6 +353,7 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   if (const char* e = getenv("LMOT_COOP")) c->coop_launch = atoi(e) != 0;
   if (const char* e = getenv("LMOT_TRK_CTAS")) { const int v = atoi(e); if (v >= 8 && v <= 4096) c->trk_ctas = v; }     // tuning only
   if (const char* e = getenv("LMOT_FIT_CTAS")) { const int v = atoi(e); if (v >= 8 && v <= 4096) c->fit_ctas = v; }
+  if (const char* e = getenv("LMOT_GROUND_HALF")) c->ground_half_sms = atoi(e) != 0;
   if (const char* e = getenv("LMOT_PTS_PER_CTA")) { const int v = atoi(e); if (v >= 256 && v <= 16384) c->pts_per_cta = v; }
   int rc = LMOT_OK;
   // The tracker is the one sequential chain of the pipeline (frame f+1's tracker needs frame f's table): its CTAs get
@@ -868,14 +869,14 @@ int lmot_debug_timeline(lmot_ctx* ctx, float* out, int cap_frames, int* n_frames
 }
 
 // diagnostic: %globaltimer spans (ns) of the tracker kernels of the last 32 tracker steps: out[32][8] = TA first start, TA last end,
-// TB start, TB end, TC start, TC end, tracks in the table, visible tracks; *next = ring position of the NEXT step (oldest entry)
+// TB start, TB end, TC start, TC end, latest start of a TA CTA that had a track, same for TB; then out[256..271] = phase stamps of the last spawn_output_kernel (fast path), out[272..287] = of the first track's warp of the last imm_update_kernel; *next = ring position of the NEXT step (oldest entry)
 int lmot_debug_tracker_trace(lmot_ctx* ctx, unsigned long long* out, int* next) {
   if (!ctx || !out) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
   int rc = lmot_sync(ctx);
   if (rc) return rc;
   if (!c->d_trk_trace) return LMOT_ERR_STATE;
-  LMOT_CUDA(c, cudaMemcpy(out, c->d_trk_trace, 32 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  LMOT_CUDA(c, cudaMemcpy(out, c->d_trk_trace, (32 * 8 + 32) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   if (next) *next = (int)(c->trk_frames % 32);
   return LMOT_OK;
 }
@@ -889,8 +890,8 @@ int lmot_debug_phase_clock(lmot_ctx* ctx, unsigned long long* out, int cap_ctas,
   if (!c->d_phase_clock) {
     LMOT_CUDA(c, cudaMalloc(&c->d_phase_clock, (size_t)c->fused_max_ctas * 8 * sizeof(unsigned long long)));
     LMOT_CUDA(c, cudaMemset(c->d_phase_clock, 0, (size_t)c->fused_max_ctas * 8 * sizeof(unsigned long long)));
-    LMOT_CUDA(c, cudaMalloc(&c->d_trk_trace, 32 * 8 * sizeof(unsigned long long)));
-    LMOT_CUDA(c, cudaMemset(c->d_trk_trace, 0, 32 * 8 * sizeof(unsigned long long)));
+    LMOT_CUDA(c, cudaMalloc(&c->d_trk_trace, (32 * 8 + 32) * sizeof(unsigned long long)));
+    LMOT_CUDA(c, cudaMemset(c->d_trk_trace, 0, (32 * 8 + 32) * sizeof(unsigned long long)));
     if (n_ctas) *n_ctas = 0;
     return LMOT_OK;
   }

@@ -600,7 +600,16 @@ int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bo
   // never more than can be co-resident
   int G = (n + c->pts_per_cta - 1) / c->pts_per_cta;
   if (G < kMinCtas) G = kMinCtas;
-  if (G > c->fused_max_ctas) G = c->fused_max_ctas;
+  int cap = c->fused_max_ctas;
+  // Inside the frame pipeline the kernel keeps to HALF of the SMs (as long as its chunks still fit in shared memory): a
+  // 1024-thread CTA holds 47 K of an SM's 64 K registers, and with the box-fitting CTAs of another frame next to it the SM has no
+  // room for a CTA of the tracker chain -- measured: the last imm_predict_gate CTA started 10-15 us after the first one, the
+  // sequential chain (the bound of frames/s) was 84 us per frame instead of 55.  Detection has >100 us of slack per frame.
+  if (fuse_count && c->ground_half_sms) {
+    const int half = cap / 2 > kMinCtas ? cap / 2 : kMinCtas;
+    if ((long long)half * kMaxResTiles * kTilePts >= (long long)n) cap = half;
+  }
+  if (G > cap) G = cap;
   int chunk = (n + G - 1) / G;
   if (chunk > kMaxTiles * kTilePts) return LMOT_ERR_CAPACITY;
   const int parity = (int)(s->epoch & 1u);

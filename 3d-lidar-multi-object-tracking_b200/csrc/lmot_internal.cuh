@@ -170,6 +170,7 @@ struct Ctx {
   unsigned long long trk_frames = 0;
   unsigned long long* d_phase_clock = nullptr;   // diagnostic: [CTAs][8] %globaltimer stamps of the last ground launch (lmot_debug_phase_clock)
   int last_ground_ctas = 0;
+  bool ground_half_sms = true;         // frame pipeline: ground kernel on half of the SMs (ground.cu ground_launch; LMOT_GROUND_HALF=0 disables, A/B only)
   int pts_per_cta = 768;               // target chunk of the fused ground kernel (LMOT_PTS_PER_CTA overrides, tuning only)
   unsigned long long* d_mt_raw = nullptr;  // raw mt19937_64(0) outputs (shared, read only)
 
@@ -191,6 +192,7 @@ struct Ctx {
   cudaStream_t pub_stream = nullptr;   // device -> host publication of finished frames
   int* d_act_list = nullptr;           // [max_tracks] tracks to visit next frame (built by spawn_output_kernel)
   double4* d_pos = nullptr;            // [max_tracks] packed (x, y, yaw, -) of every track's merged state
+  void* d_summary = nullptr;           // [max_tracks] ActSummary (tracker.cu): what TC needs of each active track, written by TB
   Result* last_trk_res = nullptr;      // result block of the previous tracker step (its device copy seeds the next one)
   bool act_valid = false;              // false after the table was written from the host: rebuilt before the next step
   int trk_ctas = 592, gate_words = 0;

@@ -187,6 +187,7 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
   const int tid = threadIdx.x, lane = tid & 31, model = tid >> 5;
   const int n_act = trk[CNT_N_ACT];
   const int M = det[CNT_N_BOXES];
+  if (trace && tid == 0 && (int)blockIdx.x < n_act) { unsigned long long tn; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn)); atomicMax(&trace[6], tn); }   // latest start of a CTA that has a track
   const double kStdA = (model == 2) ? 3.0 : 2.0;       // std_a_{cv,ctrv,rm}_ ukf.cpp:68-70 (= std_*_yawdd_ :71-73)
   const double lambda_aug = 3 - 7;
   const double w0 = lambda_aug / (lambda_aug + 7), wi = 0.5 / (7 + lambda_aug);
@@ -459,6 +460,20 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
 
 // ------------------------------------------------------------------------------------------------ TB
 constexpr int kTBWarps = 4;
+
+// What TC needs of an active track, 128 bytes per entry of the active list, written by TB (which has the record staged in
+// shared memory anyway) and read by TC with one coalesced load: TC's merge / spawn / output logic is a chain of dependent
+// steps, and every step that fetched its operands from the 1.6 KB records was one more L2 round trip on the sequential chain.
+struct __align__(16) ActSummary {
+  double x, y, yaw, v;               // merged state x_merge_(0), (1), (3), (2)
+  double initx, inity;               // initMeas
+  double mp0, mp1, mp2;              // modeProb
+  float bb[8];                       // BBox corners 0..3, (x, y)
+  int k, trackNum, lifetime;
+  unsigned char isStatic, isVis, pad[2];
+  int pad2[2];
+};
+static_assert(sizeof(ActSummary) == 128, "ActSummary is copied as sixteen 8-byte words");
 static_assert(sizeof(TrackState) % 8 == 0, "TrackState is copied as 8-byte words");
 constexpr int kTrackWords = (int)(sizeof(TrackState) / 8);
 
@@ -494,84 +509,124 @@ __device__ void update_box_yaw(float bb[][3], int n, double cpx, double cpy, dou
   }
 }
 
-// updateBB :565-653, executed by one lane
-__device__ void update_bb(TrackState& t) {
+// updateBB :565-653, executed by the whole warp on the track staged in shared memory.  The reference's statements in its
+// order; what is independent runs on different lanes: the two centre points and the two areas (lane 0: BBox, lane 1:
+// bestBBox -- same code, different operand), the sixteen corner rotations (lane = corner).  getBBoxYaw of an UNCHANGED box
+// (deltaArea >= 0) is the same pure function of the same operands as the first evaluation and is not repeated.
+__device__ void update_bb_warp(TrackState& t, int lane) {
   if (!t.isVisBB) return;
   if (t.nBest == 0) {
-    for (int p = 0; p < 8; ++p) for (int c = 0; c < 3; ++c) t.bestBBox[p][c] = t.BBox[p][c];
-    t.nBest = t.nBBox;
-    t.bestYaw = bbox_yaw(t.BBox, t.x[0][3]);
+    const float v = (lane < 24) ? (&t.BBox[0][0])[lane] : 0.f;
+    __syncwarp();
+    if (lane < 24) (&t.bestBBox[0][0])[lane] = v;
+    if (lane == 0) { t.nBest = t.nBBox; t.bestYaw = bbox_yaw(t.BBox, t.x[0][3]); }
+    __syncwarp();
     return;
   }
-  double cpx, cpy, bcx, bcy;
-  cp_from_corners(t.BBox[0][0], t.BBox[0][1], t.BBox[1][0], t.BBox[1][1], t.BBox[2][0], t.BBox[2][1], t.BBox[3][0], t.BBox[3][1], cpx, cpy);
-  cp_from_corners(t.bestBBox[0][0], t.bestBBox[0][1], t.bestBBox[1][0], t.bestBBox[1][1], t.bestBBox[2][0], t.bestBBox[2][1],
-                  t.bestBBox[3][0], t.bestBBox[3][1], bcx, bcy);
+  const float (*bbp)[3] = (lane == 1) ? t.bestBBox : t.BBox;
+  double cx, cy;
+  cp_from_corners(bbp[0][0], bbp[0][1], bbp[1][0], bbp[1][1], bbp[2][0], bbp[2][1], bbp[3][0], bbp[3][1], cx, cy);
+  const double ar = bbox_area(bbp);
+  const double cpx = __shfl_sync(0xFFFFFFFFu, cx, 0), cpy = __shfl_sync(0xFFFFFFFFu, cy, 0);
+  const double bcx = __shfl_sync(0xFFFFFFFFu, cx, 1), bcy = __shfl_sync(0xFFFFFFFFu, cy, 1);
   const double dtx = cpx - bcx, dty = cpy - bcy;
-  const double yaw = bbox_yaw(t.BBox, t.x[0][3]);
-  const double deltaArea = bbox_area(t.BBox) - bbox_area(t.bestBBox);
+  const double ukfYaw = t.x[0][3];
+  const double yaw = bbox_yaw(t.BBox, ukfYaw);
+  const double deltaArea = __shfl_sync(0xFFFFFFFFu, ar, 0) - __shfl_sync(0xFFFFFFFFu, ar, 1);
+  const int nB = t.nBBox;
+  __syncwarp();
   if (deltaArea < 0) {                         // updateVisBoxArea :496-510
-    for (int i = 0; i < t.nBBox; ++i) {
-      t.BBox[i][0] = (float)(t.bestBBox[i][0] + dtx);
-      t.BBox[i][1] = (float)(t.bestBBox[i][1] + dty);
+    if (lane < nB) {
+      t.BBox[lane][0] = (float)(t.bestBBox[lane][0] + dtx);
+      t.BBox[lane][1] = (float)(t.bestBBox[lane][1] + dty);
     }
   } else if (deltaArea > 0) {
-    for (int p = 0; p < 8; ++p) for (int c = 0; c < 3; ++c) t.bestBBox[p][c] = t.BBox[p][c];
-    t.nBest = t.nBBox;
+    const float v = (lane < 24) ? (&t.BBox[0][0])[lane] : 0.f;
+    if (lane < 24) (&t.bestBBox[0][0])[lane] = v;
+    if (lane == 0) t.nBest = nB;
   }
-  const double currentYaw = bbox_yaw(t.BBox, t.x[0][3]);
+  __syncwarp();
+  const double currentYaw = (deltaArea < 0) ? bbox_yaw(t.BBox, ukfYaw) : yaw;
   const double DiffYaw = yaw - currentYaw;
   if (fabs(DiffYaw) > bbYawChangeThres) {
   } else if (fabs(DiffYaw) < bbYawChangeThres) {
     const double cd = cos(DiffYaw), sd = sin(DiffYaw);
-    update_box_yaw(t.BBox, t.nBBox, cpx, cpy, cd, sd);
-    update_box_yaw(t.bestBBox, t.nBBox, cpx, cpy, cd, sd);
-    t.bestYaw = yaw;
+    // updateBoxYaw :512-532 on both boxes (n = nBBox for both, like the reference): lane < 8 -> BBox, 8 <= lane < 16 -> bestBBox
+    const int i = lane & 7;
+    if (lane < 16 && i < nB) {
+      float (*bb)[3] = (lane < 8) ? t.BBox : t.bestBBox;
+      const double preX = bb[i][0], preY = bb[i][1];
+      bb[i][0] = (float)(cd * (preX - cpx) - sd * (preY - cpy) + cpx);
+      bb[i][1] = (float)(sd * (preX - cpx) + cd * (preY - cpy) + cpy);
+    }
+    if (lane == 0) t.bestYaw = yaw;
   }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(kTBWarps * 32)
 imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, const int* __restrict__ det, const float* __restrict__ boxes,
                   const unsigned* __restrict__ gate, const int* __restrict__ first_setter, const uint8_t* __restrict__ skip,
-                  int words, const int* __restrict__ act_list, unsigned long long* trace) {
+                  int words, const int* __restrict__ act_list, ActSummary* __restrict__ summary, unsigned long long* trace,
+                  unsigned long long* __restrict__ phase) {
   extern __shared__ unsigned short s_list_all[];          // per warp: indices of the gated boxes, in box order
   __shared__ TrackState s_trk[kTBWarps];
+  __shared__ ActSummary s_sum[kTBWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   pdl_wait();                              // TA has finished (gate rows, first_setter, predicted states are visible)
   pdl_launch_dependents();                 // TC's CTA may line up behind this grid
+  // diagnostic: %globaltimer stamps of the first track's warp
+  auto mark = [&](int i) { if (phase && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); phase[16 + i] = t; } };
+  mark(0);
   trace_start(trace, 1);
   struct TraceEnd { unsigned long long* t; __device__ ~TraceEnd() { __syncthreads(); trace_end(t, 1); } } trace_at_exit{trace};
   const int n_act = trk[CNT_N_ACT];
   const int M = det[CNT_N_BOXES];
+  if (trace && threadIdx.x == 0 && (int)blockIdx.x * kTBWarps < n_act) { unsigned long long tn; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn)); atomicMax(&trace[7], tn); }
   unsigned short* s_list = s_list_all + (size_t)warp * words * 32;
   const int nchunk = (M + 31) >> 5;
 
   for (int q = blockIdx.x * kTBWarps + warp; q < n_act; q += gridDim.x * kTBWarps) {
     const int it = act_list[q];
-    if (skip[it]) continue;
+    const bool skipped = skip[it] != 0;      // dead, or killed by TA's guards: no update, but TC still wants its summary
     // stage the whole track (1.6 KB) in shared memory with coalesced 8-byte loads: the update below touches almost
     // every field several times, and every one of those touches would otherwise be its own trip to L2 / HBM
     {
       const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&tracks[it]);
       unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_trk[warp]);
-      for (int w = lane; w < kTrackWords; w += 32) dst[w] = src[w];
+      constexpr int kIt = (kTrackWords + 31) / 32;
+      unsigned long long v[kIt];                     // all loads in flight before the first store: one round trip, not kIt
+#pragma unroll
+      for (int u = 0; u < kIt; ++u) { const int w = lane + 32 * u; v[u] = (w < kTrackWords) ? src[w] : 0ull; }
+#pragma unroll
+      for (int u = 0; u < kIt; ++u) { const int w = lane + 32 * u; if (w < kTrackWords) dst[w] = v[u]; }
     }
     __syncwarp();
+    mark(1);
     TrackState& t = s_trk[warp];
-    do {
+    if (!skipped) do {
     const int trackNum0 = t.trackNum;
     const bool secondInit = (trackNum0 == 1);
     // ---- lifetime_ (:232): a gated box counts unless an earlier track already matched it
     int nmeas = 0, life = 0;
-    for (int ch = 0; ch < nchunk; ++ch) {
-      const unsigned g = gate[(size_t)it * words + ch];
-      const int b = ch * 32 + lane;
-      const bool cnt = ((g >> lane) & 1u) && (first_setter[b] >= it);
-      life += __popc(__ballot_sync(0xFFFFFFFFu, cnt));
-      if ((g >> lane) & 1u) s_list[nmeas + __popc(g & ((1u << lane) - 1u))] = (unsigned short)b;
-      nmeas += __popc(g);
+    for (int ch0 = 0; ch0 < nchunk; ch0 += 4) {      // four chunks per batch: two round trips (gate words, then first_setter), not two per chunk
+      unsigned g4[4]; int fs4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) g4[u] = (ch0 + u < nchunk) ? gate[(size_t)it * words + ch0 + u] : 0u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) fs4[u] = ((g4[u] >> lane) & 1u) ? first_setter[(ch0 + u) * 32 + lane] : INT_MAX;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned g = g4[u];
+        const int b = (ch0 + u) * 32 + lane;
+        const bool cnt = ((g >> lane) & 1u) && (fs4[u] >= it);
+        life += __popc(__ballot_sync(0xFFFFFFFFu, cnt));
+        if ((g >> lane) & 1u) s_list[nmeas + __popc(g & ((1u << lane) - 1u))] = (unsigned short)b;
+        nmeas += __popc(g);
+      }
     }
     __syncwarp();
+    mark(2);
     const int lifetime = t.lifetime + life;
 
     // measurement prediction used by the gate (same selection as TA)
@@ -631,12 +686,15 @@ imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, 
       }
     }
     __syncwarp();
+    mark(3);
     if (lane == 0) {
       t.lifetime = lifetime;
       if (isVis) { t.isVisBB = 1; t.nBBox = 8; }
-      update_bb(t);                                     // :877
     }
     __syncwarp();
+    update_bb_warp(t, lane);                            // :877
+    __syncwarp();
+    mark(4);
 
     if (secondInit) {                                   // :882-921
       if (lane == 0) {
@@ -692,26 +750,41 @@ imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, 
           e = exp((t0 * Si[0] + t1 * Si[2]) * d0 + (t0 * Si[1] + t1 * Si[3]) * d1);
         }
       };
-      double es = 0;
-      for (int k = 0; k < nmeas; ++k) { double d0, d1, e; meas(k, d0, d1, e); es += e; }
-      eSum[m] = es;
-      const double betaZero = bb / (bb + es);
-      double sX0 = 0, sX1 = 0;
-      for (int k = 0; k < nmeas; ++k) {
-        double d0, d1, e; meas(k, d0, d1, e);
-        const double beta = e / (bb + es);
-        sX0 += beta * d0; sX1 += beta * d1;
-      }
+      double es = 0, betaZero, sX0 = 0, sX1 = 0;
       double sP[4] = {0, 0, 0, 0};
-      for (int k = 0; k < nmeas; ++k) {
-        double d[2], e; meas(k, d[0], d[1], e);
-        const double beta = e / (bb + es);
-        const double sXv[2] = {sX0, sX1};
+      if (nmeas <= 32) {
+        // lane k holds measurement k: the per-measurement factors (one fp64 division, the products) are computed by all lanes
+        // at once; only the SUMS run over k in the reference's order (same operands, same operations, same bits) -- the
+        // division and the exp no longer sit inside three serial loops per model
+        for (int k = 0; k < nmeas; ++k) es += __shfl_sync(0xFFFFFFFFu, le, k);
+        betaZero = bb / (bb + es);
+        const double beta = (lane < nmeas) ? le / (bb + es) : 0.0;
+        const double p0 = beta * ld0, p1 = beta * ld1;
+        for (int k = 0; k < nmeas; ++k) { sX0 += __shfl_sync(0xFFFFFFFFu, p0, k); sX1 += __shfl_sync(0xFFFFFFFFu, p1, k); }
+        const double t00 = p0 * ld0 - sX0 * sX0, t01 = p0 * ld1 - sX0 * sX1, t10 = p1 * ld0 - sX1 * sX0, t11 = p1 * ld1 - sX1 * sX1;
+        for (int k = 0; k < nmeas; ++k) {
+          sP[0] += __shfl_sync(0xFFFFFFFFu, t00, k); sP[1] += __shfl_sync(0xFFFFFFFFu, t01, k);
+          sP[2] += __shfl_sync(0xFFFFFFFFu, t10, k); sP[3] += __shfl_sync(0xFFFFFFFFu, t11, k);
+        }
+      } else {
+        for (int k = 0; k < nmeas; ++k) { double d0, d1, e; meas(k, d0, d1, e); es += e; }
+        betaZero = bb / (bb + es);
+        for (int k = 0; k < nmeas; ++k) {
+          double d0, d1, e; meas(k, d0, d1, e);
+          const double beta = e / (bb + es);
+          sX0 += beta * d0; sX1 += beta * d1;
+        }
+        for (int k = 0; k < nmeas; ++k) {
+          double d[2], e; meas(k, d[0], d[1], e);
+          const double beta = e / (bb + es);
+          const double sXv[2] = {sX0, sX1};
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+          for (int r = 0; r < 2; ++r)
 #pragma unroll
-          for (int c = 0; c < 2; ++c) sP[r * 2 + c] += ((beta * d[r]) * d[c] - sXv[r] * sXv[c]);
+            for (int c = 0; c < 2; ++c) sP[r * 2 + c] += ((beta * d[r]) * d[c] - sXv[r] * sXv[c]);
+        }
       }
+      eSum[m] = es;
       const double* K = t.K[m];
       const double* S = t.S[m];
 #pragma unroll
@@ -729,15 +802,24 @@ imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, 
       }
       Pnew[m] = Pe;
     }
+    mark(5);
     const double Vk = kPi * sqrt(gammaG * det2(t.S[mm]));     // S is untouched by the update, same max model
     double lam[3];
-    const double powN = pow(Vk, numMeas), pow1N = (numMeas != 0) ? pow(Vk, 1 - numMeas) : 0.0;   // same arguments for all three models
-    for (int m = 0; m < 3; ++m) {
-      if (numMeas != 0)
-        lam[m] = (1 - pG * pD) / powN + pD * pow1N * eSum[m] / (numMeas * sqrt(2 * kPi * det2(t.S[m])));
-      else
-        lam[m] = (1 - pG * pD) / powN;
+    {
+      // the two pow() (same base, exponents numMeas and 1 - numMeas) on lanes 0 / 1, the three model terms on lanes 0..2: one pass
+      // through pow / sqrt / the divisions instead of two and three
+      const double ex = (lane == 1) ? 1 - numMeas : numMeas;
+      const double pw = pow(Vk, ex);
+      const double powN = __shfl_sync(0xFFFFFFFFu, pw, 0);
+      const double pow1N = (numMeas != 0) ? __shfl_sync(0xFFFFFFFFu, pw, 1) : 0.0;
+      const int ml = (lane < 3) ? lane : 0;
+      const double em = (ml == 0) ? eSum[0] : (ml == 1) ? eSum[1] : eSum[2];
+      double lv;
+      if (numMeas != 0) lv = (1 - pG * pD) / powN + pD * pow1N * em / (numMeas * sqrt(2 * kPi * det2(t.S[ml])));
+      else lv = (1 - pG * pD) / powN;
+      lam[0] = __shfl_sync(0xFFFFFFFFu, lv, 0); lam[1] = __shfl_sync(0xFFFFFFFFu, lv, 1); lam[2] = __shfl_sync(0xFFFFFFFFu, lv, 2);
     }
+    mark(6);
     // ---- PostProcessIMMUKF: UpdateModeProb (ukf.cpp:384-397), MergeEstimationAndCovariance (:419-437)
     double mp[3] = {t.modeProb[0], t.modeProb[1], t.modeProb[2]};
     const double sumG = lam[0] * mp[0] + lam[1] * mp[1] + lam[2] * mp[2];
@@ -771,12 +853,26 @@ imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, 
     }
     } while (false);
     __syncwarp();
-    {
+    mark(7);
+    if (!skipped) {
       const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_trk[warp]);
       unsigned long long* dst = reinterpret_cast<unsigned long long*>(&tracks[it]);
       for (int w = lane; w < kTrackWords; w += 32) dst[w] = src[w];
     }
+    if (lane == 0) {
+      ActSummary& a = s_sum[warp];
+      a.x = t.x[0][0]; a.y = t.x[0][1]; a.yaw = t.x[0][3]; a.v = t.x[0][2];
+      a.initx = t.initMeas[0]; a.inity = t.initMeas[1];
+      a.mp0 = t.modeProb[0]; a.mp1 = t.modeProb[1]; a.mp2 = t.modeProb[2];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a.bb[e] = t.BBox[e >> 1][e & 1];
+      a.k = it; a.trackNum = t.trackNum; a.lifetime = t.lifetime;
+      a.isStatic = t.isStatic; a.isVis = t.isVisBB; a.pad[0] = a.pad[1] = 0; a.pad2[0] = a.pad2[1] = 0;
+    }
     __syncwarp();
+    if (lane < 16) reinterpret_cast<unsigned long long*>(&summary[q])[lane] = reinterpret_cast<const unsigned long long*>(&s_sum[warp])[lane];
+    __syncwarp();
+    mark(8);
   }
 }
 
@@ -863,6 +959,302 @@ __device__ __forceinline__ int emit_track(TrackState& t, int i, double ego_yaw, 
   return vis;
 }
 
+// dst[0..n) = src[0..n) by the whole CTA, U loads in flight per thread before the first store.  (A plain
+// `for (...) dst[e] = src[e]` over pointers the compiler cannot prove distinct is a chain of load -> store -> load round
+// trips; on the one CTA of the tracker's sequential chain every one of them is ~1 us.)
+template <typename T, int U>
+__device__ __forceinline__ void cta_copy(T* dst, const T* src, int n) {
+  for (int base = 0; base < n; base += kTCThreads * U) {
+    T v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int e = base + u * kTCThreads + (int)threadIdx.x; if (e < n) v[u] = src[e]; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int e = base + u * kTCThreads + (int)threadIdx.x; if (e < n) dst[e] = v[u]; }
+  }
+}
+
+// the two halves of cta_copy for the first U * kTCThreads items, so that the loads of SEVERAL arrays can be in flight together
+template <typename T, int U>
+__device__ __forceinline__ void cta_load(T (&v)[U], const T* src, int n) {
+#pragma unroll
+  for (int u = 0; u < U; ++u) { const int e = u * kTCThreads + (int)threadIdx.x; if (e < n) v[u] = src[e]; }
+}
+template <typename T, int U>
+__device__ __forceinline__ void cta_store(T* dst, const T (&v)[U], int n) {
+#pragma unroll
+  for (int u = 0; u < U; ++u) { const int e = u * kTCThreads + (int)threadIdx.x; if (e < n) dst[e] = v[u]; }
+}
+
+// per-track outputs (:995-1041) + static flag (:1045-1081) from values instead of the record (the fast path of TC holds an
+// active track's fields in registers); same statements as emit_track.  Returns the new isStatic.
+__device__ __forceinline__ int emit_values(int i, double tx, double ty, double yaw, double v, double mx, double my, double mp0, double mp1,
+                                           double mp2, int trackNum, int lifetime, int isStatic, int vis, double ego_yaw, const OutPtrs& o,
+                                           double4* __restrict__ pos, double& distFromInit) {
+  distFromInit = sqrt((tx - mx) * (tx - mx) + (ty - my) * (ty - my));
+  double tyaw = yaw;
+  tyaw += ego_yaw;
+  tyaw = wrap_pi(tyaw);
+  o.targets[3 * i] = (float)tx; o.targets[3 * i + 1] = (float)ty; o.targets[3 * i + 2] = (float)(-1.73 / 2);
+  o.vandyaw[2 * i] = v; o.vandyaw[2 * i + 1] = tyaw;
+  o.is_vis[i] = (uint8_t)vis;
+  int st = 0;
+  if (isStatic) st = 1;
+  else if (trackNum == 5 && lifetime > 8) {
+    if ((distFromInit < 3.0) && (mp2 > mp0 || mp2 > mp1)) st = 1;
+  }
+  o.is_static[i] = (uint8_t)st;
+  o.track_manage[i] = trackNum;
+  pos[i] = make_double4(tx, ty, yaw, 0.0);
+  return st;
+}
+
+constexpr int kFastVis = kTCThreads;  // the fast path holds every active track in one thread: at most that many visible boxes
+
+// TC, fast path: at most kTCThreads active tracks (thread q <-> entry q of the active list).  Everything the merge / spawn /
+// output logic needs of an active track arrives in ONE coalesced load of TB's 128-byte summaries and stays in registers and
+// shared memory; the 1.6 KB records are only written (trackNum / isStatic / distFromInit changes, new tracks), never waited
+// for, except the 96-byte box of a visible track, whose load is in flight during the merge.  Same results as the general
+// path below, statement for statement; see there for why mergeOverSegmentation reduces to imax / has5.
+struct TCFastShared {
+  int w[33];
+  int ncand, ncont, carry;
+  int imax[kTCThreads];
+  unsigned char cont[kFastVis];
+  unsigned char h5[kFastVis];
+  int vid[kFastVis];
+  float bx[kFastVis][8];
+  float4 ab[kFastVis];
+  double px[kTCThreads], py[kTCThreads];
+  float4 t4[kTCThreads];              // per active track: float position, pre-test margin, track index (bits; -1 = not live)
+  unsigned cand[kCandCap];            // (visible slot << 16) | thread of the track
+};
+
+__device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict__ tracks, int* __restrict__ trk, int* __restrict__ det,
+                                        const float* __restrict__ boxes, int* __restrict__ first_setter, double ego_yaw, int max_tracks,
+                                        const OutPtrs& o, const OutPtrs& prev, int* __restrict__ act_list, double4* __restrict__ pos,
+                                        const ActSummary* __restrict__ summary, int T0, int n_act0, int M, unsigned long long* __restrict__ trace,
+                                        unsigned long long* __restrict__ phase) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  auto mark = [&](int i) { if (phase && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); phase[i] = t; } };
+  mark(0);
+  const bool have = tid < n_act0;
+  // ---- one round trip: the summaries, the previous result block, the spawn inputs
+  ActSummary r;
+  if (have) {
+    const uint4* src = reinterpret_cast<const uint4*>(&summary[tid]);
+    uint4* dst = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dst[e] = src[e];
+  } else {
+    r.k = -1; r.trackNum = 0; r.isVis = 0; r.isStatic = 0; r.lifetime = 0; r.x = r.y = r.yaw = r.v = 0; r.initx = r.inity = 0; r.mp0 = r.mp1 = r.mp2 = 0;
+  }
+  const bool cp = prev.targets != o.targets;
+  // everything else this kernel reads that does not depend on the summaries: the frame's box list (it travels with the
+  // results), the previous result block (dead tracks: unchanged), the packed yaw of every track, the spawn inputs.  ALL loads
+  // are issued before the first store -- each load -> store pair behind another one was one more L2 round trip (~0.45 us)
+  constexpr int UB = 4, UT = 4, UM = 2, UY = 4;
+  const int nbx = M * 6, ntg = cp ? (T0 * 12 + 15) / 16 : 0, ntm = cp ? (T0 * 4 + 15) / 16 : 0, nsv = cp ? (T0 + 15) / 16 : 0;
+  uint4 vbx[UB], vtg[UT], vtm[UM], vst[1], vvi[1];
+  double pz[UY], pv[UY];
+  cta_load(vbx, reinterpret_cast<const uint4*>(boxes), nbx);
+  const int fs0 = (tid < M) ? first_setter[tid] : 0;            // first pass of the spawn loop below
+  float bc[8] = {0, 0, 0, 0, 0, 0, 0, 0};                      // corners 0..3 (x, y) of this thread's box
+  if (tid < M) {
+    const float4* b4 = reinterpret_cast<const float4*>(boxes + (size_t)tid * 24);   // 96-byte boxes: 16-byte aligned
+    const float4 q0 = b4[0], q1 = b4[1], q2 = b4[2];
+    bc[0] = q0.x; bc[1] = q0.y; bc[2] = q0.w; bc[3] = q1.x; bc[4] = q1.z; bc[5] = q1.w; bc[6] = q2.y; bc[7] = q2.z;
+  }
+  int hdr_in[4] = {0, 0, 0, 0};
+  if (tid == 0) { hdr_in[0] = det[CNT_N_ELEV]; hdr_in[1] = det[CNT_N_GROUND]; hdr_in[2] = det[CNT_NUM_CLUSTER]; hdr_in[3] = det[CNT_ERROR]; }
+  cta_load(vtg, reinterpret_cast<const uint4*>(prev.targets), ntg);
+  cta_load(vtm, reinterpret_cast<const uint4*>(prev.track_manage), ntm);
+  cta_load(vst, reinterpret_cast<const uint4*>(prev.is_static), nsv);
+  cta_load(vvi, reinterpret_cast<const uint4*>(prev.is_vis), nsv);
+#pragma unroll
+  for (int u = 0; u < UY; ++u) {
+    const int e = u * kTCThreads + tid;
+    pz[u] = 0; pv[u] = 0;
+    if (e < T0) { pz[u] = pos[e].z; if (cp) pv[u] = prev.vandyaw[2 * e]; }
+  }
+  // ---- stores (and the rare remainders beyond the first batch of each array)
+  cta_store(reinterpret_cast<uint4*>(o.boxes), vbx, nbx);
+  if (nbx > UB * kTCThreads) cta_copy<uint4, UB>(reinterpret_cast<uint4*>(o.boxes) + UB * kTCThreads, reinterpret_cast<const uint4*>(boxes) + UB * kTCThreads, nbx - UB * kTCThreads);
+  cta_store(reinterpret_cast<uint4*>(o.targets), vtg, ntg);
+  if (ntg > UT * kTCThreads) cta_copy<uint4, UT>(reinterpret_cast<uint4*>(o.targets) + UT * kTCThreads, reinterpret_cast<const uint4*>(prev.targets) + UT * kTCThreads, ntg - UT * kTCThreads);
+  cta_store(reinterpret_cast<uint4*>(o.track_manage), vtm, ntm);
+  if (ntm > UM * kTCThreads) cta_copy<uint4, UM>(reinterpret_cast<uint4*>(o.track_manage) + UM * kTCThreads, reinterpret_cast<const uint4*>(prev.track_manage) + UM * kTCThreads, ntm - UM * kTCThreads);
+  cta_store(reinterpret_cast<uint4*>(o.is_static), vst, nsv);
+  cta_store(reinterpret_cast<uint4*>(o.is_vis), vvi, nsv);
+  if (nsv > kTCThreads) {
+    cta_copy<uint4, 1>(reinterpret_cast<uint4*>(o.is_static) + kTCThreads, reinterpret_cast<const uint4*>(prev.is_static) + kTCThreads, nsv - kTCThreads);
+    cta_copy<uint4, 1>(reinterpret_cast<uint4*>(o.is_vis) + kTCThreads, reinterpret_cast<const uint4*>(prev.is_vis) + kTCThreads, nsv - kTCThreads);
+  }
+  // dead tracks: v unchanged, yaw re-offset by THIS frame's ego yaw (:1004-1008); active ones are re-emitted below
+#pragma unroll
+  for (int u = 0; u < UY; ++u) {
+    const int e = u * kTCThreads + tid;
+    if (e < T0) { if (cp) o.vandyaw[2 * e] = pv[u]; o.vandyaw[2 * e + 1] = wrap_pi(pz[u] + ego_yaw); }
+  }
+  for (int base = UY * kTCThreads; base < T0; base += kTCThreads * UY) {
+    double qz[UY], qv[UY];
+#pragma unroll
+    for (int u = 0; u < UY; ++u) {
+      const int e = base + u * kTCThreads + tid;
+      qz[u] = 0; qv[u] = 0;
+      if (e < T0) { qz[u] = pos[e].z; if (cp) qv[u] = prev.vandyaw[2 * e]; }
+    }
+#pragma unroll
+    for (int u = 0; u < UY; ++u) {
+      const int e = base + u * kTCThreads + tid;
+      if (e < T0) { if (cp) o.vandyaw[2 * e] = qv[u]; o.vandyaw[2 * e + 1] = wrap_pi(qz[u] + ego_yaw); }
+    }
+  }
+  mark(1);
+  const int vis = (have && r.isVis) ? 1 : 0;
+  float2 vb[12];                                     // the visible track's whole box (8 x 3 floats) for the output list
+  if (vis) {
+    const float2* src = reinterpret_cast<const float2*>(&tracks[r.k].BBox[0][0]);
+#pragma unroll
+    for (int e = 0; e < 12; ++e) vb[e] = src[e];
+  }
+  if (have) pos[r.k] = make_double4(r.x, r.y, r.yaw, 0.0);     // pass B and the general path read positions from here
+  S.px[tid] = r.x; S.py[tid] = r.y; S.imax[tid] = -1;
+  {
+    const float fx = (float)r.x, fy = (float)r.y;
+    S.t4[tid] = make_float4(fx, fy, 0.011f + 2.0e-7f * (fabsf(fx) + fabsf(fy)), __int_as_float((have && r.trackNum != 0) ? r.k : -1));
+  }
+  if (tid == 0) { S.ncand = 0; S.ncont = 0; S.carry = 0; }
+
+  // ---- visible boxes in track order (the active list is sorted by track index)
+  int vslot, nv;
+  block_offsets(vis, 0, S.w, vslot, nv);          // (its barriers also publish the shared arrays above)
+  if (vis) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) S.bx[vslot][e] = r.bb[e];
+    S.ab[vslot] = make_float4(fminf(fminf(r.bb[0], r.bb[2]), fminf(r.bb[4], r.bb[6])), fmaxf(fmaxf(r.bb[0], r.bb[2]), fmaxf(r.bb[4], r.bb[6])),
+                              fminf(fminf(r.bb[1], r.bb[3]), fminf(r.bb[5], r.bb[7])), fmaxf(fmaxf(r.bb[1], r.bb[3]), fmaxf(r.bb[5], r.bb[7])));
+    S.vid[vslot] = r.k; S.h5[vslot] = 0;
+  }
+  __syncthreads();
+
+  mark(2);
+  // ---- mergeOverSegmentation, pass A: imax = largest visible box index containing this (live) track
+  // (track x box) pairs spread over the whole CTA: a warp takes every 8th box (broadcast loads), its lanes the tracks
+  {
+    const int warp = tid >> 5;
+    const float4* __restrict__ abp = S.ab;
+    const float4* __restrict__ t4p = S.t4;
+    const int* __restrict__ vidp = S.vid;
+    for (int v = warp; v < nv; v += kTCThreads / 32) {
+      const float4 ab = abp[v];
+      const int vid = vidp[v];
+      for (int jt = lane; jt < n_act0; jt += 32) {
+        const float4 tj = t4p[jt];
+        const int kj = __float_as_int(tj.w);
+        if (kj >= 0 && kj != vid && !(tj.x < ab.x - tj.z || tj.x > ab.y + tj.z || tj.y < ab.z - tj.z || tj.y > ab.w + tj.z)) {
+          const int slot = atomicAdd(&S.ncand, 1);
+          if (slot < kCandCap) S.cand[slot] = ((unsigned)v << 16) | (unsigned)jt;
+          else if (overseg_cond(S.bx[v], reinterpret_cast<const float*>(&S.ab[v]), S.px[jt], S.py[jt])) atomicMax(&S.imax[jt], vid);
+        }
+      }
+    }
+  }
+  int imax = -1;
+  __syncthreads();
+  mark(3);
+  {
+    const int ncand = min(S.ncand, kCandCap);
+    for (int e = tid; e < ncand; e += kTCThreads) {      // the exact fp64 tests, one pair per thread
+      const int v = (int)(S.cand[e] >> 16), jt = (int)(S.cand[e] & 0xFFFFu);
+      if (overseg_cond(S.bx[v], reinterpret_cast<const float*>(&S.ab[v]), S.px[jt], S.py[jt])) atomicMax(&S.imax[jt], S.vid[v]);
+    }
+  }
+  __syncthreads();
+  mark(4);
+  imax = max(imax, S.imax[tid]);
+  // ---- pass B: has5 for the rare visible box that sits inside another one, against EVERY track (dead ones included)
+  if (vis && imax >= 0 && r.trackNum != 0) S.cont[atomicAdd(&S.ncont, 1)] = (unsigned char)vslot;
+  __syncthreads();
+  {
+    const int ncont = S.ncont;
+    for (int cidx = 0; cidx < ncont; ++cidx) {
+      const int v = S.cont[cidx], k = S.vid[v];
+      const float4 ab = S.ab[v];
+      for (int j = tid; j < T0; j += kTCThreads) {
+        const double4 pj = pos[j];
+        const float px = (float)pj.x, py = (float)pj.y;
+        const float mg = 0.011f + 2.0e-7f * (fabsf(px) + fabsf(py));
+        if (j != k && !(px < ab.x - mg || px > ab.y + mg || py < ab.z - mg || py > ab.w + mg) &&
+            overseg_cond(S.bx[v], reinterpret_cast<const float*>(&S.ab[v]), pj.x, pj.y)) S.h5[v] = 1;
+      }
+    }
+    if (ncont > 0) __syncthreads();
+  }
+  mark(5);
+  int trackNum = r.trackNum;
+  if (have && trackNum != 0 && nv > 0) {
+    const bool has5 = vis && S.h5[vslot] != 0;
+    if (imax >= 0 && (!has5 || imax > r.k)) trackNum = 0;
+    else if (has5) trackNum = 5;
+    if (trackNum != r.trackNum) tracks[r.k].trackNum = trackNum;
+  }
+
+  // ---- outputs of the active tracks, visible boxes in track order, the surviving part of the active list
+  int act = 0;
+  if (have) {
+    double dfi;
+    const int st = emit_values(r.k, r.x, r.y, r.yaw, r.v, r.initx, r.inity, r.mp0, r.mp1, r.mp2, trackNum, r.lifetime, r.isStatic, vis, ego_yaw, o, pos, dfi);
+    tracks[r.k].distFromInit = dfi;
+    if (st && !r.isStatic) tracks[r.k].isStatic = 1;
+    act = (trackNum != 0 || vis) ? 1 : 0;
+  }
+  if (vis) {
+    float2* dst = reinterpret_cast<float2*>(o.vis_bb + (size_t)vslot * 24);
+#pragma unroll
+    for (int e = 0; e < 12; ++e) dst[e] = vb[e];
+  }
+  mark(6);
+  int aex, atot;
+  block_offsets(0, act, S.w, aex, atot);
+  const int n_keep = atot >> 16;
+  if (act) act_list[aex >> 16] = r.k;
+
+  mark(7);
+  // ---- spawn one UKF per unmatched box, in box order (:972-989); the spawning thread also emits the new track
+  for (int b0 = 0; b0 < M; b0 += kTCThreads) {
+    const int b = b0 + tid;
+    const int un = (b < M && (b0 == 0 ? fs0 : first_setter[b]) == INT_MAX) ? 1 : 0;
+    int ex, tot;
+    block_offsets(un, 0, S.w, ex, tot);
+    const int p = T0 + S.carry + ex;
+    if (un && p < max_tracks) {
+      double cx, cy;
+      if (b0 == 0) cp_from_corners(bc[0], bc[1], bc[2], bc[3], bc[4], bc[5], bc[6], bc[7], cx, cy);
+      else cp_from_box(boxes + (size_t)b * 24, cx, cy);
+      ukf_initialize(tracks[p], cx, cy);
+      double dfi;
+      emit_values(p, cx, cy, 0.0, 0.0, 0.0, 0.0, 0.33, 0.33, 0.33, 1, 0, 0, 0, ego_yaw, o, pos, dfi);
+      tracks[p].distFromInit = dfi;
+      act_list[n_keep + (p - T0)] = p;
+    }
+    if (b < M) first_setter[b] = INT_MAX;        // ready for the next frame
+    __syncthreads();
+    if (tid == 0) S.carry += tot;
+    __syncthreads();
+  }
+  mark(8);
+  int T = T0 + S.carry;
+  if (T > max_tracks) T = max_tracks;
+  if (tid == 0) {
+    trk[CNT_N_TRACKS] = T; trk[CNT_N_VIS] = nv; trk[CNT_N_ACT] = n_keep + (T - T0);
+    o.hdr[HDR_N_ELEV] = hdr_in[0]; o.hdr[HDR_N_GROUND] = hdr_in[1]; o.hdr[HDR_NUM_CLUSTER] = hdr_in[2];
+    o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = nv; o.hdr[HDR_ERROR] = (T0 + S.carry > max_tracks) ? (int)LMOT_ERR_CAPACITY : hdr_in[3];
+    det[CNT_ERROR] = 0;
+    trace_end(trace, 2);
+    mark(9);
+  }
+}
+
 // TC.  The track table only ever grows (dead tracks keep their slot, like targets_), and the reference re-emits every track
 // every frame.  Everything here that walks the table does so through coalesced side arrays; everything that touches the
 // 1.6 KB TrackState records is limited to the ACTIVE tracks:
@@ -872,13 +1264,20 @@ __device__ __forceinline__ int emit_track(TrackState& t, int i, double ego_yaw, 
 //     of every track is its state's yaw plus THIS frame's ego yaw: `pos`, a packed (x, y, yaw) per track, refreshed for the
 //     active tracks only.
 // `full` (first step after the table was written from the host): everything is rebuilt from the records.
-__global__ void __launch_bounds__(kTCThreads)
+__global__ void __launch_bounds__(kTCThreads, 1)
 spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int* __restrict__ det, const float* __restrict__ boxes,
                     int* __restrict__ first_setter, int* __restrict__ imax_arr, int* __restrict__ vis_list,
                     uint8_t* __restrict__ has5_arr, int first_frame, int compat_first, double ego_yaw, int max_tracks, OutPtrs o,
-                    OutPtrs prev, int full, int* __restrict__ act_list, double4* __restrict__ pos, unsigned long long* __restrict__ trace) {
+                    OutPtrs prev, int full, int* __restrict__ act_list, double4* __restrict__ pos, const ActSummary* __restrict__ summary,
+                    unsigned long long* __restrict__ trace, unsigned long long* __restrict__ phase) {
   pdl_wait();                              // TB has finished
   trace_start(trace, 2);
+  if (!full && !(first_frame && compat_first) && trk[CNT_N_ACT] <= kTCThreads) {
+    __shared__ TCFastShared s_fast;
+    const int M = det[CNT_N_BOXES];
+    tc_fast(s_fast, tracks, trk, det, boxes, first_setter, ego_yaw, max_tracks, o, prev, act_list, pos, summary, trk[CNT_N_TRACKS], trk[CNT_N_ACT], M, trace, phase);
+    return;
+  }
   __shared__ int s_w[33];
   __shared__ int s_carry, s_carry2, s_nvis, s_ncand, s_ncont;
   __shared__ unsigned char s_cont[kVisChunk];           // visible boxes that sit inside another visible box
@@ -1099,7 +1498,6 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
     o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = s_carry; o.hdr[HDR_ERROR] = det[CNT_ERROR];
     det[CNT_ERROR] = 0;
     trace_end(trace, 2);
-    if (trace) { trace[6] = (unsigned long long)T; trace[7] = (unsigned long long)nv; }
   }
 }
 
@@ -1162,6 +1560,7 @@ int tracker_alloc(Ctx* c) {
   LMOT_CUDA(c, cudaMalloc(&c->d_vis_list, (size_t)TC * sizeof(int)));
   LMOT_CUDA(c, cudaMalloc(&c->d_act_list, (size_t)TC * sizeof(int)));
   LMOT_CUDA(c, cudaMalloc(&c->d_pos, (size_t)TC * sizeof(double4)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_summary, (size_t)TC * sizeof(ActSummary)));
   LMOT_CUDA(c, cudaMemsetAsync(c->d_pos, 0, (size_t)TC * sizeof(double4), c->trk_stream));
   c->last_trk_res = nullptr;
   c->act_valid = false;
@@ -1174,7 +1573,7 @@ int tracker_alloc(Ctx* c) {
 
 void tracker_free(Ctx* c) {
   cudaFree(c->d_tracks); cudaFree(c->d_trk_counters); cudaFree(c->d_gate); cudaFree(c->d_setter); cudaFree(c->d_first_setter);
-  cudaFree(c->d_skip); cudaFree(c->d_new_num); cudaFree(c->d_live_list); cudaFree(c->d_vis_list); cudaFree(c->d_act_list); cudaFree(c->d_pos);
+  cudaFree(c->d_skip); cudaFree(c->d_new_num); cudaFree(c->d_live_list); cudaFree(c->d_vis_list); cudaFree(c->d_act_list); cudaFree(c->d_pos); cudaFree(c->d_summary);
   if (c->h_trk_counters) cudaFreeHost(c->h_trk_counters);
 }
 
@@ -1246,7 +1645,8 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
     cfg.attrs = &pdl; cfg.numAttrs = 1;
     LMOT_CUDA(c, cudaLaunchKernelEx(&cfg, imm_update_kernel, c->d_tracks, (const int*)c->d_trk_counters, (const int*)det, d_boxes,
                                     (const unsigned*)c->d_gate, (const int*)c->d_first_setter, (const uint8_t*)c->d_skip, c->gate_words,
-                                    (const int*)c->d_act_list, trace));
+                                    (const int*)c->d_act_list, reinterpret_cast<ActSummary*>(c->d_summary), trace,
+                                    c->d_trk_trace ? c->d_trk_trace + 256 : (unsigned long long*)nullptr));
     kernel_mark(c, sl, st);
   }
   {
@@ -1258,7 +1658,8 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
     cfg.attrs = &pdl; cfg.numAttrs = 1;
     LMOT_CUDA(c, cudaLaunchKernelEx(&cfg, spawn_output_kernel, c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_first_setter, c->d_new_num,
                                     c->d_vis_list, c->d_skip, first, compat, h.egoPoint[2], c->prm.max_tracks, o, po, full, c->d_act_list,
-                                    c->d_pos, trace));
+                                    c->d_pos, reinterpret_cast<const ActSummary*>(c->d_summary), trace,
+                                    c->d_trk_trace ? c->d_trk_trace + 256 : (unsigned long long*)nullptr));
   }
   kernel_mark(c, sl, st);
   LMOT_CUDA(c, cudaGetLastError());

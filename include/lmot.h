@@ -232,7 +232,8 @@ int lmot_debug_label_grid(lmot_ctx* ctx, int32_t* grid, int* num_cluster);
  * ring, of the stage boundaries [0..4] and of every kernel [5..] of each of those frames -- pipelined submissions included */
 int lmot_debug_timeline(lmot_ctx* ctx, float* out, int cap_frames, int* n_frames, int* row_stride);
 
-/* diagnostic (after the phase clock was switched on): %globaltimer spans of the tracker kernels of the last 32 tracker steps */
+/* diagnostic (after the phase clock was switched on): %globaltimer spans of the tracker kernels of the last 32 tracker steps,
+ * out[32][8], followed by 32 phase stamps of the last imm_update / spawn_output launch: out must hold 288 words */
 int lmot_debug_tracker_trace(lmot_ctx* ctx, unsigned long long* out, int* next);
 
 /* diagnostic: first call switches on the phase clock of ground_fused_kernel; later calls return the %globaltimer stamps

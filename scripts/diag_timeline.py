@@ -13,7 +13,8 @@ ts, frames = bench.make_frames(synth, W + K)
 n = frames.shape[1]
 d = torch.from_numpy(frames).cuda()
 torch.cuda.synchronize()
-for depth in (1, 4):
+BRIEF = os.environ.get("DIAG_BRIEF", "0") == "1"
+for depth in [int(x) for x in os.environ.get("DIAG_DEPTHS", "1,4").split(",")]:
     prm = lmot.default_params(); prm.pipeline_depth = depth
     ctx = lmot.Lmot(prm)
     st = torch.cuda.Stream(); torch.cuda.set_stream(st); ctx.set_stream(st.cuda_stream)
@@ -24,7 +25,7 @@ for depth in (1, 4):
     names = ["start", "ground", "cluster", "box", "tracker"] + list(bench.KERNEL_NAMES)
     print(f"--- pipeline_depth {depth}: {len(tl)} frames; columns = completion time (us) relative to the oldest frame's start")
     print("frame " + " ".join(f"{x[:9]:>9s}" for x in names))
-    for f, row in enumerate(tl[-14:]):
+    for f, row in enumerate(tl[-14:] if not BRIEF else []):
         print(f"{f:5d} " + " ".join(f"{v:9.1f}" for v in row[: len(names)]))
     if len(tl) > 12:
         per = (tl[-1, 4] - tl[-11, 4]) / 10
@@ -34,8 +35,7 @@ for depth in (1, 4):
         det = tl[-10:, 10] - tl[-10:, 0]
         print(f"  detection start -> box_fit done {det.mean():.1f} us; box_fit done -> TA done {(tl[-10:, 11] - tl[-10:, 10]).mean():.1f} us")
     tr = ctx.debug_phase_clock()
-    if len(tr): print(f"last frame: ground kernel span {(tr[:, 7].max() - tr[:, 0].min()) / 1e3:.2f} us (CTA stamps); "
-                      f"spawn_output start->end by %globaltimer: {(int(tr[0, 1]) - int(tr[0, 0])) / 1e3:.2f} us, T = {int(tr[0, 2])}, visible = {int(tr[0, 3])}")
+    if len(tr): print(f"last frame: ground kernel span {(tr[:, 7].max() - tr[:, 0].min()) / 1e3:.2f} us (CTA stamps)")
     ctx.enable_timing(False)
     # the same loop without timing events: frames/s as bench.py measures `value`
     ctx.tracker_reset()
@@ -49,10 +49,15 @@ for depth in (1, 4):
     ctx.flush(); e1.record(st); torch.cuda.synchronize()
     hn = ctx.debug_host_ns()
     tt = ctx.debug_tracker_trace().astype(np.int64)[-12:]
+    ph = ctx.last_tc_phases.astype(np.int64); ph = ph[ph > 0]
+    pb = ctx.last_tb_phases.astype(np.int64); pb = pb[pb > 0]
+    if len(pb) > 1: print("  TB phases of track 0 (us after its start: staged, gate list, association, update_bb, PDA, lambda, merge+end, written back):", " ".join(f"{(x - pb[0]) / 1e3:.2f}" for x in pb[1:]))
+    if len(ph) > 1: print("  TC phases (us after its start: loads issued, summaries in, boxes staged, pass A, exact tests, pass B, emit, act list, spawn, end):", " ".join(f"{(x - ph[0]) / 1e3:.2f}" for x in ph[1:]))
     ta, tb, tc = (tt[:, 1] - tt[:, 0]) / 1e3, (tt[:, 3] - tt[:, 2]) / 1e3, (tt[:, 5] - tt[:, 4]) / 1e3
     g1, g2, g3 = (tt[:, 2] - tt[:, 1]) / 1e3, (tt[:, 4] - tt[:, 3]) / 1e3, (tt[1:, 0] - tt[:-1, 5]) / 1e3
+    la, lb = (tt[:, 6] - tt[:, 0]) / 1e3, (tt[:, 7] - tt[:, 2]) / 1e3
     print(f"  tracker chain by %globaltimer, no events in the streams (mean of the last 12 steps, us): TA {ta.mean():.1f} | gap {g1.mean():.1f} | "
           f"TB {tb.mean():.1f} | gap {g2.mean():.1f} | TC {tc.mean():.1f} | gap to the next frame's TA {g3.mean():.1f}  "
-          f"(TA start to next TA start {((tt[1:, 0] - tt[:-1, 0]) / 1e3).mean():.1f})")
+          f"(TA start to next TA start {((tt[1:, 0] - tt[:-1, 0]) / 1e3).mean():.1f}); last working CTA starts {la.mean():.1f} after TA's first, {lb.mean():.1f} after TB's first")
     print(f"  no timing events: {K / (e0.elapsed_time(e1) * 1e-3):.0f} frames/s ({1e3 * e0.elapsed_time(e1) / K:.1f} us/frame); python loop {1e6 * th / K:.1f} us/frame, inside the library {hn[0] / 1e3 / (W + K):.1f} us/frame")
     ctx.close()
