@@ -370,7 +370,8 @@ class Lmot:
         self._chk(self.lib.lmot_debug_tracker_trace(self.h, raw.ctypes.data_as(C.POINTER(C.c_ulonglong)), C.byref(nxt)))
         buf = raw[:256].reshape(32, 8).copy()
         self.last_tc_phases = raw[256:272].copy()
-        self.last_tb_phases = raw[272:].copy()        # same for the first track's warp of imm_update_kernel       # %globaltimer stamps inside the last spawn_output_kernel (fast path)
+        self.last_tb_phases = raw[272:282].copy()
+        self.last_gate_phases = raw[282:].copy()     # [0] gate kernel entry, [1] gate kernel after its wait, [2] TA CTA 0 entry (before its wait)        # same for the first track's warp of imm_update_kernel       # %globaltimer stamps inside the last spawn_output_kernel (fast path)
         for k in (0, 2, 4):
             buf[:, k] = ~buf[:, k]        # starts are stored complemented (see trace_start in tracker.cu)
         return np.roll(buf, -nxt.value, axis=0)

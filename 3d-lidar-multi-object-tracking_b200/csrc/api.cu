@@ -132,19 +132,29 @@ int submit(Ctx* c, Slot* s, Result* r, const float4* d_pts, int n, bool with_tra
   if (c->timing) cudaEventRecord(r->ev[1], s->stream);
   if ((rc = cluster_launch(c, s, s->stream, n, true))) return rc;
   if (c->timing) cudaEventRecord(r->ev[2], s->stream);
-  if ((rc = boxfit_launch(c, s, s->stream, n))) return rc;
+  if ((rc = boxfit_launch(c, s, s->stream, n, with_tracker))) return rc;      // with_tracker: posts the slot's detection semaphore
   if (c->timing) cudaEventRecord(r->ev[3], s->stream);
   LMOT_CUDA(c, cudaEventRecord(s->ev_det_done, s->stream));
   if (with_tracker) {
-    LMOT_CUDA(c, cudaStreamWaitEvent(c->trk_stream, s->ev_det_done, 0));
-    if ((rc = tracker_launch(c, s, c->trk_stream, s->d_boxes, s->d_counters, ts, v, yaw))) return rc;
-    if (c->timing) cudaEventRecord(r->ev[4], c->trk_stream);
-    LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, c->trk_stream));      // the slot is free: its boxes / counters were consumed
-    LMOT_CUDA(c, cudaEventRecord(r->ev_tc, c->trk_stream));
-    // device block -> pinned host block, off the tracker's sequential chain
-    LMOT_CUDA(c, cudaStreamWaitEvent(c->pub_stream, r->ev_tc, 0));
-    if ((rc = tracker_publish(c, r, c->pub_stream))) return rc;
-    LMOT_CUDA(c, cudaEventRecord(r->ev_done, c->pub_stream));
+    // the tracker waits for this frame's detection on the DEVICE (gate kernel), or on ev_det_done where that is not possible
+    bool gated = false;
+    if ((rc = tracker_launch(c, s, c->trk_stream, s->d_boxes, s->d_counters, ts, v, yaw, true, &gated))) return rc;
+    if (gated) {
+      // Nothing but kernels on the tracker stream (an event record between spawn_output_kernel and the next frame's gate
+      // kernel would serialise the two launches): publish_kernel polls the device-side step count, and "the slot is free"
+      // is recorded behind it on the publish stream -- ~10 us later than strictly necessary, detection has >100 us of slack
+      if ((rc = tracker_publish(c, r, c->pub_stream))) return rc;
+      LMOT_CUDA(c, cudaEventRecord(r->ev_done, c->pub_stream));
+      LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, c->pub_stream));
+    } else {
+      if (c->timing) cudaEventRecord(r->ev[4], c->trk_stream);
+      LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, c->trk_stream));      // the slot is free: its boxes / counters were consumed
+      LMOT_CUDA(c, cudaEventRecord(r->ev_tc, c->trk_stream));
+      // device block -> pinned host block, off the tracker's sequential chain
+      LMOT_CUDA(c, cudaStreamWaitEvent(c->pub_stream, r->ev_tc, 0));
+      if ((rc = tracker_publish(c, r, c->pub_stream))) return rc;
+      LMOT_CUDA(c, cudaEventRecord(r->ev_done, c->pub_stream));
+    }
   } else {
     // no spawn_output_kernel will snapshot the counters / boxes: copy them before the slot is reused
     LMOT_CUDA(c, cudaMemcpyAsync(r->h_det, s->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
@@ -299,7 +309,7 @@ int lmot_default_params(lmot_params* p) {
   p->max_points = 1 << 20; p->max_clusters = 4096; p->max_boxes = 1024; p->max_tracks = 8192;
   p->node_prefilter = 0; p->filter_z_min = -3.0f; p->filter_z_max = 1.0f;
   p->filter_x_min = -15.f; p->filter_x_max = 5.f; p->filter_y_min = -50.f; p->filter_y_max = 50.f;
-  p->pipeline_depth = 4;
+  p->pipeline_depth = 8;   // detection takes ~150 us per frame: 8 frames in flight keep it ahead of the ~40 us tracker chain
   p->result_ring = 32;
   return LMOT_OK;
 }
@@ -876,8 +886,14 @@ int lmot_debug_tracker_trace(lmot_ctx* ctx, unsigned long long* out, int* next) 
   int rc = lmot_sync(ctx);
   if (rc) return rc;
   if (!c->d_trk_trace) return LMOT_ERR_STATE;
-  LMOT_CUDA(c, cudaMemcpy(out, c->d_trk_trace, (32 * 8 + 32) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  if (next) *next = (int)(c->trk_frames % 32);
+  // the last 32 steps, oldest first (rows of steps that never ran stay zero), then the 32 phase stamps
+  for (int i = 0; i < 32; ++i) {
+    const long long f = (long long)c->trk_frames - 32 + i;
+    if (f < 0) { memset(out + i * 8, 0, 8 * sizeof(unsigned long long)); continue; }
+    LMOT_CUDA(c, cudaMemcpy(out + i * 8, c->d_trk_trace + (size_t)(f % kTraceRows) * 8, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  }
+  LMOT_CUDA(c, cudaMemcpy(out + 256, c->d_trk_trace + (size_t)kTraceRows * 8, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (next) *next = 0;
   return LMOT_OK;
 }
 
@@ -890,8 +906,9 @@ int lmot_debug_phase_clock(lmot_ctx* ctx, unsigned long long* out, int cap_ctas,
   if (!c->d_phase_clock) {
     LMOT_CUDA(c, cudaMalloc(&c->d_phase_clock, (size_t)c->fused_max_ctas * 8 * sizeof(unsigned long long)));
     LMOT_CUDA(c, cudaMemset(c->d_phase_clock, 0, (size_t)c->fused_max_ctas * 8 * sizeof(unsigned long long)));
-    LMOT_CUDA(c, cudaMalloc(&c->d_trk_trace, (32 * 8 + 32) * sizeof(unsigned long long)));
-    LMOT_CUDA(c, cudaMemset(c->d_trk_trace, 0, (32 * 8 + 32) * sizeof(unsigned long long)));
+    LMOT_CUDA(c, cudaMalloc(&c->d_trk_trace, ((size_t)kTraceRows * 8 + 32) * sizeof(unsigned long long)));
+    LMOT_CUDA(c, cudaMemset(c->d_trk_trace, 0, ((size_t)kTraceRows * 8 + 32) * sizeof(unsigned long long)));
+    c->trk_frames = 0;
     if (n_ctas) *n_ctas = 0;
     return LMOT_OK;
   }

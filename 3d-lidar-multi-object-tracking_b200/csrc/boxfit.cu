@@ -212,7 +212,7 @@ box_fit_kernel(const float4* __restrict__ sorted_pts, const int* __restrict__ se
                const int* __restrict__ seg_size, int* __restrict__ counters, BoxParams P,
                const unsigned long long* __restrict__ mt_raw, int n_raw, int max_clusters, int max_boxes,
                float* __restrict__ cl_box, float* __restrict__ cl_marker, uint8_t* __restrict__ cl_ok,
-               float* __restrict__ boxes, float* __restrict__ markers, int* __restrict__ done) {
+               float* __restrict__ boxes, float* __restrict__ markers, int* __restrict__ done, int* __restrict__ det_sem) {
   __shared__ int s_lo[kCols], s_hi[kCols];
   __shared__ short s_hx[kHullCap], s_hy[kHullCap];
   __shared__ short s_cx[kCols], s_clo[kCols], s_chi[kCols];     // occupied pixel columns, compacted
@@ -530,6 +530,12 @@ box_fit_kernel(const float4* __restrict__ sorted_pts, const int* __restrict__ se
     if (carry > max_boxes) { counters[CNT_ERROR] = LMOT_ERR_CAPACITY; carry = max_boxes; }
     counters[CNT_N_BOXES] = carry;
   }
+  // the frame's detection stages are complete: post the slot's semaphore for the tracker's gate kernel (tracker.cu), which takes
+  // the place of a stream-level event wait in front of the tracker chain
+  if (det_sem) {
+    __syncthreads();
+    if (tid == 0) { __threadfence(); atomicAdd(det_sem, 1); }
+  }
 }
 
 }  // namespace
@@ -562,17 +568,19 @@ int boxfit_alloc(Ctx* c, Slot* s) {
   LMOT_CUDA(c, cudaMalloc(&s->d_markers, (size_t)c->prm.max_boxes * 6 * sizeof(float)));
   LMOT_CUDA(c, cudaMalloc(&s->d_done, sizeof(int)));
   LMOT_CUDA(c, cudaMemsetAsync(s->d_done, 0, sizeof(int), s->stream));
+  LMOT_CUDA(c, cudaMalloc(&s->d_det_sem, sizeof(int)));
+  LMOT_CUDA(c, cudaMemsetAsync(s->d_det_sem, 0, sizeof(int), s->stream));
   return LMOT_OK;
 }
 
 void boxfit_free(Slot* s) {
   cudaFree(s->d_pcid); cudaFree(s->d_table); cudaFree(s->d_seg_start); cudaFree(s->d_seg_size); cudaFree(s->d_sorted_pts);
   cudaFree(s->d_cl_box); cudaFree(s->d_cl_marker); cudaFree(s->d_cl_ok); cudaFree(s->d_boxes); cudaFree(s->d_markers);
-  cudaFree(s->d_done);
+  cudaFree(s->d_done); cudaFree(s->d_det_sem);
 }
 
 // inputs: s->d_elev / CNT_N_ELEV, s->d_cart (from clustering), s->d_label_grid / CNT_NUM_CLUSTER
-int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper) {
+int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper, bool post_sem) {
   const int K1 = c->prm.max_clusters + 1;
   const int tiles = (n_upper + kTile - 1) / kTile;
   const size_t sh = (size_t)K1 * sizeof(int);
@@ -596,7 +604,7 @@ int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper) {
   P.t_ratio_max = p.t_ratio_max; P.min_len_ratio = p.min_len_ratio; P.t_pt_per_m3 = p.t_pt_per_m3;
   box_fit_kernel<<<c->fit_ctas, kFitThreads, 0, st>>>(s->d_sorted_pts, s->d_seg_start, s->d_seg_size, s->d_counters, P,
                                                       c->d_mt_raw, c->n_mt_raw, c->prm.max_clusters, c->prm.max_boxes, s->d_cl_box,
-                                                      s->d_cl_marker, s->d_cl_ok, s->d_boxes, s->d_markers, s->d_done);
+                                                      s->d_cl_marker, s->d_cl_ok, s->d_boxes, s->d_markers, s->d_done, post_sem ? s->d_det_sem : (int*)nullptr);
   kernel_mark(c, s, st);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;

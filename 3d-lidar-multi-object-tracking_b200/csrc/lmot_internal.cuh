@@ -61,6 +61,7 @@ struct TrackerHost {
 };
 
 constexpr int kMaxKernelEvents = 20;
+constexpr int kTraceRows = 1024;      // diagnostic ring of per-frame tracker kernel spans (8 words each), then 32 phase stamps
 
 // Result block: where one frame's results land.  Pinned, device-mapped host memory written by the kernels themselves
 // (box compaction, spawn_output_kernel) -- the stores ARE the D2H transfer; the host waits on ev_done and reads.
@@ -145,6 +146,7 @@ struct Slot {
   float* d_boxes = nullptr;            // [max_boxes][8][3] accepted boxes, cluster-id order
   float* d_markers = nullptr;          // [max_boxes][6]
   int* d_done = nullptr;               // last-CTA-done counter
+  int* d_det_sem = nullptr;            // semaphore: +1 by box_fit_kernel's last CTA (frame submissions), -1 by spawn_output_kernel
 
   struct Result* res = nullptr;        // result block of the frame currently (or last) processed on this slot
 };
@@ -166,7 +168,7 @@ struct Ctx {
   int max_points = 0, max_sort_tiles = 0, fit_ctas = 296, n_mt_raw = 0;
   bool coop_launch = false;            // LMOT_COOP=1: cudaLaunchCooperativeKernel for the ground kernel (A/B diagnostics)
   int fused_max_ctas = 0;              // co-residency limit of the cooperative ground kernel on this device
-  unsigned long long* d_trk_trace = nullptr;     // diagnostic: [32][8] per-frame kernel spans of the tracker chain (same switch)
+  unsigned long long* d_trk_trace = nullptr;     // diagnostic: [kTraceRows][8] per-frame kernel spans of the tracker chain + 32 phase stamps (same switch)
   unsigned long long trk_frames = 0;
   unsigned long long* d_phase_clock = nullptr;   // diagnostic: [CTAs][8] %globaltimer stamps of the last ground launch (lmot_debug_phase_clock)
   int last_ground_ctas = 0;
@@ -192,6 +194,8 @@ struct Ctx {
   cudaStream_t pub_stream = nullptr;   // device -> host publication of finished frames
   int* d_act_list = nullptr;           // [max_tracks] tracks to visit next frame (built by spawn_output_kernel)
   double4* d_pos = nullptr;            // [max_tracks] packed (x, y, yaw, -) of every track's merged state
+  unsigned* d_tc_seq = nullptr;        // tracker steps completed (counted by spawn_output_kernel, polled by publish_kernel)
+  unsigned tc_launched = 0;            // host: tracker steps launched
   void* d_summary = nullptr;           // [max_tracks] ActSummary (tracker.cu): what TC needs of each active track, written by TB
   Result* last_trk_res = nullptr;      // result block of the previous tracker step (its device copy seeds the next one)
   bool act_valid = false;              // false after the table was written from the host: rebuilt before the next step
@@ -260,13 +264,13 @@ int cluster_outputs_launch(Ctx* c, Slot* s, cudaStream_t st);      // makeCluste
 int boxfit_alloc(Ctx* c, Slot* s);
 int boxfit_alloc_shared(Ctx* c);
 void boxfit_free(Slot* s);
-int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper);
+int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper, bool post_sem = false);
 void origin_points_fold(TrackerHost& h, double timestamp, double v_gps, double yaw_gps);
 int tracker_alloc(Ctx* c);
 void tracker_free(Ctx* c);
 // boxes: device float[M][8][3] with M in det_counters[CNT_N_BOXES]; results into the slot's pinned host block
 int tracker_launch(Ctx* c, Slot* s, cudaStream_t st, const float* d_boxes, const int* det_counters, double timestamp, double v_gps,
-                   double yaw_gps);
+                   double yaw_gps, bool gate = false, bool* gated = nullptr);   // gate: wait for the slot's detection semaphore on the device (tracker.cu)
 int tracker_publish(Ctx* c, Result* r, cudaStream_t st);            // device block of r -> pinned host block
 int boxes_publish(Ctx* c, Slot* s, Result* r, cudaStream_t st);     // detection-only: slot box list -> pinned host block
 

@@ -24,6 +24,7 @@
 // All state is fp64 like the reference (Eigen::MatrixXd); this file is compiled with -fmad=false so that the
 // operation sequence matches the x86-64 build of the reference except for libm (sin/cos/exp/pow/atan2 <= 2 ulp).
 #include <cfloat>
+#include <cstdlib>
 #include <climits>
 #include <vector>
 #include "lmot_internal.cuh"
@@ -158,6 +159,32 @@ __device__ void ukf_initialize(TrackState& t, double zx, double zy) {   // UKF::
   t.trackNum = 1; t.lifetime = 0; t.nVelo = 0; t.nBBox = 0; t.nBest = 0; t.isStatic = 0; t.isVisBB = 0;
 }
 
+// ------------------------------------------------------------------------------------------------ gate
+// The tracker of frame f+1 needs (a) the tracker of frame f (same stream) and (b) the detection stages of frame f+1 (another
+// stream).  (b) as a stream-level event wait in front of TA costs a full launch latency on the sequential chain AFTER the
+// previous spawn_output_kernel has drained (measured 6.5-9.4 us of 44 per frame), because an event wait cannot sit between two
+// programmatically dependent launches.  Instead: box_fit_kernel's last CTA posts a per-slot semaphore, and this one-warp
+// kernel -- launched as a programmatic dependent of the previous frame's spawn_output_kernel, so it is resident early --
+// polls it, THEN lets TA's CTAs come (they hold SM resources, so they must not be resident while anything they wait for is
+// still outside this stream: a ground kernel that needs every one of its CTAs co-resident could starve), then waits for the
+// previous tracker step.  TA's own griddepcontrol.wait returns when this kernel has completed, i.e. when both (a) and (b) hold.
+__global__ void __launch_bounds__(32)
+tracker_gate_kernel(const int* __restrict__ det_sem, unsigned long long* __restrict__ phase) {
+  if (phase && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); phase[26] = t; }
+  if (threadIdx.x == 0) {
+    unsigned spin = 0;
+    int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(det_sem) : "memory");
+      if (++spin > (1u << 22)) __trap();       // detection never finished (seconds): fail loudly instead of hanging the stream
+    } while (v < 1);
+  }
+  __syncwarp();
+  pdl_launch_dependents();
+  pdl_wait();
+  if (phase && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); phase[27] = t; }
+}
+
 // ------------------------------------------------------------------------------------------------ TA
 constexpr int kTAThreads = 128;     // warps 0-2: one motion model each; warp 3: explosion guard, then helps gating
 
@@ -179,8 +206,11 @@ __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(
 __global__ void __launch_bounds__(kTAThreads, 4)     // <= 128 registers: a CTA (16 K registers) fits on an SM next to a ground-kernel CTA (47 K)
 imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, const int* __restrict__ det, const float* __restrict__ boxes,
                         double dt, unsigned* __restrict__ gate, unsigned* __restrict__ setter, int* __restrict__ first_setter,
-                        uint8_t* __restrict__ skip, int words, const int* __restrict__ act_list, unsigned long long* trace) {
+                        uint8_t* __restrict__ skip, int words, const int* __restrict__ act_list, unsigned long long* trace,
+                        unsigned long long* __restrict__ phase) {
   __shared__ TAShared sh;
+  if (phase && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); phase[28] = t; }
+  pdl_wait();                              // (gated launch: the gate kernel, hence the previous tracker step and this frame's detection, is complete)
   pdl_launch_dependents();                 // TB's CTAs may line up behind this grid
   trace_start(trace, 0);
   struct TraceEnd { unsigned long long* t; __device__ ~TraceEnd() { __syncthreads(); trace_end(t, 0); } } trace_at_exit{trace};
@@ -459,7 +489,6 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ TB
-constexpr int kTBWarps = 4;
 
 // What TC needs of an active track, 128 bytes per entry of the active list, written by TB (which has the record staged in
 // shared memory anyway) and read by TC with one coalesced load: TC's merge / spawn / output logic is a chain of dependent
@@ -497,16 +526,6 @@ __device__ double bbox_yaw(const float b[][3], double ukfYaw) {
   if (diffYaw < kPi * 0.5) return yaw;
   yaw += kPi;
   return wrap_pi(yaw);
-}
-
-// updateBoxYaw :512-532.  The reference evaluates cos(dyaw) / sin(dyaw) four times per corner; they are pure functions of
-// the same argument, so cd / sd are computed once by the caller (bit-identical, 60 fp64 trig evaluations fewer per track).
-__device__ void update_box_yaw(float bb[][3], int n, double cpx, double cpy, double cd, double sd) {
-  for (int i = 0; i < n; ++i) {
-    const double preX = bb[i][0], preY = bb[i][1];
-    bb[i][0] = (float)(cd * (preX - cpx) - sd * (preY - cpy) + cpx);
-    bb[i][1] = (float)(sd * (preX - cpx) + cd * (preY - cpy) + cpy);
-  }
 }
 
 // updateBB :565-653, executed by the whole warp on the track staged in shared memory.  The reference's statements in its
@@ -564,315 +583,341 @@ __device__ void update_bb_warp(TrackState& t, int lane) {
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kTBWarps * 32)
+constexpr int kTBThreads = 128;     // warps 0-2: PDA update of one motion model each; warp 3: box association + updateBB
+
+struct TBShared {
+  TrackState trk;                   // the track, staged (1.6 KB)
+  ActSummary sum;
+  double xnew[3][5];                // per model: updated state
+  double Pnew[3][25];               // per model: updated covariance
+  double eSum[3];
+  int tn_out, life_out;             // trackNum / lifetime_ to store once every warp has read the old values
+};
+
+// One CTA per active track.  What the reference does one after the other for a track, and what does not depend on each other,
+// runs on different warps: the PDA update of the three motion models (each its own S^-1, Gaussian kernels, beta weights,
+// K nu, covariance update -- identical code, different model) on warps 0..2, measurement bookkeeping / box association /
+// updateBB on warp 3; then warp 0 alone: association likelihoods, mode probabilities, merged estimate.
+__global__ void __launch_bounds__(kTBThreads)
 imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, const int* __restrict__ det, const float* __restrict__ boxes,
                   const unsigned* __restrict__ gate, const int* __restrict__ first_setter, const uint8_t* __restrict__ skip,
                   int words, const int* __restrict__ act_list, ActSummary* __restrict__ summary, unsigned long long* trace,
                   unsigned long long* __restrict__ phase) {
-  extern __shared__ unsigned short s_list_all[];          // per warp: indices of the gated boxes, in box order
-  __shared__ TrackState s_trk[kTBWarps];
-  __shared__ ActSummary s_sum[kTBWarps];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  extern __shared__ unsigned short s_list[];              // indices of the gated boxes, in box order
+  __shared__ TBShared sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_wait();                              // TA has finished (gate rows, first_setter, predicted states are visible)
   pdl_launch_dependents();                 // TC's CTA may line up behind this grid
-  // diagnostic: %globaltimer stamps of the first track's warp
-  auto mark = [&](int i) { if (phase && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); phase[16 + i] = t; } };
+  // diagnostic: %globaltimer stamps of the first track's CTA
+  auto mark = [&](int i) { if (phase && blockIdx.x == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); phase[16 + i] = t; } };
   mark(0);
   trace_start(trace, 1);
   struct TraceEnd { unsigned long long* t; __device__ ~TraceEnd() { __syncthreads(); trace_end(t, 1); } } trace_at_exit{trace};
   const int n_act = trk[CNT_N_ACT];
   const int M = det[CNT_N_BOXES];
-  if (trace && threadIdx.x == 0 && (int)blockIdx.x * kTBWarps < n_act) { unsigned long long tn; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn)); atomicMax(&trace[7], tn); }
-  unsigned short* s_list = s_list_all + (size_t)warp * words * 32;
+  if (trace && tid == 0 && (int)blockIdx.x < n_act) { unsigned long long tn; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn)); atomicMax(&trace[7], tn); }
   const int nchunk = (M + 31) >> 5;
+  TrackState& t = sh.trk;
 
-  for (int q = blockIdx.x * kTBWarps + warp; q < n_act; q += gridDim.x * kTBWarps) {
+  for (int q = blockIdx.x; q < n_act; q += gridDim.x) {
     const int it = act_list[q];
     const bool skipped = skip[it] != 0;      // dead, or killed by TA's guards: no update, but TC still wants its summary
+    __syncthreads();                         // the previous track's readers are done with the shared copy
     // stage the whole track (1.6 KB) in shared memory with coalesced 8-byte loads: the update below touches almost
     // every field several times, and every one of those touches would otherwise be its own trip to L2 / HBM
     {
       const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&tracks[it]);
-      unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_trk[warp]);
-      constexpr int kIt = (kTrackWords + 31) / 32;
-      unsigned long long v[kIt];                     // all loads in flight before the first store: one round trip, not kIt
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sh.trk);
+      constexpr int kIt = (kTrackWords + kTBThreads - 1) / kTBThreads;
+      unsigned long long v[kIt];                     // all loads in flight before the first store
 #pragma unroll
-      for (int u = 0; u < kIt; ++u) { const int w = lane + 32 * u; v[u] = (w < kTrackWords) ? src[w] : 0ull; }
+      for (int u = 0; u < kIt; ++u) { const int w = tid + kTBThreads * u; v[u] = (w < kTrackWords) ? src[w] : 0ull; }
 #pragma unroll
-      for (int u = 0; u < kIt; ++u) { const int w = lane + 32 * u; if (w < kTrackWords) dst[w] = v[u]; }
+      for (int u = 0; u < kIt; ++u) { const int w = tid + kTBThreads * u; if (w < kTrackWords) dst[w] = v[u]; }
     }
-    __syncwarp();
+    __syncthreads();
     mark(1);
-    TrackState& t = s_trk[warp];
-    if (!skipped) do {
-    const int trackNum0 = t.trackNum;
-    const bool secondInit = (trackNum0 == 1);
-    // ---- lifetime_ (:232): a gated box counts unless an earlier track already matched it
-    int nmeas = 0, life = 0;
-    for (int ch0 = 0; ch0 < nchunk; ch0 += 4) {      // four chunks per batch: two round trips (gate words, then first_setter), not two per chunk
-      unsigned g4[4]; int fs4[4];
+    bool pda = false;                        // CTA-uniform: the track reaches filterPDA
+    int nmeas = 0, mm = 0;
+    double numMeas = 0;
+    if (!skipped) {
+      const int trackNum0 = t.trackNum;
+      const bool secondInit = (trackNum0 == 1);
+      // ---- lifetime_ (:232): a gated box counts unless an earlier track already matched it.  Every warp derives the list for
+      // itself (same loads, same values: no CTA barrier in front of the model warps)
+      int life = 0;
+      for (int ch0 = 0; ch0 < nchunk; ch0 += 4) {      // four chunks per batch: two round trips (gate words, then first_setter), not two per chunk
+        unsigned g4[4]; int fs4[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) g4[u] = (ch0 + u < nchunk) ? gate[(size_t)it * words + ch0 + u] : 0u;
+        for (int u = 0; u < 4; ++u) g4[u] = (ch0 + u < nchunk) ? gate[(size_t)it * words + ch0 + u] : 0u;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) fs4[u] = ((g4[u] >> lane) & 1u) ? first_setter[(ch0 + u) * 32 + lane] : INT_MAX;
+        for (int u = 0; u < 4; ++u) fs4[u] = ((g4[u] >> lane) & 1u) ? first_setter[(ch0 + u) * 32 + lane] : INT_MAX;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const unsigned g = g4[u];
-        const int b = (ch0 + u) * 32 + lane;
-        const bool cnt = ((g >> lane) & 1u) && (fs4[u] >= it);
-        life += __popc(__ballot_sync(0xFFFFFFFFu, cnt));
-        if ((g >> lane) & 1u) s_list[nmeas + __popc(g & ((1u << lane) - 1u))] = (unsigned short)b;
-        nmeas += __popc(g);
-      }
-    }
-    __syncwarp();
-    mark(2);
-    const int lifetime = t.lifetime + life;
-
-    // measurement prediction used by the gate (same selection as TA)
-    const double dcv = det2(t.S[0]), dctrv = det2(t.S[1]), drm = det2(t.S[2]);
-    int mm;
-    if (dcv > dctrv) mm = (dcv > drm) ? 0 : 2; else mm = (dctrv > drm) ? 1 : 2;
-
-    int measCount = nmeas;     // measVec.size()
-    double sx = 0, sy = 0;     // the single measurement of a secondInit track
-    if (secondInit) {
-      // the last running minimum == first occurrence of the smallest NIS (:238-255)
-      double S4[4], Si[4];
-      for (int e = 0; e < 4; ++e) S4[e] = t.S[mm][e] * 4;
-      inv2_lu(S4, Si);
-      double best = DBL_MAX; int bi = INT_MAX; double bx = 0, by = 0;
-      for (int k = lane; k < nmeas; k += 32) {
-        double cx, cy;
-        cp_from_box(boxes + (size_t)s_list[k] * 24, cx, cy);
-        const double d0 = cx - t.zPred[mm][0], d1 = cy - t.zPred[mm][1];
-        const double nis = (d0 * Si[0] + d1 * Si[2]) * d0 + (d0 * Si[1] + d1 * Si[3]) * d1;
-        if (nis < best) { best = nis; bi = k; bx = cx; by = cy; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xFFFFFFFFu, best, o), ox = __shfl_xor_sync(0xFFFFFFFFu, bx, o), oy = __shfl_xor_sync(0xFFFFFFFFu, by, o);
-        const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
-        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; bx = ox; by = oy; }
-      }
-      measCount = (nmeas > 0) ? 1 : 0;
-      sx = bx; sy = by;
-    }
-
-    // ---- associateBB (:416-463) + getNearestEuclidBBox (:396-413): int minDist => first box with the smallest
-    // floor(distance); secondInit tracks have an empty bboxVec
-    int isVis = 0;
-    if (!secondInit && nmeas > 0 && trackNum0 == 5 && lifetime > lifeTimeThres) {
-      const double px = t.x[0][0], py = t.x[0][1];
-      long long key = LLONG_MAX;      // (floor(dist) << 32) | position
-      for (int k = lane; k < nmeas; k += 32) {
-        double cx, cy;
-        cp_from_box(boxes + (size_t)s_list[k] * 24, cx, cy);
-        const double dist = sqrt((px - cx) * (px - cx) + (py - cy) * (py - cy));
-        if (dist < 999) { const long long kk = ((long long)(int)dist << 32) | (unsigned)k; key = key < kk ? key : kk; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { const long long ok = __shfl_xor_sync(0xFFFFFFFFu, key, o); key = key < ok ? key : ok; }
-      int minDist = 999, minInd = 0;
-      if (key != LLONG_MAX) { minDist = (int)(key >> 32); minInd = (int)(key & 0xFFFFFFFFll); }
-      if (minDist < distanceThres) {
-        const float* b = boxes + (size_t)s_list[minInd] * 24;
-        if (lane < 8) {
-          const int c = lane & 3;
-          t.BBox[lane][0] = b[c * 3]; t.BBox[lane][1] = b[c * 3 + 1];
-          t.BBox[lane][2] = (lane < 4) ? (float)-1.73 : 0.f;
-        }
-        isVis = 1;
-      }
-    }
-    __syncwarp();
-    mark(3);
-    if (lane == 0) {
-      t.lifetime = lifetime;
-      if (isVis) { t.isVisBB = 1; t.nBBox = 8; }
-    }
-    __syncwarp();
-    update_bb_warp(t, lane);                            // :877
-    __syncwarp();
-    mark(4);
-
-    if (secondInit) {                                   // :882-921
-      if (lane == 0) {
-        if (measCount == 0) t.trackNum = 0;
-        else {
-          t.initMeas[0] = t.x[0][0]; t.initMeas[1] = t.x[0][1];
-          const double dX = sx - t.x[0][0], dY = sy - t.x[0][1];
-          const double targetYaw = wrap_pi(atan2(dY, dX));
-          for (int m = 0; m < 4; ++m) { t.x[m][0] = sx; t.x[m][1] = sy; t.x[m][2] = 2; t.x[m][3] = targetYaw; }
-          t.trackNum = trackNum0 + 1;
+        for (int u = 0; u < 4; ++u) {
+          const unsigned g = g4[u];
+          const int b = (ch0 + u) * 32 + lane;
+          const bool cnt = ((g >> lane) & 1u) && (fs4[u] >= it);
+          life += __popc(__ballot_sync(0xFFFFFFFFu, cnt));
+          if ((g >> lane) & 1u) s_list[nmeas + __popc(g & ((1u << lane) - 1u))] = (unsigned short)b;   // (all warps store the same values)
+          nmeas += __popc(g);
         }
       }
-      continue;
-    }
-    int tn = trackNum0;                                 // :924-944
-    if (measCount > 0) {
-      if (tn < 3) tn++;
-      else if (tn == 3) tn = 5;
-      else if (tn >= 5) tn = 5;
-    } else {
-      if (tn < 5) tn = 0;
-      else if (tn >= 5 && tn < 10) tn++;
-      else tn = 0;                                      // `else if (trackNum = 10) trackNum = 0` (:941)
-    }
-    if (lane == 0) t.trackNum = tn;
-    if (tn == 0) continue;
+      __syncwarp();
+      mark(2);
+      const int lifetime = t.lifetime + life;
 
-    // ---- filterPDA (:259-394): the three models in turn; scalars replicated on every lane
-    const double numMeas = (double)measCount;
-    const double bb = 2 * numMeas * (1 - pD * pG) / (gammaG * pD);
-    double eSum[3];
-    double xnew[3][5];      // updated model states (all lanes)
-    double Pnew[3];         // lane e < 25: updated covariance element of each model
-    // centre point of every gated box once (lane k <-> measurement k; beyond 32 measurements recomputed on the fly):
-    // the reference re-derives it in each of its nine loops
-    double mcx = 0, mcy = 0;
-    if (lane < nmeas) cp_from_box(boxes + (size_t)s_list[lane] * 24, mcx, mcy);
-    for (int m = 0; m < 3; ++m) {
-      double Si[4];
-      inv2_lu(t.S[m], Si);
-      const double zp0 = t.zPred[m][0], zp1 = t.zPred[m][1];
-      // per-lane innovation and Gaussian kernel of "its" measurement
-      const double ld0 = mcx - zp0, ld1 = mcy - zp1;
-      double le = 0;
-      if (lane < nmeas) { const double t0 = -0.5 * ld0, t1 = -0.5 * ld1; le = exp((t0 * Si[0] + t1 * Si[2]) * ld0 + (t0 * Si[1] + t1 * Si[3]) * ld1); }
-      auto meas = [&](int k, double& d0, double& d1, double& e) {        // k is warp-uniform
-        if (k < 32) { d0 = __shfl_sync(0xFFFFFFFFu, ld0, k); d1 = __shfl_sync(0xFFFFFFFFu, ld1, k); e = __shfl_sync(0xFFFFFFFFu, le, k); }
-        else {
-          double cx, cy;
-          cp_from_box(boxes + (size_t)s_list[k] * 24, cx, cy);
-          d0 = cx - zp0; d1 = cy - zp1;
-          const double t0 = -0.5 * d0, t1 = -0.5 * d1;
-          e = exp((t0 * Si[0] + t1 * Si[2]) * d0 + (t0 * Si[1] + t1 * Si[3]) * d1);
-        }
-      };
-      double es = 0, betaZero, sX0 = 0, sX1 = 0;
-      double sP[4] = {0, 0, 0, 0};
-      if (nmeas <= 32) {
-        // lane k holds measurement k: the per-measurement factors (one fp64 division, the products) are computed by all lanes
-        // at once; only the SUMS run over k in the reference's order (same operands, same operations, same bits) -- the
-        // division and the exp no longer sit inside three serial loops per model
-        for (int k = 0; k < nmeas; ++k) es += __shfl_sync(0xFFFFFFFFu, le, k);
-        betaZero = bb / (bb + es);
-        const double beta = (lane < nmeas) ? le / (bb + es) : 0.0;
-        const double p0 = beta * ld0, p1 = beta * ld1;
-        for (int k = 0; k < nmeas; ++k) { sX0 += __shfl_sync(0xFFFFFFFFu, p0, k); sX1 += __shfl_sync(0xFFFFFFFFu, p1, k); }
-        const double t00 = p0 * ld0 - sX0 * sX0, t01 = p0 * ld1 - sX0 * sX1, t10 = p1 * ld0 - sX1 * sX0, t11 = p1 * ld1 - sX1 * sX1;
-        for (int k = 0; k < nmeas; ++k) {
-          sP[0] += __shfl_sync(0xFFFFFFFFu, t00, k); sP[1] += __shfl_sync(0xFFFFFFFFu, t01, k);
-          sP[2] += __shfl_sync(0xFFFFFFFFu, t10, k); sP[3] += __shfl_sync(0xFFFFFFFFu, t11, k);
+      // measurement prediction used by the gate (same selection as TA)
+      const double dcv = det2(t.S[0]), dctrv = det2(t.S[1]), drm = det2(t.S[2]);
+      if (dcv > dctrv) mm = (dcv > drm) ? 0 : 2; else mm = (dctrv > drm) ? 1 : 2;
+
+      if (secondInit) {                                   // :882-921, all of it on warp 3
+        if (warp == 3) {
+          // the last running minimum == first occurrence of the smallest NIS (:238-255)
+          double S4[4], Si[4];
+          for (int e = 0; e < 4; ++e) S4[e] = t.S[mm][e] * 4;
+          inv2_lu(S4, Si);
+          double best = DBL_MAX; int bi = INT_MAX; double bx = 0, by = 0;
+          for (int k = lane; k < nmeas; k += 32) {
+            double cx, cy;
+            cp_from_box(boxes + (size_t)s_list[k] * 24, cx, cy);
+            const double d0 = cx - t.zPred[mm][0], d1 = cy - t.zPred[mm][1];
+            const double nis = (d0 * Si[0] + d1 * Si[2]) * d0 + (d0 * Si[1] + d1 * Si[3]) * d1;
+            if (nis < best) { best = nis; bi = k; bx = cx; by = cy; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xFFFFFFFFu, best, o), ox = __shfl_xor_sync(0xFFFFFFFFu, bx, o), oy = __shfl_xor_sync(0xFFFFFFFFu, by, o);
+            const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+            if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; bx = ox; by = oy; }
+          }
+          if (lane == 0) {
+            sh.life_out = lifetime;
+            if (nmeas == 0) sh.tn_out = 0;
+            else {
+              t.initMeas[0] = t.x[0][0]; t.initMeas[1] = t.x[0][1];
+              const double dX = bx - t.x[0][0], dY = by - t.x[0][1];
+              const double targetYaw = wrap_pi(atan2(dY, dX));
+              for (int m = 0; m < 4; ++m) { t.x[m][0] = bx; t.x[m][1] = by; t.x[m][2] = 2; t.x[m][3] = targetYaw; }
+              sh.tn_out = trackNum0 + 1;
+            }
+          }
         }
       } else {
-        for (int k = 0; k < nmeas; ++k) { double d0, d1, e; meas(k, d0, d1, e); es += e; }
-        betaZero = bb / (bb + es);
-        for (int k = 0; k < nmeas; ++k) {
-          double d0, d1, e; meas(k, d0, d1, e);
-          const double beta = e / (bb + es);
-          sX0 += beta * d0; sX1 += beta * d1;
+        int tn = trackNum0;                               // :924-944 (measVec.size() == nmeas)
+        if (nmeas > 0) {
+          if (tn < 3) tn++;
+          else if (tn == 3) tn = 5;
+          else if (tn >= 5) tn = 5;
+        } else {
+          if (tn < 5) tn = 0;
+          else if (tn >= 5 && tn < 10) tn++;
+          else tn = 0;                                    // `else if (trackNum = 10) trackNum = 0` (:941)
         }
-        for (int k = 0; k < nmeas; ++k) {
-          double d[2], e; meas(k, d[0], d[1], e);
-          const double beta = e / (bb + es);
-          const double sXv[2] = {sX0, sX1};
+        pda = (tn != 0);
+        numMeas = (double)nmeas;
+        if (warp == 3) {
+          // ---- associateBB (:416-463) + getNearestEuclidBBox (:396-413): int minDist => first box with the smallest
+          // floor(distance)
+          int isVis = 0;
+          if (nmeas > 0 && trackNum0 == 5 && lifetime > lifeTimeThres) {
+            const double px = t.x[0][0], py = t.x[0][1];
+            long long key = LLONG_MAX;      // (floor(dist) << 32) | position
+            for (int k = lane; k < nmeas; k += 32) {
+              double cx, cy;
+              cp_from_box(boxes + (size_t)s_list[k] * 24, cx, cy);
+              const double dist = sqrt((px - cx) * (px - cx) + (py - cy) * (py - cy));
+              if (dist < 999) { const long long kk = ((long long)(int)dist << 32) | (unsigned)k; key = key < kk ? key : kk; }
+            }
 #pragma unroll
-          for (int r = 0; r < 2; ++r)
+            for (int o = 16; o > 0; o >>= 1) { const long long ok = __shfl_xor_sync(0xFFFFFFFFu, key, o); key = key < ok ? key : ok; }
+            int minDist = 999, minInd = 0;
+            if (key != LLONG_MAX) { minDist = (int)(key >> 32); minInd = (int)(key & 0xFFFFFFFFll); }
+            if (minDist < distanceThres) {
+              const float* b = boxes + (size_t)s_list[minInd] * 24;
+              if (lane < 8) {
+                const int c = lane & 3;
+                t.BBox[lane][0] = b[c * 3]; t.BBox[lane][1] = b[c * 3 + 1];
+                t.BBox[lane][2] = (lane < 4) ? (float)-1.73 : 0.f;
+              }
+              isVis = 1;
+            }
+          }
+          if (lane == 0) {
+            sh.life_out = lifetime; sh.tn_out = tn;
+            if (isVis) { t.isVisBB = 1; t.nBBox = 8; }
+          }
+          __syncwarp();
+          update_bb_warp(t, lane);                          // :877 (reads x_merge_ before warp 0 replaces it below)
+        } else if (pda) {
+          // ---- filterPDA (:259-394) for model `warp`; scalars replicated on every lane
+          const int m = warp;
+          const double bb = 2 * numMeas * (1 - pD * pG) / (gammaG * pD);
+          // centre point of every gated box once (lane k <-> measurement k; beyond 32 measurements recomputed on the fly)
+          double mcx = 0, mcy = 0;
+          if (lane < nmeas) cp_from_box(boxes + (size_t)s_list[lane] * 24, mcx, mcy);
+          double Si[4];
+          inv2_lu(t.S[m], Si);
+          const double zp0 = t.zPred[m][0], zp1 = t.zPred[m][1];
+          // per-lane innovation and Gaussian kernel of "its" measurement
+          const double ld0 = mcx - zp0, ld1 = mcy - zp1;
+          double le = 0;
+          if (lane < nmeas) { const double t0 = -0.5 * ld0, t1 = -0.5 * ld1; le = exp((t0 * Si[0] + t1 * Si[2]) * ld0 + (t0 * Si[1] + t1 * Si[3]) * ld1); }
+          double es = 0, betaZero, sX0 = 0, sX1 = 0;
+          double sP[4] = {0, 0, 0, 0};
+          if (nmeas <= 32) {
+            // lane k holds measurement k: the per-measurement factors (one fp64 division, the products) are computed by all
+            // lanes at once; only the SUMS run over k in the reference's order (same operands, same operations, same bits)
+            for (int k = 0; k < nmeas; ++k) es += __shfl_sync(0xFFFFFFFFu, le, k);
+            betaZero = bb / (bb + es);
+            const double beta = (lane < nmeas) ? le / (bb + es) : 0.0;
+            const double p0 = beta * ld0, p1 = beta * ld1;
+            for (int k = 0; k < nmeas; ++k) { sX0 += __shfl_sync(0xFFFFFFFFu, p0, k); sX1 += __shfl_sync(0xFFFFFFFFu, p1, k); }
+            const double t00 = p0 * ld0 - sX0 * sX0, t01 = p0 * ld1 - sX0 * sX1, t10 = p1 * ld0 - sX1 * sX0, t11 = p1 * ld1 - sX1 * sX1;
+            for (int k = 0; k < nmeas; ++k) {
+              sP[0] += __shfl_sync(0xFFFFFFFFu, t00, k); sP[1] += __shfl_sync(0xFFFFFFFFu, t01, k);
+              sP[2] += __shfl_sync(0xFFFFFFFFu, t10, k); sP[3] += __shfl_sync(0xFFFFFFFFu, t11, k);
+            }
+          } else {
+            auto meas = [&](int k, double& d0, double& d1, double& e) {        // k is warp-uniform
+              if (k < 32) { d0 = __shfl_sync(0xFFFFFFFFu, ld0, k); d1 = __shfl_sync(0xFFFFFFFFu, ld1, k); e = __shfl_sync(0xFFFFFFFFu, le, k); }
+              else {
+                double cx, cy;
+                cp_from_box(boxes + (size_t)s_list[k] * 24, cx, cy);
+                d0 = cx - zp0; d1 = cy - zp1;
+                const double t0 = -0.5 * d0, t1 = -0.5 * d1;
+                e = exp((t0 * Si[0] + t1 * Si[2]) * d0 + (t0 * Si[1] + t1 * Si[3]) * d1);
+              }
+            };
+            for (int k = 0; k < nmeas; ++k) { double d0, d1, e; meas(k, d0, d1, e); es += e; }
+            betaZero = bb / (bb + es);
+            for (int k = 0; k < nmeas; ++k) {
+              double d0, d1, e; meas(k, d0, d1, e);
+              const double beta = e / (bb + es);
+              sX0 += beta * d0; sX1 += beta * d1;
+            }
+            for (int k = 0; k < nmeas; ++k) {
+              double d[2], e; meas(k, d[0], d[1], e);
+              const double beta = e / (bb + es);
+              const double sXv[2] = {sX0, sX1};
 #pragma unroll
-            for (int c = 0; c < 2; ++c) sP[r * 2 + c] += ((beta * d[r]) * d[c] - sXv[r] * sXv[c]);
+              for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) sP[r * 2 + c] += ((beta * d[r]) * d[c] - sXv[r] * sXv[c]);
+            }
+          }
+          const double* K = t.K[m];
+          const double* S = t.S[m];
+          if (lane < 5) {
+            double xr = t.x[1 + m][lane] + (K[lane * 2] * sX0 + K[lane * 2 + 1] * sX1);
+            if (lane == 3) xr = wrap_pi(xr);
+            sh.xnew[m][lane] = xr;
+          }
+          if (lane < 25) {
+            const int r = lane / 5, c = lane % 5;
+            const double KS0 = K[r * 2] * S[0] + K[r * 2 + 1] * S[2], KS1 = K[r * 2] * S[1] + K[r * 2 + 1] * S[3];
+            const double KP0 = K[r * 2] * sP[0] + K[r * 2 + 1] * sP[2], KP1 = K[r * 2] * sP[1] + K[r * 2 + 1] * sP[3];
+            const double KSK = KS0 * K[c * 2] + KS1 * K[c * 2 + 1], KPK = KP0 * K[c * 2] + KP1 * K[c * 2 + 1];
+            const double P = t.P[1 + m][lane];
+            double Pe;
+            if (numMeas != 0) Pe = betaZero * P + (1 - betaZero) * (P - KSK) + KPK;
+            else Pe = P - KSK;
+            sh.Pnew[m][lane] = Pe;
+          }
+          if (lane == 0) sh.eSum[m] = es;
         }
       }
-      eSum[m] = es;
-      const double* K = t.K[m];
-      const double* S = t.S[m];
-#pragma unroll
-      for (int r = 0; r < 5; ++r) xnew[m][r] = t.x[1 + m][r] + (K[r * 2] * sX0 + K[r * 2 + 1] * sX1);
-      xnew[m][3] = wrap_pi(xnew[m][3]);
-      double Pe = 0;
-      if (lane < 25) {
-        const int r = lane / 5, c = lane % 5;
-        const double KS0 = K[r * 2] * S[0] + K[r * 2 + 1] * S[2], KS1 = K[r * 2] * S[1] + K[r * 2 + 1] * S[3];
-        const double KP0 = K[r * 2] * sP[0] + K[r * 2 + 1] * sP[2], KP1 = K[r * 2] * sP[1] + K[r * 2 + 1] * sP[3];
-        const double KSK = KS0 * K[c * 2] + KS1 * K[c * 2 + 1], KPK = KP0 * K[c * 2] + KP1 * K[c * 2 + 1];
-        const double P = t.P[1 + m][lane];
-        if (numMeas != 0) Pe = betaZero * P + (1 - betaZero) * (P - KSK) + KPK;
-        else Pe = P - KSK;
-      }
-      Pnew[m] = Pe;
     }
+    __syncthreads();
+    mark(3);
+    if (!skipped && warp == 0) {
+      if (pda) {
+        const double Vk = kPi * sqrt(gammaG * det2(t.S[mm]));     // S is untouched by the update, same max model
+        double lam[3];
+        {
+          // the two pow() (same base, exponents numMeas and 1 - numMeas) on lanes 0 / 1, the three model terms on lanes 0..2: one
+          // pass through pow / sqrt / the divisions instead of two and three
+          const double ex = (lane == 1) ? 1 - numMeas : numMeas;
+          const double pw = pow(Vk, ex);
+          const double powN = __shfl_sync(0xFFFFFFFFu, pw, 0);
+          const double pow1N = (numMeas != 0) ? __shfl_sync(0xFFFFFFFFu, pw, 1) : 0.0;
+          const int ml = (lane < 3) ? lane : 0;
+          const double em = sh.eSum[ml];
+          double lv;
+          if (numMeas != 0) lv = (1 - pG * pD) / powN + pD * pow1N * em / (numMeas * sqrt(2 * kPi * det2(t.S[ml])));
+          else lv = (1 - pG * pD) / powN;
+          lam[0] = __shfl_sync(0xFFFFFFFFu, lv, 0); lam[1] = __shfl_sync(0xFFFFFFFFu, lv, 1); lam[2] = __shfl_sync(0xFFFFFFFFu, lv, 2);
+        }
+        mark(4);
+        // ---- PostProcessIMMUKF: UpdateModeProb (ukf.cpp:384-397), MergeEstimationAndCovariance (:419-437)
+        double mp[3] = {t.modeProb[0], t.modeProb[1], t.modeProb[2]};
+        const double sumG = lam[0] * mp[0] + lam[1] * mp[1] + lam[2] * mp[2];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) { mp[m] = (lam[m] * mp[m]) / sumG; }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) if (fabs(mp[m]) < 0.0001) mp[m] = 0.0001;
+        double xnew[3][5];
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+          for (int e = 0; e < 5; ++e) xnew[m][e] = sh.xnew[m][e];
+        double xm[5];
+#pragma unroll
+        for (int e = 0; e < 5; ++e) xm[e] = mp[0] * xnew[0][e] + mp[1] * xnew[1][e] + mp[2] * xnew[2][e];
+        xm[3] = wrap_pi(xm[3]);
+        double myaw;
+        if (mp[0] > mp[1]) myaw = (mp[0] > mp[2]) ? xnew[0][3] : xnew[2][3];
+        else               myaw = (mp[1] > mp[2]) ? xnew[1][3] : xnew[2][3];
+        xm[3] = myaw;
+        if (lane < 25) {
+          const int r = lane / 5, c = lane % 5;
+          const double Pn0 = sh.Pnew[0][lane], Pn1 = sh.Pnew[1][lane], Pn2 = sh.Pnew[2][lane];
+          const double xr0 = sh.xnew[0][r], xr1 = sh.xnew[1][r], xr2 = sh.xnew[2][r];
+          const double xc0 = sh.xnew[0][c], xc1 = sh.xnew[1][c], xc2 = sh.xnew[2][c];
+          const double xmr = (r == 0) ? xm[0] : (r == 1) ? xm[1] : (r == 2) ? xm[2] : (r == 3) ? xm[3] : xm[4];
+          const double xmc = (c == 0) ? xm[0] : (c == 1) ? xm[1] : (c == 2) ? xm[2] : (c == 3) ? xm[3] : xm[4];
+          const double a0 = mp[0] * (Pn0 + (xr0 - xmr) * (xc0 - xmc));
+          const double a1 = mp[1] * (Pn1 + (xr1 - xmr) * (xc1 - xmc));
+          const double a2 = mp[2] * (Pn2 + (xr2 - xmr) * (xc2 - xmc));
+          t.P[0][lane] = a0 + a1 + a2;
+          t.P[1][lane] = Pn0; t.P[2][lane] = Pn1; t.P[3][lane] = Pn2;
+        }
+        if (lane < 5) {
+          const double xml = (lane == 0) ? xm[0] : (lane == 1) ? xm[1] : (lane == 2) ? xm[2] : (lane == 3) ? xm[3] : xm[4];
+          t.x[0][lane] = xml; t.x[1][lane] = sh.xnew[0][lane]; t.x[2][lane] = sh.xnew[1][lane]; t.x[3][lane] = sh.xnew[2][lane];
+        }
+        if (lane == 0) {
+          t.modeProb[0] = mp[0]; t.modeProb[1] = mp[1]; t.modeProb[2] = mp[2];
+          t.x_merge_yaw = myaw;
+          int nv = t.nVelo;                                 // velo_history_ :955-959
+          if (nv == 3) { t.velo[0] = t.velo[1]; t.velo[1] = t.velo[2]; nv = 2; }
+          t.velo[nv] = xm[2];
+          t.nVelo = nv + 1;
+        }
+      }
+      if (lane == 0) { t.trackNum = sh.tn_out; t.lifetime = sh.life_out; }
+    }
+    __syncthreads();
     mark(5);
-    const double Vk = kPi * sqrt(gammaG * det2(t.S[mm]));     // S is untouched by the update, same max model
-    double lam[3];
-    {
-      // the two pow() (same base, exponents numMeas and 1 - numMeas) on lanes 0 / 1, the three model terms on lanes 0..2: one pass
-      // through pow / sqrt / the divisions instead of two and three
-      const double ex = (lane == 1) ? 1 - numMeas : numMeas;
-      const double pw = pow(Vk, ex);
-      const double powN = __shfl_sync(0xFFFFFFFFu, pw, 0);
-      const double pow1N = (numMeas != 0) ? __shfl_sync(0xFFFFFFFFu, pw, 1) : 0.0;
-      const int ml = (lane < 3) ? lane : 0;
-      const double em = (ml == 0) ? eSum[0] : (ml == 1) ? eSum[1] : eSum[2];
-      double lv;
-      if (numMeas != 0) lv = (1 - pG * pD) / powN + pD * pow1N * em / (numMeas * sqrt(2 * kPi * det2(t.S[ml])));
-      else lv = (1 - pG * pD) / powN;
-      lam[0] = __shfl_sync(0xFFFFFFFFu, lv, 0); lam[1] = __shfl_sync(0xFFFFFFFFu, lv, 1); lam[2] = __shfl_sync(0xFFFFFFFFu, lv, 2);
+    if (!skipped) {
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&sh.trk);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(&tracks[it]);
+      for (int w = tid; w < kTrackWords; w += kTBThreads) dst[w] = src[w];
+    }
+    if (warp == 0) {
+      if (lane == 0) {
+        ActSummary& a = sh.sum;
+        a.x = t.x[0][0]; a.y = t.x[0][1]; a.yaw = t.x[0][3]; a.v = t.x[0][2];
+        a.initx = t.initMeas[0]; a.inity = t.initMeas[1];
+        a.mp0 = t.modeProb[0]; a.mp1 = t.modeProb[1]; a.mp2 = t.modeProb[2];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a.bb[e] = t.BBox[e >> 1][e & 1];
+        a.k = it; a.trackNum = t.trackNum; a.lifetime = t.lifetime;
+        a.isStatic = t.isStatic; a.isVis = t.isVisBB; a.pad[0] = a.pad[1] = 0; a.pad2[0] = a.pad2[1] = 0;
+      }
+      __syncwarp();
+      if (lane < 16) reinterpret_cast<unsigned long long*>(&summary[q])[lane] = reinterpret_cast<const unsigned long long*>(&sh.sum)[lane];
     }
     mark(6);
-    // ---- PostProcessIMMUKF: UpdateModeProb (ukf.cpp:384-397), MergeEstimationAndCovariance (:419-437)
-    double mp[3] = {t.modeProb[0], t.modeProb[1], t.modeProb[2]};
-    const double sumG = lam[0] * mp[0] + lam[1] * mp[1] + lam[2] * mp[2];
-    for (int m = 0; m < 3; ++m) { mp[m] = (lam[m] * mp[m]) / sumG; }
-    for (int m = 0; m < 3; ++m) if (fabs(mp[m]) < 0.0001) mp[m] = 0.0001;
-    double xm[5];
-#pragma unroll
-    for (int e = 0; e < 5; ++e) xm[e] = mp[0] * xnew[0][e] + mp[1] * xnew[1][e] + mp[2] * xnew[2][e];
-    xm[3] = wrap_pi(xm[3]);
-    double myaw;
-    if (mp[0] > mp[1]) myaw = (mp[0] > mp[2]) ? xnew[0][3] : xnew[2][3];
-    else               myaw = (mp[1] > mp[2]) ? xnew[1][3] : xnew[2][3];
-    xm[3] = myaw;
-    __syncwarp();
-    if (lane < 25) {
-      const int r = lane / 5, c = lane % 5;
-      const double a0 = mp[0] * (Pnew[0] + (xnew[0][r] - xm[r]) * (xnew[0][c] - xm[c]));
-      const double a1 = mp[1] * (Pnew[1] + (xnew[1][r] - xm[r]) * (xnew[1][c] - xm[c]));
-      const double a2 = mp[2] * (Pnew[2] + (xnew[2][r] - xm[r]) * (xnew[2][c] - xm[c]));
-      t.P[0][lane] = a0 + a1 + a2;
-      t.P[1][lane] = Pnew[0]; t.P[2][lane] = Pnew[1]; t.P[3][lane] = Pnew[2];
-    }
-    if (lane < 5) { t.x[0][lane] = xm[lane]; t.x[1][lane] = xnew[0][lane]; t.x[2][lane] = xnew[1][lane]; t.x[3][lane] = xnew[2][lane]; }
-    if (lane == 0) {
-      t.modeProb[0] = mp[0]; t.modeProb[1] = mp[1]; t.modeProb[2] = mp[2];
-      t.x_merge_yaw = myaw;
-      int nv = t.nVelo;                                 // velo_history_ :955-959
-      if (nv == 3) { t.velo[0] = t.velo[1]; t.velo[1] = t.velo[2]; nv = 2; }
-      t.velo[nv] = xm[2];
-      t.nVelo = nv + 1;
-    }
-    } while (false);
-    __syncwarp();
-    mark(7);
-    if (!skipped) {
-      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_trk[warp]);
-      unsigned long long* dst = reinterpret_cast<unsigned long long*>(&tracks[it]);
-      for (int w = lane; w < kTrackWords; w += 32) dst[w] = src[w];
-    }
-    if (lane == 0) {
-      ActSummary& a = s_sum[warp];
-      a.x = t.x[0][0]; a.y = t.x[0][1]; a.yaw = t.x[0][3]; a.v = t.x[0][2];
-      a.initx = t.initMeas[0]; a.inity = t.initMeas[1];
-      a.mp0 = t.modeProb[0]; a.mp1 = t.modeProb[1]; a.mp2 = t.modeProb[2];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) a.bb[e] = t.BBox[e >> 1][e & 1];
-      a.k = it; a.trackNum = t.trackNum; a.lifetime = t.lifetime;
-      a.isStatic = t.isStatic; a.isVis = t.isVisBB; a.pad[0] = a.pad[1] = 0; a.pad2[0] = a.pad2[1] = 0;
-    }
-    __syncwarp();
-    if (lane < 16) reinterpret_cast<unsigned long long*>(&summary[q])[lane] = reinterpret_cast<const unsigned long long*>(&s_sum[warp])[lane];
-    __syncwarp();
-    mark(8);
   }
 }
 
@@ -1269,9 +1314,15 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
                     int* __restrict__ first_setter, int* __restrict__ imax_arr, int* __restrict__ vis_list,
                     uint8_t* __restrict__ has5_arr, int first_frame, int compat_first, double ego_yaw, int max_tracks, OutPtrs o,
                     OutPtrs prev, int full, int* __restrict__ act_list, double4* __restrict__ pos, const ActSummary* __restrict__ summary,
-                    unsigned long long* __restrict__ trace, unsigned long long* __restrict__ phase) {
+                    unsigned long long* __restrict__ trace, unsigned long long* __restrict__ phase, int* __restrict__ det_sem,
+                    unsigned* __restrict__ tc_seq) {
+  pdl_launch_dependents();                 // the next frame's gate kernel may become resident
   pdl_wait();                              // TB has finished
+  // every exit: this step's results are complete -> count it (release); publish_kernel, on its own stream, polls the count
+  // instead of waiting for a stream event, so that nothing but kernels sits on the tracker stream
+  struct Done { unsigned* p; __device__ ~Done() { __syncthreads(); if (threadIdx.x == 0) { __threadfence(); atomicAdd(p, 1u); } } } done_at_exit{tc_seq};
   trace_start(trace, 2);
+  if (det_sem && threadIdx.x == 0) atomicSub(det_sem, 1);     // this frame's detection results are being consumed (posted by box_fit_kernel)
   if (!full && !(first_frame && compat_first) && trk[CNT_N_ACT] <= kTCThreads) {
     __shared__ TCFastShared s_fast;
     const int M = det[CNT_N_BOXES];
@@ -1510,18 +1561,27 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, size_t bytes,
   for (size_t e = tid; e < n16; e += nthreads) d[e] = s[e];
 }
 
-__global__ void __launch_bounds__(1024)
-publish_kernel(OutPtrs d, OutPtrs h) {
+constexpr int kPubThreads = 128;    // small on purpose: it may sit on an SM polling while detection kernels need that SM's registers
+__global__ void __launch_bounds__(kPubThreads)
+publish_kernel(OutPtrs d, OutPtrs h, const unsigned* __restrict__ tc_seq, unsigned want) {
   const int tid = threadIdx.x;
+  if (tid == 0) {              // wait until `want` tracker steps have completed (spawn_output_kernel counts them)
+    unsigned spin = 0, v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(tc_seq) : "memory");
+      if (++spin > (1u << 23)) __trap();
+    } while ((int)(v - want) < 0);
+  }
+  __syncthreads();
   const int T = d.hdr[HDR_N_TRACKS], V = d.hdr[HDR_N_VIS], M = d.hdr[HDR_N_BOXES];
-  copy16(h.boxes, d.boxes, (size_t)M * 96, tid, 1024);
-  copy16(h.targets, d.targets, (size_t)T * 12, tid, 1024);
-  copy16(h.vandyaw, d.vandyaw, (size_t)T * 16, tid, 1024);
-  copy16(h.track_manage, d.track_manage, (size_t)T * 4, tid, 1024);
-  copy16(h.is_static, d.is_static, (size_t)T, tid, 1024);
-  copy16(h.is_vis, d.is_vis, (size_t)T, tid, 1024);
-  copy16(h.vis_bb, d.vis_bb, (size_t)V * 96, tid, 1024);
-  copy16(h.hdr, d.hdr, HDR_COUNT * sizeof(int), tid, 1024);
+  copy16(h.boxes, d.boxes, (size_t)M * 96, tid, kPubThreads);
+  copy16(h.targets, d.targets, (size_t)T * 12, tid, kPubThreads);
+  copy16(h.vandyaw, d.vandyaw, (size_t)T * 16, tid, kPubThreads);
+  copy16(h.track_manage, d.track_manage, (size_t)T * 4, tid, kPubThreads);
+  copy16(h.is_static, d.is_static, (size_t)T, tid, kPubThreads);
+  copy16(h.is_vis, d.is_vis, (size_t)T, tid, kPubThreads);
+  copy16(h.vis_bb, d.vis_bb, (size_t)V * 96, tid, kPubThreads);
+  copy16(h.hdr, d.hdr, HDR_COUNT * sizeof(int), tid, kPubThreads);
 }
 
 // detection-only submissions: the box list of the slot -> the result's host block
@@ -1561,19 +1621,22 @@ int tracker_alloc(Ctx* c) {
   LMOT_CUDA(c, cudaMalloc(&c->d_act_list, (size_t)TC * sizeof(int)));
   LMOT_CUDA(c, cudaMalloc(&c->d_pos, (size_t)TC * sizeof(double4)));
   LMOT_CUDA(c, cudaMalloc(&c->d_summary, (size_t)TC * sizeof(ActSummary)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_tc_seq, sizeof(unsigned)));
+  LMOT_CUDA(c, cudaMemsetAsync(c->d_tc_seq, 0, sizeof(unsigned), c->trk_stream));
+  c->tc_launched = 0;
   LMOT_CUDA(c, cudaMemsetAsync(c->d_pos, 0, (size_t)TC * sizeof(double4), c->trk_stream));
   c->last_trk_res = nullptr;
   c->act_valid = false;
   fill_int_kernel<<<(MB + 255) / 256, 256, 0, c->trk_stream>>>(c->d_first_setter, MB, INT_MAX);
   LMOT_CUDA(c, cudaGetLastError());
-  const size_t sh = (size_t)kTBWarps * c->gate_words * 32 * sizeof(unsigned short);
+  const size_t sh = (size_t)c->gate_words * 32 * sizeof(unsigned short);
   LMOT_CUDA(c, cudaFuncSetAttribute(imm_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
   return LMOT_OK;
 }
 
 void tracker_free(Ctx* c) {
   cudaFree(c->d_tracks); cudaFree(c->d_trk_counters); cudaFree(c->d_gate); cudaFree(c->d_setter); cudaFree(c->d_first_setter);
-  cudaFree(c->d_skip); cudaFree(c->d_new_num); cudaFree(c->d_live_list); cudaFree(c->d_vis_list); cudaFree(c->d_act_list); cudaFree(c->d_pos); cudaFree(c->d_summary);
+  cudaFree(c->d_skip); cudaFree(c->d_new_num); cudaFree(c->d_live_list); cudaFree(c->d_vis_list); cudaFree(c->d_act_list); cudaFree(c->d_pos); cudaFree(c->d_summary); cudaFree(c->d_tc_seq);
   if (c->h_trk_counters) cudaFreeHost(c->h_trk_counters);
 }
 
@@ -1606,7 +1669,7 @@ void origin_points_fold(TrackerHost& h, double timestamp, double v_gps, double y
 
 // boxes: device float[M][8][3] with M in det_counters[CNT_N_BOXES]; results into the DEVICE block of sl->res
 int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, const int* det_counters, double timestamp, double v_gps,
-                   double yaw_gps) {
+                   double yaw_gps, bool gate, bool* gated) {
   origin_points_fold(c->th, timestamp, v_gps, yaw_gps);
   TrackerHost& h = c->th;
   Result* r = sl->res;
@@ -1616,10 +1679,19 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
   const int compat = c->prm.oracle_compat_first_frame ? 1 : 0;
   unsigned long long* trace = nullptr;     // diagnostic: [32 frames][8] first start / last end of TA, TB, TC
   if (c->d_trk_trace) {
-    trace = c->d_trk_trace + (size_t)(c->trk_frames % 32) * 8;
-    LMOT_CUDA(c, cudaMemsetAsync(trace, 0, 64, st));
+    // rows are zeroed kTraceRows frames at a time: a memset in front of every step would sit between two programmatically
+    // dependent launches of the chain and serialise them
+    if (c->trk_frames % kTraceRows == 0) LMOT_CUDA(c, cudaMemsetAsync(c->d_trk_trace, 0, (size_t)kTraceRows * 8 * sizeof(unsigned long long), st));
+    trace = c->d_trk_trace + (size_t)(c->trk_frames % kTraceRows) * 8;
   }
+  unsigned long long* phase = c->d_trk_trace ? c->d_trk_trace + (size_t)kTraceRows * 8 : nullptr;
   ++c->trk_frames;
+  // `gate` (frame submissions): the detection stages of this frame post sl->d_det_sem.  Either the gate kernel waits for it on
+  // the device (see tracker_gate_kernel), or -- timing mode, the reference's first-frame quirk -- the stream waits for the event.
+  const bool use_gate = gate && !c->timing && !(first && compat);
+  if (gate && !use_gate) LMOT_CUDA(c, cudaStreamWaitEvent(st, sl->ev_det_done, 0));
+  int* det_sem = gate ? sl->d_det_sem : nullptr;
+  if (gated) *gated = use_gate;
   const int full = c->act_valid ? 0 : 1;   // the table was written from the host since the last frame: rebuild the side arrays
   if (full) {
     LMOT_CUDA(c, cudaMemsetAsync(c->d_trk_counters + CNT_N_ACT, 0, sizeof(int), st));
@@ -1631,9 +1703,21 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
   c->last_trk_res = r;
   if (!(first && compat)) {
     const double dt = first ? 0.0 : (timestamp - h.timestamp) / 1000000.0;     // :807
-    const size_t sh = (size_t)kTBWarps * c->gate_words * 32 * sizeof(unsigned short);
-    imm_predict_gate_kernel<<<c->trk_ctas, kTAThreads, 0, st>>>(c->d_tracks, c->d_trk_counters, det, d_boxes, dt, c->d_gate, c->d_setter,
-                                                                 c->d_first_setter, c->d_skip, c->gate_words, c->d_act_list, trace);
+    const size_t sh = (size_t)c->gate_words * 32 * sizeof(unsigned short);
+    {
+      cudaLaunchAttribute pa;
+      pa.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      pa.val.programmaticStreamSerializationAllowed = use_gate ? 1 : 0;
+      if (use_gate) {
+        cudaLaunchConfig_t gc = {};
+        gc.gridDim = dim3(1); gc.blockDim = dim3(32); gc.dynamicSmemBytes = 0; gc.stream = st; gc.attrs = &pa; gc.numAttrs = 1;
+        LMOT_CUDA(c, cudaLaunchKernelEx(&gc, tracker_gate_kernel, (const int*)det_sem, phase));
+      }
+      cudaLaunchConfig_t ac = {};
+      ac.gridDim = dim3(c->trk_ctas); ac.blockDim = dim3(kTAThreads); ac.dynamicSmemBytes = 0; ac.stream = st; ac.attrs = &pa; ac.numAttrs = 1;
+      LMOT_CUDA(c, cudaLaunchKernelEx(&ac, imm_predict_gate_kernel, c->d_tracks, (const int*)c->d_trk_counters, (const int*)det, d_boxes, dt,
+                                      c->d_gate, c->d_setter, c->d_first_setter, c->d_skip, c->gate_words, (const int*)c->d_act_list, trace, phase));
+    }
     kernel_mark(c, sl, st);
     // TB and TC: programmatic dependent launches (their CTAs wait on the device for the preceding grid, see pdl_wait); timing
     // mode records an event between the kernels, which needs the ordinary full serialisation
@@ -1641,12 +1725,11 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
     pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     pdl.val.programmaticStreamSerializationAllowed = c->timing ? 0 : 1;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(c->trk_ctas / kTBWarps + 1); cfg.blockDim = dim3(kTBWarps * 32); cfg.dynamicSmemBytes = sh; cfg.stream = st;
+    cfg.gridDim = dim3(c->trk_ctas); cfg.blockDim = dim3(kTBThreads); cfg.dynamicSmemBytes = sh; cfg.stream = st;
     cfg.attrs = &pdl; cfg.numAttrs = 1;
     LMOT_CUDA(c, cudaLaunchKernelEx(&cfg, imm_update_kernel, c->d_tracks, (const int*)c->d_trk_counters, (const int*)det, d_boxes,
                                     (const unsigned*)c->d_gate, (const int*)c->d_first_setter, (const uint8_t*)c->d_skip, c->gate_words,
-                                    (const int*)c->d_act_list, reinterpret_cast<ActSummary*>(c->d_summary), trace,
-                                    c->d_trk_trace ? c->d_trk_trace + 256 : (unsigned long long*)nullptr));
+                                    (const int*)c->d_act_list, reinterpret_cast<ActSummary*>(c->d_summary), trace, phase));
     kernel_mark(c, sl, st);
   }
   {
@@ -1658,8 +1741,8 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
     cfg.attrs = &pdl; cfg.numAttrs = 1;
     LMOT_CUDA(c, cudaLaunchKernelEx(&cfg, spawn_output_kernel, c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_first_setter, c->d_new_num,
                                     c->d_vis_list, c->d_skip, first, compat, h.egoPoint[2], c->prm.max_tracks, o, po, full, c->d_act_list,
-                                    c->d_pos, reinterpret_cast<const ActSummary*>(c->d_summary), trace,
-                                    c->d_trk_trace ? c->d_trk_trace + 256 : (unsigned long long*)nullptr));
+                                    c->d_pos, reinterpret_cast<const ActSummary*>(c->d_summary), trace, phase, det_sem, c->d_tc_seq));
+    ++c->tc_launched;
   }
   kernel_mark(c, sl, st);
   LMOT_CUDA(c, cudaGetLastError());
@@ -1673,7 +1756,7 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
 int tracker_publish(Ctx* c, Result* r, cudaStream_t st) {
   OutPtrs d{r->d_targets, r->d_vandyaw, r->d_manage, r->d_static, r->d_vis, r->d_visbb, r->d_hdr, r->d_boxes};
   OutPtrs h{r->h_targets, r->h_vandyaw, r->h_manage, r->h_static, r->h_vis, r->h_visbb, r->h_hdr, r->h_boxes};
-  publish_kernel<<<1, 1024, 0, st>>>(d, h);
+  publish_kernel<<<1, kPubThreads, 0, st>>>(d, h, c->d_tc_seq, c->tc_launched);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }

@@ -51,7 +51,10 @@ for depth in [int(x) for x in os.environ.get("DIAG_DEPTHS", "1,4").split(",")]:
     tt = ctx.debug_tracker_trace().astype(np.int64)[-12:]
     ph = ctx.last_tc_phases.astype(np.int64); ph = ph[ph > 0]
     pb = ctx.last_tb_phases.astype(np.int64); pb = pb[pb > 0]
-    if len(pb) > 1: print("  TB phases of track 0 (us after its start: staged, gate list, association, update_bb, PDA, lambda, merge+end, written back):", " ".join(f"{(x - pb[0]) / 1e3:.2f}" for x in pb[1:]))
+    gp = ctx.last_gate_phases.astype(np.int64)
+    full = ctx.debug_tracker_trace().astype(np.int64)
+    if gp[0] > 0: print(f"  last step: gate entry {(gp[0] - full[-2, 5]) / 1e3:.2f} us after the PREVIOUS step's TC end, gate released {(gp[1] - full[-2, 5]) / 1e3:.2f}, TA CTA 0 entry {(gp[2] - full[-2, 5]) / 1e3:.2f}, TA start {(full[-1, 0] - full[-2, 5]) / 1e3:.2f}; previous TC start {(full[-2, 4] - full[-2, 5]) / 1e3:.2f}, previous TB start {(full[-2, 2] - full[-2, 5]) / 1e3:.2f}")
+    if len(pb) > 1: print("  TB phases of CTA 0 (us after its start: staged, gate list, model warps + box warp done, lambda, merged, written back):", " ".join(f"{(x - pb[0]) / 1e3:.2f}" for x in pb[1:]))
     if len(ph) > 1: print("  TC phases (us after its start: loads issued, summaries in, boxes staged, pass A, exact tests, pass B, emit, act list, spawn, end):", " ".join(f"{(x - ph[0]) / 1e3:.2f}" for x in ph[1:]))
     ta, tb, tc = (tt[:, 1] - tt[:, 0]) / 1e3, (tt[:, 3] - tt[:, 2]) / 1e3, (tt[:, 5] - tt[:, 4]) / 1e3
     g1, g2, g3 = (tt[:, 2] - tt[:, 1]) / 1e3, (tt[:, 4] - tt[:, 3]) / 1e3, (tt[1:, 0] - tt[:-1, 5]) / 1e3
