@@ -75,7 +75,7 @@ class FrameOut(C.Structure):
 # every symbol include/lmot.h declares (tests assert the library exports all of them)
 ABI_SYMBOLS = [
     "lmot_default_params", "lmot_create", "lmot_destroy", "lmot_strerror", "lmot_last_error", "lmot_build_info",
-    "lmot_set_stream", "lmot_ground_remove", "lmot_component_cluster", "lmot_cluster_outputs", "lmot_box_fit", "lmot_track_step", "lmot_frame",
+    "lmot_set_stream", "lmot_pinned_alloc", "lmot_pinned_free", "lmot_ground_remove", "lmot_component_cluster", "lmot_cluster_outputs", "lmot_box_fit", "lmot_track_step", "lmot_frame",
     "lmot_frame_dev", "lmot_frame_fetch", "lmot_frame_submit", "lmot_frame_collect", "lmot_frames_in_flight", "lmot_frame_ready", "lmot_flush",
     "lmot_ground_remove_dev", "lmot_detect_dev", "lmot_sync",
     "lmot_origin_points", "lmot_tracker_table", "lmot_tracker_set_num_tracks", "lmot_tracker_reset", "lmot_tracker_num_tracks", "lmot_tracker_dump", "lmot_tracker_load",
@@ -366,12 +366,13 @@ class Lmot:
 
     def debug_tracker_trace(self):
         """(32, 8) uint64 ns, oldest step first: TA start, TA end, TB start, TB end, TC start, TC end, latest start of a working TA CTA, same for TB."""
-        raw = np.zeros(32 * 8 + 32, np.uint64); nxt = C.c_int(0)
+        raw = np.zeros(32 * 8 + 64, np.uint64); nxt = C.c_int(0)
         self._chk(self.lib.lmot_debug_tracker_trace(self.h, raw.ctypes.data_as(C.POINTER(C.c_ulonglong)), C.byref(nxt)))
         buf = raw[:256].reshape(32, 8).copy()
         self.last_tc_phases = raw[256:272].copy()
         self.last_tb_phases = raw[272:282].copy()
-        self.last_gate_phases = raw[282:].copy()     # [0] gate kernel entry, [1] gate kernel after its wait, [2] TA CTA 0 entry (before its wait)        # same for the first track's warp of imm_update_kernel       # %globaltimer stamps inside the last spawn_output_kernel (fast path)
+        self.last_ta_phases = raw[288:304].copy()    # CTA 0 of imm_predict_gate_kernel
+        self.last_gate_phases = raw[282:288].copy()     # [0] gate kernel entry, [1] gate kernel after its wait, [2] TA CTA 0 entry (before its wait)        # same for the first track's warp of imm_update_kernel       # %globaltimer stamps inside the last spawn_output_kernel (fast path)
         for k in (0, 2, 4):
             buf[:, k] = ~buf[:, k]        # starts are stored complemented (see trace_start in tracker.cu)
         return np.roll(buf, -nxt.value, axis=0)

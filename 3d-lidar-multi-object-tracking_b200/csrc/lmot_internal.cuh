@@ -194,6 +194,8 @@ struct Ctx {
   cudaStream_t pub_stream = nullptr;   // device -> host publication of finished frames
   int* d_act_list = nullptr;           // [max_tracks] tracks to visit next frame (built by spawn_output_kernel)
   double4* d_pos = nullptr;            // [max_tracks] packed (x, y, yaw, -) of every track's merged state
+  int* d_meas_n = nullptr;             // [max_tracks] TA -> TB: number of gated boxes of the track (-1: not provided)
+  void* d_meas_ctr = nullptr;          // [max_tracks][32] double2: centre points of the first 32 gated boxes, box order
   unsigned* d_tc_seq = nullptr;        // tracker steps completed (counted by spawn_output_kernel, polled by publish_kernel)
   unsigned tc_launched = 0;            // host: tracker steps launched
   void* d_summary = nullptr;           // [max_tracks] ActSummary (tracker.cu): what TC needs of each active track, written by TB

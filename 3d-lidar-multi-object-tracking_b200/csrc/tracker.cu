@@ -199,6 +199,7 @@ struct TAShared {
   double detS[3];        // per model: det(S), computed by the model's own warp
   int flag;              // 0 run, 1 skip (dead track)
   int explode;           // det(P_merge) > 10 or P_merge(4,4) > 1000 (:828-831), computed by warp 3 while warps 0-2 predict
+  unsigned gbits[8];     // gate bits of the (at most 8) 32-box chunks, for the compact measurement list handed to TB
 };
 
 __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(kTAThreads, 4)     // <= 128 registers: a CTA 
 imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, const int* __restrict__ det, const float* __restrict__ boxes,
                         double dt, unsigned* __restrict__ gate, unsigned* __restrict__ setter, int* __restrict__ first_setter,
                         uint8_t* __restrict__ skip, int words, const int* __restrict__ act_list, unsigned long long* trace,
-                        unsigned long long* __restrict__ phase) {
+                        unsigned long long* __restrict__ phase, int* __restrict__ meas_n, double2* __restrict__ meas_ctr) {
   __shared__ TAShared sh;
   if (phase && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); phase[28] = t; }
   pdl_wait();                              // (gated launch: the gate kernel, hence the previous tracker step and this frame's detection, is complete)
@@ -218,6 +219,9 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
   const int n_act = trk[CNT_N_ACT];
   const int M = det[CNT_N_BOXES];
   if (trace && tid == 0 && (int)blockIdx.x < n_act) { unsigned long long tn; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn)); atomicMax(&trace[6], tn); }   // latest start of a CTA that has a track
+  // diagnostic: %globaltimer stamps of CTA 0 (thread 0 = lane 0 of the CV model's warp)
+  auto mark = [&](int i) { if (phase && blockIdx.x == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); phase[32 + i] = t; } };
+  mark(0);
   const double kStdA = (model == 2) ? 3.0 : 2.0;       // std_a_{cv,ctrv,rm}_ ukf.cpp:68-70 (= std_*_yawdd_ :71-73)
   const double lambda_aug = 3 - 7;
   const double w0 = lambda_aug / (lambda_aug + 7), wi = 0.5 / (7 + lambda_aug);
@@ -240,6 +244,7 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
     for (int e = tid; e < 75; e += kTAThreads) sh.Pp[e / 25][e % 25] = t.P[1 + e / 25][e % 25];
     const double mp0 = t.modeProb[0], mp1 = t.modeProb[1], mp2 = t.modeProb[2];
     __syncthreads();
+    mark(1);
     if (sh.flag) continue;
     // guard :828-831 on the side: the serial 5x5 LU no longer sits in front of the prediction
     if (tid == 96) sh.explode = (det_lu<5>(t.P[0]) > 10 || t.P[0][24] > 1000) ? 1 : 0;
@@ -265,6 +270,7 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
       sh.Pm[model][lane] = t0 + t1 + t2;
     }
     __syncwarp();
+    mark(2);
     // ---- Prediction (:630-772): P_aug.llt() with Eigen's early exit on a non-positive pivot (LLT.h:271-295)
     if (lane == 0) {
       // 5x5 block in registers, fully unrolled (packed lower triangle); the two augmentation rows are diagonal
@@ -309,6 +315,7 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
       L[6 * 7 + 6] = stop ? s2 : sqrt(s2);
     }
     __syncwarp();
+    mark(3);
     if (lane < 15) {      // one sigma point per lane (:682-735)
       const double sq = sqrt(lambda_aug + 7);
       double a[7];
@@ -352,6 +359,7 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
       o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3; o[4] = s4;
     }
     __syncwarp();
+    mark(4);
     // predicted mean (:737-744), every lane sums in sigma-point order
 #pragma unroll
     for (int e = 0; e < 5; ++e) {
@@ -376,6 +384,7 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
         Pe = Pe + (((i == 0) ? w0 : wi) * dr) * dc;
       }
     }
+    mark(5);
     // ---- UpdateLidar (:778-902)
 #pragma unroll
     for (int i = 0; i < 15; ++i) { const double w = (i == 0) ? w0 : wi; zp0 = zp0 + w * sh.Xs[model][i][0]; zp1 = zp1 + w * sh.Xs[model][i][1]; }
@@ -404,6 +413,7 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
     inv2_lu(sh.S[model], Si);
     if (lane == 0) sh.detS[model] = det2(sh.S[model]);     // for findMaxZandS below: each warp its own model, not every warp all three
     }   // model < 3
+    mark(6);
     __syncthreads();                      // the guard's verdict is in
     if (sh.explode) {
       if (tid == 0) { t.trackNum = 0; skip[it] = 1; }
@@ -437,17 +447,17 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
       if (tid == 0) { t.trackNum = 0; skip[it] = 1; }
       continue;
     }
+    mark(7);
     const double z0 = sh.zp[mm][0], z1 = sh.zp[mm][1];
     inv2_lu(S4, Si);
     const bool secondInit = (trackNum == 1);
     // ---- measurementValidation (:205-257): gate bits for every box; warps take 32-box chunks round-robin
     const int nchunk = (M + 31) >> 5;
     if (!secondInit) {
-      for (int ch = model; ch < nchunk; ch += 4) {
+      auto gate_chunk = [&](int ch, double& cx, double& cy, bool& g) -> unsigned {
         const int b = ch * 32 + lane;
-        bool g = false;
+        g = false; cx = 0; cy = 0;
         if (b < M) {
-          double cx, cy;
           cp_from_box(boxes + (size_t)b * 24, cx, cy);
           const double d0 = cx - z0, d1 = cy - z1;
           const double nis = (d0 * Si[0] + d1 * Si[2]) * d0 + (d0 * Si[1] + d1 * Si[3]) * d1;
@@ -456,9 +466,43 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
         const unsigned bits = __ballot_sync(0xFFFFFFFFu, g);
         if (lane == 0) { gate[(size_t)it * words + ch] = bits; setter[(size_t)it * words + ch] = bits; }
         if (g) atomicMin(&first_setter[b], it);
+        return bits;
+      };
+      // Up to 256 boxes (8 chunks, two per warp) the centre points of the gated boxes are also handed to TB as a compact list
+      // in box order (meas_ctr[it][0..31], count in meas_n[it]): TB's model warps then start their update straight away instead
+      // of re-deriving the list from the gate words (two dependent L2 round trips) and gathering the boxes (a third)
+      const bool compact = nchunk <= 8;
+      double ccx[2] = {0, 0}, ccy[2] = {0, 0};
+      unsigned cb[2] = {0, 0};
+      bool cg[2] = {false, false};
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int ch = model + 4 * ci;
+        if (ch < nchunk) {
+          cb[ci] = gate_chunk(ch, ccx[ci], ccy[ci], cg[ci]);
+          if (compact && lane == 0) sh.gbits[ch] = cb[ci];
+        }
       }
+      for (int ch = model + 8; ch < nchunk; ch += 4) { double cx, cy; bool g; gate_chunk(ch, cx, cy, g); }
+      if (compact) {
+        __syncthreads();                  // (uniform: every thread of the CTA is in this branch)
+        int total = 0;
+        for (int c2 = 0; c2 < nchunk; ++c2) total += __popc(sh.gbits[c2]);
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int ch = model + 4 * ci;
+          if (ch < nchunk && cg[ci]) {
+            int off = __popc(cb[ci] & ((1u << lane) - 1u));
+            for (int c2 = 0; c2 < ch; ++c2) off += __popc(sh.gbits[c2]);
+            if (off < 32) meas_ctr[(size_t)it * 32 + off] = make_double2(ccx[ci], ccy[ci]);
+          }
+        }
+        if (tid == 0) meas_n[it] = total;
+      } else if (tid == 0) meas_n[it] = -1;
+      mark(8);
     } else if (model == 0) {
       // secondInit (:238-246): every running minimum of the NIS marks its box; chunks in order with a carried minimum
+      if (lane == 0) meas_n[it] = -1;
       double run = 999;
       for (int ch = 0; ch < nchunk; ++ch) {
         const int b = ch * 32 + lane;
@@ -602,7 +646,7 @@ __global__ void __launch_bounds__(kTBThreads)
 imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, const int* __restrict__ det, const float* __restrict__ boxes,
                   const unsigned* __restrict__ gate, const int* __restrict__ first_setter, const uint8_t* __restrict__ skip,
                   int words, const int* __restrict__ act_list, ActSummary* __restrict__ summary, unsigned long long* trace,
-                  unsigned long long* __restrict__ phase) {
+                  unsigned long long* __restrict__ phase, const int* __restrict__ meas_n, const double2* __restrict__ meas_ctr) {
   extern __shared__ unsigned short s_list[];              // indices of the gated boxes, in box order
   __shared__ TBShared sh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -622,6 +666,10 @@ imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, 
   for (int q = blockIdx.x; q < n_act; q += gridDim.x) {
     const int it = act_list[q];
     const bool skipped = skip[it] != 0;      // dead, or killed by TA's guards: no update, but TC still wants its summary
+    // TA's compact measurement list (count, centre points of the first 32 gated boxes in box order): in flight together with
+    // the staging loads below.  -1 / more than 32: derive the list from the gate words as before
+    const int nm_ta = skipped ? -1 : meas_n[it];
+    const double2 ctr_ta = skipped ? make_double2(0.0, 0.0) : meas_ctr[(size_t)it * 32 + lane];
     __syncthreads();                         // the previous track's readers are done with the shared copy
     // stage the whole track (1.6 KB) in shared memory with coalesced 8-byte loads: the update below touches almost
     // every field several times, and every one of those touches would otherwise be its own trip to L2 / HBM
@@ -646,6 +694,9 @@ imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, 
       // ---- lifetime_ (:232): a gated box counts unless an earlier track already matched it.  Every warp derives the list for
       // itself (same loads, same values: no CTA barrier in front of the model warps)
       int life = 0;
+      const bool quick = warp < 3 && !secondInit && nm_ta >= 0 && nm_ta <= 32;   // model warps: everything they need came from TA
+      if (quick) nmeas = nm_ta;
+      else
       for (int ch0 = 0; ch0 < nchunk; ch0 += 4) {      // four chunks per batch: two round trips (gate words, then first_setter), not two per chunk
         unsigned g4[4]; int fs4[4];
 #pragma unroll
@@ -754,7 +805,8 @@ imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, 
           const double bb = 2 * numMeas * (1 - pD * pG) / (gammaG * pD);
           // centre point of every gated box once (lane k <-> measurement k; beyond 32 measurements recomputed on the fly)
           double mcx = 0, mcy = 0;
-          if (lane < nmeas) cp_from_box(boxes + (size_t)s_list[lane] * 24, mcx, mcy);
+          if (quick) { if (lane < nmeas) { mcx = ctr_ta.x; mcy = ctr_ta.y; } }
+          else if (lane < nmeas) cp_from_box(boxes + (size_t)s_list[lane] * 24, mcx, mcy);
           double Si[4];
           inv2_lu(t.S[m], Si);
           const double zp0 = t.zPred[m][0], zp1 = t.zPred[m][1];
@@ -1074,6 +1126,14 @@ struct TCFastShared {
   unsigned cand[kCandCap];            // (visible slot << 16) | thread of the track
 };
 
+// a (visible box, track) pair passed the single-precision bounds pre-test: queue it for the exact test (one pair per thread
+// later), or -- queue full -- test it here.  Not inlined: the callers' loops stay small, this is the rare path.
+__device__ __noinline__ void tc_candidate(TCFastShared& S, int v, int jt) {
+  const int slot = atomicAdd(&S.ncand, 1);
+  if (slot < kCandCap) S.cand[slot] = ((unsigned)v << 16) | (unsigned)jt;
+  else if (overseg_cond(S.bx[v], reinterpret_cast<const float*>(&S.ab[v]), S.px[jt], S.py[jt])) atomicMax(&S.imax[jt], S.vid[v]);
+}
+
 __device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict__ tracks, int* __restrict__ trk, int* __restrict__ det,
                                         const float* __restrict__ boxes, int* __restrict__ first_setter, double ego_yaw, int max_tracks,
                                         const OutPtrs& o, const OutPtrs& prev, int* __restrict__ act_list, double4* __restrict__ pos,
@@ -1184,22 +1244,28 @@ __device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict_
 
   mark(2);
   // ---- mergeOverSegmentation, pass A: imax = largest visible box index containing this (live) track
-  // (track x box) pairs spread over the whole CTA: a warp takes every 8th box (broadcast loads), its lanes the tracks
+  // (track x box) pairs spread over the whole CTA: a warp takes every 8th box (broadcast loads); its lanes hold the tracks
+  // jt = lane, lane + 32, ... in REGISTERS for the whole loop, so an iteration is two independent shared-memory loads and
+  // compares (the previous form, one dependent load chain per pair, took 2.9 us for ~90 boxes x ~100 tracks)
   {
     const int warp = tid >> 5;
-    const float4* __restrict__ abp = S.ab;
-    const float4* __restrict__ t4p = S.t4;
-    const int* __restrict__ vidp = S.vid;
+    constexpr int kPerLane = kTCThreads / 32;
+    float4 tj[kPerLane];
+#pragma unroll
+    for (int u = 0; u < kPerLane; ++u) {
+      const int jt = lane + 32 * u;
+      tj[u] = (jt < n_act0) ? S.t4[jt] : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    }
+    const int nu = (n_act0 + 31) >> 5;                   // lanes-worth of tracks actually present (uniform)
     for (int v = warp; v < nv; v += kTCThreads / 32) {
-      const float4 ab = abp[v];
-      const int vid = vidp[v];
-      for (int jt = lane; jt < n_act0; jt += 32) {
-        const float4 tj = t4p[jt];
-        const int kj = __float_as_int(tj.w);
-        if (kj >= 0 && kj != vid && !(tj.x < ab.x - tj.z || tj.x > ab.y + tj.z || tj.y < ab.z - tj.z || tj.y > ab.w + tj.z)) {
-          const int slot = atomicAdd(&S.ncand, 1);
-          if (slot < kCandCap) S.cand[slot] = ((unsigned)v << 16) | (unsigned)jt;
-          else if (overseg_cond(S.bx[v], reinterpret_cast<const float*>(&S.ab[v]), S.px[jt], S.py[jt])) atomicMax(&S.imax[jt], vid);
+      const float4 ab = S.ab[v];
+      const int vid = S.vid[v];
+#pragma unroll
+      for (int u = 0; u < kPerLane; ++u) {
+        if (u < nu) {
+          const int kj = __float_as_int(tj[u].w);
+          if (kj >= 0 && kj != vid && !(tj[u].x < ab.x - tj[u].z || tj[u].x > ab.y + tj[u].z || tj[u].y < ab.z - tj[u].z || tj[u].y > ab.w + tj[u].z))
+            tc_candidate(S, v, lane + 32 * u);
         }
       }
     }
@@ -1309,7 +1375,7 @@ __device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict_
 //     of every track is its state's yaw plus THIS frame's ego yaw: `pos`, a packed (x, y, yaw) per track, refreshed for the
 //     active tracks only.
 // `full` (first step after the table was written from the host): everything is rebuilt from the records.
-__global__ void __launch_bounds__(kTCThreads, 1)
+__global__ void __launch_bounds__(kTCThreads, 2)
 spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int* __restrict__ det, const float* __restrict__ boxes,
                     int* __restrict__ first_setter, int* __restrict__ imax_arr, int* __restrict__ vis_list,
                     uint8_t* __restrict__ has5_arr, int first_frame, int compat_first, double ego_yaw, int max_tracks, OutPtrs o,
@@ -1621,6 +1687,10 @@ int tracker_alloc(Ctx* c) {
   LMOT_CUDA(c, cudaMalloc(&c->d_act_list, (size_t)TC * sizeof(int)));
   LMOT_CUDA(c, cudaMalloc(&c->d_pos, (size_t)TC * sizeof(double4)));
   LMOT_CUDA(c, cudaMalloc(&c->d_summary, (size_t)TC * sizeof(ActSummary)));
+  LMOT_CUDA(c, cudaMalloc(&c->d_meas_n, (size_t)TC * sizeof(int)));
+  LMOT_CUDA(c, cudaMemsetAsync(c->d_meas_n, 0xFF, (size_t)TC * sizeof(int), c->trk_stream));
+  LMOT_CUDA(c, cudaMalloc(&c->d_meas_ctr, (size_t)TC * 32 * sizeof(double2)));
+  LMOT_CUDA(c, cudaMemsetAsync(c->d_meas_ctr, 0, (size_t)TC * 32 * sizeof(double2), c->trk_stream));
   LMOT_CUDA(c, cudaMalloc(&c->d_tc_seq, sizeof(unsigned)));
   LMOT_CUDA(c, cudaMemsetAsync(c->d_tc_seq, 0, sizeof(unsigned), c->trk_stream));
   c->tc_launched = 0;
@@ -1636,7 +1706,7 @@ int tracker_alloc(Ctx* c) {
 
 void tracker_free(Ctx* c) {
   cudaFree(c->d_tracks); cudaFree(c->d_trk_counters); cudaFree(c->d_gate); cudaFree(c->d_setter); cudaFree(c->d_first_setter);
-  cudaFree(c->d_skip); cudaFree(c->d_new_num); cudaFree(c->d_live_list); cudaFree(c->d_vis_list); cudaFree(c->d_act_list); cudaFree(c->d_pos); cudaFree(c->d_summary); cudaFree(c->d_tc_seq);
+  cudaFree(c->d_skip); cudaFree(c->d_new_num); cudaFree(c->d_live_list); cudaFree(c->d_vis_list); cudaFree(c->d_act_list); cudaFree(c->d_pos); cudaFree(c->d_summary); cudaFree(c->d_tc_seq); cudaFree(c->d_meas_n); cudaFree(c->d_meas_ctr);
   if (c->h_trk_counters) cudaFreeHost(c->h_trk_counters);
 }
 
@@ -1716,7 +1786,8 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
       cudaLaunchConfig_t ac = {};
       ac.gridDim = dim3(c->trk_ctas); ac.blockDim = dim3(kTAThreads); ac.dynamicSmemBytes = 0; ac.stream = st; ac.attrs = &pa; ac.numAttrs = 1;
       LMOT_CUDA(c, cudaLaunchKernelEx(&ac, imm_predict_gate_kernel, c->d_tracks, (const int*)c->d_trk_counters, (const int*)det, d_boxes, dt,
-                                      c->d_gate, c->d_setter, c->d_first_setter, c->d_skip, c->gate_words, (const int*)c->d_act_list, trace, phase));
+                                      c->d_gate, c->d_setter, c->d_first_setter, c->d_skip, c->gate_words, (const int*)c->d_act_list, trace, phase,
+                                      c->d_meas_n, reinterpret_cast<double2*>(c->d_meas_ctr)));
     }
     kernel_mark(c, sl, st);
     // TB and TC: programmatic dependent launches (their CTAs wait on the device for the preceding grid, see pdl_wait); timing
@@ -1729,7 +1800,8 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
     cfg.attrs = &pdl; cfg.numAttrs = 1;
     LMOT_CUDA(c, cudaLaunchKernelEx(&cfg, imm_update_kernel, c->d_tracks, (const int*)c->d_trk_counters, (const int*)det, d_boxes,
                                     (const unsigned*)c->d_gate, (const int*)c->d_first_setter, (const uint8_t*)c->d_skip, c->gate_words,
-                                    (const int*)c->d_act_list, reinterpret_cast<ActSummary*>(c->d_summary), trace, phase));
+                                    (const int*)c->d_act_list, reinterpret_cast<ActSummary*>(c->d_summary), trace, phase,
+                                    (const int*)c->d_meas_n, reinterpret_cast<const double2*>(c->d_meas_ctr)));
     kernel_mark(c, sl, st);
   }
   {

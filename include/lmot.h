@@ -27,6 +27,7 @@
 #ifndef LMOT_H
 #define LMOT_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -110,6 +111,11 @@ const char* lmot_build_info(void);
  * pipeline).  NULL restores the context's own stream -- the legacy default stream (handle 0) cannot be selected, create a
  * stream instead (CUDA events recorded on stream 0 are not ordered with the pipeline's non-blocking streams). */
 int lmot_set_stream(lmot_ctx* ctx, void* cuda_stream);
+
+/* Page-locked host memory for frames handed to lmot_frame / lmot_frame_submit (a pageable buffer makes the H2D copy
+ * synchronous and half as fast).  A ROS node allocates its PointCloud2 staging buffer with this; NULL without a CUDA device. */
+void* lmot_pinned_alloc(size_t bytes);
+void lmot_pinned_free(void* p);
 
 /* ---- stage entry points, HOST buffers (synchronous: H2D, kernels, D2H, stream sync) -------------------- */
 
@@ -233,7 +239,7 @@ int lmot_debug_label_grid(lmot_ctx* ctx, int32_t* grid, int* num_cluster);
 int lmot_debug_timeline(lmot_ctx* ctx, float* out, int cap_frames, int* n_frames, int* row_stride);
 
 /* diagnostic (after the phase clock was switched on): %globaltimer spans of the tracker kernels of the last 32 tracker steps,
- * out[32][8], followed by 32 phase stamps of the last imm_update / spawn_output launch: out must hold 288 words */
+ * out[32][8], followed by 64 phase stamps of the last launches of the chain's kernels: out must hold 320 words */
 int lmot_debug_tracker_trace(lmot_ctx* ctx, unsigned long long* out, int* next);
 
 /* diagnostic: first call switches on the phase clock of ground_fused_kernel; later calls return the %globaltimer stamps

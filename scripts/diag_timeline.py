@@ -39,12 +39,24 @@ for depth in [int(x) for x in os.environ.get("DIAG_DEPTHS", "1,4").split(",")]:
     ctx.enable_timing(False)
     # the same loop without timing events: frames/s as bench.py measures `value`
     ctx.tracker_reset()
-    for i in range(W): ctx.frame_dev(d[i].data_ptr(), n, ts[i])
+    HOST = os.environ.get("DIAG_HOST", "0") == "1"
+    if HOST:
+        h_pin = torch.from_numpy(frames).pin_memory(); h_np = h_pin.numpy()
+        for i in range(W): ctx.frame(h_np[i], ts[i])
+    else:
+        for i in range(W): ctx.frame_dev(d[i].data_ptr(), n, ts[i])
     torch.cuda.synchronize(); ctx.sync()
     import time
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter(); e0.record(st)
-    for i in range(W, W + K): ctx.frame_dev(d[i].data_ptr(), n, ts[i])
+    if HOST:      # the e2e path: pinned HOST frames through frame_submit / frame_collect
+        infl = 0
+        for i in range(W, W + K):
+            if infl == 31: ctx.frame_collect(); infl -= 1
+            ctx.frame_submit(h_np[i], ts[i]); infl += 1
+        while infl: ctx.frame_collect(); infl -= 1
+    else:
+        for i in range(W, W + K): ctx.frame_dev(d[i].data_ptr(), n, ts[i])
     th = time.perf_counter() - t0
     ctx.flush(); e1.record(st); torch.cuda.synchronize()
     hn = ctx.debug_host_ns()
@@ -54,6 +66,8 @@ for depth in [int(x) for x in os.environ.get("DIAG_DEPTHS", "1,4").split(",")]:
     gp = ctx.last_gate_phases.astype(np.int64)
     full = ctx.debug_tracker_trace().astype(np.int64)
     if gp[0] > 0: print(f"  last step: gate entry {(gp[0] - full[-2, 5]) / 1e3:.2f} us after the PREVIOUS step's TC end, gate released {(gp[1] - full[-2, 5]) / 1e3:.2f}, TA CTA 0 entry {(gp[2] - full[-2, 5]) / 1e3:.2f}, TA start {(full[-1, 0] - full[-2, 5]) / 1e3:.2f}; previous TC start {(full[-2, 4] - full[-2, 5]) / 1e3:.2f}, previous TB start {(full[-2, 2] - full[-2, 5]) / 1e3:.2f}")
+    pa = ctx.last_ta_phases.astype(np.int64); pa = pa[pa > 0]
+    if len(pa) > 1: print("  TA phases of CTA 0 (us after its start: staged, mixed, Cholesky, sigma points, mean+cov, S/Tc/S^-1, written back, gated):", " ".join(f"{(x - pa[0]) / 1e3:.2f}" for x in pa[1:]))
     if len(pb) > 1: print("  TB phases of CTA 0 (us after its start: staged, gate list, model warps + box warp done, lambda, merged, written back):", " ".join(f"{(x - pb[0]) / 1e3:.2f}" for x in pb[1:]))
     if len(ph) > 1: print("  TC phases (us after its start: loads issued, summaries in, boxes staged, pass A, exact tests, pass B, emit, act list, spawn, end):", " ".join(f"{(x - ph[0]) / 1e3:.2f}" for x in ph[1:]))
     ta, tb, tc = (tt[:, 1] - tt[:, 0]) / 1e3, (tt[:, 3] - tt[:, 2]) / 1e3, (tt[:, 5] - tt[:, 4]) / 1e3
