@@ -137,6 +137,10 @@ class Lmot:
         if getattr(self, "h", None):
             self.lib.lmot_destroy(self.h)
             self.h = None
+            self.lib.lmot_pinned_free.argtypes = [C.c_void_p]
+            for ptr in getattr(self, "_pinned", []):
+                self.lib.lmot_pinned_free(ptr)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -272,6 +276,19 @@ class Lmot:
     def flush(self):
         """Device-side join: the caller stream waits for everything submitted so far."""
         self._chk(self.lib.lmot_flush(self.h))
+
+    def pinned_array(self, shape, dtype=np.float32) -> np.ndarray:
+        """numpy array in page-locked host memory (lmot_pinned_alloc); freed when the context closes."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.lib.lmot_pinned_alloc.restype = C.c_void_p
+        self.lib.lmot_pinned_alloc.argtypes = [C.c_size_t]
+        ptr = self.lib.lmot_pinned_alloc(nbytes)
+        if not ptr:
+            raise LmotError(-1, "lmot_pinned_alloc failed")
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(ptr)
+        buf = (C.c_char * nbytes).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
     def frame_submit(self, points, timestamp_us, v_gps=0.0, yaw_gps=0.0):
         """Asynchronous host frame (pinned memory recommended); collect results later with frame_collect()."""

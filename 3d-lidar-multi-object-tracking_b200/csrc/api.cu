@@ -8,6 +8,7 @@
 // the kernels straight into the slot's pinned, device-mapped host block; the host only waits on an event.
 #include <cmath>
 #include <cstring>
+#include <cstdint>
 #include <cstdlib>
 #include <new>
 #include <chrono>
@@ -363,6 +364,7 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   if (const char* e = getenv("LMOT_COOP")) c->coop_launch = atoi(e) != 0;
   if (const char* e = getenv("LMOT_TRK_CTAS")) { const int v = atoi(e); if (v >= 8 && v <= 4096) c->trk_ctas = v; }     // tuning only
   if (const char* e = getenv("LMOT_FIT_CTAS")) { const int v = atoi(e); if (v >= 8 && v <= 4096) c->fit_ctas = v; }
+  if (const char* e = getenv("LMOT_ZERO_COPY")) c->zero_copy = atoi(e) != 0;
   if (const char* e = getenv("LMOT_GROUND_HALF")) c->ground_half_sms = atoi(e) != 0;
   if (const char* e = getenv("LMOT_PTS_PER_CTA")) { const int v = atoi(e); if (v >= 256 && v <= 16384) c->pts_per_cta = v; }
   int rc = LMOT_OK;
@@ -625,8 +627,22 @@ int lmot_frame_submit(lmot_ctx* ctx, const float* points, int n, int stride, dou
   Slot* s = acquire_slot(c);
   Result* r = acquire_result(c, false);
   if (!r) return LMOT_ERR_STATE;
-  // (Measured: end-to-end frames/s is bound by these copies -- 1.9 MB is 37 us of PCIe time at 52 GB/s plus ~10 us of set-up and
-  // completion per copy.  A copy stream of its own changed nothing, two alternating ones made cudaMemcpyAsync block the host.)
+  // (Measured: end-to-end frames/s is bound by these copies -- one 1.9 MB copy per frame sustains ~39 GB/s, 49 us per frame,
+  // against 41 us for the tracker chain.  A copy stream of its own changed nothing, two alternating ones made cudaMemcpyAsync
+  // block the host.)
+  // ZERO COPY (opt-in, LMOT_ZERO_COPY=1): a frame in page-locked host memory (lmot_pinned_alloc, cudaHostAlloc, cudaHostRegister) is
+  // not copied; under unified addressing the ground kernel's bulk copies read it over PCIe straight into shared memory, so every
+  // input byte crosses the link once and never touches HBM (possible whenever the launch keeps each CTA's chunk resident,
+  // ground_reads_input_once).  Bit-identical results (tests/test_pipeline_gpu.py) -- but MEASURED SLOWER than the copy engine on
+  // B200: SM-issued reads reach ~26 GB/s of the link (74 us per 1.9 MB frame, 13.4 k frames/s end to end) where cudaMemcpyAsync
+  // sustains ~39 GB/s at this copy size (49 us, 20.4 k frames/s).  Hence off by default.  The buffer must stay untouched until
+  // the frame has been collected (the same contract as the asynchronous copy).
+  if (c->zero_copy && stride == 4 && n > 0 && n <= c->max_points && (reinterpret_cast<uintptr_t>(points) & 15u) == 0 && ground_reads_input_once(c, n)) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, points) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+      return submit(c, s, r, reinterpret_cast<const float4*>(pa.devicePointer), n, true, timestamp_us, v_gps, yaw_gps);
+    cudaGetLastError();      // (pageable memory: not an error, take the copy path)
+  }
   LMOT_CUDA(c, cudaStreamWaitEvent(s->stream, s->ev_trk_done, 0));
   int rc = upload_points(c, s, s->stream, points, n, stride, s->d_points);
   if (rc) return rc;

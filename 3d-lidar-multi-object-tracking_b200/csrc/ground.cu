@@ -593,6 +593,14 @@ int ground_cells_debug(Ctx* c, Slot* s, cudaStream_t st) {
   return LMOT_OK;
 }
 
+// does a frame of n points stay resident in shared memory in the frame pipeline's launch geometry?  (then the kernel reads every
+// input byte exactly once, and the frame may be read straight from pinned host memory -- api.cu lmot_frame_submit)
+bool ground_reads_input_once(const Ctx* c, int n) {
+  int cap = c->fused_max_ctas;
+  if (c->ground_half_sms) { const int half = cap / 2 > kMinCtas ? cap / 2 : kMinCtas; if ((long long)half * kMaxResTiles * kTilePts >= (long long)n) cap = half; }
+  return (long long)cap * kMaxResTiles * kTilePts >= (long long)n;
+}
+
 int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count, bool want_labels) {
   s->cur_points = pts;
   s->cur_n = n;

@@ -172,6 +172,7 @@ struct Ctx {
   unsigned long long trk_frames = 0;
   unsigned long long* d_phase_clock = nullptr;   // diagnostic: [CTAs][8] %globaltimer stamps of the last ground launch (lmot_debug_phase_clock)
   int last_ground_ctas = 0;
+  bool zero_copy = false;              // lmot_frame_submit: pinned host frames are read by the ground kernel directly (LMOT_ZERO_COPY=1; off: slower than the copy engine)
   bool ground_half_sms = true;         // frame pipeline: ground kernel on half of the SMs (ground.cu ground_launch; LMOT_GROUND_HALF=0 disables, A/B only)
   int pts_per_cta = 768;               // target chunk of the fused ground kernel (LMOT_PTS_PER_CTA overrides, tuning only)
   unsigned long long* d_mt_raw = nullptr;  // raw mt19937_64(0) outputs (shared, read only)
@@ -257,6 +258,7 @@ void ground_free(Slot* s);
 // want_labels: also write the per-point u8 label array (stage entry point); the frame pipeline skips it
 int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count = false, bool want_labels = true);
 int ground_cells_debug(Ctx* c, Slot* s, cudaStream_t st);
+bool ground_reads_input_once(const Ctx* c, int n);
 int ground_repack(Ctx* c, cudaStream_t st, const float* d_in, int n, int stride, float4* d_out);
 int cluster_alloc(Ctx* c, Slot* s);
 void cluster_free(Slot* s);

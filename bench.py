@@ -12,8 +12,9 @@ a different frame (the ring of W+K frames is larger than the 126 MB L2, so input
 
 Printed JSON (rank 0, one line):
   value     whole-job frames/s with the frames already resident in HBM (CUDA events around K steps, max over ranks)
-  e2e       frames/s through the reference-facing C ABI call lmot_frame() on HOST buffers: every step copies the frame
-            H2D from pinned memory, runs the four stages and copies boxes + track outputs back, then synchronises
+  e2e       frames/s through the reference-facing C ABI on HOST buffers (lmot_frame_submit / lmot_frame_collect, pinned frames):
+            every step copies its frame H2D, runs the four stages and reads boxes + track outputs back; timed by the C++ loop
+            host/frame_loop.cpp (the reference's host language), the same loop from Python/ctypes is reported next to it
   roofline  ground_fused_kernel (the whole ground-removal stage in one cooperative launch, the only stage that streams
             the whole frame): algorithmic bytes per frame / its CUDA-event duration, vs the measured HBM peak
   cpu_baseline  the reference's own four entry points on a bounded sample of the same frames, one host thread
@@ -42,9 +43,9 @@ SCENE = dict(n_objects=150, lattice_pitch=3.8, ped_fraction=0.65, seed=1)   # ~6
 KERNEL_NAMES = ("ground_fused", "ccl_cluster", "tile_hist", "seg_offsets", "scatter", "box_fit",
                 "imm_predict_gate", "imm_update", "spawn_output")
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE ground_fused_kernel launch at the bench workload, from the committed
-# `ncu --set full` capture profiles/r1z_ncu_full_ground.csv (2.040 MB read: the frame once, plus the polar grid; 8-11 KB
+# `ncu --set full` capture profiles/r1z_ncu_full_ground.csv (2.03 MB read: the frame once, plus the polar grid; 0 bytes
 # written: the 3.9 MB of output clouds stay in the 126 MB L2 within the measured launch)
-TRAFFIC_NCU = 2.05e6
+TRAFFIC_NCU = 2.03e6
 KERNELS_PER_FRAME = len(KERNEL_NAMES) + 2   # ground 1 (also bins the elevated points) + cluster 1 + box 4 + tracker 3, + the tracker's gate kernel + publish_kernel
 
 
@@ -440,6 +441,13 @@ def main():
     hb1.record(stream)
     torch.cuda.synchronize()
     h2d_gbs = 8 * tmp_d.numel() * 4 / (hb0.elapsed_time(hb1) * 1e-3) / 1e9
+    # ... and one copy PER FRAME (what lmot_frame_submit issues): the per-copy set-up cost is not negligible at 1.9 MB
+    hb0.record(stream)
+    for i in range(64):
+        tmp_d[i % 8].copy_(h_frames[i % (W + K)], non_blocking=True)
+    hb1.record(stream)
+    torch.cuda.synchronize()
+    h2d_frame_us = 1e3 * hb0.elapsed_time(hb1) / 64
     del tmp_d
 
     # ---- (3) end to end through the C ABI with host buffers: `e2e`
@@ -548,7 +556,7 @@ def main():
                        "pipeline_depth": int(ctx.params.pipeline_depth), "result_ring": int(ctx.params.result_ring),
                        "l2_policy": f"every step reads a different frame of a {ring_mb:.0f} MiB ring (> 126 MB L2)"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": int(d2h),
-                    "pinned_h2d_gbs_this_box": h2d_gbs, "pcie_bound_frames_per_s": h2d_gbs * 1e9 / frame_bytes,
+                    "pinned_h2d_gbs_this_box": h2d_gbs, "h2d_us_per_frame_copy_this_box": h2d_frame_us, "pcie_bound_frames_per_s": 1e6 / h2d_frame_us,
                     "driver": ("host/frame_loop.cpp: C++ loop over lmot_frame_submit / lmot_frame_collect, pinned host frames" if native else "python ctypes loop"),
                     "host_us_per_step": ({"submit": native["submit_us_per_frame"], "collect_incl_wait": native["collect_us_per_frame"]} if native
                                          else {"submit": 1e6 * t_submit / K, "collect_incl_wait": 1e6 * t_collect / K}),
