@@ -76,3 +76,33 @@ def test_ros_node_shells_compile():
                             os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "ros", "include"),
                             os.path.join(ROOT, "ros", "src", node + "_node.cpp")], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_frame_loop_driver_builds_and_fails_loudly_without_a_gpu(pkg, tmp_path):
+    """host/frame_loop.cpp (the C++ submit / collect loop bench.py times `e2e` with) builds against include/lmot.h and the in-tree
+    library; without a CUDA device it must stop with an error (pinned allocation / lmot_create fail), never fall back."""
+    import subprocess
+    import torch
+    src = os.path.join(pkg.HERE, "host", "frame_loop.cpp")
+    exe = str(tmp_path / "frame_loop")
+    subprocess.run(["g++", "-std=c++14", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", pkg.HERE, "-llmot",
+                    "-Wl,-rpath," + pkg.HERE], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+    if not torch.cuda.is_available():
+        f = tmp_path / "frames.bin"
+        np.zeros((2, 64, 4), np.float32).tofile(f)
+        r = subprocess.run([exe, str(f), "2", "64", "1", "1"], capture_output=True, text=True)
+        assert r.returncode != 0 and r.stdout.strip() == ""
+
+
+def test_pinned_alloc_without_a_gpu_returns_null(pkg):
+    import torch
+    if torch.cuda.is_available():
+        return
+    lib = pkg.load_library()
+    lib.lmot_pinned_alloc.restype = ctypes.c_void_p
+    lib.lmot_pinned_alloc.argtypes = [ctypes.c_size_t]
+    assert not lib.lmot_pinned_alloc(1 << 20)
+    lib.lmot_pinned_free.argtypes = [ctypes.c_void_p]
+    lib.lmot_pinned_free(None)
