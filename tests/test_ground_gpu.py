@@ -85,6 +85,25 @@ def test_edge_cases(lm, ref_intended):
     assert np.array_equal(a["elevated"][:, :3], e_ref)
 
 
+def test_non_finite_points(lm, ref_intended, synth):
+    """NaN / Inf coordinates as the reference treats them: a non-finite x or y never passes the range filter; a NaN z never wins
+    `z < minZ` and is never `< hGround + 0.25` (elevated); +Inf z is elevated, -Inf z becomes its cell's minimum."""
+    nan, inf = np.nan, np.inf
+    pts = synth.uniform_cloud(6000, 21).copy()
+    special = np.array([[nan, 1, -1.7, 0], [5, nan, -1.7, 0], [5, 5, nan, 0], [inf, 0, -1.7, 0], [5, -inf, -1.7, 0], [6, 6, inf, 0],
+                        [6, 6, -inf, 0], [-inf, inf, nan, 0], [nan, nan, nan, 0], [7, 7, -1.7, 0]], np.float32)
+    for k, row in enumerate(special):
+        pts[37 + 599 * k] = row
+    out = lm.ground_remove(pts)
+    e_ref, g_ref = ref_intended.ground_remove(pts)
+    assert np.array_equal(out["elevated"][:, :3].view(np.uint32), e_ref.view(np.uint32))
+    assert np.array_equal(out["ground"][:, :3].view(np.uint32), g_ref.view(np.uint32))
+    g_gpu, g_r = lm.debug_polar_grid(), ref_intended.polar_grid(pts)
+    for k in ("minz", "height", "smoothed", "hdiff"):
+        assert np.array_equal(g_gpu[k].view(np.uint32), g_r[k].view(np.uint32)), k
+    assert np.array_equal(g_gpu["isground"], g_r["isground"])
+
+
 def test_repeatable_and_stateless(lm, synth):
     pts = synth.uniform_cloud(30000, 11)
     a = lm.ground_remove(pts)
