@@ -2,10 +2,11 @@
 // stream/event ordering of the frame pipeline and capacity checks; every algorithmic step is a CUDA kernel in
 // ground.cu / cluster.cu / boxfit.cu / tracker.cu.  There is deliberately no CPU implementation of any stage here.
 //
-// Frame pipeline: a context owns `pipeline_depth` detection slots (own stream + own buffers each) and one tracker
-// stream.  Frame f runs ground -> cluster -> box on slot f % depth; the tracker stream waits for the slot's boxes,
-// folds them into the track table, and releases the slot.  Results (counts, boxes, per-track outputs) are stored by
-// the kernels straight into the slot's pinned, device-mapped host block; the host only waits on an event.
+// Frame pipeline: a context owns `pipeline_depth` detection slots (own stream + own buffers each), one tracker stream
+// and one publish stream.  Frame f runs ground -> cluster -> box on slot f % depth; the tracker chain (gate -> TA -> TB
+// -> TC, tracker.cu) waits ON THE DEVICE for the slot's boxes and folds them into the track table; publish_kernel moves
+// the frame's results (counts, boxes, per-track outputs) from their device block into the pinned, device-mapped host
+// block of the result ring and releases the slot; the host only waits on an event.
 #include <cmath>
 #include <cstring>
 #include <cstdint>

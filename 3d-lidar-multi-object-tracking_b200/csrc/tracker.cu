@@ -7,19 +7,24 @@
 //   (c) append-order spawning of new tracks (:972-989),
 // all deterministic functions of per-(track, box) predicates, so tracks run in parallel:
 //
-//   TA imm_predict_gate_kernel  3 warps per track (one per motion model CV/CTRV/RM): explosion guards (:826-831),
+//   G  tracker_gate_kernel      one warp: waits (on the device) for this frame's detection stages, then lets TA's CTAs come.
+//   TA imm_predict_gate_kernel  one CTA per active track, 3 warps = motion models CV/CTRV/RM: explosion guards (:826-831),
 //                               IMM mixing + interaction (ukf.cpp:439-500), 7-dim augmented sigma points with Eigen's
 //                               early-exit Cholesky (lane = sigma point), model propagation, weighted mean /
 //                               covariance (lane = matrix element), lidar S / K (ukf.cpp:778-902); then the chi-square
 //                               gate of every box against the max-det(S) model (:843-869) -> gate / setter bit
-//                               rows and first_setter[box] = min track index (atomicMin).
-//   TB imm_update_kernel        1 warp per track: lifetime_, measurement list, box association (:416-463), updateBB
-//                               (:565-653), secondInit (:882-921), track-number machine (:924-944), PDA update with
-//                               association likelihoods (:259-394), IMM mode-probability update and merge
-//                               (ukf.cpp:384-437).
+//                               rows, first_setter[box] = min track index (atomicMin), compact list of gated centres.
+//   TB imm_update_kernel        one CTA per active track: warps 0-2 the PDA update of one model each (:259-394), warp 3
+//                               lifetime_, measurement list, box association (:416-463), updateBB (:565-653), secondInit
+//                               (:882-921); then warp 0: association likelihoods, track-number machine (:924-944), IMM
+//                               mode-probability update and merge (ukf.cpp:384-437); 128-byte summary for TC.
 //   TC spawn_output_kernel      one CTA: mergeOverSegmentation as "the last write of the reference's (i,j) loop" over
 //                               (live x visible) and (visible x all) pairs, then spawn a UKF per unmatched box in box
-//                               order, per-track outputs, static flag.
+//                               order, per-track outputs, static flag.  Fast path (<= 256 active tracks) from TB's
+//                               summaries, general path from the records.
+//   P  publish_kernel           device result block -> pinned host block, on its own stream (polls TC's step counter).
+// G -> TA -> TB -> TC are programmatic dependent launches of one another (griddepcontrol); in steady state the tracker
+// stream carries nothing else.
 //
 // All state is fp64 like the reference (Eigen::MatrixXd); this file is compiled with -fmad=false so that the
 // operation sequence matches the x86-64 build of the reference except for libm (sin/cos/exp/pow/atan2 <= 2 ulp).
