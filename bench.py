@@ -397,6 +397,12 @@ def main():
     ctx.tracker_reset()
     for i in range(W):
         ctx.frame_dev(d_frames[i].data_ptr(), n_pts, ts[i])
+    # every timed step reads a frame no earlier step has read; with the default K the ring is 3x the 126 MB L2.  A short run
+    # (ring < L2) could still find its frames in L2 from the upload above: push them out with a buffer larger than L2
+    small_ring = ring_mb < 160
+    if small_ring:
+        l2_flush = torch.empty(192 * 2**20, dtype=torch.uint8, device="cuda")
+        l2_flush.zero_()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -569,7 +575,8 @@ def main():
                        "tracks_in_table_end": int(len(res_dev["track_manage"])), "rule_filter": "INTENDED",
                        "parallelism": f"{world} independent sensor stream(s), one per GPU, no collective on the data path",
                        "pipeline_depth": int(ctx.params.pipeline_depth), "result_ring": int(ctx.params.result_ring),
-                       "l2_policy": f"every step reads a different frame of a {ring_mb:.0f} MiB ring (> 126 MB L2)"},
+                       "l2_policy": (f"every step reads a different frame of a {ring_mb:.0f} MiB ring (> 126 MB L2)" if not small_ring else
+                                     f"every step reads a different frame of a {ring_mb:.0f} MiB ring, L2 flushed (192 MiB written) before the timed region")},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": int(d2h),
                     "pinned_h2d_gbs_this_box": h2d_gbs, "h2d_us_per_frame_copy_this_box": h2d_frame_us, "pcie_bound_frames_per_s": 1e6 / h2d_frame_us,
                     "driver": ("host/frame_loop.cpp: C++ loop over lmot_frame_submit / lmot_frame_collect, pinned host frames" if native else "python ctypes loop"),
