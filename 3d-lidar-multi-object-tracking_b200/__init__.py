@@ -65,6 +65,17 @@ class TrackOut(C.Structure):
     ]
 
 
+MAX_BATCH = 8
+
+
+class BatchOut(C.Structure):
+    _fields_ = [
+        ("n_frames", C.c_int),
+        ("n_elevated", C.c_int * MAX_BATCH), ("n_ground", C.c_int * MAX_BATCH), ("num_cluster", C.c_int * MAX_BATCH), ("n_boxes", C.c_int * MAX_BATCH),
+        ("n_boxes_total", C.c_int), ("boxes", C.POINTER(C.c_float)), ("max_boxes", C.c_int), ("tracks", TrackOut),
+    ]
+
+
 class FrameOut(C.Structure):
     _fields_ = [
         ("n_elevated", C.c_int), ("n_ground", C.c_int), ("num_cluster", C.c_int), ("n_boxes", C.c_int),
@@ -78,6 +89,8 @@ ABI_SYMBOLS = [
     "lmot_set_stream", "lmot_pinned_alloc", "lmot_pinned_free", "lmot_ground_remove", "lmot_component_cluster", "lmot_cluster_outputs", "lmot_box_fit", "lmot_track_step", "lmot_frame",
     "lmot_frame_dev", "lmot_frame_fetch", "lmot_frame_submit", "lmot_frame_collect", "lmot_frames_in_flight", "lmot_frame_ready", "lmot_flush",
     "lmot_ground_remove_dev", "lmot_detect_dev", "lmot_sync",
+    "lmot_batch_submit", "lmot_batch_dev", "lmot_batch_detect_dev", "lmot_batch_collect", "lmot_batch_fetch", "lmot_batch", "lmot_batch_ground_ccl_dev",
+    "lmot_debug_stage_clocks",
     "lmot_origin_points", "lmot_tracker_table", "lmot_tracker_set_num_tracks", "lmot_tracker_reset", "lmot_tracker_num_tracks", "lmot_tracker_dump", "lmot_tracker_load",
     "lmot_debug_polar_grid", "lmot_debug_cell_index", "lmot_debug_label_grid", "lmot_debug_phase_clock", "lmot_debug_timeline", "lmot_debug_tracker_trace", "lmot_selftest_atan2f",
     "lmot_enable_timing", "lmot_last_stage_ms", "lmot_last_kernel_ms", "lmot_debug_host_ns",
@@ -316,6 +329,80 @@ class Lmot:
         fo, bufs = self._frame_out(cap or self.params.max_tracks, want_boxes)
         self._chk(self.lib.lmot_frame_fetch(self.h, C.byref(fo)))
         return self._frame_result(fo, bufs, want_boxes)
+
+    # ---- batched ticks: F sensor streams, one frame each, one shared track table (BASELINE.json configs[3]) --------
+    def _batch_args(self, frames, device: bool):
+        F = len(frames)
+        ptrs = (C.c_void_p * F)()
+        ns = (C.c_int * F)()
+        keep = []
+        stride = 4
+        for i, f in enumerate(frames):
+            if device:
+                ptrs[i], ns[i] = int(f[0]), int(f[1])
+            else:
+                p, n, stride = _pts(f)
+                keep.append(p)
+                ptrs[i], ns[i] = p.ctypes.data, n
+        return ptrs, ns, F, stride, keep
+
+    def _batch_result(self, bo, bufs, want_boxes=True):
+        r = Lmot._track_result(bo.tracks, bufs)
+        F = bo.n_frames
+        r.update(n_frames=F, n_elevated=list(bo.n_elevated[:F]), n_ground=list(bo.n_ground[:F]), num_cluster=list(bo.num_cluster[:F]),
+                 n_boxes=list(bo.n_boxes[:F]), boxes=bufs["boxes"][: bo.n_boxes_total].copy() if want_boxes else bufs["boxes"][:0])
+        return r
+
+    def _batch_out(self, cap, want_boxes=True):
+        to, bufs = self._track_out(cap)
+        bo = BatchOut()
+        if want_boxes:
+            bo.boxes = _fp(bufs["boxes"])
+        bo.max_boxes = self.params.max_boxes
+        bo.tracks = to
+        return bo, bufs
+
+    def batch(self, frames, timestamp_us, v_gps=0.0, yaw_gps=0.0, cap: int | None = None):
+        """One tick, synchronous: `frames` = list of (N_i, >=3) host arrays (one per sensor stream)."""
+        ptrs, ns, F, stride, keep = self._batch_args(frames, False)
+        bo, bufs = self._batch_out(cap or self.params.max_tracks)
+        self._chk(self.lib.lmot_batch(self.h, ptrs, ns, F, stride, C.c_double(timestamp_us), C.c_double(v_gps), C.c_double(yaw_gps), C.byref(bo)))
+        return self._batch_result(bo, bufs)
+
+    def batch_submit(self, frames, timestamp_us, v_gps=0.0, yaw_gps=0.0):
+        ptrs, ns, F, stride, keep = self._batch_args(frames, False)
+        self._keep = keep          # the copies are asynchronous: the host arrays must outlive the call
+        self._chk(self.lib.lmot_batch_submit(self.h, ptrs, ns, F, stride, C.c_double(timestamp_us), C.c_double(v_gps), C.c_double(yaw_gps)))
+
+    def batch_dev(self, dev_frames, timestamp_us, v_gps=0.0, yaw_gps=0.0):
+        """dev_frames = list of (device pointer, n) of stride-4 float frames."""
+        ptrs, ns, F, _, _ = self._batch_args(dev_frames, True)
+        self._chk(self.lib.lmot_batch_dev(self.h, ptrs, ns, F, C.c_double(timestamp_us), C.c_double(v_gps), C.c_double(yaw_gps)))
+
+    def batch_detect_dev(self, dev_frames):
+        ptrs, ns, F, _, _ = self._batch_args(dev_frames, True)
+        self._chk(self.lib.lmot_batch_detect_dev(self.h, ptrs, ns, F))
+
+    def batch_ground_ccl_dev(self, dev_frames):
+        ptrs, ns, F, _, _ = self._batch_args(dev_frames, True)
+        self._chk(self.lib.lmot_batch_ground_ccl_dev(self.h, ptrs, ns, F))
+
+    def batch_collect(self, cap: int | None = None, want_boxes: bool = True):
+        bo, bufs = self._batch_out(cap or self.params.max_tracks, want_boxes)
+        self._chk(self.lib.lmot_batch_collect(self.h, C.byref(bo)))
+        return self._batch_result(bo, bufs, want_boxes)
+
+    def batch_fetch(self, cap: int | None = None, want_boxes: bool = True):
+        bo, bufs = self._batch_out(cap or self.params.max_tracks, want_boxes)
+        self._chk(self.lib.lmot_batch_fetch(self.h, C.byref(bo)))
+        return self._batch_result(bo, bufs, want_boxes)
+
+    def debug_stage_clocks(self, which: int):
+        """which = 1: (frames, 16) stamps of the last ccl_bitmap_kernel; 2: (CTAs, 8) of the last box_fit_kernel (phase clock armed)."""
+        buf = np.zeros((4096, 16), np.uint64)
+        n = C.c_int(0); w = C.c_int(0)
+        self._chk(self.lib.lmot_debug_stage_clocks(self.h, int(which), buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), 4096, C.byref(n), C.byref(w)))
+        return buf.reshape(-1)[: n.value * w.value].reshape(n.value, w.value).copy()
 
     def tracker_reset(self):
         self._chk(self.lib.lmot_tracker_reset(self.h))

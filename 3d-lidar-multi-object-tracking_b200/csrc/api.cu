@@ -88,6 +88,7 @@ int check_device_error(Ctx* c, Slot* s, cudaStream_t st) {
 // wait until nothing of this context is running on the device and forget uncollected results
 int drain(Ctx* c) {
   for (int i = 0; i < c->n_slots; ++i) LMOT_CUDA(c, cudaStreamSynchronize(c->slots[i].stream));
+  for (int i = 0; i < c->n_bslots; ++i) LMOT_CUDA(c, cudaStreamSynchronize(c->bslots[i].stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->trk_stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->pub_stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -121,12 +122,38 @@ Result* acquire_result(Ctx* c, bool drop_oldest) {
   return r;
 }
 
+// the tracker chain + publication of one tick: boxes / counters of `s` (a detection slot, or a batch bank) -> track table -> result block r
+int submit_tracker(Ctx* c, Slot* s, Result* r, const float* d_boxes, const int* d_counters, double ts, double v, double yaw) {
+  int rc;
+  // the tracker waits for this tick's detection on the DEVICE (gate kernel), or on ev_det_done where that is not possible
+  bool gated = false;
+  if ((rc = tracker_launch(c, s, c->trk_stream, d_boxes, d_counters, ts, v, yaw, true, &gated))) return rc;
+  if (gated) {
+    // Nothing but kernels on the tracker stream (an event record between spawn_output_kernel and the next frame's gate
+    // kernel would serialise the two launches): publish_kernel polls the device-side step count, and "the slot is free"
+    // is recorded behind it on the publish stream -- ~10 us later than strictly necessary, detection has >100 us of slack
+    if ((rc = tracker_publish(c, r, c->pub_stream))) return rc;
+    LMOT_CUDA(c, cudaEventRecord(r->ev_done, c->pub_stream));
+    LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, c->pub_stream));
+  } else {
+    if (c->timing) cudaEventRecord(r->ev[4], c->trk_stream);
+    LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, c->trk_stream));      // the slot is free: its boxes / counters were consumed
+    LMOT_CUDA(c, cudaEventRecord(r->ev_tc, c->trk_stream));
+    // device block -> pinned host block, off the tracker's sequential chain
+    LMOT_CUDA(c, cudaStreamWaitEvent(c->pub_stream, r->ev_tc, 0));
+    if ((rc = tracker_publish(c, r, c->pub_stream))) return rc;
+    LMOT_CUDA(c, cudaEventRecord(r->ev_done, c->pub_stream));
+  }
+  return LMOT_OK;
+}
+
 // the asynchronous frame: detection on the slot stream, tracker on the tracker stream
 int submit(Ctx* c, Slot* s, Result* r, const float4* d_pts, int n, bool with_tracker, double ts, double v, double yaw) {
   int rc;
   struct Tail { Ctx* c; double t0; ~Tail() { c->host_ns[0] += now_ns() - t0; } } tail{c, now_ns()};
   s->res = r;
   r->n_kev = 0;
+  r->batch_frames = 0;
   // the slot's previous boxes / counters must have been consumed by the tracker
   LMOT_CUDA(c, cudaStreamWaitEvent(s->stream, s->ev_trk_done, 0));
   if (c->timing) cudaEventRecord(r->ev[0], s->stream);
@@ -138,31 +165,100 @@ int submit(Ctx* c, Slot* s, Result* r, const float4* d_pts, int n, bool with_tra
   if (c->timing) cudaEventRecord(r->ev[3], s->stream);
   LMOT_CUDA(c, cudaEventRecord(s->ev_det_done, s->stream));
   if (with_tracker) {
-    // the tracker waits for this frame's detection on the DEVICE (gate kernel), or on ev_det_done where that is not possible
-    bool gated = false;
-    if ((rc = tracker_launch(c, s, c->trk_stream, s->d_boxes, s->d_counters, ts, v, yaw, true, &gated))) return rc;
-    if (gated) {
-      // Nothing but kernels on the tracker stream (an event record between spawn_output_kernel and the next frame's gate
-      // kernel would serialise the two launches): publish_kernel polls the device-side step count, and "the slot is free"
-      // is recorded behind it on the publish stream -- ~10 us later than strictly necessary, detection has >100 us of slack
-      if ((rc = tracker_publish(c, r, c->pub_stream))) return rc;
-      LMOT_CUDA(c, cudaEventRecord(r->ev_done, c->pub_stream));
-      LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, c->pub_stream));
-    } else {
-      if (c->timing) cudaEventRecord(r->ev[4], c->trk_stream);
-      LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, c->trk_stream));      // the slot is free: its boxes / counters were consumed
-      LMOT_CUDA(c, cudaEventRecord(r->ev_tc, c->trk_stream));
-      // device block -> pinned host block, off the tracker's sequential chain
-      LMOT_CUDA(c, cudaStreamWaitEvent(c->pub_stream, r->ev_tc, 0));
-      if ((rc = tracker_publish(c, r, c->pub_stream))) return rc;
-      LMOT_CUDA(c, cudaEventRecord(r->ev_done, c->pub_stream));
-    }
+    if ((rc = submit_tracker(c, s, r, s->d_boxes, s->d_counters, ts, v, yaw))) return rc;
   } else {
     // no spawn_output_kernel will snapshot the counters / boxes: copy them before the slot is reused
     LMOT_CUDA(c, cudaMemcpyAsync(r->h_det, s->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     if ((rc = boxes_publish(c, s, r, s->stream))) return rc;
     LMOT_CUDA(c, cudaEventRecord(s->ev_trk_done, s->stream));
     LMOT_CUDA(c, cudaEventRecord(r->ev_done, s->stream));
+  }
+  r->has_tracks = with_tracker;
+  if (!r->in_flight) { r->in_flight = true; ++c->n_in_flight; }
+  return LMOT_OK;
+}
+
+// ---- batched ticks: F sensor streams, one frame each, ONE track table (BASELINE.json configs[3]) -------------------------
+// Their own detection slots (allocated on first use, two banks of F so that the detection of tick t+1 overlaps the tracker of
+// tick t); a bank's kernels all run on its first slot's stream.  `bank` is a pseudo-slot: the concatenated box list, its
+// counters, the detection semaphore and the events the tracker hand-over needs.
+int slot_create(Ctx* c, Slot* s, int index);
+void slot_destroy(Slot* s);
+
+int batch_ensure(Ctx* c, int F) {
+  if (F <= c->batch_frames) return LMOT_OK;
+  // (re)allocate for the larger batch: nothing of the old banks may be in flight
+  for (int i = 0; i < c->n_bslots; ++i) LMOT_CUDA(c, cudaStreamSynchronize(c->bslots[i].stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->trk_stream));
+  LMOT_CUDA(c, cudaStreamSynchronize(c->pub_stream));
+  for (int i = c->n_bslots; i < kBatchBanks * F; ++i) {
+    int rc = slot_create(c, &c->bslots[i], 1000 + i);
+    if (rc) return rc;
+    c->n_bslots = i + 1;
+  }
+  for (int b = 0; b < kBatchBanks; ++b) {
+    Slot* k = &c->bank[b];
+    if (k->d_boxes) continue;
+    k->index = 2000 + b;
+    LMOT_CUDA(c, cudaMalloc(&k->d_boxes, (size_t)c->prm.max_boxes * 24 * sizeof(float)));
+    LMOT_CUDA(c, cudaMalloc(&k->d_counters, CNT_COUNT * sizeof(int)));
+    LMOT_CUDA(c, cudaMemset(k->d_counters, 0, CNT_COUNT * sizeof(int)));
+    LMOT_CUDA(c, cudaMalloc(&k->d_det_sem, sizeof(int)));
+    LMOT_CUDA(c, cudaMemset(k->d_det_sem, 0, sizeof(int)));
+    LMOT_CUDA(c, cudaEventCreateWithFlags(&k->ev_det_done, cudaEventDisableTiming));
+    LMOT_CUDA(c, cudaEventCreateWithFlags(&k->ev_trk_done, cudaEventDisableTiming));
+    LMOT_CUDA(c, cudaEventCreateWithFlags(&k->ev_fork, cudaEventDisableTiming));
+    LMOT_CUDA(c, cudaEventRecord(k->ev_trk_done, c->stream));
+    LMOT_CUDA(c, cudaEventRecord(k->ev_det_done, c->stream));
+    k->res = &c->results[0];
+  }
+  LMOT_CUDA(c, cudaDeviceSynchronize());
+  c->batch_frames = F;
+  return LMOT_OK;
+}
+
+void batch_destroy(Ctx* c) {
+  for (int i = 0; i < c->n_bslots; ++i) slot_destroy(&c->bslots[i]);
+  for (int b = 0; b < kBatchBanks; ++b) {
+    Slot* k = &c->bank[b];
+    cudaFree(k->d_boxes); cudaFree(k->d_counters); cudaFree(k->d_det_sem);
+    if (k->ev_det_done) cudaEventDestroy(k->ev_det_done);
+    if (k->ev_trk_done) cudaEventDestroy(k->ev_trk_done);
+    if (k->ev_fork) cudaEventDestroy(k->ev_fork);
+  }
+}
+
+// one tick: F device-resident frames (slot buffers or caller pointers) -> batched ground / CCL / box fitting -> concatenated boxes
+// -> (optionally) the tracker.  d_pts[i] == nullptr: the frame was uploaded into the slot's own buffer.
+int batch_submit(Ctx* c, int bank_i, Result* r, const float4* const* d_pts, const int* n, int F, bool with_tracker, double ts, double v, double yaw) {
+  int rc;
+  struct Tail { Ctx* c; double t0; ~Tail() { c->host_ns[0] += now_ns() - t0; } } tail{c, now_ns()};
+  Slot* k = &c->bank[bank_i];
+  Slot* sl[kMaxBatch];
+  const float4* pp[kMaxBatch];
+  for (int i = 0; i < F; ++i) { sl[i] = &c->bslots[bank_i * c->batch_frames + i]; pp[i] = d_pts[i] ? d_pts[i] : sl[i]->d_points; }
+  cudaStream_t st = sl[0]->stream;
+  k->res = r; sl[0]->res = r;
+  r->n_kev = 0;
+  r->batch_frames = F;
+  if (c->timing) cudaEventRecord(r->ev[0], st);
+  if ((rc = ground_launch_batch(c, sl, F, pp, n, st, true, false))) return rc;
+  if (c->timing) cudaEventRecord(r->ev[1], st);
+  if ((rc = ccl_launch_batch(c, sl, F, st))) return rc;
+  if (c->timing) cudaEventRecord(r->ev[2], st);
+  if ((rc = boxfit_launch_batch(c, sl, F, st, n, false))) return rc;
+  int* d_fc = nullptr;                       // the per-frame counts go straight into the result's pinned, device-mapped block
+  LMOT_CUDA(c, cudaHostGetDevicePointer((void**)&d_fc, r->h_frame_counts, 0));
+  if ((rc = boxes_concat_launch(c, sl, F, st, k->d_boxes, k->d_counters, d_fc, with_tracker ? k->d_det_sem : nullptr))) return rc;
+  if (c->timing) cudaEventRecord(r->ev[3], st);
+  LMOT_CUDA(c, cudaEventRecord(k->ev_det_done, st));
+  if (with_tracker) {
+    if ((rc = submit_tracker(c, k, r, k->d_boxes, k->d_counters, ts, v, yaw))) return rc;
+  } else {
+    LMOT_CUDA(c, cudaMemcpyAsync(r->h_det, k->d_counters, CNT_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if ((rc = boxes_publish(c, k, r, st))) return rc;
+    LMOT_CUDA(c, cudaEventRecord(k->ev_trk_done, st));
+    LMOT_CUDA(c, cudaEventRecord(r->ev_done, st));
   }
   r->has_tracks = with_tracker;
   if (!r->in_flight) { r->in_flight = true; ++c->n_in_flight; }
@@ -222,6 +318,8 @@ int result_create(Ctx* c, Result* r) {
   memset(r->h_hdr, 0, HDR_COUNT * sizeof(int));
   LMOT_CUDA(c, cudaHostAlloc(&r->h_det, CNT_COUNT * sizeof(int), fl));
   memset(r->h_det, 0, CNT_COUNT * sizeof(int));
+  LMOT_CUDA(c, cudaHostAlloc(&r->h_frame_counts, 4 * kMaxBatch * sizeof(int), fl));
+  memset(r->h_frame_counts, 0, 4 * kMaxBatch * sizeof(int));
   LMOT_CUDA(c, cudaHostAlloc(&r->h_boxes, (size_t)MB * 24 * sizeof(float) + 16, fl));
   // + 16 bytes: spawn_output_kernel writes whole 16-byte words
   LMOT_CUDA(c, cudaHostAlloc(&r->h_targets, (size_t)TC * 3 * sizeof(float) + 16, fl));
@@ -254,6 +352,7 @@ int result_create(Ctx* c, Result* r) {
 void result_destroy(Result* r) {
   if (r->h_hdr) cudaFreeHost(r->h_hdr);
   if (r->h_det) cudaFreeHost(r->h_det);
+  if (r->h_frame_counts) cudaFreeHost(r->h_frame_counts);
   if (r->h_boxes) cudaFreeHost(r->h_boxes);
   if (r->h_targets) cudaFreeHost(r->h_targets);
   if (r->h_vandyaw) cudaFreeHost(r->h_vandyaw);
@@ -363,6 +462,7 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   c->gp.tol = p.ground_tolerance;
   gauss_taps(c->gp.tap);
   if (const char* e = getenv("LMOT_COOP")) c->coop_launch = atoi(e) != 0;
+  if (const char* e = getenv("LMOT_SPIN_LIMIT")) c->spin_limit = (unsigned)strtoul(e, nullptr, 0);   // 0: device-side waits never trap (debuggers, MPS)
   if (const char* e = getenv("LMOT_TRK_CTAS")) { const int v = atoi(e); if (v >= 8 && v <= 4096) c->trk_ctas = v; }     // tuning only
   if (const char* e = getenv("LMOT_FIT_CTAS")) { const int v = atoi(e); if (v >= 8 && v <= 4096) c->fit_ctas = v; }
   if (const char* e = getenv("LMOT_ZERO_COPY")) c->zero_copy = atoi(e) != 0;
@@ -394,9 +494,10 @@ void lmot_destroy(lmot_ctx* ctx) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (int i = 0; i < c->n_slots; ++i) slot_destroy(&c->slots[i]);
+  batch_destroy(c);
   for (int i = 0; i < c->n_results; ++i) result_destroy(&c->results[i]);
   tracker_free(c);
-  cudaFree(c->d_phase_clock); cudaFree(c->d_trk_trace);
+  cudaFree(c->d_phase_clock); cudaFree(c->d_trk_trace); cudaFree(c->d_ccl_clock); cudaFree(c->d_fit_clock);
   cudaFree(c->d_mt_raw);
   if (c->trk_stream) cudaStreamDestroy(c->trk_stream);
   if (c->pub_stream) cudaStreamDestroy(c->pub_stream);
@@ -422,6 +523,7 @@ int lmot_sync(lmot_ctx* ctx) {
   if (!ctx) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
   for (int i = 0; i < c->n_slots; ++i) LMOT_CUDA(c, cudaStreamSynchronize(c->slots[i].stream));
+  for (int i = 0; i < c->n_bslots; ++i) LMOT_CUDA(c, cudaStreamSynchronize(c->bslots[i].stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->trk_stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->pub_stream));
   LMOT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -436,6 +538,10 @@ int lmot_flush(lmot_ctx* ctx) {
     LMOT_CUDA(c, cudaStreamWaitEvent(c->stream, c->slots[i].ev_det_done, 0));
     LMOT_CUDA(c, cudaStreamWaitEvent(c->stream, c->slots[i].ev_trk_done, 0));
   }
+  for (int b = 0; b < kBatchBanks && c->batch_frames > 0; ++b) {
+    LMOT_CUDA(c, cudaStreamWaitEvent(c->stream, c->bank[b].ev_det_done, 0));
+    LMOT_CUDA(c, cudaStreamWaitEvent(c->stream, c->bank[b].ev_trk_done, 0));
+  }
   if (c->last_res && c->last_res->ev_done) LMOT_CUDA(c, cudaStreamWaitEvent(c->stream, c->last_res->ev_done, 0));   // publication is in order
   return LMOT_OK;
 }
@@ -448,7 +554,8 @@ int lmot_ground_remove_dev(lmot_ctx* ctx, const float* d_points, int n) {
   if (c->n_in_flight > 0) { int rc = drain(c); if (rc) return rc; }     // slot 0 may still be busy with a pipelined frame
   Slot* s = &c->slots[0];
   c->last_slot = 0;
-  return ground_launch(c, s, c->stream, reinterpret_cast<const float4*>(d_points), n);
+  // (no label array, no debug grid: what the frame pipeline launches, minus the clustering bit planes)
+  return ground_launch(c, s, c->stream, reinterpret_cast<const float4*>(d_points), n, false, false);
 }
 
 int lmot_ground_remove(lmot_ctx* ctx, const float* points, int n, int stride, uint8_t* labels, float* elevated,
@@ -703,6 +810,132 @@ int lmot_frame(lmot_ctx* ctx, const float* points, int n, int stride, double tim
   return lmot_frame_collect(ctx, out);
 }
 
+// ---------------------------------------------------------------------------------------------- batched ticks
+static int batch_common(lmot_ctx* ctx, const float* const* points, const int* n, int n_frames, int stride, bool host, bool with_tracker,
+                        double ts, double v, double yaw) {
+  if (!ctx || !points || !n || n_frames < 1 || n_frames > kMaxBatch) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  for (int i = 0; i < n_frames; ++i) {
+    if (n[i] < 0 || (n[i] > 0 && !points[i])) return LMOT_ERR_INVALID;
+    if (n[i] > c->max_points) return LMOT_ERR_CAPACITY;
+    if (!host && n[i] > 0 && (reinterpret_cast<uintptr_t>(points[i]) & 15u)) return LMOT_ERR_INVALID;   // bulk copies need 16-byte alignment
+  }
+  if (host && c->n_in_flight >= c->n_results) return LMOT_ERR_STATE;
+  int rc = batch_ensure(c, n_frames);
+  if (rc) return rc;
+  Result* r = acquire_result(c, !host);
+  if (!r) return LMOT_ERR_STATE;
+  const int b = c->next_bank;
+  c->next_bank = (c->next_bank + 1) % kBatchBanks;
+  Slot* k = &c->bank[b];
+  Slot* s0 = &c->bslots[b * c->batch_frames];
+  cudaStream_t st = s0->stream;
+  // the bank's previous tick must have been consumed by the tracker; device frames: ordered after the caller's stream
+  LMOT_CUDA(c, cudaStreamWaitEvent(st, k->ev_trk_done, 0));
+  const float4* dp[kMaxBatch];
+  if (host) {
+    for (int i = 0; i < n_frames; ++i) {
+      Slot* s = &c->bslots[b * c->batch_frames + i];
+      if ((rc = upload_points(c, s, st, points[i], n[i], stride, s->d_points))) return rc;
+      dp[i] = nullptr;
+    }
+  } else {
+    LMOT_CUDA(c, cudaEventRecord(k->ev_fork, c->stream));
+    LMOT_CUDA(c, cudaStreamWaitEvent(st, k->ev_fork, 0));
+    for (int i = 0; i < n_frames; ++i) dp[i] = reinterpret_cast<const float4*>(points[i]);
+  }
+  return batch_submit(c, b, r, dp, n, n_frames, with_tracker, ts, v, yaw);
+}
+
+int lmot_batch_submit(lmot_ctx* ctx, const float* const* points, const int* n, int n_frames, int stride_floats, double timestamp_us,
+                      double v_gps, double yaw_gps) {
+  return batch_common(ctx, points, n, n_frames, stride_floats, true, true, timestamp_us, v_gps, yaw_gps);
+}
+
+int lmot_batch_dev(lmot_ctx* ctx, const float* const* d_points, const int* n, int n_frames, double timestamp_us, double v_gps, double yaw_gps) {
+  return batch_common(ctx, d_points, n, n_frames, 4, false, true, timestamp_us, v_gps, yaw_gps);
+}
+
+int lmot_batch_detect_dev(lmot_ctx* ctx, const float* const* d_points, const int* n, int n_frames) {
+  return batch_common(ctx, d_points, n, n_frames, 4, false, false, 0, 0, 0);
+}
+
+// ground removal + connected components of F device frames in two launches on the CALLER's stream (bench.py times the
+// ground_removal + CCL roofline of the batched configuration with it; results stay on the device)
+int lmot_batch_ground_ccl_dev(lmot_ctx* ctx, const float* const* d_points, const int* n, int n_frames) {
+  if (!ctx || !d_points || !n || n_frames < 1 || n_frames > kMaxBatch) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  int rc = batch_ensure(c, n_frames);
+  if (rc) return rc;
+  if (c->n_in_flight > 0 && (rc = drain(c))) return rc;
+  Slot* sl[kMaxBatch];
+  const float4* pp[kMaxBatch];
+  for (int i = 0; i < n_frames; ++i) {
+    if (n[i] < 0 || n[i] > c->max_points || (n[i] > 0 && (!d_points[i] || (reinterpret_cast<uintptr_t>(d_points[i]) & 15u)))) return LMOT_ERR_INVALID;
+    sl[i] = &c->bslots[i]; pp[i] = reinterpret_cast<const float4*>(d_points[i]);
+  }
+  sl[0]->res = &c->results[0];
+  c->results[0].n_kev = 0;
+  if ((rc = ground_launch_batch(c, sl, n_frames, pp, n, c->stream, true, false))) return rc;
+  return ccl_launch_batch(c, sl, n_frames, c->stream);
+}
+
+static int batch_fill(Ctx* c, Result* r, int rc0, lmot_batch_out* out, const lmot_frame_out& fo) {
+  if (!out) return rc0;
+  const int F = r->batch_frames;
+  out->n_frames = F;
+  for (int i = 0; i < kMaxBatch; ++i) {
+    const bool in = i < F;
+    out->n_elevated[i] = in ? r->h_frame_counts[4 * i] : 0; out->n_ground[i] = in ? r->h_frame_counts[4 * i + 1] : 0;
+    out->num_cluster[i] = in ? r->h_frame_counts[4 * i + 2] : 0; out->n_boxes[i] = in ? r->h_frame_counts[4 * i + 3] : 0;
+  }
+  out->n_boxes_total = fo.n_boxes;
+  out->tracks = fo.tracks;
+  return rc0;
+}
+
+int lmot_batch_collect(lmot_ctx* ctx, lmot_batch_out* out) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  if (c->n_in_flight <= 0) return LMOT_ERR_STATE;
+  Result* r = &c->results[c->res_oldest];
+  int guard = 0;
+  while (!r->in_flight && guard++ < c->n_results) { c->res_oldest = (c->res_oldest + 1) % c->n_results; r = &c->results[c->res_oldest]; }
+  if (!r->in_flight) return LMOT_ERR_STATE;
+  lmot_frame_out fo{};
+  if (out) { fo.boxes = out->boxes; fo.max_boxes = out->max_boxes; fo.tracks = out->tracks; }
+  const int rc = collect_result(c, r, out ? &fo : nullptr);
+  r->in_flight = false;
+  --c->n_in_flight;
+  c->res_oldest = (c->res_oldest + 1) % c->n_results;
+  return batch_fill(c, r, rc, out, fo);
+}
+
+int lmot_batch_fetch(lmot_ctx* ctx, lmot_batch_out* out) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  Result* r = c->last_res;
+  lmot_frame_out fo{};
+  if (out) { fo.boxes = out->boxes; fo.max_boxes = out->max_boxes; fo.tracks = out->tracks; }
+  const int rc = collect_result(c, r, out ? &fo : nullptr);
+  for (int i = 0; i < c->n_results; ++i) c->results[i].in_flight = false;
+  c->n_in_flight = 0;
+  c->res_oldest = c->res_next;
+  return batch_fill(c, r, rc, out, fo);
+}
+
+int lmot_batch(lmot_ctx* ctx, const float* const* points, const int* n, int n_frames, int stride_floats, double timestamp_us, double v_gps,
+               double yaw_gps, lmot_batch_out* out) {
+  if (!ctx) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  if (c->n_in_flight > 0) { int rc = drain(c); if (rc) return rc; }
+  int rc = lmot_batch_submit(ctx, points, n, n_frames, stride_floats, timestamp_us, v_gps, yaw_gps);
+  if (rc) return rc;
+  return lmot_batch_collect(ctx, out);
+}
+
 int lmot_origin_points(lmot_ctx* ctx, double timestamp_us, double v_gps, double yaw_gps, double out6[6]) {
   if (!ctx || !out6) return LMOT_ERR_INVALID;
   TrackerHost h = ctx->c.th;                       // peek: fold on a copy
@@ -842,20 +1075,26 @@ int lmot_debug_polar_grid(lmot_ctx* ctx, float* minz, float* height, float* smoo
   if (rc) return rc;
   Slot* s = &c->slots[c->last_slot];
   cudaStream_t st = c->stream;
+  // The fused kernel keeps its polar grid in shared memory, per CTA and only for the channels that CTA's points need: the four
+  // intermediate grids are recomputed here from the launch's min-z keys.  hGround / isGround come from what the fused kernel's
+  // CTAs actually USED wherever one of them evaluated the cell (stage entry points leave that in d_hg), else from the recomputation.
+  if ((rc = ground_grids_debug(c, s, st))) return rc;
   const size_t b = kPolarCells * sizeof(float);
   if (minz) LMOT_CUDA(c, cudaMemcpyAsync(minz, s->d_minz, b, cudaMemcpyDeviceToHost, st));
   if (height) LMOT_CUDA(c, cudaMemcpyAsync(height, s->d_height, b, cudaMemcpyDeviceToHost, st));
   if (smoothed) LMOT_CUDA(c, cudaMemcpyAsync(smoothed, s->d_smoothed, b, cudaMemcpyDeviceToHost, st));
   if (hdiff) LMOT_CUDA(c, cudaMemcpyAsync(hdiff, s->d_hdiff, b, cudaMemcpyDeviceToHost, st));
-  std::vector<float> hg;
+  std::vector<float> hg, hu;
   if (hground || isground) {
-    hg.resize(kPolarCells);
-    LMOT_CUDA(c, cudaMemcpyAsync(hg.data(), s->d_hg, b, cudaMemcpyDeviceToHost, st));
+    hg.resize(kPolarCells); hu.resize(kPolarCells);
+    LMOT_CUDA(c, cudaMemcpyAsync(hg.data(), s->d_hg_dbg, b, cudaMemcpyDeviceToHost, st));
+    LMOT_CUDA(c, cudaMemcpyAsync(hu.data(), s->d_hg, b, cudaMemcpyDeviceToHost, st));
   }
   LMOT_CUDA(c, cudaStreamSynchronize(st));
   for (int k = 0; k < kPolarCells && (hground || isground); ++k) {
-    const bool g = !(std::isinf(hg[k]) && hg[k] < 0);
-    if (hground) hground[k] = g ? hg[k] : 0.f;
+    const float v = std::isnan(hu[k]) ? hg[k] : hu[k];
+    const bool g = !(std::isinf(v) && v < 0);
+    if (hground) hground[k] = g ? v : 0.f;
     if (isground) isground[k] = g ? 1 : 0;
   }
   return LMOT_OK;
@@ -935,6 +1174,10 @@ int lmot_debug_phase_clock(lmot_ctx* ctx, unsigned long long* out, int cap_ctas,
     LMOT_CUDA(c, cudaMemset(c->d_phase_clock, 0, (size_t)c->fused_max_ctas * 8 * sizeof(unsigned long long)));
     LMOT_CUDA(c, cudaMalloc(&c->d_trk_trace, ((size_t)kTraceRows * 8 + 64) * sizeof(unsigned long long)));
     LMOT_CUDA(c, cudaMemset(c->d_trk_trace, 0, ((size_t)kTraceRows * 8 + 64) * sizeof(unsigned long long)));
+    LMOT_CUDA(c, cudaMalloc(&c->d_ccl_clock, (size_t)kMaxBatch * 16 * sizeof(unsigned long long)));
+    LMOT_CUDA(c, cudaMemset(c->d_ccl_clock, 0, (size_t)kMaxBatch * 16 * sizeof(unsigned long long)));
+    LMOT_CUDA(c, cudaMalloc(&c->d_fit_clock, (size_t)kFitClockCtas * 8 * sizeof(unsigned long long)));
+    LMOT_CUDA(c, cudaMemset(c->d_fit_clock, 0, (size_t)kFitClockCtas * 8 * sizeof(unsigned long long)));
     c->trk_frames = 0;
     if (n_ctas) *n_ctas = 0;
     return LMOT_OK;
@@ -942,6 +1185,24 @@ int lmot_debug_phase_clock(lmot_ctx* ctx, unsigned long long* out, int cap_ctas,
   const int g = c->last_ground_ctas < cap_ctas ? c->last_ground_ctas : cap_ctas;
   if (out && g > 0) LMOT_CUDA(c, cudaMemcpy(out, c->d_phase_clock, (size_t)g * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   if (n_ctas) *n_ctas = g;
+  return LMOT_OK;
+}
+
+// diagnostic (after the phase clock was switched on): %globaltimer stamps of the last ccl_bitmap_kernel launch (which = 1:
+// out[frames][16]) or of the last box_fit_kernel launch (which = 2: out[CTAs][8]: start, first cluster's point pass done, first
+// cluster fitted, all clusters done, end)
+int lmot_debug_stage_clocks(lmot_ctx* ctx, int which, unsigned long long* out, int cap_rows, int* n_rows, int* row_words) {
+  if (!ctx || !out || (which != 1 && which != 2)) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  int rc = lmot_sync(ctx);
+  if (rc) return rc;
+  if (!c->d_ccl_clock) return LMOT_ERR_STATE;
+  const int words = which == 1 ? 16 : 8;
+  int rows = which == 1 ? kMaxBatch : (c->last_fit_ctas < kFitClockCtas ? c->last_fit_ctas : kFitClockCtas);
+  if (rows > cap_rows) rows = cap_rows;
+  if (rows > 0) LMOT_CUDA(c, cudaMemcpy(out, which == 1 ? c->d_ccl_clock : c->d_fit_clock, (size_t)rows * words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (n_rows) *n_rows = rows;
+  if (row_words) *row_words = words;
   return LMOT_OK;
 }
 

@@ -35,10 +35,22 @@ constexpr int kColShift = 899 - 450;
 constexpr int kHullCap = 2048;
 
 // ---------------------------------------------------------------------------------------------- B1
+// One frame of a launch (blockIdx.y): every buffer the four kernels touch for it (the Slot's, see lmot_internal.cuh)
+struct FitFrame {
+  const uint16_t* cart; const int* label_grid; int* counters;
+  uint16_t* pcid; int* table; int* seg_start; int* seg_size;
+  const float4* elev; float4* sorted_pts;
+  float* cl_box; float* cl_marker; uint8_t* cl_ok;
+  float* boxes; float* markers; int* done; int* det_sem;
+};
+struct FitBatch { FitFrame f[kMaxBatch]; };
+
 __global__ void __launch_bounds__(kTile)
-tile_hist_kernel(const uint16_t* __restrict__ cart, const int* __restrict__ label_grid, const int* __restrict__ counters,
-                 uint16_t* __restrict__ pcid, int* __restrict__ table, int max_clusters) {
+tile_hist_kernel(const __grid_constant__ FitBatch B, int max_clusters) {
   extern __shared__ int s_hist[];
+  const FitFrame& F = B.f[blockIdx.y];
+  const uint16_t* __restrict__ cart = F.cart; const int* __restrict__ label_grid = F.label_grid; const int* __restrict__ counters = F.counters;
+  uint16_t* __restrict__ pcid = F.pcid; int* __restrict__ table = F.table;
   const int n = counters[CNT_N_ELEV];
   const int K = min(counters[CNT_NUM_CLUSTER], max_clusters);
   const int tile = blockIdx.x;
@@ -62,10 +74,12 @@ tile_hist_kernel(const uint16_t* __restrict__ cart, const int* __restrict__ labe
 
 // ---------------------------------------------------------------------------------------------- B2
 __global__ void __launch_bounds__(1024)
-seg_offsets_kernel(int* __restrict__ table, int* counters,
-                   int* __restrict__ seg_start, int* __restrict__ seg_size, int max_clusters, int* __restrict__ done) {
+seg_offsets_kernel(const __grid_constant__ FitBatch B, int max_clusters) {
   __shared__ int s_warp[32];
   __shared__ int s_carry;
+  const FitFrame& F = B.f[blockIdx.x];
+  int* __restrict__ table = F.table; int* counters = F.counters;
+  int* __restrict__ seg_start = F.seg_start; int* __restrict__ seg_size = F.seg_size; int* __restrict__ done = F.done;
   const int n = counters[CNT_N_ELEV];
   int K = counters[CNT_NUM_CLUSTER];
   if (threadIdx.x == 0) {
@@ -116,9 +130,11 @@ seg_offsets_kernel(int* __restrict__ table, int* counters,
 
 // ---------------------------------------------------------------------------------------------- B3
 __global__ void __launch_bounds__(kTile)
-scatter_kernel(const uint16_t* __restrict__ pcid, const float4* __restrict__ elev, const int* __restrict__ counters,
-               const int* __restrict__ table, const int* __restrict__ seg_start, float4* __restrict__ sorted_pts, int max_clusters) {
+scatter_kernel(const __grid_constant__ FitBatch B, int max_clusters) {
   extern __shared__ int s_cur[];
+  const FitFrame& F = B.f[blockIdx.y];
+  const uint16_t* __restrict__ pcid = F.pcid; const float4* __restrict__ elev = F.elev; const int* __restrict__ counters = F.counters;
+  const int* __restrict__ table = F.table; const int* __restrict__ seg_start = F.seg_start; float4* __restrict__ sorted_pts = F.sorted_pts;
   const int n = counters[CNT_N_ELEV];
   const int K = min(counters[CNT_NUM_CLUSTER], max_clusters);
   const int tile = blockIdx.x;
@@ -207,19 +223,27 @@ __device__ bool rule_filter(const float pc[4][2], float maxZ, int n, const BoxPa
   return false;
 }
 
+__device__ __forceinline__ void fit_mark(unsigned long long* clk, int slot) {
+  if (clk && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); const unsigned row = blockIdx.y * gridDim.x + blockIdx.x; if (row < (unsigned)kFitClockCtas) clk[row * 8 + slot] = t; }
+}
+
 __global__ void __launch_bounds__(kFitThreads)
-box_fit_kernel(const float4* __restrict__ sorted_pts, const int* __restrict__ seg_start,
-               const int* __restrict__ seg_size, int* __restrict__ counters, BoxParams P,
+box_fit_kernel(const __grid_constant__ FitBatch B, const __grid_constant__ BoxParams P,
                const unsigned long long* __restrict__ mt_raw, int n_raw, int max_clusters, int max_boxes,
-               float* __restrict__ cl_box, float* __restrict__ cl_marker, uint8_t* __restrict__ cl_ok,
-               float* __restrict__ boxes, float* __restrict__ markers, int* __restrict__ done, int* __restrict__ det_sem) {
+               unsigned long long* __restrict__ clk) {
+  const FitFrame& F = B.f[blockIdx.y];
+  const float4* __restrict__ sorted_pts = F.sorted_pts; const int* __restrict__ seg_start = F.seg_start; const int* __restrict__ seg_size = F.seg_size;
+  int* __restrict__ counters = F.counters;
+  float* __restrict__ cl_box = F.cl_box; float* __restrict__ cl_marker = F.cl_marker; uint8_t* __restrict__ cl_ok = F.cl_ok;
+  float* __restrict__ boxes = F.boxes; float* __restrict__ markers = F.markers; int* __restrict__ done = F.done; int* __restrict__ det_sem = F.det_sem;
   __shared__ int s_lo[kCols], s_hi[kCols];
   __shared__ short s_hx[kHullCap], s_hy[kHullCap];
   __shared__ short s_cx[kCols], s_clo[kCols], s_chi[kCols];     // occupied pixel columns, compacted
   __shared__ uint8_t s_flag8[kCols];
   __shared__ unsigned long long s_red64[kFitThreads / 32];
-  __shared__ float s_redf[kFitThreads / 32];
-  __shared__ double s_redd[kFitThreads / 32];
+  __shared__ unsigned long long s_part64[2][kFitThreads / 32];
+  __shared__ double s_partd[3][kFitThreads / 32];
+  __shared__ float s_partf[7][kFitThreads / 32];
   __shared__ int s_redi[kFitThreads / 32];
   __shared__ int s_m;                        // hull size
   __shared__ int s_best;                     // best edge
@@ -233,6 +257,7 @@ box_fit_kernel(const float4* __restrict__ sorted_pts, const int* __restrict__ se
   const float half = P.roi / 2;
   const float pic = P.pic_scale * P.roi;     // 900
 
+  fit_mark(clk, 0);
   for (int k = blockIdx.x + 1; k <= K; k += gridDim.x) {
     const int n = seg_size[k];
     const float4* seg = sorted_pts + seg_start[k];          // the cluster's points, cloud order
@@ -271,13 +296,50 @@ box_fit_kernel(const float4* __restrict__ sorted_pts, const int* __restrict__ se
       mnx = fminf(mnx, q.x); mny = fminf(mny, q.y); mnz = fminf(mnz, q.z);
       mxx = fmaxf(mxx, q.x); mxy = fmaxf(mxy, q.y); mxz = fmaxf(mxz, q.z);
     }
-    kmin = block_reduce(kmin, MinU64(), s_red64);
-    kmax = block_reduce(kmax, MaxU64(), s_red64);
-    maxZ = block_reduce(maxZ, MaxF(), s_redf);
-    sx = block_reduce(sx, AddD(), s_redd); sy = block_reduce(sy, AddD(), s_redd); sz = block_reduce(sz, AddD(), s_redd);
-    mnx = block_reduce(mnx, MinF(), s_redf); mny = block_reduce(mny, MinF(), s_redf); mnz = block_reduce(mnz, MinF(), s_redf);
-    mxx = block_reduce(mxx, MaxF(), s_redf); mxy = block_reduce(mxy, MaxF(), s_redf); mxz = block_reduce(mxz, MaxF(), s_redf);
+    // thirteen block-wide reductions as ONE: shuffles inside the warp, one exchange of the per-warp partials through shared
+    // memory, threads 0..12 fold one quantity each (26 CTA barriers before, 2 now)
+    {
+      const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xFFFFFFFFu, kmin, o), b = __shfl_xor_sync(0xFFFFFFFFu, kmax, o);
+        kmin = kmin < a ? kmin : a; kmax = kmax > b ? kmax : b;
+        maxZ = fmaxf(maxZ, __shfl_xor_sync(0xFFFFFFFFu, maxZ, o));
+        sx += __shfl_xor_sync(0xFFFFFFFFu, sx, o); sy += __shfl_xor_sync(0xFFFFFFFFu, sy, o); sz += __shfl_xor_sync(0xFFFFFFFFu, sz, o);
+        mnx = fminf(mnx, __shfl_xor_sync(0xFFFFFFFFu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xFFFFFFFFu, mny, o)); mnz = fminf(mnz, __shfl_xor_sync(0xFFFFFFFFu, mnz, o));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xFFFFFFFFu, mxx, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xFFFFFFFFu, mxy, o)); mxz = fmaxf(mxz, __shfl_xor_sync(0xFFFFFFFFu, mxz, o));
+      }
+      __syncthreads();                       // (the previous cluster's readers of s_part are done)
+      if (lane == 0) {
+        s_part64[0][warp] = kmin; s_part64[1][warp] = kmax;
+        s_partd[0][warp] = sx; s_partd[1][warp] = sy; s_partd[2][warp] = sz;
+        s_partf[0][warp] = maxZ; s_partf[1][warp] = mnx; s_partf[2][warp] = mny; s_partf[3][warp] = mnz;
+        s_partf[4][warp] = mxx; s_partf[5][warp] = mxy; s_partf[6][warp] = mxz;
+      }
+      __syncthreads();
+      constexpr int NW = kFitThreads / 32;
+      if (tid < 2) {
+        unsigned long long r = s_part64[tid][0];
+        for (int w = 1; w < NW; ++w) { const unsigned long long v = s_part64[tid][w]; r = (tid == 0) ? (r < v ? r : v) : (r > v ? r : v); }
+        s_part64[tid][0] = r;
+      } else if (tid < 5) {
+        double r = s_partd[tid - 2][0];
+        for (int w = 1; w < NW; ++w) r += s_partd[tid - 2][w];
+        s_partd[tid - 2][0] = r;
+      } else if (tid < 12) {
+        const int q = tid - 5;
+        float r = s_partf[q][0];
+        for (int w = 1; w < NW; ++w) r = (q == 0 || q >= 4) ? fmaxf(r, s_partf[q][w]) : fminf(r, s_partf[q][w]);
+        s_partf[q][0] = r;
+      }
+      __syncthreads();
+      kmin = s_part64[0][0]; kmax = s_part64[1][0];
+      sx = s_partd[0][0]; sy = s_partd[1][0]; sz = s_partd[2][0];
+      maxZ = s_partf[0][0]; mnx = s_partf[1][0]; mny = s_partf[2][0]; mnz = s_partf[3][0];
+      mxx = s_partf[4][0]; mxy = s_partf[5][0]; mxz = s_partf[6][0];
+    }
 
+    if (k == (int)blockIdx.x + 1) fit_mark(clk, 1);
     // first-occurrence min / max slope points (:268-280).  If no slope beats the 999 / -999 seeds the reference
     // reads uninitialised floats; defined here as (0,0).
     float minMx = 0.f, minMy = 0.f, maxMx = 0.f, maxMy = 0.f;
@@ -476,6 +538,7 @@ box_fit_kernel(const float4* __restrict__ sorted_pts, const int* __restrict__ se
       }
       __syncthreads();
     }
+    if (k == (int)blockIdx.x + 1) fit_mark(clk, 2);
     for (int c = 0; c < 4; ++c) { pc[c][0] = s_pc[c][0]; pc[c][1] = s_pc[c][1]; }
     const bool ok = rule_filter(pc, maxZ, n, P);
     if (tid == 0) {
@@ -493,7 +556,8 @@ box_fit_kernel(const float4* __restrict__ sorted_pts, const int* __restrict__ se
     __syncthreads();
   }
 
-  // ---- the last CTA compacts the accepted boxes in cluster-id order
+  fit_mark(clk, 3);
+  // ---- the last CTA of the frame compacts the accepted boxes in cluster-id order
   __threadfence();
   __syncthreads();
   if (tid == 0) s_flag = (atomicAdd(done, 1) == (int)gridDim.x - 1);
@@ -536,6 +600,45 @@ box_fit_kernel(const float4* __restrict__ sorted_pts, const int* __restrict__ se
     __syncthreads();
     if (tid == 0) { __threadfence(); atomicAdd(det_sem, 1); }
   }
+  fit_mark(clk, 4);
+}
+
+// batched submissions (one frame per sensor stream): the frames' box lists, concatenated in stream order, are ONE measurement
+// list for the tracker (tracking/main.cpp:98-141 unpacks whatever the trackbox message holds; one immUkfJpdaf call per tick)
+__global__ void __launch_bounds__(256)
+concat_boxes_kernel(const __grid_constant__ FitBatch B, int n_frames, int max_boxes, float* __restrict__ boxes, int* __restrict__ counters,
+                    int* __restrict__ frame_counts, int* __restrict__ det_sem) {
+  __shared__ int s_off[kMaxBatch + 1];
+  if (threadIdx.x == 0) {
+    int acc = 0, err = 0;
+    for (int f = 0; f < n_frames; ++f) {
+      s_off[f] = acc;
+      const int* fc = B.f[f].counters;
+      acc += fc[CNT_N_BOXES];
+      if (fc[CNT_ERROR]) err = fc[CNT_ERROR];
+      frame_counts[4 * f] = fc[CNT_N_ELEV]; frame_counts[4 * f + 1] = fc[CNT_N_GROUND];
+      frame_counts[4 * f + 2] = fc[CNT_NUM_CLUSTER]; frame_counts[4 * f + 3] = fc[CNT_N_BOXES];
+      B.f[f].counters[CNT_ERROR] = 0;
+    }
+    s_off[n_frames] = acc;
+    if (acc > max_boxes) err = LMOT_ERR_CAPACITY;
+    counters[CNT_N_BOXES] = acc < max_boxes ? acc : max_boxes;
+    counters[CNT_ERROR] = err;
+    // what the single-frame path reports per frame, summed over the batch (the tracker copies them into the result header)
+    int ne = 0, ng = 0, nc = 0;
+    for (int f = 0; f < n_frames; ++f) { ne += frame_counts[4 * f]; ng += frame_counts[4 * f + 1]; nc += frame_counts[4 * f + 2]; }
+    counters[CNT_N_ELEV] = ne; counters[CNT_N_GROUND] = ng; counters[CNT_NUM_CLUSTER] = nc;
+  }
+  __syncthreads();
+  for (int f = 0; f < n_frames; ++f) {
+    const int off = s_off[f], cnt = min(s_off[f + 1], max_boxes) - off;
+    const float* src = B.f[f].boxes;
+    for (int e = threadIdx.x; e < cnt * 24; e += 256) boxes[(size_t)off * 24 + e] = src[e];
+  }
+  if (det_sem) {
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(det_sem, 1); }
+  }
 }
 
 }  // namespace
@@ -550,6 +653,12 @@ int boxfit_alloc_shared(Ctx* c) {
   c->max_sort_tiles = (c->max_points + kTile - 1) / kTile;
   LMOT_CUDA(c, cudaMalloc(&c->d_mt_raw, sizeof(raw)));
   LMOT_CUDA(c, cudaMemcpy(c->d_mt_raw, raw, sizeof(raw), cudaMemcpyHostToDevice));
+  // tile_hist / scatter keep one int per cluster id in dynamic shared memory (lmot_create bounds max_clusters accordingly)
+  const int sh = (c->prm.max_clusters + 1) * (int)sizeof(int);
+  if (sh > 48 * 1024) {
+    LMOT_CUDA(c, cudaFuncSetAttribute(tile_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh));
+    LMOT_CUDA(c, cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh));
+  }
   return LMOT_OK;
 }
 
@@ -579,20 +688,30 @@ void boxfit_free(Slot* s) {
   cudaFree(s->d_done); cudaFree(s->d_det_sem);
 }
 
-// inputs: s->d_elev / CNT_N_ELEV, s->d_cart (from clustering), s->d_label_grid / CNT_NUM_CLUSTER
-int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper, bool post_sem) {
+static void fit_frame_of(const Slot* s, FitFrame& f, bool post_sem) {
+  f.cart = s->d_cart; f.label_grid = s->d_label_grid; f.counters = s->d_counters;
+  f.pcid = s->d_pcid; f.table = s->d_table; f.seg_start = s->d_seg_start; f.seg_size = s->d_seg_size;
+  f.elev = s->d_elev; f.sorted_pts = s->d_sorted_pts;
+  f.cl_box = s->d_cl_box; f.cl_marker = s->d_cl_marker; f.cl_ok = s->d_cl_ok;
+  f.boxes = s->d_boxes; f.markers = s->d_markers; f.done = s->d_done; f.det_sem = post_sem ? s->d_det_sem : nullptr;
+}
+
+// inputs per frame: s->d_elev / CNT_N_ELEV, s->d_cart (from clustering), s->d_label_grid / CNT_NUM_CLUSTER.
+// F > 1: one frame per sensor stream; the four kernels run over the union of the frames' clusters (blockIdx.y = frame).
+int boxfit_launch_batch(Ctx* c, Slot* const* slots, int F, cudaStream_t st, const int* n_upper, bool post_sem) {
+  if (F < 1 || F > kMaxBatch) return LMOT_ERR_INVALID;
   const int K1 = c->prm.max_clusters + 1;
-  const int tiles = (n_upper + kTile - 1) / kTile;
+  int tiles = 0;
+  for (int i = 0; i < F; ++i) { const int t = (n_upper[i] + kTile - 1) / kTile; if (t > tiles) tiles = t; }
   const size_t sh = (size_t)K1 * sizeof(int);
-  if (tiles > 0)
-    tile_hist_kernel<<<tiles, kTile, sh, st>>>(s->d_cart, s->d_label_grid, s->d_counters, s->d_pcid, s->d_table, c->prm.max_clusters);
-  if (tiles > 0) kernel_mark(c, s, st);
-  seg_offsets_kernel<<<1, 1024, 0, st>>>(s->d_table, s->d_counters, s->d_seg_start, s->d_seg_size, c->prm.max_clusters, s->d_done);
-  kernel_mark(c, s, st);
-  if (tiles > 0)
-    scatter_kernel<<<tiles, kTile, sh, st>>>(s->d_pcid, s->d_elev, s->d_counters, s->d_table, s->d_seg_start, s->d_sorted_pts,
-                                             c->prm.max_clusters);
-  if (tiles > 0) kernel_mark(c, s, st);
+  FitBatch B;
+  for (int i = 0; i < F; ++i) fit_frame_of(slots[i], B.f[i], post_sem && F == 1);
+  for (int i = F; i < kMaxBatch; ++i) B.f[i] = B.f[0];
+  Slot* s0 = slots[0];
+  if (tiles > 0) { tile_hist_kernel<<<dim3(tiles, F), kTile, sh, st>>>(B, c->prm.max_clusters); kernel_mark(c, s0, st); }
+  seg_offsets_kernel<<<F, 1024, 0, st>>>(B, c->prm.max_clusters);
+  kernel_mark(c, s0, st);
+  if (tiles > 0) { scatter_kernel<<<dim3(tiles, F), kTile, sh, st>>>(B, c->prm.max_clusters); kernel_mark(c, s0, st); }
   BoxParams P;
   const lmot_params& p = c->prm;
   P.roi = p.roi_m;
@@ -602,12 +721,30 @@ int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper, bool post_sem) 
   P.t_height_min = p.t_height_min; P.t_height_max = p.t_height_max; P.t_width_min = p.t_width_min; P.t_width_max = p.t_width_max;
   P.t_len_min = p.t_len_min; P.t_len_max = p.t_len_max; P.t_area_max = p.t_area_max; P.t_ratio_min = p.t_ratio_min;
   P.t_ratio_max = p.t_ratio_max; P.min_len_ratio = p.min_len_ratio; P.t_pt_per_m3 = p.t_pt_per_m3;
-  box_fit_kernel<<<c->fit_ctas, kFitThreads, 0, st>>>(s->d_sorted_pts, s->d_seg_start, s->d_seg_size, s->d_counters, P,
-                                                      c->d_mt_raw, c->n_mt_raw, c->prm.max_clusters, c->prm.max_boxes, s->d_cl_box,
-                                                      s->d_cl_marker, s->d_cl_ok, s->d_boxes, s->d_markers, s->d_done, post_sem ? s->d_det_sem : (int*)nullptr);
-  kernel_mark(c, s, st);
+  // one CTA per cluster: a frame rarely holds more than a few hundred clusters, F frames share the grid
+  const int gx = F == 1 ? c->fit_ctas : (c->fit_ctas / 2 > 8 ? c->fit_ctas / 2 : 8);
+  box_fit_kernel<<<dim3(gx, F), kFitThreads, 0, st>>>(B, P, c->d_mt_raw, c->n_mt_raw, c->prm.max_clusters, c->prm.max_boxes, c->d_fit_clock);
+  c->last_fit_ctas = gx * F;
+  kernel_mark(c, s0, st);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
+}
+
+// the frames' box lists concatenated in stream order -> d_boxes / counters of the batch (the tracker's measurement list)
+int boxes_concat_launch(Ctx* c, Slot* const* slots, int F, cudaStream_t st, float* d_boxes, int* d_counters, int* d_frame_counts, int* det_sem) {
+  FitBatch B;
+  for (int i = 0; i < F; ++i) fit_frame_of(slots[i], B.f[i], false);
+  for (int i = F; i < kMaxBatch; ++i) B.f[i] = B.f[0];
+  concat_boxes_kernel<<<1, 256, 0, st>>>(B, F, c->prm.max_boxes, d_boxes, d_counters, d_frame_counts, det_sem);
+  kernel_mark(c, slots[0], st);
+  LMOT_CUDA(c, cudaGetLastError());
+  return LMOT_OK;
+}
+
+int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper, bool post_sem) {
+  Slot* sl[1] = {s};
+  const int nu[1] = {n_upper};
+  return boxfit_launch_batch(c, sl, 1, st, nu, post_sem);
 }
 
 }  // namespace lmot

@@ -104,16 +104,52 @@ __device__ __forceinline__ unsigned piece_starts(unsigned m) { return m & ~(m <<
 // index (inside its word) of the piece that contains set bit p of word m
 __device__ __forceinline__ int piece_of(unsigned m, int p) { return __popc(piece_starts(m) & ((2u << p) - 1u)) - 1; }
 
+// One frame of a launch (blockIdx.x): bit planes in, label grid + cluster count out
+struct CclFrame {
+  unsigned* once; unsigned* twice; unsigned* prev_occ;
+  int* out;
+  int* counters;
+};
+struct CclBatch { CclFrame f[kMaxBatch]; };
+
+// pointer jumping: re-point x at its grandparent until its parent is a root.  Only the owner of x stores to L[x] here and every
+// store moves x to an ancestor, so the walks of all threads run concurrently and shorten each other: a chain of n pieces
+// (a tall object: one link per grid row) collapses in ~log2(n) rounds instead of n dependent loads per thread.
+__device__ __forceinline__ int uf_compress(volatile int* L, int x) {
+  int p = L[x];
+  while (true) {
+    const int g = L[p];
+    if (g == p) break;
+    L[x] = g;
+    p = g;
+  }
+  return p;
+}
+
+__device__ __forceinline__ void ccl_mark(unsigned long long* clk, int slot) {
+  if (clk && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); clk[blockIdx.x * 16 + slot] = t; }
+}
+
+// ONE CTA per frame, everything in shared memory:
+//   A  seed = `twice` plane; re-arm the planes          B  occupied = seed dilated 3x3
+//   C  one node per piece; its first parent is the SMALLEST neighbour it touches: the leftmost touching piece of the row above,
+//      else the piece it continues from the previous word, else itself (plain stores, no atomics: a forest, ids decrease upwards)
+//   D  pointer jumping                                  E  the remaining adjacencies (a piece touching several pieces above, or
+//      one above and one to the left) as union-find unions over the now flat forest
+//   F  pointer jumping again                            G  id = 1 + rank of the root in raster order, sparse label-grid update
 __global__ void __launch_bounds__(kCclThreads, 1)
-ccl_bitmap_kernel(unsigned* __restrict__ once, unsigned* __restrict__ twice, unsigned* __restrict__ prev_occ, int* __restrict__ out,
-                  int* __restrict__ counters) {
+ccl_bitmap_kernel(const __grid_constant__ CclBatch B, unsigned long long* __restrict__ clk) {
   extern __shared__ __align__(16) unsigned char ccl_smem[];
   int* s_par = reinterpret_cast<int*>(ccl_smem);                       // [32000] parent node, later -(cluster id) at roots
   unsigned* s_seed = reinterpret_cast<unsigned*>(s_par + kNodes);       // [2000]
   unsigned* s_occ = s_seed + kBitWords;                                 // [2000]
   unsigned* s_prev = s_occ + kBitWords;                                 // [2000]
   int* s_warp = reinterpret_cast<int*>(s_prev + kBitWords);             // [32] + total
+  const CclFrame& F = B.f[blockIdx.x];
+  unsigned* __restrict__ once = F.once; unsigned* __restrict__ twice = F.twice; unsigned* __restrict__ prev_occ = F.prev_occ;
+  int* __restrict__ out = F.out;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  ccl_mark(clk, 0);
 
   // Thread t owns the two consecutive words 2t, 2t+1 (t < 1000) in every step.
   const int w0 = 2 * tid;
@@ -128,6 +164,7 @@ ccl_bitmap_kernel(unsigned* __restrict__ once, unsigned* __restrict__ twice, uns
     reinterpret_cast<uint2*>(twice)[tid] = make_uint2(0u, 0u);
   }
   __syncthreads();
+  ccl_mark(clk, 1);
   // B: occupied = seed dilated 3x3, clipped at the border (:137-214)
   unsigned occ[2] = {0u, 0u};
   if (own) {
@@ -144,34 +181,23 @@ ccl_bitmap_kernel(unsigned* __restrict__ once, unsigned* __restrict__ twice, uns
     reinterpret_cast<uint2*>(prev_occ)[tid] = make_uint2(occ[0], occ[1]);
   }
   __syncthreads();
-  // C: one node per piece; a piece that continues the previous word's run starts as its child
+  ccl_mark(clk, 2);
+  // C: one node per piece, first parent = smallest touching neighbour.  `extra` (per word, one bit per piece): the piece has
+  // further adjacencies that step E must union.
+  unsigned extra[2] = {0u, 0u};
   if (own) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const unsigned m = occ[h];
       if (!m) continue;
-      const int w = w0 + h, k = w & 7;
-      const int np = __popc(piece_starts(m));
-      for (int j = 0; j < np; ++j) s_par[w * kPiecesPerWord + j] = w * kPiecesPerWord + j;
-      if ((m & 1u) && k > 0) {
-        const unsigned l = (h == 1) ? occ[0] : s_occ[w - 1];
-        if (l >> 31) s_par[w * kPiecesPerWord] = (w - 1) * kPiecesPerWord + __popc(piece_starts(l)) - 1;
-      }
-    }
-  }
-  __syncthreads();
-  // D: 8-connectivity to the row above: every piece of row x-1 that intersects [a-1, b+1]
-  if (own) {
-    volatile int* Lv = s_par;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const unsigned m = occ[h];
       const int w = w0 + h, x = w >> 3, k = w & 7;
-      if (!m || x == 0) continue;
-      const unsigned up = s_occ[w - kRowWords];
-      const unsigned upl = k > 0 ? s_occ[w - kRowWords - 1] : 0u;
-      const unsigned upr = k < kRowWords - 1 ? s_occ[w - kRowWords + 1] : 0u;
-      if (!(up | (upl >> 31) | (upr & 1u))) continue;
+      unsigned up = 0u, upl = 0u, upr = 0u;
+      if (x > 0) {
+        up = s_occ[w - kRowWords];
+        upl = k > 0 ? s_occ[w - kRowWords - 1] : 0u;
+        upr = k < kRowWords - 1 ? s_occ[w - kRowWords + 1] : 0u;
+      }
+      const unsigned left = (k > 0) ? ((h == 1) ? occ[0] : s_occ[w - 1]) : 0u;
       unsigned rest = m;
       int j = 0;
       while (rest) {
@@ -181,23 +207,89 @@ ccl_bitmap_kernel(unsigned* __restrict__ once, unsigned* __restrict__ twice, uns
         const unsigned pm = (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << a;
         rest &= ~pm;
         const int me = w * kPiecesPerWord + j;
-        ++j;
-        unsigned touched = up & (pm | (pm << 1) | (pm >> 1));
-        while (touched) {
-          const int p = __ffs(touched) - 1;
-          uf_union(Lv, s_par, me, (w - kRowWords) * kPiecesPerWord + piece_of(up, p));
-          const unsigned tu = ~(up >> p);
-          const int lu = tu ? __ffs(tu) - 1 : 32;
-          touched &= ~((lu >= 32 ? 0xFFFFFFFFu : ((1u << lu) - 1u)) << p);
+        int par = me, links = 0;
+        // same row: the run continues from the previous word (its last piece)
+        const bool cont = (a == 0) && (left >> 31);
+        // row above, right to left so that the LAST assignment is the leftmost (smallest id): word to the right (its first
+        // piece), the pieces of the word above, the word to the left (its last piece)
+        if (a + len == 32 && (upr & 1u)) { par = (w - kRowWords + 1) * kPiecesPerWord; ++links; }
+        const unsigned touched = up & (pm | (pm << 1) | (pm >> 1));
+        if (touched) {
+          par = (w - kRowWords) * kPiecesPerWord + piece_of(up, __ffs(touched) - 1);
+          // number of distinct pieces of `up` under `touched`: starts inside it, plus one if its lowest bit continues a piece
+          const unsigned st = piece_starts(up) & touched;
+          links += __popc(st) + (((touched & (0u - touched)) & ~piece_starts(up)) ? 1 : 0);
         }
-        if (a == 0 && (upl >> 31)) uf_union(Lv, s_par, me, (w - kRowWords - 1) * kPiecesPerWord + __popc(piece_starts(upl)) - 1);
-        if (a + len == 32 && (upr & 1u)) uf_union(Lv, s_par, me, (w - kRowWords + 1) * kPiecesPerWord);
+        if (a == 0 && (upl >> 31)) {
+          // the last piece of the word above-left; if it runs on into bit 0 of `up` it IS the first touched piece (same node
+          // reached through its continuation link): not a further adjacency
+          par = (w - kRowWords - 1) * kPiecesPerWord + __popc(piece_starts(upl)) - 1;
+          ++links;
+        }
+        if (cont) { if (links == 0) par = (w - 1) * kPiecesPerWord + __popc(piece_starts(left)) - 1; ++links; }
+        s_par[me] = par;
+        if (links > 1) extra[h] |= 1u << j;
+        ++j;
       }
     }
   }
   __syncthreads();
-  // E: flatten (read-only walks; every store of this pass is a final root, so concurrent walks stay correct),
-  // F: roots of the thread's words
+  ccl_mark(clk, 3);
+  // D: flatten the forest
+  if (own) {
+    volatile int* Lv = s_par;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int np = __popc(piece_starts(occ[h]));
+      for (int j = 0; j < np; ++j) uf_compress(Lv, (w0 + h) * kPiecesPerWord + j);
+    }
+  }
+  __syncthreads();
+  ccl_mark(clk, 4);
+  // E: the adjacencies step C did not use (all of them, for the few pieces that have more than one)
+  if (own) {
+    volatile int* Lv = s_par;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (!extra[h]) continue;
+      const unsigned m = occ[h];
+      const int w = w0 + h, x = w >> 3, k = w & 7;
+      unsigned up = 0u, upl = 0u, upr = 0u;
+      if (x > 0) {
+        up = s_occ[w - kRowWords];
+        upl = k > 0 ? s_occ[w - kRowWords - 1] : 0u;
+        upr = k < kRowWords - 1 ? s_occ[w - kRowWords + 1] : 0u;
+      }
+      const unsigned left = (k > 0) ? ((h == 1) ? occ[0] : s_occ[w - 1]) : 0u;
+      unsigned rest = m;
+      int j = 0;
+      while (rest) {
+        const int a = __ffs(rest) - 1;
+        const unsigned t = ~(rest >> a);
+        const int len = t ? __ffs(t) - 1 : 32;
+        const unsigned pm = (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << a;
+        rest &= ~pm;
+        const int me = w * kPiecesPerWord + j;
+        if ((extra[h] >> j) & 1u) {
+          unsigned touched = up & (pm | (pm << 1) | (pm >> 1));
+          while (touched) {
+            const int p = __ffs(touched) - 1;
+            uf_union(Lv, s_par, me, (w - kRowWords) * kPiecesPerWord + piece_of(up, p));
+            const unsigned tu = ~(up >> p);
+            const int lu = tu ? __ffs(tu) - 1 : 32;
+            touched &= ~((lu >= 32 ? 0xFFFFFFFFu : ((1u << lu) - 1u)) << p);
+          }
+          if (a == 0 && (upl >> 31)) uf_union(Lv, s_par, me, (w - kRowWords - 1) * kPiecesPerWord + __popc(piece_starts(upl)) - 1);
+          if (a + len == 32 && (upr & 1u)) uf_union(Lv, s_par, me, (w - kRowWords + 1) * kPiecesPerWord);
+          if (a == 0 && (left >> 31)) uf_union(Lv, s_par, me, (w - 1) * kPiecesPerWord + __popc(piece_starts(left)) - 1);
+        }
+        ++j;
+      }
+    }
+  }
+  __syncthreads();
+  ccl_mark(clk, 5);
+  // F: flatten again (the unions re-pointed some roots), count the roots of the thread's words
   int roots = 0;
   unsigned rootmask[2] = {0u, 0u};
   if (own) {
@@ -209,9 +301,8 @@ ccl_bitmap_kernel(unsigned* __restrict__ once, unsigned* __restrict__ twice, uns
       const int np = __popc(piece_starts(m));
       for (int j = 0; j < np; ++j) {
         const int nd = (w0 + h) * kPiecesPerWord + j;
-        const int r = uf_root(Lv, nd);
-        Lv[nd] = r;
-        if (r == nd) { ++roots; rootmask[h] |= 1u << j; }
+        if (Lv[nd] == nd) { ++roots; rootmask[h] |= 1u << j; }     // (roots stay roots: nobody unions any more)
+        else uf_compress(Lv, nd);
       }
     }
   }
@@ -221,13 +312,14 @@ ccl_bitmap_kernel(unsigned* __restrict__ once, unsigned* __restrict__ twice, uns
   for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
   if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
+  ccl_mark(clk, 6);
   if (warp == 0) {
     const int v = s_warp[lane];
     int wi = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += t; }
     s_warp[lane] = wi - v;
-    if (lane == 31) counters[CNT_NUM_CLUSTER] = wi;
+    if (lane == 31) F.counters[CNT_NUM_CLUSTER] = wi;
   }
   __syncthreads();
   {
@@ -239,6 +331,7 @@ ccl_bitmap_kernel(unsigned* __restrict__ once, unsigned* __restrict__ twice, uns
     }
   }
   __syncthreads();
+  ccl_mark(clk, 7);
   // G: label grid, sparse: cells occupied now get their id, cells occupied only in the previous frame are cleared
   if (own) {
 #pragma unroll
@@ -262,6 +355,7 @@ ccl_bitmap_kernel(unsigned* __restrict__ once, unsigned* __restrict__ twice, uns
       }
     }
   }
+  ccl_mark(clk, 8);
 }
 
 // ---- the cluster node's side outputs (src/cluster/main.cpp:62-99), SURVEY.md §8(f)3 ------------------------------
@@ -372,8 +466,22 @@ int cluster_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper, bool counted) 
     cart_mark_kernel<<<(n_upper + 255) / 256, 256, 0, st>>>(s->d_elev, s->d_counters, c->prm.roi_m, s->d_cart, once, twice);
     kernel_mark(c, s, st);
   }
-  ccl_bitmap_kernel<<<1, kCclThreads, kCclSmem, st>>>(once, twice, prev, s->d_label_grid, s->d_counters);
-  kernel_mark(c, s, st);
+  Slot* sl[1] = {s};
+  return ccl_launch_batch(c, sl, 1, st);
+}
+
+// connected components of F frames in one launch, one CTA per frame (the bit planes were marked by the ground kernel)
+int ccl_launch_batch(Ctx* c, Slot* const* slots, int F, cudaStream_t st) {
+  if (F < 1 || F > kMaxBatch) return LMOT_ERR_INVALID;
+  CclBatch B;
+  for (int i = 0; i < F; ++i) {
+    Slot* s = slots[i];
+    B.f[i].once = s->d_cart_bits; B.f[i].twice = s->d_cart_bits + kBitWords; B.f[i].prev_occ = s->d_cart_bits + 2 * kBitWords;
+    B.f[i].out = s->d_label_grid; B.f[i].counters = s->d_counters;
+  }
+  for (int i = F; i < kMaxBatch; ++i) B.f[i] = B.f[0];
+  ccl_bitmap_kernel<<<F, kCclThreads, kCclSmem, st>>>(B, c->d_ccl_clock);
+  kernel_mark(c, slots[0], st);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }

@@ -21,6 +21,7 @@
 //
 // Everything that decides a cell index or a label is IEEE round-to-nearest without FMA contraction, so the
 // results are bit-identical to the reference built for x86-64.
+#include <cstring>
 #include <mutex>
 #include "lmot_internal.cuh"
 #include "exact_math.cuh"
@@ -250,8 +251,8 @@ __device__ __forceinline__ void polar_grid_slice(const GroundParams& p, const un
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// grid-wide barrier of a cooperative launch (all CTAs co-resident).  The counter is never reset: launch k of a slot
-// waits for `target` = arrivals of all earlier launches + the arrivals this barrier needs (host-side bookkeeping).
+// frame-wide barrier (all CTAs of a frame co-resident).  The counter is never reset: launch k of a slot waits for
+// `target` = arrivals of all earlier launches + the arrivals this barrier needs (host-side bookkeeping).
 // diagnostic (scripts/ground_phases.py): %globaltimer of thread 0 at the phase boundaries, [CTA][8]; nullptr in production
 __device__ __forceinline__ void phase_mark(unsigned long long* clk, int slot) {
   if (clk && threadIdx.x == 0) {
@@ -266,14 +267,14 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, unsigned spin_limit) {
   __syncthreads();
   if (threadIdx.x == 0) {
     // release: the CTA's writes (ordered before this thread by the barrier above) become visible before the arrival
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
     unsigned spin = 0;
     while ((int)(ld_relaxed_u32(bar) - target) < 0)
-      if (++spin > (1u << 22)) __trap();           // a lost CTA must not hang the GPU
+      if (spin_limit && ++spin > spin_limit) __trap();   // a lost CTA must not hang the GPU (0 = wait for ever: debuggers, MPS)
     asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire: the other CTAs' writes are visible to this CTA from here on
   }
   __syncthreads();
@@ -285,19 +286,25 @@ constexpr int kMaxResTiles = 7;                     // tiles of a CTA's chunk th
 constexpr int kDescStride = 16;                     // u64 words between two CTAs' count descriptors (128 bytes)
 constexpr int kLookBatch = 5;                       // 5 x 32 >= 148 CTAs: all predecessors in one batch of loads
 constexpr int kMaxTiles = 16;                       // tiles per chunk (labels of a thread's points: 2 bits each in one register)
-// dynamic shared memory layout (bytes): fixed part, then the resident tiles, then the cell ids of every tile of the chunk.
-// The launch allocates only what its chunk length needs (a 120 k-point frame on 148 CTAs: one tile, 26 KB), so the
-// ground kernels of several frames in flight (pipeline slots, other sensor streams) can be co-resident on an SM.
+constexpr int kPendCap = 2048;                      // points of a chunk whose cell needs the exact evaluation, queued for a compact pass
+constexpr unsigned kPending = 0xFFFDu;              // cell id of a queued point until that pass has run
+constexpr int kGridPerThread = (kPolarCells + kFusedThreads - 1) / kFusedThreads;   // 10: cells of a CTA's window per thread, at most
+// dynamic shared memory layout (bytes): fixed part (incl. the CTA's private copy of the polar grid: height + ground flag of
+// every cell of the channels its points touch), then the resident tiles, then the cell ids of every tile of the chunk.
 constexpr int kOffBar = 0;                                                  // [7] mbarriers
-constexpr int kOffH = 128;                                                  // [1440] float
-constexpr int kOffCnt = kOffH + kMaxLocCells * 4;                           // [16][32] u32 elevated | ground << 16 per warp
+constexpr int kOffMeta = 64;                                                // chmask[3], npend, nch
+constexpr int kOffCnt = 128;                                                // [16][32] u32 elevated | ground << 16 per warp
 constexpr int kOffWex = kOffCnt + kMaxTiles * 32 * 4;                       // [16][32] u32 exclusive inside the tile
 constexpr int kOffTtot = kOffWex + kMaxTiles * 32 * 4;                      // [16] u32 tile totals
 constexpr int kOffBase = kOffTtot + kMaxTiles * 4;                          // [2] u32 chunk base (elevated, ground)
-constexpr int kOffG = kOffBase + 16;                                        // [1440] u8
-constexpr int kOffPts = (kOffG + kMaxLocCells + 127) & ~127;                // [res_tiles][1024] float4, then [tiles][1024] u16
+constexpr int kOffChl = kOffBase + 16;                                      // [96] u8 channels of the window (bit 7: own)
+constexpr int kOffPend = (kOffChl + 96 + 15) & ~15;                         // [kPendCap] u16
+constexpr int kOffG = kOffPend + kPendCap * 2;                              // [9600] u8
+constexpr int kOffH = (kOffG + kPolarCells + 127) & ~127;                   // [9600] float
+constexpr int kOffPts = (kOffH + kPolarCells * 4 + 127) & ~127;             // [res_tiles][1024] float4, then [tiles][1024] u16
 __host__ __device__ constexpr int fused_smem_bytes(int res_tiles, int tiles) { return kOffPts + res_tiles * kTilePts * 16 + tiles * kTilePts * 2; }
 constexpr int kFusedSmem = fused_smem_bytes(kMaxResTiles, kMaxTiles);
+static_assert(kFusedSmem <= 227 * 1024, "ground_fused_kernel: shared memory budget");
 
 struct FusedOut {
   uint8_t* labels;          // nullable
@@ -307,29 +314,85 @@ struct FusedOut {
   unsigned* cart_once;      // nullable: bit planes of the cartesian grid (cluster.cu)
   unsigned* cart_twice;
   int* counters;
+  float* dbg_hg;            // nullable (stage entry points): hGround of the cells this CTA evaluated, for lmot_debug_polar_grid
 };
 
+// one frame of a launch: CTAs [frame * ctas_per_frame, (frame + 1) * ctas_per_frame) work on it and synchronise among themselves only
+struct FrameIO {
+  const float4* pts;
+  int n, chunk;
+  unsigned* keys;           // min-z keys of this launch
+  unsigned* keys_next;      // the other grid of the slot, re-armed for its next launch
+  unsigned* bar;
+  unsigned bar_target;
+  unsigned epoch;
+  unsigned long long* desc;
+  FusedOut out;
+};
+struct GroundBatch {
+  int n_frames, ctas_per_frame;
+  unsigned spin_limit;
+  FrameIO f[kMaxBatch];
+};
+
+// the fast evaluation of polar_cell(): cell id, kNoCell (certainly outside the range window) or kPending (within the guard band
+// of a cell boundary, or not a number: the exact evaluation decides)
+__device__ __forceinline__ unsigned polar_cell_fast(float x, float y, const GroundParams& p) {
+  const float d2 = fadd(fmul(x, x), fmul(y, y));
+  const float t = __fmaf_rn(d2, rsqrtf(d2), -p.r_min) * p.bin_scale;
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float z = __fdividef(mn, mx);
+  const float u = z * z;
+  float a = 0.00782548263669014f;
+  a = __fmaf_rn(a, u, -0.03689862787723541f);
+  a = __fmaf_rn(a, u, 0.08374155312776566f);
+  a = __fmaf_rn(a, u, -0.13480405509471893f);
+  a = __fmaf_rn(a, u, 0.19879871606826782f);
+  a = __fmaf_rn(a, u, -0.3332637548446655f);
+  a = __fmaf_rn(a, u, 0.9999993443489075f);
+  a = a * z;
+  if (ay > ax) a = 1.57079632679489661923f - a;
+  if (x < 0.f) a = 3.14159265358979323846f - a;
+  if (y < 0.f) a = -a;
+  const float sc = __fmaf_rn(a, (float)(kNumChannel / 6.28318530717958647692), (float)(kNumChannel / 2));
+  if (t < -kBinGuard || t > (float)kNumBin + kBinGuard) return kNoCell;      // certainly outside (rMin, rMax)
+  const float tf = floorf(t), cf = floorf(sc);
+  const float tr = t - tf, cr = sc - cf;
+  if (!(tr > kBinGuard && tr < 1.0f - kBinGuard && cr > kChanGuard && cr < 1.0f - kChanGuard)) return kPending;
+  return (unsigned)((int)cf * kNumBin + (int)tf);
+}
+
+// ONE launch per frame -- or per batch of frames (one per sensor stream): phase 1 bins, a frame-wide barrier, then every CTA
+// evaluates the polar-grid stages for the channels ITS points fall into (plus one halo channel per side for the median filter)
+// in its own shared memory and labels its points from there: no second barrier, no round trip of the grid through L2.
 __global__ void __launch_bounds__(kFusedThreads, 1)
-ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundParams p, unsigned* __restrict__ keys,
-                    unsigned* __restrict__ keys_next, float* __restrict__ o_minz, float* __restrict__ o_height,
-                    float* __restrict__ o_smoothed, float* __restrict__ o_hdiff, float* __restrict__ o_hg, unsigned* bar,
-                    unsigned bar_base, unsigned long long* desc, unsigned epoch, FusedOut out, float roi,
+ground_fused_kernel(const __grid_constant__ GroundBatch B, const __grid_constant__ GroundParams p, float roi,
                     unsigned long long* __restrict__ phase_clock) {
   extern __shared__ __align__(128) unsigned char fsm[];
+  const int Gf = B.ctas_per_frame;
+  const int frame = blockIdx.x / Gf, cta = blockIdx.x - frame * Gf;
+  const FrameIO& F = B.f[frame];
+  const float4* __restrict__ pts = F.pts;
+  const int n = F.n, chunk = F.chunk;
+  unsigned* __restrict__ keys = F.keys;
+  const FusedOut out = F.out;
   const int T_max = (chunk + kTilePts - 1) / kTilePts;                     // tiles of a full chunk (what the launch allocated for)
   const int res_tiles = T_max < kMaxResTiles ? T_max : kMaxResTiles;
   uint64_t* s_full = reinterpret_cast<uint64_t*>(fsm + kOffBar);
-  float* s_H = reinterpret_cast<float*>(fsm + kOffH);
+  unsigned* s_meta = reinterpret_cast<unsigned*>(fsm + kOffMeta);          // [0..2] channel mask, [3] pending points, [4] window channels
   unsigned* s_cnt = reinterpret_cast<unsigned*>(fsm + kOffCnt);
   unsigned* s_wex = reinterpret_cast<unsigned*>(fsm + kOffWex);
   unsigned* s_ttot = reinterpret_cast<unsigned*>(fsm + kOffTtot);
   unsigned* s_base = reinterpret_cast<unsigned*>(fsm + kOffBase);
+  uint8_t* s_chl = fsm + kOffChl;
+  uint16_t* s_pend = reinterpret_cast<uint16_t*>(fsm + kOffPend);
   uint8_t* s_G = fsm + kOffG;
+  float* s_H = reinterpret_cast<float*>(fsm + kOffH);
   float4* s_pts = reinterpret_cast<float4*>(fsm + kOffPts);
   uint16_t* s_cell = reinterpret_cast<uint16_t*>(fsm + kOffPts + res_tiles * kTilePts * 16);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int cta = blockIdx.x, G = gridDim.x;
   const long long beg_ll = (long long)cta * chunk;
   const int beg = beg_ll < n ? (int)beg_ll : n;
   const int end = min(n, beg + chunk);
@@ -337,7 +400,7 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
   const int T = (cnt + kTilePts - 1) / kTilePts;
 
   phase_mark(phase_clock, 0);
-  // ---- phase 0: arm the TMA copies of the resident tiles; re-arm the OTHER key grid for the next frame
+  // ---- phase 0: arm the TMA copies of the resident tiles; re-arm the OTHER key grid for the slot's next frame
   if (tid == 0) {
     for (int t = 0; t < kMaxResTiles; ++t) mbar_init(&s_full[t], 1);
     fence_mbar_init();
@@ -347,70 +410,225 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
       bulk_copy_g2s(s_pts + t * kTilePts, pts + beg + t * kTilePts, bytes, &s_full[t]);
     }
   }
-  for (int k = cta * kFusedThreads + tid; k < kPolarCells; k += G * kFusedThreads) keys_next[k] = fkey(1000.f);  // Cell::Cell(): minZ = 1000
+  if (tid < 8) s_meta[tid] = 0u;
+  for (int k = cta * kFusedThreads + tid; k < kPolarCells; k += Gf * kFusedThreads) F.keys_next[k] = fkey(1000.f);  // Cell::Cell(): minZ = 1000
   __syncthreads();
 
-  // ---- phase 1: point -> polar cell, min z per cell
-  for (int t = 0; t < T; ++t) {
-    const int li = t * kTilePts + tid;
-    const bool valid = li < cnt;
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t < res_tiles) {
-      mbar_wait(&s_full[t], 0u);
-      if (valid) q = s_pts[li];
-    } else if (valid) q = __ldg(&pts[beg + li]);
-    unsigned c = kNoCell;
-    unsigned key = 0xFFFFFFFFu;
-    bool pre = false;                              // removed by the node's pre-filters (src/groundremove/main.cpp:104-112)
-    if (valid && p.prefilter)
-      pre = !(isfinite(q.x) && isfinite(q.y) && isfinite(q.z) && q.z >= p.fz0 && q.z <= p.fz1 &&   // PassThrough: inclusive
-              q.x > p.fx0 && q.x < p.fx1 && q.y > p.fy0 && q.y < p.fy1);                            // ConditionalRemoval: strict
-    if (valid && !pre) {
-      c = polar_cell(q.x, q.y, p);
-      float z = q.z;
-      if (z == 0.f) z = 0.f;                       // -0 -> +0 (`z < minZ` does not order them either)
-      if (c != kNoCell && z == z) key = fkey(z);   // NaN z never wins `z < minZ` (ground_removal.cpp:41)
+  // ---- phase 1: point -> polar cell, min z per cell.  Two tiles per iteration: two independent dependency chains per thread
+  for (int t0 = 0; t0 < T; t0 += 2) {
+    float4 q[2];
+    bool valid[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int t = t0 + u;
+      const int li = t * kTilePts + tid;
+      valid[u] = t < T && li < cnt;
+      q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < T) {
+        if (t < res_tiles) {
+          mbar_wait(&s_full[t], 0u);
+          if (valid[u]) q[u] = s_pts[li];
+        } else if (valid[u]) q[u] = __ldg(&pts[beg + li]);
+      }
     }
-    s_cell[li] = pre ? kPreFiltered : (uint16_t)c;
-    // consecutive HDL-64 returns fall into the same cell: one atomic per distinct cell per warp.  Most warps hold a single
-    // cell (32 returns of one ring span 1.5 degrees, a channel 4.5): they skip the match and reduce over the whole warp.
-    const unsigned c0 = __shfl_sync(0xFFFFFFFFu, c, 0);
-    if (__all_sync(0xFFFFFFFFu, c == c0)) {
-      const unsigned kmin = __reduce_min_sync(0xFFFFFFFFu, key);
-      if (lane == 0 && c0 != kNoCell && kmin != 0xFFFFFFFFu) atomicMin(&keys[c0], kmin);
-    } else {
-      const unsigned grp = __match_any_sync(0xFFFFFFFFu, c);
-      const unsigned kmin = __reduce_min_sync(grp, key);
-      if (c != kNoCell && lane == __ffs(grp) - 1 && kmin != 0xFFFFFFFFu) atomicMin(&keys[c], kmin);
+    unsigned c[2], key[2];
+    bool pre[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      c[u] = kNoCell;
+      key[u] = 0xFFFFFFFFu;
+      pre[u] = false;                              // removed by the node's pre-filters (src/groundremove/main.cpp:104-112)
+      if (valid[u] && p.prefilter)
+        pre[u] = !(isfinite(q[u].x) && isfinite(q[u].y) && isfinite(q[u].z) && q[u].z >= p.fz0 && q[u].z <= p.fz1 &&   // PassThrough: inclusive
+                   q[u].x > p.fx0 && q[u].x < p.fx1 && q[u].y > p.fy0 && q[u].y < p.fy1);                               // ConditionalRemoval: strict
+      if (valid[u] && !pre[u]) {
+        c[u] = polar_cell_fast(q[u].x, q[u].y, p);
+        float z = q[u].z;
+        if (z == 0.f) z = 0.f;                     // -0 -> +0 (`z < minZ` does not order them either)
+        if (z == z) key[u] = fkey(z);              // NaN z never wins `z < minZ` (ground_removal.cpp:41)
+      }
     }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int t = t0 + u;
+      if (t >= T) break;                           // (CTA-uniform)
+      const int li = t * kTilePts + tid;
+      unsigned cc = c[u];
+      // the ~1.6 per mille of points that need the exact evaluation are queued and evaluated by full warps after the loop
+      // (inline, their ~170 instructions ran with one or two active lanes and stalled the other 30)
+      const unsigned pm = __ballot_sync(0xFFFFFFFFu, cc == kPending);
+      if (pm) {
+        unsigned base = 0;
+        if (lane == __ffs(pm) - 1) base = atomicAdd(&s_meta[3], (unsigned)__popc(pm));
+        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(pm) - 1);
+        if (cc == kPending) {
+          const unsigned slot = base + __popc(pm & ((1u << lane) - 1u));
+          if (slot < (unsigned)kPendCap) s_pend[slot] = (uint16_t)li;
+          else cc = polar_cell_exact(q[u].x, q[u].y, p);       // queue full (adversarial clouds): evaluate here
+        }
+      }
+      s_cell[li] = pre[u] ? kPreFiltered : (uint16_t)cc;
+      if (cc >= (unsigned)kPolarCells) cc = kNoCell;           // pending: contributes later
+      const unsigned k = (cc == kNoCell) ? 0xFFFFFFFFu : key[u];
+      // consecutive HDL-64 returns fall into the same cell: one atomic per distinct cell per warp.  Most warps hold a single
+      // cell (32 returns of one ring span 1.5 degrees, a channel 4.5): they skip the match and reduce over the whole warp.
+      const unsigned c0 = __shfl_sync(0xFFFFFFFFu, cc, 0);
+      if (__all_sync(0xFFFFFFFFu, cc == c0)) {
+        const unsigned kmin = __reduce_min_sync(0xFFFFFFFFu, k);
+        if (lane == 0 && c0 != kNoCell) {
+          const unsigned ch = c0 / (unsigned)kNumBin;
+          atomicOr(&s_meta[ch >> 5], 1u << (ch & 31u));
+          if (kmin != 0xFFFFFFFFu) atomicMin(&keys[c0], kmin);
+        }
+      } else {
+        const unsigned grp = __match_any_sync(0xFFFFFFFFu, cc);
+        const unsigned kmin = __reduce_min_sync(grp, k);
+        if (cc != kNoCell && lane == __ffs(grp) - 1) {
+          const unsigned ch = cc / (unsigned)kNumBin;
+          atomicOr(&s_meta[ch >> 5], 1u << (ch & 31u));
+          if (kmin != 0xFFFFFFFFu) atomicMin(&keys[cc], kmin);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int np = min((int)s_meta[3], kPendCap);
+    for (int i = tid; i < np; i += kFusedThreads) {
+      const int li = s_pend[i];
+      const float4 q = ((li >> 10) < res_tiles) ? s_pts[li] : __ldg(&pts[beg + li]);
+      const unsigned cc = polar_cell_exact(q.x, q.y, p);
+      s_cell[li] = (uint16_t)cc;
+      if (cc != kNoCell) {
+        const unsigned ch = cc / (unsigned)kNumBin;
+        atomicOr(&s_meta[ch >> 5], 1u << (ch & 31u));
+        float z = q.z;
+        if (z == 0.f) z = 0.f;
+        if (z == z) atomicMin(&keys[cc], fkey(z));
+      }
+    }
+  }
+  __syncthreads();
+  // the CTA's window of the polar grid: the channels its points fall into (`own`) and one more on each side
+  if (warp == 0) {
+    const unsigned m0 = s_meta[0], m1 = s_meta[1], m2 = s_meta[2] & 0xFFFFu;
+    const unsigned n0 = m0 | (m0 << 1) | (m0 >> 1) | (m1 << 31);
+    const unsigned n1 = m1 | (m1 << 1) | (m1 >> 1) | (m0 >> 31) | (m2 << 31);
+    const unsigned n2 = (m2 | (m2 << 1) | (m2 >> 1) | (m1 >> 31)) & 0xFFFFu;
+    const unsigned need[3] = {n0, n1, n2}, own[3] = {m0, m1, m2};
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      if ((need[w] >> lane) & 1u) s_chl[base + __popc(need[w] & ((1u << lane) - 1u))] = (uint8_t)((32 * w + lane) | (((own[w] >> lane) & 1u) ? 0x80 : 0));
+      base += __popc(need[w]);
+    }
+    if (lane == 0) s_meta[4] = (unsigned)base;
   }
   phase_mark(phase_clock, 1);
-  grid_barrier(bar, bar_base + (unsigned)G);
+  grid_barrier(F.bar, F.bar_target, B.spin_limit);
   phase_mark(phase_clock, 2);
 
-  // ---- phase 2: the polar grid, channels split over the first min(G, 80) CTAs
+  // ---- phase 2: the polar-grid stages for the CTA's window, cells indexed as in the global grid (channel * 120 + bin)
   {
-    const int gc = G < kNumChannel ? G : kNumChannel;
-    if (cta < gc) {
-      const int own0 = cta * kNumChannel / gc, own1 = (cta + 1) * kNumChannel / gc;
-      polar_grid_slice(p, keys, own0, own1 - own0, s_H, s_G, o_minz, o_height, o_smoothed, o_hdiff, o_hg);
+    const int n_cells = (int)s_meta[4] * kNumBin;
+    // (a4) height clamp, ground_removal.cpp:192-197
+    for (int l = tid; l < n_cells; l += kFusedThreads) {
+      const int lc = l / kNumBin, b = l - lc * kNumBin, idx = (s_chl[lc] & 0x7F) * kNumBin + b;
+      const float zi = fkey_inv(__ldcg(&keys[idx]));
+      float h;
+      if (zi > p.t_hmin && zi < p.t_hmax) h = zi;
+      else if (zi > p.t_hmax) h = p.h_sensor;
+      else h = p.t_hmin;
+      s_H[idx] = h;
     }
+    __syncthreads();
+    // (a5) blur, (a6) hDiff, (a7) ground flag -- per channel, neighbours along bin
+    for (int l = tid; l < n_cells; l += kFusedThreads) {
+      const int lc = l / kNumBin, b = l - lc * kNumBin, idx = (s_chl[lc] & 0x7F) * kNumBin + b;
+      const float h = s_H[idx];
+      double acc = 0.0;                                       // gaus_blur.cpp:58-65, order j = i-1, i, i+1
+      if (b > 0) acc = __dadd_rn(acc, __dmul_rn(p.tap[0], (double)s_H[idx - 1]));
+      acc = __dadd_rn(acc, __dmul_rn(p.tap[1], (double)h));
+      if (b < kNumBin - 1) acc = __dadd_rn(acc, __dmul_rn(p.tap[2], (double)s_H[idx + 1]));
+      const float sm = (float)acc;
+      float hd;                                               // ground_removal.cpp:95-117
+      if (b == 0) hd = fsub(h, s_H[idx + 1]);
+      else if (b == kNumBin - 1) hd = fsub(h, s_H[idx - 1]);
+      else {
+        const float pre = fsub(h, s_H[idx - 1]), post = fsub(h, s_H[idx + 1]);
+        hd = (pre > post) ? pre : post;
+      }
+      s_G[idx] = ((sm < p.t_hmax && hd < p.t_hdiff) || (h < p.t_hmax && hd < p.t_hdiff)) ? 1 : 0;  // :205-214
+    }
+    __syncthreads();
+    // (a8) applyMedianFilter, ground_removal.cpp:120-146, own channels, IN PLACE: a cell flips only if its four neighbours
+    // are ground already, so no neighbour of a flipping cell is a candidate itself -- nobody reads what this pass writes
+    for (int l = tid; l < n_cells; l += kFusedThreads) {
+      const int lc = l / kNumBin, b = l - lc * kNumBin;
+      const int chl = s_chl[lc], ch = chl & 0x7F, idx = ch * kNumBin + b;
+      if ((chl & 0x80) && ch >= 1 && ch < kNumChannel - 1 && b >= 1 && b < kNumBin - 1 && !s_G[idx] && s_G[idx + 1] && s_G[idx - 1] &&
+          s_G[idx + kNumBin] && s_G[idx - kNumBin]) {
+        const float a = s_H[idx + 1], bb = s_H[idx - 1], c2 = s_H[idx + kNumBin], d = s_H[idx - kNumBin];
+        const float lo1 = fminf(a, bb), hi1 = fmaxf(a, bb), lo2 = fminf(c2, d), hi2 = fmaxf(c2, d);
+        const float m1 = fmaxf(lo1, lo2), m2 = fminf(hi1, hi2);  // the two middle values of the sorted four
+        s_H[idx] = fdiv(fadd(m1, m2), 2.f);
+        s_G[idx] = 1;
+      }
+    }
+    __syncthreads();
+    // (a8) outlierFilter, ground_removal.cpp:149-174: in place along bin, so cell b sees the value written at b-1.
+    // With T = tHmin, a cell is rewritten iff  A(b): all of b-1..b+2 ground, H[b]==T and (H[b+1]!=T or H[b+2]!=T),
+    // and its left value is not T -- either originally, or because b-1 was itself rewritten.  Two consecutive rewrites
+    // force H[b-1]==H[b]==T and H[b+1]!=T, which rules out a rewrite at b-2 (its b+2 is H[b]==T, its b+1 is T): the chain
+    // is at most two cells long, so every cell's final value is a closed form of the ORIGINAL H[b-2..b+2], G[b-2..b+2].
+    {
+      const float Tm = p.t_hmin;
+      float newh[kGridPerThread];
+      unsigned mod = 0;
+#pragma unroll
+      for (int j = 0; j < kGridPerThread; ++j) {
+        const int l = tid + j * kFusedThreads;
+        newh[j] = 0.f;
+        if (l < n_cells) {
+          const int lc = l / kNumBin, b = l - lc * kNumBin;
+          const int chl = s_chl[lc], ch = chl & 0x7F, idx = ch * kNumBin + b;
+          if ((chl & 0x80) && ch >= 1 && ch < kNumChannel - 1 && b >= 1 && b < kNumBin - 2 && s_G[idx] && s_G[idx + 1] && s_G[idx - 1] &&
+              s_G[idx + 2]) {
+            const float h1 = s_H[idx - 1], h2 = s_H[idx], h3 = s_H[idx + 1], h4 = s_H[idx + 2];
+            if (h2 == Tm && (h3 != Tm || h4 != Tm)) {               // A(b)
+              float left = h1;
+              bool ok = (h1 != Tm);
+              if (!ok && b - 1 >= 1 && s_G[idx - 2]) {              // was b-1 rewritten?  A(b-1) with H[b]==T needs H[b+1]!=T
+                const float h0 = s_H[idx - 2];
+                if (h3 != Tm && h0 != Tm) { left = fdiv(fadd(h0, h3), 2.f); ok = true; }   // b-1 took its second branch
+              }
+              if (ok) { newh[j] = (h3 != Tm) ? fdiv(fadd(left, h3), 2.f) : fdiv(fadd(left, h4), 2.f); mod |= 1u << j; }
+            }
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < kGridPerThread; ++j)
+        if (mod & (1u << j)) {
+          const int l = tid + j * kFusedThreads, lc = l / kNumBin, b = l - lc * kNumBin;
+          s_H[(s_chl[lc] & 0x7F) * kNumBin + b] = newh[j];
+        }
+    }
+    __syncthreads();
+    // hGround == height for every ground cell (updateGround() follows every height write of a ground cell)
+    if (out.dbg_hg)
+      for (int l = tid; l < n_cells; l += kFusedThreads) {
+        const int lc = l / kNumBin, b = l - lc * kNumBin;
+        const int chl = s_chl[lc], idx = (chl & 0x7F) * kNumBin + b;
+        if (chl & 0x80) out.dbg_hg[idx] = s_G[idx] ? s_H[idx] : -INFINITY;
+      }
   }
   phase_mark(phase_clock, 3);
-  grid_barrier(bar, bar_base + 2u * (unsigned)G);
   phase_mark(phase_clock, 4);
 
-  // ---- phase 3: labels (ground_removal.cpp:221-247), per-warp counts
+  // ---- phase 3: labels (ground_removal.cpp:221-247) from the CTA's own copy of the grid, per-warp counts
   unsigned labs = 0;                                // 2 bits per tile: 0 dropped, 1 ground, 2 elevated
-  // hGround of this thread's points in the resident tiles: all loads issued before the first is used (one L2 round trip for
-  // the whole chunk instead of one per tile)
-  float hv[kMaxResTiles];
-#pragma unroll
-  for (int t = 0; t < kMaxResTiles; ++t) {
-    hv[t] = 0.f;
-    const int li = t * kTilePts + tid;
-    if (t < T && li < cnt) { const unsigned c = s_cell[li]; if (c < kPreFiltered) hv[t] = __ldcg(&o_hg[c]); }
-  }
   for (int t = 0; t < T; ++t) {
     const int li = t * kTilePts + tid;
     int lab = 0;
@@ -419,13 +637,8 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
       if (c == kNoCell) lab = p.prefilter ? 3 : 0;      // in neither output; with the node pre-filters on: still an aux point
       else if (c != kPreFiltered) {
         const float z = (t < res_tiles) ? s_pts[li].z : __ldg(&pts[beg + li]).z;
-        float h;                                                // -inf for non-ground cells -> elevated
-        switch (t) {                                            // (register array: constant indices only)
-          case 0: h = hv[0]; break; case 1: h = hv[1]; break; case 2: h = hv[2]; break; case 3: h = hv[3]; break;
-          case 4: h = hv[4]; break; case 5: h = hv[5]; break; case 6: h = hv[6]; break;
-          default: h = __ldcg(&o_hg[c]);
-        }
-        lab = ((double)z < __dadd_rn((double)h, p.tol)) ? 1 : 2;   // :236-246
+        // hGround of a non-ground cell is never read by the reference (:236); such points are elevated
+        lab = (s_G[c] && (double)z < __dadd_rn((double)s_H[c], p.tol)) ? 1 : 2;   // :236-246
       }
     }
     labs |= (unsigned)lab << (2 * t);
@@ -445,7 +658,7 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
   }
   __syncthreads();
   if (warp == 0) {
-    // chunk totals -> published once; every CTA sums the totals of its predecessors (all CTAs are co-resident)
+    // chunk totals -> published once; every CTA sums the totals of its predecessors (all CTAs of the frame are co-resident)
     unsigned te = 0, tg = 0;
     if (lane < T) { const unsigned v = s_ttot[lane]; te = v & 0xFFFFu; tg = v >> 16; }
 #pragma unroll
@@ -453,7 +666,8 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
     // one word per CTA: launch tag (32) | elevated (16) | ground (16); a chunk holds at most 16384 points.  The words sit
     // kDescStride apart (one 128-byte line each): with all of them in ten adjacent lines, 148 CTAs polling the same
     // L2 slices serialised the whole exchange (measured: 4-6 us instead of one L2 round trip)
-    volatile unsigned long long* d = desc;
+    const unsigned epoch = F.epoch;
+    volatile unsigned long long* d = F.desc;
     if (lane == 0) d[cta * kDescStride] = ((unsigned long long)epoch << 32) | ((unsigned long long)te << 16) | tg;
     unsigned se = 0, sg = 0;
     for (int j0 = 0; j0 < cta; j0 += 32 * kLookBatch) {      // kLookBatch independent loads in flight per lane: one L2 round trip
@@ -466,7 +680,7 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
         unsigned spin = 0;
         while ((unsigned)(v[q] >> 32) != epoch) {
           v[q] = d[j * kDescStride];
-          if (++spin > (1u << 22)) __trap();
+          if (B.spin_limit && ++spin > B.spin_limit) __trap();
         }
         se += (unsigned)(v[q] >> 16) & 0xFFFFu; sg += (unsigned)v[q] & 0xFFFFu;
       }
@@ -475,7 +689,7 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
     for (int o = 16; o > 0; o >>= 1) { se += __shfl_xor_sync(0xFFFFFFFFu, se, o); sg += __shfl_xor_sync(0xFFFFFFFFu, sg, o); }
     if (lane == 0) {
       s_base[0] = se; s_base[1] = sg;
-      if (cta == G - 1) { out.counters[CNT_N_ELEV] = (int)(se + te); out.counters[CNT_N_GROUND] = (int)(sg + tg); }
+      if (cta == Gf - 1) { out.counters[CNT_N_ELEV] = (int)(se + te); out.counters[CNT_N_GROUND] = (int)(sg + tg); }
     }
   }
   __syncthreads();
@@ -509,6 +723,18 @@ ground_fused_kernel(const float4* __restrict__ pts, int n, int chunk, GroundPara
     run_e += tt & 0xFFFFu; run_g += tt >> 16;
   }
   phase_mark(phase_clock, 7);
+}
+
+// inspection only (lmot_debug_polar_grid): all five 80x120 grids of the reference from the min-z keys of the last launch, ten
+// channels per CTA.  (The fused kernel evaluates, per CTA, only the channels that CTA's points need, and keeps them in shared memory.)
+__global__ void __launch_bounds__(kFusedThreads)
+polar_grid_debug_kernel(GroundParams p, const unsigned* __restrict__ keys, float* __restrict__ o_minz, float* __restrict__ o_height,
+                        float* __restrict__ o_smoothed, float* __restrict__ o_hdiff, float* __restrict__ o_hg) {
+  __shared__ float s_H[kMaxLocCells];
+  __shared__ uint8_t s_G[kMaxLocCells];
+  const int gc = gridDim.x;
+  const int own0 = blockIdx.x * kNumChannel / gc, own1 = (blockIdx.x + 1) * kNumChannel / gc;
+  polar_grid_slice(p, keys, own0, own1 - own0, s_H, s_G, o_minz, o_height, o_smoothed, o_hdiff, o_hg);
 }
 
 // inspection only (lmot_debug_cell_index): the fused kernel keeps the cell ids in shared memory
@@ -574,7 +800,7 @@ int ground_alloc(Ctx* c, Slot* s) {
 
 void ground_free(Slot* s) {
   cudaFree(s->d_points); cudaFree(s->d_stage_in); cudaFree(s->d_cell); cudaFree(s->d_polar_key); cudaFree(s->d_minz);
-  cudaFree(s->d_height); cudaFree(s->d_smoothed); cudaFree(s->d_hdiff); cudaFree(s->d_hg); cudaFree(s->d_labels);
+  cudaFree(s->d_height); cudaFree(s->d_smoothed); cudaFree(s->d_hdiff); cudaFree(s->d_hg); cudaFree(s->d_hg_dbg); cudaFree(s->d_labels);
   cudaFree(s->d_elev); cudaFree(s->d_ground); cudaFree(s->d_gdesc); cudaFree(s->d_gbar); cudaFree(s->d_counters);
   if (s->h_counters) cudaFreeHost(s->h_counters);
   if (s->h_set) cudaFreeHost(s->h_set);
@@ -601,64 +827,99 @@ bool ground_reads_input_once(const Ctx* c, int n) {
   return (long long)cap * kMaxResTiles * kTilePts >= (long long)n;
 }
 
-int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count, bool want_labels) {
-  s->cur_points = pts;
-  s->cur_n = n;
-  // CTAs: enough that a chunk is a handful of 16 KB tiles, never fewer than kMinCtas (channel split of phase 2),
-  // never more than can be co-resident
-  int G = (n + c->pts_per_cta - 1) / c->pts_per_cta;
+// One launch for F frames (F = 1: the frame pipeline and the stage entry points; F > 1: one frame per sensor stream, api.cu
+// lmot_batch_*).  Frame i runs on slots[i]'s buffers; its CTAs are [i * G, (i + 1) * G) of the grid and synchronise among themselves.
+int ground_launch_batch(Ctx* c, Slot* const* slots, int F, const float4* const* pts, const int* n, cudaStream_t st, bool fuse_count,
+                        bool want_labels) {
+  if (F < 1 || F > kMaxBatch) return LMOT_ERR_INVALID;
+  int n_max = 0;
+  for (int i = 0; i < F; ++i) { slots[i]->cur_points = pts[i]; slots[i]->cur_n = n[i]; if (n[i] > n_max) n_max = n[i]; }
+  // CTAs per frame: enough that a chunk is a handful of 16 KB tiles, never more than can be co-resident
+  int G = (n_max + c->pts_per_cta - 1) / c->pts_per_cta;
   if (G < kMinCtas) G = kMinCtas;
-  int cap = c->fused_max_ctas;
+  int cap = c->fused_max_ctas / F;
   // Inside the frame pipeline the kernel keeps to HALF of the SMs (as long as its chunks still fit in shared memory): a
   // 1024-thread CTA holds 47 K of an SM's 64 K registers, and with the box-fitting CTAs of another frame next to it the SM has no
   // room for a CTA of the tracker chain -- measured: the last imm_predict_gate CTA started 10-15 us after the first one, the
   // sequential chain (the bound of frames/s) was 84 us per frame instead of 55.  Detection has >100 us of slack per frame.
-  if (fuse_count && c->ground_half_sms) {
+  if (F == 1 && fuse_count && c->ground_half_sms) {
     const int half = cap / 2 > kMinCtas ? cap / 2 : kMinCtas;
-    if ((long long)half * kMaxResTiles * kTilePts >= (long long)n) cap = half;
+    if ((long long)half * kMaxResTiles * kTilePts >= (long long)n_max) cap = half;
   }
+  if (cap < 1) return LMOT_ERR_CAPACITY;
   if (G > cap) G = cap;
-  int chunk = (n + G - 1) / G;
-  if (chunk > kMaxTiles * kTilePts) return LMOT_ERR_CAPACITY;
-  const int parity = (int)(s->epoch & 1u);
-  s->epoch += 1;
-  unsigned* keys = s->d_polar_key + parity * kPolarCells;
-  unsigned* keys_next = s->d_polar_key + (1 - parity) * kPolarCells;
-  FusedOut out;
-  out.labels = want_labels ? s->d_labels : nullptr;
-  out.elev = s->d_elev; out.ground = s->d_ground;
-  out.cart = fuse_count ? s->d_cart : nullptr;
-  out.cart_once = fuse_count ? s->d_cart_bits : nullptr;
-  out.cart_twice = fuse_count ? s->d_cart_bits + 2000 : nullptr;
-  out.counters = s->d_counters;
-  unsigned bar_base = s->bar_base, epoch = s->epoch;
+  GroundBatch B;
+  memset(&B, 0, sizeof(B));
+  B.n_frames = F; B.ctas_per_frame = G; B.spin_limit = c->spin_limit;
+  int chunk_max = 0;
+  for (int i = 0; i < F; ++i) {
+    Slot* s = slots[i];
+    FrameIO& f = B.f[i];
+    f.pts = pts[i]; f.n = n[i];
+    f.chunk = (n[i] + G - 1) / G;
+    if (f.chunk > kMaxTiles * kTilePts) return LMOT_ERR_CAPACITY;
+    if (f.chunk > chunk_max) chunk_max = f.chunk;
+    const int parity = (int)(s->epoch & 1u);
+    s->epoch += 1;
+    f.keys = s->d_polar_key + parity * kPolarCells;
+    f.keys_next = s->d_polar_key + (1 - parity) * kPolarCells;
+    f.bar = s->d_gbar; f.bar_target = s->bar_base + (unsigned)G;
+    f.epoch = s->epoch; f.desc = s->d_gdesc;
+    f.out.labels = want_labels ? s->d_labels : nullptr;
+    f.out.elev = s->d_elev; f.out.ground = s->d_ground;
+    f.out.cart = fuse_count ? s->d_cart : nullptr;
+    f.out.cart_once = fuse_count ? s->d_cart_bits : nullptr;
+    f.out.cart_twice = fuse_count ? s->d_cart_bits + 2000 : nullptr;
+    f.out.counters = s->d_counters;
+    f.out.dbg_hg = want_labels ? s->d_hg : nullptr;
+    s->bar_base += (unsigned)G;
+  }
+  // stage entry points: the CTAs leave hGround of the cells they evaluated in d_hg; whatever no CTA needed stays NaN (0xFF bytes)
+  if (want_labels)
+    for (int i = 0; i < F; ++i) LMOT_CUDA(c, cudaMemsetAsync(slots[i]->d_hg, 0xFF, kPolarCells * sizeof(float), st));
   float roi = c->prm.roi_m;
   GroundParams gp = c->gp;
-  void* args[] = {(void*)&pts, (void*)&n, (void*)&chunk, (void*)&gp, (void*)&keys, (void*)&keys_next, (void*)&s->d_minz,
-                  (void*)&s->d_height, (void*)&s->d_smoothed, (void*)&s->d_hdiff, (void*)&s->d_hg, (void*)&s->d_gbar,
-                  (void*)&bar_base, (void*)&s->d_gdesc, (void*)&epoch, (void*)&out, (void*)&roi, (void*)&c->d_phase_clock};
-  const int tiles = (chunk + kTilePts - 1) / kTilePts;
+  void* args[] = {(void*)&B, (void*)&gp, (void*)&roi, (void*)&c->d_phase_clock};
+  // every frame's chunk is laid out with the tile count of the longest one (the kernel derives its layout from its own chunk;
+  // a shorter chunk just leaves the tail of the allocation unused)
+  const int tiles = (chunk_max + kTilePts - 1) / kTilePts;
   const size_t smem = (size_t)fused_smem_bytes(tiles < kMaxResTiles ? tiles : kMaxResTiles, tiles > 0 ? tiles : 1);
   if (c->coop_launch) {
-    LMOT_CUDA(c, cudaLaunchCooperativeKernel((const void*)ground_fused_kernel, dim3(G), dim3(kFusedThreads), args, smem, st));
+    LMOT_CUDA(c, cudaLaunchCooperativeKernel((const void*)ground_fused_kernel, dim3(G * F), dim3(kFusedThreads), args, smem, st));
   } else {
     // Ordinary launch + the guarantee a cooperative launch would give, obtained differently.  A cooperative launch makes
     // the driver wait for an idle device, i.e. it serialises the frame pipeline's streams (measured: the detection stages of
-    // different frames stopped overlapping).  The kernel's grid barrier only needs all G CTAs to BECOME resident: G <= one
+    // different frames stopped overlapping).  The kernel's barrier only needs all G * F CTAs to BECOME resident: G * F <= one
     // CTA per SM (fused_max_ctas), every other kernel on the device terminates without waiting for this one, and ground
     // kernels never wait for each other because they are chained through one per-device event -- at most one is in flight,
     // so no two partially resident grids can starve each other.  (Several PROCESSES sharing the GPU through MPS are outside
-    // this guarantee; the barrier then traps after ~2 s instead of hanging.)
+    // this guarantee; the barrier then traps after `spin_limit` polls instead of hanging -- LMOT_SPIN_LIMIT=0 waits for ever.)
     std::lock_guard<std::mutex> lk(g_ground_mutex);
     cudaEvent_t& ev = g_ground_done[c->device & 63];
     if (!ev) LMOT_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     else LMOT_CUDA(c, cudaStreamWaitEvent(st, ev, 0));
-    LMOT_CUDA(c, cudaLaunchKernel((const void*)ground_fused_kernel, dim3(G), dim3(kFusedThreads), args, smem, st));
+    LMOT_CUDA(c, cudaLaunchKernel((const void*)ground_fused_kernel, dim3(G * F), dim3(kFusedThreads), args, smem, st));
     LMOT_CUDA(c, cudaEventRecord(ev, st));
   }
-  s->bar_base += 2u * (unsigned)G;
-  c->last_ground_ctas = G;
-  kernel_mark(c, s, st);
+  c->last_ground_ctas = G * F;
+  kernel_mark(c, slots[0], st);
+  return LMOT_OK;
+}
+
+int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count, bool want_labels) {
+  Slot* sl[1] = {s};
+  const float4* pp[1] = {pts};
+  const int nn[1] = {n};
+  return ground_launch_batch(c, sl, 1, pp, nn, st, fuse_count, want_labels);
+}
+
+// all five polar grids of the slot's LAST ground launch, recomputed from its min-z keys (inspection only)
+int ground_grids_debug(Ctx* c, Slot* s, cudaStream_t st) {
+  if (s->epoch == 0) return LMOT_ERR_STATE;
+  if (!s->d_hg_dbg) LMOT_CUDA(c, cudaMalloc(&s->d_hg_dbg, kPolarCells * sizeof(float)));
+  const unsigned* keys = s->d_polar_key + ((s->epoch - 1u) & 1u) * kPolarCells;
+  polar_grid_debug_kernel<<<kMinCtas, kFusedThreads, 0, st>>>(c->gp, keys, s->d_minz, s->d_height, s->d_smoothed, s->d_hdiff, s->d_hg_dbg);
+  LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }
 

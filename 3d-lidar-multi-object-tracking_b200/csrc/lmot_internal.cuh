@@ -16,6 +16,7 @@ constexpr int kCartCells = kNumGrid * kNumGrid;      // 62500
 constexpr uint16_t kNoCell = 0xFFFFu;
 constexpr uint16_t kPreFiltered = 0xFFFEu;           // removed by the ground node's pre-filters (never reaches groundRemove)
 constexpr int kScanTile = 1024;                      // points per tile of the stable-partition scan
+constexpr int kMaxBatch = 8;                         // frames (one per sensor stream) of one batched launch, lmot_batch_*
 
 // device-side counters of one frame (one int each; written by kernels, read by later kernels and by fetch)
 enum Counter {
@@ -69,6 +70,8 @@ constexpr int kTraceRows = 1024;      // diagnostic ring of per-frame tracker ke
 struct Result {
   int* h_hdr = nullptr;                // [16] n_elev, n_ground, num_cluster, n_boxes, n_tracks, n_vis, error
   int* h_det = nullptr;                // [CNT_COUNT] raw detection counters (detect-only submissions)
+  int* h_frame_counts = nullptr;       // [kMaxBatch][4] batched ticks: n_elev, n_ground, num_cluster, n_boxes of every frame
+  int batch_frames = 0;                // frames of the tick this block holds (0: a single-frame submission)
   float* h_boxes = nullptr;            // [max_boxes][24]
   float* h_targets = nullptr; double* h_vandyaw = nullptr; int* h_manage = nullptr;
   uint8_t* h_static = nullptr; uint8_t* h_vis = nullptr; float* h_visbb = nullptr;
@@ -110,7 +113,8 @@ struct Slot {
   float* d_height = nullptr;           // [9600]
   float* d_smoothed = nullptr;         // [9600]
   float* d_hdiff = nullptr;            // [9600]
-  float* d_hg = nullptr;               // [9600] hGround of ground cells, -inf for non-ground cells
+  float* d_hg = nullptr;               // [9600] stage entry points: hGround of the cells some CTA evaluated (-inf: not ground, NaN: nobody needed it)
+  float* d_hg_dbg = nullptr;           // [9600] the same grid recomputed as a whole by polar_grid_debug_kernel (allocated on first use)
   uint8_t* d_labels = nullptr;         // per point 0/1/2
   float4* d_elev = nullptr;            // compacted elevated cloud
   float4* d_ground = nullptr;          // compacted ground cloud
@@ -154,6 +158,8 @@ struct Slot {
 enum HostHdr { HDR_N_ELEV = 0, HDR_N_GROUND, HDR_NUM_CLUSTER, HDR_N_BOXES, HDR_N_TRACKS, HDR_N_VIS, HDR_ERROR, HDR_COUNT = 16 };
 
 constexpr int kMaxSlots = 8;
+constexpr int kFitClockCtas = 4096;                  // rows of the box-fitting phase clock (diagnostic)
+constexpr int kBatchBanks = 2;                       // batched ticks: detection of tick t+1 overlaps the tracker of tick t
 constexpr int kMaxResults = 64;
 
 struct Ctx {
@@ -172,8 +178,12 @@ struct Ctx {
   unsigned long long trk_frames = 0;
   unsigned long long* d_phase_clock = nullptr;   // diagnostic: [CTAs][8] %globaltimer stamps of the last ground launch (lmot_debug_phase_clock)
   int last_ground_ctas = 0;
+  unsigned long long* d_fit_clock = nullptr;     // diagnostic: [CTAs][8] stamps of the last box_fit_kernel launch (same switch)
+  int last_fit_ctas = 0;
+  unsigned long long* d_ccl_clock = nullptr;     // diagnostic: [frames][16] %globaltimer stamps of the last ccl_bitmap_kernel launch (same switch)
   bool zero_copy = false;              // lmot_frame_submit: pinned host frames are read by the ground kernel directly (LMOT_ZERO_COPY=1; off: slower than the copy engine)
   bool ground_half_sms = true;         // frame pipeline: ground kernel on half of the SMs (ground.cu ground_launch; LMOT_GROUND_HALF=0 disables, A/B only)
+  unsigned spin_limit = 1u << 24;      // polls after which a device-side wait traps instead of hanging the GPU (LMOT_SPIN_LIMIT, 0 = wait for ever)
   int pts_per_cta = 768;               // target chunk of the fused ground kernel (LMOT_PTS_PER_CTA overrides, tuning only)
   unsigned long long* d_mt_raw = nullptr;  // raw mt19937_64(0) outputs (shared, read only)
 
@@ -182,6 +192,10 @@ struct Ctx {
   Slot slots[kMaxSlots];
   int next_slot = 0;                   // slot of the next submission
   int last_slot = 0;                   // slot of the most recent submission (debug getters read it)
+  // ---- batched ticks (lmot_batch_*): own detection slots, kBatchBanks x batch_frames, allocated on first use
+  Slot bslots[kBatchBanks * kMaxBatch];
+  int n_bslots = 0, batch_frames = 0, next_bank = 0;
+  Slot bank[kBatchBanks];              // pseudo-slots: concatenated boxes + counters + semaphore + events of a bank
 
   // ---- result ring
   int n_results = 1;
@@ -257,18 +271,23 @@ void ground_free(Slot* s);
 // pts: device float4 array of n points; fuse_count: also bin the elevated points into the slot's cartesian count grid
 // want_labels: also write the per-point u8 label array (stage entry point); the frame pipeline skips it
 int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count = false, bool want_labels = true);
+int ground_launch_batch(Ctx* c, Slot* const* slots, int F, const float4* const* pts, const int* n, cudaStream_t st, bool fuse_count, bool want_labels);
 int ground_cells_debug(Ctx* c, Slot* s, cudaStream_t st);
+int ground_grids_debug(Ctx* c, Slot* s, cudaStream_t st);   // d_minz / d_height / d_smoothed / d_hdiff / d_hg_dbg from the last launch's keys
 bool ground_reads_input_once(const Ctx* c, int n);
 int ground_repack(Ctx* c, cudaStream_t st, const float* d_in, int n, int stride, float4* d_out);
 int cluster_alloc(Ctx* c, Slot* s);
 void cluster_free(Slot* s);
 int cluster_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper, bool counted = false);
+int ccl_launch_batch(Ctx* c, Slot* const* slots, int F, cudaStream_t st);
 int cluster_cells_only(Ctx* c, Slot* s, cudaStream_t st, int n_upper);
 int cluster_outputs_launch(Ctx* c, Slot* s, cudaStream_t st);      // makeClusteredCloud / setObsMsg / createCostMap  // d_cart for a cloud whose label grid comes from the caller
 int boxfit_alloc(Ctx* c, Slot* s);
 int boxfit_alloc_shared(Ctx* c);
 void boxfit_free(Slot* s);
 int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper, bool post_sem = false);
+int boxfit_launch_batch(Ctx* c, Slot* const* slots, int F, cudaStream_t st, const int* n_upper, bool post_sem);
+int boxes_concat_launch(Ctx* c, Slot* const* slots, int F, cudaStream_t st, float* d_boxes, int* d_counters, int* d_frame_counts, int* det_sem);
 void origin_points_fold(TrackerHost& h, double timestamp, double v_gps, double yaw_gps);
 int tracker_alloc(Ctx* c);
 void tracker_free(Ctx* c);

@@ -211,6 +211,35 @@ int lmot_ground_remove_dev(lmot_ctx* ctx, const float* d_points, int n);
 int lmot_detect_dev(lmot_ctx* ctx, const float* d_points, int n); /* ground + cluster + box, no tracker */
 int lmot_sync(lmot_ctx* ctx);
 
+/* ---- batched ticks: several sensor streams, ONE shared track table (BASELINE.json configs[3]) ------------------------------
+ * One tick = one frame from each of n_frames (<= LMOT_MAX_BATCH) sensors.  Ground removal, clustering and box fitting of all
+ * frames run as ONE launch per stage (CTA groups own frames); the frames' box lists, concatenated in stream order, are the
+ * measurement list of ONE immUkfJpdaf step -- what the reference does when one tracking node receives the boxes of several
+ * cluster nodes in one trackbox message (tracking/main.cpp:98-141,166; the monolithic callback object_tracking0/src/main.cpp:51-121
+ * per stream).  Per-frame results are identical to lmot_ground_remove / lmot_component_cluster / lmot_box_fit on that frame, the
+ * track outputs to lmot_track_step on the concatenation.  Submission / collection follow lmot_frame_submit / lmot_frame_collect
+ * (same result ring; ticks and single frames may be mixed, the tracker folds them in submission order). */
+#define LMOT_MAX_BATCH 8
+typedef struct lmot_batch_out {
+  int n_frames;                                   /* out */
+  int n_elevated[LMOT_MAX_BATCH], n_ground[LMOT_MAX_BATCH], num_cluster[LMOT_MAX_BATCH], n_boxes[LMOT_MAX_BATCH];   /* out, per frame */
+  int n_boxes_total;                              /* out: boxes in `boxes` (frame 0's first, then frame 1's, ...) */
+  float* boxes;                                   /* nullable, [max_boxes*8*3] */
+  int max_boxes;
+  lmot_track_out tracks;
+} lmot_batch_out;
+int lmot_batch_submit(lmot_ctx* ctx, const float* const* points, const int* n, int n_frames, int stride_floats, double timestamp_us,
+                      double v_gps, double yaw_gps);          /* HOST frames (pinned memory recommended) */
+int lmot_batch_dev(lmot_ctx* ctx, const float* const* d_points, const int* n, int n_frames, double timestamp_us, double v_gps,
+                   double yaw_gps);                           /* DEVICE frames, stride 4 floats, 16-byte aligned; ordered after the caller stream */
+int lmot_batch_detect_dev(lmot_ctx* ctx, const float* const* d_points, const int* n, int n_frames);   /* no tracker step */
+int lmot_batch_collect(lmot_ctx* ctx, lmot_batch_out* out);   /* oldest submitted tick */
+int lmot_batch_fetch(lmot_ctx* ctx, lmot_batch_out* out);     /* most recent tick; older uncollected results are dropped */
+int lmot_batch(lmot_ctx* ctx, const float* const* points, const int* n, int n_frames, int stride_floats, double timestamp_us,
+               double v_gps, double yaw_gps, lmot_batch_out* out);   /* submit + collect */
+/* ground removal + connected components only, two launches on the caller stream, results stay on the device (roofline measurement) */
+int lmot_batch_ground_ccl_dev(lmot_ctx* ctx, const float* const* d_points, const int* n, int n_frames);
+
 /* ---- tracker state (checkpoint / teacher-forced parity tests) ------------------------------------------ */
 int lmot_tracker_reset(lmot_ctx* ctx);
 int lmot_tracker_num_tracks(lmot_ctx* ctx, int* n);
@@ -245,6 +274,10 @@ int lmot_debug_tracker_trace(lmot_ctx* ctx, unsigned long long* out, int* next);
 /* diagnostic: first call switches on the phase clock of ground_fused_kernel; later calls return the %globaltimer stamps
  * (ns) thread 0 of every CTA took at its 8 phase boundaries during the last launch: out[n_ctas][8] */
 int lmot_debug_phase_clock(lmot_ctx* ctx, unsigned long long* out, int cap_ctas, int* n_ctas);
+
+/* diagnostic (phase clock on): %globaltimer stamps of the last ccl_bitmap_kernel (which = 1, rows = frames, 16 words each) or
+ * box_fit_kernel launch (which = 2, rows = CTAs, 8 words each) */
+int lmot_debug_stage_clocks(lmot_ctx* ctx, int which, unsigned long long* out, int cap_rows, int* n_rows, int* row_words);
 
 /* host-side self test of the bit-exact atan2f restatement against the host libm (no GPU needed) */
 int lmot_selftest_atan2f(const float* y, const float* x, int n, float* out);
