@@ -635,9 +635,10 @@ concat_boxes_kernel(const __grid_constant__ FitBatch B, int n_frames, int max_bo
     const float* src = B.f[f].boxes;
     for (int e = threadIdx.x; e < cnt * 24; e += 256) boxes[(size_t)off * 24 + e] = src[e];
   }
-  if (det_sem) {
-    __syncthreads();
-    if (threadIdx.x == 0) { __threadfence(); atomicAdd(det_sem, 1); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();                // frame_counts lives in pinned host memory: the host reads it after the tick's completion event
+    if (det_sem) atomicAdd(det_sem, 1);
   }
 }
 
