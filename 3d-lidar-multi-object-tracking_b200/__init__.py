@@ -30,6 +30,7 @@ LIB_PATH = os.path.join(HERE, "liblmot.so")
 TRACK_DUMP_DOUBLES = 236
 
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4
+WARN_TRACK_TABLE_FULL = 1
 RULE_INTENDED, RULE_GCC13_O2_COMPAT = 0, 1
 
 
@@ -91,7 +92,7 @@ ABI_SYMBOLS = [
     "lmot_ground_remove_dev", "lmot_detect_dev", "lmot_sync",
     "lmot_batch_submit", "lmot_batch_dev", "lmot_batch_detect_dev", "lmot_batch_collect", "lmot_batch_fetch", "lmot_batch", "lmot_batch_ground_ccl_dev",
     "lmot_debug_stage_clocks",
-    "lmot_origin_points", "lmot_tracker_table", "lmot_tracker_set_num_tracks", "lmot_tracker_reset", "lmot_tracker_num_tracks", "lmot_tracker_dump", "lmot_tracker_load",
+    "lmot_origin_points", "lmot_tracker_table", "lmot_tracker_set_num_tracks", "lmot_tracker_reset", "lmot_tracker_num_tracks", "lmot_tracker_dump", "lmot_tracker_load", "lmot_tracker_get_ego", "lmot_tracker_set_ego",
     "lmot_debug_polar_grid", "lmot_debug_cell_index", "lmot_debug_label_grid", "lmot_debug_phase_clock", "lmot_debug_timeline", "lmot_debug_tracker_trace", "lmot_selftest_atan2f",
     "lmot_enable_timing", "lmot_last_stage_ms", "lmot_last_kernel_ms", "lmot_debug_host_ns",
 ]
@@ -162,8 +163,9 @@ class Lmot:
             pass
 
     def _chk(self, st: int):
-        if st != OK:
+        if st < 0:
             raise LmotError(st, self.lib.lmot_strerror(st).decode() + " | " + self.lib.lmot_last_error(self.h).decode())
+        self.last_warning = st          # > 0: LMOT_WARN_* (the call's outputs are valid)
 
     def set_stream(self, cuda_stream_handle: int | None):
         self._chk(self.lib.lmot_set_stream(self.h, C.c_void_p(cuda_stream_handle or 0)))
@@ -426,6 +428,16 @@ class Lmot:
             d = np.zeros((1, TRACK_DUMP_DOUBLES), np.float64)
         self._chk(self.lib.lmot_tracker_load(self.h, d.ctypes.data_as(C.POINTER(C.c_double)), n, int(init), C.c_double(timestamp_us),
                                              C.c_double(ego_velo), C.c_double(ego_yaw), C.c_double(ego_pre_yaw), C.c_double(ego_point_yaw)))
+
+    def tracker_get_ego(self) -> np.ndarray:
+        e = np.zeros(8, np.float64)
+        self._chk(self.lib.lmot_tracker_get_ego(self.h, e.ctypes.data_as(C.POINTER(C.c_double))))
+        return e
+
+    def tracker_set_ego(self, ego8):
+        e = np.ascontiguousarray(ego8, np.float64)
+        assert e.shape == (8,)
+        self._chk(self.lib.lmot_tracker_set_ego(self.h, e.ctypes.data_as(C.POINTER(C.c_double))))
 
     def tracker_table(self):
         """-> (device pointer, bytes per track, capacity) of the track table (for NCCL broadcast, see shared_tracker.py)"""

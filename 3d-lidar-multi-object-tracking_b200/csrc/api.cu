@@ -279,7 +279,8 @@ int copy_track_outputs(const Result* s, lmot_track_out* out) {
     if (out->is_vis) memcpy(out->is_vis, s->h_vis, (size_t)n);
   }
   if (nvc > 0 && out->vis_bb) memcpy(out->vis_bb, s->h_visbb, (size_t)nvc * 24 * sizeof(float));
-  return (T > out->cap) ? LMOT_ERR_CAPACITY : LMOT_OK;
+  const bool wants = out->targets || out->vandyaw || out->track_manage || out->is_static || out->is_vis || out->vis_bb;
+  return (wants && T > out->cap) ? LMOT_ERR_CAPACITY : LMOT_OK;      // a zero-initialised lmot_track_out asks for the counts only
 }
 
 // results of a finished frame from its pinned host block
@@ -297,9 +298,10 @@ int collect_result(Ctx* c, Result* r, lmot_frame_out* out) {
   if (!r->has_tracks) {   // detect only: no kernel wrote the header
     r->h_hdr[HDR_N_ELEV] = r->h_det[CNT_N_ELEV]; r->h_hdr[HDR_N_GROUND] = r->h_det[CNT_N_GROUND];
     r->h_hdr[HDR_NUM_CLUSTER] = r->h_det[CNT_NUM_CLUSTER]; r->h_hdr[HDR_N_BOXES] = r->h_det[CNT_N_BOXES];
-    r->h_hdr[HDR_N_TRACKS] = 0; r->h_hdr[HDR_N_VIS] = 0; r->h_hdr[HDR_ERROR] = r->h_det[CNT_ERROR];
+    r->h_hdr[HDR_N_TRACKS] = 0; r->h_hdr[HDR_N_VIS] = 0; r->h_hdr[HDR_ERROR] = r->h_det[CNT_ERROR]; r->h_hdr[HDR_WARN] = 0;
   }
   const int err = r->h_hdr[HDR_ERROR];
+  const int warn = r->has_tracks ? r->h_hdr[HDR_WARN] : 0;
   if (out) {
     out->n_elevated = r->h_hdr[HDR_N_ELEV]; out->n_ground = r->h_hdr[HDR_N_GROUND];
     out->num_cluster = r->h_hdr[HDR_NUM_CLUSTER]; out->n_boxes = r->h_hdr[HDR_N_BOXES];
@@ -308,7 +310,7 @@ int collect_result(Ctx* c, Result* r, lmot_frame_out* out) {
     const int rc = copy_track_outputs(r, &out->tracks);
     if (rc && !err) return rc;
   }
-  return err ? err : LMOT_OK;
+  return err ? err : warn;      // warn > 0 (LMOT_WARN_*): the outputs are valid
 }
 
 int result_create(Ctx* c, Result* r) {
@@ -422,6 +424,7 @@ const char* lmot_strerror(int s) {
     case LMOT_ERR_CUDA: return "CUDA error (no CPU fallback exists)";
     case LMOT_ERR_CAPACITY: return "capacity exceeded";
     case LMOT_ERR_STATE: return "invalid call sequence / not available";
+    case LMOT_WARN_TRACK_TABLE_FULL: return "warning: track table full (max_tracks): unmatched boxes spawn no new track, existing tracks are still updated and reported";
     default: return "unknown status";
   }
 }
@@ -436,11 +439,14 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   lmot_params p;
   if (params) p = *params; else lmot_default_params(&p);
   if (p.max_points <= 0 || p.max_clusters <= 0 || p.max_boxes <= 0 || p.max_tracks <= 0) return LMOT_ERR_INVALID;
-  if (p.max_clusters > 65534 || p.max_boxes > 65535) return LMOT_ERR_INVALID;   // u16 cluster ids / box indices
+  if (p.max_clusters > 50000 || p.max_boxes > 65535) return LMOT_ERR_INVALID;   // u16 cluster ids / box indices; one int per cluster id in the sort kernels' shared memory (<= 200 KB)
   if (p.pipeline_depth < 1) p.pipeline_depth = 1;
   if (p.pipeline_depth > kMaxSlots) p.pipeline_depth = kMaxSlots;
   if (p.result_ring < 1) p.result_ring = 1;
   if (p.result_ring > kMaxResults) p.result_ring = kMaxResults;
+  // the frame pipeline uses up to 8 detection streams + tracker + publish stream per context; with the default of 8 hardware work
+  // queues, streams alias and serialise each other.  Only effective if this process has not created its CUDA context yet.
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return LMOT_ERR_CUDA;
   if (cudaSetDevice(device) != cudaSuccess) return LMOT_ERR_CUDA;
@@ -548,8 +554,9 @@ int lmot_flush(lmot_ctx* ctx) {
 
 // ---------------------------------------------------------------------------------------------- stage entry points
 int lmot_ground_remove_dev(lmot_ctx* ctx, const float* d_points, int n) {
-  if (!ctx || n < 0 || (n > 0 && !d_points)) return LMOT_ERR_INVALID;
+  if (!ctx || n < 0 || (n > 0 && !d_points) || (reinterpret_cast<uintptr_t>(d_points) & 15u)) return LMOT_ERR_INVALID;   // cp.async.bulk: 16-byte aligned
   Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
   if (n > c->max_points) return LMOT_ERR_CAPACITY;
   if (c->n_in_flight > 0) { int rc = drain(c); if (rc) return rc; }     // slot 0 may still be busy with a pipelined frame
   Slot* s = &c->slots[0];
@@ -701,13 +708,14 @@ int lmot_track_step(lmot_ctx* ctx, const float* boxes, int m, double timestamp_u
   }
   const int err = s->res->h_hdr[HDR_ERROR];
   rc = copy_track_outputs(s->res, out);
-  return err ? err : rc;
+  return err ? err : (rc ? rc : s->res->h_hdr[HDR_WARN]);
 }
 
 // ---------------------------------------------------------------------------------------------- frame pipeline
 int lmot_detect_dev(lmot_ctx* ctx, const float* d_points, int n) {
-  if (!ctx || n < 0 || (n > 0 && !d_points)) return LMOT_ERR_INVALID;
+  if (!ctx || n < 0 || (n > 0 && !d_points) || (reinterpret_cast<uintptr_t>(d_points) & 15u)) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
   if (n > c->max_points) return LMOT_ERR_CAPACITY;
   Slot* s = acquire_slot(c);
   Result* r = acquire_result(c, true);
@@ -717,8 +725,9 @@ int lmot_detect_dev(lmot_ctx* ctx, const float* d_points, int n) {
 }
 
 int lmot_frame_dev(lmot_ctx* ctx, const float* d_points, int n, double timestamp_us, double v_gps, double yaw_gps) {
-  if (!ctx || n < 0 || (n > 0 && !d_points)) return LMOT_ERR_INVALID;
+  if (!ctx || n < 0 || (n > 0 && !d_points) || (reinterpret_cast<uintptr_t>(d_points) & 15u)) return LMOT_ERR_INVALID;
   Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
   if (n > c->max_points) return LMOT_ERR_CAPACITY;
   Slot* s = acquire_slot(c);
   Result* r = acquire_result(c, true);
@@ -1063,6 +1072,30 @@ int lmot_tracker_load(lmot_ctx* ctx, const double* dumps, int n, int init, doubl
   c->th = TrackerHost();
   c->th.init = init != 0; c->th.timestamp = timestamp_us; c->th.egoVelo = ego_velo; c->th.egoYaw = ego_yaw;
   c->th.egoPreYaw = ego_pre_yaw; c->th.egoPoint[2] = ego_point_yaw;
+  // (like the oracle's ref_tracker_load, which clears egoDeltaHis_: the dead-reckoning fold restarts from (0, 0, -pi/2) and
+  //  ego_point_yaw is only egoPoints_[0][2] until the next step recomputes it.  A checkpoint that must keep the accumulated ego
+  //  pose restores it with lmot_tracker_set_ego.)
+  return LMOT_OK;
+}
+
+// the frame-level scalars of getOriginPoints / immUkfJpdaf (imm_ukf_jpda.cpp:19-24,56-58) incl. the accumulated dead-reckoning pose
+int lmot_tracker_get_ego(lmot_ctx* ctx, double ego8[8]) {
+  if (!ctx || !ego8) return LMOT_ERR_INVALID;
+  const TrackerHost& h = ctx->c.th;
+  ego8[0] = h.init ? 1.0 : 0.0; ego8[1] = h.timestamp; ego8[2] = h.egoVelo; ego8[3] = h.egoYaw; ego8[4] = h.egoPreYaw;
+  ego8[5] = h.fold[0]; ego8[6] = h.fold[1]; ego8[7] = h.fold[2];
+  return LMOT_OK;
+}
+
+int lmot_tracker_set_ego(lmot_ctx* ctx, const double ego8[8]) {
+  if (!ctx || !ego8) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  int rc = drain(c);
+  if (rc) return rc;
+  TrackerHost& h = c->th;
+  h.init = ego8[0] != 0.0; h.timestamp = ego8[1]; h.egoVelo = ego8[2]; h.egoYaw = ego8[3]; h.egoPreYaw = ego8[4];
+  h.fold[0] = ego8[5]; h.fold[1] = ego8[6]; h.fold[2] = ego8[7];
+  h.egoPoint[0] = h.fold[0]; h.egoPoint[1] = h.fold[1]; h.egoPoint[2] = h.fold[2];
   return LMOT_OK;
 }
 

@@ -280,21 +280,30 @@ box_fit_kernel(const __grid_constant__ FitBatch B, const __grid_constant__ BoxPa
     float maxZ = -99.f;
     double sx = 0, sy = 0, sz = 0;
     float mnx = FLT_MAX, mny = FLT_MAX, mnz = FLT_MAX, mxx = -FLT_MAX, mxy = -FLT_MAX, mxz = -FLT_MAX;
-    for (int j = tid; j < n; j += kFitThreads) {
-      const float4 q = __ldg(&seg[j]);
-      const int x = (int)floorf((q.x + half) * P.pic_scale);
-      const int y = (int)floorf((q.y + half) * P.pic_scale);
-      const int picX = x, picY = (int)(pic - (float)y);
-      const int offX = picX + offsetInitX, offY = picY + offsetInitY;
-      const int col = offX + kColShift;
-      if (col >= 0 && col < kCols) { atomicMin(&s_lo[col], offY); atomicMax(&s_hi[col], offY); }
-      const float m = q.y / q.x;
-      if (m < 999.f) { const unsigned long long key = ((unsigned long long)okey(m) << 32) | (unsigned)j; kmin = kmin < key ? kmin : key; }
-      if (m > -999.f) { const unsigned long long key = ((unsigned long long)okey(m) << 32) | (0xFFFFFFFFu - (unsigned)j); kmax = kmax > key ? kmax : key; }
-      if (q.z > maxZ) maxZ = q.z;
-      sx += q.x; sy += q.y; sz += q.z;
-      mnx = fminf(mnx, q.x); mny = fminf(mny, q.y); mnz = fminf(mnz, q.z);
-      mxx = fmaxf(mxx, q.x); mxy = fmaxf(mxy, q.y); mxz = fmaxf(mxz, q.z);
+    // four points per thread in flight: as a plain loop this was one L2 round trip per iteration (18 us for a 5000-point cluster)
+    for (int j0 = tid; j0 < n; j0 += 4 * kFitThreads) {
+      float4 qq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int j = j0 + u * kFitThreads; qq[u] = (j < n) ? __ldg(&seg[j]) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * kFitThreads;
+        if (j >= n) break;
+        const float4 q = qq[u];
+        const int x = (int)floorf((q.x + half) * P.pic_scale);
+        const int y = (int)floorf((q.y + half) * P.pic_scale);
+        const int picX = x, picY = (int)(pic - (float)y);
+        const int offX = picX + offsetInitX, offY = picY + offsetInitY;
+        const int col = offX + kColShift;
+        if (col >= 0 && col < kCols) { atomicMin(&s_lo[col], offY); atomicMax(&s_hi[col], offY); }
+        const float m = q.y / q.x;
+        if (m < 999.f) { const unsigned long long key = ((unsigned long long)okey(m) << 32) | (unsigned)j; kmin = kmin < key ? kmin : key; }
+        if (m > -999.f) { const unsigned long long key = ((unsigned long long)okey(m) << 32) | (0xFFFFFFFFu - (unsigned)j); kmax = kmax > key ? kmax : key; }
+        if (q.z > maxZ) maxZ = q.z;
+        sx += q.x; sy += q.y; sz += q.z;
+        mnx = fminf(mnx, q.x); mny = fminf(mny, q.y); mnz = fminf(mnz, q.z);
+        mxx = fmaxf(mxx, q.x); mxy = fmaxf(mxy, q.y); mxz = fmaxf(mxz, q.z);
+      }
     }
     // thirteen block-wide reductions as ONE: shuffles inside the warp, one exchange of the per-warp partials through shared
     // memory, threads 0..12 fold one quantity each (26 CTA barriers before, 2 now)

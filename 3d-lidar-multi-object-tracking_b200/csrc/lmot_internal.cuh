@@ -155,7 +155,7 @@ struct Slot {
   struct Result* res = nullptr;        // result block of the frame currently (or last) processed on this slot
 };
 
-enum HostHdr { HDR_N_ELEV = 0, HDR_N_GROUND, HDR_NUM_CLUSTER, HDR_N_BOXES, HDR_N_TRACKS, HDR_N_VIS, HDR_ERROR, HDR_COUNT = 16 };
+enum HostHdr { HDR_N_ELEV = 0, HDR_N_GROUND, HDR_NUM_CLUSTER, HDR_N_BOXES, HDR_N_TRACKS, HDR_N_VIS, HDR_ERROR, HDR_WARN, HDR_COUNT = 16 };
 
 constexpr int kMaxSlots = 8;
 constexpr int kFitClockCtas = 4096;                  // rows of the box-fitting phase clock (diagnostic)

@@ -174,14 +174,14 @@ __device__ void ukf_initialize(TrackState& t, double zx, double zy) {   // UKF::
 // still outside this stream: a ground kernel that needs every one of its CTAs co-resident could starve), then waits for the
 // previous tracker step.  TA's own griddepcontrol.wait returns when this kernel has completed, i.e. when both (a) and (b) hold.
 __global__ void __launch_bounds__(32)
-tracker_gate_kernel(const int* __restrict__ det_sem, unsigned long long* __restrict__ phase) {
+tracker_gate_kernel(const int* __restrict__ det_sem, unsigned long long* __restrict__ phase, unsigned spin_limit) {
   if (phase && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); phase[26] = t; }
   if (threadIdx.x == 0) {
     unsigned spin = 0;
     int v;
     do {
       asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(det_sem) : "memory");
-      if (++spin > (1u << 22)) __trap();       // detection never finished (seconds): fail loudly instead of hanging the stream
+      if (spin_limit && ++spin > spin_limit) __trap();       // detection never finished (seconds): fail loudly instead of hanging the stream (0: wait for ever)
     } while (v < 1);
   }
   __syncwarp();
@@ -1364,7 +1364,8 @@ __device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict_
   if (tid == 0) {
     trk[CNT_N_TRACKS] = T; trk[CNT_N_VIS] = nv; trk[CNT_N_ACT] = n_keep + (T - T0);
     o.hdr[HDR_N_ELEV] = hdr_in[0]; o.hdr[HDR_N_GROUND] = hdr_in[1]; o.hdr[HDR_NUM_CLUSTER] = hdr_in[2];
-    o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = nv; o.hdr[HDR_ERROR] = (T0 + S.carry > max_tracks) ? (int)LMOT_ERR_CAPACITY : hdr_in[3];
+    o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = nv; o.hdr[HDR_ERROR] = hdr_in[3];
+    o.hdr[HDR_WARN] = (T0 + S.carry > max_tracks) ? (int)LMOT_WARN_TRACK_TABLE_FULL : 0;   // existing tracks' outputs stay valid: a warning, not an error
     det[CNT_ERROR] = 0;
     trace_end(trace, 2);
     mark(9);
@@ -1428,7 +1429,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
       }
       trk[CNT_N_TRACKS] = T; trk[CNT_N_VIS] = 0; trk[CNT_N_ACT] = T; act_list[0] = 0;
       o.hdr[HDR_N_ELEV] = det[CNT_N_ELEV]; o.hdr[HDR_N_GROUND] = det[CNT_N_GROUND]; o.hdr[HDR_NUM_CLUSTER] = det[CNT_NUM_CLUSTER];
-      o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = 0; o.hdr[HDR_ERROR] = det[CNT_ERROR];
+      o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = 0; o.hdr[HDR_ERROR] = det[CNT_ERROR]; o.hdr[HDR_WARN] = 0;
       det[CNT_ERROR] = 0;
     }
     for (int b = tid; b < M; b += kTCThreads) first_setter[b] = INT_MAX;
@@ -1582,7 +1583,8 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
     __syncthreads();
   }
   int T = T0 + s_carry;
-  if (T > max_tracks) { if (tid == 0) det[CNT_ERROR] = LMOT_ERR_CAPACITY; T = max_tracks; }
+  const int table_full = (T > max_tracks) ? 1 : 0;      // boxes beyond the table's capacity spawn no track (warning; every existing track is still updated and emitted)
+  if (T > max_tracks) T = max_tracks;
   __syncthreads();
   if (tid == 0) s_carry = 0;
   __syncthreads();
@@ -1618,6 +1620,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
     trk[CNT_N_TRACKS] = T; trk[CNT_N_VIS] = s_carry; trk[CNT_N_ACT] = s_carry2;
     o.hdr[HDR_N_ELEV] = det[CNT_N_ELEV]; o.hdr[HDR_N_GROUND] = det[CNT_N_GROUND]; o.hdr[HDR_NUM_CLUSTER] = det[CNT_NUM_CLUSTER];
     o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = s_carry; o.hdr[HDR_ERROR] = det[CNT_ERROR];
+    o.hdr[HDR_WARN] = table_full ? (int)LMOT_WARN_TRACK_TABLE_FULL : 0;
     det[CNT_ERROR] = 0;
     trace_end(trace, 2);
   }
@@ -1634,13 +1637,13 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, size_t bytes,
 
 constexpr int kPubThreads = 128;    // small on purpose: it may sit on an SM polling while detection kernels need that SM's registers
 __global__ void __launch_bounds__(kPubThreads)
-publish_kernel(OutPtrs d, OutPtrs h, const unsigned* __restrict__ tc_seq, unsigned want) {
+publish_kernel(OutPtrs d, OutPtrs h, const unsigned* __restrict__ tc_seq, unsigned want, unsigned spin_limit) {
   const int tid = threadIdx.x;
   if (tid == 0) {              // wait until `want` tracker steps have completed (spawn_output_kernel counts them)
     unsigned spin = 0, v;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(tc_seq) : "memory");
-      if (++spin > (1u << 23)) __trap();
+      if (spin_limit && ++spin > spin_limit) __trap();
     } while ((int)(v - want) < 0);
   }
   __syncthreads();
@@ -1786,7 +1789,7 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
       if (use_gate) {
         cudaLaunchConfig_t gc = {};
         gc.gridDim = dim3(1); gc.blockDim = dim3(32); gc.dynamicSmemBytes = 0; gc.stream = st; gc.attrs = &pa; gc.numAttrs = 1;
-        LMOT_CUDA(c, cudaLaunchKernelEx(&gc, tracker_gate_kernel, (const int*)det_sem, phase));
+        LMOT_CUDA(c, cudaLaunchKernelEx(&gc, tracker_gate_kernel, (const int*)det_sem, phase, c->spin_limit));
       }
       cudaLaunchConfig_t ac = {};
       ac.gridDim = dim3(c->trk_ctas); ac.blockDim = dim3(kTAThreads); ac.dynamicSmemBytes = 0; ac.stream = st; ac.attrs = &pa; ac.numAttrs = 1;
@@ -1833,7 +1836,7 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
 int tracker_publish(Ctx* c, Result* r, cudaStream_t st) {
   OutPtrs d{r->d_targets, r->d_vandyaw, r->d_manage, r->d_static, r->d_vis, r->d_visbb, r->d_hdr, r->d_boxes};
   OutPtrs h{r->h_targets, r->h_vandyaw, r->h_manage, r->h_static, r->h_vis, r->h_visbb, r->h_hdr, r->h_boxes};
-  publish_kernel<<<1, kPubThreads, 0, st>>>(d, h, c->d_tc_seq, c->tc_launched);
+  publish_kernel<<<1, kPubThreads, 0, st>>>(d, h, c->d_tc_seq, c->tc_launched, c->spin_limit);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }

@@ -49,7 +49,7 @@ int main(int argc, char** argv) {
   out.tracks.is_static = is_static.data(); out.tracks.is_vis = is_vis.data(); out.tracks.vis_bb = visbb.data();
 
   for (int i = 0; i < W; ++i)
-    if ((rc = lmot_frame(ctx, frames + (size_t)i * frame_floats, np, 4, (i + 1) * dt_us, 0.0, 0.0, &out))) { fprintf(stderr, "lmot_frame: %s (%s)\n", lmot_strerror(rc), lmot_last_error(ctx)); return 5; }
+    if ((rc = lmot_frame(ctx, frames + (size_t)i * frame_floats, np, 4, (i + 1) * dt_us, 0.0, 0.0, &out)) < 0) { fprintf(stderr, "lmot_frame: %s (%s)\n", lmot_strerror(rc), lmot_last_error(ctx)); return 5; }
   lmot_sync(ctx);
 
   const int depth = prm.result_ring - 1;       // frames the host may be ahead of the results it has read back
@@ -60,16 +60,16 @@ int main(int argc, char** argv) {
   for (int i = W; i < W + K; ++i) {
     if (in_flight == depth) {
       const double a = now_s();
-      if ((rc = lmot_frame_collect(ctx, &out))) { fprintf(stderr, "collect: %s (%s)\n", lmot_strerror(rc), lmot_last_error(ctx)); return 6; }
+      if ((rc = lmot_frame_collect(ctx, &out)) < 0) { fprintf(stderr, "collect: %s (%s)\n", lmot_strerror(rc), lmot_last_error(ctx)); return 6; }
       t_collect += now_s() - a; ++collected; --in_flight; sum_tracks += out.tracks.n_tracks; sum_boxes += out.n_boxes;
     }
     const double a = now_s();
-    if ((rc = lmot_frame_submit(ctx, frames + (size_t)i * frame_floats, np, 4, (i + 1) * dt_us, 0.0, 0.0))) { fprintf(stderr, "submit: %s (%s)\n", lmot_strerror(rc), lmot_last_error(ctx)); return 6; }
+    if ((rc = lmot_frame_submit(ctx, frames + (size_t)i * frame_floats, np, 4, (i + 1) * dt_us, 0.0, 0.0)) < 0) { fprintf(stderr, "submit: %s (%s)\n", lmot_strerror(rc), lmot_last_error(ctx)); return 6; }
     t_submit += now_s() - a; ++in_flight;
   }
   while (in_flight > 0) {
     const double a = now_s();
-    if ((rc = lmot_frame_collect(ctx, &out))) { fprintf(stderr, "collect: %s (%s)\n", lmot_strerror(rc), lmot_last_error(ctx)); return 6; }
+    if ((rc = lmot_frame_collect(ctx, &out)) < 0) { fprintf(stderr, "collect: %s (%s)\n", lmot_strerror(rc), lmot_last_error(ctx)); return 6; }
     t_collect += now_s() - a; ++collected; --in_flight; sum_tracks += out.tracks.n_tracks; sum_boxes += out.n_boxes;
   }
   lmot_sync(ctx);

@@ -16,7 +16,7 @@
  *                              one callback (device-resident between stages, one H2D and one D2H per frame)
  *
  * Conventions: plain pointers and sizes, caller-owned buffers, no C++/torch types.  Every function returns
- * LMOT_OK (0) or a negative lmot_status.  A context owns one CUDA device, one stream and all scratch memory;
+ * LMOT_OK (0), a negative status (error), or a positive one (warning: the outputs are valid).  A context owns one CUDA device, one stream and all scratch memory;
  * it is NOT thread-safe (the reference's functions are non-re-entrant too); use one context per sensor stream.
  * There is no CPU fallback: without a usable CUDA device lmot_create fails with LMOT_ERR_CUDA.
  *
@@ -44,7 +44,12 @@ typedef enum lmot_status {
   LMOT_ERR_INVALID = -1,   /* bad argument */
   LMOT_ERR_CUDA = -2,      /* CUDA runtime/driver error, or no device (there is no CPU fallback) */
   LMOT_ERR_CAPACITY = -3,  /* input exceeds a capacity fixed at lmot_create (points, clusters, boxes, tracks) */
-  LMOT_ERR_STATE = -4      /* call sequence error (e.g. fetch before run) */
+  LMOT_ERR_STATE = -4,     /* call sequence error (e.g. fetch before run) */
+  /* positive = warning: the call did its work and every output is valid */
+  LMOT_WARN_TRACK_TABLE_FULL = 1   /* max_tracks tracks exist (dead ones keep their slot, like the reference's targets_): boxes no track
+                                      matched spawn no new track this frame; existing tracks are updated and reported as usual.  At the
+                                      default 8192 and ~3 spawns per frame that is ~4.5 min of a 10 Hz stream; size max_tracks for the
+                                      session (1.6 KB of device memory per track) or call lmot_tracker_reset between sequences. */
 } lmot_status;
 
 /* ruleBasedFilter (box_fitting.cpp:97-158) falls off its end without a return when a nested size check fails:
@@ -247,6 +252,12 @@ int lmot_tracker_num_tracks(lmot_ctx* ctx, int* n);
 int lmot_tracker_dump(lmot_ctx* ctx, double* dumps, int cap, int* n);
 int lmot_tracker_load(lmot_ctx* ctx, const double* dumps, int n, int init, double timestamp_us, double ego_velo,
                       double ego_yaw, double ego_pre_yaw, double ego_point_yaw);
+/* The frame-level state of getOriginPoints (imm_ukf_jpda.cpp:74-172), i.e. the other half of a checkpoint:
+ * ego8 = {init, timestamp_us, egoVelo, egoYaw, egoPreYaw, x, y, yaw of the accumulated dead-reckoning pose}.
+ * lmot_tracker_load restarts the dead reckoning at (0, 0, -pi/2) like the test oracle does; call lmot_tracker_set_ego AFTER it to
+ * continue a sequence with a moving ego exactly where lmot_tracker_get_ego left it. */
+int lmot_tracker_get_ego(lmot_ctx* ctx, double ego8[8]);
+int lmot_tracker_set_ego(lmot_ctx* ctx, const double ego8[8]);
 
 /* Device view of the track table for multi-GPU use (several sensor streams feeding ONE tracker): the owner
  * rank broadcasts `bytes_per_track * n` bytes from *dev_ptr with NCCL, the other ranks receive into their own table and

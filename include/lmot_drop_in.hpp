@@ -45,7 +45,7 @@ inline lmot_ctx* context(const lmot_params* params = nullptr, int device = 0) {
 inline void shutdown() { lmot_ctx*& ctx = context_slot(); if (ctx) { lmot_destroy(ctx); ctx = nullptr; } }
 
 inline void check(int rc, const char* what) {
-  if (rc != LMOT_OK) throw std::runtime_error(std::string(what) + ": " + lmot_strerror(rc) + " | " + lmot_last_error(context_slot()));
+  if (rc < 0) throw std::runtime_error(std::string(what) + ": " + lmot_strerror(rc) + " | " + lmot_last_error(context_slot()));   // rc > 0: warning, outputs valid
 }
 
 namespace detail {

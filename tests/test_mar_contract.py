@@ -4,7 +4,9 @@ csrc/boxfit.cu) against OpenCV's own cv2.minAreaRect + cv2.boxPoints (python-ope
 OpenCV is NOT part of /root/reference (the reference calls the system "Open CV 3.2", README.md:88), so this is the
 only anchor for that call: the contract must produce the same rectangle as a set of corners (OpenCV's float
 rotating-calipers arithmetic differs in the last digits; the corner ORDER convention changed in OpenCV 4.5.1 and is
-not compared)."""
+not compared).  Every non-degenerate set is checked and a disagreement FAILS the test; the only sets exempt from the corner
+comparison are those whose minimum area is attained, to 1e-4 relative, by hull edges of two different orientations (the
+minimiser is then not unique and either rectangle is a correct answer) -- they are counted and printed."""
 import ctypes as C
 import os
 
@@ -25,21 +27,76 @@ def _mar(pts):
     return m, out.reshape(4, 2)
 
 
-def _match_sets(a, b, tol):
-    used = set()
-    for p in a:
-        d = np.hypot(b[:, 0] - p[0], b[:, 1] - p[1])
-        j = int(np.argmin(d))
-        assert d[j] < tol, (a, b)
-        used.add(j)
-    return len(used)
+def _hull(pts):
+    """strict convex hull of integer points (Andrew), as oracle/mar_contract.cpp builds it -- exact integers"""
+    P = sorted(set(map(tuple, pts)))
+    if len(P) <= 2:
+        return P
+
+    def cr(o, a, b):
+        return (a[0] - o[0]) * (b[1] - o[1]) - (a[1] - o[1]) * (b[0] - o[0])
+    lo, up = [], []
+    for q in P:
+        while len(lo) >= 2 and cr(lo[-2], lo[-1], q) <= 0:
+            lo.pop()
+        lo.append(q)
+    for q in reversed(P):
+        while len(up) >= 2 and cr(up[-2], up[-1], q) <= 0:
+            up.pop()
+        up.append(q)
+    return lo[:-1] + up[:-1]
+
+
+def _orientation_is_unique(pts, rel=1e-4):
+    """True unless a hull edge of ANOTHER orientation (not parallel / perpendicular to the winner) encloses the set in a rectangle
+    whose exact area is within `rel` of the minimum: only then may two correct implementations return different rectangles."""
+    from fractions import Fraction
+    h = _hull(pts)
+    m = len(h)
+    areas = []
+    for i in range(m):
+        dx, dy = h[(i + 1) % m][0] - h[i][0], h[(i + 1) % m][1] - h[i][1]
+        s = [x * dx + y * dy for x, y in h]
+        t = [-x * dy + y * dx for x, y in h]
+        areas.append((Fraction((max(s) - min(s)) * (max(t) - min(t)), dx * dx + dy * dy), (dx, dy)))
+    best, bd = min(areas, key=lambda a: a[0])
+    for a, d in areas:
+        same = (d[0] * bd[1] - d[1] * bd[0] == 0) or (d[0] * bd[0] + d[1] * bd[1] == 0)
+        if not same and a <= best * (1 + Fraction(rel)):
+            return False
+    return True
+
+
+def _corner_set_distance(mine, theirs):
+    return max(float(np.min(np.hypot(theirs[:, 0] - p[0], theirs[:, 1] - p[1]))) for p in mine)
+
+
+def _check_against_opencv(pts, stats):
+    """EVERY pixel set with >= 3 hull vertices: same minimum area as cv2.minAreaRect, and -- unless the minimum is attained (to
+    1e-4 relative) by hull edges of two different orientations -- the same four corners as cv2.boxPoints to 0.02 px.
+    A mismatch FAILS; ties are counted and reported, never silently skipped."""
+    m, mine = _mar(pts)
+    if m < 3:
+        return
+    rect = cv2.minAreaRect(pts.astype(np.float32).reshape(-1, 1, 2))
+    theirs = cv2.boxPoints(rect)
+    area_cv = rect[1][0] * rect[1][1]
+    e1, e2 = np.hypot(*(mine[0] - mine[1])), np.hypot(*(mine[2] - mine[1]))
+    assert abs(e1 * e2 - area_cv) <= 1e-3 * max(area_cv, 1.0) + 1e-2, (e1 * e2, area_cv)
+    if _orientation_is_unique(pts.tolist()):
+        d = _corner_set_distance(mine, theirs)
+        assert d < 0.02, (d, mine, theirs)        # 0.02 px = 1.1 mm at 18 px/m; measured worst 2.8e-4 px
+        stats["unique"] += 1
+        stats["worst"] = max(stats["worst"], d)
+    else:
+        stats["tied"] += 1
 
 
 @pytest.mark.skipif(not os.path.exists(LIB), reason="oracle port not built")
 def test_contract_matches_opencv_rectangles():
     rng = np.random.default_rng(0)
-    checked = 0
-    for it in range(300):
+    stats = dict(unique=0, tied=0, worst=0.0)
+    for it in range(600):
         n = int(rng.integers(3, 400))
         kind = it % 4
         if kind == 0:
@@ -53,22 +110,44 @@ def test_contract_matches_opencv_rectangles():
             pts = np.stack([300 + t, 300 + 0.37 * t + rng.normal(0, 1.5, n)], 1)
         else:                # small cluster, many duplicates
             pts = rng.integers(440, 460, (n, 2))
-        pts = np.floor(pts).astype(np.int32)
-        m, mine = _mar(pts)
-        if m < 3:
-            continue
-        rect = cv2.minAreaRect(pts.astype(np.float32).reshape(-1, 1, 2))
-        theirs = cv2.boxPoints(rect)
-        area_cv = rect[1][0] * rect[1][1]
-        e1, e2 = np.hypot(*(mine[0] - mine[1])), np.hypot(*(mine[2] - mine[1]))
-        # same minimum area (two different rectangles can tie within float noise, so compare areas first)
-        assert abs(e1 * e2 - area_cv) <= 1e-3 * max(area_cv, 1.0) + 1e-2
-        if abs(e1 - e2) > 0.5 and min(e1, e2) > 0.5:
-            # unique orientation: corners must coincide as a set (tolerance 0.02 px ~ 1e-3 m at 18 px/m)
-            d = max(np.min(np.hypot(theirs[:, 0] - p[0], theirs[:, 1] - p[1])) for p in mine)
-            if d < 0.05:
-                checked += 1
-    assert checked > 150
+        _check_against_opencv(np.floor(pts).astype(np.int32), stats)
+    print("MAR contract vs cv2.minAreaRect, synthetic sets:", stats)
+    assert stats["unique"] > 500 and stats["tied"] < 0.1 * stats["unique"]
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="oracle port not built")
+def test_contract_matches_opencv_on_hdl64_cluster_pixels():
+    """The pixel sets box fitting actually hands to cv::minAreaRect: clusters of synthetic HDL-64 frames, pixelised exactly as
+    /root/reference/object_tracking/src/cluster/box_fitting.cpp:218-252 does (18 px/m, offsets relative to the cluster's point #0)."""
+    import importlib
+    from oracle import ref as oracle
+    synth = importlib.import_module("3d-lidar-multi-object-tracking_b200.synth")
+    o = oracle.PortOracle("intended")
+    stats = dict(unique=0, tied=0, worst=0.0)
+    roi = np.float32(50.0)
+    pic = np.float32(900.0) / roi
+    for seed in (3, 4):
+        for _, pts in synth.frames(synth.SceneConfig(seed=seed, n_objects=150, lattice_pitch=3.8, ped_fraction=0.65), 2):
+            e, _ = o.ground_remove(pts)
+            grid, k = o.component_clustering(e)
+            x, y = e[:, 0].astype(np.float32), e[:, 1].astype(np.float32)
+            xc, yc = x + roi / 2, y + roi / 2
+            inside = (xc >= 0) & (xc < roi) & (yc >= 0) & (yc < roi)
+            xi = np.floor(np.float32(250) * xc / roi).astype(int)
+            yi = np.floor(np.float32(250) * yc / roi).astype(int)
+            cid = np.zeros(len(e), int)
+            cid[inside] = grid[xi[inside], yi[inside]]
+            for c in range(1, k + 1):
+                q = e[cid == c]
+                if len(q) < 3:
+                    continue
+                px = np.floor((q[:, 0] + roi / 2) * pic).astype(np.int64)
+                py = (pic * roi - np.floor((q[:, 1] + roi / 2) * pic).astype(np.float32)).astype(np.int64)
+                off_x = int(roi * pic / 2 - np.float32(px[0]))
+                off_y = int(roi * pic / 2 - np.float32(py[0]))
+                _check_against_opencv(np.stack([px + off_x, py + off_y], 1).astype(np.int32), stats)
+    print("MAR contract vs cv2.minAreaRect, HDL-64 cluster pixel sets:", stats)
+    assert stats["unique"] > 100
 
 
 @pytest.mark.skipif(not os.path.exists(LIB), reason="oracle port not built")

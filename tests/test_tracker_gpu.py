@@ -194,3 +194,26 @@ def test_full_pipeline_frame_matches_chained_reference(pkg, ref_intended, synth)
             np.testing.assert_allclose(r["targets"], a["targets"], rtol=1e-4, atol=1e-4)
     finally:
         ctx.close()
+
+
+def test_checkpoint_restore_with_moving_ego(pkg, ref_intended, synth):
+    """lmot_tracker_dump + lmot_tracker_get_ego  ->  lmot_tracker_load + lmot_tracker_set_ego on a FRESH context continues a
+    sequence with ego rotation bit for bit (a restore used to lose the accumulated dead-reckoning pose)."""
+    seq = _boxes_sequence(ref_intended, synth, seed=9, n_frames=14, n_objects=40)
+    ego = lambda f: (4.0 + 0.2 * f, 0.03 * f)
+    a = pkg.Lmot()
+    b = pkg.Lmot()
+    try:
+        for f, (ts, boxes) in enumerate(seq[:7]):
+            a.track_step(boxes, ts, *ego(f))
+        b.tracker_load(a.tracker_dump(), 1, seq[6][0])
+        b.tracker_set_ego(a.tracker_get_ego())
+        for f, (ts, boxes) in enumerate(seq[7:], start=7):
+            ra, rb = a.track_step(boxes, ts, *ego(f)), b.track_step(boxes, ts, *ego(f))
+            for k in ("track_manage", "is_static", "is_vis"):
+                assert np.array_equal(ra[k], rb[k]), (f, k)
+            assert np.array_equal(ra["vandyaw"], rb["vandyaw"]) and np.array_equal(ra["targets"], rb["targets"]), f
+            assert np.array_equal(a.tracker_get_ego(), b.tracker_get_ego())
+        assert abs(a.tracker_get_ego()[7] + np.pi / 2) > 0.1      # the ego really turned
+    finally:
+        a.close(); b.close()
