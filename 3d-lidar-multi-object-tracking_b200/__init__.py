@@ -54,6 +54,7 @@ class Params(C.Structure):
         ("max_points", C.c_int), ("max_clusters", C.c_int), ("max_boxes", C.c_int), ("max_tracks", C.c_int),
         ("node_prefilter", C.c_int), ("filter_z_min", C.c_float), ("filter_z_max", C.c_float),
         ("filter_x_min", C.c_float), ("filter_x_max", C.c_float), ("filter_y_min", C.c_float), ("filter_y_max", C.c_float),
+        ("global_frame", C.c_int),
         ("pipeline_depth", C.c_int), ("result_ring", C.c_int),
     ]
 
@@ -428,6 +429,12 @@ class Lmot:
             d = np.zeros((1, TRACK_DUMP_DOUBLES), np.float64)
         self._chk(self.lib.lmot_tracker_load(self.h, d.ctypes.data_as(C.POINTER(C.c_double)), n, int(init), C.c_double(timestamp_us),
                                              C.c_double(ego_velo), C.c_double(ego_yaw), C.c_double(ego_pre_yaw), C.c_double(ego_point_yaw)))
+
+    def origin_points(self, timestamp_us, v_gps=0.0, yaw_gps=0.0) -> np.ndarray:
+        """getOriginPoints for this frame WITHOUT advancing the tracker: (x, y, yaw, x, y, yaw + pi/2)."""
+        o = np.zeros(6, np.float64)
+        self._chk(self.lib.lmot_origin_points(self.h, C.c_double(timestamp_us), C.c_double(v_gps), C.c_double(yaw_gps), o.ctypes.data_as(C.POINTER(C.c_double))))
+        return o
 
     def tracker_get_ego(self) -> np.ndarray:
         e = np.zeros(8, np.float64)

@@ -161,7 +161,9 @@ int submit(Ctx* c, Slot* s, Result* r, const float4* d_pts, int n, bool with_tra
   if (c->timing) cudaEventRecord(r->ev[1], s->stream);
   if ((rc = cluster_launch(c, s, s->stream, n, true))) return rc;
   if (c->timing) cudaEventRecord(r->ev[2], s->stream);
-  if ((rc = boxfit_launch(c, s, s->stream, n, with_tracker))) return rc;      // with_tracker: posts the slot's detection semaphore
+  const bool gf = with_tracker && c->prm.global_frame;
+  if ((rc = boxfit_launch(c, s, s->stream, n, with_tracker && !gf))) return rc;      // with_tracker: posts the slot's detection semaphore
+  if (gf && (rc = boxes_to_global_launch(c, s, s->stream, s->d_boxes, s->d_counters, ts, v, yaw, true))) return rc;   // ... or this one does
   if (c->timing) cudaEventRecord(r->ev[3], s->stream);
   LMOT_CUDA(c, cudaEventRecord(s->ev_det_done, s->stream));
   if (with_tracker) {
@@ -201,6 +203,7 @@ int batch_ensure(Ctx* c, int F) {
     if (k->d_boxes) continue;
     k->index = 2000 + b;
     LMOT_CUDA(c, cudaMalloc(&k->d_boxes, (size_t)c->prm.max_boxes * 24 * sizeof(float)));
+    LMOT_CUDA(c, cudaMalloc(&k->d_boxes_g, (size_t)c->prm.max_boxes * 24 * sizeof(float)));
     LMOT_CUDA(c, cudaMalloc(&k->d_counters, CNT_COUNT * sizeof(int)));
     LMOT_CUDA(c, cudaMemset(k->d_counters, 0, CNT_COUNT * sizeof(int)));
     LMOT_CUDA(c, cudaMalloc(&k->d_det_sem, sizeof(int)));
@@ -221,7 +224,7 @@ void batch_destroy(Ctx* c) {
   for (int i = 0; i < c->n_bslots; ++i) slot_destroy(&c->bslots[i]);
   for (int b = 0; b < kBatchBanks; ++b) {
     Slot* k = &c->bank[b];
-    cudaFree(k->d_boxes); cudaFree(k->d_counters); cudaFree(k->d_det_sem);
+    cudaFree(k->d_boxes); cudaFree(k->d_boxes_g); cudaFree(k->d_counters); cudaFree(k->d_det_sem);
     if (k->ev_det_done) cudaEventDestroy(k->ev_det_done);
     if (k->ev_trk_done) cudaEventDestroy(k->ev_trk_done);
     if (k->ev_fork) cudaEventDestroy(k->ev_fork);
@@ -249,7 +252,9 @@ int batch_submit(Ctx* c, int bank_i, Result* r, const float4* const* d_pts, cons
   if ((rc = boxfit_launch_batch(c, sl, F, st, n, false))) return rc;
   int* d_fc = nullptr;                       // the per-frame counts go straight into the result's pinned, device-mapped block
   LMOT_CUDA(c, cudaHostGetDevicePointer((void**)&d_fc, r->h_frame_counts, 0));
-  if ((rc = boxes_concat_launch(c, sl, F, st, k->d_boxes, k->d_counters, d_fc, with_tracker ? k->d_det_sem : nullptr))) return rc;
+  const bool gf = with_tracker && c->prm.global_frame;
+  if ((rc = boxes_concat_launch(c, sl, F, st, k->d_boxes, k->d_counters, d_fc, (with_tracker && !gf) ? k->d_det_sem : nullptr))) return rc;
+  if (gf && (rc = boxes_to_global_launch(c, k, st, k->d_boxes, k->d_counters, ts, v, yaw, true))) return rc;
   if (c->timing) cudaEventRecord(r->ev[3], st);
   LMOT_CUDA(c, cudaEventRecord(k->ev_det_done, st));
   if (with_tracker) {
@@ -410,6 +415,7 @@ int lmot_default_params(lmot_params* p) {
   p->rule_filter = LMOT_RULE_INTENDED;
   p->oracle_compat_first_frame = 1;
   p->max_points = 1 << 20; p->max_clusters = 4096; p->max_boxes = 1024; p->max_tracks = 8192;
+  p->global_frame = 0;
   p->node_prefilter = 0; p->filter_z_min = -3.0f; p->filter_z_max = 1.0f;
   p->filter_x_min = -15.f; p->filter_x_max = 5.f; p->filter_y_min = -50.f; p->filter_y_max = 50.f;
   p->pipeline_depth = 8;   // detection takes ~150 us per frame: 8 frames in flight keep it ahead of the ~40 us tracker chain
@@ -468,6 +474,7 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   c->gp.tol = p.ground_tolerance;
   gauss_taps(c->gp.tap);
   if (const char* e = getenv("LMOT_COOP")) c->coop_launch = atoi(e) != 0;
+  if (const char* e = getenv("LMOT_CCL")) { const int v = atoi(e); if (v == 2 || v == 3) c->ccl_variant = v; }
   if (const char* e = getenv("LMOT_SPIN_LIMIT")) c->spin_limit = (unsigned)strtoul(e, nullptr, 0);   // 0: device-side waits never trap (debuggers, MPS)
   if (const char* e = getenv("LMOT_TRK_CTAS")) { const int v = atoi(e); if (v >= 8 && v <= 4096) c->trk_ctas = v; }     // tuning only
   if (const char* e = getenv("LMOT_FIT_CTAS")) { const int v = atoi(e); if (v >= 8 && v <= 4096) c->fit_ctas = v; }
@@ -696,6 +703,7 @@ int lmot_track_step(lmot_ctx* ctx, const float* boxes, int m, double timestamp_u
   if (m > 0) LMOT_CUDA(c, cudaMemcpyAsync(s->d_boxes, boxes, (size_t)m * 24 * sizeof(float), cudaMemcpyHostToDevice, st));
   if ((rc = set_counter(c, s, st, CNT_N_BOXES, m))) return rc;
   if (c->timing) cudaEventRecord(s->res->ev[3], st);
+  if (c->prm.global_frame && (rc = boxes_to_global_launch(c, s, st, s->d_boxes, s->d_counters, timestamp_us, v_gps, yaw_gps, false))) return rc;
   if ((rc = tracker_launch(c, s, st, s->d_boxes, s->d_counters, timestamp_us, v_gps, yaw_gps))) return rc;
   if (c->timing) cudaEventRecord(s->res->ev[4], st);
   if ((rc = tracker_publish(c, s->res, st))) return rc;
@@ -1108,9 +1116,8 @@ int lmot_debug_polar_grid(lmot_ctx* ctx, float* minz, float* height, float* smoo
   if (rc) return rc;
   Slot* s = &c->slots[c->last_slot];
   cudaStream_t st = c->stream;
-  // The fused kernel keeps its polar grid in shared memory, per CTA and only for the channels that CTA's points need: the four
-  // intermediate grids are recomputed here from the launch's min-z keys.  hGround / isGround come from what the fused kernel's
-  // CTAs actually USED wherever one of them evaluated the cell (stage entry points leave that in d_hg), else from the recomputation.
+  // The fused kernel writes only what its phase 3 needs; the four intermediate grids are recomputed here from the launch's min-z
+  // keys.  hGround / isGround are the fused kernel's own (stage entry points leave them in d_hg).
   if ((rc = ground_grids_debug(c, s, st))) return rc;
   const size_t b = kPolarCells * sizeof(float);
   if (minz) LMOT_CUDA(c, cudaMemcpyAsync(minz, s->d_minz, b, cudaMemcpyDeviceToHost, st));
@@ -1125,7 +1132,7 @@ int lmot_debug_polar_grid(lmot_ctx* ctx, float* minz, float* height, float* smoo
   }
   LMOT_CUDA(c, cudaStreamSynchronize(st));
   for (int k = 0; k < kPolarCells && (hground || isground); ++k) {
-    const float v = std::isnan(hu[k]) ? hg[k] : hu[k];
+    const float v = s->hg_valid ? hu[k] : hg[k];
     const bool g = !(std::isinf(v) && v < 0);
     if (hground) hground[k] = g ? v : 0.f;
     if (isground) isground[k] = g ? 1 : 0;

@@ -684,6 +684,7 @@ int boxfit_alloc(Ctx* c, Slot* s) {
   LMOT_CUDA(c, cudaMalloc(&s->d_cl_marker, (size_t)K1 * 6 * sizeof(float)));
   LMOT_CUDA(c, cudaMalloc(&s->d_cl_ok, K1));
   LMOT_CUDA(c, cudaMalloc(&s->d_boxes, (size_t)c->prm.max_boxes * 24 * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_boxes_g, (size_t)c->prm.max_boxes * 24 * sizeof(float)));
   LMOT_CUDA(c, cudaMalloc(&s->d_markers, (size_t)c->prm.max_boxes * 6 * sizeof(float)));
   LMOT_CUDA(c, cudaMalloc(&s->d_done, sizeof(int)));
   LMOT_CUDA(c, cudaMemsetAsync(s->d_done, 0, sizeof(int), s->stream));
@@ -694,7 +695,7 @@ int boxfit_alloc(Ctx* c, Slot* s) {
 
 void boxfit_free(Slot* s) {
   cudaFree(s->d_pcid); cudaFree(s->d_table); cudaFree(s->d_seg_start); cudaFree(s->d_seg_size); cudaFree(s->d_sorted_pts);
-  cudaFree(s->d_cl_box); cudaFree(s->d_cl_marker); cudaFree(s->d_cl_ok); cudaFree(s->d_boxes); cudaFree(s->d_markers);
+  cudaFree(s->d_cl_box); cudaFree(s->d_cl_marker); cudaFree(s->d_cl_ok); cudaFree(s->d_boxes); cudaFree(s->d_boxes_g); cudaFree(s->d_markers);
   cudaFree(s->d_done); cudaFree(s->d_det_sem);
 }
 

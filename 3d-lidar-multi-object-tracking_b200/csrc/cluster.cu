@@ -358,6 +358,257 @@ ccl_bitmap_kernel(const __grid_constant__ CclBatch B, unsigned long long* __rest
   ccl_mark(clk, 8);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// ccl_dense_kernel: the same algorithm on DENSE node ids.  ccl_bitmap_kernel numbers a piece word * 16 + k: the 32 lanes of a
+// warp then hit the same shared-memory bank on every parent access, each thread walks its own ragged list of pieces, and the
+// flattening walks are data-dependent loops of dependent loads (measured 18-23 us per frame, 8 of them in the second flatten).
+// Here a block-wide scan of the pieces per word gives every piece its raster-order rank as id (still monotone: the smallest id of
+// a component is its first piece in raster order), so that
+//   * flattening is SYNCHRONOUS pointer jumping, thread t on ids t, t + 1024, ...: conflict-free, log2(depth) rounds;
+//   * the adjacencies step C cannot express as a parent link go to a pair list and are united one pair per thread.
+constexpr int kPairCap = 4096;
+constexpr int kDenseSmem = kNodes * 4 + 3 * kBitWords * 4 + (kBitWords + 8) * 4 + kPairCap * 4 + 64 * 4;
+
+__device__ __forceinline__ void ccl_flatten_rounds(volatile int* L, int P) {
+  int changed;
+  do {
+    changed = 0;
+    for (int id = threadIdx.x; id < P; id += kCclThreads) {
+      const int p = L[id], g = L[p];
+      if (g != p) { L[id] = g; changed = 1; }
+    }
+  } while (__syncthreads_or(changed));
+}
+
+__global__ void __launch_bounds__(kCclThreads, 1)
+ccl_dense_kernel(const __grid_constant__ CclBatch B, unsigned long long* __restrict__ clk) {
+  extern __shared__ __align__(16) unsigned char ccl_smem[];
+  int* s_par = reinterpret_cast<int*>(ccl_smem);                       // [<= 32000] parent id, later -(cluster id) at roots
+  unsigned* s_seed = reinterpret_cast<unsigned*>(s_par + kNodes);       // [2000]
+  unsigned* s_occ = s_seed + kBitWords;                                 // [2000]
+  unsigned* s_prev = s_occ + kBitWords;                                 // [2000]
+  int* s_wbase = reinterpret_cast<int*>(s_prev + kBitWords);            // [2000 + 1] id of the first piece of every word
+  unsigned* s_pairs = reinterpret_cast<unsigned*>(s_wbase + kBitWords + 8);   // [kPairCap] a | b << 16
+  int* s_warp = reinterpret_cast<int*>(s_pairs + kPairCap);             // [32] + total, [40] pair count
+  const CclFrame& F = B.f[blockIdx.x];
+  unsigned* __restrict__ once = F.once; unsigned* __restrict__ twice = F.twice; unsigned* __restrict__ prev_occ = F.prev_occ;
+  int* __restrict__ out = F.out;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  ccl_mark(clk, 0);
+  const int w0 = 2 * tid;
+  const bool own = tid < kBitWords / 2;
+  // A: seed = cells with more than one point (component_clustering.cpp:136); the bit planes are re-armed for the next frame
+  if (own) {
+    const uint2 tw = __ldcg(reinterpret_cast<const uint2*>(twice) + tid);
+    const uint2 pv = __ldcg(reinterpret_cast<const uint2*>(prev_occ) + tid);
+    s_seed[w0] = tw.x; s_seed[w0 + 1] = tw.y;
+    s_prev[w0] = pv.x; s_prev[w0 + 1] = pv.y;
+    reinterpret_cast<uint2*>(once)[tid] = make_uint2(0u, 0u);
+    reinterpret_cast<uint2*>(twice)[tid] = make_uint2(0u, 0u);
+  }
+  if (tid == 0) s_warp[40] = 0;
+  __syncthreads();
+  ccl_mark(clk, 1);
+  // B: occupied = seed dilated 3x3, clipped at the border (:137-214); ids: exclusive scan of the pieces per word
+  unsigned occ[2] = {0u, 0u};
+  int np0 = 0, np1 = 0;
+  if (own) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int w = w0 + h, x = w >> 3, k = w & 7;
+      unsigned o = hdil(s_seed + x * kRowWords, k);
+      if (x > 0) o |= hdil(s_seed + (x - 1) * kRowWords, k);
+      if (x < kNumGrid - 1) o |= hdil(s_seed + (x + 1) * kRowWords, k);
+      if (k == kRowWords - 1) o &= kLastWordMask;
+      occ[h] = o;
+      s_occ[w] = o;
+    }
+    reinterpret_cast<uint2*>(prev_occ)[tid] = make_uint2(occ[0], occ[1]);
+    np0 = __popc(piece_starts(occ[0])); np1 = __popc(piece_starts(occ[1]));
+  }
+  int P;
+  {
+    const int cnt = np0 + np1;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int v = s_warp[lane];
+      int wi = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += t; }
+      s_warp[lane] = wi - v;
+      if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    const int base = s_warp[warp] + incl - cnt;
+    if (own) { s_wbase[w0] = base; s_wbase[w0 + 1] = base + np0; }
+    P = s_warp[32];
+  }
+  __syncthreads();
+  ccl_mark(clk, 2);
+  // C: first parent = the smallest neighbour a piece touches (leftmost touching piece of the row above, else the piece it
+  // continues from the previous word, else itself); every OTHER adjacency becomes a pair for step E
+  if (own) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const unsigned m = occ[h];
+      if (!m) continue;
+      const int w = w0 + h, x = w >> 3, k = w & 7;
+      unsigned up = 0u, upl = 0u, upr = 0u;
+      int bu = 0, bul = 0, bur = 0;
+      if (x > 0) {
+        up = s_occ[w - kRowWords]; bu = s_wbase[w - kRowWords];
+        if (k > 0) { upl = s_occ[w - kRowWords - 1]; bul = s_wbase[w - kRowWords - 1]; }
+        if (k < kRowWords - 1) { upr = s_occ[w - kRowWords + 1]; bur = s_wbase[w - kRowWords + 1]; }
+      }
+      const unsigned left = (k > 0) ? ((h == 1) ? occ[0] : s_occ[w - 1]) : 0u;
+      const int bl = (k > 0) ? s_wbase[w - 1] : 0;
+      const int mybase = s_wbase[w];
+      unsigned rest = m;
+      int j = 0;
+      while (rest) {
+        const int a = __ffs(rest) - 1;
+        const unsigned t = ~(rest >> a);                       // first zero above a ends the piece
+        const int len = t ? __ffs(t) - 1 : 32;
+        const unsigned pm = (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << a;
+        rest &= ~pm;
+        const int me = mybase + j;
+        ++j;
+        // neighbours in DEcreasing id order; the last one found is the parent, the others go to the pair list
+        int par = me;
+        auto link = [&](int nb) {
+          if (par != me) {                                     // the previous candidate loses: remember it as a pair
+            const int slot = atomicAdd(&s_warp[40], 1);
+            if (slot < kPairCap) s_pairs[slot] = (unsigned)me | ((unsigned)par << 16);   // (list full: step E re-derives ALL adjacencies instead)
+          }
+          par = nb;
+        };
+        if (a == 0 && (left >> 31)) link(bl + __popc(piece_starts(left)) - 1);                 // same row, previous word
+        if (a + len == 32 && (upr & 1u)) link(bur);                                             // row above, word to the right
+        unsigned touched = up & (pm | (pm << 1) | (pm >> 1));                                   // row above, same word: right to left
+        while (touched) {
+          const int p = 31 - __clz(touched);
+          const int q = piece_of(up, p);
+          link(bu + q);
+          // clear this whole piece from `touched`: all bits from its start upwards
+          const unsigned startbit = piece_starts(up) & ((2u << p) - 1u);                       // starts at or below p
+          const int sb = 31 - __clz(startbit);                                                  // the start of the piece containing p
+          touched &= (1u << sb) - 1u;
+        }
+        if (a == 0 && (upl >> 31)) link(bul + __popc(piece_starts(upl)) - 1);                   // row above, word to the left
+        s_par[me] = par;
+      }
+    }
+  }
+  __syncthreads();
+  ccl_mark(clk, 3);
+  volatile int* Lv = s_par;
+  // D: flatten
+  ccl_flatten_rounds(Lv, P);
+  ccl_mark(clk, 4);
+  // E: the remaining adjacencies, one pair per thread
+  if (s_warp[40] <= kPairCap) {
+    const int npairs = s_warp[40];
+    for (int i = tid; i < npairs; i += kCclThreads) { const unsigned pr = s_pairs[i]; uf_union(Lv, s_par, (int)(pr & 0xFFFFu), (int)(pr >> 16)); }
+  } else if (own) {
+    // more pairs than the list holds (checkerboard-like occupancy): every thread unites ALL adjacencies of its own pieces
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const unsigned m = occ[h];
+      if (!m) continue;
+      const int w = w0 + h, x = w >> 3, k = w & 7;
+      unsigned up = 0u, upl = 0u, upr = 0u;
+      int bu = 0, bul = 0, bur = 0;
+      if (x > 0) {
+        up = s_occ[w - kRowWords]; bu = s_wbase[w - kRowWords];
+        if (k > 0) { upl = s_occ[w - kRowWords - 1]; bul = s_wbase[w - kRowWords - 1]; }
+        if (k < kRowWords - 1) { upr = s_occ[w - kRowWords + 1]; bur = s_wbase[w - kRowWords + 1]; }
+      }
+      const unsigned left = (k > 0) ? ((h == 1) ? occ[0] : s_occ[w - 1]) : 0u;
+      const int bl = (k > 0) ? s_wbase[w - 1] : 0;
+      unsigned rest = m;
+      int me = s_wbase[w];
+      while (rest) {
+        const int a = __ffs(rest) - 1;
+        const unsigned t = ~(rest >> a);
+        const int len = t ? __ffs(t) - 1 : 32;
+        const unsigned pm = (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << a;
+        rest &= ~pm;
+        if (a == 0 && (left >> 31)) uf_union(Lv, s_par, me, bl + __popc(piece_starts(left)) - 1);
+        if (a + len == 32 && (upr & 1u)) uf_union(Lv, s_par, me, bur);
+        unsigned touched = up & (pm | (pm << 1) | (pm >> 1));
+        while (touched) {
+          const int p = 31 - __clz(touched);
+          uf_union(Lv, s_par, me, bu + piece_of(up, p));
+          const unsigned startbit = piece_starts(up) & ((2u << p) - 1u);
+          touched &= (1u << (31 - __clz(startbit))) - 1u;
+        }
+        if (a == 0 && (upl >> 31)) uf_union(Lv, s_par, me, bul + __popc(piece_starts(upl)) - 1);
+        ++me;
+      }
+    }
+  }
+  __syncthreads();
+  ccl_mark(clk, 5);
+  // F: flatten again
+  ccl_flatten_rounds(Lv, P);
+  ccl_mark(clk, 6);
+  // G: id = 1 + rank of the root among all roots in id (= raster) order (:247-257); thread t ranks the ids [t*c, (t+1)*c)
+  {
+    const int c = (P + kCclThreads - 1) / kCclThreads;
+    const int i0 = min(tid * c, P), i1 = min(i0 + c, P);
+    int roots = 0;
+    for (int id = i0; id < i1; ++id) roots += (s_par[id] == id) ? 1 : 0;
+    int incl = roots;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int v = s_warp[lane];
+      int wi = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += t; }
+      s_warp[lane] = wi - v;
+      if (lane == 31) F.counters[CNT_NUM_CLUSTER] = wi;
+    }
+    __syncthreads();
+    int rank = s_warp[warp] + incl - roots;
+    // (every non-root points at its root after F, so turning roots into -(id) cannot confuse a concurrent reader: nobody reads
+    // parents between here and the barrier below)
+    for (int id = i0; id < i1; ++id) if (s_par[id] == id) s_par[id] = -(++rank);
+  }
+  __syncthreads();
+  ccl_mark(clk, 7);
+  // H: label grid, sparse: cells occupied now get their id, cells occupied only in the previous frame are cleared
+  if (own) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int w = w0 + h;
+      const unsigned m = occ[h];
+      int* o = out + (w >> 3) * kNumGrid + (w & 7) * 32;
+      unsigned gone = s_prev[w] & ~m;
+      while (gone) { const int b = __ffs(gone) - 1; gone &= gone - 1; o[b] = 0; }
+      unsigned rest = m;
+      int id = s_wbase[w];
+      while (rest) {
+        const int a = __ffs(rest) - 1;
+        const unsigned t = ~(rest >> a);
+        const int len = t ? __ffs(t) - 1 : 32;
+        rest &= ~((len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << a);
+        int r = s_par[id];
+        ++id;
+        if (r >= 0) r = s_par[r];                               // non-root: its root holds -(id)
+        for (int b = a; b < a + len; ++b) o[b] = -r;
+      }
+    }
+  }
+  ccl_mark(clk, 8);
+}
+
 // ---- the cluster node's side outputs (src/cluster/main.cpp:62-99), SURVEY.md §8(f)3 ------------------------------
 //   makeClusteredCloud (component_clustering.cpp:308-335): every elevated point inside the ROI whose cell carries a label
 //       becomes the CENTRE of its cell at z = -1, in cloud order
@@ -446,6 +697,7 @@ int cluster_alloc(Ctx* c, Slot* s) {
   LMOT_CUDA(c, cudaMemsetAsync(s->d_label_grid, 0, kCartCells * sizeof(int), s->stream));
   s->label_grid_foreign = false;
   LMOT_CUDA(c, cudaFuncSetAttribute(ccl_bitmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCclSmem));
+  LMOT_CUDA(c, cudaFuncSetAttribute(ccl_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem));
   return LMOT_OK;
 }
 
@@ -480,7 +732,8 @@ int ccl_launch_batch(Ctx* c, Slot* const* slots, int F, cudaStream_t st) {
     B.f[i].out = s->d_label_grid; B.f[i].counters = s->d_counters;
   }
   for (int i = F; i < kMaxBatch; ++i) B.f[i] = B.f[0];
-  ccl_bitmap_kernel<<<F, kCclThreads, kCclSmem, st>>>(B, c->d_ccl_clock);
+  if (c->ccl_variant == 2) ccl_bitmap_kernel<<<F, kCclThreads, kCclSmem, st>>>(B, c->d_ccl_clock);     // LMOT_CCL=2: A/B only
+  else ccl_dense_kernel<<<F, kCclThreads, kDenseSmem, st>>>(B, c->d_ccl_clock);
   kernel_mark(c, slots[0], st);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;

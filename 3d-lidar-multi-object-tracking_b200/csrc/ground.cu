@@ -114,10 +114,24 @@ constexpr int kMaxLocChan = kNumChannel / kMinCtas + 2;
 constexpr int kMaxLocCells = kMaxLocChan * kNumBin;  // 1440
 constexpr int kCellsPerThread = (kMaxLocCells + kFusedThreads - 1) / kFusedThreads;   // 2
 
+// ground_removal.cpp:236-246 labels a point ground iff  (double)z < (double)hGround + 0.25  and its cell is a ground cell.  The
+// right-hand side depends on the cell only: this is the largest float `lim` with (double)lim < (double)h + tol, so that the
+// per-point test is ONE float compare, z <= lim (identical for every float z; NaN for non-ground cells: never true).
+__device__ __forceinline__ float label_limit(float h, bool is_ground, double tol) {
+  if (!is_ground) return __int_as_float(0x7FC00000);
+  const double thr = __dadd_rn((double)h, tol);
+  float f = __double2float_rd(thr);                    // largest float <= thr
+  if ((double)f == thr) {                              // ... but the test is strict: step to the next float below
+    const int b = __float_as_int(f);
+    f = (f == 0.f) ? __int_as_float(0x80000001) : __int_as_float(b > 0 ? b - 1 : b + 1);
+  }
+  return f;
+}
+
 __device__ __forceinline__ void polar_grid_slice(const GroundParams& p, const unsigned* __restrict__ keys, int own0, int n_own,
                                                  float* H, uint8_t* G, float* __restrict__ o_minz, float* __restrict__ o_height,
                                                  float* __restrict__ o_smoothed, float* __restrict__ o_hdiff,
-                                                 float* __restrict__ o_hg) {
+                                                 float* __restrict__ o_hg, float* __restrict__ o_lim = nullptr) {
   const int tid = threadIdx.x;
   const int ch0 = own0 - 1;                                   // global channel of local channel 0 (may be -1)
   const int n_cells = (n_own + 2) * kNumBin;
@@ -131,7 +145,7 @@ __device__ __forceinline__ void polar_grid_slice(const GroundParams& p, const un
       float h = 0.f;
       if (ch >= 0 && ch < kNumChannel) {
         const float zi = fkey_inv(__ldcg(&keys[ch * kNumBin + b]));
-        if (lc >= 1 && lc <= n_own) o_minz[ch * kNumBin + b] = zi;
+        if (lc >= 1 && lc <= n_own && o_minz) o_minz[ch * kNumBin + b] = zi;
         if (zi > p.t_hmin && zi < p.t_hmax) h = zi;
         else if (zi > p.t_hmax) h = p.h_sensor;
         else h = p.t_hmin;
@@ -162,7 +176,7 @@ __device__ __forceinline__ void polar_grid_slice(const GroundParams& p, const un
           const float pre = fsub(h, H[l - 1]), post = fsub(h, H[l + 1]);
           hd = (pre > post) ? pre : post;
         }
-        if (lc >= 1 && lc <= n_own) { o_smoothed[ch * kNumBin + b] = sm; o_hdiff[ch * kNumBin + b] = hd; }
+        if (lc >= 1 && lc <= n_own && o_smoothed) { o_smoothed[ch * kNumBin + b] = sm; o_hdiff[ch * kNumBin + b] = hd; }
         g = ((sm < p.t_hmax && hd < p.t_hdiff) || (h < p.t_hmax && hd < p.t_hdiff)) ? 1 : 0;  // :205-214
       }
       G[l] = g;
@@ -243,8 +257,9 @@ __device__ __forceinline__ void polar_grid_slice(const GroundParams& p, const un
     if (l < n_cells) {
       const int lc = l / kNumBin, b = l - lc * kNumBin, ch = ch0 + lc;
       if (lc >= 1 && lc <= n_own) {
-        o_height[ch * kNumBin + b] = H[l];
-        o_hg[ch * kNumBin + b] = G[l] ? H[l] : -INFINITY;
+        if (o_height) o_height[ch * kNumBin + b] = H[l];
+        if (o_hg) o_hg[ch * kNumBin + b] = G[l] ? H[l] : -INFINITY;
+        if (o_lim) o_lim[ch * kNumBin + b] = label_limit(H[l], G[l] != 0, p.tol);
       }
     }
   }
@@ -288,20 +303,20 @@ constexpr int kLookBatch = 5;                       // 5 x 32 >= 148 CTAs: all p
 constexpr int kMaxTiles = 16;                       // tiles per chunk (labels of a thread's points: 2 bits each in one register)
 constexpr int kPendCap = 2048;                      // points of a chunk whose cell needs the exact evaluation, queued for a compact pass
 constexpr unsigned kPending = 0xFFFDu;              // cell id of a queued point until that pass has run
-constexpr int kGridPerThread = (kPolarCells + kFusedThreads - 1) / kFusedThreads;   // 10: cells of a CTA's window per thread, at most
-// dynamic shared memory layout (bytes): fixed part (incl. the CTA's private copy of the polar grid: height + ground flag of
-// every cell of the channels its points touch), then the resident tiles, then the cell ids of every tile of the chunk.
+constexpr int kKeysPerThread = (kPolarCells + kFusedThreads - 1) / kFusedThreads;   // 10: cells of the CTA's key grid per thread
+// dynamic shared memory layout (bytes): fixed part (incl. the CTA's private min-z key grid), then the resident tiles, then the cell
+// ids of every tile of the chunk.
 constexpr int kOffBar = 0;                                                  // [7] mbarriers
-constexpr int kOffMeta = 64;                                                // chmask[3], npend, nch
+constexpr int kOffMeta = 64;                                                // [3] pending points
 constexpr int kOffCnt = 128;                                                // [16][32] u32 elevated | ground << 16 per warp
 constexpr int kOffWex = kOffCnt + kMaxTiles * 32 * 4;                       // [16][32] u32 exclusive inside the tile
 constexpr int kOffTtot = kOffWex + kMaxTiles * 32 * 4;                      // [16] u32 tile totals
 constexpr int kOffBase = kOffTtot + kMaxTiles * 4;                          // [2] u32 chunk base (elevated, ground)
-constexpr int kOffChl = kOffBase + 16;                                      // [96] u8 channels of the window (bit 7: own)
-constexpr int kOffPend = (kOffChl + 96 + 15) & ~15;                         // [kPendCap] u16
-constexpr int kOffG = kOffPend + kPendCap * 2;                              // [9600] u8
-constexpr int kOffH = (kOffG + kPolarCells + 127) & ~127;                   // [9600] float
-constexpr int kOffPts = (kOffH + kPolarCells * 4 + 127) & ~127;             // [res_tiles][1024] float4, then [tiles][1024] u16
+constexpr int kOffPend = (kOffBase + 16 + 15) & ~15;                        // [kPendCap] u16
+constexpr int kOffG = kOffPend + kPendCap * 2;                              // [1440] u8   polar-grid slice
+constexpr int kOffH = (kOffG + kMaxLocCells + 127) & ~127;                  // [1440] float
+constexpr int kOffKeys = (kOffH + kMaxLocCells * 4 + 127) & ~127;           // [9600] u32  min-z keys of the CTA's own points
+constexpr int kOffPts = (kOffKeys + kPolarCells * 4 + 127) & ~127;          // [res_tiles][1024] float4, then [tiles][1024] u16
 __host__ __device__ constexpr int fused_smem_bytes(int res_tiles, int tiles) { return kOffPts + res_tiles * kTilePts * 16 + tiles * kTilePts * 2; }
 constexpr int kFusedSmem = fused_smem_bytes(kMaxResTiles, kMaxTiles);
 static_assert(kFusedSmem <= 227 * 1024, "ground_fused_kernel: shared memory budget");
@@ -314,7 +329,6 @@ struct FusedOut {
   unsigned* cart_once;      // nullable: bit planes of the cartesian grid (cluster.cu)
   unsigned* cart_twice;
   int* counters;
-  float* dbg_hg;            // nullable (stage entry points): hGround of the cells this CTA evaluated, for lmot_debug_polar_grid
 };
 
 // one frame of a launch: CTAs [frame * ctas_per_frame, (frame + 1) * ctas_per_frame) work on it and synchronise among themselves only
@@ -327,6 +341,8 @@ struct FrameIO {
   unsigned bar_target;
   unsigned epoch;
   unsigned long long* desc;
+  float* hg;                // [9600] nullable (inspection): hGround of ground cells, -inf otherwise
+  float* lim;               // [9600] label limit of every cell (label_limit): phase 2 -> phase 3
   FusedOut out;
 };
 struct GroundBatch {
@@ -363,9 +379,10 @@ __device__ __forceinline__ unsigned polar_cell_fast(float x, float y, const Grou
   return (unsigned)((int)cf * kNumBin + (int)tf);
 }
 
-// ONE launch per frame -- or per batch of frames (one per sensor stream): phase 1 bins, a frame-wide barrier, then every CTA
-// evaluates the polar-grid stages for the channels ITS points fall into (plus one halo channel per side for the median filter)
-// in its own shared memory and labels its points from there: no second barrier, no round trip of the grid through L2.
+// ONE launch per frame -- or per batch of frames (one per sensor stream), CTA groups own frames and synchronise among themselves.
+// (Round 2 also tried "no second barrier": every CTA evaluating the polar grid for the channels its own points fall into, in shared
+// memory.  With ring-major clouds a chunk spans most of the 80 channels, so 148 CTAs each redid ~90 % of the grid: 7 M of the
+// kernel's 17 M warp instructions at 1 M points, 9 us -- profiles/README.md.  The grid is evaluated ONCE, spread over the CTAs.)
 __global__ void __launch_bounds__(kFusedThreads, 1)
 ground_fused_kernel(const __grid_constant__ GroundBatch B, const __grid_constant__ GroundParams p, float roi,
                     unsigned long long* __restrict__ phase_clock) {
@@ -380,12 +397,12 @@ ground_fused_kernel(const __grid_constant__ GroundBatch B, const __grid_constant
   const int T_max = (chunk + kTilePts - 1) / kTilePts;                     // tiles of a full chunk (what the launch allocated for)
   const int res_tiles = T_max < kMaxResTiles ? T_max : kMaxResTiles;
   uint64_t* s_full = reinterpret_cast<uint64_t*>(fsm + kOffBar);
-  unsigned* s_meta = reinterpret_cast<unsigned*>(fsm + kOffMeta);          // [0..2] channel mask, [3] pending points, [4] window channels
+  unsigned* s_meta = reinterpret_cast<unsigned*>(fsm + kOffMeta);          // [3] pending points
   unsigned* s_cnt = reinterpret_cast<unsigned*>(fsm + kOffCnt);
   unsigned* s_wex = reinterpret_cast<unsigned*>(fsm + kOffWex);
   unsigned* s_ttot = reinterpret_cast<unsigned*>(fsm + kOffTtot);
   unsigned* s_base = reinterpret_cast<unsigned*>(fsm + kOffBase);
-  uint8_t* s_chl = fsm + kOffChl;
+  unsigned* s_keys = reinterpret_cast<unsigned*>(fsm + kOffKeys);
   uint16_t* s_pend = reinterpret_cast<uint16_t*>(fsm + kOffPend);
   uint8_t* s_G = fsm + kOffG;
   float* s_H = reinterpret_cast<float*>(fsm + kOffH);
@@ -411,6 +428,8 @@ ground_fused_kernel(const __grid_constant__ GroundBatch B, const __grid_constant
     }
   }
   if (tid < 8) s_meta[tid] = 0u;
+#pragma unroll
+  for (int j = 0; j < kKeysPerThread; ++j) { const int k = tid + j * kFusedThreads; if (k < kPolarCells) s_keys[k] = 0xFFFFFFFFu; }
   for (int k = cta * kFusedThreads + tid; k < kPolarCells; k += Gf * kFusedThreads) F.keys_next[k] = fkey(1000.f);  // Cell::Cell(): minZ = 1000
   __syncthreads();
 
@@ -470,25 +489,15 @@ ground_fused_kernel(const __grid_constant__ GroundBatch B, const __grid_constant
       s_cell[li] = pre[u] ? kPreFiltered : (uint16_t)cc;
       if (cc >= (unsigned)kPolarCells) cc = kNoCell;           // pending: contributes later
       const unsigned k = (cc == kNoCell) ? 0xFFFFFFFFu : key[u];
-      // consecutive HDL-64 returns fall into the same cell: one atomic per distinct cell per warp.  Most warps hold a single
-      // cell (32 returns of one ring span 1.5 degrees, a channel 4.5): they skip the match and reduce over the whole warp.
+      // min z per cell into the CTA's OWN key grid in shared memory (flushed to the frame's grid once, below).  Consecutive HDL-64
+      // returns fall into the same cell: a warp that holds a single cell reduces over its lanes and issues one atomic; any other
+      // warp lets the shared-memory atomic unit sort it out (one instruction; the match / group-reduce / leader code this
+      // replaces was ~40 instructions on ~40 % of the warps of a dense frame)
       const unsigned c0 = __shfl_sync(0xFFFFFFFFu, cc, 0);
       if (__all_sync(0xFFFFFFFFu, cc == c0)) {
         const unsigned kmin = __reduce_min_sync(0xFFFFFFFFu, k);
-        if (lane == 0 && c0 != kNoCell) {
-          const unsigned ch = c0 / (unsigned)kNumBin;
-          atomicOr(&s_meta[ch >> 5], 1u << (ch & 31u));
-          if (kmin != 0xFFFFFFFFu) atomicMin(&keys[c0], kmin);
-        }
-      } else {
-        const unsigned grp = __match_any_sync(0xFFFFFFFFu, cc);
-        const unsigned kmin = __reduce_min_sync(grp, k);
-        if (cc != kNoCell && lane == __ffs(grp) - 1) {
-          const unsigned ch = cc / (unsigned)kNumBin;
-          atomicOr(&s_meta[ch >> 5], 1u << (ch & 31u));
-          if (kmin != 0xFFFFFFFFu) atomicMin(&keys[cc], kmin);
-        }
-      }
+        if (lane == 0 && kmin != 0xFFFFFFFFu) atomicMin(&s_keys[c0], kmin);
+      } else if (k != 0xFFFFFFFFu) atomicMin(&s_keys[cc], k);
     }
   }
   __syncthreads();
@@ -500,149 +509,46 @@ ground_fused_kernel(const __grid_constant__ GroundBatch B, const __grid_constant
       const unsigned cc = polar_cell_exact(q.x, q.y, p);
       s_cell[li] = (uint16_t)cc;
       if (cc != kNoCell) {
-        const unsigned ch = cc / (unsigned)kNumBin;
-        atomicOr(&s_meta[ch >> 5], 1u << (ch & 31u));
         float z = q.z;
         if (z == 0.f) z = 0.f;
-        if (z == z) atomicMin(&keys[cc], fkey(z));
+        if (z == z) atomicMin(&s_keys[cc], fkey(z));
       }
     }
   }
   __syncthreads();
-  // the CTA's window of the polar grid: the channels its points fall into (`own`) and one more on each side
-  if (warp == 0) {
-    const unsigned m0 = s_meta[0], m1 = s_meta[1], m2 = s_meta[2] & 0xFFFFu;
-    const unsigned n0 = m0 | (m0 << 1) | (m0 >> 1) | (m1 << 31);
-    const unsigned n1 = m1 | (m1 << 1) | (m1 >> 1) | (m0 >> 31) | (m2 << 31);
-    const unsigned n2 = (m2 | (m2 << 1) | (m2 >> 1) | (m1 >> 31)) & 0xFFFFu;
-    const unsigned need[3] = {n0, n1, n2}, own[3] = {m0, m1, m2};
-    int base = 0;
+  // flush: one global atomic per cell this CTA saw a point in
 #pragma unroll
-    for (int w = 0; w < 3; ++w) {
-      if ((need[w] >> lane) & 1u) s_chl[base + __popc(need[w] & ((1u << lane) - 1u))] = (uint8_t)((32 * w + lane) | (((own[w] >> lane) & 1u) ? 0x80 : 0));
-      base += __popc(need[w]);
-    }
-    if (lane == 0) s_meta[4] = (unsigned)base;
+  for (int j = 0; j < kKeysPerThread; ++j) {
+    const int k = tid + j * kFusedThreads;
+    if (k < kPolarCells) { const unsigned v = s_keys[k]; if (v != 0xFFFFFFFFu) atomicMin(&keys[k], v); }
   }
   phase_mark(phase_clock, 1);
   grid_barrier(F.bar, F.bar_target, B.spin_limit);
   phase_mark(phase_clock, 2);
 
-  // ---- phase 2: the polar-grid stages for the CTA's window, cells indexed as in the global grid (channel * 120 + bin)
+  // ---- phase 2: the polar grid, channels split over the first min(Gf, 80) CTAs of the frame (one halo channel per side recomputed)
   {
-    const int n_cells = (int)s_meta[4] * kNumBin;
-    // (a4) height clamp, ground_removal.cpp:192-197.  ALL of the thread's key loads are issued before the first is used: as a plain
-    // loop this was one L2 round trip (~0.7 us) per iteration, 9 us for the 70-odd channels a CTA of a dense frame needs
-    {
-      unsigned kv[kGridPerThread];
-#pragma unroll
-      for (int j = 0; j < kGridPerThread; ++j) {
-        const int l = tid + j * kFusedThreads;
-        kv[j] = 0u;
-        if (l < n_cells) { const int lc = l / kNumBin, b = l - lc * kNumBin; kv[j] = __ldcg(&keys[(s_chl[lc] & 0x7F) * kNumBin + b]); }
-      }
-#pragma unroll
-      for (int j = 0; j < kGridPerThread; ++j) {
-        const int l = tid + j * kFusedThreads;
-        if (l < n_cells) {
-          const int lc = l / kNumBin, b = l - lc * kNumBin, idx = (s_chl[lc] & 0x7F) * kNumBin + b;
-          const float zi = fkey_inv(kv[j]);
-          float h;
-          if (zi > p.t_hmin && zi < p.t_hmax) h = zi;
-          else if (zi > p.t_hmax) h = p.h_sensor;
-          else h = p.t_hmin;
-          s_H[idx] = h;
-        }
-      }
+    const int gc = Gf < kNumChannel ? Gf : kNumChannel;
+    if (cta < gc) {
+      const int own0 = cta * kNumChannel / gc, own1 = (cta + 1) * kNumChannel / gc;
+      polar_grid_slice(p, keys, own0, own1 - own0, s_H, s_G, (float*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr, F.hg, F.lim);
     }
-    __syncthreads();
-    // (a5) blur, (a6) hDiff, (a7) ground flag -- per channel, neighbours along bin
-    for (int l = tid; l < n_cells; l += kFusedThreads) {
-      const int lc = l / kNumBin, b = l - lc * kNumBin, idx = (s_chl[lc] & 0x7F) * kNumBin + b;
-      const float h = s_H[idx];
-      double acc = 0.0;                                       // gaus_blur.cpp:58-65, order j = i-1, i, i+1
-      if (b > 0) acc = __dadd_rn(acc, __dmul_rn(p.tap[0], (double)s_H[idx - 1]));
-      acc = __dadd_rn(acc, __dmul_rn(p.tap[1], (double)h));
-      if (b < kNumBin - 1) acc = __dadd_rn(acc, __dmul_rn(p.tap[2], (double)s_H[idx + 1]));
-      const float sm = (float)acc;
-      float hd;                                               // ground_removal.cpp:95-117
-      if (b == 0) hd = fsub(h, s_H[idx + 1]);
-      else if (b == kNumBin - 1) hd = fsub(h, s_H[idx - 1]);
-      else {
-        const float pre = fsub(h, s_H[idx - 1]), post = fsub(h, s_H[idx + 1]);
-        hd = (pre > post) ? pre : post;
-      }
-      s_G[idx] = ((sm < p.t_hmax && hd < p.t_hdiff) || (h < p.t_hmax && hd < p.t_hdiff)) ? 1 : 0;  // :205-214
-    }
-    __syncthreads();
-    // (a8) applyMedianFilter, ground_removal.cpp:120-146, own channels, IN PLACE: a cell flips only if its four neighbours
-    // are ground already, so no neighbour of a flipping cell is a candidate itself -- nobody reads what this pass writes
-    for (int l = tid; l < n_cells; l += kFusedThreads) {
-      const int lc = l / kNumBin, b = l - lc * kNumBin;
-      const int chl = s_chl[lc], ch = chl & 0x7F, idx = ch * kNumBin + b;
-      if ((chl & 0x80) && ch >= 1 && ch < kNumChannel - 1 && b >= 1 && b < kNumBin - 1 && !s_G[idx] && s_G[idx + 1] && s_G[idx - 1] &&
-          s_G[idx + kNumBin] && s_G[idx - kNumBin]) {
-        const float a = s_H[idx + 1], bb = s_H[idx - 1], c2 = s_H[idx + kNumBin], d = s_H[idx - kNumBin];
-        const float lo1 = fminf(a, bb), hi1 = fmaxf(a, bb), lo2 = fminf(c2, d), hi2 = fmaxf(c2, d);
-        const float m1 = fmaxf(lo1, lo2), m2 = fminf(hi1, hi2);  // the two middle values of the sorted four
-        s_H[idx] = fdiv(fadd(m1, m2), 2.f);
-        s_G[idx] = 1;
-      }
-    }
-    __syncthreads();
-    // (a8) outlierFilter, ground_removal.cpp:149-174: in place along bin, so cell b sees the value written at b-1.
-    // With T = tHmin, a cell is rewritten iff  A(b): all of b-1..b+2 ground, H[b]==T and (H[b+1]!=T or H[b+2]!=T),
-    // and its left value is not T -- either originally, or because b-1 was itself rewritten.  Two consecutive rewrites
-    // force H[b-1]==H[b]==T and H[b+1]!=T, which rules out a rewrite at b-2 (its b+2 is H[b]==T, its b+1 is T): the chain
-    // is at most two cells long, so every cell's final value is a closed form of the ORIGINAL H[b-2..b+2], G[b-2..b+2].
-    {
-      const float Tm = p.t_hmin;
-      float newh[kGridPerThread];
-      unsigned mod = 0;
-#pragma unroll
-      for (int j = 0; j < kGridPerThread; ++j) {
-        const int l = tid + j * kFusedThreads;
-        newh[j] = 0.f;
-        if (l < n_cells) {
-          const int lc = l / kNumBin, b = l - lc * kNumBin;
-          const int chl = s_chl[lc], ch = chl & 0x7F, idx = ch * kNumBin + b;
-          if ((chl & 0x80) && ch >= 1 && ch < kNumChannel - 1 && b >= 1 && b < kNumBin - 2 && s_G[idx] && s_G[idx + 1] && s_G[idx - 1] &&
-              s_G[idx + 2]) {
-            const float h1 = s_H[idx - 1], h2 = s_H[idx], h3 = s_H[idx + 1], h4 = s_H[idx + 2];
-            if (h2 == Tm && (h3 != Tm || h4 != Tm)) {               // A(b)
-              float left = h1;
-              bool ok = (h1 != Tm);
-              if (!ok && b - 1 >= 1 && s_G[idx - 2]) {              // was b-1 rewritten?  A(b-1) with H[b]==T needs H[b+1]!=T
-                const float h0 = s_H[idx - 2];
-                if (h3 != Tm && h0 != Tm) { left = fdiv(fadd(h0, h3), 2.f); ok = true; }   // b-1 took its second branch
-              }
-              if (ok) { newh[j] = (h3 != Tm) ? fdiv(fadd(left, h3), 2.f) : fdiv(fadd(left, h4), 2.f); mod |= 1u << j; }
-            }
-          }
-        }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int j = 0; j < kGridPerThread; ++j)
-        if (mod & (1u << j)) {
-          const int l = tid + j * kFusedThreads, lc = l / kNumBin, b = l - lc * kNumBin;
-          s_H[(s_chl[lc] & 0x7F) * kNumBin + b] = newh[j];
-        }
-    }
-    __syncthreads();
-    // hGround == height for every ground cell (updateGround() follows every height write of a ground cell)
-    if (out.dbg_hg)
-      for (int l = tid; l < n_cells; l += kFusedThreads) {
-        const int lc = l / kNumBin, b = l - lc * kNumBin;
-        const int chl = s_chl[lc], idx = (chl & 0x7F) * kNumBin + b;
-        if (chl & 0x80) out.dbg_hg[idx] = s_G[idx] ? s_H[idx] : -INFINITY;
-      }
   }
   phase_mark(phase_clock, 3);
+  grid_barrier(F.bar, F.bar_target + (unsigned)Gf, B.spin_limit);
   phase_mark(phase_clock, 4);
 
-  // ---- phase 3: labels (ground_removal.cpp:221-247) from the CTA's own copy of the grid, per-warp counts
+  // ---- phase 3: labels (ground_removal.cpp:221-247), per-warp counts
   unsigned labs = 0;                                // 2 bits per tile: 0 dropped, 1 ground, 2 elevated
+  // label limits of this thread's points in the resident tiles: all loads issued before the first is used (one L2 round trip for
+  // the whole chunk instead of one per tile)
+  float lv[kMaxResTiles];
+#pragma unroll
+  for (int t = 0; t < kMaxResTiles; ++t) {
+    lv[t] = __int_as_float(0x7FC00000);
+    const int li = t * kTilePts + tid;
+    if (t < T && li < cnt) { const unsigned c = s_cell[li]; if (c < kPreFiltered) lv[t] = __ldcg(&F.lim[c]); }
+  }
   for (int t = 0; t < T; ++t) {
     const int li = t * kTilePts + tid;
     int lab = 0;
@@ -651,8 +557,13 @@ ground_fused_kernel(const __grid_constant__ GroundBatch B, const __grid_constant
       if (c == kNoCell) lab = p.prefilter ? 3 : 0;      // in neither output; with the node pre-filters on: still an aux point
       else if (c != kPreFiltered) {
         const float z = (t < res_tiles) ? s_pts[li].z : __ldg(&pts[beg + li]).z;
-        // hGround of a non-ground cell is never read by the reference (:236); such points are elevated
-        lab = (s_G[c] && (double)z < __dadd_rn((double)s_H[c], p.tol)) ? 1 : 2;   // :236-246
+        float lm;
+        switch (t) {                                            // (register array: constant indices only)
+          case 0: lm = lv[0]; break; case 1: lm = lv[1]; break; case 2: lm = lv[2]; break; case 3: lm = lv[3]; break;
+          case 4: lm = lv[4]; break; case 5: lm = lv[5]; break; case 6: lm = lv[6]; break;
+          default: lm = __ldcg(&F.lim[c]);
+        }
+        lab = (z <= lm) ? 1 : 2;                                // == (double)z < hGround + 0.25 on a ground cell (:236-246), see label_limit
       }
     }
     labs |= (unsigned)lab << (2 * t);
@@ -795,6 +706,7 @@ int ground_alloc(Ctx* c, Slot* s) {
   LMOT_CUDA(c, cudaMalloc(&s->d_smoothed, kPolarCells * sizeof(float)));
   LMOT_CUDA(c, cudaMalloc(&s->d_hdiff, kPolarCells * sizeof(float)));
   LMOT_CUDA(c, cudaMalloc(&s->d_hg, kPolarCells * sizeof(float)));
+  LMOT_CUDA(c, cudaMalloc(&s->d_lim, kPolarCells * sizeof(float)));
   LMOT_CUDA(c, cudaMalloc(&s->d_labels, np));
   LMOT_CUDA(c, cudaMalloc(&s->d_elev, np * sizeof(float4)));
   LMOT_CUDA(c, cudaMalloc(&s->d_ground, np * sizeof(float4)));
@@ -814,7 +726,7 @@ int ground_alloc(Ctx* c, Slot* s) {
 
 void ground_free(Slot* s) {
   cudaFree(s->d_points); cudaFree(s->d_stage_in); cudaFree(s->d_cell); cudaFree(s->d_polar_key); cudaFree(s->d_minz);
-  cudaFree(s->d_height); cudaFree(s->d_smoothed); cudaFree(s->d_hdiff); cudaFree(s->d_hg); cudaFree(s->d_hg_dbg); cudaFree(s->d_labels);
+  cudaFree(s->d_height); cudaFree(s->d_smoothed); cudaFree(s->d_hdiff); cudaFree(s->d_hg); cudaFree(s->d_lim); cudaFree(s->d_hg_dbg); cudaFree(s->d_labels);
   cudaFree(s->d_elev); cudaFree(s->d_ground); cudaFree(s->d_gdesc); cudaFree(s->d_gbar); cudaFree(s->d_counters);
   if (s->h_counters) cudaFreeHost(s->h_counters);
   if (s->h_set) cudaFreeHost(s->h_set);
@@ -878,6 +790,8 @@ int ground_launch_batch(Ctx* c, Slot* const* slots, int F, const float4* const* 
     f.keys = s->d_polar_key + parity * kPolarCells;
     f.keys_next = s->d_polar_key + (1 - parity) * kPolarCells;
     f.bar = s->d_gbar; f.bar_target = s->bar_base + (unsigned)G;
+    f.hg = want_labels ? s->d_hg : nullptr; f.lim = s->d_lim;
+    s->hg_valid = want_labels;
     f.epoch = s->epoch; f.desc = s->d_gdesc;
     f.out.labels = want_labels ? s->d_labels : nullptr;
     f.out.elev = s->d_elev; f.out.ground = s->d_ground;
@@ -885,12 +799,8 @@ int ground_launch_batch(Ctx* c, Slot* const* slots, int F, const float4* const* 
     f.out.cart_once = fuse_count ? s->d_cart_bits : nullptr;
     f.out.cart_twice = fuse_count ? s->d_cart_bits + 2000 : nullptr;
     f.out.counters = s->d_counters;
-    f.out.dbg_hg = want_labels ? s->d_hg : nullptr;
-    s->bar_base += (unsigned)G;
+    s->bar_base += 2u * (unsigned)G;
   }
-  // stage entry points: the CTAs leave hGround of the cells they evaluated in d_hg; whatever no CTA needed stays NaN (0xFF bytes)
-  if (want_labels)
-    for (int i = 0; i < F; ++i) LMOT_CUDA(c, cudaMemsetAsync(slots[i]->d_hg, 0xFF, kPolarCells * sizeof(float), st));
   float roi = c->prm.roi_m;
   GroundParams gp = c->gp;
   void* args[] = {(void*)&B, (void*)&gp, (void*)&roi, (void*)&c->d_phase_clock};

@@ -53,6 +53,9 @@ struct TrackState {
   uint8_t isStatic, isVisBB;
 };
 
+// planar rigid transform, rows (m0 m1 . m2) / (m3 m4 . m5) of a 4x4 whose third row is (0 0 1 0): lmot_params.global_frame
+struct Xf2 { int on = 0; float m[6] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f}; };
+
 // frame-level scalars of imm_ukf_jpda.cpp:19-24,56-58 (host side: a handful of doubles per frame)
 struct TrackerHost {
   bool init = false;
@@ -84,6 +87,7 @@ struct Result {
   cudaEvent_t ev_done = nullptr;
   bool in_flight = false;              // submitted and not yet collected / dropped
   bool has_tracks = false;             // went through the tracker (frame) or not (detect only)
+  Xf2 back;                            // global_frame: global -> sensor transform of this frame, applied by publish_kernel
   // timing (lmot_enable_timing): stage boundaries and one event after every kernel
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t kev[kMaxKernelEvents] = {};
@@ -113,7 +117,9 @@ struct Slot {
   float* d_height = nullptr;           // [9600]
   float* d_smoothed = nullptr;         // [9600]
   float* d_hdiff = nullptr;            // [9600]
-  float* d_hg = nullptr;               // [9600] stage entry points: hGround of the cells some CTA evaluated (-inf: not ground, NaN: nobody needed it)
+  float* d_hg = nullptr;               // [9600] stage entry points: hGround of ground cells as the fused kernel evaluated it, -inf for non-ground cells
+  bool hg_valid = false;               // the last launch wrote d_hg
+  float* d_lim = nullptr;              // [9600] label limit of every cell (ground.cu label_limit): ground phase 2 -> phase 3
   float* d_hg_dbg = nullptr;           // [9600] the same grid recomputed as a whole by polar_grid_debug_kernel (allocated on first use)
   uint8_t* d_labels = nullptr;         // per point 0/1/2
   float4* d_elev = nullptr;            // compacted elevated cloud
@@ -148,6 +154,7 @@ struct Slot {
   float* d_cl_marker = nullptr;        // [max_clusters+1][6]
   uint8_t* d_cl_ok = nullptr;          // [max_clusters+1] rule filter verdict
   float* d_boxes = nullptr;            // [max_boxes][8][3] accepted boxes, cluster-id order
+  float* d_boxes_g = nullptr;          // [max_boxes][8][3] the same list in the dead-reckoned global frame (lmot_params.global_frame)
   float* d_markers = nullptr;          // [max_boxes][6]
   int* d_done = nullptr;               // last-CTA-done counter
   int* d_det_sem = nullptr;            // semaphore: +1 by box_fit_kernel's last CTA (frame submissions), -1 by spawn_output_kernel
@@ -180,6 +187,7 @@ struct Ctx {
   int last_ground_ctas = 0;
   unsigned long long* d_fit_clock = nullptr;     // diagnostic: [CTAs][8] stamps of the last box_fit_kernel launch (same switch)
   int last_fit_ctas = 0;
+  int ccl_variant = 3;                 // 3: ccl_dense_kernel; 2: ccl_bitmap_kernel (LMOT_CCL, A/B diagnostics)
   unsigned long long* d_ccl_clock = nullptr;     // diagnostic: [frames][16] %globaltimer stamps of the last ccl_bitmap_kernel launch (same switch)
   bool zero_copy = false;              // lmot_frame_submit: pinned host frames are read by the ground kernel directly (LMOT_ZERO_COPY=1; off: slower than the copy engine)
   bool ground_half_sms = true;         // frame pipeline: ground kernel on half of the SMs (ground.cu ground_launch; LMOT_GROUND_HALF=0 disables, A/B only)
@@ -294,6 +302,8 @@ void tracker_free(Ctx* c);
 // boxes: device float[M][8][3] with M in det_counters[CNT_N_BOXES]; results into the slot's pinned host block
 int tracker_launch(Ctx* c, Slot* s, cudaStream_t st, const float* d_boxes, const int* det_counters, double timestamp, double v_gps,
                    double yaw_gps, bool gate = false, bool* gated = nullptr);   // gate: wait for the slot's detection semaphore on the device (tracker.cu)
+int boxes_to_global_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, const int* det_counters, double timestamp, double v_gps,
+                           double yaw_gps, bool post_sem);
 int tracker_publish(Ctx* c, Result* r, cudaStream_t st);            // device block of r -> pinned host block
 int boxes_publish(Ctx* c, Slot* s, Result* r, cudaStream_t st);     // detection-only: slot box list -> pinned host block
 

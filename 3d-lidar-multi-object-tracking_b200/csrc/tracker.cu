@@ -1140,7 +1140,7 @@ __device__ __noinline__ void tc_candidate(TCFastShared& S, int v, int jt) {
 }
 
 __device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict__ tracks, int* __restrict__ trk, int* __restrict__ det,
-                                        const float* __restrict__ boxes, int* __restrict__ first_setter, double ego_yaw, int max_tracks,
+                                        const float* __restrict__ boxes, const float* __restrict__ boxes_pub, int* __restrict__ first_setter, double ego_yaw, int max_tracks,
                                         const OutPtrs& o, const OutPtrs& prev, int* __restrict__ act_list, double4* __restrict__ pos,
                                         const ActSummary* __restrict__ summary, int T0, int n_act0, int M, unsigned long long* __restrict__ trace,
                                         unsigned long long* __restrict__ phase) {
@@ -1166,7 +1166,7 @@ __device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict_
   const int nbx = M * 6, ntg = cp ? (T0 * 12 + 15) / 16 : 0, ntm = cp ? (T0 * 4 + 15) / 16 : 0, nsv = cp ? (T0 + 15) / 16 : 0;
   uint4 vbx[UB], vtg[UT], vtm[UM], vst[1], vvi[1];
   double pz[UY], pv[UY];
-  cta_load(vbx, reinterpret_cast<const uint4*>(boxes), nbx);
+  cta_load(vbx, reinterpret_cast<const uint4*>(boxes_pub), nbx);     // (sensor-frame list; `boxes` is the tracker's input, in the global frame when lmot_params.global_frame is on)
   const int fs0 = (tid < M) ? first_setter[tid] : 0;            // first pass of the spawn loop below
   float bc[8] = {0, 0, 0, 0, 0, 0, 0, 0};                      // corners 0..3 (x, y) of this thread's box
   if (tid < M) {
@@ -1188,7 +1188,7 @@ __device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict_
   }
   // ---- stores (and the rare remainders beyond the first batch of each array)
   cta_store(reinterpret_cast<uint4*>(o.boxes), vbx, nbx);
-  if (nbx > UB * kTCThreads) cta_copy<uint4, UB>(reinterpret_cast<uint4*>(o.boxes) + UB * kTCThreads, reinterpret_cast<const uint4*>(boxes) + UB * kTCThreads, nbx - UB * kTCThreads);
+  if (nbx > UB * kTCThreads) cta_copy<uint4, UB>(reinterpret_cast<uint4*>(o.boxes) + UB * kTCThreads, reinterpret_cast<const uint4*>(boxes_pub) + UB * kTCThreads, nbx - UB * kTCThreads);
   cta_store(reinterpret_cast<uint4*>(o.targets), vtg, ntg);
   if (ntg > UT * kTCThreads) cta_copy<uint4, UT>(reinterpret_cast<uint4*>(o.targets) + UT * kTCThreads, reinterpret_cast<const uint4*>(prev.targets) + UT * kTCThreads, ntg - UT * kTCThreads);
   cta_store(reinterpret_cast<uint4*>(o.track_manage), vtm, ntm);
@@ -1383,7 +1383,7 @@ __device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict_
 // `full` (first step after the table was written from the host): everything is rebuilt from the records.
 __global__ void __launch_bounds__(kTCThreads, 2)
 spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int* __restrict__ det, const float* __restrict__ boxes,
-                    int* __restrict__ first_setter, int* __restrict__ imax_arr, int* __restrict__ vis_list,
+                    const float* __restrict__ boxes_pub, int* __restrict__ first_setter, int* __restrict__ imax_arr, int* __restrict__ vis_list,
                     uint8_t* __restrict__ has5_arr, int first_frame, int compat_first, double ego_yaw, int max_tracks, OutPtrs o,
                     OutPtrs prev, int full, int* __restrict__ act_list, double4* __restrict__ pos, const ActSummary* __restrict__ summary,
                     unsigned long long* __restrict__ trace, unsigned long long* __restrict__ phase, int* __restrict__ det_sem,
@@ -1398,7 +1398,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   if (!full && !(first_frame && compat_first) && trk[CNT_N_ACT] <= kTCThreads) {
     __shared__ TCFastShared s_fast;
     const int M = det[CNT_N_BOXES];
-    tc_fast(s_fast, tracks, trk, det, boxes, first_setter, ego_yaw, max_tracks, o, prev, act_list, pos, summary, trk[CNT_N_TRACKS], trk[CNT_N_ACT], M, trace, phase);
+    tc_fast(s_fast, tracks, trk, det, boxes, boxes_pub, first_setter, ego_yaw, max_tracks, o, prev, act_list, pos, summary, trk[CNT_N_TRACKS], trk[CNT_N_ACT], M, trace, phase);
     return;
   }
   __shared__ int s_w[33];
@@ -1433,10 +1433,10 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
       det[CNT_ERROR] = 0;
     }
     for (int b = tid; b < M; b += kTCThreads) first_setter[b] = INT_MAX;
-    for (int e = tid; e < M * 24; e += kTCThreads) o.boxes[e] = boxes[e];
+    for (int e = tid; e < M * 24; e += kTCThreads) o.boxes[e] = boxes_pub[e];
     return;
   }
-  for (int e = tid; e < M * 24; e += kTCThreads) o.boxes[e] = boxes[e];     // the frame's box list travels with its results
+  for (int e = tid; e < M * 24; e += kTCThreads) o.boxes[e] = boxes_pub[e];     // the frame's box list travels with its results
 
   // ---- start the frame's result block from the previous one (dead tracks: unchanged), refresh the positions of the
   // active tracks, collect the visible ones (a subset of the active list, which is sorted by track index)
@@ -1635,9 +1635,17 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, size_t bytes,
   for (size_t e = tid; e < n16; e += nthreads) d[e] = s[e];
 }
 
+// p' = M p as pcl::transformPointCloud evaluates it with the Eigen::Matrix4f pcl_ros builds from a tf::Transform: single
+// precision, ((m0 x + m1 y) + m2 z) + m3 per row, no contraction.  Planar rigid transforms only: row 2 is (0, 0, 1, 0).
+__device__ __forceinline__ void xf_apply(const Xf2& M, float x, float y, float z, float& ox, float& oy, float& oz) {
+  ox = fadd(fadd(fadd(fmul(M.m[0], x), fmul(M.m[1], y)), fmul(0.f, z)), M.m[2]);
+  oy = fadd(fadd(fadd(fmul(M.m[3], x), fmul(M.m[4], y)), fmul(0.f, z)), M.m[5]);
+  oz = fadd(fadd(fadd(fmul(0.f, x), fmul(0.f, y)), fmul(1.f, z)), 0.f);
+}
+
 constexpr int kPubThreads = 128;    // small on purpose: it may sit on an SM polling while detection kernels need that SM's registers
 __global__ void __launch_bounds__(kPubThreads)
-publish_kernel(OutPtrs d, OutPtrs h, const unsigned* __restrict__ tc_seq, unsigned want, unsigned spin_limit) {
+publish_kernel(OutPtrs d, OutPtrs h, const unsigned* __restrict__ tc_seq, unsigned want, unsigned spin_limit, Xf2 back) {
   const int tid = threadIdx.x;
   if (tid == 0) {              // wait until `want` tracker steps have completed (spawn_output_kernel counts them)
     unsigned spin = 0, v;
@@ -1649,13 +1657,33 @@ publish_kernel(OutPtrs d, OutPtrs h, const unsigned* __restrict__ tc_seq, unsign
   __syncthreads();
   const int T = d.hdr[HDR_N_TRACKS], V = d.hdr[HDR_N_VIS], M = d.hdr[HDR_N_BOXES];
   copy16(h.boxes, d.boxes, (size_t)M * 96, tid, kPubThreads);
-  copy16(h.targets, d.targets, (size_t)T * 12, tid, kPubThreads);
+  if (!back.on) {
+    copy16(h.targets, d.targets, (size_t)T * 12, tid, kPubThreads);
+    copy16(h.vis_bb, d.vis_bb, (size_t)V * 96, tid, kPubThreads);
+  } else {
+    // global frame -> sensor frame for what the node publishes (tracking/main.cpp:182-195); the device block stays global:
+    // the next step starts from it
+    for (int i = tid; i < T; i += kPubThreads) xf_apply(back, d.targets[3 * i], d.targets[3 * i + 1], d.targets[3 * i + 2], h.targets[3 * i], h.targets[3 * i + 1], h.targets[3 * i + 2]);
+    for (int i = tid; i < V * 8; i += kPubThreads) xf_apply(back, d.vis_bb[3 * i], d.vis_bb[3 * i + 1], d.vis_bb[3 * i + 2], h.vis_bb[3 * i], h.vis_bb[3 * i + 1], h.vis_bb[3 * i + 2]);
+  }
   copy16(h.vandyaw, d.vandyaw, (size_t)T * 16, tid, kPubThreads);
   copy16(h.track_manage, d.track_manage, (size_t)T * 4, tid, kPubThreads);
   copy16(h.is_static, d.is_static, (size_t)T, tid, kPubThreads);
   copy16(h.is_vis, d.is_vis, (size_t)T, tid, kPubThreads);
-  copy16(h.vis_bb, d.vis_bb, (size_t)V * 96, tid, kPubThreads);
   copy16(h.hdr, d.hdr, HDR_COUNT * sizeof(int), tid, kPubThreads);
+}
+
+// lmot_params.global_frame: the frame's boxes (sensor frame) -> the dead-reckoned global frame the tracker works in
+// (tracking/main.cpp:142-158: pcl_ros::transformPointCloud("/global", bBoxes[i], ...)).  One CTA; also takes over posting the
+// detection semaphore from box fitting, because the tracker must not start before this list exists.
+__global__ void __launch_bounds__(256)
+boxes_to_global_kernel(const float* __restrict__ boxes, const int* __restrict__ det, float* __restrict__ boxes_g, Xf2 fwd, int* __restrict__ det_sem) {
+  const int M = det[CNT_N_BOXES];
+  for (int i = threadIdx.x; i < M * 8; i += 256) xf_apply(fwd, boxes[3 * i], boxes[3 * i + 1], boxes[3 * i + 2], boxes_g[3 * i], boxes_g[3 * i + 1], boxes_g[3 * i + 2]);
+  if (det_sem) {
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(det_sem, 1); }
+  }
 }
 
 // detection-only submissions: the box list of the slot -> the result's host block
@@ -1746,9 +1774,49 @@ void origin_points_fold(TrackerHost& h, double timestamp, double v_gps, double y
 }
 
 // boxes: device float[M][8][3] with M in det_counters[CNT_N_BOXES]; results into the DEVICE block of sl->res
+// planar rigid transform of the "global" frame: pose (x, y, yaw) of `global` in the sensor frame, as the tracking node broadcasts it
+// (tracking/main.cpp:76-83: setOrigin(egoPoints[0][0..1]), setRPY(0, 0, egoPoints[0][2])).  back: global -> sensor = that pose
+// itself; fwd: sensor -> global = its inverse.  The 3x3 basis as tf::Matrix3x3::setRotation derives it from the quaternion
+// tf::Quaternion::setRPY builds, the inverse as tf::Transform::inverse() (transpose, -(R^T t)), all in double, then narrowed to
+// the Eigen::Matrix4f pcl_ros::transformPointCloud multiplies with.  (tf / pcl_ros are not in /root/reference: this arithmetic is
+// the documented contract of this library, tests/test_global_frame_gpu.py restates it in numpy.)
+void global_frame_xf(const double ego[3], Xf2* fwd, Xf2* back) {
+  const double half = ego[2] * 0.5;
+  const double qz = sin(half), qw = cos(half);        // setRPY(0, 0, yaw): x = y = 0
+  const double d = qz * qz + qw * qw, s = 2.0 / d;
+  const double zs = qz * s, wz = qw * zs, zz = qz * zs;
+  const double r00 = 1.0 - zz, r01 = -wz, r10 = wz, r11 = 1.0 - zz;
+  back->on = 1;
+  back->m[0] = (float)r00; back->m[1] = (float)r01; back->m[2] = (float)ego[0];
+  back->m[3] = (float)r10; back->m[4] = (float)r11; back->m[5] = (float)ego[1];
+  // inverse: basis transposed, origin -(R^T t)
+  const double tx = -(r00 * ego[0] + r10 * ego[1]), ty = -(r01 * ego[0] + r11 * ego[1]);
+  fwd->on = 1;
+  fwd->m[0] = (float)r00; fwd->m[1] = (float)r10; fwd->m[2] = (float)tx;
+  fwd->m[3] = (float)r01; fwd->m[4] = (float)r11; fwd->m[5] = (float)ty;
+}
+
+// sensor-frame boxes of slot `sl` -> sl->d_boxes_g in the global frame of THIS frame's ego pose (peeked: tracker_launch folds it);
+// post_sem: post the slot's detection semaphore afterwards (frame pipeline)
+int boxes_to_global_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, const int* det_counters, double timestamp, double v_gps,
+                           double yaw_gps, bool post_sem) {
+  TrackerHost peek = c->th;
+  origin_points_fold(peek, timestamp, v_gps, yaw_gps);
+  Xf2 fwd, back;
+  global_frame_xf(peek.egoPoint, &fwd, &back);
+  boxes_to_global_kernel<<<1, 256, 0, st>>>(d_boxes, det_counters, sl->d_boxes_g, fwd, post_sem ? sl->d_det_sem : nullptr);
+  kernel_mark(c, sl, st);
+  LMOT_CUDA(c, cudaGetLastError());
+  return LMOT_OK;
+}
+
 int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, const int* det_counters, double timestamp, double v_gps,
                    double yaw_gps, bool gate, bool* gated) {
   origin_points_fold(c->th, timestamp, v_gps, yaw_gps);
+  // global_frame: the tracker reads the list boxes_to_global_launch prepared, the results carry the sensor-frame list
+  const float* d_boxes_pub = d_boxes;
+  if (c->prm.global_frame) { d_boxes = sl->d_boxes_g; Xf2 fwd; global_frame_xf(c->th.egoPoint, &fwd, &sl->res->back); }
+  else sl->res->back.on = 0;
   TrackerHost& h = c->th;
   Result* r = sl->res;
   OutPtrs o{r->d_targets, r->d_vandyaw, r->d_manage, r->d_static, r->d_vis, r->d_visbb, r->d_hdr, r->d_boxes};
@@ -1819,7 +1887,7 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(1); cfg.blockDim = dim3(kTCThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cfg.attrs = &pdl; cfg.numAttrs = 1;
-    LMOT_CUDA(c, cudaLaunchKernelEx(&cfg, spawn_output_kernel, c->d_tracks, c->d_trk_counters, det, d_boxes, c->d_first_setter, c->d_new_num,
+    LMOT_CUDA(c, cudaLaunchKernelEx(&cfg, spawn_output_kernel, c->d_tracks, c->d_trk_counters, det, d_boxes, d_boxes_pub, c->d_first_setter, c->d_new_num,
                                     c->d_vis_list, c->d_skip, first, compat, h.egoPoint[2], c->prm.max_tracks, o, po, full, c->d_act_list,
                                     c->d_pos, reinterpret_cast<const ActSummary*>(c->d_summary), trace, phase, det_sem, c->d_tc_seq));
     ++c->tc_launched;
@@ -1836,7 +1904,7 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
 int tracker_publish(Ctx* c, Result* r, cudaStream_t st) {
   OutPtrs d{r->d_targets, r->d_vandyaw, r->d_manage, r->d_static, r->d_vis, r->d_visbb, r->d_hdr, r->d_boxes};
   OutPtrs h{r->h_targets, r->h_vandyaw, r->h_manage, r->h_static, r->h_vis, r->h_visbb, r->h_hdr, r->h_boxes};
-  publish_kernel<<<1, kPubThreads, 0, st>>>(d, h, c->d_tc_seq, c->tc_launched, c->spin_limit);
+  publish_kernel<<<1, kPubThreads, 0, st>>>(d, h, c->d_tc_seq, c->tc_launched, c->spin_limit, r->back);
   LMOT_CUDA(c, cudaGetLastError());
   return LMOT_OK;
 }

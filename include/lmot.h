@@ -96,6 +96,13 @@ typedef struct lmot_params {
   float filter_z_min, filter_z_max;   /* -3.0, 1.0  (ROS params filter_z_min / filter_z_max, main.cpp:147-148) */
   float filter_x_min, filter_x_max;   /* -15, 5     (main.cpp:68-71) */
   float filter_y_min, filter_y_max;   /* -50, 50    (main.cpp:73-76) */
+  /* The `tracking` ROS node does not hand the boxes to immUkfJpdaf as they come: it moves them into a dead-reckoned "global" frame
+   * first (pose of that frame in the sensor frame = egoPoints[0] of getOriginPoints, broadcast as tf velodyne -> global) and moves
+   * targetPoints / visBBs back afterwards (tracking/main.cpp:76-83,142-158,182-195).  1: lmot_track_step / lmot_frame* / lmot_batch*
+   * do the same on the device: boxes in, targets / vis_bb out stay in the SENSOR frame, the tracker state (and what lmot_tracker_dump
+   * shows) is in the global frame.  0 (default): immUkfJpdaf as a function, boxes used as given.  The transform arithmetic is
+   * pcl_ros::transformPointCloud's (float 4x4 from a double tf::Transform); tf and pcl_ros are not part of the reference tree. */
+  int global_frame;          /* 0 */
   /* frames in flight inside one context: detection stages of frame f+1.. overlap the tracker of frame f (1..8, default 4) */
   int pipeline_depth;
   /* result blocks (pinned host memory) = how many submitted frames may wait to be collected (1..64, default 32) */

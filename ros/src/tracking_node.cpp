@@ -3,14 +3,19 @@
 // Same ROS surface as the reference's node (object_tracking/tracking/main.cpp:413-445): node "obj_track", subscribes
 // "track_box" (object_tracking/trackbox) and "/gps/odom" (ego speed / yaw), publishes the track markers on
 // "visualization_marker" (arrows, coloured points) and the visible boxes on "visualization_marker2".
-// getOriginPoints + immUkfJpdaf are ONE liblmot call (lmot_track_step).  The reference moves the boxes into a "global" frame
-// with tf before tracking and back afterwards (main.cpp:142-195); with the ego pose folded inside lmot_track_step that round
-// trip is the identity on what is published, so the shell stays in the sensor frame.  Timestamps are passed in microseconds
-// (the reference's tracker divides by 1e6, imm_ukf_jpda.cpp:807; its own shell passes seconds -- a bug not reproduced here).
+// getOriginPoints + the tf round trip + immUkfJpdaf are ONE liblmot call: with lmot_params.global_frame = 1, lmot_track_step moves the
+// boxes into the dead-reckoned "global" frame on the device before tracking and moves targets / visible boxes back afterwards,
+// exactly where the reference calls pcl_ros::transformPointCloud (main.cpp:142-158,182-195); the UKF states, velocities,
+// distFromInit and the static flag are therefore world-frame quantities as in the reference node.  The velodyne -> global transform
+// is broadcast from lmot_origin_points like main.cpp:76-83 does from getOriginPoints.
+// Timestamp: the reference node passes header.stamp.toSec() -- SECONDS -- to a tracker that divides by 1e6 (imm_ukf_jpda.cpp:807),
+// i.e. the deployed reference runs with dt ~ 1e-7 s.  Default here = the same (drop-in for what is deployed); the private parameter
+// ~stamp_in_microseconds:=true feeds the physically meaningful value instead.
 // Needs ROS (catkin) and the package's generated message headers.
 #include <ros/ros.h>
 #include <nav_msgs/Odometry.h>
 #include <tf/transform_datatypes.h>
+#include <tf/transform_broadcaster.h>
 #include <visualization_msgs/Marker.h>
 #include <object_tracking/trackbox.h>
 #include <cmath>
@@ -22,6 +27,7 @@ namespace {
 lmot_ctx* g_ctx = nullptr;
 ros::Publisher g_pub_markers, g_pub_boxes;
 double g_v_gps = 0.0, g_yaw_gps = 0.0;
+bool g_stamp_us = false;
 constexpr int kCap = 8192;
 std::vector<float> g_boxes, g_targets((size_t)kCap * 3), g_visbb((size_t)kCap * 24);
 std::vector<double> g_vy((size_t)kCap * 2);
@@ -48,9 +54,21 @@ void on_boxes(const object_tracking::trackbox& in) {
   lmot_track_out o{};
   o.cap = kCap; o.targets = g_targets.data(); o.vandyaw = g_vy.data(); o.track_manage = g_manage.data();
   o.is_static = g_static.data(); o.is_vis = g_vis.data(); o.vis_bb = g_visbb.data();
-  const double stamp_us = in.header.stamp.toSec() * 1.0e6;
-  const int rc = lmot_track_step(g_ctx, g_boxes.data(), m, stamp_us, g_v_gps, g_yaw_gps, &o);
-  if (rc != LMOT_OK) { ROS_ERROR_THROTTLE(1.0, "lmot_track_step: %s (%s)", lmot_strerror(rc), lmot_last_error(g_ctx)); return; }
+  const double stamp = g_stamp_us ? in.header.stamp.toSec() * 1.0e6 : in.header.stamp.toSec();      // main.cpp:72
+  // tf velodyne -> global from this frame's ego pose (main.cpp:74-83); lmot_origin_points peeks, lmot_track_step folds the same values
+  double ego[6];
+  if (lmot_origin_points(g_ctx, stamp, g_v_gps, g_yaw_gps, ego) == LMOT_OK) {
+    static tf::TransformBroadcaster br;
+    tf::Transform transform;
+    transform.setOrigin(tf::Vector3(ego[0], ego[1], 0.0));
+    tf::Quaternion q;
+    q.setRPY(0, 0, ego[2]);
+    transform.setRotation(q);
+    br.sendTransform(tf::StampedTransform(transform, in.header.stamp, "velodyne", "global"));
+  }
+  const int rc = lmot_track_step(g_ctx, g_boxes.data(), m, stamp, g_v_gps, g_yaw_gps, &o);
+  if (rc < 0) { ROS_ERROR_THROTTLE(1.0, "lmot_track_step: %s (%s)", lmot_strerror(rc), lmot_last_error(g_ctx)); return; }
+  if (rc > 0) ROS_WARN_THROTTLE(10.0, "lmot_track_step: %s", lmot_strerror(rc));      // e.g. track table full: outputs are valid, keep publishing
 
   // arrows: moving, visible, live tracks (speed = length, yaw = direction)
   for (int i = 0; i < o.n_tracks; ++i) {
@@ -91,8 +109,10 @@ int main(int argc, char** argv) {
   lmot_params prm;
   lmot_default_params(&prm);
   prm.max_tracks = kCap;
+  prm.global_frame = 1;          // track in the dead-reckoned global frame like the reference node (main.cpp:142-195)
   int device = 0;
   nh.param<int>("cuda_device", device, 0);
+  ros::NodeHandle("~").param<bool>("stamp_in_microseconds", g_stamp_us, false);
   const int rc = lmot_create(&g_ctx, &prm, device);
   if (rc != LMOT_OK) { ROS_FATAL("lmot_create: %s -- this node has no CPU path", lmot_strerror(rc)); return 1; }
   g_pub_markers = nh.advertise<visualization_msgs::Marker>("visualization_marker", 0);
