@@ -18,6 +18,13 @@ Printed JSON (rank 0, one line):
   roofline  ground_fused_kernel (the whole ground-removal stage in one cooperative launch, the only stage that streams
             the whole frame): algorithmic bytes per frame / its CUDA-event duration, vs the measured HBM peak
   cpu_baseline  the reference's own four entry points on a bounded sample of the same frames, one host thread
+  parity_check  the CUDA path against the reference ON THE BENCH SCENE, frame by frame over the cpu_baseline sample: counts, boxes
+            (bit-exact), trackManage (identical), UKF states of well-conditioned tracks (<= 1e-4); a failing check withholds `value`
+  windows   the K-step timed region is repeated `windows` times on consecutive frames (barrier + synchronize on both sides of
+            each); `value`, `ms_per_step` and `e2e` are the MEDIAN window, `window_values` lists all of them
+  latency_us    p50 / p99 per stage and per frame, one frame in flight (CUDA events) and at the pipeline's depth (host clock)
+  batched_8x120k  BASELINE.json configs[3]: 8 sensor streams, one frame each per tick, one shared track table: ticks through
+            lmot_batch_dev, and the ground_removal + CCL roofline of the two batched launches
 """
 from __future__ import annotations
 
@@ -46,6 +53,7 @@ KERNEL_NAMES = ("ground_fused", "ccl_cluster", "tile_hist", "seg_offsets", "scat
 # `ncu --set full` capture profiles/r1z_ncu_full_ground.csv (2.03 MB read: the frame once, plus the polar grid; 0 bytes
 # written: the 3.9 MB of output clouds stay in the 126 MB L2 within the measured launch)
 TRAFFIC_NCU = 2.03e6
+TRAFFIC_SOURCE = "constant: ncu --set full capture of round 1 (profiles/r1z_ncu_full_ground.csv), not measured by this run"
 KERNELS_PER_FRAME = len(KERNEL_NAMES) + 2   # ground 1 (also bins the elevated points) + cluster 1 + box 4 + tracker 3, + the tracker's gate kernel + publish_kernel
 
 
@@ -288,7 +296,7 @@ def tracker_stress(ctx, steps=40, warm=5):
             "kernel_us": {n: float(1e3 * v) for n, v in zip(("imm_predict_gate", "imm_update", "spawn_output"), np.mean(np.array(kern), 0))}}
 
 
-def run_native_e2e(frames, W, K, n_pts, rank, local_rank, world):
+def run_native_e2e(frames, W, K, n_pts, rank, local_rank, world, windows=1, in_flight=0):
     """host/frame_loop (C++ submit / collect loop over the C ABI, pinned host frames) on this rank's GPU.
     -> (parsed JSON line, None) or (None, reason); never raises, no collectives inside."""
     import tempfile
@@ -312,13 +320,13 @@ def run_native_e2e(frames, W, K, n_pts, rank, local_rank, world):
         env = dict(os.environ)
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
         env["CUDA_VISIBLE_DEVICES"] = (vis.split(",")[local_rank] if vis else str(local_rank))
-        out = subprocess.run([drv, path, str(W + K), str(n_pts), str(W), str(K), "100000"], env=env, stdout=subprocess.PIPE,
+        out = subprocess.run([drv, path, str(len(frames)), str(n_pts), str(W), str(K), "100000", str(windows), str(in_flight)], env=env, stdout=subprocess.PIPE,
                              stderr=subprocess.PIPE, text=True, timeout=600)
         if out.returncode != 0:
             return None, f"frame_loop exit {out.returncode}: {out.stderr.strip()[:300]}"
         native = json.loads(out.stdout.strip().splitlines()[-1])
-        if native.get("frames") != K:
-            return None, f"frame_loop collected {native.get('frames')} of {K} frames"
+        if native.get("frames") != K * windows:
+            return None, f"frame_loop collected {native.get('frames')} of {K * windows} frames"
         return native, None
     except Exception as ex:          # noqa: BLE001 -- a broken side measurement must not take the benchmark line down
         return None, f"{type(ex).__name__}: {ex}"
@@ -327,16 +335,161 @@ def run_native_e2e(frames, W, K, n_pts, rank, local_rank, world):
             os.unlink(path)
 
 
+# ------------------------------------------------------------------------------------------- parity on the bench scene
+def _rel_err(a, b):
+    scale = np.maximum(np.maximum(np.abs(a), np.abs(b)), 1e-3)
+    err = np.abs(a - b) / scale
+    err[np.isnan(a) & np.isnan(b)] = 0
+    err[np.isnan(err)] = np.inf
+    return err
+
+
+def _pd_tracks(dump):
+    """live tracks whose merged covariance is positive definite in the reference (an indefinite filter amplifies 1-ulp libm
+    differences chaotically; the reference itself kills it a few frames later -- tests/test_tracker_gpu.py)"""
+    ok = np.zeros(len(dump), bool)
+    for i, d in enumerate(dump):
+        if d[0] <= 0:
+            continue
+        P = d[24:49].reshape(5, 5)
+        if np.all(np.isfinite(P)):
+            ok[i] = np.linalg.eigvalsh((P + P.T) / 2).min() > 1e-9
+    return ok
+
+
+def cpu_baseline_and_parity(ctx, oracle_mod, frames, ts, n_sample, W, K, d_frames, n_pts):
+    """The reference's four entry points, one host thread, on the first frames of the bench workload (timed) -- and, untimed, the
+    CUDA path on the SAME frames compared with what the reference just produced."""
+    o = oracle_mod.RefOracle("intended") if oracle_mod.have_ref("intended") else oracle_mod.PortOracle("intended")
+    kind = "reference" if isinstance(o, oracle_mod.RefOracle) else "port"
+    Wc = 10
+    n = min(Wc + n_sample, len(frames))
+    o.tracker_reset()
+    ctx.tracker_reset()
+    tt = 0.0
+    chk = dict(frames=0, ok=True, first_failure=None, pd_excluded=0, tracks_compared=0, max_state_rel_err=0.0, state_frames=0)
+
+    def fail(i, what):
+        if chk["ok"]:
+            chk["ok"], chk["first_failure"] = False, f"frame {i}: {what}"
+
+    for i in range(n):
+        t0 = time.perf_counter()
+        e, g = o.ground_remove(frames[i]); grid, k = o.component_clustering(e); boxes, _ = o.box_fitting(e, grid, k)
+        a = o.tracker_step(boxes, ts[i])
+        if i >= Wc:
+            tt += time.perf_counter() - t0
+        ctx.frame_dev(d_frames[i].data_ptr(), n_pts, ts[i])
+        r = ctx.frame_fetch()
+        chk["frames"] += 1
+        if (r["n_elevated"], r["n_ground"], r["num_cluster"]) != (len(e), len(g), k):
+            fail(i, f"counts {(r['n_elevated'], r['n_ground'], r['num_cluster'])} vs reference {(len(e), len(g), k)}")
+        elif r["boxes"].shape != boxes.shape or not np.array_equal(r["boxes"].view(np.uint32), boxes.view(np.uint32)):
+            fail(i, "boxes differ (bit-exact bar)")
+        elif not (np.array_equal(r["track_manage"], a["track_manage"]) and np.array_equal(r["is_static"], a["is_static"]) and np.array_equal(r["is_vis"], a["is_vis"])):
+            fail(i, "trackManage / static / visible flags differ")
+        if chk["ok"] and (i % 5 == 4 or i == n - 1):          # UKF states + covariances of every track, every 5th frame
+            da, db = o.tracker_dump(), ctx.tracker_dump()
+            if da.shape != db.shape or not np.array_equal(da[:, 0:4], db[:, 0:4]):
+                fail(i, "track table integers differ")
+            else:
+                pd = _pd_tracks(da)
+                chk["pd_excluded"] = max(chk["pd_excluded"], int((da[:, 0] > 0).sum() - pd.sum()))
+                chk["tracks_compared"] = max(chk["tracks_compared"], int(pd.sum()))
+                err = _rel_err(da[pd][:, 4:175], db[pd][:, 4:175])
+                if err.size:
+                    chk["max_state_rel_err"] = max(chk["max_state_rel_err"], float(err.max()))
+                    if err.max() >= 1e-4:
+                        fail(i, f"UKF state relative error {float(err.max()):.3g} > 1e-4")
+                chk["state_frames"] += 1
+    ns = n - Wc
+    chk["bars"] = "counts + boxes bit-exact, trackManage/static/visible identical every frame; x/P/modeProb/zPred/S/K <= 1e-4 rel. every 5th frame on tracks whose reference covariance is positive definite (pd_excluded = most live tracks excluded on a frame)"
+    cpu = {"value": ns / tt, "unit": "frames/s", "cores": 1, "kind": kind, "host_cpu": host_cpu_name(), "host_cores": os.cpu_count(),
+           "sample": f"first {ns} frames of the same workload after {Wc} warm-up frames, single thread (the reference is single-threaded per node)"}
+    return cpu, chk
+
+
+def pct(a, q):
+    a = np.sort(np.asarray(a, np.float64))
+    return float(a[min(len(a) - 1, int(q * len(a)))]) if len(a) else None
+
+
+# ------------------------------------------------------------------------------------------- batched ticks (configs[3])
+def batched_block(lmot, synth, local_rank, stream, peak, ticks=12, warm=3, F=8):
+    """BASELINE.json configs[3]: F sensor streams (scenes of different seeds), one frame each per tick, ONE track table.
+    (a) ticks/s through lmot_batch_dev with the tick frames resident in HBM (ring of ticks > L2), (b) the ground_removal + CCL
+    roofline of the two batched launches (lmot_batch_ground_ccl_dev), CUDA events on the launching stream."""
+    import torch
+    streams = [[p for _, p in synth.frames(synth.SceneConfig(**{**SCENE, "seed": 101 + s}), warm + ticks)] for s in range(F)]
+    n = len(streams[0][0])
+    dev = [torch.from_numpy(np.stack(st_)).cuda() for st_ in streams]
+    ctx = lmot.Lmot(device=local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    args = lambda t: [(dev[s_][t].data_ptr(), n) for s_ in range(F)]
+    # (b) roofline of ground + CCL
+    for t in range(warm):
+        ctx.batch_ground_ccl_dev(args(t))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3 * ticks
+    e0.record(stream)
+    for i in range(reps):
+        ctx.batch_ground_ccl_dev(args(warm + i % ticks))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    gc_us = 1e3 * e0.elapsed_time(e1) / reps
+    ne = nf = 0
+    for s_ in range(F):
+        r = ctx.ground_remove(streams[s_][warm]); ne += len(r["elevated"]); nf += len(r["elevated"]) + len(r["ground"])
+    bytes_ground = F * (16 * n + 9600 * 24) + 16 * nf             # SURVEY.md §8d per frame, summed over the tick
+    bytes_ccl = 20 * ne + F * 2 * 62500 * 4
+    # (a) whole ticks, tracker included
+    ctx.tracker_reset()
+    for t in range(warm):
+        ctx.batch_dev(args(t), 1e5 * (t + 1))
+    ctx.flush(); torch.cuda.synchronize()
+    e0.record(stream)
+    for t in range(warm, warm + ticks):
+        ctx.batch_dev(args(t), 1e5 * (t + 1))
+    ctx.flush()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    tick_ms = e0.elapsed_time(e1) / ticks
+    res = ctx.batch_fetch()
+    ctx.enable_timing(True)
+    ctx.tracker_reset()
+    km = []
+    for t in range(warm + ticks):
+        ctx.batch_dev(args(t), 1e5 * (t + 1)); ctx.batch_fetch(want_boxes=False)
+        if t >= warm:
+            km.append(ctx.last_kernel_ms())
+    ctx.enable_timing(False)
+    names = ("ground_fused[8 frames]", "ccl[8]", "tile_hist[8]", "seg_offsets[8]", "scatter[8]", "box_fit[8]", "concat_boxes", "imm_predict_gate", "imm_update", "spawn_output")
+    kus = np.mean(np.array(km), 0) * 1e3 if km and len(set(map(len, km))) == 1 else []
+    ctx.close()
+    ach = (bytes_ground + bytes_ccl) / gc_us / 1e3
+    return {"workload": f"{F} sensor streams x {n} points per tick, one shared track table (BASELINE.json configs[3])", "streams": F, "ticks": ticks,
+            "frames_per_s": 1e3 * F / tick_ms, "ticks_per_s": 1e3 / tick_ms, "ms_per_tick": tick_ms,
+            "live_tracks_end": int((res["track_manage"] > 0).sum()), "tracks_in_table_end": int(len(res["track_manage"])), "boxes_last_tick": int(len(res["boxes"])),
+            "roofline": {"bound": "hbm", "kernels": "ground_fused_kernel + ccl kernel, ONE launch each for the 8 frames (CTA groups / one CTA per frame)",
+                         "algorithmic_bytes_ground": int(bytes_ground), "algorithmic_bytes_ccl": int(bytes_ccl), "us_per_tick_both_launches": gc_us,
+                         "achieved": ach, "unit": "GB/s", "peak": peak, "frac": ach / peak},
+            "kernel_us_timing_mode": ({k_: float(v) for k_, v in zip(names, kus)} if len(kus) == len(names) else [float(v) for v in kus]),
+            "l2_policy": f"every tick reads {F} frames no earlier tick of the window has read ({(warm + ticks) * F * n * 16 / 2**20:.0f} MiB ring)"}
+
+
 # ------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--windows", type=int, default=0, help="repetitions of the K-step timed window (0 = auto: 5 for short runs, 1 from K = 200)")
     ap.add_argument("--impl", default="lmot", choices=["lmot", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=60, help="frames of the CPU baseline sample (rank 0, N=1)")
+    ap.add_argument("--cpu-sample", type=int, default=60, help="frames of the CPU baseline / parity sample (rank 0, N=1)")
     ap.add_argument("--tracker-stress", type=int, default=40, help="timed steps of the 1024x256 tracker-only workload (0 = skip; rank 0, N=1)")
     ap.add_argument("--dense-frames", type=int, default=10, help="1M-point frames for the dense roofline measurement (0 = skip)")
+    ap.add_argument("--batch-ticks", type=int, default=12, help="ticks of the batched 8 x 120 k configuration (0 = skip; rank 0)")
     ap.add_argument("--shared-tracker", choices=["off", "streams", "frames"], default="off",
                     help="N>1 only: all ranks feed ONE track table (NCCL all_gather of boxes, tracker on rank 0, NCCL broadcast of the "
                          "outputs and of the table): 'streams' = N sensors per tick (configs[3]), 'frames' = one sensor, frames sharded "
@@ -362,9 +515,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lmot = importlib.import_module(PKG)
     K, W = args.steps, max(args.warmup, 3)
+    R = args.windows if args.windows > 0 else max(1, min(5, 200 // max(K, 1)))
 
-    # ---- inputs: W+K consecutive frames of this rank's sensor stream, resident in HBM and in pinned host memory
-    ts, frames = make_frames(synth, W + K, seed_offset=rank)
+    # ---- inputs: W + R*K consecutive frames of this rank's sensor stream, resident in HBM and in pinned host memory
+    ts, frames = make_frames(synth, W + R * K, seed_offset=rank)
     n_pts = int(frames.shape[1])
     h_frames = torch.from_numpy(frames).pin_memory()
     d_frames = h_frames.cuda(non_blocking=True)
@@ -385,7 +539,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)      # nvidia-smi samples every 100 ms across all three timed passes below
+    sampler = ClockSampler(local_rank)      # nvidia-smi samples every 100 ms across all timed passes below
     sampler.start()
     if args.shared_tracker != "off" and world > 1:
         run_shared_tracker(args, lmot, ctx, d_frames, ts, n_pts, rank, world, local_rank, stream)
@@ -393,7 +547,7 @@ def main():
         dist.destroy_process_group()
         return
 
-    # ---- (1) device-resident throughput: `value`
+    # ---- (1) device-resident throughput: `value`.  R windows of exactly K steps, each bracketed by barrier + synchronize.
     ctx.tracker_reset()
     for i in range(W):
         ctx.frame_dev(d_frames[i].data_ptr(), n_pts, ts[i])
@@ -403,34 +557,38 @@ def main():
     if small_ring:
         l2_flush = torch.empty(192 * 2**20, dtype=torch.uint8, device="cuda")
         l2_flush.zero_()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(W, W + K):
-        ctx.frame_dev(d_frames[i].data_ptr(), n_pts, ts[i])
-    ctx.flush()                      # device-side join of the context's internal streams into the timing stream
-    e1.record(stream)
-    barrier()
-    dev_ms = e0.elapsed_time(e1)
+    win_ms = []
+    for r_ in range(R):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(W + r_ * K, W + (r_ + 1) * K):
+            ctx.frame_dev(d_frames[i].data_ptr(), n_pts, ts[i])
+        ctx.flush()                      # device-side join of the context's internal streams into the timing stream
+        e1.record(stream)
+        barrier()
+        win_ms.append(e0.elapsed_time(e1))
     res_dev = ctx.frame_fetch()
     live_tracks = int((res_dev["track_manage"] > 0).sum())
 
-    # ---- (2) per-stage device time of the same frames (CUDA events on the launching stream): roofline numerator
+    # ---- (2) per-stage device time of the same frames, ONE frame in flight (CUDA events on the launching stream)
     ctx.tracker_reset()
     ctx.enable_timing(True)
-    stage_ms = np.zeros(4)
+    per_stage, per_frame_dev = [], []
     kern_ms = None
     n_elev_sum = 0
     for i in range(W + K):
         ctx.frame_dev(d_frames[i].data_ptr(), n_pts, ts[i])
         r = ctx.frame_fetch(want_boxes=False)
         if i >= W:
-            stage_ms += ctx.last_stage_ms()
+            sm = ctx.last_stage_ms()
+            per_stage.append(sm); per_frame_dev.append(sum(sm))
             km = np.array(ctx.last_kernel_ms())
             kern_ms = km if kern_ms is None or len(kern_ms) != len(km) else kern_ms + km
             n_elev_sum += r["n_elevated"] + r["n_ground"]
     ctx.enable_timing(False)
-    stage_ms /= K
+    per_stage = np.array(per_stage)
+    stage_ms = per_stage.mean(0)
     n_f = n_elev_sum / K                                         # points that survive the range filter, per frame
     ground_bytes = 16 * n_pts + 16 * n_f + 9600 * 24             # read XYZI + write both clouds + grid
     peak, peak_src = measured_peak_gbs()
@@ -477,6 +635,11 @@ def main():
                  "achieved": db / (ms * 1e-3) / 1e9, "unit": "GB/s", "peak": peak, "frac": db / (ms * 1e-3) / 1e9 / peak}
         del d_dense
 
+    # ---- (2c) BASELINE.json configs[3]: 8 streams x 120 k per tick, batched launches, one track table
+    batched = None
+    if rank == 0 and args.batch_ticks > 0:
+        batched = batched_block(lmot, synth, local_rank, stream, peak, ticks=args.batch_ticks)
+
     # ---- H2D bandwidth of this box (context for `e2e`: every step moves the 1.92 MB frame over PCIe)
     hb0, hb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tmp_d = torch.empty_like(d_frames[:8])
@@ -495,10 +658,10 @@ def main():
     h2d_frame_us = 1e3 * hb0.elapsed_time(hb1) / 64
     del tmp_d
 
-    # ---- (3) end to end through the C ABI with host buffers: `e2e`
+    # ---- (3) end to end through the C ABI with host buffers: `e2e` (Python loop: one window; the C++ loop below is the figure)
     ctx.tracker_reset()
     h_np = h_frames.numpy()
-    depth = int(ctx.params.result_ring) - 1     # frames the host may be ahead of the results it has read back
+    depth = min(int(ctx.params.result_ring) - 1, 2 * int(ctx.params.pipeline_depth))     # frames the host may be ahead of the results it has read back
     for i in range(W):
         ctx.frame(h_np[i], ts[i])
     barrier()
@@ -507,7 +670,7 @@ def main():
     collected = 0
     t_submit = t_collect = 0.0
     in_flight = 0
-    for i in range(W, W + K):            # every step: H2D of its frame; every result is read back inside the region
+    for i in range(W, W + R * K):        # every step: H2D of its frame; every result is read back inside the region
         if in_flight == depth:
             tc = time.perf_counter(); r = ctx.frame_collect(); t_collect += time.perf_counter() - tc
             collected += 1; in_flight -= 1
@@ -517,15 +680,15 @@ def main():
         tc = time.perf_counter(); r = ctx.frame_collect(); t_collect += time.perf_counter() - tc
         collected += 1; in_flight -= 1
     barrier()
-    e2e_py_s = time.perf_counter() - t0
-    assert collected == K
+    e2e_py_s = (time.perf_counter() - t0) / R
+    assert collected == R * K
     d2h = 16 * 4 + r["boxes"].size * 4 + len(r["track_manage"]) * (12 + 16 + 4 + 1 + 1) + r["vis_bb"].size * 4
     py_live = int((r["track_manage"] > 0).sum())
 
     # ---- (3b) the same loop in the reference's host language: host/frame_loop.cpp (C++ over the same two C-ABI calls, pinned host
-    # frames, every result collected).  This is `e2e`; the Python loop above pays ~15 us of interpreter + ctypes time per frame.
+    # frames, every result collected, R windows of K steps with lmot_sync on both sides).  This is `e2e`.
     barrier()
-    native, native_err = run_native_e2e(frames, W, K, n_pts, rank, local_rank, world)
+    native, native_err = run_native_e2e(frames, W, K, n_pts, rank, local_rank, world, windows=R)
     if native is not None and not (native["tracks_last"] == len(r["track_manage"]) and native["live_tracks_last"] == py_live):
         # same frames, same tracker: the native loop must end in the state the Python loop ended in
         native_err, native = f"frame_loop ended in a different tracker state: {native} vs {len(r['track_manage'])} tracks / {py_live} live", None
@@ -533,75 +696,86 @@ def main():
         e2e_s, d2h = native["e2e_s"], native["d2h_bytes_last"]
     else:
         e2e_s = e2e_py_s             # (reported as such: e2e.driver says which loop was timed, e2e.native_driver_error why)
+    # ... and once more with ONE frame in flight: the latency of a frame through the host API (submit call -> results copied out)
+    lat1 = None
+    if rank == 0:
+        lat1, _ = run_native_e2e(frames, W, min(K, 100), n_pts, rank, local_rank, world, windows=1, in_flight=1)
     clocks = sampler.stop()
 
-    # ---- aggregate over ranks (max time)
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    # ---- aggregate over ranks (max time per window, then the median window)
+    t = torch.tensor(win_ms + [e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    win_max = [float(x) for x in t[:R]]
+    dev_ms_max, e2e_ms_max = float(np.median(win_max)) if R % 2 else float(sorted(win_max)[(R - 1) // 2]), float(t[R])
     value = world * K / (dev_ms_max * 1e-3)
     e2e = world * K / (e2e_ms_max * 1e-3)
 
-    cpu_baseline = None
+    cpu_baseline = parity = None
     if rank == 0 and world == 1 and args.cpu_sample > 0:
         from oracle import ref as oracle     # the checker / baseline, never the measured product
-        o = oracle.RefOracle("intended") if oracle.have_ref("intended") else oracle.PortOracle("intended")
-        kind = "reference" if isinstance(o, oracle.RefOracle) else "port"
-        S, Wc = args.cpu_sample, 10
-        o.tracker_reset()
-        tt = 0.0
-        for i in range(min(Wc + S, W + K)):
-            t0 = time.perf_counter()
-            e, g = o.ground_remove(frames[i]); grid, k = o.component_clustering(e); boxes, _ = o.box_fitting(e, grid, k)
-            o.tracker_step(boxes, ts[i])
-            if i >= Wc:
-                tt += time.perf_counter() - t0
-        ns = min(Wc + S, W + K) - Wc
-        cpu_baseline = {"value": ns / tt, "unit": "frames/s", "cores": 1, "kind": kind, "host_cpu": host_cpu_name(),
-                        "host_cores": os.cpu_count(),
-                        "sample": f"first {ns} frames of the same workload after {Wc} warm-up frames, single thread (the reference is single-threaded per node)"}
+        cpu_baseline, parity = cpu_baseline_and_parity(ctx, oracle, frames, ts, args.cpu_sample, W, K, d_frames, n_pts)
 
     stress = None
     if rank == 0 and world == 1 and args.tracker_stress > 0:
         stress = tracker_stress(ctx, steps=args.tracker_stress)
 
     if rank == 0:
+        stage_names = ("ground", "cluster", "box", "tracker")
+        latency = {
+            "one_frame_in_flight_device": {"frame": {"p50": 1e3 * pct(per_frame_dev, 0.5), "p99": 1e3 * pct(per_frame_dev, 0.99)},
+                                           **{n: {"p50": 1e3 * pct(per_stage[:, j], 0.5), "p99": 1e3 * pct(per_stage[:, j], 0.99)} for j, n in enumerate(stage_names)},
+                                           "how": f"CUDA events around the stages of {K} frames submitted one at a time (lmot_frame_dev + fetch), device time, us"},
+            "one_frame_in_flight_host_api": ({"frame": {"p50": lat1["latency_us_p50"], "p99": lat1["latency_us_p99"]},
+                                              "how": "host clock, lmot_frame_submit call -> results copied out by lmot_frame_collect, H2D of the frame included (host/frame_loop.cpp, in_flight = 1)"} if lat1 else None),
+            "pipelined_host_api": ({"frame": {"p50": native["latency_us_p50"], "p99": native["latency_us_p99"]}, "in_flight": native["in_flight"],
+                                    "how": "same clock with the pipeline full: in_flight frames submitted ahead of the results read back (queueing included)"} if native else None),
+        }
+        ok = parity is None or parity["ok"]
         line = {
-            "metric": "HDL-64 frames/sec (120K pts, 64 tracks)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": "HDL-64 frames/sec (120K pts, 64 tracks)", "value": (value if ok else None), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "windows": R, "window_values": [world * K / (w_ * 1e-3) for w_ in win_max],
             "dtype": "f32 points / f64 tracker", "data": "synthetic",
             "config": {"workload": WORKLOAD, "points_per_frame": n_pts, "scene": SCENE, "live_tracks_end": live_tracks,
                        "tracks_in_table_end": int(len(res_dev["track_manage"])), "rule_filter": "INTENDED",
                        "parallelism": f"{world} independent sensor stream(s), one per GPU, no collective on the data path",
                        "pipeline_depth": int(ctx.params.pipeline_depth), "result_ring": int(ctx.params.result_ring),
                        "l2_policy": (f"every step reads a different frame of a {ring_mb:.0f} MiB ring (> 126 MB L2)" if not small_ring else
-                                     f"every step reads a different frame of a {ring_mb:.0f} MiB ring, L2 flushed (192 MiB written) before the timed region")},
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": int(d2h),
+                                     f"every step reads a different frame of a {ring_mb:.0f} MiB ring, L2 flushed (192 MiB written) before the first timed window")},
+            "parity_check": parity,
+            "e2e": {"value": (e2e if ok else None), "unit": "frames/s", "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": int(d2h),
+                    "windows": (native["windows"] if native else 1), "window_values": ([world * K / w_ for w_ in native["window_s"]] if native else None),
                     "pinned_h2d_gbs_this_box": h2d_gbs, "h2d_us_per_frame_copy_this_box": h2d_frame_us, "pcie_bound_frames_per_s": 1e6 / h2d_frame_us,
                     "driver": ("host/frame_loop.cpp: C++ loop over lmot_frame_submit / lmot_frame_collect, pinned host frames" if native else "python ctypes loop"),
                     "native_driver_error": native_err,
                     "host_us_per_step": ({"submit": native["submit_us_per_frame"], "collect_incl_wait": native["collect_us_per_frame"]} if native
-                                         else {"submit": 1e6 * t_submit / K, "collect_incl_wait": 1e6 * t_collect / K}),
+                                         else {"submit": 1e6 * t_submit / (R * K), "collect_incl_wait": 1e6 * t_collect / (R * K)}),
                     "python_ctypes_loop": {"value": world * K / e2e_py_s, "unit": "frames/s", "note": "same two calls from a Python loop (this rank)",
-                                           "host_us_per_step": {"submit": 1e6 * t_submit / K, "collect_incl_wait": 1e6 * t_collect / K}}},
-            "gpu_launches": KERNELS_PER_FRAME * K,
+                                           "host_us_per_step": {"submit": 1e6 * t_submit / (R * K), "collect_incl_wait": 1e6 * t_collect / (R * K)}}},
+            "gpu_launches": KERNELS_PER_FRAME * K * R,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "ground_fused_kernel (the whole ground_removal stage: bin + polar grid + classify/partition, one cooperative launch)",
+            "latency_us": latency,
+            "roofline": {"bound": "hbm", "kernel": "ground_fused_kernel (the whole ground_removal stage: bin + polar grid + classify/partition, one launch)",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "algorithmic_bytes_per_launch": ground_bytes, "avg_launch_ms": float(ground_launch_ms),
-                         "launches_timed": K, "traffic": TRAFFIC_NCU,
-                         "note": "latency bound at 120 k points: 3.84 MB is 0.6 us of HBM time, the kernel needs two grid-wide barriers and one count exchange; see roofline_dense_1m"},
-            "stage_ms": {n: float(v) for n, v in zip(("ground", "cluster", "box", "tracker"), stage_ms)},
+                         "launches_timed": K, "traffic": TRAFFIC_NCU, "traffic_source": TRAFFIC_SOURCE,
+                         "note": "latency bound at 120 k points: 3.84 MB is 0.6 us of HBM time, the kernel needs two frame-wide barriers and one count exchange; see roofline_dense_1m and batched_8x120k.roofline"},
+            "stage_ms": {n: float(v) for n, v in zip(stage_names, stage_ms)},
             "kernel_us_warm": ({n: float(1e3 * v / K) for n, v in zip(KERNEL_NAMES, kern_ms)} if kern_ms is not None and len(kern_ms) == len(KERNEL_NAMES) else None),
             "roofline_dense_1m": dense,
+            "batched_8x120k": batched,
             "tracker_stress_1024x256": stress,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
+        if not ok:
+            sys.stderr.write("bench.py: parity_check FAILED (" + str(parity["first_failure"]) + ") -- value withheld\n")
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        raise SystemExit(1)
 
 
 if __name__ == "__main__":

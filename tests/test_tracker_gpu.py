@@ -217,3 +217,40 @@ def test_checkpoint_restore_with_moving_ego(pkg, ref_intended, synth):
         assert abs(a.tracker_get_ego()[7] + np.pi / 2) > 0.1      # the ego really turned
     finally:
         a.close(); b.close()
+
+
+def test_free_running_bench_scene_100_frames(pkg, ref_intended, synth):
+    """The benchmark's own scene (bench.py SCENE: 150 objects on a 3.8 m lattice, 65 % pedestrians, ~64 live tracks), 100 frames,
+    both trackers free-running from the first frame: identical trackManage / lifetime / static / visible flags on EVERY frame, UKF
+    states <= 1e-4 relative on the tracks whose merged covariance is still positive definite in the reference -- and a count of
+    how many live tracks that filter excludes (nobody had counted)."""
+    ref = ref_intended
+    cfg = synth.SceneConfig(n_objects=150, lattice_pitch=3.8, ped_fraction=0.65, seed=1)
+    ctx = pkg.Lmot()
+    try:
+        ref.tracker_reset()
+        worst, excl_max, excl_sum, live_sum, compared = 0.0, 0, 0, 0, 0
+        for f, (ts, pts) in enumerate(synth.frames(cfg, 100)):
+            e, _ = ref.ground_remove(pts)
+            g, k = ref.component_clustering(e)
+            boxes, _ = ref.box_fitting(e, g, k)
+            a = ref.tracker_step(boxes, ts)
+            b = ctx.track_step(boxes, ts)
+            assert np.array_equal(a["track_manage"], b["track_manage"]), f
+            assert np.array_equal(a["is_vis"], b["is_vis"]) and np.array_equal(a["is_static"], b["is_static"]), f
+            if f % 4 == 3 or f == 99:
+                da, db = ref.tracker_dump(), ctx.tracker_dump()
+                assert np.array_equal(da[:, INTS], db[:, INTS]), f
+                ok = _pd_tracks(da)
+                live = int((da[:, 0] > 0).sum())
+                excl = live - int(ok.sum())
+                excl_max = max(excl_max, excl); excl_sum += excl; live_sum += live; compared += int(ok.sum())
+                err = _rel_err(da[ok][:, STATE], db[ok][:, STATE])
+                if err.size:
+                    worst = max(worst, float(err.max()))
+                    assert err.max() < TOL, (f, float(err.max()))
+        assert (a["track_manage"] > 0).sum() >= 40
+        print(f"bench scene, 100 frames free-running: worst relative state error {worst:.3g} over {compared} track-frames; "
+              f"positive-definite filter excluded {excl_sum} of {live_sum} live track-frames (at most {excl_max} on one frame)")
+    finally:
+        ctx.close()
