@@ -155,11 +155,13 @@ def render(scene: Scene) -> np.ndarray:
     return pts
 
 
-def frames(cfg: SceneConfig, n_frames: int):
-    """Yield (timestamp_us, points) for n_frames consecutive frames of one scene."""
+def frames(cfg: SceneConfig, n_frames: int, only=None):
+    """Yield (timestamp_us, points) for n_frames consecutive frames of one scene.  `only(f)`: render just the frames it accepts
+    (the scene still advances through all of them) -- a rank that holds every world-th frame of a frame-sharded sequence."""
     sc = make_scene(cfg)
     for f in range(n_frames):
-        yield (f + 1) * DT_US, render(sc)
+        if only is None or only(f):
+            yield (f + 1) * DT_US, render(sc)
         advance(sc)
 
 

@@ -212,41 +212,68 @@ def run_reference(args, synth):
 
 
 # ------------------------------------------------------------------------------------------- shared track table (N > 1)
-def run_shared_tracker(args, lmot, ctx, d_frames, ts, n_pts, rank, world, local_rank, stream):
-    """All ranks detect on their own frame, then feed ONE track table owned by rank 0 (the only exchange step of the path)."""
+def shared_tracker_block(lmot, synth, rank, world, local_rank, ticks=10, warm=3):
+    """N GPUs feeding ONE track table through the C++ shared tracker (include/lmot_shared.h, host/shared_tracker.cpp: NCCL
+    all-gather of device box lists, tracker on rank 0, NCCL broadcast of count + table; nothing but a 4-byte count crosses a host).
+      streams: every rank its own 120 k-point sensor stream, ONE tracker step per tick on the concatenation (configs[3] across GPUs)
+      frames : ONE dense 1 M-point sensor, frame t*N + r on rank r, folded in frame order (BASELINE.json configs[4])
+    Ticks are host-synchronous (the owner reads the outputs back every tick); time = host clock between barriers, max over ranks."""
     import torch
     import torch.distributed as dist
-    st_mod = importlib.import_module(PKG + ".shared_tracker")
-    K, W = args.steps, max(args.warmup, 3)
-    st = st_mod.SharedTracker(ctx, owner=0, max_boxes=int(ctx.params.max_boxes), device=torch.device("cuda", local_rank))
-    sharded = args.shared_tracker == "frames"
-    ctx.tracker_reset()
+    uid = [lmot.shared_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx = lmot.Lmot(device=local_rank)
+    st = lmot.SharedTracker(ctx, rank, world, 0, uid[0])
+    out = {"host_code": "host/shared_tracker.cpp (C++, NCCL C API) over liblmot.so", "owner_rank": 0}
+    for mode in ("streams", "frames"):
+        if mode == "streams":
+            seq = list(synth.frames(synth.SceneConfig(**{**SCENE, "seed": SCENE["seed"] + rank}), warm + ticks))
+            tick_ts = [s_[0] for s_ in seq]
+            dt = 0.0
+            workload = f"{world} sensor streams x 120 k points per tick"
+        else:
+            cfg = synth.dense_config(n_objects=400, lattice_pitch=2.3, ped_fraction=0.9, seed=11)
+            seq = [(t_, p_[:1_000_000]) for t_, p_ in synth.frames(cfg, (warm + ticks) * world, only=lambda f: f % world == rank)]
+            tick_ts = [synth.DT_US * (t * world + 1) for t in range(warm + ticks)]
+            dt = synth.DT_US
+            workload = f"one dense sensor, 1 M points per frame, {world} consecutive frames per tick (frame-sharded)"
+        dev = [torch.from_numpy(np.ascontiguousarray(p_)).cuda() for _, p_ in seq]
+        ctx.tracker_reset()
+        m = lmot.SHARED_STREAMS if mode == "streams" else lmot.SHARED_FRAMES
+        for t in range(warm):
+            st.tick_dev(dev[t].data_ptr(), len(seq[t][1]), tick_ts[t], mode=m, frame_dt_us=dt)
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        phases = np.zeros(4)
+        for t in range(warm, warm + ticks):
+            r = st.tick_dev(dev[t].data_ptr(), len(seq[t][1]), tick_ts[t], mode=m, frame_dt_us=dt)
+            phases += np.array(list(st.last_us().values()))
+        dist.barrier(); torch.cuda.synchronize()
+        sec = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        ph = torch.tensor(phases / ticks, dtype=torch.float64, device="cuda")
+        dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+        nt = torch.tensor([len(r["track_manage"]) if rank == 0 else 0, int((r["track_manage"] > 0).sum()) if rank == 0 else 0], device="cuda")
+        dist.broadcast(nt, src=0)
+        out[mode] = {"workload": workload, "ticks": ticks, "frames_per_s": world * ticks / float(sec[0]), "ms_per_tick": 1e3 * float(sec[0]) / ticks,
+                     "tracks_in_table_end": int(nt[0]), "live_tracks_end": int(nt[1]), "table_bytes_broadcast_last_tick": int(nt[0]) * 1648,
+                     "device_us_per_tick_max_over_ranks": dict(zip(("detect", "allgather_boxes", "tracker_owner", "broadcast_count_and_table"), (float(x) for x in ph)))}
+        del dev
+    st.close()
+    ctx.close()
+    return out
 
-    def tick(i):
-        ctx.detect_dev(d_frames[i].data_ptr(), n_pts)
-        r = ctx.frame_fetch()
-        base_ts = ts[i] * world if sharded else ts[i]
-        return st.step(r["boxes"], base_ts, frame_sharded=sharded)
 
-    for i in range(W):
-        tick(i)
-    dist.barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(W, W + K):
-        out = tick(i)
-    dist.barrier(); torch.cuda.synchronize()
-    sec = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+def run_shared_tracker(args, lmot, synth, rank, world, local_rank):
+    """--shared-tracker: only the shared-table configuration (the default N > 1 line carries the same block next to the independent streams)."""
+    blk = shared_tracker_block(lmot, synth, rank, world, local_rank, ticks=max(4, min(args.steps, 30)))
     if rank == 0:
-        fps = world * K / float(sec[0])
+        mode = blk[args.shared_tracker]
         print(json.dumps({
-            "metric": "HDL-64 frames/sec (120K pts, shared track table)", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": 1e3 * float(sec[0]) / K, "higher_is_better": True, "scaling": "weak" if not sharded else "strong", "vs_baseline": None,
-            "dtype": "f32 points / f64 tracker", "data": "synthetic",
-            "config": {"workload": "hdl64_120k_shared_tracker_" + args.shared_tracker, "points_per_frame": n_pts, "scene": SCENE,
-                       "tracks_in_table_end": int(len(out["track_manage"])), "live_tracks_end": int((out["track_manage"] > 0).sum()),
-                       "parallelism": f"detection on {world} GPUs, one track table on rank 0, NCCL all_gather(boxes) + broadcast(outputs, table)"},
-            "gpu_launches": KERNELS_PER_FRAME * K}))
+            "metric": "HDL-64 frames/sec (shared track table)", "value": mode["frames_per_s"], "unit": "frames/s", "n_gpus": world, "steps": mode["ticks"], "warmup": 3,
+            "ms_per_step": mode["ms_per_tick"], "higher_is_better": True, "scaling": "weak" if args.shared_tracker == "streams" else "strong", "vs_baseline": None,
+            "dtype": "f32 points / f64 tracker", "data": "synthetic", "config": {"workload": "shared_tracker_" + args.shared_tracker, **mode}, "shared_tracker": blk,
+            "gpu_launches": KERNELS_PER_FRAME * mode["ticks"]}))
 
 
 # ------------------------------------------------------------------------------------------- tracker in isolation (configs[2])
@@ -490,6 +517,7 @@ def main():
     ap.add_argument("--tracker-stress", type=int, default=40, help="timed steps of the 1024x256 tracker-only workload (0 = skip; rank 0, N=1)")
     ap.add_argument("--dense-frames", type=int, default=10, help="1M-point frames for the dense roofline measurement (0 = skip)")
     ap.add_argument("--batch-ticks", type=int, default=12, help="ticks of the batched 8 x 120 k configuration (0 = skip; rank 0)")
+    ap.add_argument("--shared-ticks", type=int, default=8, help="N>1: ticks of the shared-track-table block (both modes) appended to the default line (0 = skip)")
     ap.add_argument("--shared-tracker", choices=["off", "streams", "frames"], default="off",
                     help="N>1 only: all ranks feed ONE track table (NCCL all_gather of boxes, tracker on rank 0, NCCL broadcast of the "
                          "outputs and of the table): 'streams' = N sensors per tick (configs[3]), 'frames' = one sensor, frames sharded "
@@ -542,8 +570,8 @@ def main():
     sampler = ClockSampler(local_rank)      # nvidia-smi samples every 100 ms across all timed passes below
     sampler.start()
     if args.shared_tracker != "off" and world > 1:
-        run_shared_tracker(args, lmot, ctx, d_frames, ts, n_pts, rank, world, local_rank, stream)
         ctx.close()
+        run_shared_tracker(args, lmot, synth, rank, world, local_rank)
         dist.destroy_process_group()
         return
 
@@ -720,6 +748,11 @@ def main():
     if rank == 0 and world == 1 and args.tracker_stress > 0:
         stress = tracker_stress(ctx, steps=args.tracker_stress)
 
+    # ---- N > 1: the one real exchange step of the path, several GPUs feeding ONE track table (collective: every rank takes part)
+    shared = None
+    if world > 1 and args.shared_ticks > 0:
+        shared = shared_tracker_block(lmot, synth, rank, world, local_rank, ticks=args.shared_ticks)
+
     if rank == 0:
         stage_names = ("ground", "cluster", "box", "tracker")
         latency = {
@@ -766,6 +799,7 @@ def main():
             "roofline_dense_1m": dense,
             "batched_8x120k": batched,
             "tracker_stress_1024x256": stress,
+            "shared_tracker": shared,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
