@@ -87,12 +87,12 @@ class FrameOut(C.Structure):
 
 # every symbol include/lmot.h declares (tests assert the library exports all of them)
 ABI_SYMBOLS = [
-    "lmot_default_params", "lmot_create", "lmot_destroy", "lmot_strerror", "lmot_last_error", "lmot_build_info",
+    "lmot_default_params", "lmot_create", "lmot_destroy", "lmot_get_params", "lmot_strerror", "lmot_last_error", "lmot_build_info",
     "lmot_set_stream", "lmot_pinned_alloc", "lmot_pinned_free", "lmot_ground_remove", "lmot_component_cluster", "lmot_cluster_outputs", "lmot_box_fit", "lmot_track_step", "lmot_frame",
     "lmot_frame_dev", "lmot_frame_fetch", "lmot_frame_submit", "lmot_frame_collect", "lmot_frames_in_flight", "lmot_frame_ready", "lmot_flush",
     "lmot_ground_remove_dev", "lmot_detect_dev", "lmot_sync",
     "lmot_batch_submit", "lmot_batch_dev", "lmot_batch_detect_dev", "lmot_batch_collect", "lmot_batch_fetch", "lmot_batch", "lmot_batch_ground_ccl_dev",
-    "lmot_debug_stage_clocks",
+    "lmot_debug_stage_clocks", "lmot_detect_boxes_dev", "lmot_track_step_lists_dev", "lmot_tracker_counters_dev", "lmot_tracker_table_received",
     "lmot_origin_points", "lmot_tracker_table", "lmot_tracker_set_num_tracks", "lmot_tracker_reset", "lmot_tracker_num_tracks", "lmot_tracker_dump", "lmot_tracker_load", "lmot_tracker_get_ego", "lmot_tracker_set_ego",
     "lmot_debug_polar_grid", "lmot_debug_cell_index", "lmot_debug_label_grid", "lmot_debug_phase_clock", "lmot_debug_timeline", "lmot_debug_tracker_trace", "lmot_selftest_atan2f",
     "lmot_enable_timing", "lmot_last_stage_ms", "lmot_last_kernel_ms", "lmot_debug_host_ns",
@@ -532,3 +532,67 @@ def selftest_atan2f(y, x) -> np.ndarray:
     if st != OK:
         raise LmotError(st, "selftest")
     return out
+
+
+# ---- several GPUs, one track table: ctypes mirror of include/lmot_shared.h (liblmot_shared.so = host/shared_tracker.cpp + NCCL) ----
+SHARED_LIB_PATH = os.path.join(HERE, "liblmot_shared.so")
+SHARED_STREAMS, SHARED_FRAMES = 0, 1
+SHARED_ABI_SYMBOLS = ["lmot_shared_unique_id", "lmot_shared_create", "lmot_shared_destroy", "lmot_shared_tick_dev", "lmot_shared_last_us", "lmot_shared_last_error"]
+_shared_lib = None
+
+
+def load_shared_library() -> C.CDLL:
+    global _shared_lib
+    if _shared_lib is None:
+        load_library()
+        if not os.path.exists(SHARED_LIB_PATH):
+            raise OSError(f"{SHARED_LIB_PATH} not built")
+        lib = C.CDLL(SHARED_LIB_PATH)
+        lib.lmot_shared_last_error.restype = C.c_char_p
+        lib.lmot_shared_last_error.argtypes = [C.c_void_p]
+        lib.lmot_shared_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p]
+        lib.lmot_shared_destroy.argtypes = [C.c_void_p]
+        lib.lmot_shared_tick_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.POINTER(TrackOut)]
+        lib.lmot_shared_last_us.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        _shared_lib = lib
+    return _shared_lib
+
+
+def shared_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    st = load_shared_library().lmot_shared_unique_id(buf)
+    if st != OK:
+        raise LmotError(st, "lmot_shared_unique_id")
+    return buf.raw
+
+
+class SharedTracker:
+    """One rank of `world` GPUs feeding ONE track table (owner rank runs the tracker; NCCL all-gather of boxes, broadcast of the table)."""
+
+    def __init__(self, ctx: Lmot, rank: int, world: int, owner: int, unique_id: bytes):
+        self.lib = load_shared_library()
+        self.ctx, self.rank, self.world, self.owner = ctx, rank, world, owner
+        h = C.c_void_p()
+        st = self.lib.lmot_shared_create(C.byref(h), ctx.h, rank, world, owner, unique_id)
+        if st != OK:
+            raise LmotError(st, "lmot_shared_create")
+        self.h = h
+
+    def tick_dev(self, d_ptr: int, n: int, timestamp_us, v_gps=0.0, yaw_gps=0.0, mode=SHARED_STREAMS, frame_dt_us=0.0, cap: int | None = None):
+        to, bufs = self.ctx._track_out(cap or self.ctx.params.max_tracks)
+        st = self.lib.lmot_shared_tick_dev(self.h, C.c_void_p(d_ptr), int(n), float(timestamp_us), float(v_gps), float(yaw_gps), int(mode), float(frame_dt_us), C.byref(to))
+        if st < 0:
+            raise LmotError(st, self.lib.lmot_shared_last_error(self.h).decode())
+        if self.rank == self.owner:
+            return Lmot._track_result(to, bufs)
+        return dict(n_tracks=to.n_tracks)
+
+    def last_us(self):
+        us = (C.c_float * 4)()
+        self.lib.lmot_shared_last_us(self.h, us)
+        return dict(zip(("detect", "allgather", "tracker", "broadcast"), (float(x) for x in us)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lmot_shared_destroy(self.h)
+            self.h = None

@@ -437,6 +437,12 @@ const char* lmot_strerror(int s) {
 
 const char* lmot_build_info(void) { return "liblmot sm_100a, nvcc " __DATE__ " -fmad=false"; }
 
+int lmot_get_params(const lmot_ctx* ctx, lmot_params* out) {
+  if (!ctx || !out) return LMOT_ERR_INVALID;
+  *out = ctx->c.prm;
+  return LMOT_OK;
+}
+
 const char* lmot_last_error(const lmot_ctx* ctx) { return ctx ? ctx->c.last_error.c_str() : ""; }
 
 int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
@@ -951,6 +957,62 @@ int lmot_batch(lmot_ctx* ctx, const float* const* points, const int* n, int n_fr
   int rc = lmot_batch_submit(ctx, points, n, n_frames, stride_floats, timestamp_us, v_gps, yaw_gps);
   if (rc) return rc;
   return lmot_batch_collect(ctx, out);
+}
+
+// ---------------------------------------------------------------------------------------------- device-side hand-over (multi-GPU)
+// Several sensor streams on several GPUs feeding ONE tracker (host/shared_tracker.cpp): detection leaves its box
+// list on the device, the lists travel rank to rank with NCCL, the owner folds them in WITHOUT a host bounce.
+int lmot_detect_boxes_dev(lmot_ctx* ctx, const float** d_boxes, const int** d_n_boxes) {
+  if (!ctx || !d_boxes || !d_n_boxes) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  Slot* s = &c->slots[c->last_slot];       // the slot of the most recent lmot_detect_dev / lmot_frame_dev
+  *d_boxes = s->d_boxes;
+  *d_n_boxes = s->d_counters + CNT_N_BOXES;
+  return LMOT_OK;
+}
+
+int lmot_tracker_counters_dev(lmot_ctx* ctx, int** d_n_tracks) {
+  if (!ctx || !d_n_tracks) return LMOT_ERR_INVALID;
+  *d_n_tracks = ctx->c.d_trk_counters + CNT_N_TRACKS;
+  return LMOT_OK;
+}
+
+// n_lists box lists of capacity cap_per_list boxes each (d_lists[l * cap_per_list * 24], lengths d_counts[l], all DEVICE memory,
+// ordered after the work queued on the caller stream) are concatenated in list order and folded into the track table as ONE
+// immUkfJpdaf step.  Asynchronous on the caller stream; results with lmot_frame_fetch.
+int lmot_track_step_lists_dev(lmot_ctx* ctx, const float* d_lists, const int* d_counts, int n_lists, int cap_per_list, double timestamp_us,
+                              double v_gps, double yaw_gps) {
+  if (!ctx || !d_lists || !d_counts || n_lists < 1 || n_lists > kMaxBatch || cap_per_list < 1) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  int rc = batch_ensure(c, 1);              // the bank's box buffer + counters are the tracker's input
+  if (rc) return rc;
+  Slot* k = &c->bank[0];                    // (ordering is the caller stream's; no host synchronisation here)
+  Result* r = acquire_result(c, true);
+  k->res = r;
+  r->n_kev = 0; r->batch_frames = 0;
+  cudaStream_t st = c->stream;
+  if ((rc = boxes_pack_lists_launch(c, st, d_lists, d_counts, n_lists, cap_per_list, k->d_boxes, k->d_counters))) return rc;
+  if (c->prm.global_frame && (rc = boxes_to_global_launch(c, k, st, k->d_boxes, k->d_counters, timestamp_us, v_gps, yaw_gps, false))) return rc;
+  if ((rc = tracker_launch(c, k, st, k->d_boxes, k->d_counters, timestamp_us, v_gps, yaw_gps))) return rc;
+  if ((rc = tracker_publish(c, r, st))) return rc;
+  LMOT_CUDA(c, cudaEventRecord(r->ev_done, st));
+  LMOT_CUDA(c, cudaEventRecord(k->ev_trk_done, st));
+  LMOT_CUDA(c, cudaEventRecord(k->ev_det_done, st));
+  r->has_tracks = true;
+  if (!r->in_flight) { r->in_flight = true; ++c->n_in_flight; }
+  return LMOT_OK;
+}
+
+// after the table was received from another rank (NCCL broadcast into lmot_tracker_table's pointer, count already in the device
+// counter lmot_tracker_counters_dev points at): rebuild the side arrays before the next step.  n = the count, as the host knows it.
+int lmot_tracker_table_received(lmot_ctx* ctx, int n) {
+  if (!ctx || n < 0 || n > ctx->c.prm.max_tracks) return LMOT_ERR_INVALID;
+  Ctx* c = &ctx->c;
+  c->h_trk_counters[CNT_N_TRACKS] = n;
+  c->act_valid = false;
+  c->last_trk_res = nullptr;
+  return LMOT_OK;
 }
 
 int lmot_origin_points(lmot_ctx* ctx, double timestamp_us, double v_gps, double yaw_gps, double out6[6]) {

@@ -764,6 +764,34 @@ int boxes_concat_launch(Ctx* c, Slot* const* slots, int F, cudaStream_t st, floa
   return LMOT_OK;
 }
 
+// n_lists padded device box lists (capacity cap boxes each, lengths in d_counts) -> one contiguous list + the counter block the
+// tracker reads (multi-GPU hand-over: the lists arrived by ncclAllGather)
+__global__ void __launch_bounds__(256)
+pack_lists_kernel(const float* __restrict__ lists, const int* __restrict__ counts, int n_lists, int cap, int max_boxes, float* __restrict__ boxes,
+                  int* __restrict__ counters) {
+  __shared__ int s_off[kMaxBatch + 1];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int l = 0; l < n_lists; ++l) { s_off[l] = acc; acc += min(max(counts[l], 0), cap); }
+    s_off[n_lists] = acc;
+    counters[CNT_N_BOXES] = acc < max_boxes ? acc : max_boxes;
+    counters[CNT_ERROR] = acc > max_boxes ? (int)LMOT_ERR_CAPACITY : 0;
+    counters[CNT_N_ELEV] = 0; counters[CNT_N_GROUND] = 0; counters[CNT_NUM_CLUSTER] = 0;
+  }
+  __syncthreads();
+  for (int l = 0; l < n_lists; ++l) {
+    const int off = s_off[l], cnt = min(s_off[l + 1], max_boxes) - off;
+    const float* src = lists + (size_t)l * cap * 24;
+    for (int e = threadIdx.x; e < cnt * 24; e += 256) boxes[(size_t)off * 24 + e] = src[e];
+  }
+}
+
+int boxes_pack_lists_launch(Ctx* c, cudaStream_t st, const float* d_lists, const int* d_counts, int n_lists, int cap, float* d_boxes, int* d_counters) {
+  pack_lists_kernel<<<1, 256, 0, st>>>(d_lists, d_counts, n_lists, cap, c->prm.max_boxes, d_boxes, d_counters);
+  LMOT_CUDA(c, cudaGetLastError());
+  return LMOT_OK;
+}
+
 int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper, bool post_sem) {
   Slot* sl[1] = {s};
   const int nu[1] = {n_upper};

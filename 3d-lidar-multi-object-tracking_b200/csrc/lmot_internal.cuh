@@ -295,6 +295,7 @@ int boxfit_alloc_shared(Ctx* c);
 void boxfit_free(Slot* s);
 int boxfit_launch(Ctx* c, Slot* s, cudaStream_t st, int n_upper, bool post_sem = false);
 int boxfit_launch_batch(Ctx* c, Slot* const* slots, int F, cudaStream_t st, const int* n_upper, bool post_sem);
+int boxes_pack_lists_launch(Ctx* c, cudaStream_t st, const float* d_lists, const int* d_counts, int n_lists, int cap, float* d_boxes, int* d_counters);
 int boxes_concat_launch(Ctx* c, Slot* const* slots, int F, cudaStream_t st, float* d_boxes, int* d_counters, int* d_frame_counts, int* det_sem);
 void origin_points_fold(TrackerHost& h, double timestamp, double v_gps, double yaw_gps);
 int tracker_alloc(Ctx* c);

@@ -114,6 +114,7 @@ typedef struct lmot_ctx lmot_ctx;
 int lmot_default_params(lmot_params* p);
 int lmot_create(lmot_ctx** out, const lmot_params* params, int device);
 void lmot_destroy(lmot_ctx* ctx);
+int lmot_get_params(const lmot_ctx* ctx, lmot_params* out);   /* the parameters the context runs with (capacities after clamping) */
 const char* lmot_strerror(int status);
 const char* lmot_last_error(const lmot_ctx* ctx); /* text of the last CUDA error seen by this context */
 const char* lmot_build_info(void);
@@ -271,6 +272,20 @@ int lmot_tracker_set_ego(lmot_ctx* ctx, const double ego8[8]);
  * then call lmot_tracker_set_num_tracks.  The pointer stays valid for the life of the context. */
 int lmot_tracker_table(lmot_ctx* ctx, void** dev_ptr, int* bytes_per_track, int* capacity);
 int lmot_tracker_set_num_tracks(lmot_ctx* ctx, int n);
+
+/* ---- device-side hand-over for several GPUs feeding ONE tracker (host/shared_tracker.cpp uses these with NCCL) ---
+ * lmot_detect_boxes_dev      : device pointers to the box list (float[max_boxes*24]) and its length (int) of the most recent
+ *                              lmot_detect_dev on this context -- the send buffers of the ncclAllGather
+ * lmot_track_step_lists_dev  : n_lists (<= LMOT_MAX_BATCH) padded DEVICE box lists of cap_per_list boxes each, lengths in d_counts,
+ *                              concatenated in list order -> ONE immUkfJpdaf step (imm_ukf_jpda.cpp:704), asynchronous on the caller
+ *                              stream and ordered after the work already queued on it; results with lmot_frame_fetch
+ * lmot_tracker_counters_dev  : device pointer to the number of tracks in the table (the count that travels with the table)
+ * lmot_tracker_table_received: after an ncclBroadcast into lmot_tracker_table's pointer (and of the count): the table holds n tracks now */
+int lmot_detect_boxes_dev(lmot_ctx* ctx, const float** d_boxes, const int** d_n_boxes);
+int lmot_track_step_lists_dev(lmot_ctx* ctx, const float* d_lists, const int* d_counts, int n_lists, int cap_per_list, double timestamp_us,
+                              double v_gps, double yaw_gps);
+int lmot_tracker_counters_dev(lmot_ctx* ctx, int** d_n_tracks);
+int lmot_tracker_table_received(lmot_ctx* ctx, int n);
 
 /* ---- inspection of the last frame's device state (parity tests, debugging) ----------------------------- */
 /* polar grid after ground removal: each float[80*120] / uint8[80*120], nullable */

@@ -14,6 +14,8 @@ inline void spin() {}
 struct Publisher { template <class M> void publish(const M&) const {} };
 struct Subscriber {};
 struct NodeHandle {
+  NodeHandle() {}
+  explicit NodeHandle(const std::string&) {}
   template <class T> bool param(const std::string&, T& v, const T& d) const { v = d; return false; }
   template <class M> Publisher advertise(const std::string&, int) { return Publisher(); }
   template <class M> Subscriber subscribe(const std::string&, int, void (*)(const std::shared_ptr<const M>&)) { return Subscriber(); }

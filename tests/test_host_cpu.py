@@ -106,3 +106,13 @@ def test_pinned_alloc_without_a_gpu_returns_null(pkg):
     assert not lib.lmot_pinned_alloc(1 << 20)
     lib.lmot_pinned_free.argtypes = [ctypes.c_void_p]
     lib.lmot_pinned_free(None)
+
+
+def test_shared_tracker_library_exports_every_declared_symbol(pkg):
+    """include/lmot_shared.h <-> liblmot_shared.so (C++ over liblmot.so + NCCL); no compute without GPUs."""
+    lib = pkg.load_shared_library()
+    header = open(os.path.join(os.path.dirname(pkg.HERE), "include", "lmot_shared.h")).read()
+    declared = sorted(set(re.findall(r"\b(lmot_shared_[a-z0-9_]+)\s*\(", header)))
+    assert declared and set(declared) == set(pkg.SHARED_ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
