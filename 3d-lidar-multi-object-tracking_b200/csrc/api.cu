@@ -157,9 +157,9 @@ int submit(Ctx* c, Slot* s, Result* r, const float4* d_pts, int n, bool with_tra
   // the slot's previous boxes / counters must have been consumed by the tracker
   LMOT_CUDA(c, cudaStreamWaitEvent(s->stream, s->ev_trk_done, 0));
   if (c->timing) cudaEventRecord(r->ev[0], s->stream);
-  if ((rc = ground_launch(c, s, s->stream, d_pts, n, true, false))) return rc;
+  if ((rc = ground_launch(c, s, s->stream, d_pts, n, true, false, c->fuse_ccl))) return rc;
   if (c->timing) cudaEventRecord(r->ev[1], s->stream);
-  if ((rc = cluster_launch(c, s, s->stream, n, true))) return rc;
+  if (!c->fuse_ccl && (rc = cluster_launch(c, s, s->stream, n, true))) return rc;      // (fused: the ground kernel's last CTA did it)
   if (c->timing) cudaEventRecord(r->ev[2], s->stream);
   const bool gf = with_tracker && c->prm.global_frame;
   if ((rc = boxfit_launch(c, s, s->stream, n, with_tracker && !gf))) return rc;      // with_tracker: posts the slot's detection semaphore
@@ -245,9 +245,9 @@ int batch_submit(Ctx* c, int bank_i, Result* r, const float4* const* d_pts, cons
   r->n_kev = 0;
   r->batch_frames = F;
   if (c->timing) cudaEventRecord(r->ev[0], st);
-  if ((rc = ground_launch_batch(c, sl, F, pp, n, st, true, false))) return rc;
+  if ((rc = ground_launch_batch(c, sl, F, pp, n, st, true, false, c->fuse_ccl))) return rc;
   if (c->timing) cudaEventRecord(r->ev[1], st);
-  if ((rc = ccl_launch_batch(c, sl, F, st))) return rc;
+  if (!c->fuse_ccl && (rc = ccl_launch_batch(c, sl, F, st))) return rc;
   if (c->timing) cudaEventRecord(r->ev[2], st);
   if ((rc = boxfit_launch_batch(c, sl, F, st, n, false))) return rc;
   int* d_fc = nullptr;                       // the per-frame counts go straight into the result's pinned, device-mapped block
@@ -480,7 +480,7 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   c->gp.tol = p.ground_tolerance;
   gauss_taps(c->gp.tap);
   if (const char* e = getenv("LMOT_COOP")) c->coop_launch = atoi(e) != 0;
-  if (const char* e = getenv("LMOT_CCL")) { const int v = atoi(e); if (v == 2 || v == 3) c->ccl_variant = v; }
+  if (const char* e = getenv("LMOT_FUSE_CCL")) c->fuse_ccl = atoi(e) != 0;
   if (const char* e = getenv("LMOT_SPIN_LIMIT")) c->spin_limit = (unsigned)strtoul(e, nullptr, 0);   // 0: device-side waits never trap (debuggers, MPS)
   if (const char* e = getenv("LMOT_TRK_CTAS")) { const int v = atoi(e); if (v >= 8 && v <= 4096) c->trk_ctas = v; }     // tuning only
   if (const char* e = getenv("LMOT_FIT_CTAS")) { const int v = atoi(e); if (v >= 8 && v <= 4096) c->fit_ctas = v; }
@@ -901,8 +901,8 @@ int lmot_batch_ground_ccl_dev(lmot_ctx* ctx, const float* const* d_points, const
   }
   sl[0]->res = &c->results[0];
   c->results[0].n_kev = 0;
-  if ((rc = ground_launch_batch(c, sl, n_frames, pp, n, c->stream, true, false))) return rc;
-  return ccl_launch_batch(c, sl, n_frames, c->stream);
+  if ((rc = ground_launch_batch(c, sl, n_frames, pp, n, c->stream, true, false, c->fuse_ccl))) return rc;
+  return c->fuse_ccl ? LMOT_OK : ccl_launch_batch(c, sl, n_frames, c->stream);
 }
 
 static int batch_fill(Ctx* c, Result* r, int rc0, lmot_batch_out* out, const lmot_frame_out& fo) {

@@ -26,6 +26,7 @@
 #include "lmot_internal.cuh"
 #include "exact_math.cuh"
 #include "tma.cuh"
+#include "ccl_device.cuh"
 
 namespace lmot {
 
@@ -320,6 +321,7 @@ constexpr int kOffPts = (kOffKeys + kPolarCells * 4 + 127) & ~127;          // [
 __host__ __device__ constexpr int fused_smem_bytes(int res_tiles, int tiles) { return kOffPts + res_tiles * kTilePts * 16 + tiles * kTilePts * 2; }
 constexpr int kFusedSmem = fused_smem_bytes(kMaxResTiles, kMaxTiles);
 static_assert(kFusedSmem <= 227 * 1024, "ground_fused_kernel: shared memory budget");
+static_assert(kDenseSmem <= kFusedSmem, "the fused CCL reuses the ground kernel's shared memory");
 
 struct FusedOut {
   uint8_t* labels;          // nullable
@@ -344,6 +346,10 @@ struct FrameIO {
   float* hg;                // [9600] nullable (inspection): hGround of ground cells, -inf otherwise
   float* lim;               // [9600] label limit of every cell (label_limit): phase 2 -> phase 3
   FusedOut out;
+  // fused frame path: the last CTA of the frame to finish phase 3 labels the connected components of the bit planes all of them marked
+  int fuse_ccl;
+  unsigned* done_ctr;       // atomicInc counter of finished CTAs (wraps to 0 at G: needs no reset)
+  CclFrame ccl;
 };
 struct GroundBatch {
   int n_frames, ctas_per_frame;
@@ -648,6 +654,20 @@ ground_fused_kernel(const __grid_constant__ GroundBatch B, const __grid_constant
     run_e += tt & 0xFFFFu; run_g += tt >> 16;
   }
   phase_mark(phase_clock, 7);
+
+  // ---- component clustering of this frame by the last of its CTAs to get here: no launch (and no launch latency) between ground
+  // removal and clustering, and the CCL of a frame that finishes early overlaps the other frames' tails (batched launches)
+  if (F.fuse_ccl) {
+    __shared__ int s_last;
+    __threadfence();                               // the CTA's bit-plane atomics and cartesian cells are visible device-wide ...
+    __syncthreads();
+    if (tid == 0) s_last = (atomicInc(F.done_ctr, (unsigned)Gf - 1u) == (unsigned)Gf - 1u) ? 1 : 0;    // ... before it counts as finished
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      ccl_dense_body(F.ccl, fsm, nullptr, 0);     // 1,024 threads, reuses the kernel's dynamic shared memory (>= kDenseSmem, see ground_launch_batch)
+    }
+  }
 }
 
 // inspection only (lmot_debug_polar_grid): all five 80x120 grids of the reference from the min-z keys of the last launch, ten
@@ -712,8 +732,8 @@ int ground_alloc(Ctx* c, Slot* s) {
   LMOT_CUDA(c, cudaMalloc(&s->d_ground, np * sizeof(float4)));
   LMOT_CUDA(c, cudaMalloc(&s->d_gdesc, (size_t)kDescStride * c->fused_max_ctas * sizeof(unsigned long long)));
   LMOT_CUDA(c, cudaMemsetAsync(s->d_gdesc, 0, (size_t)kDescStride * c->fused_max_ctas * sizeof(unsigned long long), st));
-  LMOT_CUDA(c, cudaMalloc(&s->d_gbar, sizeof(unsigned)));
-  LMOT_CUDA(c, cudaMemsetAsync(s->d_gbar, 0, sizeof(unsigned), st));
+  LMOT_CUDA(c, cudaMalloc(&s->d_gbar, 2 * sizeof(unsigned)));            // [0] barrier arrivals, [1] finished CTAs (fused CCL)
+  LMOT_CUDA(c, cudaMemsetAsync(s->d_gbar, 0, 2 * sizeof(unsigned), st));
   s->bar_base = 0; s->epoch = 0;
   LMOT_CUDA(c, cudaMalloc(&s->d_counters, CNT_COUNT * sizeof(int)));
   LMOT_CUDA(c, cudaMemsetAsync(s->d_counters, 0, CNT_COUNT * sizeof(int), st));
@@ -756,7 +776,8 @@ bool ground_reads_input_once(const Ctx* c, int n) {
 // One launch for F frames (F = 1: the frame pipeline and the stage entry points; F > 1: one frame per sensor stream, api.cu
 // lmot_batch_*).  Frame i runs on slots[i]'s buffers; its CTAs are [i * G, (i + 1) * G) of the grid and synchronise among themselves.
 int ground_launch_batch(Ctx* c, Slot* const* slots, int F, const float4* const* pts, const int* n, cudaStream_t st, bool fuse_count,
-                        bool want_labels) {
+                        bool want_labels, bool fuse_ccl) {
+  if (fuse_ccl && !fuse_count) return LMOT_ERR_INVALID;
   if (F < 1 || F > kMaxBatch) return LMOT_ERR_INVALID;
   int n_max = 0;
   for (int i = 0; i < F; ++i) { slots[i]->cur_points = pts[i]; slots[i]->cur_n = n[i]; if (n[i] > n_max) n_max = n[i]; }
@@ -791,6 +812,9 @@ int ground_launch_batch(Ctx* c, Slot* const* slots, int F, const float4* const* 
     f.keys_next = s->d_polar_key + (1 - parity) * kPolarCells;
     f.bar = s->d_gbar; f.bar_target = s->bar_base + (unsigned)G;
     f.hg = want_labels ? s->d_hg : nullptr; f.lim = s->d_lim;
+    f.fuse_ccl = fuse_ccl ? 1 : 0; f.done_ctr = s->d_gbar + 1;
+    f.ccl.once = s->d_cart_bits; f.ccl.twice = s->d_cart_bits + 2000; f.ccl.prev_occ = s->d_cart_bits + 4000;
+    f.ccl.out = s->d_label_grid; f.ccl.counters = s->d_counters;
     s->hg_valid = want_labels;
     f.epoch = s->epoch; f.desc = s->d_gdesc;
     f.out.labels = want_labels ? s->d_labels : nullptr;
@@ -807,7 +831,8 @@ int ground_launch_batch(Ctx* c, Slot* const* slots, int F, const float4* const* 
   // every frame's chunk is laid out with the tile count of the longest one (the kernel derives its layout from its own chunk;
   // a shorter chunk just leaves the tail of the allocation unused)
   const int tiles = (chunk_max + kTilePts - 1) / kTilePts;
-  const size_t smem = (size_t)fused_smem_bytes(tiles < kMaxResTiles ? tiles : kMaxResTiles, tiles > 0 ? tiles : 1);
+  size_t smem = (size_t)fused_smem_bytes(tiles < kMaxResTiles ? tiles : kMaxResTiles, tiles > 0 ? tiles : 1);
+  if (fuse_ccl && smem < (size_t)kDenseSmem) smem = kDenseSmem;
   if (c->coop_launch) {
     LMOT_CUDA(c, cudaLaunchCooperativeKernel((const void*)ground_fused_kernel, dim3(G * F), dim3(kFusedThreads), args, smem, st));
   } else {
@@ -830,11 +855,11 @@ int ground_launch_batch(Ctx* c, Slot* const* slots, int F, const float4* const* 
   return LMOT_OK;
 }
 
-int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count, bool want_labels) {
+int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count, bool want_labels, bool fuse_ccl) {
   Slot* sl[1] = {s};
   const float4* pp[1] = {pts};
   const int nn[1] = {n};
-  return ground_launch_batch(c, sl, 1, pp, nn, st, fuse_count, want_labels);
+  return ground_launch_batch(c, sl, 1, pp, nn, st, fuse_count, want_labels, fuse_ccl);
 }
 
 // all five polar grids of the slot's LAST ground launch, recomputed from its min-z keys (inspection only)

@@ -187,7 +187,7 @@ struct Ctx {
   int last_ground_ctas = 0;
   unsigned long long* d_fit_clock = nullptr;     // diagnostic: [CTAs][8] stamps of the last box_fit_kernel launch (same switch)
   int last_fit_ctas = 0;
-  int ccl_variant = 3;                 // 3: ccl_dense_kernel; 2: ccl_bitmap_kernel (LMOT_CCL, A/B diagnostics)
+  bool fuse_ccl = true;                // frame / batch path: clustering runs in the ground kernel's tail (LMOT_FUSE_CCL=0: separate launch, A/B + phase stamps)
   unsigned long long* d_ccl_clock = nullptr;     // diagnostic: [frames][16] %globaltimer stamps of the last ccl_bitmap_kernel launch (same switch)
   bool zero_copy = false;              // lmot_frame_submit: pinned host frames are read by the ground kernel directly (LMOT_ZERO_COPY=1; off: slower than the copy engine)
   bool ground_half_sms = true;         // frame pipeline: ground kernel on half of the SMs (ground.cu ground_launch; LMOT_GROUND_HALF=0 disables, A/B only)
@@ -278,8 +278,8 @@ int ground_alloc(Ctx* c, Slot* s);
 void ground_free(Slot* s);
 // pts: device float4 array of n points; fuse_count: also bin the elevated points into the slot's cartesian count grid
 // want_labels: also write the per-point u8 label array (stage entry point); the frame pipeline skips it
-int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count = false, bool want_labels = true);
-int ground_launch_batch(Ctx* c, Slot* const* slots, int F, const float4* const* pts, const int* n, cudaStream_t st, bool fuse_count, bool want_labels);
+int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count = false, bool want_labels = true, bool fuse_ccl = false);
+int ground_launch_batch(Ctx* c, Slot* const* slots, int F, const float4* const* pts, const int* n, cudaStream_t st, bool fuse_count, bool want_labels, bool fuse_ccl = false);
 int ground_cells_debug(Ctx* c, Slot* s, cudaStream_t st);
 int ground_grids_debug(Ctx* c, Slot* s, cudaStream_t st);   // d_minz / d_height / d_smoothed / d_hdiff / d_hg_dbg from the last launch's keys
 bool ground_reads_input_once(const Ctx* c, int n);

@@ -49,7 +49,7 @@ for s in range(F):
     r = ctx.ground_remove(streams[s][0]); ne += len(r["elevated"]); nf += len(r["elevated"]) + len(r["ground"])
 bg = F * (16 * n + 9600 * 24) + 16 * nf
 bc = 20 * ne + F * 2 * 62500 * 4
-print(json.dumps(dict(case=f"batched tick {F} x 120 k: ground + CCL (two launches)", us_per_tick=us, ground_bytes=bg, ccl_bytes=bc,
+print(json.dumps(dict(case=f"batched tick {F} x 120 k: ground + CCL (one launch unless LMOT_FUSE_CCL=0)", us_per_tick=us, ground_bytes=bg, ccl_bytes=bc,
                       gbs=(bg + bc) / us / 1e3, frac=(bg + bc) / us / 1e3 / peak)), flush=True)
 ctx.enable_timing(True)
 ctx.tracker_reset()

@@ -1,6 +1,7 @@
 """Diagnostic: where do the detection kernels spend their time?  %globaltimer stamps at the phase boundaries of
 ground_fused_kernel (every CTA), ccl_bitmap_kernel (per frame) and box_fit_kernel (every CTA; the slowest one is the kernel)."""
 import importlib, os, sys
+os.environ.setdefault("LMOT_FUSE_CCL", "0")     # the CCL phase stamps need the stand-alone kernel (the product fuses it into the ground kernel's tail)
 import numpy as np
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -2,6 +2,7 @@
 ticks (8 x 120 k: ground, CCL, counting sort, box fitting) without the tracker.
   ncu --set full --import-source on --clock-control none -k regex:"ground_fused|ccl_|box_fit" --launch-skip 2 -c 8 -o gpurun_out/r2_detect python scripts/prof_detect.py"""
 import importlib, os, sys
+os.environ.setdefault("LMOT_FUSE_CCL", "0")     # profile clustering as its own kernel
 import numpy as np
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
