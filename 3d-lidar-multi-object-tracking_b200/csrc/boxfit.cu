@@ -11,7 +11,7 @@
 // ties, the random index picks the i-th point), so the gather is a STABLE counting sort by cluster id:
 //   B1 tile_hist_kernel    per 1024-point tile: cluster id of each point (label grid lookup through the u16 cell
 //                          id kept by clustering) + shared-memory histogram -> table[tile][cluster]
-//   B2 seg_offsets_kernel  exclusive scan over tiles per cluster, then over clusters -> segment starts
+//   B2 seg_offsets_body    exclusive scan over tiles per cluster, then over clusters -> segment starts (run by B1's last CTA)
 //   B3 scatter_kernel      stable in-tile ranks (warp match_any, warps in order) -> sorted point indices
 //   B4 box_fit_kernel      one CTA per cluster (grid-stride), all of getBoundingBox; the last CTA to finish
 //                          compacts the accepted boxes in cluster-id order (:355,365 skip rejected clusters).
@@ -42,8 +42,11 @@ struct FitFrame {
   const float4* elev; float4* sorted_pts;
   float* cl_box; float* cl_marker; uint8_t* cl_ok;
   float* boxes; float* markers; int* done; int* det_sem;
+  unsigned* hist_ctr;      // atomicInc counter of finished tile_hist CTAs (wraps at the grid size: needs no reset)
 };
 struct FitBatch { FitFrame f[kMaxBatch]; };
+
+__device__ __forceinline__ void seg_offsets_body(const FitFrame& F, int max_clusters);
 
 __global__ void __launch_bounds__(kTile)
 tile_hist_kernel(const __grid_constant__ FitBatch B, int max_clusters) {
@@ -54,7 +57,7 @@ tile_hist_kernel(const __grid_constant__ FitBatch B, int max_clusters) {
   const int n = counters[CNT_N_ELEV];
   const int K = min(counters[CNT_NUM_CLUSTER], max_clusters);
   const int tile = blockIdx.x;
-  if (tile * kTile >= n) return;
+  if (tile * kTile < n) {
   for (int k = threadIdx.x; k <= K; k += kTile) s_hist[k] = 0;
   __syncthreads();
   const int i = tile * kTile + threadIdx.x;
@@ -70,14 +73,22 @@ tile_hist_kernel(const __grid_constant__ FitBatch B, int max_clusters) {
   __syncthreads();
   int* row = table + (size_t)tile * (max_clusters + 1);
   for (int k = threadIdx.x; k <= K; k += kTile) row[k] = s_hist[k];
+  }
+  // B2 by the last CTA of the frame to get here (tiles past the end of the cloud count too)
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicInc(F.hist_ctr, gridDim.x - 1u) == gridDim.x - 1u) ? 1 : 0;
+  __syncthreads();
+  if (s_last) { __threadfence(); seg_offsets_body(F, max_clusters); }
 }
 
 // ---------------------------------------------------------------------------------------------- B2
-__global__ void __launch_bounds__(1024)
-seg_offsets_kernel(const __grid_constant__ FitBatch B, int max_clusters) {
+// exclusive scan over tiles per cluster, then over clusters -> segment starts.  One CTA of 1,024 threads per frame: the LAST
+// tile_hist CTA of the frame to finish runs it (no launch in between); seg_offsets_kernel wraps it for frames without points.
+__device__ __forceinline__ void seg_offsets_body(const FitFrame& F, int max_clusters) {
   __shared__ int s_warp[32];
   __shared__ int s_carry;
-  const FitFrame& F = B.f[blockIdx.x];
   int* __restrict__ table = F.table; int* counters = F.counters;
   int* __restrict__ seg_start = F.seg_start; int* __restrict__ seg_size = F.seg_size; int* __restrict__ done = F.done;
   const int n = counters[CNT_N_ELEV];
@@ -127,6 +138,9 @@ seg_offsets_kernel(const __grid_constant__ FitBatch B, int max_clusters) {
   }
   if (threadIdx.x == 0) counters[CNT_N_CLUSTERED] = s_carry;
 }
+
+__global__ void __launch_bounds__(1024)
+seg_offsets_kernel(const __grid_constant__ FitBatch B, int max_clusters) { seg_offsets_body(B.f[blockIdx.x], max_clusters); }
 
 // ---------------------------------------------------------------------------------------------- B3
 __global__ void __launch_bounds__(kTile)
@@ -461,20 +475,57 @@ box_fit_kernel(const __grid_constant__ FitBatch B, const __grid_constant__ BoxPa
         s_flag8[i] = (lowv ? 1 : 0) | (upv ? 2 : 0);
       }
       __syncthreads();
-      if (tid == 0) {
-        int m = 0;
-        if (W == 1) {
-          s_hx[0] = s_cx[0]; s_hy[0] = s_clo[0]; m = 1;
+      // hull sequence = lower-chain vertices left to right, then upper-chain vertices right to left: positions from two block-wide
+      // counts (thread t owns the compacted columns [8t, 8t+8)); as a loop on thread 0 this was 2 W dependent shared-memory
+      // round trips -- 12 us for a 400-column cluster, the longest phase of the slowest CTA
+      if (W == 1) {
+        if (tid == 0) {
+          int m = 1;
+          s_hx[0] = s_cx[0]; s_hy[0] = s_clo[0];
           if (s_chi[0] != s_clo[0]) { s_hx[1] = s_cx[0]; s_hy[1] = s_chi[0]; m = 2; }
-        } else {
-          for (int i = 0; i < W; ++i)
-            if (s_flag8[i] & 1) { if (m < kHullCap) { s_hx[m] = s_cx[i]; s_hy[m] = s_clo[i]; } ++m; }
-          for (int i = W - 1; i >= 0; --i)
-            // the lo point of the first / last column already sits in the lower chain
-            if ((s_flag8[i] & 2) && !((i == 0 || i == W - 1) && s_chi[i] == s_clo[i])) { if (m < kHullCap) { s_hx[m] = s_cx[i]; s_hy[m] = s_chi[i]; } ++m; }
+          s_m = m;
         }
-        if (m > kHullCap) { counters[CNT_ERROR] = LMOT_ERR_CAPACITY; m = kHullCap; }
-        s_m = m;
+      } else {
+        const int lane = tid & 31, warp = tid >> 5;
+        unsigned lowm = 0, upm = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = tid * 8 + u;
+          if (i < W) {
+            const int fl = s_flag8[i];
+            if (fl & 1) lowm |= 1u << u;
+            // the lo point of the first / last column already sits in the lower chain
+            if ((fl & 2) && !((i == 0 || i == W - 1) && s_chi[i] == s_clo[i])) upm |= 1u << u;
+          }
+        }
+        const int cl = __popc(lowm), cu = __popc(upm);
+        int il = cl, iu = cu;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int a = __shfl_up_sync(0xFFFFFFFFu, il, o), b = __shfl_up_sync(0xFFFFFFFFu, iu, o);
+          if (lane >= o) { il += a; iu += b; }
+        }
+        if (lane == 31) { s_redi[warp] = il; s_bidx[warp] = iu; }
+        __syncthreads();
+        int bl = 0, bu = 0, tl = 0, tu = 0;
+        for (int w = 0; w < kFitThreads / 32; ++w) { if (w < warp) { bl += s_redi[w]; bu += s_bidx[w]; } tl += s_redi[w]; tu += s_bidx[w]; }
+        int pl = bl + il - cl;                        // lower-chain vertices before this thread's columns
+        int pu_after = tu - (bu + iu);                // upper-chain vertices AFTER this thread's columns (they come first, right to left)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = tid * 8 + u;
+          if ((lowm >> u) & 1u) { if (pl < kHullCap) { s_hx[pl] = s_cx[i]; s_hy[pl] = s_clo[i]; } ++pl; }
+        }
+#pragma unroll
+        for (int u = 7; u >= 0; --u) {
+          const int i = tid * 8 + u;
+          if ((upm >> u) & 1u) { const int pos = tl + pu_after; if (pos < kHullCap) { s_hx[pos] = s_cx[i]; s_hy[pos] = s_chi[i]; } ++pu_after; }
+        }
+        if (tid == 0) {
+          int m = tl + tu;
+          if (m > kHullCap) { counters[CNT_ERROR] = LMOT_ERR_CAPACITY; m = kHullCap; }
+          s_m = m;
+        }
       }
       __syncthreads();
       const int m = s_m;
@@ -698,8 +749,8 @@ int boxfit_alloc(Ctx* c, Slot* s) {
   LMOT_CUDA(c, cudaMalloc(&s->d_boxes, (size_t)c->prm.max_boxes * 24 * sizeof(float)));
   LMOT_CUDA(c, cudaMalloc(&s->d_boxes_g, (size_t)c->prm.max_boxes * 24 * sizeof(float)));
   LMOT_CUDA(c, cudaMalloc(&s->d_markers, (size_t)c->prm.max_boxes * 6 * sizeof(float)));
-  LMOT_CUDA(c, cudaMalloc(&s->d_done, sizeof(int)));
-  LMOT_CUDA(c, cudaMemsetAsync(s->d_done, 0, sizeof(int), s->stream));
+  LMOT_CUDA(c, cudaMalloc(&s->d_done, 2 * sizeof(int)));                 // [0] finished box_fit CTAs, [1] finished tile_hist CTAs
+  LMOT_CUDA(c, cudaMemsetAsync(s->d_done, 0, 2 * sizeof(int), s->stream));
   LMOT_CUDA(c, cudaMalloc(&s->d_det_sem, sizeof(int)));
   LMOT_CUDA(c, cudaMemsetAsync(s->d_det_sem, 0, sizeof(int), s->stream));
   return LMOT_OK;
@@ -717,6 +768,7 @@ static void fit_frame_of(const Slot* s, FitFrame& f, bool post_sem) {
   f.elev = s->d_elev; f.sorted_pts = s->d_sorted_pts;
   f.cl_box = s->d_cl_box; f.cl_marker = s->d_cl_marker; f.cl_ok = s->d_cl_ok;
   f.boxes = s->d_boxes; f.markers = s->d_markers; f.done = s->d_done; f.det_sem = post_sem ? s->d_det_sem : nullptr;
+  f.hist_ctr = reinterpret_cast<unsigned*>(s->d_done + 1);
 }
 
 // inputs per frame: s->d_elev / CNT_N_ELEV, s->d_cart (from clustering), s->d_label_grid / CNT_NUM_CLUSTER.
@@ -731,8 +783,8 @@ int boxfit_launch_batch(Ctx* c, Slot* const* slots, int F, cudaStream_t st, cons
   for (int i = 0; i < F; ++i) fit_frame_of(slots[i], B.f[i], post_sem && F == 1);
   for (int i = F; i < kMaxBatch; ++i) B.f[i] = B.f[0];
   Slot* s0 = slots[0];
-  if (tiles > 0) { tile_hist_kernel<<<dim3(tiles, F), kTile, sh, st>>>(B, c->prm.max_clusters); kernel_mark(c, s0, st); }
-  seg_offsets_kernel<<<F, 1024, 0, st>>>(B, c->prm.max_clusters);
+  if (tiles > 0) tile_hist_kernel<<<dim3(tiles, F), kTile, sh, st>>>(B, c->prm.max_clusters);     // + segment offsets by its last CTA per frame
+  else seg_offsets_kernel<<<F, 1024, 0, st>>>(B, c->prm.max_clusters);
   kernel_mark(c, s0, st);
   if (tiles > 0) { scatter_kernel<<<dim3(tiles, F), kTile, sh, st>>>(B, c->prm.max_clusters); kernel_mark(c, s0, st); }
   BoxParams P;
