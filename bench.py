@@ -453,7 +453,8 @@ def batched_block(lmot, synth, local_rank, stream, peak, ticks=12, warm=3, F=8):
     dev = [torch.from_numpy(np.stack(st_)).cuda() for st_ in streams]
     ctx = lmot.Lmot(device=local_rank)
     ctx.set_stream(stream.cuda_stream)
-    args = lambda t: [(dev[s_][t].data_ptr(), n) for s_ in range(F)]
+    prepared = [ctx.batch_prepare([(dev[s_][t].data_ptr(), n) for s_ in range(F)]) for t in range(warm + ticks)]
+    args = lambda t: prepared[t]
     # (b) roofline of ground + CCL
     for t in range(warm):
         ctx.batch_ground_ccl_dev(args(t))

