@@ -276,3 +276,34 @@ def test_free_running_bench_scene_100_frames(pkg, ref_intended, synth):
               f"track-frames above 1e-4 (frame, track, error, drift of the reference's own restatement): {above}")
     finally:
         ctx.close()
+
+
+def test_track_table_full_is_a_warning_and_existing_tracks_keep_going(pkg, ref_intended, synth):
+    """the table is append-only like the reference's targets_; when max_tracks is reached the step must still update
+    and report every existing track (status LMOT_WARN_TRACK_TABLE_FULL = +1), only the spawning of new tracks stops."""
+    ref = ref_intended
+    seq = _boxes_sequence(ref, synth, seed=21, n_frames=9, n_objects=60)
+    p = pkg.default_params()
+    p.max_tracks = 48
+    ctx = pkg.Lmot(p)
+    try:
+        ref.tracker_reset()
+        warned = 0
+        for f, (ts, boxes) in enumerate(seq):
+            a = ref.tracker_step(boxes, ts)
+            b = ctx.track_step(boxes, ts, cap=48)
+            n = len(b["track_manage"])
+            assert n <= 48
+            if len(a["track_manage"]) > 48:
+                assert ctx.last_warning == pkg.WARN_TRACK_TABLE_FULL and n == 48, f
+                warned += 1
+                if warned <= 3:      # new tracks have larger indices: for a few frames they cannot influence the first 48
+                    assert np.array_equal(a["track_manage"][:48], b["track_manage"]), f
+                    np.testing.assert_allclose(b["targets"], a["targets"][:48], rtol=1e-4, atol=1e-4)
+            else:
+                assert ctx.last_warning == 0 and np.array_equal(a["track_manage"], b["track_manage"]), f
+        assert warned >= 2
+        g = pkg.Params()
+        assert ctx.lib.lmot_get_params(ctx.h, __import__("ctypes").byref(g)) == 0 and g.max_tracks == 48
+    finally:
+        ctx.close()
