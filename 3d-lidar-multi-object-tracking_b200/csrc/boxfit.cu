@@ -29,7 +29,7 @@ namespace lmot {
 namespace {
 
 constexpr int kTile = 1024;
-constexpr int kFitThreads = 256;
+constexpr int kFitThreads = 512;      // one CTA per cluster: the largest cluster IS the kernel (16 us of point pass at 256 threads)
 constexpr int kCols = 1800;        // pixel columns a cluster can span: offsetX-450 = picX-initPicX in [-899,899]
 constexpr int kColShift = 899 - 450;
 constexpr int kHullCap = 2048;
@@ -106,12 +106,12 @@ __device__ __forceinline__ void seg_offsets_body(const FitFrame& F, int max_clus
     const int k = k0 + threadIdx.x;
     int total = 0;
     if (k <= K) {
-      for (int t0 = 0; t0 < n_tiles; t0 += 8) {        // 8 independent loads in flight, then the dependent prefix
-        int v[8];
+      for (int t0 = 0; t0 < n_tiles; t0 += 16) {       // 16 independent loads in flight, then the dependent prefix
+        int v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = (t0 + u < n_tiles) ? table[(size_t)(t0 + u) * stride + k] : 0;
+        for (int u = 0; u < 16; ++u) v[u] = (t0 + u < n_tiles) ? table[(size_t)(t0 + u) * stride + k] : 0;
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < 16; ++u)
           if (t0 + u < n_tiles) { table[(size_t)(t0 + u) * stride + k] = total; total += v[u]; }
       }
     }
@@ -241,7 +241,7 @@ __device__ __forceinline__ void fit_mark(unsigned long long* clk, int slot) {
   if (clk && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); const unsigned row = blockIdx.y * gridDim.x + blockIdx.x; if (row < (unsigned)kFitClockCtas) clk[row * 8 + slot] = t; }
 }
 
-__global__ void __launch_bounds__(kFitThreads, 4)     // <= 64 registers: four CTAs (clusters) per SM instead of three
+__global__ void __launch_bounds__(kFitThreads, 2)     // <= 64 registers: two 512-thread CTAs (clusters) per SM
 box_fit_kernel(const __grid_constant__ FitBatch B, const __grid_constant__ BoxParams P,
                const unsigned long long* __restrict__ mt_raw, int n_raw, int max_clusters, int max_boxes,
                unsigned long long* __restrict__ clk) {

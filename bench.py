@@ -50,11 +50,12 @@ SCENE = dict(n_objects=150, lattice_pitch=3.8, ped_fraction=0.65, seed=1)   # ~6
 KERNEL_NAMES = ("ground_fused+ccl", "tile_hist+seg_offsets", "scatter", "box_fit",
                 "imm_predict_gate", "imm_update", "spawn_output")        # clustering runs in the ground kernel's last CTA (LMOT_FUSE_CCL=0: own launch)
 KERNEL_NAMES_UNFUSED = ("ground_fused", "ccl_cluster") + KERNEL_NAMES[1:]
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE ground_fused_kernel launch at the bench workload, from the committed
-# `ncu --set full` capture profiles/r1z_ncu_full_ground.csv (2.03 MB read: the frame once, plus the polar grid; 0 bytes
-# written: the 3.9 MB of output clouds stay in the 126 MB L2 within the measured launch)
-TRAFFIC_NCU = 2.03e6
-TRAFFIC_SOURCE = "constant: ncu --set full capture of round 1 (profiles/r1z_ncu_full_ground.csv), not measured by this run"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE ground_fused_kernel launch at the bench workload (pipeline geometry, 74 CTAs,
+# clustering fused into its tail), from the committed `ncu --set full` capture profiles/r2g_ncu_full_ground_pipeline.csv (2.07 MB read:
+# the frame once, plus the polar grid and the bit planes; 0 bytes written: the 3.9 MB of output clouds stay in the 126 MB L2 within
+# the measured launch)
+TRAFFIC_NCU = 2.07e6
+TRAFFIC_SOURCE = "constant from the committed ncu --set full capture profiles/r2g_ncu_full_ground_pipeline.csv (dram__bytes_read.sum + dram__bytes_write.sum of one launch), not measured by this run"
 KERNELS_PER_FRAME = len(KERNEL_NAMES) + 2   # ground + clustering 1 (one launch) + box 3 + tracker 3, + the tracker's gate kernel + publish_kernel
 
 
