@@ -186,7 +186,9 @@ tracker_gate_kernel(const int* __restrict__ det_sem, unsigned long long* __restr
   }
   __syncwarp();
   pdl_launch_dependents();
-  pdl_wait();
+  // (no griddepcontrol.wait: this kernel may finish before the previous frame's spawn_output_kernel does.  TA's CTAs, resident from
+  // here on, wait for that step through its completion counter -- one L2 poll after spawn_output_kernel's last store instead of two
+  // grid-completion hops (TC -> this kernel -> TA), which were most of the 5.2 us between TC's end and the next TA's start.)
   if (phase && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); phase[27] = t; }
 }
 
@@ -213,11 +215,22 @@ __global__ void __launch_bounds__(kTAThreads, 4)     // <= 128 registers: a CTA 
 imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, const int* __restrict__ det, const float* __restrict__ boxes,
                         double dt, unsigned* __restrict__ gate, unsigned* __restrict__ setter, int* __restrict__ first_setter,
                         uint8_t* __restrict__ skip, int words, const int* __restrict__ act_list, unsigned long long* trace,
-                        unsigned long long* __restrict__ phase, int* __restrict__ meas_n, double2* __restrict__ meas_ctr) {
+                        unsigned long long* __restrict__ phase, int* __restrict__ meas_n, double2* __restrict__ meas_ctr,
+                        const unsigned* __restrict__ tc_seq, unsigned tc_want, unsigned spin_limit) {
   __shared__ TAShared sh;
   if (phase && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); phase[28] = t; }
-  pdl_wait();                              // (gated launch: the gate kernel, hence the previous tracker step and this frame's detection, is complete)
+  pdl_wait();                              // (gated launch: the gate kernel, hence this frame's detection, is complete)
   pdl_launch_dependents();                 // TB's CTAs may line up behind this grid
+  // the previous tracker step: spawn_output_kernel counts itself complete (release) after its last store.  It is ONE resident CTA
+  // that needs nothing more to finish, so spinning here cannot starve it (unlike a wait for detection, see tracker_gate_kernel).
+  if (threadIdx.x == 0) {
+    unsigned spin = 0, v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(tc_seq) : "memory");
+      if (spin_limit && ++spin > spin_limit) __trap();
+    } while ((int)(v - tc_want) < 0);
+  }
+  __syncthreads();
   trace_start(trace, 0);
   struct TraceEnd { unsigned long long* t; __device__ ~TraceEnd() { __syncthreads(); trace_end(t, 0); } } trace_at_exit{trace};
   const int tid = threadIdx.x, lane = tid & 31, model = tid >> 5;
@@ -1863,7 +1876,7 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
       ac.gridDim = dim3(c->trk_ctas); ac.blockDim = dim3(kTAThreads); ac.dynamicSmemBytes = 0; ac.stream = st; ac.attrs = &pa; ac.numAttrs = 1;
       LMOT_CUDA(c, cudaLaunchKernelEx(&ac, imm_predict_gate_kernel, c->d_tracks, (const int*)c->d_trk_counters, (const int*)det, d_boxes, dt,
                                       c->d_gate, c->d_setter, c->d_first_setter, c->d_skip, c->gate_words, (const int*)c->d_act_list, trace, phase,
-                                      c->d_meas_n, reinterpret_cast<double2*>(c->d_meas_ctr)));
+                                      c->d_meas_n, reinterpret_cast<double2*>(c->d_meas_ctr), (const unsigned*)c->d_tc_seq, c->tc_launched, c->spin_limit));
     }
     kernel_mark(c, sl, st);
     // TB and TC: programmatic dependent launches (their CTAs wait on the device for the preceding grid, see pdl_wait); timing

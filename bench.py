@@ -522,6 +522,7 @@ def main():
     ap.add_argument("--tracker-stress", type=int, default=40, help="timed steps of the 1024x256 tracker-only workload (0 = skip; rank 0, N=1)")
     ap.add_argument("--dense-frames", type=int, default=10, help="1M-point frames for the dense roofline measurement (0 = skip)")
     ap.add_argument("--batch-ticks", type=int, default=12, help="ticks of the batched 8 x 120 k configuration (0 = skip; rank 0)")
+    ap.add_argument("--pipeline-depth", type=int, default=0, help="frames in flight inside the context (0 = the library default, 8)")
     ap.add_argument("--shared-ticks", type=int, default=8, help="N>1: ticks of the shared-track-table block (both modes) appended to the default line (0 = skip)")
     ap.add_argument("--shared-tracker", choices=["off", "streams", "frames"], default="off",
                     help="N>1 only: all ranks feed ONE track table (NCCL all_gather of boxes, tracker on rank 0, NCCL broadcast of the "
@@ -558,7 +559,10 @@ def main():
     torch.cuda.synchronize()
     ring_mb = d_frames.numel() * 4 / 2**20
 
-    ctx = lmot.Lmot(device=local_rank)
+    prm = lmot.default_params()
+    if args.pipeline_depth > 0:
+        prm.pipeline_depth = args.pipeline_depth
+    ctx = lmot.Lmot(prm, device=local_rank)
     # a REAL stream: torch's default stream has handle 0, which lmot_set_stream reads as "use the context's own stream" --
     # CUDA events recorded on stream 0 would then not be ordered with the pipeline at all
     stream = torch.cuda.Stream(device=local_rank)
