@@ -29,10 +29,19 @@ namespace lmot {
 namespace {
 
 constexpr int kTile = 1024;
-constexpr int kFitThreads = 512;      // one CTA per cluster: the largest cluster IS the kernel (16 us of point pass at 256 threads)
+constexpr int kFitThreadsFrame = 512;   // one CTA per cluster: the largest cluster IS the kernel of a single frame (16 us of point pass at 256 threads)
+constexpr int kFitThreadsBatch = 256;   // batched ticks hold ~8x the clusters: more, smaller CTAs per SM finish the union sooner (51 us at 512, 45 at 256)
 constexpr int kCols = 1800;        // pixel columns a cluster can span: offsetX-450 = picX-initPicX in [-899,899]
 constexpr int kColShift = 899 - 450;
 constexpr int kHullCap = 2048;
+
+// Programmatic dependent launch inside a slot's detection stream: scatter behind tile_hist, box_fit behind scatter.  The dependent's
+// CTAs become resident once EVERY CTA of the kernel before it has started (they all trigger at their first instruction) and wait there
+// for it to finish -- its launch latency leaves the frame's critical path.  Deadlock-free next to the ground kernel's own barrier: a
+// waiting CTA only ever waits for a grid that is completely resident and waits for nobody.  (Not used in front of tile_hist: its CTAs
+// would hold SM slots for the ~12 us of the ground kernel, slots the tracker chain needs.)
+__device__ __forceinline__ void fit_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void fit_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------- B1
 // One frame of a launch (blockIdx.y): every buffer the four kernels touch for it (the Slot's, see lmot_internal.cuh)
@@ -51,6 +60,7 @@ __device__ __forceinline__ void seg_offsets_body(const FitFrame& F, int max_clus
 __global__ void __launch_bounds__(kTile)
 tile_hist_kernel(const __grid_constant__ FitBatch B, int max_clusters) {
   extern __shared__ int s_hist[];
+  fit_pdl_trigger();
   const FitFrame& F = B.f[blockIdx.y];
   const uint16_t* __restrict__ cart = F.cart; const int* __restrict__ label_grid = F.label_grid; const int* __restrict__ counters = F.counters;
   uint16_t* __restrict__ pcid = F.pcid; int* __restrict__ table = F.table;
@@ -146,6 +156,8 @@ seg_offsets_kernel(const __grid_constant__ FitBatch B, int max_clusters) { seg_o
 __global__ void __launch_bounds__(kTile)
 scatter_kernel(const __grid_constant__ FitBatch B, int max_clusters) {
   extern __shared__ int s_cur[];
+  fit_pdl_trigger();
+  fit_pdl_wait();                          // tile_hist_kernel (+ the segment offsets of its last CTA) is complete
   const FitFrame& F = B.f[blockIdx.y];
   const uint16_t* __restrict__ pcid = F.pcid; const float4* __restrict__ elev = F.elev; const int* __restrict__ counters = F.counters;
   const int* __restrict__ table = F.table; const int* __restrict__ seg_start = F.seg_start; float4* __restrict__ sorted_pts = F.sorted_pts;
@@ -199,7 +211,7 @@ __device__ __forceinline__ T block_reduce(T v, Op op, T* s_buf) {
   if (lane == 0) s_buf[warp] = v;
   __syncthreads();
   T r = s_buf[0];
-  for (int w = 1; w < kFitThreads / 32; ++w) r = op(r, s_buf[w]);
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = op(r, s_buf[w]);
   return r;
 }
 
@@ -241,10 +253,14 @@ __device__ __forceinline__ void fit_mark(unsigned long long* clk, int slot) {
   if (clk && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); const unsigned row = blockIdx.y * gridDim.x + blockIdx.x; if (row < (unsigned)kFitClockCtas) clk[row * 8 + slot] = t; }
 }
 
-__global__ void __launch_bounds__(kFitThreads, 2)     // <= 64 registers: two 512-thread CTAs (clusters) per SM
+template <int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT)     // <= 64 registers: 1,024 threads of box fitting per SM
 box_fit_kernel(const __grid_constant__ FitBatch B, const __grid_constant__ BoxParams P,
                const unsigned long long* __restrict__ mt_raw, int n_raw, int max_clusters, int max_boxes,
                unsigned long long* __restrict__ clk) {
+  constexpr int kFitThreads = NT;
+  fit_pdl_trigger();
+  fit_pdl_wait();                          // scatter_kernel is complete
   const FitFrame& F = B.f[blockIdx.y];
   const float4* __restrict__ sorted_pts = F.sorted_pts; const int* __restrict__ seg_start = F.seg_start; const int* __restrict__ seg_size = F.seg_size;
   int* __restrict__ counters = F.counters;
@@ -794,7 +810,18 @@ int boxfit_launch_batch(Ctx* c, Slot* const* slots, int F, cudaStream_t st, cons
   if (tiles > 0) tile_hist_kernel<<<dim3(tiles, F), kTile, sh, st>>>(B, c->prm.max_clusters);     // + segment offsets by its last CTA per frame
   else seg_offsets_kernel<<<F, 1024, 0, st>>>(B, c->prm.max_clusters);
   kernel_mark(c, s0, st);
-  if (tiles > 0) { scatter_kernel<<<dim3(tiles, F), kTile, sh, st>>>(B, c->prm.max_clusters); kernel_mark(c, s0, st); }
+  // scatter and box_fit as programmatic dependents of the kernel before them (timing mode records an event between the kernels,
+  // which needs the ordinary full serialisation)
+  cudaLaunchAttribute pdl;
+  pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl.val.programmaticStreamSerializationAllowed = c->timing ? 0 : 1;
+  const int max_clusters = c->prm.max_clusters;
+  if (tiles > 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(tiles, F); cfg.blockDim = dim3(kTile); cfg.dynamicSmemBytes = sh; cfg.stream = st; cfg.attrs = &pdl; cfg.numAttrs = 1;
+    LMOT_CUDA(c, cudaLaunchKernelEx(&cfg, scatter_kernel, B, max_clusters));
+    kernel_mark(c, s0, st);
+  }
   BoxParams P;
   const lmot_params& p = c->prm;
   P.roi = p.roi_m;
@@ -806,7 +833,15 @@ int boxfit_launch_batch(Ctx* c, Slot* const* slots, int F, cudaStream_t st, cons
   P.t_ratio_max = p.t_ratio_max; P.min_len_ratio = p.min_len_ratio; P.t_pt_per_m3 = p.t_pt_per_m3;
   // one CTA per cluster: a frame rarely holds more than a few hundred clusters, F frames share the grid
   const int gx = F == 1 ? c->fit_ctas : (c->fit_ctas / 2 > 8 ? c->fit_ctas / 2 : 8);
-  box_fit_kernel<<<dim3(gx, F), kFitThreads, 0, st>>>(B, P, c->d_mt_raw, c->n_mt_raw, c->prm.max_clusters, c->prm.max_boxes, c->d_fit_clock);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, F); cfg.blockDim = dim3(F == 1 ? kFitThreadsFrame : kFitThreadsBatch); cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = &pdl; cfg.numAttrs = 1;
+    const unsigned long long* mt = c->d_mt_raw;
+    const int n_raw = c->n_mt_raw, max_boxes = c->prm.max_boxes;
+    unsigned long long* clk = c->d_fit_clock;
+    if (F == 1) LMOT_CUDA(c, cudaLaunchKernelEx(&cfg, box_fit_kernel<kFitThreadsFrame>, B, P, mt, n_raw, max_clusters, max_boxes, clk));
+    else LMOT_CUDA(c, cudaLaunchKernelEx(&cfg, box_fit_kernel<kFitThreadsBatch>, B, P, mt, n_raw, max_clusters, max_boxes, clk));
+  }
   c->last_fit_ctas = gx * F;
   kernel_mark(c, s0, st);
   LMOT_CUDA(c, cudaGetLastError());
