@@ -512,6 +512,7 @@ void lmot_destroy(lmot_ctx* ctx) {
   Ctx* c = &ctx->c;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  ground_chain_forget(c->device, true);
   for (int i = 0; i < c->n_slots; ++i) slot_destroy(&c->slots[i]);
   batch_destroy(c);
   for (int i = 0; i < c->n_results; ++i) result_destroy(&c->results[i]);
@@ -534,6 +535,8 @@ void lmot_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 int lmot_set_stream(lmot_ctx* ctx, void* s) {
   if (!ctx) return LMOT_ERR_INVALID;
+  cudaSetDevice(ctx->c.device);
+  ground_chain_forget(ctx->c.device, false);       // (the stream being replaced must still be valid, lmot.h)
   ctx->c.stream = s ? (cudaStream_t)s : ctx->c.own_stream;
   return LMOT_OK;
 }
@@ -575,7 +578,7 @@ int lmot_ground_remove_dev(lmot_ctx* ctx, const float* d_points, int n) {
   Slot* s = &c->slots[0];
   c->last_slot = 0;
   // (no label array, no debug grid: what the frame pipeline launches, minus the clustering bit planes)
-  return ground_launch(c, s, c->stream, reinterpret_cast<const float4*>(d_points), n, false, false);
+  return ground_launch(c, s, c->stream, reinterpret_cast<const float4*>(d_points), n, false, false, false, true);
 }
 
 int lmot_ground_remove(lmot_ctx* ctx, const float* points, int n, int stride, uint8_t* labels, float* elevated,
@@ -901,7 +904,7 @@ int lmot_batch_ground_ccl_dev(lmot_ctx* ctx, const float* const* d_points, const
   }
   sl[0]->res = &c->results[0];
   c->results[0].n_kev = 0;
-  if ((rc = ground_launch_batch(c, sl, n_frames, pp, n, c->stream, true, false, c->fuse_ccl))) return rc;
+  if ((rc = ground_launch_batch(c, sl, n_frames, pp, n, c->stream, true, false, c->fuse_ccl, c->fuse_ccl))) return rc;
   return c->fuse_ccl ? LMOT_OK : ccl_launch_batch(c, sl, n_frames, c->stream);
 }
 

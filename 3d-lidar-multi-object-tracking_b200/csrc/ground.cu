@@ -32,8 +32,16 @@ namespace lmot {
 
 namespace {
 
-std::mutex g_ground_mutex;                 // one ground kernel in flight per device (see ground_launch)
-cudaEvent_t g_ground_done[64] = {};
+std::mutex g_ground_mutex;                 // one ground kernel in flight per device (see ground_launch_batch)
+// the chain of ground kernels of a device: every launch waits for the previous one.  On the same stream that is stream order; on
+// another stream it is `done`, recorded right behind the launch -- or, for the stand-alone entry points (`chain`), only when a
+// launch on another stream needs it: kernel / event record / kernel costs ~2 us more per launch than kernel / kernel.
+struct GroundChain {
+  cudaEvent_t done = nullptr;
+  cudaStream_t last = nullptr;
+  bool have_last = false, recorded = false, record_pending = false;
+};
+GroundChain g_chain[64];
 
 __device__ __forceinline__ unsigned fkey(float f) {
   const unsigned u = __float_as_uint(f);
@@ -278,9 +286,12 @@ __device__ __forceinline__ void phase_mark(unsigned long long* clk, int slot) {
   }
 }
 
-__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, unsigned spin_limit) {
@@ -288,10 +299,11 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, uns
   if (threadIdx.x == 0) {
     // release: the CTA's writes (ordered before this thread by the barrier above) become visible before the arrival
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+    // acquire on the polling load itself: the load that sees the last arrival synchronises with every arrival before it (they
+    // are read-modify-writes on one word: one release sequence) -- no separate fence on the way out
     unsigned spin = 0;
-    while ((int)(ld_relaxed_u32(bar) - target) < 0)
+    while ((int)(ld_acquire_u32(bar) - target) < 0)
       if (spin_limit && ++spin > spin_limit) __trap();   // a lost CTA must not hang the GPU (0 = wait for ever: debuggers, MPS)
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire: the other CTAs' writes are visible to this CTA from here on
   }
   __syncthreads();
 }
@@ -307,7 +319,7 @@ constexpr unsigned kPending = 0xFFFDu;              // cell id of a queued point
 constexpr int kKeysPerThread = (kPolarCells + kFusedThreads - 1) / kFusedThreads;   // 10: cells of the CTA's key grid per thread
 // dynamic shared memory layout (bytes): fixed part (incl. the CTA's private min-z key grid), then the resident tiles, then the cell
 // ids of every tile of the chunk.
-constexpr int kOffBar = 0;                                                  // [7] mbarriers
+constexpr int kOffBar = 0;                                                  // [7] mbarriers of the tiles + [1] of the label limits
 constexpr int kOffMeta = 64;                                                // [3] pending points
 constexpr int kOffCnt = 128;                                                // [16][32] u32 elevated | ground << 16 per warp
 constexpr int kOffWex = kOffCnt + kMaxTiles * 32 * 4;                       // [16][32] u32 exclusive inside the tile
@@ -385,6 +397,89 @@ __device__ __forceinline__ unsigned polar_cell_fast(float x, float y, const Grou
   return (unsigned)((int)cf * kNumBin + (int)tf);
 }
 
+__device__ __forceinline__ void smem_min_u32(uint32_t addr, unsigned v) {
+  asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// Two tiles of phase 1 (see the kernel).  FULL: both tiles exist, are resident in shared memory and hold kTilePts points each;
+// PRE: the node's pre-filters are on.
+template <bool FULL, bool PRE>
+__device__ __forceinline__ void bin_pair(int t0, int T, int cnt, int res_tiles, int beg, const float4* __restrict__ pts, const float4* s_pts,
+                                         uint16_t* s_cell, uint64_t* s_full, unsigned* s_meta, uint16_t* s_pend, uint32_t keys_sa,
+                                         const GroundParams& p) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  float4 q[2];
+  bool valid[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int t = t0 + u;
+    const int li = t * kTilePts + tid;
+    if (FULL) {
+      valid[u] = true;
+      mbar_wait(&s_full[t], 0u);
+      q[u] = s_pts[li];
+    } else {
+      valid[u] = t < T && li < cnt;
+      q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < T) {
+        if (t < res_tiles) {
+          mbar_wait(&s_full[t], 0u);
+          if (valid[u]) q[u] = s_pts[li];
+        } else if (valid[u]) q[u] = __ldg(&pts[beg + li]);
+      }
+    }
+  }
+  unsigned c[2], key[2];
+  bool pre[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    c[u] = kNoCell;
+    key[u] = 0xFFFFFFFFu;
+    pre[u] = false;                              // removed by the node's pre-filters (src/groundremove/main.cpp:104-112)
+    if (PRE && valid[u])
+      pre[u] = !(isfinite(q[u].x) && isfinite(q[u].y) && isfinite(q[u].z) && q[u].z >= p.fz0 && q[u].z <= p.fz1 &&   // PassThrough: inclusive
+                 q[u].x > p.fx0 && q[u].x < p.fx1 && q[u].y > p.fy0 && q[u].y < p.fy1);                               // ConditionalRemoval: strict
+    if (valid[u] && !pre[u]) {
+      c[u] = polar_cell_fast(q[u].x, q[u].y, p);
+      float z = q[u].z;
+      if (z == 0.f) z = 0.f;                     // -0 -> +0 (`z < minZ` does not order them either)
+      if (z == z) key[u] = fkey(z);              // NaN z never wins `z < minZ` (ground_removal.cpp:41)
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int t = t0 + u;
+    if (!FULL && t >= T) break;                  // (CTA-uniform)
+    const int li = t * kTilePts + tid;
+    unsigned cc = c[u];
+    // the ~1.6 per mille of points that need the exact evaluation are queued and evaluated by full warps after the loop
+    // (inline, their ~170 instructions ran with one or two active lanes and stalled the other 30)
+    const unsigned pm = __ballot_sync(0xFFFFFFFFu, cc == kPending);
+    if (pm) {
+      unsigned base = 0;
+      if (lane == __ffs(pm) - 1) base = atomicAdd(&s_meta[3], (unsigned)__popc(pm));
+      base = __shfl_sync(0xFFFFFFFFu, base, __ffs(pm) - 1);
+      if (cc == kPending) {
+        const unsigned slot = base + __popc(pm & ((1u << lane) - 1u));
+        if (slot < (unsigned)kPendCap) s_pend[slot] = (uint16_t)li;
+        else cc = polar_cell_exact(q[u].x, q[u].y, p);       // queue full (adversarial clouds): evaluate here
+      }
+    }
+    s_cell[li] = (PRE && pre[u]) ? kPreFiltered : (uint16_t)cc;
+    if (cc >= (unsigned)kPolarCells) cc = kNoCell;           // pending: contributes later
+    const unsigned k = (cc == kNoCell) ? 0xFFFFFFFFu : key[u];
+    // min z per cell into the CTA's OWN key grid in shared memory (flushed to the frame's grid once, below).  Consecutive HDL-64
+    // returns fall into the same cell: a warp that holds a single cell reduces over its lanes and issues one atomic; any other
+    // warp lets the shared-memory atomic unit sort it out (one instruction; the match / group-reduce / leader code this
+    // replaces was ~40 instructions on ~40 % of the warps of a dense frame)
+    const unsigned c0 = __shfl_sync(0xFFFFFFFFu, cc, 0);
+    if (__all_sync(0xFFFFFFFFu, cc == c0)) {
+      const unsigned kmin = __reduce_min_sync(0xFFFFFFFFu, k);
+      if (lane == 0 && kmin != 0xFFFFFFFFu) smem_min_u32(keys_sa + c0 * 4u, kmin);
+    } else if (k != 0xFFFFFFFFu) smem_min_u32(keys_sa + cc * 4u, k);
+  }
+}
+
 // ONE launch per frame -- or per batch of frames (one per sensor stream), CTA groups own frames and synchronise among themselves.
 // (Round 2 also tried "no second barrier": every CTA evaluating the polar grid for the channels its own points fall into, in shared
 // memory.  With ring-major clouds a chunk spans most of the 80 channels, so 148 CTAs each redid ~90 % of the grid: 7 M of the
@@ -424,87 +519,37 @@ ground_fused_kernel(const __grid_constant__ GroundBatch B, const __grid_constant
 
   phase_mark(phase_clock, 0);
   // ---- phase 0: arm the TMA copies of the resident tiles; re-arm the OTHER key grid for the slot's next frame
+  // (a launch chained behind the previous ground kernel of its stream -- ground_launch_batch, `chain` -- becomes resident while that
+  // kernel drains: everything up to griddep_wait() touches shared memory only; the wait returns when the preceding grid has
+  // completed and its writes are visible.  An ordinary launch passes through both instructions.)
+  griddep_launch_dependents();
   if (tid == 0) {
-    for (int t = 0; t < kMaxResTiles; ++t) mbar_init(&s_full[t], 1);
+    for (int t = 0; t <= kMaxResTiles; ++t) mbar_init(&s_full[t], 1);      // [kMaxResTiles]: the label limits, phase 3
     fence_mbar_init();
+  }
+  if (tid < 8) s_meta[tid] = 0u;
+#pragma unroll
+  for (int j = 0; j < kKeysPerThread; ++j) { const int k = tid + j * kFusedThreads; if (k < kPolarCells) s_keys[k] = 0xFFFFFFFFu; }
+  griddep_wait();
+  if (tid == 0) {
     for (int t = 0; t < T && t < res_tiles; ++t) {
       const uint32_t bytes = (uint32_t)min(kTilePts, cnt - t * kTilePts) * 16u;
       mbar_arrive_expect_tx(&s_full[t], bytes);
       bulk_copy_g2s(s_pts + t * kTilePts, pts + beg + t * kTilePts, bytes, &s_full[t]);
     }
   }
-  if (tid < 8) s_meta[tid] = 0u;
-#pragma unroll
-  for (int j = 0; j < kKeysPerThread; ++j) { const int k = tid + j * kFusedThreads; if (k < kPolarCells) s_keys[k] = 0xFFFFFFFFu; }
   for (int k = cta * kFusedThreads + tid; k < kPolarCells; k += Gf * kFusedThreads) F.keys_next[k] = fkey(1000.f);  // Cell::Cell(): minZ = 1000
   __syncthreads();
 
-  // ---- phase 1: point -> polar cell, min z per cell.  Two tiles per iteration: two independent dependency chains per thread
-  for (int t0 = 0; t0 < T; t0 += 2) {
-    float4 q[2];
-    bool valid[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int t = t0 + u;
-      const int li = t * kTilePts + tid;
-      valid[u] = t < T && li < cnt;
-      q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t < T) {
-        if (t < res_tiles) {
-          mbar_wait(&s_full[t], 0u);
-          if (valid[u]) q[u] = s_pts[li];
-        } else if (valid[u]) q[u] = __ldg(&pts[beg + li]);
-      }
-    }
-    unsigned c[2], key[2];
-    bool pre[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      c[u] = kNoCell;
-      key[u] = 0xFFFFFFFFu;
-      pre[u] = false;                              // removed by the node's pre-filters (src/groundremove/main.cpp:104-112)
-      if (valid[u] && p.prefilter)
-        pre[u] = !(isfinite(q[u].x) && isfinite(q[u].y) && isfinite(q[u].z) && q[u].z >= p.fz0 && q[u].z <= p.fz1 &&   // PassThrough: inclusive
-                   q[u].x > p.fx0 && q[u].x < p.fx1 && q[u].y > p.fy0 && q[u].y < p.fy1);                               // ConditionalRemoval: strict
-      if (valid[u] && !pre[u]) {
-        c[u] = polar_cell_fast(q[u].x, q[u].y, p);
-        float z = q[u].z;
-        if (z == 0.f) z = 0.f;                     // -0 -> +0 (`z < minZ` does not order them either)
-        if (z == z) key[u] = fkey(z);              // NaN z never wins `z < minZ` (ground_removal.cpp:41)
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int t = t0 + u;
-      if (t >= T) break;                           // (CTA-uniform)
-      const int li = t * kTilePts + tid;
-      unsigned cc = c[u];
-      // the ~1.6 per mille of points that need the exact evaluation are queued and evaluated by full warps after the loop
-      // (inline, their ~170 instructions ran with one or two active lanes and stalled the other 30)
-      const unsigned pm = __ballot_sync(0xFFFFFFFFu, cc == kPending);
-      if (pm) {
-        unsigned base = 0;
-        if (lane == __ffs(pm) - 1) base = atomicAdd(&s_meta[3], (unsigned)__popc(pm));
-        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(pm) - 1);
-        if (cc == kPending) {
-          const unsigned slot = base + __popc(pm & ((1u << lane) - 1u));
-          if (slot < (unsigned)kPendCap) s_pend[slot] = (uint16_t)li;
-          else cc = polar_cell_exact(q[u].x, q[u].y, p);       // queue full (adversarial clouds): evaluate here
-        }
-      }
-      s_cell[li] = pre[u] ? kPreFiltered : (uint16_t)cc;
-      if (cc >= (unsigned)kPolarCells) cc = kNoCell;           // pending: contributes later
-      const unsigned k = (cc == kNoCell) ? 0xFFFFFFFFu : key[u];
-      // min z per cell into the CTA's OWN key grid in shared memory (flushed to the frame's grid once, below).  Consecutive HDL-64
-      // returns fall into the same cell: a warp that holds a single cell reduces over its lanes and issues one atomic; any other
-      // warp lets the shared-memory atomic unit sort it out (one instruction; the match / group-reduce / leader code this
-      // replaces was ~40 instructions on ~40 % of the warps of a dense frame)
-      const unsigned c0 = __shfl_sync(0xFFFFFFFFu, cc, 0);
-      if (__all_sync(0xFFFFFFFFu, cc == c0)) {
-        const unsigned kmin = __reduce_min_sync(0xFFFFFFFFu, k);
-        if (lane == 0 && kmin != 0xFFFFFFFFu) atomicMin(&s_keys[c0], kmin);
-      } else if (k != 0xFFFFFFFFu) atomicMin(&s_keys[cc], k);
-    }
+  // ---- phase 1: point -> polar cell, min z per cell.  Two tiles per iteration: two independent dependency chains per thread.
+  // Pairs of complete resident tiles (all of a chunk but its tail) run the variant without bounds / residency / pre-filter tests.
+  {
+    const uint32_t keys_sa = smem_u32(s_keys);
+    const int full_end = p.prefilter ? 0 : (min(cnt / kTilePts, res_tiles) & ~1);
+    int t0 = 0;
+    for (; t0 < full_end; t0 += 2) bin_pair<true, false>(t0, T, cnt, res_tiles, beg, pts, s_pts, s_cell, s_full, s_meta, s_pend, keys_sa, p);
+    if (p.prefilter) for (; t0 < T; t0 += 2) bin_pair<false, true>(t0, T, cnt, res_tiles, beg, pts, s_pts, s_cell, s_full, s_meta, s_pend, keys_sa, p);
+    else for (; t0 < T; t0 += 2) bin_pair<false, false>(t0, T, cnt, res_tiles, beg, pts, s_pts, s_cell, s_full, s_meta, s_pend, keys_sa, p);
   }
   __syncthreads();
   {
@@ -546,6 +591,35 @@ ground_fused_kernel(const __grid_constant__ GroundBatch B, const __grid_constant
 
   // ---- phase 3: labels (ground_removal.cpp:221-247), per-warp counts
   unsigned labs = 0;                                // 2 bits per tile: 0 dropped, 1 ground, 2 elevated
+  // Long chunks: the 38 KB of label limits come into shared memory with ONE bulk copy (over the key grid, which was flushed before
+  // barrier 1) -- a gather of scattered cells from L2 moves a 32-byte sector per point, 6,800 points per CTA of a 1 M point frame
+  // made that 2.3 us.  Short chunks (an HDL-64 frame over 74-148 CTAs) touch fewer sectors than the grid has: they gather.
+  const bool stage_lim = chunk > 2 * kTilePts;      // (frame-uniform)
+  if (stage_lim) {
+    if (tid == 0) {
+      asm volatile("fence.proxy.async;" ::: "memory");   // the limits were written through the generic proxy (other CTAs; acquired by the barrier); so was s_keys
+      mbar_arrive_expect_tx(&s_full[kMaxResTiles], (uint32_t)(kPolarCells * sizeof(float)));
+      bulk_copy_g2s(s_keys, F.lim, (uint32_t)(kPolarCells * sizeof(float)), &s_full[kMaxResTiles]);
+    }
+    const float* s_lim = reinterpret_cast<const float*>(s_keys);
+    mbar_wait(&s_full[kMaxResTiles], 0u);
+    for (int t = 0; t < T; ++t) {
+      const int li = t * kTilePts + tid;
+      int lab = 0;
+      if (li < cnt) {
+        const unsigned c = s_cell[li];
+        if (c == kNoCell) lab = p.prefilter ? 3 : 0;
+        else if (c != kPreFiltered) {
+          const float z = (t < res_tiles) ? s_pts[li].z : __ldg(&pts[beg + li]).z;
+          lab = (z <= s_lim[c]) ? 1 : 2;
+        }
+      }
+      labs |= (unsigned)lab << (2 * t);
+      const unsigned be = __ballot_sync(0xFFFFFFFFu, lab == 2);
+      const unsigned bg = __ballot_sync(0xFFFFFFFFu, lab == 1);
+      if (lane == 0) s_cnt[t * 32 + warp] = (unsigned)__popc(be) | ((unsigned)__popc(bg) << 16);
+    }
+  } else {
   // label limits of this thread's points in the resident tiles: all loads issued before the first is used (one L2 round trip for
   // the whole chunk instead of one per tile)
   float lv[kMaxResTiles];
@@ -576,6 +650,7 @@ ground_fused_kernel(const __grid_constant__ GroundBatch B, const __grid_constant
     const unsigned be = __ballot_sync(0xFFFFFFFFu, lab == 2);
     const unsigned bg = __ballot_sync(0xFFFFFFFFu, lab == 1);
     if (lane == 0) s_cnt[t * 32 + warp] = (unsigned)__popc(be) | ((unsigned)__popc(bg) << 16);
+  }
   }
   __syncthreads();
   phase_mark(phase_clock, 5);
@@ -776,7 +851,7 @@ bool ground_reads_input_once(const Ctx* c, int n) {
 // One launch for F frames (F = 1: the frame pipeline and the stage entry points; F > 1: one frame per sensor stream, api.cu
 // lmot_batch_*).  Frame i runs on slots[i]'s buffers; its CTAs are [i * G, (i + 1) * G) of the grid and synchronise among themselves.
 int ground_launch_batch(Ctx* c, Slot* const* slots, int F, const float4* const* pts, const int* n, cudaStream_t st, bool fuse_count,
-                        bool want_labels, bool fuse_ccl) {
+                        bool want_labels, bool fuse_ccl, bool chain) {
   if (fuse_ccl && !fuse_count) return LMOT_ERR_INVALID;
   if (F < 1 || F > kMaxBatch) return LMOT_ERR_INVALID;
   int n_max = 0;
@@ -844,22 +919,51 @@ int ground_launch_batch(Ctx* c, Slot* const* slots, int F, const float4* const* 
     // so no two partially resident grids can starve each other.  (Several PROCESSES sharing the GPU through MPS are outside
     // this guarantee; the barrier then traps after `spin_limit` polls instead of hanging -- LMOT_SPIN_LIMIT=0 waits for ever.)
     std::lock_guard<std::mutex> lk(g_ground_mutex);
-    cudaEvent_t& ev = g_ground_done[c->device & 63];
-    if (!ev) LMOT_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    else LMOT_CUDA(c, cudaStreamWaitEvent(st, ev, 0));
-    LMOT_CUDA(c, cudaLaunchKernel((const void*)ground_fused_kernel, dim3(G * F), dim3(kFusedThreads), args, smem, st));
-    LMOT_CUDA(c, cudaEventRecord(ev, st));
+    GroundChain& g = g_chain[c->device & 63];
+    if (!g.done) LMOT_CUDA(c, cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+    const bool same_stream = g.have_last && g.last == st;
+    if (!same_stream) {
+      if (g.record_pending) { LMOT_CUDA(c, cudaEventRecord(g.done, g.last)); g.record_pending = false; g.recorded = true; }
+      if (g.recorded) LMOT_CUDA(c, cudaStreamWaitEvent(st, g.done, 0));
+    }
+    // chained behind a ground kernel on the same stream: programmatic dependent launch -- this grid's CTAs become resident and set
+    // up their shared memory while the previous grid drains (its fused clustering tail included), see the kernel's griddep_wait()
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G * F); cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (chain && same_stream && g.record_pending && !c->timing) ? 1 : 0;
+    LMOT_CUDA(c, cudaLaunchKernelExC(&cfg, (const void*)ground_fused_kernel, args));
+    if (chain) g.record_pending = true;
+    else { LMOT_CUDA(c, cudaEventRecord(g.done, st)); g.record_pending = false; g.recorded = true; }
+    g.last = st; g.have_last = true;
   }
   c->last_ground_ctas = G * F;
   kernel_mark(c, slots[0], st);
   return LMOT_OK;
 }
 
-int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count, bool want_labels, bool fuse_ccl) {
+int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count, bool want_labels, bool fuse_ccl, bool chain) {
   Slot* sl[1] = {s};
   const float4* pp[1] = {pts};
   const int nn[1] = {n};
-  return ground_launch_batch(c, sl, 1, pp, nn, st, fuse_count, want_labels, fuse_ccl);
+  return ground_launch_batch(c, sl, 1, pp, nn, st, fuse_count, want_labels, fuse_ccl, chain);
+}
+
+// a stream is about to go away.  Caller's stream replaced (lmot_set_stream; the old one is still valid): record what a later launch
+// on another stream would have recorded on it.  Context destroyed after a device-wide synchronise (`device_idle`): nothing is left
+// to wait for, and the stream handle may already be stale -- just drop it.
+void ground_chain_forget(int device, bool device_idle) {
+  std::lock_guard<std::mutex> lk(g_ground_mutex);
+  GroundChain& g = g_chain[device & 63];
+  if (g.record_pending && g.done && !device_idle) {
+    if (cudaEventRecord(g.done, g.last) == cudaSuccess) g.recorded = true;
+    else cudaGetLastError();
+  }
+  g.record_pending = false;
+  g.have_last = false;
 }
 
 // all five polar grids of the slot's LAST ground launch, recomputed from its min-z keys (inspection only)

@@ -278,8 +278,11 @@ int ground_alloc(Ctx* c, Slot* s);
 void ground_free(Slot* s);
 // pts: device float4 array of n points; fuse_count: also bin the elevated points into the slot's cartesian count grid
 // want_labels: also write the per-point u8 label array (stage entry point); the frame pipeline skips it
-int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count = false, bool want_labels = true, bool fuse_ccl = false);
-int ground_launch_batch(Ctx* c, Slot* const* slots, int F, const float4* const* pts, const int* n, cudaStream_t st, bool fuse_count, bool want_labels, bool fuse_ccl = false);
+// `chain`: stand-alone entry points -- nothing of the library follows on `st` before the next ground launch; consecutive launches on
+// one stream then run as programmatic dependents without an event between them (ground.cu, GroundChain)
+int ground_launch(Ctx* c, Slot* s, cudaStream_t st, const float4* pts, int n, bool fuse_count = false, bool want_labels = true, bool fuse_ccl = false, bool chain = false);
+int ground_launch_batch(Ctx* c, Slot* const* slots, int F, const float4* const* pts, const int* n, cudaStream_t st, bool fuse_count, bool want_labels, bool fuse_ccl = false, bool chain = false);
+void ground_chain_forget(int device, bool device_idle);
 int ground_cells_debug(Ctx* c, Slot* s, cudaStream_t st);
 int ground_grids_debug(Ctx* c, Slot* s, cudaStream_t st);   // d_minz / d_height / d_smoothed / d_hdiff / d_hg_dbg from the last launch's keys
 bool ground_reads_input_once(const Ctx* c, int n);

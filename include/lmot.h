@@ -122,7 +122,9 @@ const char* lmot_build_info(void);
 /* Caller stream (cudaStream_t passed as void*): stage-by-stage entry points run on it, and the frame pipeline forks from /
  * joins into it (lmot_frame_dev orders a frame after the work already queued on it; lmot_flush makes it wait for the
  * pipeline).  NULL restores the context's own stream -- the legacy default stream (handle 0) cannot be selected, create a
- * stream instead (CUDA events recorded on stream 0 are not ordered with the pipeline's non-blocking streams). */
+ * stream instead (CUDA events recorded on stream 0 are not ordered with the pipeline's non-blocking streams).  The stream being
+ * replaced must still be valid at this call (the library may record an event on it), and a caller stream must be replaced
+ * (or the context destroyed) before that stream is destroyed. */
 int lmot_set_stream(lmot_ctx* ctx, void* cuda_stream);
 
 /* Page-locked host memory for frames handed to lmot_frame / lmot_frame_submit (a pageable buffer makes the H2D copy
