@@ -307,6 +307,7 @@ int collect_result(Ctx* c, Result* r, lmot_frame_out* out) {
   }
   const int err = r->h_hdr[HDR_ERROR];
   const int warn = r->has_tracks ? r->h_hdr[HDR_WARN] : 0;
+  if (r->has_tracks) c->last_n_act = r->h_hdr[HDR_N_ACT];
   if (out) {
     out->n_elevated = r->h_hdr[HDR_N_ELEV]; out->n_ground = r->h_hdr[HDR_N_GROUND];
     out->num_cluster = r->h_hdr[HDR_NUM_CLUSTER]; out->n_boxes = r->h_hdr[HDR_N_BOXES];
@@ -483,6 +484,7 @@ int lmot_create(lmot_ctx** out, const lmot_params* params, int device) {
   if (const char* e = getenv("LMOT_FUSE_CCL")) c->fuse_ccl = atoi(e) != 0;
   if (const char* e = getenv("LMOT_SPIN_LIMIT")) c->spin_limit = (unsigned)strtoul(e, nullptr, 0);   // 0: device-side waits never trap (debuggers, MPS)
   if (const char* e = getenv("LMOT_TRK_CTAS")) { const int v = atoi(e); if (v >= 8 && v <= 4096) c->trk_ctas = v; }     // tuning only
+  if (const char* e = getenv("LMOT_TC_WIDE")) c->tc_force = atoi(e) != 0 ? 1 : 0;      // tests: pin spawn_output_kernel's variant (default: by active-track count)
   if (const char* e = getenv("LMOT_FIT_CTAS")) { const int v = atoi(e); if (v >= 8 && v <= 4096) c->fit_ctas = v; }
   if (const char* e = getenv("LMOT_ZERO_COPY")) c->zero_copy = atoi(e) != 0;
   if (const char* e = getenv("LMOT_GROUND_HALF")) c->ground_half_sms = atoi(e) != 0;
@@ -724,6 +726,7 @@ int lmot_track_step(lmot_ctx* ctx, const float* boxes, int m, double timestamp_u
     for (int i = 0; i < s->res->n_kev; ++i) cudaEventElapsedTime(&c->kernel_ms[i], i == 0 ? s->res->ev[3] : s->res->kev[i - 1], s->res->kev[i]);
   }
   const int err = s->res->h_hdr[HDR_ERROR];
+  c->last_n_act = s->res->h_hdr[HDR_N_ACT];
   rc = copy_track_outputs(s->res, out);
   return err ? err : (rc ? rc : s->res->h_hdr[HDR_WARN]);
 }

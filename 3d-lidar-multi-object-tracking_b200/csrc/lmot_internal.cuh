@@ -162,7 +162,7 @@ struct Slot {
   struct Result* res = nullptr;        // result block of the frame currently (or last) processed on this slot
 };
 
-enum HostHdr { HDR_N_ELEV = 0, HDR_N_GROUND, HDR_NUM_CLUSTER, HDR_N_BOXES, HDR_N_TRACKS, HDR_N_VIS, HDR_ERROR, HDR_WARN, HDR_COUNT = 16 };
+enum HostHdr { HDR_N_ELEV = 0, HDR_N_GROUND, HDR_NUM_CLUSTER, HDR_N_BOXES, HDR_N_TRACKS, HDR_N_VIS, HDR_ERROR, HDR_WARN, HDR_N_ACT, HDR_COUNT = 16 };
 
 constexpr int kMaxSlots = 8;
 constexpr int kFitClockCtas = 4096;                  // rows of the box-fitting phase clock (diagnostic)
@@ -225,6 +225,9 @@ struct Ctx {
   Result* last_trk_res = nullptr;      // result block of the previous tracker step (its device copy seeds the next one)
   bool act_valid = false;              // false after the table was written from the host: rebuilt before the next step
   int trk_ctas = 592, gate_words = 0;
+  int last_n_act = 0;          // active tracks (live or visible) in the last result the host has read: picks spawn_output_kernel's variant
+  bool tc_wide = false;
+  int tc_force = -1;           // LMOT_TC_WIDE: -1 by count, 0 / 1 pinned
   TrackState* d_tracks = nullptr;      // [max_tracks] append-only table; dead tracks keep their slot
   int* d_trk_counters = nullptr;       // [CNT_COUNT] CNT_N_TRACKS / CNT_N_VIS / CNT_ERROR of the track table
   int* h_trk_counters = nullptr;       // pinned mirror

@@ -206,7 +206,7 @@ struct TAShared {
   double detS[3];        // per model: det(S), computed by the model's own warp
   int flag;              // 0 run, 1 skip (dead track)
   int explode;           // det(P_merge) > 10 or P_merge(4,4) > 1000 (:828-831), computed by warp 3 while warps 0-2 predict
-  unsigned gbits[8];     // gate bits of the (at most 8) 32-box chunks, for the compact measurement list handed to TB
+  unsigned gbits[16];    // gate bits of the (at most 16) 32-box chunks, for the compact measurement list handed to TB
 };
 
 __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
@@ -486,28 +486,30 @@ imm_predict_gate_kernel(TrackState* __restrict__ tracks, const int* __restrict__
         if (g) atomicMin(&first_setter[b], it);
         return bits;
       };
-      // Up to 256 boxes (8 chunks, two per warp) the centre points of the gated boxes are also handed to TB as a compact list
+      // Up to 512 boxes (16 chunks, four per warp) the centre points of the gated boxes are also handed to TB as a compact list
       // in box order (meas_ctr[it][0..31], count in meas_n[it]): TB's model warps then start their update straight away instead
       // of re-deriving the list from the gate words (two dependent L2 round trips) and gathering the boxes (a third)
-      const bool compact = nchunk <= 8;
-      double ccx[2] = {0, 0}, ccy[2] = {0, 0};
-      unsigned cb[2] = {0, 0};
-      bool cg[2] = {false, false};
+      constexpr int kCW = 4;
+      const bool compact = nchunk <= 4 * kCW;
+      double ccx[kCW], ccy[kCW];
+      unsigned cb[kCW];
+      bool cg[kCW];
 #pragma unroll
-      for (int ci = 0; ci < 2; ++ci) {
+      for (int ci = 0; ci < kCW; ++ci) {
         const int ch = model + 4 * ci;
+        ccx[ci] = 0; ccy[ci] = 0; cb[ci] = 0; cg[ci] = false;
         if (ch < nchunk) {
           cb[ci] = gate_chunk(ch, ccx[ci], ccy[ci], cg[ci]);
           if (compact && lane == 0) sh.gbits[ch] = cb[ci];
         }
       }
-      for (int ch = model + 8; ch < nchunk; ch += 4) { double cx, cy; bool g; gate_chunk(ch, cx, cy, g); }
+      for (int ch = model + 4 * kCW; ch < nchunk; ch += 4) { double cx, cy; bool g; gate_chunk(ch, cx, cy, g); }
       if (compact) {
         __syncthreads();                  // (uniform: every thread of the CTA is in this branch)
         int total = 0;
         for (int c2 = 0; c2 < nchunk; ++c2) total += __popc(sh.gbits[c2]);
 #pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
+        for (int ci = 0; ci < kCW; ++ci) {
           const int ch = model + 4 * ci;
           if (ch < nchunk && cg[ci]) {
             int off = __popc(cb[ci] & ((1u << lane) - 1u));
@@ -715,14 +717,14 @@ imm_update_kernel(TrackState* __restrict__ tracks, const int* __restrict__ trk, 
       const bool quick = warp < 3 && !secondInit && nm_ta >= 0 && nm_ta <= 32;   // model warps: everything they need came from TA
       if (quick) nmeas = nm_ta;
       else
-      for (int ch0 = 0; ch0 < nchunk; ch0 += 4) {      // four chunks per batch: two round trips (gate words, then first_setter), not two per chunk
-        unsigned g4[4]; int fs4[4];
+      for (int ch0 = 0; ch0 < nchunk; ch0 += 8) {      // eight chunks per batch: two round trips (gate words, then first_setter), not two per chunk
+        unsigned g4[8]; int fs4[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) g4[u] = (ch0 + u < nchunk) ? gate[(size_t)it * words + ch0 + u] : 0u;
+        for (int u = 0; u < 8; ++u) g4[u] = (ch0 + u < nchunk) ? gate[(size_t)it * words + ch0 + u] : 0u;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) fs4[u] = ((g4[u] >> lane) & 1u) ? first_setter[(ch0 + u) * 32 + lane] : INT_MAX;
+        for (int u = 0; u < 8; ++u) fs4[u] = ((g4[u] >> lane) & 1u) ? first_setter[(ch0 + u) * 32 + lane] : INT_MAX;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const unsigned g = g4[u];
           const int b = (ch0 + u) * 32 + lane;
           const bool cnt = ((g >> lane) & 1u) && (fs4[u] >= it);
@@ -1019,6 +1021,9 @@ __device__ __forceinline__ bool overseg_cond(const float* c, const float* ab, do
 
 constexpr int kTCThreads = 256;      // ONE small CTA: 16 K registers, so it starts on any SM next to the resident detection kernels
                                      // instead of waiting for a whole SM to drain (a 1024-thread CTA needs the full register file)
+constexpr int kTCWide = 512;         // the same kernel for scenes with 257..512 active tracks (multi-sensor ticks, dense traffic): the
+                                     // fast path holds one active track per thread (tracker_launch picks the variant from the last
+                                     // active-track count the host has seen; either variant is correct for any count)
 constexpr int kVisChunk = 128;       // visible boxes staged in shared memory per pass
 constexpr int kCandCap = 1024;       // (box, track) pairs that pass the bounds pre-test, per pass (more: tested inline)
 
@@ -1077,27 +1082,27 @@ __device__ __forceinline__ int emit_track(TrackState& t, int i, double ego_yaw, 
 // dst[0..n) = src[0..n) by the whole CTA, U loads in flight per thread before the first store.  (A plain
 // `for (...) dst[e] = src[e]` over pointers the compiler cannot prove distinct is a chain of load -> store -> load round
 // trips; on the one CTA of the tracker's sequential chain every one of them is ~1 us.)
-template <typename T, int U>
+template <int NT, typename T, int U>
 __device__ __forceinline__ void cta_copy(T* dst, const T* src, int n) {
-  for (int base = 0; base < n; base += kTCThreads * U) {
+  for (int base = 0; base < n; base += NT * U) {
     T v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) { const int e = base + u * kTCThreads + (int)threadIdx.x; if (e < n) v[u] = src[e]; }
+    for (int u = 0; u < U; ++u) { const int e = base + u * NT + (int)threadIdx.x; if (e < n) v[u] = src[e]; }
 #pragma unroll
-    for (int u = 0; u < U; ++u) { const int e = base + u * kTCThreads + (int)threadIdx.x; if (e < n) dst[e] = v[u]; }
+    for (int u = 0; u < U; ++u) { const int e = base + u * NT + (int)threadIdx.x; if (e < n) dst[e] = v[u]; }
   }
 }
 
-// the two halves of cta_copy for the first U * kTCThreads items, so that the loads of SEVERAL arrays can be in flight together
-template <typename T, int U>
+// the two halves of cta_copy for the first U * NT items, so that the loads of SEVERAL arrays can be in flight together
+template <int NT, typename T, int U>
 __device__ __forceinline__ void cta_load(T (&v)[U], const T* src, int n) {
 #pragma unroll
-  for (int u = 0; u < U; ++u) { const int e = u * kTCThreads + (int)threadIdx.x; if (e < n) v[u] = src[e]; }
+  for (int u = 0; u < U; ++u) { const int e = u * NT + (int)threadIdx.x; if (e < n) v[u] = src[e]; }
 }
-template <typename T, int U>
+template <int NT, typename T, int U>
 __device__ __forceinline__ void cta_store(T* dst, const T (&v)[U], int n) {
 #pragma unroll
-  for (int u = 0; u < U; ++u) { const int e = u * kTCThreads + (int)threadIdx.x; if (e < n) dst[e] = v[u]; }
+  for (int u = 0; u < U; ++u) { const int e = u * NT + (int)threadIdx.x; if (e < n) dst[e] = v[u]; }
 }
 
 // per-track outputs (:995-1041) + static flag (:1045-1081) from values instead of the record (the fast path of TC holds an
@@ -1123,36 +1128,38 @@ __device__ __forceinline__ int emit_values(int i, double tx, double ty, double y
   return st;
 }
 
-constexpr int kFastVis = kTCThreads;  // the fast path holds every active track in one thread: at most that many visible boxes
 
-// TC, fast path: at most kTCThreads active tracks (thread q <-> entry q of the active list).  Everything the merge / spawn /
+// TC, fast path: at most NT active tracks (thread q <-> entry q of the active list).  Everything the merge / spawn /
 // output logic needs of an active track arrives in ONE coalesced load of TB's 128-byte summaries and stays in registers and
 // shared memory; the 1.6 KB records are only written (trackNum / isStatic / distFromInit changes, new tracks), never waited
 // for, except the 96-byte box of a visible track, whose load is in flight during the merge.  Same results as the general
 // path below, statement for statement; see there for why mergeOverSegmentation reduces to imax / has5.
+template <int NT>
 struct TCFastShared {
   int w[33];
   int ncand, ncont, carry;
-  int imax[kTCThreads];
-  unsigned char cont[kFastVis];
-  unsigned char h5[kFastVis];
-  int vid[kFastVis];
-  float bx[kFastVis][8];
-  float4 ab[kFastVis];
-  double px[kTCThreads], py[kTCThreads];
-  float4 t4[kTCThreads];              // per active track: float position, pre-test margin, track index (bits; -1 = not live)
+  int imax[NT];
+  unsigned short cont[NT];             // (every active track sits in one thread: at most NT visible boxes)
+  unsigned char h5[NT];
+  int vid[NT];
+  float bx[NT][8];
+  float4 ab[NT];
+  double px[NT], py[NT];
+  float4 t4[NT];              // per active track: float position, pre-test margin, track index (bits; -1 = not live)
   unsigned cand[kCandCap];            // (visible slot << 16) | thread of the track
 };
 
 // a (visible box, track) pair passed the single-precision bounds pre-test: queue it for the exact test (one pair per thread
 // later), or -- queue full -- test it here.  Not inlined: the callers' loops stay small, this is the rare path.
-__device__ __noinline__ void tc_candidate(TCFastShared& S, int v, int jt) {
+template <int NT>
+__device__ __noinline__ void tc_candidate(TCFastShared<NT>& S, int v, int jt) {
   const int slot = atomicAdd(&S.ncand, 1);
   if (slot < kCandCap) S.cand[slot] = ((unsigned)v << 16) | (unsigned)jt;
   else if (overseg_cond(S.bx[v], reinterpret_cast<const float*>(&S.ab[v]), S.px[jt], S.py[jt])) atomicMax(&S.imax[jt], S.vid[v]);
 }
 
-__device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict__ tracks, int* __restrict__ trk, int* __restrict__ det,
+template <int NT>
+__device__ __forceinline__ void tc_fast(TCFastShared<NT>& S, TrackState* __restrict__ tracks, int* __restrict__ trk, int* __restrict__ det,
                                         const float* __restrict__ boxes, const float* __restrict__ boxes_pub, int* __restrict__ first_setter, double ego_yaw, int max_tracks,
                                         const OutPtrs& o, const OutPtrs& prev, int* __restrict__ act_list, double4* __restrict__ pos,
                                         const ActSummary* __restrict__ summary, int T0, int n_act0, int M, unsigned long long* __restrict__ trace,
@@ -1179,7 +1186,7 @@ __device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict_
   const int nbx = M * 6, ntg = cp ? (T0 * 12 + 15) / 16 : 0, ntm = cp ? (T0 * 4 + 15) / 16 : 0, nsv = cp ? (T0 + 15) / 16 : 0;
   uint4 vbx[UB], vtg[UT], vtm[UM], vst[1], vvi[1];
   double pz[UY], pv[UY];
-  cta_load(vbx, reinterpret_cast<const uint4*>(boxes_pub), nbx);     // (sensor-frame list; `boxes` is the tracker's input, in the global frame when lmot_params.global_frame is on)
+  cta_load<NT>(vbx, reinterpret_cast<const uint4*>(boxes_pub), nbx);     // (sensor-frame list; `boxes` is the tracker's input, in the global frame when lmot_params.global_frame is on)
   const int fs0 = (tid < M) ? first_setter[tid] : 0;            // first pass of the spawn loop below
   float bc[8] = {0, 0, 0, 0, 0, 0, 0, 0};                      // corners 0..3 (x, y) of this thread's box
   if (tid < M) {
@@ -1189,46 +1196,46 @@ __device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict_
   }
   int hdr_in[4] = {0, 0, 0, 0};
   if (tid == 0) { hdr_in[0] = det[CNT_N_ELEV]; hdr_in[1] = det[CNT_N_GROUND]; hdr_in[2] = det[CNT_NUM_CLUSTER]; hdr_in[3] = det[CNT_ERROR]; }
-  cta_load(vtg, reinterpret_cast<const uint4*>(prev.targets), ntg);
-  cta_load(vtm, reinterpret_cast<const uint4*>(prev.track_manage), ntm);
-  cta_load(vst, reinterpret_cast<const uint4*>(prev.is_static), nsv);
-  cta_load(vvi, reinterpret_cast<const uint4*>(prev.is_vis), nsv);
+  cta_load<NT>(vtg, reinterpret_cast<const uint4*>(prev.targets), ntg);
+  cta_load<NT>(vtm, reinterpret_cast<const uint4*>(prev.track_manage), ntm);
+  cta_load<NT>(vst, reinterpret_cast<const uint4*>(prev.is_static), nsv);
+  cta_load<NT>(vvi, reinterpret_cast<const uint4*>(prev.is_vis), nsv);
 #pragma unroll
   for (int u = 0; u < UY; ++u) {
-    const int e = u * kTCThreads + tid;
+    const int e = u * NT + tid;
     pz[u] = 0; pv[u] = 0;
     if (e < T0) { pz[u] = pos[e].z; if (cp) pv[u] = prev.vandyaw[2 * e]; }
   }
   // ---- stores (and the rare remainders beyond the first batch of each array)
-  cta_store(reinterpret_cast<uint4*>(o.boxes), vbx, nbx);
-  if (nbx > UB * kTCThreads) cta_copy<uint4, UB>(reinterpret_cast<uint4*>(o.boxes) + UB * kTCThreads, reinterpret_cast<const uint4*>(boxes_pub) + UB * kTCThreads, nbx - UB * kTCThreads);
-  cta_store(reinterpret_cast<uint4*>(o.targets), vtg, ntg);
-  if (ntg > UT * kTCThreads) cta_copy<uint4, UT>(reinterpret_cast<uint4*>(o.targets) + UT * kTCThreads, reinterpret_cast<const uint4*>(prev.targets) + UT * kTCThreads, ntg - UT * kTCThreads);
-  cta_store(reinterpret_cast<uint4*>(o.track_manage), vtm, ntm);
-  if (ntm > UM * kTCThreads) cta_copy<uint4, UM>(reinterpret_cast<uint4*>(o.track_manage) + UM * kTCThreads, reinterpret_cast<const uint4*>(prev.track_manage) + UM * kTCThreads, ntm - UM * kTCThreads);
-  cta_store(reinterpret_cast<uint4*>(o.is_static), vst, nsv);
-  cta_store(reinterpret_cast<uint4*>(o.is_vis), vvi, nsv);
-  if (nsv > kTCThreads) {
-    cta_copy<uint4, 1>(reinterpret_cast<uint4*>(o.is_static) + kTCThreads, reinterpret_cast<const uint4*>(prev.is_static) + kTCThreads, nsv - kTCThreads);
-    cta_copy<uint4, 1>(reinterpret_cast<uint4*>(o.is_vis) + kTCThreads, reinterpret_cast<const uint4*>(prev.is_vis) + kTCThreads, nsv - kTCThreads);
+  cta_store<NT>(reinterpret_cast<uint4*>(o.boxes), vbx, nbx);
+  if (nbx > UB * NT) cta_copy<NT, uint4, UB>(reinterpret_cast<uint4*>(o.boxes) + UB * NT, reinterpret_cast<const uint4*>(boxes_pub) + UB * NT, nbx - UB * NT);
+  cta_store<NT>(reinterpret_cast<uint4*>(o.targets), vtg, ntg);
+  if (ntg > UT * NT) cta_copy<NT, uint4, UT>(reinterpret_cast<uint4*>(o.targets) + UT * NT, reinterpret_cast<const uint4*>(prev.targets) + UT * NT, ntg - UT * NT);
+  cta_store<NT>(reinterpret_cast<uint4*>(o.track_manage), vtm, ntm);
+  if (ntm > UM * NT) cta_copy<NT, uint4, UM>(reinterpret_cast<uint4*>(o.track_manage) + UM * NT, reinterpret_cast<const uint4*>(prev.track_manage) + UM * NT, ntm - UM * NT);
+  cta_store<NT>(reinterpret_cast<uint4*>(o.is_static), vst, nsv);
+  cta_store<NT>(reinterpret_cast<uint4*>(o.is_vis), vvi, nsv);
+  if (nsv > NT) {
+    cta_copy<NT, uint4, 1>(reinterpret_cast<uint4*>(o.is_static) + NT, reinterpret_cast<const uint4*>(prev.is_static) + NT, nsv - NT);
+    cta_copy<NT, uint4, 1>(reinterpret_cast<uint4*>(o.is_vis) + NT, reinterpret_cast<const uint4*>(prev.is_vis) + NT, nsv - NT);
   }
   // dead tracks: v unchanged, yaw re-offset by THIS frame's ego yaw (:1004-1008); active ones are re-emitted below
 #pragma unroll
   for (int u = 0; u < UY; ++u) {
-    const int e = u * kTCThreads + tid;
+    const int e = u * NT + tid;
     if (e < T0) { if (cp) o.vandyaw[2 * e] = pv[u]; o.vandyaw[2 * e + 1] = wrap_pi(pz[u] + ego_yaw); }
   }
-  for (int base = UY * kTCThreads; base < T0; base += kTCThreads * UY) {
+  for (int base = UY * NT; base < T0; base += NT * UY) {
     double qz[UY], qv[UY];
 #pragma unroll
     for (int u = 0; u < UY; ++u) {
-      const int e = base + u * kTCThreads + tid;
+      const int e = base + u * NT + tid;
       qz[u] = 0; qv[u] = 0;
       if (e < T0) { qz[u] = pos[e].z; if (cp) qv[u] = prev.vandyaw[2 * e]; }
     }
 #pragma unroll
     for (int u = 0; u < UY; ++u) {
-      const int e = base + u * kTCThreads + tid;
+      const int e = base + u * NT + tid;
       if (e < T0) { if (cp) o.vandyaw[2 * e] = qv[u]; o.vandyaw[2 * e + 1] = wrap_pi(qz[u] + ego_yaw); }
     }
   }
@@ -1267,23 +1274,27 @@ __device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict_
   // compares (the previous form, one dependent load chain per pair, took 2.9 us for ~90 boxes x ~100 tracks)
   {
     const int warp = tid >> 5;
-    constexpr int kPerLane = kTCThreads / 32;
-    float4 tj[kPerLane];
+    constexpr int kPerLane = NT / 32;
+    constexpr int kGrp = 8;                                // tracks a lane holds at a time (the wide variant walks the boxes twice)
+#pragma unroll 1
+    for (int g = 0; g < kPerLane && g * 32 < n_act0; g += kGrp) {
+      float4 tj[kGrp];
 #pragma unroll
-    for (int u = 0; u < kPerLane; ++u) {
-      const int jt = lane + 32 * u;
-      tj[u] = (jt < n_act0) ? S.t4[jt] : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-    }
-    const int nu = (n_act0 + 31) >> 5;                   // lanes-worth of tracks actually present (uniform)
-    for (int v = warp; v < nv; v += kTCThreads / 32) {
-      const float4 ab = S.ab[v];
-      const int vid = S.vid[v];
+      for (int u = 0; u < kGrp; ++u) {
+        const int jt = lane + 32 * (g + u);
+        tj[u] = (jt < n_act0) ? S.t4[jt] : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+      }
+      const int nu = ((n_act0 + 31) >> 5) - g;             // lanes-worth of tracks actually present in this group (uniform)
+      for (int v = warp; v < nv; v += NT / 32) {
+        const float4 ab = S.ab[v];
+        const int vid = S.vid[v];
 #pragma unroll
-      for (int u = 0; u < kPerLane; ++u) {
-        if (u < nu) {
-          const int kj = __float_as_int(tj[u].w);
-          if (kj >= 0 && kj != vid && !(tj[u].x < ab.x - tj[u].z || tj[u].x > ab.y + tj[u].z || tj[u].y < ab.z - tj[u].z || tj[u].y > ab.w + tj[u].z))
-            tc_candidate(S, v, lane + 32 * u);
+        for (int u = 0; u < kGrp; ++u) {
+          if (u < nu) {
+            const int kj = __float_as_int(tj[u].w);
+            if (kj >= 0 && kj != vid && !(tj[u].x < ab.x - tj[u].z || tj[u].x > ab.y + tj[u].z || tj[u].y < ab.z - tj[u].z || tj[u].y > ab.w + tj[u].z))
+              tc_candidate<NT>(S, v, lane + 32 * (g + u));
+          }
         }
       }
     }
@@ -1293,7 +1304,7 @@ __device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict_
   mark(3);
   {
     const int ncand = min(S.ncand, kCandCap);
-    for (int e = tid; e < ncand; e += kTCThreads) {      // the exact fp64 tests, one pair per thread
+    for (int e = tid; e < ncand; e += NT) {      // the exact fp64 tests, one pair per thread
       const int v = (int)(S.cand[e] >> 16), jt = (int)(S.cand[e] & 0xFFFFu);
       if (overseg_cond(S.bx[v], reinterpret_cast<const float*>(&S.ab[v]), S.px[jt], S.py[jt])) atomicMax(&S.imax[jt], S.vid[v]);
     }
@@ -1302,14 +1313,14 @@ __device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict_
   mark(4);
   imax = max(imax, S.imax[tid]);
   // ---- pass B: has5 for the rare visible box that sits inside another one, against EVERY track (dead ones included)
-  if (vis && imax >= 0 && r.trackNum != 0) S.cont[atomicAdd(&S.ncont, 1)] = (unsigned char)vslot;
+  if (vis && imax >= 0 && r.trackNum != 0) S.cont[atomicAdd(&S.ncont, 1)] = (unsigned short)vslot;
   __syncthreads();
   {
     const int ncont = S.ncont;
     for (int cidx = 0; cidx < ncont; ++cidx) {
       const int v = S.cont[cidx], k = S.vid[v];
       const float4 ab = S.ab[v];
-      for (int j = tid; j < T0; j += kTCThreads) {
+      for (int j = tid; j < T0; j += NT) {
         const double4 pj = pos[j];
         const float px = (float)pj.x, py = (float)pj.y;
         const float mg = 0.011f + 2.0e-7f * (fabsf(px) + fabsf(py));
@@ -1350,7 +1361,7 @@ __device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict_
 
   mark(7);
   // ---- spawn one UKF per unmatched box, in box order (:972-989); the spawning thread also emits the new track
-  for (int b0 = 0; b0 < M; b0 += kTCThreads) {
+  for (int b0 = 0; b0 < M; b0 += NT) {
     const int b = b0 + tid;
     const int un = (b < M && (b0 == 0 ? fs0 : first_setter[b]) == INT_MAX) ? 1 : 0;
     int ex, tot;
@@ -1379,6 +1390,7 @@ __device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict_
     o.hdr[HDR_N_ELEV] = hdr_in[0]; o.hdr[HDR_N_GROUND] = hdr_in[1]; o.hdr[HDR_NUM_CLUSTER] = hdr_in[2];
     o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = nv; o.hdr[HDR_ERROR] = hdr_in[3];
     o.hdr[HDR_WARN] = (T0 + S.carry > max_tracks) ? (int)LMOT_WARN_TRACK_TABLE_FULL : 0;   // existing tracks' outputs stay valid: a warning, not an error
+    o.hdr[HDR_N_ACT] = n_keep + (T - T0);
     det[CNT_ERROR] = 0;
     trace_end(trace, 2);
     mark(9);
@@ -1394,7 +1406,8 @@ __device__ __forceinline__ void tc_fast(TCFastShared& S, TrackState* __restrict_
 //     of every track is its state's yaw plus THIS frame's ego yaw: `pos`, a packed (x, y, yaw) per track, refreshed for the
 //     active tracks only.
 // `full` (first step after the table was written from the host): everything is rebuilt from the records.
-__global__ void __launch_bounds__(kTCThreads, 2)
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == kTCThreads ? 2 : 1)
 spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int* __restrict__ det, const float* __restrict__ boxes,
                     const float* __restrict__ boxes_pub, int* __restrict__ first_setter, int* __restrict__ imax_arr, int* __restrict__ vis_list,
                     uint8_t* __restrict__ has5_arr, int first_frame, int compat_first, double ego_yaw, int max_tracks, OutPtrs o,
@@ -1408,10 +1421,11 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   struct Done { unsigned* p; __device__ ~Done() { __syncthreads(); if (threadIdx.x == 0) { __threadfence(); atomicAdd(p, 1u); } } } done_at_exit{tc_seq};
   trace_start(trace, 2);
   if (det_sem && threadIdx.x == 0) atomicSub(det_sem, 1);     // this frame's detection results are being consumed (posted by box_fit_kernel)
-  if (!full && !(first_frame && compat_first) && trk[CNT_N_ACT] <= kTCThreads) {
-    __shared__ TCFastShared s_fast;
+  if (!full && !(first_frame && compat_first) && trk[CNT_N_ACT] <= NT) {
+    extern __shared__ __align__(16) unsigned char tc_dyn[];          // sizeof(TCFastShared<NT>), tracker_launch
+    TCFastShared<NT>& s_fast = *reinterpret_cast<TCFastShared<NT>*>(tc_dyn);
     const int M = det[CNT_N_BOXES];
-    tc_fast(s_fast, tracks, trk, det, boxes, boxes_pub, first_setter, ego_yaw, max_tracks, o, prev, act_list, pos, summary, trk[CNT_N_TRACKS], trk[CNT_N_ACT], M, trace, phase);
+    tc_fast<NT>(s_fast, tracks, trk, det, boxes, boxes_pub, first_setter, ego_yaw, max_tracks, o, prev, act_list, pos, summary, trk[CNT_N_TRACKS], trk[CNT_N_ACT], M, trace, phase);
     return;
   }
   __shared__ int s_w[33];
@@ -1442,34 +1456,34 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
       }
       trk[CNT_N_TRACKS] = T; trk[CNT_N_VIS] = 0; trk[CNT_N_ACT] = T; act_list[0] = 0;
       o.hdr[HDR_N_ELEV] = det[CNT_N_ELEV]; o.hdr[HDR_N_GROUND] = det[CNT_N_GROUND]; o.hdr[HDR_NUM_CLUSTER] = det[CNT_NUM_CLUSTER];
-      o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = 0; o.hdr[HDR_ERROR] = det[CNT_ERROR]; o.hdr[HDR_WARN] = 0;
+      o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = 0; o.hdr[HDR_ERROR] = det[CNT_ERROR]; o.hdr[HDR_WARN] = 0; o.hdr[HDR_N_ACT] = T;
       det[CNT_ERROR] = 0;
     }
-    for (int b = tid; b < M; b += kTCThreads) first_setter[b] = INT_MAX;
-    for (int e = tid; e < M * 24; e += kTCThreads) o.boxes[e] = boxes_pub[e];
+    for (int b = tid; b < M; b += NT) first_setter[b] = INT_MAX;
+    for (int e = tid; e < M * 24; e += NT) o.boxes[e] = boxes_pub[e];
     return;
   }
-  for (int e = tid; e < M * 24; e += kTCThreads) o.boxes[e] = boxes_pub[e];     // the frame's box list travels with its results
+  for (int e = tid; e < M * 24; e += NT) o.boxes[e] = boxes_pub[e];     // the frame's box list travels with its results
 
   // ---- start the frame's result block from the previous one (dead tracks: unchanged), refresh the positions of the
   // active tracks, collect the visible ones (a subset of the active list, which is sorted by track index)
   if (!full) {
     const bool cp = prev.targets != o.targets;   // same block (result_ring == 1, or the synchronous entry points): patch in place
     if (cp) {
-      for (int e = tid; e < (T0 * 12 + 15) / 16; e += kTCThreads) reinterpret_cast<uint4*>(o.targets)[e] = reinterpret_cast<const uint4*>(prev.targets)[e];
-      for (int e = tid; e < (T0 * 4 + 15) / 16; e += kTCThreads) reinterpret_cast<uint4*>(o.track_manage)[e] = reinterpret_cast<const uint4*>(prev.track_manage)[e];
-      for (int e = tid; e < (T0 + 15) / 16; e += kTCThreads) {
+      for (int e = tid; e < (T0 * 12 + 15) / 16; e += NT) reinterpret_cast<uint4*>(o.targets)[e] = reinterpret_cast<const uint4*>(prev.targets)[e];
+      for (int e = tid; e < (T0 * 4 + 15) / 16; e += NT) reinterpret_cast<uint4*>(o.track_manage)[e] = reinterpret_cast<const uint4*>(prev.track_manage)[e];
+      for (int e = tid; e < (T0 + 15) / 16; e += NT) {
         reinterpret_cast<uint4*>(o.is_static)[e] = reinterpret_cast<const uint4*>(prev.is_static)[e];
         reinterpret_cast<uint4*>(o.is_vis)[e] = reinterpret_cast<const uint4*>(prev.is_vis)[e];
       }
     }
-    for (int e = tid; e < T0; e += kTCThreads) {      // v is the state's; the yaw is re-offset by THIS frame's ego yaw for every track (:1004-1008)
+    for (int e = tid; e < T0; e += NT) {      // v is the state's; the yaw is re-offset by THIS frame's ego yaw for every track (:1004-1008)
       if (cp) o.vandyaw[2 * e] = prev.vandyaw[2 * e];
       o.vandyaw[2 * e + 1] = wrap_pi(pos[e].z + ego_yaw);
     }
   }
   const int n_scan = full ? T0 : n_act0;       // entries to visit: the whole table, or the active list
-  for (int q0 = 0; q0 < n_scan; q0 += kTCThreads) {
+  for (int q0 = 0; q0 < n_scan; q0 += NT) {
     const int q = q0 + tid;
     int vis = 0, k = 0;
     if (q < n_scan) {
@@ -1499,10 +1513,10 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   // Visible boxes + bounds are staged in shared memory; a single-precision bounds pre-test (the margin covers the rounding
   // of the position to float) selects the few pairs that get the exact fp64 test, queued so that they run one per THREAD.
   auto stage_boxes = [&](int v0, int nc) {
-    for (int e = tid; e < nc * 8; e += kTCThreads) { const int v = e >> 3, q = e & 7; s_bx[v][q] = tracks[vis_list[v0 + v]].BBox[q >> 1][q & 1]; }
+    for (int e = tid; e < nc * 8; e += NT) { const int v = e >> 3, q = e & 7; s_bx[v][q] = tracks[vis_list[v0 + v]].BBox[q >> 1][q & 1]; }
     if (tid == 0) { s_ncand = 0; s_ncont = 0; }
     __syncthreads();
-    for (int v = tid; v < nc; v += kTCThreads) {
+    for (int v = tid; v < nc; v += NT) {
       const float* c = s_bx[v];
       s_ab[v] = make_float4(fminf(fminf(c[0], c[2]), fminf(c[4], c[6])), fmaxf(fmaxf(c[0], c[2]), fmaxf(c[4], c[6])),
                             fminf(fminf(c[1], c[3]), fminf(c[5], c[7])), fmaxf(fmaxf(c[1], c[3]), fmaxf(c[5], c[7])));
@@ -1511,12 +1525,12 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
     __syncthreads();
   };
   if (nv > 0)
-    for (int q = tid; q < n_scan; q += kTCThreads) imax_arr[full ? q : act_list[q]] = -1;
+    for (int q = tid; q < n_scan; q += NT) imax_arr[full ? q : act_list[q]] = -1;
   __syncthreads();
   for (int v0 = 0; v0 < nv; v0 += kVisChunk) {                 // pass A
     const int nc = min(kVisChunk, nv - v0);
     stage_boxes(v0, nc);
-    for (int q = tid; q < n_scan; q += kTCThreads) {
+    for (int q = tid; q < n_scan; q += NT) {
       const int j = full ? q : act_list[q];
       if (tracks[j].trackNum == 0) continue;                    // dead (stale-visible entry of the list): cannot change
       const double4 pj = pos[j];
@@ -1533,7 +1547,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
     }
     __syncthreads();
     const int ncand = min(s_ncand, kCandCap);
-    for (int e = tid; e < ncand; e += kTCThreads) {
+    for (int e = tid; e < ncand; e += NT) {
       const int v = (int)(s_cand[e] >> 24), j = (int)(s_cand[e] & 0xFFFFFFu);
       const double4 pj = pos[j];
       if (overseg_cond(s_bx[v], reinterpret_cast<const float*>(&s_ab[v]), pj.x, pj.y)) atomicMax(&imax_arr[j], s_vid[v]);
@@ -1543,14 +1557,14 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   for (int v0 = 0; v0 < nv; v0 += kVisChunk) {                 // pass B
     const int nc = min(kVisChunk, nv - v0);
     if (nv > kVisChunk) stage_boxes(v0, nc);                    // otherwise the only chunk is still staged
-    for (int v = tid; v < nc; v += kTCThreads)
+    for (int v = tid; v < nc; v += NT)
       if (imax_arr[s_vid[v]] >= 0) s_cont[atomicAdd(&s_ncont, 1)] = (unsigned char)v;
     __syncthreads();
     const int ncont = s_ncont;
     for (int cidx = 0; cidx < ncont; ++cidx) {
       const int v = s_cont[cidx], k = s_vid[v];
       const float4 ab = s_ab[v];
-      for (int j = tid; j < T0; j += kTCThreads) {
+      for (int j = tid; j < T0; j += NT) {
         const double4 pj = pos[j];
         const float px = (float)pj.x, py = (float)pj.y;
         const float mg = 0.011f + 2.0e-7f * (fabsf(px) + fabsf(py));
@@ -1559,11 +1573,11 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
       }
     }
     __syncthreads();
-    for (int v = tid; v < nc; v += kTCThreads) has5_arr[s_vid[v]] = s_h5[v];
+    for (int v = tid; v < nc; v += NT) has5_arr[s_vid[v]] = s_h5[v];
     __syncthreads();
   }
   if (nv > 0) {       // only live tracks can change (0 -> 0 is a no-op, 5 needs a visible, hence live, track)
-    for (int q0 = 0; q0 < n_scan; q0 += kTCThreads) {
+    for (int q0 = 0; q0 < n_scan; q0 += NT) {
       const int q = q0 + tid;
       if (q < n_scan) {
         const int k = full ? q : act_list[q];
@@ -1579,7 +1593,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   __syncthreads();
 
   // ---- spawn one UKF per unmatched box, in box order (:972-989)
-  for (int b0 = 0; b0 < M; b0 += kTCThreads) {
+  for (int b0 = 0; b0 < M; b0 += NT) {
     const int b = b0 + tid;
     const int un = (b < M && first_setter[b] == INT_MAX) ? 1 : 0;
     int ex, tot;
@@ -1606,7 +1620,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
   // (stable in-place compaction: a tile is read completely before anything at or below its range is written)
   const int n_new = T - T0;
   const int n_emit = n_scan + n_new;
-  for (int q0 = 0; q0 < n_emit; q0 += kTCThreads) {
+  for (int q0 = 0; q0 < n_emit; q0 += NT) {
     const int q = q0 + tid;
     int vis = 0, act = 0, i = 0;
     if (q < n_emit) {
@@ -1634,6 +1648,7 @@ spawn_output_kernel(TrackState* __restrict__ tracks, int* __restrict__ trk, int*
     o.hdr[HDR_N_ELEV] = det[CNT_N_ELEV]; o.hdr[HDR_N_GROUND] = det[CNT_N_GROUND]; o.hdr[HDR_NUM_CLUSTER] = det[CNT_NUM_CLUSTER];
     o.hdr[HDR_N_BOXES] = M; o.hdr[HDR_N_TRACKS] = T; o.hdr[HDR_N_VIS] = s_carry; o.hdr[HDR_ERROR] = det[CNT_ERROR];
     o.hdr[HDR_WARN] = table_full ? (int)LMOT_WARN_TRACK_TABLE_FULL : 0;
+    o.hdr[HDR_N_ACT] = s_carry2;
     det[CNT_ERROR] = 0;
     trace_end(trace, 2);
   }
@@ -1750,6 +1765,9 @@ int tracker_alloc(Ctx* c) {
   LMOT_CUDA(c, cudaGetLastError());
   const size_t sh = (size_t)c->gate_words * 32 * sizeof(unsigned short);
   LMOT_CUDA(c, cudaFuncSetAttribute(imm_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+  LMOT_CUDA(c, cudaFuncSetAttribute(spawn_output_kernel<kTCThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TCFastShared<kTCThreads>)));
+  LMOT_CUDA(c, cudaFuncSetAttribute(spawn_output_kernel<kTCWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TCFastShared<kTCWide>)));
+  c->last_n_act = 0; c->tc_wide = false;
   return LMOT_OK;
 }
 
@@ -1897,10 +1915,17 @@ int tracker_launch(Ctx* c, Slot* sl, cudaStream_t st, const float* d_boxes, cons
     cudaLaunchAttribute pdl;
     pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     pdl.val.programmaticStreamSerializationAllowed = (c->timing || (first && compat)) ? 0 : 1;
+    // variant: one active track per thread on the fast path.  The host only knows the active count of the last result it has read
+    // (a few frames old inside the pipeline; the count moves by a handful per frame): switch early, with hysteresis.  A count above
+    // the variant's width runs the kernel's general path -- slower, same results.
+    if (c->last_n_act > 208) c->tc_wide = true;
+    else if (c->last_n_act < 144) c->tc_wide = false;
+    const bool wide = c->tc_force >= 0 ? c->tc_force != 0 : c->tc_wide;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(1); cfg.blockDim = dim3(kTCThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(wide ? kTCWide : kTCThreads); cfg.stream = st;
+    cfg.dynamicSmemBytes = wide ? sizeof(TCFastShared<kTCWide>) : sizeof(TCFastShared<kTCThreads>);
     cfg.attrs = &pdl; cfg.numAttrs = 1;
-    LMOT_CUDA(c, cudaLaunchKernelEx(&cfg, spawn_output_kernel, c->d_tracks, c->d_trk_counters, det, d_boxes, d_boxes_pub, c->d_first_setter, c->d_new_num,
+    LMOT_CUDA(c, cudaLaunchKernelEx(&cfg, wide ? spawn_output_kernel<kTCWide> : spawn_output_kernel<kTCThreads>, c->d_tracks, c->d_trk_counters, det, d_boxes, d_boxes_pub, c->d_first_setter, c->d_new_num,
                                     c->d_vis_list, c->d_skip, first, compat, h.egoPoint[2], c->prm.max_tracks, o, po, full, c->d_act_list,
                                     c->d_pos, reinterpret_cast<const ActSummary*>(c->d_summary), trace, phase, det_sem, c->d_tc_seq));
     ++c->tc_launched;

@@ -41,9 +41,14 @@ def _check_tick(r, per, allb, a, f):
         assert np.array_equal(r[k], a[k]), (f, k)
 
 
-@pytest.mark.parametrize("n_streams", [8, 3])
-def test_batch_equals_reference_per_frame_plus_one_tracker_step(pkg, ref_intended, synth, n_streams):
+@pytest.mark.parametrize("n_streams,tc_wide", [(8, None), (3, None), (8, "0"), (3, "1")])
+def test_batch_equals_reference_per_frame_plus_one_tracker_step(pkg, ref_intended, synth, n_streams, tc_wide, monkeypatch):
+    """tc_wide: spawn_output_kernel's variant.  None = picked from the active-track count (8 streams x 40 objects: > 256 active tracks
+    from the second tick on -> the 512-thread variant's one-track-per-thread path); "0" pins the 256-thread variant (its general
+    path takes the > 256 active tracks), "1" pins the wide one on a scene that never needs it."""
     ref = ref_intended
+    if tc_wide is not None:
+        monkeypatch.setenv("LMOT_TC_WIDE", tc_wide)
     ctx = pkg.Lmot()
     try:
         ref.tracker_reset()
