@@ -112,19 +112,53 @@ __device__ __forceinline__ void seg_offsets_body(const FitFrame& F, int max_clus
   const int n_tiles = (n + kTile - 1) / kTile;
   const int stride = max_clusters + 1;
   __syncthreads();
-  for (int k0 = 1; k0 <= K; k0 += 1024) {
-    const int k = k0 + threadIdx.x;
-    int total = 0;
-    if (k <= K) {
-      for (int t0 = 0; t0 < n_tiles; t0 += 16) {       // 16 independent loads in flight, then the dependent prefix
-        int v[16];
+  // P lanes per cluster (a power of two, aligned inside a warp): each takes a contiguous range of tiles, so that a frame of ~60 tiles
+  // and ~100 clusters is ONE batch of independent loads per lane instead of four dependent batches on 100 of the 1,024 threads
+  const int P = K <= 128 ? 8 : (K <= 256 ? 4 : (K <= 512 ? 2 : 1));
+  const int per_round = 1024 / P;
+  const int per = (n_tiles + P - 1) / P;                // tiles per lane
+  for (int k0 = 1; k0 <= K; k0 += per_round) {
+    const int k = k0 + (int)threadIdx.x / P, j = (int)threadIdx.x % P;
+    const int t_beg = min(j * per, n_tiles), t_end = min(t_beg + per, n_tiles);
+    const bool mine = k <= K;
+    int v[16];
+    int sum = 0;
+    if (mine) {
+      if (per <= 16) {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = (t0 + u < n_tiles) ? table[(size_t)(t0 + u) * stride + k] : 0;
+        for (int u = 0; u < 16; ++u) { v[u] = (t_beg + u < t_end) ? table[(size_t)(t_beg + u) * stride + k] : 0; }
 #pragma unroll
-        for (int u = 0; u < 16; ++u)
-          if (t0 + u < n_tiles) { table[(size_t)(t0 + u) * stride + k] = total; total += v[u]; }
+        for (int u = 0; u < 16; ++u) sum += v[u];
+      } else {
+        for (int t0 = t_beg; t0 < t_end; t0 += 16) {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) v[u] = (t0 + u < t_end) ? table[(size_t)(t0 + u) * stride + k] : 0;
+#pragma unroll
+          for (int u = 0; u < 16; ++u) sum += v[u];
+        }
       }
     }
+    // exclusive prefix of the lanes' sums inside the cluster's group of P lanes; the group total ends up on every lane
+    int incl_l = sum;
+    for (int o = 1; o < P; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl_l, o, P); if (j >= o) incl_l += t; }
+    const int group_total = __shfl_sync(0xFFFFFFFFu, incl_l, P - 1, P);
+    if (mine) {
+      int run = incl_l - sum;
+      if (per <= 16) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          if (t_beg + u < t_end) { table[(size_t)(t_beg + u) * stride + k] = run; run += v[u]; }
+      } else {
+        for (int t0 = t_beg; t0 < t_end; t0 += 16) {       // 16 independent loads in flight, then the dependent prefix
+#pragma unroll
+          for (int u = 0; u < 16; ++u) v[u] = (t0 + u < t_end) ? table[(size_t)(t0 + u) * stride + k] : 0;
+#pragma unroll
+          for (int u = 0; u < 16; ++u)
+            if (t0 + u < t_end) { table[(size_t)(t0 + u) * stride + k] = run; run += v[u]; }
+        }
+      }
+    }
+    const int total = (mine && j == 0) ? group_total : 0;   // one lane per cluster carries its size into the scan over clusters
     // block exclusive scan of `total` (+ carry from previous chunks of 1024 clusters)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int incl = total;
@@ -141,7 +175,7 @@ __device__ __forceinline__ void seg_offsets_body(const FitFrame& F, int max_clus
     }
     __syncthreads();
     const int excl = s_carry + s_warp[warp] + incl - total;
-    if (k <= K) { seg_start[k] = excl; seg_size[k] = total; }
+    if (mine && j == 0) { seg_start[k] = excl; seg_size[k] = total; }
     __syncthreads();
     if (threadIdx.x == 1023) s_carry = excl + total;
     __syncthreads();
@@ -176,16 +210,33 @@ scatter_kernel(const __grid_constant__ FitBatch B, int max_clusters) {
   const unsigned grp = __match_any_sync(0xFFFFFFFFu, cid);
   const int leader = __ffs(grp) - 1;
   const int rank = __popc(grp & ((1u << lane) - 1u));
-  // warps take their turn in order so that ranks follow the cloud order
-  for (int w = 0; w < kTile / 32; ++w) {
-    if (warp == w) {
-      int base = 0;
-      if (cid != 0 && lane == leader) { base = s_cur[cid]; s_cur[cid] = base + __popc(grp); }
-      base = __shfl_sync(0xFFFFFFFFu, base, leader);
-      if (cid != 0) sorted_pts[base + rank] = q;
-    }
-    __syncthreads();
+  // Ranks follow the cloud order: the warps' groups must take their segment ranges in warp order.  Every warp lists its groups
+  // (cluster id, size); warp 0 then walks the 32 lists in order, one group per lane -- a warp's groups have distinct ids, so only
+  // consecutive lists depend on each other.  (The warps taking turns behind 32 CTA barriers was ~5 of this kernel's ~8 us.)
+  __shared__ unsigned short s_gcid[kTile / 32][32];
+  __shared__ unsigned char s_gcnt[kTile / 32][32], s_gn[kTile / 32];
+  __shared__ int s_gbase[kTile / 32][32];
+  const bool is_leader = cid != 0 && lane == leader;
+  const unsigned lmask = __ballot_sync(0xFFFFFFFFu, is_leader);
+  if (is_leader) {
+    const int slot = __popc(lmask & ((1u << lane) - 1u));
+    s_gcid[warp][slot] = (unsigned short)cid; s_gcnt[warp][slot] = (unsigned char)__popc(grp);
   }
+  if (lane == 0) s_gn[warp] = (unsigned char)__popc(lmask);
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 0; w < kTile / 32; ++w) {
+      if (lane < (int)s_gn[w]) {
+        const int c = s_gcid[w][lane];
+        const int base = s_cur[c];
+        s_cur[c] = base + (int)s_gcnt[w][lane];
+        s_gbase[w][lane] = base;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (cid != 0) sorted_pts[s_gbase[warp][__popc(lmask & ((1u << leader) - 1u))] + rank] = q;
 }
 
 // ---------------------------------------------------------------------------------------------- B4
