@@ -112,6 +112,29 @@ def test_repeatable_and_stateless(lm, synth):
     assert np.array_equal(a["labels"], b["labels"]) and np.array_equal(a["elevated"], b["elevated"])
 
 
+def test_chained_device_launches_leave_the_last_frames_grid(lm, ref_intended, synth):
+    """lmot_ground_remove_dev back to back on one stream (what bench.py times for roofline_dense_1m): consecutive launches are chained
+    as programmatic dependents, the next launch's CTAs are resident and set up while the previous one drains.  They share the slot's
+    two key grids (one re-armed by the launch before), barrier counters and count descriptors: after a chain over different clouds
+    the polar grid of the LAST cloud must be the reference's, bit for bit, and the next ordinary call must be exact too."""
+    import torch
+    clouds = [synth.uniform_cloud(200000 + 1000 * i, 50 + i) for i in range(6)]
+    dev = [torch.from_numpy(c).cuda() for c in clouds]
+    torch.cuda.synchronize()
+    for rep in range(4):
+        for d, c in zip(dev, clouds):
+            lm.ground_remove_dev(d.data_ptr(), len(c))
+    lm.sync()
+    g_gpu, g_r = lm.debug_polar_grid(), ref_intended.polar_grid(clouds[-1])
+    for k in ("minz", "height", "smoothed", "hdiff"):
+        assert np.array_equal(g_gpu[k].view(np.uint32), g_r[k].view(np.uint32)), k
+    assert np.array_equal(g_gpu["isground"], g_r["isground"])
+    out = lm.ground_remove(clouds[0])
+    e, g = ref_intended.ground_remove(clouds[0])
+    assert np.array_equal(out["elevated"][:, :3].view(np.uint32), e.view(np.uint32))
+    assert np.array_equal(out["ground"][:, :3].view(np.uint32), g.view(np.uint32))
+
+
 def test_channel_boundaries_fast_and_exact_paths_agree(lm, ref_intended):
     """polar_bin_kernel takes a guarded fast path for the channel index (ground.cu, kChanGuard) and the exact fdlibm
     restatement near channel boundaries: clouds that hug the 80 boundaries from both sides, from 1e-7 rad to 1e-3 rad,
