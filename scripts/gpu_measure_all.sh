@@ -15,5 +15,5 @@ SMALL="--steps 10 --warmup 3 --cpu-sample 0 --dense-frames 0 --tracker-stress 0 
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/${T}_launches.csv python bench.py $SMALL > /dev/null 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:ground_fused -s 8 -c 2 -f -o gpurun_out/${T}_ground_pipeline python bench.py $SMALL > /dev/null 2>&1
 LMOT_FUSE_CCL=1 timeout 400 ncu --set full --import-source on --clock-control none -k regex:"ground_fused|tile_hist|scatter|box_fit|concat" --launch-skip 3 -c 6 -f -o gpurun_out/${T}_detect_fused python scripts/prof_detect.py > gpurun_out/${T}_ncu.log 2>&1; grep Profiling gpurun_out/${T}_ncu.log | head
-timeout 500 ncu --set full --clock-control none -k regex:"imm_|spawn_output|tracker_gate|publish_kernel" -s 600 -c 10 -f -o gpurun_out/${T}_tracker python bench.py --steps 200 --warmup 20 --cpu-sample 0 --dense-frames 0 --tracker-stress 0 --batch-ticks 0 > /dev/null 2>&1
+timeout 500 ncu --set full --import-source on --warp-sampling-interval 0 --clock-control none -k regex:"imm_|spawn_output|tracker_gate|publish_kernel" -s 600 -c 10 -f -o gpurun_out/${T}_tracker python bench.py --steps 200 --warmup 20 --cpu-sample 0 --dense-frames 0 --tracker-stress 0 --batch-ticks 0 > /dev/null 2>&1
 ls -la gpurun_out/${T}*
