@@ -669,6 +669,7 @@ def main():
         db = 16 * nd + 16 * nf_d + 9600 * 24
         dense = {"workload": "ground_removal stage on dense 1M-point frames", "points_per_frame": nd, "frames_in_ring": len(dfr),
                  "ring_mib": float(d_dense.numel() * 4 / 2**20), "avg_stage_ms": ms, "algorithmic_bytes_per_launch": db,
+                 "how": "launches back to back on one stream (programmatic dependents, see roofline.how), every launch a different frame of the ring",
                  "achieved": db / (ms * 1e-3) / 1e9, "unit": "GB/s", "peak": peak, "frac": db / (ms * 1e-3) / 1e9 / peak}
         del d_dense
 
@@ -802,6 +803,7 @@ def main():
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "algorithmic_bytes_per_launch": ground_bytes, "avg_launch_ms": float(ground_launch_ms),
                          "launches_timed": K, "traffic": TRAFFIC_NCU, "traffic_source": TRAFFIC_SOURCE,
+                         "how": "K launches back to back on one stream, CUDA events around the K; consecutive launches are chained as programmatic dependents (no event between them: the next launch's CTAs set up while the previous grid drains and wait in griddepcontrol.wait)",
                          "note": "latency bound at 120 k points: 3.84 MB is 0.6 us of HBM time, the kernel needs two frame-wide barriers and one count exchange; see roofline_dense_1m and batched_8x120k.roofline"},
             "stage_ms": {n: float(v) for n, v in zip(stage_names, stage_ms)},
             "kernel_us_warm": ({n: float(1e3 * v / K) for n, v in zip(KERNEL_NAMES if len(kern_ms) == len(KERNEL_NAMES) else KERNEL_NAMES_UNFUSED, kern_ms)}
