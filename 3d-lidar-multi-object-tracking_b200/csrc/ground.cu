@@ -923,7 +923,12 @@ int ground_launch_batch(Ctx* c, Slot* const* slots, int F, const float4* const* 
     if (!g.done) LMOT_CUDA(c, cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
     const bool same_stream = g.have_last && g.last == st;
     if (!same_stream) {
-      if (g.record_pending) { LMOT_CUDA(c, cudaEventRecord(g.done, g.last)); g.record_pending = false; g.recorded = true; }
+      if (g.record_pending) {
+        // (a caller stream that was destroyed without lmot_set_stream: its work still runs to completion -- wait for the device instead)
+        if (cudaEventRecord(g.done, g.last) == cudaSuccess) g.recorded = true;
+        else { cudaGetLastError(); LMOT_CUDA(c, cudaDeviceSynchronize()); }
+        g.record_pending = false;
+      }
       if (g.recorded) LMOT_CUDA(c, cudaStreamWaitEvent(st, g.done, 0));
     }
     // chained behind a ground kernel on the same stream: programmatic dependent launch -- this grid's CTAs become resident and set
